@@ -1,0 +1,205 @@
+/*
+ * tess_clusters.h -- C ABI of the B200-native per-frame adaptive-tessellation path.
+ *
+ * The reference has no FFI; the path is the body of
+ *   RendererRayTraceClustersTess::init   (src/renderer_raytrace_clusters_tess.cpp:166-407)
+ *   RendererRayTraceClustersTess::render (src/renderer_raytrace_clusters_tess.cpp:410-692, minus the three
+ *                                         vkCmdBuildClusterAccelerationStructureIndirectNV driver calls)
+ *   RendererRayTraceClustersTess::deinit
+ * behind `class Renderer` (src/renderer.hpp:70-77).  Each entry point below names the piece it replaces.
+ * All outputs stay device-resident in the reference's shaderio layouts (tess_clusters_shaderio.h), so the
+ * CLAS/BLAS builds can consume them in place.
+ *
+ * Conventions: every function returns 0 on success, a negative tc_status otherwise; no exceptions cross the
+ * ABI; buffer overflow is NOT an error (work is dropped, counters keep counting, see tc_Readback), exactly as
+ * in the reference.  A context is bound to one CUDA device and is not thread-safe; use one context per GPU.
+ * There is no CPU fallback: without a CUDA device every call fails with TC_ERR_CUDA.
+ */
+#ifndef TESS_CLUSTERS_H
+#define TESS_CLUSTERS_H
+
+#include "tess_clusters_shaderio.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define TC_API __declspec(dllexport)
+#else
+#define TC_API __attribute__((visibility("default")))
+#endif
+
+typedef enum tc_status {
+  TC_OK               = 0,
+  TC_ERR_INVALID_ARG  = -1,
+  TC_ERR_CUDA         = -2, /* no device / CUDA runtime failure; tc_last_error() has the text */
+  TC_ERR_OUT_OF_MEMORY = -3,
+  TC_ERR_NOT_READY    = -4, /* table / scene not set yet */
+  TC_ERR_LIMIT        = -5  /* configuration beyond what the kernels support (e.g. cluster > 256 tris) */
+} tc_status;
+
+/* RendererConfig switches that the reference bakes into its shaders as #defines
+ * (src/renderer.hpp:35-68, src/renderer_raytrace_clusters_tess.cpp:117-138). */
+enum {
+  TC_FLAG_PN_DISPLACEMENT       = 1u << 0, /* TESS_USE_PN                  (default on)  */
+  TC_FLAG_TRANSIENT_1X          = 1u << 1, /* TESS_USE_1X_TRANSIENTBUILDS  (default on)  */
+  TC_FLAG_TRANSIENT_2X          = 1u << 2, /* TESS_USE_2X_TRANSIENTBUILDS  (default on)  */
+  TC_FLAG_CULLING               = 1u << 3, /* DO_CULLING                   (default off) */
+  TC_FLAG_ANIMATION             = 1u << 4, /* DO_ANIMATION                 (default off) */
+  TC_FLAG_DEFAULT = TC_FLAG_PN_DISPLACEMENT | TC_FLAG_TRANSIENT_1X | TC_FLAG_TRANSIENT_2X
+};
+
+typedef struct tc_config {
+  uint32_t structSize;               /* = sizeof(tc_config), for ABI evolution */
+  int32_t  device;                   /* CUDA device ordinal */
+  uint32_t flags;                    /* TC_FLAG_* */
+  uint32_t numVisibleClusterBits;    /* MAX_VISIBLE_CLUSTERS   = 1 << bits  (reference default 20) */
+  uint32_t numSplitTriangleBits;     /* MAX_SPLIT_TRIANGLES    = 1 << bits  (16) */
+  uint32_t numPartTriangleBits;      /* MAX_PART_TRIANGLES     = 1 << bits  (20) */
+  uint32_t numGeneratedVerticesBits; /* MAX_GENERATED_VERTICES = 1 << bits  (24) */
+  uint32_t numGeneratedClusterMegs;  /* MAX_GENERATED_CLUSTER_MEGS          (1024) */
+  uint32_t splitFactor;              /* TESS_MAX_SPLIT_FACTOR, clamped to [2, 11] (8) */
+  uint32_t positionTruncateBits;     /* copied into ClasBuildInfo.packed (0) */
+  uint32_t clusterVertices;          /* scene max vertices per cluster, <= 256 (64) */
+  uint32_t clusterTriangles;         /* scene max triangles per cluster, <= 256 (64) */
+  uint32_t numBlasReservedSizes;     /* SceneBuilding.numBlasReservedSizes (stat only) */
+  uint32_t allocClasData;            /* 1: really allocate numGeneratedClusterMegs MiB for genClusterData;
+                                        0: reserve an address range only (no driver CLAS build follows) */
+} tc_config;
+
+/* One geometry = Scene::Geometry after processGeometry (src/scene.cpp:365-552): per-cluster vertex arrays,
+ * u8 local triangle indices, cluster headers, cluster bboxes, plus the per-cluster template tables that
+ * RayTracingClusterData produces from the driver (src/raytracing_cluster_data.cpp:55-268).  Host pointers. */
+typedef struct tc_geometry {
+  uint32_t         numClusters;
+  uint32_t         numVertices;       /* sum of cluster vertex counts */
+  uint32_t         numTriangles;
+  uint32_t         numLocalTriangleBytes; /* = 3 * numTriangles */
+  const float*     positions;         /* float3[numVertices] */
+  const float*     normals;           /* float3[numVertices] */
+  const float*     texcoords;         /* float2[numVertices] */
+  const tc_Cluster* clusters;         /* [numClusters] */
+  const uint8_t*   localTriangles;    /* [numLocalTriangleBytes] */
+  const tc_BBox*   clusterBboxes;     /* [numClusters] */
+  const uint64_t*  clusterTemplateAddresses;         /* [numClusters] (driver output in the reference) */
+  const uint32_t*  clusterTemplateInstantiationSizes;/* [numClusters] */
+} tc_geometry;
+
+/* Displacement texture, single channel float32, `width*height` texels row-major.  Sampled as the GLSL
+ * `texture(sampler2D, uv).r` at LOD 0 with bilinear filtering and repeat wrap, evaluated in software with a
+ * fixed operation order so that the CPU oracle and the kernels agree (DESIGN.md "texture parity"). */
+typedef struct tc_texture {
+  uint32_t     width, height;
+  const float* texels;
+} tc_texture;
+
+typedef struct tc_context tc_context;
+
+/* ---- lifetime: Renderer::init / deinit --------------------------------------------------------------- */
+TC_API int         tc_create(const tc_config* config, tc_context** out);
+TC_API void        tc_destroy(tc_context* ctx);
+TC_API const char* tc_last_error(void);
+TC_API uint32_t    tc_abi_version(void);
+
+/* TessellationTable::init (src/tessellation_table.cpp:36-100): raw table in the reference packing
+ * (vertices u|v<<16, triangles 3x8 bit, configs = 4 x u16 per raw config in x>=y>=z order) is scattered into
+ * the 16^3 lookup; templAddr4096/templSize4096 are the per-lookup-entry CLAS template address and worst-case
+ * instantiation size that initTemplates gets from the driver (:102-404) -- inputs here. */
+TC_API int tc_set_tess_table(tc_context* ctx, const uint32_t* vertices, uint32_t numVertices,
+                             const uint32_t* triangles, uint32_t numTriangles, const uint16_t* configs,
+                             uint32_t numConfigs, const uint64_t* templAddr4096, const uint32_t* templSize4096);
+
+/* Scene upload + Renderer::initBasics (src/renderer.cpp:192-210): `instances` are 192-byte RenderInstance
+ * records whose eight address members are ignored on input and patched to the device copies of
+ * geoms[geometryID].  basicClusterSizes = RayTracingClusterData::m_maxClusterSizes (clusterTriangles+1). */
+TC_API int tc_set_scene(tc_context* ctx, const tc_geometry* geoms, uint32_t numGeoms,
+                        const tc_RenderInstance* instances, uint32_t numInstances, const tc_texture* textures,
+                        uint32_t numTextures, const uint32_t* basicClusterSizes, uint32_t numBasicClusterSizes);
+
+/* Last frame's far-HiZ pyramid (src/nvhiz_vk.cpp:278-309): square pow2 R32F texture, `mipLevels` levels packed
+ * one after another (level l is (size>>l)^2 texels).  Sampled with LINEAR + MAX reduction, nearest mip,
+ * clamp-to-edge (src/nvhiz_vk.cpp:83-115).  Only read when TC_FLAG_CULLING is set. */
+TC_API int tc_set_hiz(tc_context* ctx, const float* mips, uint32_t size, uint32_t mipLevels);
+
+/* Driver stand-in for parity/bench runs: the reference's tempClusterSizes / transClusterSizes / blasBuildSizes
+ * are written by the CLAS/BLAS builds.  mode 0: leave whatever the consumer wrote; mode 1 (default): the
+ * library fills tempClusterSizes/transClusterSizes with each CLAS' reserved size before the insert step. */
+TC_API int tc_set_driver_standin(tc_context* ctx, uint32_t mode);
+
+/* ---- Renderer::render ---------------------------------------------------------------------------------
+ * frameConstants points at two consecutive FrameConstants (current, last) `strideBytes` apart
+ * (sizeof(shaderio::FrameConstants) for a reference caller, sizeof(tc_FrameConstants) otherwise).
+ * viewPos overrides SceneBuilding.viewPos when non-NULL (freezeCulling, :412).
+ * Enqueues the whole chain on the context stream and returns without synchronising. */
+TC_API int tc_frame(tc_context* ctx, const void* frameConstants, size_t strideBytes, const float* viewPosOverride);
+
+/* The driver sits between instantiate and insert in the reference.  tc_frame runs both halves back to back;
+ * a consumer that performs real CLAS builds calls these two instead. */
+TC_API int tc_frame_build(tc_context* ctx, const void* frameConstants, size_t strideBytes,
+                          const float* viewPosOverride);   /* :412-582  reset .. BUILD_SETUP_BUILD_BLAS */
+TC_API int tc_frame_insert(tc_context* ctx);               /* :661-686  blas_setup_insertion + inserts */
+
+/* Same frame replayed from a captured CUDA graph (frame constants re-read from a pinned staging copy). */
+TC_API int tc_frame_graph(tc_context* ctx, const void* frameConstants, size_t strideBytes,
+                          const float* viewPosOverride);
+
+TC_API int tc_sync(tc_context* ctx);
+
+/* Readback ring equivalent (src/resources.cpp:497-501): synchronises, copies the stats and the final
+ * SceneBuilding (counters + device addresses).  Either pointer may be NULL. */
+TC_API int tc_readback(tc_context* ctx, tc_Readback* readback, tc_SceneBuilding* building);
+
+/* Device pointer to the live SceneBuilding block (what the reference binds as BINDINGS_SCENEBUILDING_*). */
+TC_API int tc_device_scene_building(tc_context* ctx, uint64_t* deviceAddress);
+TC_API int tc_device_render_instances(tc_context* ctx, uint64_t* deviceAddress);
+TC_API int tc_device_tess_table(tc_context* ctx, tc_TessellationTable* table);
+
+/* Copy `bytes` from device address `src` (any address handed out through tc_SceneBuilding) to host memory;
+ * synchronises the context stream first.  For parity tests and host consumers. */
+TC_API int tc_download(tc_context* ctx, uint64_t src, void* dst, size_t bytes);
+
+/* CUDA stream the context enqueues on (cudaStream_t as integer), for consumers that chain GPU work. */
+TC_API int tc_stream(tc_context* ctx, uint64_t* stream);
+
+/* ---- measurement helpers (bench.py) ------------------------------------------------------------------ */
+enum {
+  TC_STAGE_INSTANCES_CLASSIFY = 0, /* names follow the reference's profiler sections (rt.cpp:435-673) */
+  TC_STAGE_CULL               = 1,
+  TC_STAGE_CLUSTER_CLASSIFY   = 2,
+  TC_STAGE_SPLIT              = 3,
+  TC_STAGE_PREP_INSTANTIATE   = 4,
+  TC_STAGE_INSERT             = 5,
+  TC_STAGE_COUNT              = 6
+};
+/* When enabled, tc_frame brackets every stage with CUDA events on the context stream. */
+TC_API int tc_enable_stage_timers(tc_context* ctx, int enable);
+/* Milliseconds per stage of the most recent tc_frame (synchronises). */
+TC_API int tc_stage_times(tc_context* ctx, float msOut[TC_STAGE_COUNT]);
+/* Number of kernels the most recent tc_frame launched. */
+TC_API int tc_last_launch_count(tc_context* ctx, uint32_t* launches);
+/* Write > L2-size bytes to evict caches between timed iterations. */
+TC_API int tc_flush_l2(tc_context* ctx);
+
+/* ---- multi-GPU (instance-sharded) --------------------------------------------------
+ * Each rank owns a contiguous instance range and runs the whole chain locally.  After tc_frame_build the
+ * host allgathers tc_shard_counts (one small record per rank, NCCL over NVLink) and hands every rank the
+ * exclusive prefix so that cluster references index a global BLAS insertion list. */
+typedef struct tc_shard_counts {
+  uint32_t tempInstantiateCounter;
+  uint32_t transBuildCounter;
+  uint32_t genVertexCounter;
+  uint32_t blasClusterCounter; /* temp + trans after clamping */
+  uint64_t genClusterDataCounter;
+  uint32_t numTotalTriangles;
+  uint32_t numInstances;
+} tc_shard_counts;
+/* Device address of the rank's tc_shard_counts block, valid after tc_frame_build (no sync). */
+TC_API int tc_device_shard_counts(tc_context* ctx, uint64_t* deviceAddress);
+/* Device address of a 2 x u32 block {globalBlasClusterBase, globalInstanceBase} the insert step adds. */
+TC_API int tc_device_shard_base(tc_context* ctx, uint64_t* deviceAddress);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+#endif /* TESS_CLUSTERS_H */
