@@ -1,0 +1,132 @@
+"""Shared parity checker: CUDA path (through the C ABI) vs the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): every integer/byte/index output bit-exact -- tess factors (via configs), config
+indices, split decisions, records, counters, index bytes, BLAS lists -- and displaced vertex positions within 1e-5
+relative.  Because the kernels assign offsets with prefix sums in the oracle's canonical order, lists compare
+byte-for-byte WITHOUT order normalisation (strictly stronger than the multiset comparison the reference allows).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from vk_tessellated_clusters_b200 import api
+
+VERTEX_RTOL = 1e-5
+
+_COUNTER_FIELDS = [
+    "viewPos", "numRenderInstances", "visibleClusterCounter", "fullClusterCounter", "partTriangleCounter", "dualPartTriangleCounter",
+    "splitTriangleCounter", "splitReadCounter", "splitWriteCounter", "splitPass", "splitPassStart", "splitPassEnd", "genVertexCounter",
+    "genClusterCounter", "genClusterDataCounter", "dispatchClassify", "dispatchTriangleSplit", "drawFullClusters", "drawPartTriangles",
+    "dispatchClusterInstantiate", "dispatchTriangleInstantiate", "dispatchBlasTempInsert", "dispatchBlasTransInsert", "positionTruncateBitCount",
+    "blasClusterCounter", "tempInstantiateCounter", "transBuildCounter", "numBlasReservedSizes",
+]
+_READBACK_FIELDS = [
+    "numVisibleClusters", "numFullClusters", "numSplitTriangles", "numPartTriangles", "numTotalTriangles", "numTempInstantiations", "numGenVertices",
+    "numBlasClusters", "numTransBuilds", "numTransPartTriangles", "numActualTransBuilds", "numActualTempInstantiations", "numGenDatas",
+    "numGenActualDatas", "numBlasReservedSizes", "numBlasActualSizes",
+]
+
+
+class ParityError(AssertionError):
+    pass
+
+
+def _eq(name, a, b):
+    if a.shape != b.shape or a.dtype != b.dtype or a.tobytes() != b.tobytes():
+        if a.shape == b.shape:
+            av, bv = a.reshape(-1), b.reshape(-1)
+            bad = np.nonzero(av.view(np.uint8).reshape(av.shape[0], -1) != bv.view(np.uint8).reshape(bv.shape[0], -1))[0]
+            first = int(bad[0]) if bad.size else -1
+            raise ParityError(f"{name}: {np.unique(bad).size} of {av.shape[0]} elements differ, first at {first}: gpu={av[first]} oracle={bv[first]}")
+        raise ParityError(f"{name}: shape/dtype mismatch {a.shape}/{a.dtype} vs {b.shape}/{b.dtype}")
+
+
+def compare_frame(gpu: api.TessClusters, orc, scene_scale: float = 1.0, check_vertices: bool = True) -> dict:
+    """Both contexts must just have run the same frame. Returns summary stats; raises ParityError on mismatch."""
+    rb_g, sb_g = gpu.readback()
+    rb_o, sb_o = orc.readback()
+    for f in _COUNTER_FIELDS:
+        if np.asarray(sb_g[f]).tobytes() != np.asarray(sb_o[f]).tobytes():
+            raise ParityError(f"SceneBuilding.{f}: gpu={sb_g[f]} oracle={sb_o[f]}")
+    for f in _READBACK_FIELDS:
+        if rb_g[f] != rb_o[f]:
+            raise ParityError(f"Readback.{f}: gpu={rb_g[f]} oracle={rb_o[f]}")
+
+    cfg = gpu.config
+    N = gpu.num_instances
+    n_vis = int(sb_o["visibleClusterCounter"])
+    n_temp, n_trans = int(sb_o["tempInstantiateCounter"]), int(sb_o["transBuildCounter"])
+    n_blas = int(sb_o["blasClusterCounter"])
+    n_split = min(int(sb_o["splitWriteCounter"]), cfg.max_split_triangles)
+    lo, hi = int(sb_o["dualPartTriangleCounter"]) & 0xFFFFFFFF, int(sb_o["dualPartTriangleCounter"]) >> 32
+    transient = bool(cfg.flags & (api.FLAG_TRANSIENT_1X | api.FLAG_TRANSIENT_2X))
+
+    def both(name, count=None):
+        return gpu.buffer(name, count, sb_g), orc.buffer(name, count)
+
+    _eq("instanceStates", *both("instanceStates", N))
+    _eq("visibleClusters", *both("visibleClusters", n_vis))
+    _eq("splitTriangles", *both("splitTriangles"))  # whole buffer incl. the 0xFF fill
+    pg, po = both("partTriangles")  # whole buffer: front = parts, tail = transient meta
+    _eq("partTriangles", pg, po)
+    _eq("tempInstanceIDs", *both("tempInstanceIDs", n_temp))
+    _eq("tempInstantiations", *both("tempInstantiations", n_temp))
+    _eq("tempClusterAddresses", *both("tempClusterAddresses", n_temp))
+    _eq("tempClusterSizes", *both("tempClusterSizes", n_temp))
+    if transient:
+        _eq("transInstanceIDs", *both("transInstanceIDs", n_trans))
+        tg, to = both("transBuilds", n_trans)
+        _eq("transBuilds", tg, to)
+        _eq("transClusterAddresses", *both("transClusterAddresses", n_trans))
+        _eq("transClusterSizes", *both("transClusterSizes", n_trans))
+    else:
+        to = np.zeros(0, dtype=api.CLAS_BUILD_DTYPE)
+    _eq("blasBuildInfos", *both("blasBuildInfos", N))
+    _eq("blasClusterAddresses", *both("blasClusterAddresses", n_blas))
+
+    stats = {"max_rel_err": 0.0, "vertices": 0, "index_bytes": 0}
+    if check_vertices:
+        n_v = min(int(sb_o["genVertexCounter"]), cfg.max_generated_vertices)
+        vg, vo = both("genVertices", n_v * 3)
+        # index bytes of transient builds alias genVertices: those ranges are compared exactly
+        is_index = np.zeros(n_v * 3, dtype=bool)
+        base = int(sb_o["genVertices"])
+        for r in to:
+            tris = int(r["packed"]) & 0x1FF
+            start = int(r["indexBuffer"]) - base
+            first, last = start // 4, (start + tris * 3 + 3) // 4
+            is_index[first:last] = True
+        stats["index_bytes"] = int(is_index.sum()) * 4
+        if is_index.any():
+            _eq("transTriIndices", vg.view(np.uint32)[is_index], vo.view(np.uint32)[is_index])
+        fg, fo = vg[~is_index].astype(np.float64), vo[~is_index].astype(np.float64)
+        if not (np.isfinite(fg).all() and np.isfinite(fo).all()):
+            raise ParityError("genVertices: non-finite values")
+        err = np.abs(fg - fo) / np.maximum(np.abs(fo), scene_scale)
+        stats["max_rel_err"] = float(err.max()) if err.size else 0.0
+        stats["vertices"] = int(fo.size // 3)
+        if stats["max_rel_err"] > VERTEX_RTOL:
+            k = int(err.argmax())
+            raise ParityError(f"genVertices: max relative error {stats['max_rel_err']:.3e} > {VERTEX_RTOL} at float {k}: gpu={fg[k]} oracle={fo[k]}")
+    stats.update({"parts": int(sb_o["partTriangleCounter"]), "splits": n_split, "temp": n_temp, "trans": n_trans, "lo": lo, "hi": hi,
+                  "triangles": int(rb_o["numTotalTriangles"]), "gen_vertices": int(sb_o["genVertexCounter"])})
+    return stats
+
+
+def make_pair(scene, table, config=None, hiz=None):
+    """Create (gpu, oracle) contexts on the same inputs; the oracle embeds the GPU context's device addresses."""
+    from oracle.oracle_binding import Oracle
+
+    config = config or api.Config()
+    gpu = api.TessClusters(config)
+    gpu.set_tess_table(table)
+    gpu.set_scene(scene)
+    orc = Oracle(config)
+    orc.set_tess_table(table)
+    orc.set_scene(scene)
+    if hiz is not None:
+        gpu.set_hiz(*hiz)
+        orc.set_hiz(*hiz)
+    _, sb = gpu.readback()
+    orc.set_addresses(sb)
+    return gpu, orc

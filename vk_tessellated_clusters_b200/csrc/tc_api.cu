@@ -1,0 +1,840 @@
+// tc_api.cu -- C ABI (include/tess_clusters.h) and host runtime of the tessellation path.
+//
+// Host-side mirror of RendererRayTraceClustersTess (src/renderer_raytrace_clusters_tess.cpp): tc_create = init()
+// buffer carving (:200-310), tc_frame = render() :412-692 without the driver's CLAS/BLAS builds, tc_destroy = deinit.
+// One context = one CUDA device + one stream; the per-frame chain is enqueued without any host synchronisation
+// and can be replayed from a CUDA graph.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tc_device.cuh"
+#include "tc_kernels.h"
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const std::string& msg)
+{
+  g_lastError = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                                 \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t _e = (expr);                                                                                           \
+    if(_e != cudaSuccess)                                                                                              \
+      return fail(_e == cudaErrorMemoryAllocation ? TC_ERR_OUT_OF_MEMORY : TC_ERR_CUDA,                                \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));                                                 \
+  } while(0)
+
+struct DeviceGeometry
+{
+  void *positions = nullptr, *normals = nullptr, *texcoords = nullptr, *clusters = nullptr, *localTriangles = nullptr, *bboxes = nullptr,
+       *templAddr = nullptr, *templSize = nullptr;
+  uint32_t numClusters = 0;
+};
+
+struct FrameStaging  // pinned host block copied to the device once per frame
+{
+  tc_FrameConstants view[2];
+  float             viewPos[4];
+};
+
+}  // namespace
+
+struct tc_context
+{
+  tc_config    cfg{};
+  int          device = 0;
+  int          numSMs = 148;
+  cudaStream_t stream = nullptr;
+  tc::KernelOccupancy occ;
+
+  uint32_t maxVisible = 0, maxPart = 0, maxSplit = 0, maxVerts = 0, maxGenClusters = 0;
+
+  // device blocks
+  tc_SceneBuilding* dBuild     = nullptr;
+  tc_SceneBuilding* dBuildTmpl = nullptr;
+  tc_Readback*      dReadback  = nullptr;
+  tc::FrameState*   dState     = nullptr;
+  uint32_t*         dEpoch     = nullptr;
+  void*             dLookback  = nullptr;
+  FrameStaging*     dFrame     = nullptr;
+  FrameStaging*     hFrame     = nullptr;  // pinned
+  tc_shard_counts*  dShardCounts = nullptr;
+  uint32_t*         dShardBase   = nullptr;
+
+  // path buffers
+  void *visibleClusters = nullptr, *splitTriangles = nullptr, *partTriangles = nullptr, *genVertices = nullptr;
+  void *tempInstanceIDs = nullptr, *tempInstantiations = nullptr, *tempClusterAddresses = nullptr, *tempClusterSizes = nullptr;
+  void *transInstanceIDs = nullptr, *transBuilds = nullptr, *transClusterAddresses = nullptr, *transClusterSizes = nullptr;
+  void *blasClusterAddresses = nullptr, *genClusterData = nullptr;
+  // per scene
+  void *instanceStates = nullptr, *blasBuildInfos = nullptr, *blasBuildSizes = nullptr, *basicClusterSizes = nullptr;
+  tc_RenderInstance* dInstances = nullptr;
+  uint32_t*          dClusterPrefix = nullptr;
+  uint32_t *         segLo = nullptr, *rankBase = nullptr;
+  std::vector<DeviceGeometry> geoms;
+  std::vector<void*>          textures;
+  uint32_t numInstances = 0, totalClusters = 0;
+
+  // table
+  void *tblVertices = nullptr, *tblTriangles = nullptr, *tblEntries = nullptr, *tblTemplAddr = nullptr, *tblTemplSize = nullptr;
+  // hiz
+  float* hiz = nullptr;
+
+  void*  flushBuf   = nullptr;
+  size_t flushBytes = 0;
+
+  tc_SceneBuilding hBuildTmpl{};
+  tc::Params       params{};
+  bool             tableSet = false, sceneSet = false;
+  uint32_t         driverStandin = 1;
+
+  // timers
+  bool        timers = false;
+  cudaEvent_t ev[TC_STAGE_COUNT + 1]{};
+  bool        evValid = false;
+  uint32_t    lastLaunches = 0;
+
+  // graph
+  cudaGraphExec_t graphExec = nullptr;
+};
+
+namespace {
+
+template <typename T>
+int dalloc(T*& ptr, size_t bytes)
+{
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+  ptr = reinterpret_cast<T*>(p);
+  return TC_OK;
+}
+
+void dfree(void* p)
+{
+  if(p)
+    cudaFree(p);
+}
+
+uint32_t split_pass_count(uint32_t hostSplitFactor)
+{  // rt.cpp:516-544
+  uint32_t coord = TC_TESSTABLE_COORD_MAX, n = 0;
+  while(coord > hostSplitFactor)
+  {
+    coord /= hostSplitFactor;
+    n++;
+  }
+  return n;
+}
+
+void free_scene(tc_context* c)
+{
+  for(auto& g : c->geoms)
+  {
+    dfree(g.positions); dfree(g.normals); dfree(g.texcoords); dfree(g.clusters); dfree(g.localTriangles); dfree(g.bboxes);
+    dfree(g.templAddr); dfree(g.templSize);
+  }
+  c->geoms.clear();
+  for(void* t : c->textures)
+    dfree(t);
+  c->textures.clear();
+  dfree(c->instanceStates); dfree(c->blasBuildInfos); dfree(c->blasBuildSizes); dfree(c->basicClusterSizes);
+  dfree(c->dInstances); dfree(c->dClusterPrefix); dfree(c->segLo); dfree(c->rankBase);
+  c->instanceStates = c->blasBuildInfos = c->blasBuildSizes = c->basicClusterSizes = nullptr;
+  c->dInstances = nullptr;
+  c->dClusterPrefix = nullptr;
+  c->segLo = c->rankBase = nullptr;
+  c->sceneSet = false;
+}
+
+void drop_graph(tc_context* c)
+{
+  if(c->graphExec)
+  {
+    cudaGraphExecDestroy(c->graphExec);
+    c->graphExec = nullptr;
+  }
+}
+
+int upload_template(tc_context* c)
+{
+  tc_SceneBuilding& b = c->hBuildTmpl;
+  memset(&b, 0, sizeof(b));
+  b.numRenderInstances       = c->numInstances;
+  b.positionTruncateBitCount = c->cfg.positionTruncateBits;
+  b.numBlasReservedSizes     = c->cfg.numBlasReservedSizes;
+  b.instanceStates        = uint64_t(c->instanceStates);
+  b.visibleClusters       = uint64_t(c->visibleClusters);
+  b.fullClusters          = 0;
+  b.splitTriangles        = uint64_t(c->splitTriangles);
+  b.partTriangles         = uint64_t(c->partTriangles);
+  b.basicClusterSizes     = uint64_t(c->basicClusterSizes);
+  b.genClusterData        = uint64_t(c->genClusterData);
+  b.genVertices           = uint64_t(c->genVertices);
+  b.tempInstanceIDs       = uint64_t(c->tempInstanceIDs);
+  b.tempInstantiations    = uint64_t(c->tempInstantiations);
+  b.tempClusterAddresses  = uint64_t(c->tempClusterAddresses);
+  b.tempClusterSizes      = uint64_t(c->tempClusterSizes);
+  b.transInstanceIDs      = uint64_t(c->transInstanceIDs);
+  b.transBuilds           = uint64_t(c->transBuilds);
+  b.transClusterAddresses = uint64_t(c->transClusterAddresses);
+  b.transClusterSizes     = uint64_t(c->transClusterSizes);
+  const bool transient    = (c->cfg.flags & (TC_FLAG_TRANSIENT_1X | TC_FLAG_TRANSIENT_2X)) != 0;
+  b.transTriMappings      = transient ? uint64_t(c->partTriangles) : 0;  // rt.cpp:293
+  b.transTriIndices       = transient ? uint64_t(c->genVertices) : 0;    // rt.cpp:251
+  b.blasBuildInfos        = uint64_t(c->blasBuildInfos);
+  b.blasBuildSizes        = uint64_t(c->blasBuildSizes);
+  b.blasClusterAddresses  = uint64_t(c->blasClusterAddresses);
+  b.blasBuildData         = 0;
+  CUDA_TRY(cudaMemcpyAsync(c->dBuildTmpl, &b, sizeof(b), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->dBuild, &b, sizeof(b), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return TC_OK;
+}
+
+void fill_params(tc_context* c)
+{
+  tc::Params& p = c->params;
+  p.build       = c->dBuild;
+  p.readback    = c->dReadback;
+  p.view        = c->dFrame->view;
+  p.instances   = c->dInstances;
+  p.instanceClusterPrefix = c->dClusterPrefix;
+  p.state       = c->dState;
+  p.tblVertices  = reinterpret_cast<const uint32_t*>(c->tblVertices);
+  p.tblTriangles = reinterpret_cast<const uint32_t*>(c->tblTriangles);
+  p.tblEntries   = reinterpret_cast<const tc_TessTableEntry*>(c->tblEntries);
+  p.tblTemplAddr = reinterpret_cast<const uint64_t*>(c->tblTemplAddr);
+  p.tblTemplSize = reinterpret_cast<const uint32_t*>(c->tblTemplSize);
+  p.basicClusterSizes = reinterpret_cast<const uint32_t*>(c->basicClusterSizes);
+  p.hiz = c->hiz;
+  p.maxVisibleClusters = c->maxVisible;
+  p.maxPartTriangles   = c->maxPart;
+  p.maxSplitTriangles  = c->maxSplit;
+  p.maxGenVertices     = c->maxVerts;
+  p.maxGenClusters     = c->maxGenClusters;
+  p.maxGenDataBytes    = (unsigned long long)c->cfg.numGeneratedClusterMegs * 1024ull * 1024ull;
+  p.splitFactor        = std::max(2u, std::min(c->cfg.splitFactor, TC_TESSTABLE_SIZE));
+  p.clusterVertices    = c->cfg.clusterVertices;
+  p.clusterTriangles   = c->cfg.clusterTriangles;
+  p.flags              = c->cfg.flags;
+  p.numInstances       = c->numInstances;
+  p.totalClusters      = c->totalClusters;
+  p.driverStandin      = c->driverStandin;
+  p.lookback           = c->dLookback;
+  p.segLo              = c->segLo;
+  p.rankBase           = c->rankBase;
+  p.shardBase          = c->dShardBase;
+}
+
+struct StageScope
+{
+  tc_context* c;
+  int         stage;
+  StageScope(tc_context* ctx, int s) : c(ctx), stage(s)
+  {
+    if(c->timers && s == 0)
+      cudaEventRecord(c->ev[0], c->stream);
+  }
+  ~StageScope()
+  {
+    if(c->timers)
+      cudaEventRecord(c->ev[stage + 1], c->stream);
+  }
+};
+
+int stage_frame_inputs(tc_context* c, const void* frameConstants, size_t strideBytes, const float* viewPosOverride)
+{
+  if(!frameConstants || strideBytes < sizeof(tc_FrameConstants))
+    return fail(TC_ERR_INVALID_ARG, "frameConstants/stride invalid");
+  memcpy(&c->hFrame->view[0], frameConstants, sizeof(tc_FrameConstants));
+  memcpy(&c->hFrame->view[1], static_cast<const uint8_t*>(frameConstants) + strideBytes, sizeof(tc_FrameConstants));
+  const float* vp = viewPosOverride ? viewPosOverride : c->hFrame->view[0].viewPos;  // freezeCulling, rt.cpp:412
+  c->hFrame->viewPos[0] = vp[0]; c->hFrame->viewPos[1] = vp[1]; c->hFrame->viewPos[2] = vp[2]; c->hFrame->viewPos[3] = 0.f;
+  return TC_OK;
+}
+
+// rt.cpp:412-582 : resets .. BUILD_SETUP_BUILD_BLAS
+int enqueue_build(tc_context* c)
+{
+  cudaStream_t s = c->stream;
+  tc::Params&  p = c->params;
+  uint32_t     launches = 0;
+  CUDA_TRY(cudaMemcpyAsync(c->dFrame, c->hFrame, sizeof(FrameStaging), cudaMemcpyHostToDevice, s));
+  {
+    StageScope sc(c, TC_STAGE_INSTANCES_CLASSIFY);
+    // vkCmdFillBuffer(splitTriangles, ~0) (:419)
+    CUDA_TRY(cudaMemsetAsync(c->splitTriangles, 0xFF, size_t(c->maxSplit) * sizeof(tc_TessTriangleInfo), s));
+    tc::launch_frame_setup(p, c->dBuildTmpl, c->dFrame->viewPos, c->dEpoch, s);
+    tc::launch_instances_classify(p, s);
+    launches += 2;
+  }
+  {
+    StageScope sc(c, TC_STAGE_CULL);
+    tc::launch_clusters_cull(p, s);
+    launches += 1;
+  }
+  {
+    StageScope sc(c, TC_STAGE_CLUSTER_CLASSIFY);
+    uint32_t tiles = (std::min(c->totalClusters, c->maxVisible) + 7) / 8;
+    uint32_t grid  = std::max(1u, std::min(tiles, uint32_t(c->numSMs * c->occ.classify)));
+    tc::launch_cluster_classify(p, c->dEpoch, grid, s);
+    launches += 1;
+  }
+  {
+    StageScope sc(c, TC_STAGE_SPLIT);
+    uint32_t passes = split_pass_count(std::max(2u, c->cfg.splitFactor));
+    uint32_t grid   = std::max(1u, uint32_t(c->numSMs * c->occ.split));
+    for(uint32_t k = 0; k < passes; k++)
+      tc::launch_triangle_split(p, c->dEpoch, k, k + 1 == passes, grid, s);
+    launches += passes;
+  }
+  {
+    StageScope sc(c, TC_STAGE_PREP_INSTANTIATE);
+    uint32_t grid = std::max(1u, uint32_t(c->numSMs * c->occ.instantiate));
+    tc::launch_instantiate(p, c->dEpoch, grid, s);
+    tc::launch_shard_counts(p, c->dShardCounts, s);
+    launches += 2;
+  }
+  c->lastLaunches = launches;
+  CUDA_TRY(cudaGetLastError());
+  return TC_OK;
+}
+
+// rt.cpp:661-686 : blas_setup_insertion + blas_clusters_insert x2
+int enqueue_insert(tc_context* c)
+{
+  StageScope sc(c, TC_STAGE_INSERT);
+  uint32_t passes = split_pass_count(std::max(2u, c->cfg.splitFactor));
+  tc::launch_blas(c->params, passes + 3, uint32_t(c->numSMs * 4), c->stream);
+  c->lastLaunches += 3;
+  CUDA_TRY(cudaGetLastError());
+  return TC_OK;
+}
+
+int check_ready(tc_context* c)
+{
+  if(!c)
+    return fail(TC_ERR_INVALID_ARG, "null context");
+  if(!c->tableSet || !c->sceneSet)
+    return fail(TC_ERR_NOT_READY, "tc_set_tess_table and tc_set_scene must be called first");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return TC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+TC_API uint32_t tc_abi_version(void) { return 1; }
+TC_API const char* tc_last_error(void) { return g_lastError.c_str(); }
+
+TC_API int tc_create(const tc_config* config, tc_context** out)
+{
+  if(!config || !out || config->structSize != sizeof(tc_config))
+    return fail(TC_ERR_INVALID_ARG, "config missing or structSize mismatch");
+  if(config->clusterVertices == 0 || config->clusterVertices > 256 || config->clusterTriangles == 0 || config->clusterTriangles > 256)
+    return fail(TC_ERR_LIMIT, "clusterVertices/clusterTriangles must be in [1, 256] (u8 local indices)");
+  if(config->numVisibleClusterBits > 26 || config->numPartTriangleBits > 28 || config->numSplitTriangleBits > 26 || config->numGeneratedVerticesBits > 31)
+    return fail(TC_ERR_LIMIT, "limit bits too large");
+  int count = 0;
+  if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(TC_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  if(config->device < 0 || config->device >= count)
+    return fail(TC_ERR_INVALID_ARG, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(config->device));
+
+  tc_context* c = new tc_context();
+  c->cfg        = *config;
+  c->device     = config->device;
+  cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, c->device);
+  c->maxVisible     = 1u << config->numVisibleClusterBits;
+  c->maxPart        = 1u << config->numPartTriangleBits;
+  c->maxSplit       = 1u << config->numSplitTriangleBits;
+  c->maxVerts       = 1u << config->numGeneratedVerticesBits;
+  c->maxGenClusters = c->maxVisible + c->maxPart;  // rt.cpp:170
+
+  auto bail = [&](int rc) {
+    tc_destroy(c);
+    return rc;
+  };
+#define TRY_RC(expr)                                                                                                   \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    int _rc = (expr);                                                                                                  \
+    if(_rc != TC_OK)                                                                                                   \
+      return bail(_rc);                                                                                                \
+  } while(0)
+#define TRY_CUDA(expr)                                                                                                 \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t _e = (expr);                                                                                           \
+    if(_e != cudaSuccess)                                                                                              \
+      return bail(fail(TC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)));                              \
+  } while(0)
+
+  TRY_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  if(tc::configure_kernels(config->clusterVertices, config->clusterTriangles, &c->occ) != 0)
+    return bail(fail(TC_ERR_CUDA, std::string("kernel configuration failed: ") + cudaGetErrorString(cudaGetLastError())));
+
+  TRY_RC(dalloc(c->dBuild, sizeof(tc_SceneBuilding)));
+  TRY_RC(dalloc(c->dBuildTmpl, sizeof(tc_SceneBuilding)));
+  TRY_RC(dalloc(c->dReadback, sizeof(tc_Readback)));
+  TRY_RC(dalloc(c->dState, tc::frame_state_bytes()));
+  TRY_RC(dalloc(c->dEpoch, 16));
+  TRY_RC(dalloc(c->dFrame, sizeof(FrameStaging)));
+  TRY_RC(dalloc(c->dShardCounts, sizeof(tc_shard_counts)));
+  TRY_RC(dalloc(c->dShardBase, 16));
+  TRY_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->hFrame), sizeof(FrameStaging)));
+  memset(c->hFrame, 0, sizeof(FrameStaging));
+  size_t lbBytes = size_t(tc::lookback_tiles_needed(c->maxVisible, c->maxSplit, c->maxPart)) * tc::lookback_desc_bytes();
+  TRY_RC(dalloc(c->dLookback, lbBytes));
+  TRY_CUDA(cudaMemset(c->dLookback, 0, lbBytes));
+  TRY_CUDA(cudaMemset(c->dEpoch, 0, 16));
+  TRY_CUDA(cudaMemset(c->dShardBase, 0, 16));
+  TRY_CUDA(cudaMemset(c->dReadback, 0, sizeof(tc_Readback)));
+  TRY_CUDA(cudaMemset(c->dState, 0, tc::frame_state_bytes()));
+
+  const size_t G = c->maxGenClusters;
+  TRY_RC(dalloc(c->visibleClusters, size_t(c->maxVisible) * sizeof(tc_ClusterInfo)));
+  TRY_RC(dalloc(c->splitTriangles, size_t(c->maxSplit) * sizeof(tc_TessTriangleInfo)));
+  TRY_RC(dalloc(c->partTriangles, size_t(c->maxPart) * sizeof(tc_TessTriangleInfo)));
+  TRY_RC(dalloc(c->genVertices, size_t(c->maxVerts) * 12));
+  TRY_RC(dalloc(c->tempInstanceIDs, G * 4));
+  TRY_RC(dalloc(c->tempInstantiations, G * sizeof(tc_TemplateInstantiateInfo)));
+  TRY_RC(dalloc(c->tempClusterAddresses, G * 8));
+  TRY_RC(dalloc(c->tempClusterSizes, G * 4));
+  if(config->flags & (TC_FLAG_TRANSIENT_1X | TC_FLAG_TRANSIENT_2X))
+  {
+    TRY_RC(dalloc(c->transInstanceIDs, G * 4));
+    TRY_RC(dalloc(c->transBuilds, G * sizeof(tc_ClasBuildInfo)));
+    TRY_RC(dalloc(c->transClusterAddresses, G * 8));
+    TRY_RC(dalloc(c->transClusterSizes, G * 4));
+  }
+  TRY_RC(dalloc(c->blasClusterAddresses, G * 8));
+  if(config->allocClasData)
+    TRY_RC(dalloc(c->genClusterData, size_t(config->numGeneratedClusterMegs) * 1024 * 1024));
+  else
+    c->genClusterData = reinterpret_cast<void*>(0x0000700000000000ull);  // address range only; nothing dereferences it
+  TRY_CUDA(cudaMemset(c->partTriangles, 0, size_t(c->maxPart) * sizeof(tc_TessTriangleInfo)));
+  TRY_CUDA(cudaMemset(c->genVertices, 0, size_t(c->maxVerts) * 12));
+  TRY_CUDA(cudaMemset(c->tempClusterSizes, 0, G * 4));
+  TRY_CUDA(cudaMemset(c->blasClusterAddresses, 0, G * 8));
+  if(c->transClusterSizes)
+    TRY_CUDA(cudaMemset(c->transClusterSizes, 0, G * 4));
+  for(int i = 0; i <= TC_STAGE_COUNT; i++)
+    TRY_CUDA(cudaEventCreate(&c->ev[i]));
+  c->evValid = true;
+#undef TRY_RC
+#undef TRY_CUDA
+  *out = c;
+  return TC_OK;
+}
+
+TC_API void tc_destroy(tc_context* c)
+{
+  if(!c)
+    return;
+  cudaSetDevice(c->device);
+  if(c->stream)
+    cudaStreamSynchronize(c->stream);
+  drop_graph(c);
+  free_scene(c);
+  dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dFrame);
+  dfree(c->dShardCounts); dfree(c->dShardBase);
+  if(c->hFrame)
+    cudaFreeHost(c->hFrame);
+  dfree(c->visibleClusters); dfree(c->splitTriangles); dfree(c->partTriangles); dfree(c->genVertices);
+  dfree(c->tempInstanceIDs); dfree(c->tempInstantiations); dfree(c->tempClusterAddresses); dfree(c->tempClusterSizes);
+  dfree(c->transInstanceIDs); dfree(c->transBuilds); dfree(c->transClusterAddresses); dfree(c->transClusterSizes);
+  dfree(c->blasClusterAddresses);
+  if(c->cfg.allocClasData)
+    dfree(c->genClusterData);
+  dfree(c->tblVertices); dfree(c->tblTriangles); dfree(c->tblEntries); dfree(c->tblTemplAddr); dfree(c->tblTemplSize);
+  dfree(c->hiz);
+  dfree(c->flushBuf);
+  if(c->evValid)
+    for(int i = 0; i <= TC_STAGE_COUNT; i++)
+      cudaEventDestroy(c->ev[i]);
+  if(c->stream)
+    cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+TC_API int tc_set_tess_table(tc_context* c, const uint32_t* vertices, uint32_t numVertices, const uint32_t* triangles, uint32_t numTriangles,
+                             const uint16_t* configs, uint32_t numConfigs, const uint64_t* templAddr4096, const uint32_t* templSize4096)
+{
+  if(!c || !vertices || !triangles || !configs || !templAddr4096 || !templSize4096)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  // TessellationTable::init lookup scatter (tessellation_table.cpp:52-81)
+  std::vector<tc_TessTableEntry> lookup(TC_TESSTABLE_LOOKUP_ENTRIES, tc_TessTableEntry{0, 0, 0, 0});
+  const tc_TessTableEntry*       orig = reinterpret_cast<const tc_TessTableEntry*>(configs);
+  auto     idx3 = [](uint32_t x, uint32_t y, uint32_t z) { return x + y * TC_TESSTABLE_LOOKUP_SIZE + z * TC_TESSTABLE_LOOKUP_SIZE * TC_TESSTABLE_LOOKUP_SIZE - 273u; };
+  uint32_t configIdx = 0;
+  for(uint32_t x = 1; x <= TC_TESSTABLE_SIZE; x++)
+    for(uint32_t y = 1; y <= x; y++)
+      for(uint32_t z = 1; z <= y; z++, configIdx++)
+      {
+        if(configIdx >= numConfigs)
+          return fail(TC_ERR_INVALID_ARG, "raw table holds fewer configs than 11-segment enumeration needs");
+        const tc_TessTableEntry& e = orig[configIdx];
+        if(uint32_t(e.firstVertex) + e.numVertices > numVertices || uint32_t(e.firstTriangle) + e.numTriangles > numTriangles)
+          return fail(TC_ERR_INVALID_ARG, "config entry points outside the vertex/triangle arrays");
+        lookup[idx3(x, y, z)] = e;
+        if(z != y && x > 1)
+          lookup[idx3(x, z, y)] = e;
+      }
+  dfree(c->tblVertices); dfree(c->tblTriangles); dfree(c->tblEntries); dfree(c->tblTemplAddr); dfree(c->tblTemplSize);
+  c->tblVertices = c->tblTriangles = c->tblEntries = c->tblTemplAddr = c->tblTemplSize = nullptr;
+  int rc;
+  if((rc = dalloc(c->tblVertices, size_t(numVertices) * 4)) || (rc = dalloc(c->tblTriangles, size_t(numTriangles) * 4))
+     || (rc = dalloc(c->tblEntries, lookup.size() * sizeof(tc_TessTableEntry))) || (rc = dalloc(c->tblTemplAddr, TC_TESSTABLE_LOOKUP_ENTRIES * 8))
+     || (rc = dalloc(c->tblTemplSize, TC_TESSTABLE_LOOKUP_ENTRIES * 4)))
+    return rc;
+  CUDA_TRY(cudaMemcpy(c->tblVertices, vertices, size_t(numVertices) * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->tblTriangles, triangles, size_t(numTriangles) * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->tblEntries, lookup.data(), lookup.size() * sizeof(tc_TessTableEntry), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->tblTemplAddr, templAddr4096, TC_TESSTABLE_LOOKUP_ENTRIES * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->tblTemplSize, templSize4096, TC_TESSTABLE_LOOKUP_ENTRIES * 4, cudaMemcpyHostToDevice));
+  c->tableSet = true;
+  drop_graph(c);
+  fill_params(c);
+  return TC_OK;
+}
+
+TC_API int tc_set_scene(tc_context* c, const tc_geometry* geoms, uint32_t numGeoms, const tc_RenderInstance* instances, uint32_t numInstances,
+                        const tc_texture* textures, uint32_t numTextures, const uint32_t* basicClusterSizes, uint32_t numBasicClusterSizes)
+{
+  if(!c || !geoms || !instances || numGeoms == 0 || numInstances == 0)
+    return fail(TC_ERR_INVALID_ARG, "scene needs at least one geometry and one instance");
+  if(numTextures > TC_MAX_TEXTURES)
+    return fail(TC_ERR_LIMIT, "too many displacement textures");
+  const bool transient = (c->cfg.flags & (TC_FLAG_TRANSIENT_1X | TC_FLAG_TRANSIENT_2X)) != 0;
+  if(transient && (!basicClusterSizes || numBasicClusterSizes < std::max(c->cfg.clusterTriangles, 32u) + 1))
+    return fail(TC_ERR_INVALID_ARG, "basicClusterSizes must hold clusterTriangles+1 (>= 33) entries when transient builds are on");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  drop_graph(c);
+  free_scene(c);
+
+  c->geoms.resize(numGeoms);
+  for(uint32_t i = 0; i < numGeoms; i++)
+  {
+    const tc_geometry& g = geoms[i];
+    DeviceGeometry&    d = c->geoms[i];
+    for(uint32_t k = 0; k < g.numClusters; k++)
+      if(g.clusters[k].numVertices > c->cfg.clusterVertices || g.clusters[k].numTriangles > c->cfg.clusterTriangles)
+        return fail(TC_ERR_LIMIT, "cluster exceeds tc_config.clusterVertices/clusterTriangles");
+    d.numClusters = g.numClusters;
+    int rc;
+    if((rc = dalloc(d.positions, size_t(g.numVertices) * 12)) || (rc = dalloc(d.normals, size_t(g.numVertices) * 12))
+       || (rc = dalloc(d.texcoords, size_t(g.numVertices) * 8)) || (rc = dalloc(d.clusters, size_t(g.numClusters) * sizeof(tc_Cluster)))
+       || (rc = dalloc(d.localTriangles, size_t(g.numLocalTriangleBytes))) || (rc = dalloc(d.bboxes, size_t(g.numClusters) * sizeof(tc_BBox)))
+       || (rc = dalloc(d.templAddr, size_t(g.numClusters) * 8)) || (rc = dalloc(d.templSize, size_t(g.numClusters) * 4)))
+      return rc;
+    CUDA_TRY(cudaMemcpy(d.positions, g.positions, size_t(g.numVertices) * 12, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.normals, g.normals, size_t(g.numVertices) * 12, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.texcoords, g.texcoords, size_t(g.numVertices) * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.clusters, g.clusters, size_t(g.numClusters) * sizeof(tc_Cluster), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.localTriangles, g.localTriangles, size_t(g.numLocalTriangleBytes), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.bboxes, g.clusterBboxes, size_t(g.numClusters) * sizeof(tc_BBox), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.templAddr, g.clusterTemplateAddresses, size_t(g.numClusters) * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.templSize, g.clusterTemplateInstantiationSizes, size_t(g.numClusters) * 4, cudaMemcpyHostToDevice));
+  }
+
+  // Renderer::initBasics address patch (renderer.cpp:199-204) + cluster prefix for the fused cull
+  std::vector<tc_RenderInstance> inst(instances, instances + numInstances);
+  std::vector<uint32_t>          prefix(numInstances + 1, 0);
+  for(uint32_t i = 0; i < numInstances; i++)
+  {
+    if(inst[i].geometryID >= numGeoms)
+      return fail(TC_ERR_INVALID_ARG, "instance references a geometry that does not exist");
+    if(inst[i].displacementIndex >= int32_t(numTextures))
+      return fail(TC_ERR_INVALID_ARG, "instance references a displacement texture that does not exist");
+    const DeviceGeometry& d      = c->geoms[inst[i].geometryID];
+    inst[i].positions            = uint64_t(d.positions);
+    inst[i].normals              = uint64_t(d.normals);
+    inst[i].texcoords            = uint64_t(d.texcoords);
+    inst[i].clusters             = uint64_t(d.clusters);
+    inst[i].clusterLocalTriangles = uint64_t(d.localTriangles);
+    inst[i].clusterBboxes        = uint64_t(d.bboxes);
+    inst[i].clusterTemplateAdresses          = uint64_t(d.templAddr);
+    inst[i].clusterTemplateInstantiatonSizes = uint64_t(d.templSize);
+    inst[i].numClusters          = d.numClusters;
+    uint64_t next                = uint64_t(prefix[i]) + d.numClusters;
+    if(next > 0xFFFFFFFFull)
+      return fail(TC_ERR_LIMIT, "more than 2^32 clusters");
+    prefix[i + 1] = uint32_t(next);
+  }
+  c->numInstances  = numInstances;
+  c->totalClusters = prefix[numInstances];
+  int rc;
+  if((rc = dalloc(c->dInstances, size_t(numInstances) * sizeof(tc_RenderInstance))) || (rc = dalloc(c->dClusterPrefix, size_t(numInstances + 1) * 4))
+     || (rc = dalloc(c->instanceStates, size_t(numInstances) * 4)) || (rc = dalloc(c->blasBuildInfos, size_t(numInstances) * sizeof(tc_BlasBuildInfo)))
+     || (rc = dalloc(c->blasBuildSizes, size_t(numInstances) * 4)) || (rc = dalloc(c->basicClusterSizes, size_t(std::max(numBasicClusterSizes, 1u)) * 4))
+     || (rc = dalloc(c->segLo, size_t(TC_MAX_SEGMENTS + 2) * (numInstances + 1) * 4)) || (rc = dalloc(c->rankBase, size_t(TC_MAX_SEGMENTS + 2) * (numInstances + 1) * 4)))
+    return rc;
+  CUDA_TRY(cudaMemcpy(c->dInstances, inst.data(), size_t(numInstances) * sizeof(tc_RenderInstance), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->dClusterPrefix, prefix.data(), size_t(numInstances + 1) * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(c->instanceStates, 0, size_t(numInstances) * 4));
+  CUDA_TRY(cudaMemset(c->blasBuildInfos, 0, size_t(numInstances) * sizeof(tc_BlasBuildInfo)));
+  CUDA_TRY(cudaMemset(c->blasBuildSizes, 0, size_t(numInstances) * 4));
+  if(basicClusterSizes && numBasicClusterSizes)
+    CUDA_TRY(cudaMemcpy(c->basicClusterSizes, basicClusterSizes, size_t(numBasicClusterSizes) * 4, cudaMemcpyHostToDevice));
+
+  c->params.numTextures = numTextures;
+  for(uint32_t t = 0; t < numTextures; t++)
+  {
+    void*  d     = nullptr;
+    size_t bytes = size_t(textures[t].width) * textures[t].height * 4;
+    if(bytes == 0)
+      return fail(TC_ERR_INVALID_ARG, "empty displacement texture");
+    if((rc = dalloc(d, bytes)))
+      return rc;
+    c->textures.push_back(d);
+    CUDA_TRY(cudaMemcpy(d, textures[t].texels, bytes, cudaMemcpyHostToDevice));
+    c->params.textures[t] = tc::DeviceTexture{reinterpret_cast<const float*>(d), textures[t].width, textures[t].height};
+  }
+  c->sceneSet = true;
+  fill_params(c);
+  return upload_template(c);
+}
+
+TC_API int tc_set_hiz(tc_context* c, const float* mips, uint32_t size, uint32_t mipLevels)
+{
+  if(!c || !mips || size == 0 || mipLevels == 0 || (size & (size - 1)))
+    return fail(TC_ERR_INVALID_ARG, "hiz must be a square power-of-two pyramid");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  size_t total = 0;
+  for(uint32_t l = 0; l < mipLevels; l++)
+  {
+    size_t s = std::max(1u, size >> l);
+    total += s * s;
+  }
+  dfree(c->hiz);
+  c->hiz = nullptr;
+  int rc = dalloc(c->hiz, total * 4);
+  if(rc)
+    return rc;
+  CUDA_TRY(cudaMemcpy(c->hiz, mips, total * 4, cudaMemcpyHostToDevice));
+  c->params.hizSize = size;
+  c->params.hizMips = mipLevels;
+  drop_graph(c);
+  fill_params(c);
+  return TC_OK;
+}
+
+TC_API int tc_set_driver_standin(tc_context* c, uint32_t mode)
+{
+  if(!c)
+    return fail(TC_ERR_INVALID_ARG, "null context");
+  c->driverStandin = mode ? 1 : 0;
+  drop_graph(c);
+  fill_params(c);
+  return TC_OK;
+}
+
+TC_API int tc_frame_build(tc_context* c, const void* frameConstants, size_t strideBytes, const float* viewPosOverride)
+{
+  int rc = check_ready(c);
+  if(rc)
+    return rc;
+  if((rc = stage_frame_inputs(c, frameConstants, strideBytes, viewPosOverride)))
+    return rc;
+  return enqueue_build(c);
+}
+
+TC_API int tc_frame_insert(tc_context* c)
+{
+  int rc = check_ready(c);
+  if(rc)
+    return rc;
+  return enqueue_insert(c);
+}
+
+TC_API int tc_frame(tc_context* c, const void* frameConstants, size_t strideBytes, const float* viewPosOverride)
+{
+  int rc = tc_frame_build(c, frameConstants, strideBytes, viewPosOverride);
+  if(rc)
+    return rc;
+  return enqueue_insert(c);
+}
+
+TC_API int tc_frame_graph(tc_context* c, const void* frameConstants, size_t strideBytes, const float* viewPosOverride)
+{
+  int rc = check_ready(c);
+  if(rc)
+    return rc;
+  if((rc = stage_frame_inputs(c, frameConstants, strideBytes, viewPosOverride)))
+    return rc;
+  if(!c->graphExec)
+  {
+    bool savedTimers = c->timers;
+    c->timers        = false;
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_build(c);
+    if(rc == TC_OK)
+      rc = enqueue_insert(c);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    c->timers     = savedTimers;
+    if(rc != TC_OK)
+      return rc;
+    if(e != cudaSuccess)
+      return fail(TC_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&c->graphExec, graph, 0);
+    cudaGraphDestroy(graph);
+    if(e != cudaSuccess)
+      return fail(TC_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+  }
+  CUDA_TRY(cudaGraphLaunch(c->graphExec, c->stream));
+  return TC_OK;
+}
+
+TC_API int tc_sync(tc_context* c)
+{
+  if(!c)
+    return fail(TC_ERR_INVALID_ARG, "null context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return TC_OK;
+}
+
+TC_API int tc_readback(tc_context* c, tc_Readback* readback, tc_SceneBuilding* building)
+{
+  if(!c)
+    return fail(TC_ERR_INVALID_ARG, "null context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if(readback)
+    CUDA_TRY(cudaMemcpyAsync(readback, c->dReadback, sizeof(tc_Readback), cudaMemcpyDeviceToHost, c->stream));
+  if(building)
+    CUDA_TRY(cudaMemcpyAsync(building, c->dBuild, sizeof(tc_SceneBuilding), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return TC_OK;
+}
+
+TC_API int tc_device_scene_building(tc_context* c, uint64_t* deviceAddress)
+{
+  if(!c || !deviceAddress)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  *deviceAddress = uint64_t(c->dBuild);
+  return TC_OK;
+}
+
+TC_API int tc_device_render_instances(tc_context* c, uint64_t* deviceAddress)
+{
+  if(!c || !deviceAddress)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  *deviceAddress = uint64_t(c->dInstances);
+  return TC_OK;
+}
+
+TC_API int tc_device_tess_table(tc_context* c, tc_TessellationTable* table)
+{
+  if(!c || !table)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  table->vertices                   = uint64_t(c->tblVertices);
+  table->triangles                  = uint64_t(c->tblTriangles);
+  table->entries                    = uint64_t(c->tblEntries);
+  table->templateAddresses          = uint64_t(c->tblTemplAddr);
+  table->templateInstantiationSizes = uint64_t(c->tblTemplSize);
+  return TC_OK;
+}
+
+TC_API int tc_download(tc_context* c, uint64_t src, void* dst, size_t bytes)
+{
+  if(!c || !dst || !src)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(dst, reinterpret_cast<const void*>(src), bytes, cudaMemcpyDeviceToHost));
+  return TC_OK;
+}
+
+TC_API int tc_stream(tc_context* c, uint64_t* stream)
+{
+  if(!c || !stream)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  *stream = uint64_t(c->stream);
+  return TC_OK;
+}
+
+TC_API int tc_enable_stage_timers(tc_context* c, int enable)
+{
+  if(!c)
+    return fail(TC_ERR_INVALID_ARG, "null context");
+  c->timers = enable != 0;
+  return TC_OK;
+}
+
+TC_API int tc_stage_times(tc_context* c, float msOut[TC_STAGE_COUNT])
+{
+  if(!c || !msOut)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for(int i = 0; i < TC_STAGE_COUNT; i++)
+  {
+    msOut[i] = 0.f;
+    if(cudaEventElapsedTime(&msOut[i], c->ev[i], c->ev[i + 1]) != cudaSuccess)
+    {
+      cudaGetLastError();
+      msOut[i] = -1.f;
+    }
+  }
+  return TC_OK;
+}
+
+TC_API int tc_last_launch_count(tc_context* c, uint32_t* launches)
+{
+  if(!c || !launches)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  *launches = c->lastLaunches;
+  return TC_OK;
+}
+
+TC_API int tc_flush_l2(tc_context* c)
+{
+  if(!c)
+    return fail(TC_ERR_INVALID_ARG, "null context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if(!c->flushBuf)
+  {
+    c->flushBytes = size_t(256) << 20;  // > 126 MB L2
+    int rc        = dalloc(c->flushBuf, c->flushBytes);
+    if(rc)
+      return rc;
+  }
+  tc::launch_flush_l2(c->flushBuf, c->flushBytes, c->stream);
+  CUDA_TRY(cudaGetLastError());
+  return TC_OK;
+}
+
+TC_API int tc_device_shard_counts(tc_context* c, uint64_t* deviceAddress)
+{
+  if(!c || !deviceAddress)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  *deviceAddress = uint64_t(c->dShardCounts);
+  return TC_OK;
+}
+
+TC_API int tc_device_shard_base(tc_context* c, uint64_t* deviceAddress)
+{
+  if(!c || !deviceAddress)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  *deviceAddress = uint64_t(c->dShardBase);
+  return TC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,509 @@
+// tc_device.cuh -- device-side helpers shared by the kernels of the tessellation path (sm_100a).
+//
+// Two numeric regimes (DESIGN.md "floating point"):
+//   EXACT  : everything that feeds an integer decision (edge factors, barycentric encode, culling bits).
+//            Written with __fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn so that ptxas can never contract to FMA and
+//            the operation order is the documented one (same order as the CPU oracle).
+//   FAST   : generated vertex positions (tolerance 1e-5 relative): FMA, rsqrt, refactored polynomials.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tess_clusters.h"
+
+namespace tc {
+
+// ------------------------------------------------------------------------------------------------------------
+// parameters handed to every kernel (by value, < 1 KB)
+// ------------------------------------------------------------------------------------------------------------
+
+struct DeviceTexture
+{
+  const float* texels;
+  uint32_t     width, height;
+};
+
+#define TC_MAX_TEXTURES 16
+#define TC_MAX_SEGMENTS 16  // part list segments: classify + up to 14 split passes
+
+// Internal per-frame state that is not part of the reference's SceneBuilding (scan tickets, segment bounds).
+struct FrameState
+{
+  uint32_t ticket[20];       // dynamic tile tickets, one per kernel launch slot
+  uint32_t done[20];         // finished-CTA counters (last CTA runs the build_setup logic)
+  uint32_t validParts;       // number of part entries written this frame (prefix property)
+  uint32_t numParts;         // parts visited by instantiate
+  uint32_t tempAfterClassify;
+  uint32_t transAfterClassify;
+  uint32_t partSegEnd[TC_MAX_SEGMENTS];  // part count after classify, after split pass 0..5
+  uint32_t numPartSegs;
+  uint32_t splitPassesLeft;
+  uint32_t hiAfterClassify;  // transient (back) side of the dual counter, constant during split
+  uint32_t pad[5];
+  // aggregated stats kept as plain counters and folded into Readback by the setup steps
+  unsigned long long genActualDatas;
+};
+
+struct Params
+{
+  tc_SceneBuilding*        build;      // live SceneBuilding (reference layout)
+  tc_Readback*             readback;
+  const tc_FrameConstants* view;       // [0] = current, [1] = last
+  const tc_RenderInstance* instances;
+  const uint32_t*          instanceClusterPrefix;  // [numInstances+1] exclusive prefix of numClusters
+  FrameState*              state;
+  // tessellation table
+  const uint32_t*          tblVertices;
+  const uint32_t*          tblTriangles;
+  const tc_TessTableEntry* tblEntries;
+  const uint64_t*          tblTemplAddr;
+  const uint32_t*          tblTemplSize;
+  const uint32_t*          basicClusterSizes;
+  // hiz
+  const float*             hiz;
+  uint32_t                 hizSize, hizMips;
+  // displacement textures
+  DeviceTexture            textures[TC_MAX_TEXTURES];
+  uint32_t                 numTextures;
+  // limits (the reference's shader macros)
+  uint32_t maxVisibleClusters, maxPartTriangles, maxSplitTriangles, maxGenVertices, maxGenClusters;
+  unsigned long long maxGenDataBytes;
+  uint32_t splitFactor, clusterVertices, clusterTriangles;
+  uint32_t flags;
+  uint32_t numInstances, totalClusters;
+  uint32_t driverStandin;
+  uint32_t epoch;  // look-back flag epoch of this launch (set per kernel by the host)
+  // look-back descriptors
+  void*    lookback;
+  // blas helpers
+  uint32_t* segLo;     // [TC_MAX_SEGMENTS+1][numInstances]
+  uint32_t* rankBase;  // [TC_MAX_SEGMENTS+1][numInstances]
+  const uint32_t* shardBase;  // {globalBlasClusterBase, globalInstanceBase}
+};
+
+__device__ __forceinline__ bool flag_pn(const Params& p) { return p.flags & TC_FLAG_PN_DISPLACEMENT; }
+__device__ __forceinline__ bool flag_1x(const Params& p) { return p.flags & TC_FLAG_TRANSIENT_1X; }
+__device__ __forceinline__ bool flag_2x(const Params& p) { return p.flags & TC_FLAG_TRANSIENT_2X; }
+__device__ __forceinline__ bool flag_transient(const Params& p) { return p.flags & (TC_FLAG_TRANSIENT_1X | TC_FLAG_TRANSIENT_2X); }
+__device__ __forceinline__ bool flag_culling(const Params& p) { return p.flags & TC_FLAG_CULLING; }
+__device__ __forceinline__ bool flag_animation(const Params& p) { return p.flags & TC_FLAG_ANIMATION; }
+
+// ------------------------------------------------------------------------------------------------------------
+// EXACT float helpers (no contraction, fixed order)
+// ------------------------------------------------------------------------------------------------------------
+
+struct F3 { float x, y, z; };
+struct F4 { float x, y, z, w; };
+
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
+
+__device__ __forceinline__ float xdot3(F3 a, F3 b) { return xadd(xadd(xmul(a.x, b.x), xmul(a.y, b.y)), xmul(a.z, b.z)); }
+__device__ __forceinline__ F3    xsub3(F3 a, F3 b) { return {xsub(a.x, b.x), xsub(a.y, b.y), xsub(a.z, b.z)}; }
+__device__ __forceinline__ float xdistance3(F3 a, F3 b)
+{
+  F3 d = xsub3(a, b);
+  return xsqrt(xdot3(d, d));
+}
+
+// GLSL mat4 * vec4, column-major, summed left to right over columns (oracle: mat4_mul)
+__device__ __forceinline__ F4 xmat4_mul(const float* m, F4 v)
+{
+  F4 r;
+  r.x = xadd(xadd(xadd(xmul(m[0], v.x), xmul(m[4], v.y)), xmul(m[8], v.z)), xmul(m[12], v.w));
+  r.y = xadd(xadd(xadd(xmul(m[1], v.x), xmul(m[5], v.y)), xmul(m[9], v.z)), xmul(m[13], v.w));
+  r.z = xadd(xadd(xadd(xmul(m[2], v.x), xmul(m[6], v.y)), xmul(m[10], v.z)), xmul(m[14], v.w));
+  r.w = xadd(xadd(xadd(xmul(m[3], v.x), xmul(m[7], v.y)), xmul(m[11], v.z)), xmul(m[15], v.w));
+  return r;
+}
+__device__ __forceinline__ F3 xtransform_point(const float* m, F3 p)
+{
+  F3 r;
+  r.x = xadd(xadd(xadd(xmul(m[0], p.x), xmul(m[4], p.y)), xmul(m[8], p.z)), m[12]);  // m[12]*1.0f == m[12]
+  r.y = xadd(xadd(xadd(xmul(m[1], p.x), xmul(m[5], p.y)), xmul(m[9], p.z)), m[13]);
+  r.z = xadd(xadd(xadd(xmul(m[2], p.x), xmul(m[6], p.y)), xmul(m[10], p.z)), m[14]);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// tessellation.glsl (EXACT)
+// ------------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t tess_encodeBarycentrics(F3 wuv)  // tessellation.glsl:48-59
+{
+  uint32_t ix = (uint32_t)xadd(xmul(wuv.x, 32768.0f), 0.5f);
+  uint32_t iy = (uint32_t)xadd(xmul(wuv.y, 32768.0f), 0.5f);
+  uint32_t iz = (uint32_t)xadd(xmul(wuv.z, 32768.0f), 0.5f);
+  if(ix > max(iy, iz))
+    ix = TC_TESSTABLE_COORD_MAX - iy - iz;
+  else if(iy > iz)
+    iy = TC_TESSTABLE_COORD_MAX - ix - iz;
+  else
+    iz = TC_TESSTABLE_COORD_MAX - ix - iy;
+  return iy | (iz << 16);
+}
+
+__device__ __forceinline__ F3 tess_decodeBarycentrics(uint32_t vtx)  // tessellation.glsl:66-76
+{
+  F3 wuv;
+  wuv.y = xmul(float(vtx & 0xFFFF), 1.0f / 32768.0f);  // exact: power-of-two scale == the reference's division
+  wuv.z = xmul(float(vtx >> 16), 1.0f / 32768.0f);
+  wuv.x = xsub(xsub(1.0f, wuv.y), wuv.z);
+  return wuv;
+}
+
+struct FactorConsts
+{
+  F3    eye;
+  float nearPlane, viewportY, tessRate;
+};
+
+__device__ __forceinline__ FactorConsts load_factor_consts(const Params& p)
+{
+  FactorConsts c;
+  c.eye       = {p.build->viewPos[0], p.build->viewPos[1], p.build->viewPos[2]};
+  c.nearPlane = p.view[0].nearPlane;
+  c.viewportY = p.view[0].viewportf[1];
+  c.tessRate  = p.view[0].tessRate;
+  return c;
+}
+
+// tess_getTessFactors (tessellation.glsl:78-99) on three world-space points whose eye distances are given
+__device__ __forceinline__ void tess_factors(const FactorConsts& c, F3 a, F3 b, F3 cc, float dA, float dB, float dC, uint32_t f[3])
+{
+  float sx = xdiv(1.0f, fmaxf(c.nearPlane, fminf(dA, dB)));
+  float sy = xdiv(1.0f, fmaxf(c.nearPlane, fminf(dB, dC)));
+  float sz = xdiv(1.0f, fmaxf(c.nearPlane, fminf(dC, dA)));
+  float ex = xdistance3(a, b), ey = xdistance3(b, cc), ez = xdistance3(cc, a);
+  float fx = rintf(xmul(xmul(xmul(ex, sx), c.viewportY), c.tessRate));  // round(): ties-to-even, see DESIGN.md
+  float fy = rintf(xmul(xmul(xmul(ey, sy), c.viewportY), c.tessRate));
+  float fz = rintf(xmul(xmul(xmul(ez, sz), c.viewportY), c.tessRate));
+  f[0] = (uint32_t)fminf(fmaxf(fx, 1.0f), 32768.0f);
+  f[1] = (uint32_t)fminf(fmaxf(fy, 1.0f), 32768.0f);
+  f[2] = (uint32_t)fminf(fmaxf(fz, 1.0f), 32768.0f);
+}
+
+__device__ __forceinline__ uint32_t tess_splitFactor(uint32_t f, uint32_t maxSplit)  // tessellation.glsl:101-104
+{
+  return min((f + TC_TESSTABLE_SIZE - 1) / TC_TESSTABLE_SIZE, maxSplit);
+}
+
+__device__ __forceinline__ uint32_t tess_configIndex(uint32_t cfg) { return cfg & ~TC_CONFIG_FLIPPED_BIT; }
+
+// tess_getConfig (tessellation.glsl:119-144): factors by value, vertex triple rotated the same way
+__device__ __forceinline__ uint32_t tess_getConfig(uint32_t fx, uint32_t fy, uint32_t fz, uint32_t& v0, uint32_t& v1, uint32_t& v2)
+{
+  uint32_t m = max(max(fx, fy), fz);
+  if(m == fy)
+  {
+    uint32_t t = fx, tv = v0;
+    fx = fy; fy = fz; fz = t;
+    v0 = v1; v1 = v2; v2 = tv;
+  }
+  else if(m == fz)
+  {
+    uint32_t t = fz, tv = v2;
+    fz = fy; fy = fx; fx = t;
+    v2 = v1; v1 = v0; v0 = tv;
+  }
+  uint32_t idx = fx + fy * 16u + fz * 256u - 273u;
+  if(fz > fy)
+    idx |= TC_CONFIG_FLIPPED_BIT;
+  return idx;
+}
+
+__device__ __forceinline__ tc_TessTableEntry tess_entry(const Params& p, uint32_t cfg)
+{
+  // 8-byte entry as one 64-bit read-only load
+  unsigned long long raw = __ldg(reinterpret_cast<const unsigned long long*>(p.tblEntries) + (tess_configIndex(cfg) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1)));
+  tc_TessTableEntry  e;
+  e.firstTriangle = uint16_t(raw);
+  e.firstVertex   = uint16_t(raw >> 16);
+  e.numTriangles  = uint16_t(raw >> 32);
+  e.numVertices   = uint16_t(raw >> 48);
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// warp utilities
+// ------------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t lanemask_lt()
+{
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ uint32_t warp_inclusive_add(uint32_t v)
+{
+#pragma unroll
+  for(int d = 1; d < 32; d <<= 1)
+  {
+    uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
+    if(lane_id() >= d)
+      v += n;
+  }
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v)
+{
+#pragma unroll
+  for(int d = 16; d > 0; d >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// decoupled look-back over fixed-size tuples.  One descriptor per tile; flags carry the launch epoch so the
+// array never needs clearing between frames.
+// ------------------------------------------------------------------------------------------------------------
+
+struct ScanTuple
+{
+  uint32_t           v[6];
+  unsigned long long d;  // 64-bit lane (CLAS data bytes)
+  __device__ __forceinline__ void add(const ScanTuple& o)
+  {
+#pragma unroll
+    for(int i = 0; i < 6; i++)
+      v[i] += o.v[i];
+    d += o.d;
+  }
+  __device__ __forceinline__ void zero()
+  {
+#pragma unroll
+    for(int i = 0; i < 6; i++)
+      v[i] = 0;
+    d = 0;
+  }
+};
+
+struct __align__(128) LookbackDesc
+{
+  ScanTuple aggregate;  // 32 B
+  ScanTuple inclusive;  // 32 B
+  uint32_t  flag;       // epoch << 2 | state (1 = aggregate ready, 2 = inclusive ready)
+  uint32_t  pad[15];
+};
+
+__device__ __forceinline__ void st_tuple(ScanTuple* dst, const ScanTuple& t)
+{
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  __stcg(d, make_uint4(t.v[0], t.v[1], t.v[2], t.v[3]));
+  __stcg(d + 1, make_uint4(t.v[4], t.v[5], uint32_t(t.d), uint32_t(t.d >> 32)));
+}
+__device__ __forceinline__ ScanTuple ld_tuple(const ScanTuple* src)
+{
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4        a = __ldcg(s), b = __ldcg(s + 1);
+  ScanTuple    t;
+  t.v[0] = a.x; t.v[1] = a.y; t.v[2] = a.z; t.v[3] = a.w;
+  t.v[4] = b.x; t.v[5] = b.y;
+  t.d    = (unsigned long long)b.z | ((unsigned long long)b.w << 32);
+  return t;
+}
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* f)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_flag(uint32_t* f, uint32_t v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ ScanTuple warp_reduce_tuple(ScanTuple t)
+{
+#pragma unroll
+  for(int d = 16; d > 0; d >>= 1)
+  {
+#pragma unroll
+    for(int i = 0; i < 6; i++)
+      t.v[i] += __shfl_xor_sync(0xffffffffu, t.v[i], d);
+    t.d += __shfl_xor_sync(0xffffffffu, t.d, d);
+  }
+  return t;
+}
+
+// Called by ONE full warp of the CTA that owns `tile`.  Publishes `aggregate`, returns the exclusive prefix of all
+// earlier tiles (same value in every lane) and publishes the inclusive prefix.
+__device__ __forceinline__ ScanTuple lookback_exclusive(LookbackDesc* descs, uint32_t tile, const ScanTuple& aggregate, uint32_t epoch)
+{
+  const uint32_t lane = lane_id();
+  const uint32_t AGG = (epoch << 2) | 1u, INC = (epoch << 2) | 2u;
+  ScanTuple      exclusive;
+  exclusive.zero();
+  if(tile == 0)
+  {
+    if(lane == 0)
+    {
+      st_tuple(&descs[0].inclusive, aggregate);
+      st_flag(&descs[0].flag, INC);
+    }
+    return exclusive;
+  }
+  if(lane == 0)
+  {
+    st_tuple(&descs[tile].aggregate, aggregate);
+    st_flag(&descs[tile].flag, AGG);
+  }
+  int32_t base = int32_t(tile) - 1;  // nearest predecessor examined by lane 0
+  while(true)
+  {
+    int32_t   t     = base - int32_t(lane);
+    uint32_t  state = 2;  // tiles before 0 behave as "inclusive = 0"
+    ScanTuple val;
+    val.zero();
+    if(t >= 0)
+    {
+      uint32_t f;
+      do
+      {
+        f = ld_flag(&descs[t].flag);
+      } while(f != AGG && f != INC);
+      state = f & 3u;
+      val   = ld_tuple(state == 2 ? &descs[t].inclusive : &descs[t].aggregate);
+    }
+    uint32_t incMask = __ballot_sync(0xffffffffu, state == 2);
+    // lanes at or before the first inclusive one contribute
+    uint32_t firstInc = incMask ? (__ffs(incMask) - 1) : 32;
+    if(lane > firstInc)
+      val.zero();
+    val = warp_reduce_tuple(val);
+    exclusive.add(val);
+    if(incMask)
+      break;
+    base -= 32;
+  }
+  if(lane == 0)
+  {
+    ScanTuple inc = exclusive;
+    inc.add(aggregate);
+    st_tuple(&descs[tile].inclusive, inc);
+    st_flag(&descs[tile].flag, INC);
+  }
+  return exclusive;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FAST vertex generation (displacement.glsl + the per-vertex body of instantiate / 2X mini)
+// ------------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ F3 f3(float x, float y, float z) { return {x, y, z}; }
+__device__ __forceinline__ F3 operator+(F3 a, F3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ F3 operator-(F3 a, F3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ F3 operator*(F3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ float dot3(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ F3 fma3(F3 a, float s, F3 acc) { return {fmaf(a.x, s, acc.x), fmaf(a.y, s, acc.y), fmaf(a.z, s, acc.z)}; }
+__device__ __forceinline__ F3 normalize3(F3 a) { return a * rsqrtf(dot3(a, a)); }
+
+__device__ __forceinline__ F3 ld_f3(const float* base, uint32_t index)
+{
+  const float* p = base + size_t(index) * 3;
+  return {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+}
+
+// software sampler: LOD 0, bilinear, repeat (same definition as the oracle's sample_displacement)
+__device__ __forceinline__ float sample_displacement(const DeviceTexture& t, float u, float v)
+{
+  float x  = fmaf(u, float(t.width), -0.5f);
+  float y  = fmaf(v, float(t.height), -0.5f);
+  float fx = floorf(x), fy = floorf(y);
+  float ax = x - fx, ay = y - fy;
+  int   w = int(t.width), h = int(t.height);
+  int   x0 = int(fx) % w, y0 = int(fy) % h;
+  if(x0 < 0) x0 += w;
+  if(y0 < 0) y0 += h;
+  int   x1 = x0 + 1 == w ? 0 : x0 + 1;
+  int   y1 = y0 + 1 == h ? 0 : y0 + 1;
+  const float* r0 = t.texels + size_t(y0) * w;
+  const float* r1 = t.texels + size_t(y1) * w;
+  float t00 = __ldg(r0 + x0), t10 = __ldg(r0 + x1), t01 = __ldg(r1 + x0), t11 = __ldg(r1 + x1);
+  float top = fmaf(t10 - t00, ax, t00);
+  float bot = fmaf(t11 - t01, ax, t01);
+  return fmaf(bot - top, ay, top);
+}
+
+struct DisplacementConsts
+{
+  float scale;   // inst.displacementScale * view.displacementScale
+  float offset;  // inst.displacementOffset + view.displacementOffset
+  int   texture; // < 0: none
+};
+
+__device__ __forceinline__ F3 ripple_deform(const tc_FrameConstants& view, F3 o, uint32_t seed, float geometrySize)
+{
+  float maxCoord  = fmaxf(fabsf(o.x), fmaxf(fabsf(o.y), fabsf(o.z)));
+  float frequency = view.animationRippleFrequency / geometrySize;
+  float phase     = view.animationState * view.animationRippleSpeed;
+  float s         = float(seed);
+  float mf        = maxCoord * frequency;
+  F3    wave      = {sinf((mf + s) + phase), cosf((mf * 3.0f + s) + phase), sinf((mf * 1.2f + s) + phase)};
+  F3    dir       = normalize3(f3(o.z, o.y, o.x));
+  float amp       = view.animationRippleAmplitude * geometrySize;
+  return {fmaf(dir.x, wave.x * amp, o.x), fmaf(dir.y, wave.y * amp, o.y), fmaf(dir.z, wave.z * amp, o.z)};
+}
+
+// Per-part data kept in registers while a thread walks the part's vertices.
+struct BaseTriangle
+{
+  // sub-triangle corners inside the base triangle: (u, v) of each, w = 1-u-v
+  float bu[3], bv[3];
+  // PN control points pre-scaled by their Bernstein multiplicity (3 for edge points, 6 for the centre)
+  F3 b300, b030, b003, b210, b120, b201, b021, b102, b012, b111;
+  F3 pos[3];  // only used when PN is off
+  F3 nrm[3];
+  float tu[3], tv[3];
+};
+
+__device__ __forceinline__ F3 project_to_plane(F3 p, F3 plane, F3 n)
+{
+  float d = dot3(p - plane, n);
+  return {fmaf(-d, n.x, p.x), fmaf(-d, n.y, p.y), fmaf(-d, n.z, p.z)};
+}
+
+// deform_setupPN (displacement.glsl:47-79), control points stored pre-multiplied
+__device__ __forceinline__ void setup_pn(BaseTriangle& b, const F3 v[3], const F3 n[3])
+{
+  const float third = 1.0f / 3.0f;
+  F3 vB030 = v[0], vB003 = v[1], vB300 = v[2];
+  F3 e300 = vB003 - vB030, e030 = vB300 - vB003, e003 = vB030 - vB300;
+  F3 vB021 = project_to_plane(fma3(e300, third, vB030), vB030, n[0]);
+  F3 vB012 = project_to_plane(fma3(e300, 2.0f * third, vB030), vB003, n[1]);
+  F3 vB102 = project_to_plane(fma3(e030, third, vB003), vB003, n[1]);
+  F3 vB201 = project_to_plane(fma3(e030, 2.0f * third, vB003), vB300, n[2]);
+  F3 vB210 = project_to_plane(fma3(e003, third, vB300), vB300, n[2]);
+  F3 vB120 = project_to_plane(fma3(e003, 2.0f * third, vB300), vB030, n[0]);
+  F3 center = (vB003 + vB030 + vB300) * third;
+  F3 vB111  = (vB021 + vB012 + vB102 + vB201 + vB210 + vB120) * (1.0f / 6.0f);
+  vB111     = fma3(vB111 - center, 0.5f, vB111);
+  b.b300 = vB300; b.b030 = vB030; b.b003 = vB003;
+  b.b210 = vB210 * 3.0f; b.b120 = vB120 * 3.0f; b.b201 = vB201 * 3.0f;
+  b.b021 = vB021 * 3.0f; b.b102 = vB102 * 3.0f; b.b012 = vB012 * 3.0f;
+  b.b111 = vB111 * 6.0f;
+}
+
+// deform_getPN (displacement.glsl:81-104): (u,v,w) = bary.xyz
+__device__ __forceinline__ F3 eval_pn(const BaseTriangle& b, float u, float v, float w)
+{
+  float u2 = u * u, v2 = v * v, w2 = w * w;
+  F3 p = b.b300 * (w2 * w);
+  p    = fma3(b.b030, u2 * u, p);
+  p    = fma3(b.b003, v2 * v, p);
+  p    = fma3(b.b210, w2 * u, p);
+  p    = fma3(b.b120, w * u2, p);
+  p    = fma3(b.b201, w2 * v, p);
+  p    = fma3(b.b021, u2 * v, p);
+  p    = fma3(b.b102, w * v2, p);
+  p    = fma3(b.b012, u * v2, p);
+  p    = fma3(b.b111, (w * u) * v, p);
+  return p;
+}
+
+}  // namespace tc

@@ -1,0 +1,1780 @@
+// tc_kernels.cu -- hand-written sm_100a kernels of the per-frame tessellation path.
+//
+// Stage map (reference shader -> kernel here), all cited relative to /root/reference:
+//   rt.cpp:412-419 resets                         -> k_frame_setup
+//   instances_classify.comp.glsl                  -> k_instances_classify
+//   clusters_cull.comp.glsl + BUILD_SETUP_CLASSIFY-> k_clusters_cull
+//   cluster_classify.comp.glsl + BUILD_SETUP_SPLIT-> k_cluster_classify   (persistent, decoupled look-back scan)
+//   triangle_split.comp.glsl + SPLIT_PASS / INSTANTIATE_TESS setup -> k_triangle_split (one launch per pass)
+//   triangle_tess_template_instantiate.comp.glsl + BUILD_SETUP_BUILD_BLAS -> k_instantiate
+//   blas_setup_insertion.comp.glsl                -> k_blas_setup
+//   blas_clusters_insert.comp.glsl                -> k_blas_insert
+//
+// Where the reference appends with global atomics (nondeterministic order) these kernels assign offsets with
+// prefix sums in the canonical order documented in DESIGN.md, so every output buffer is bit-reproducible and
+// compares byte-for-byte with the sequential CPU oracle.  The build_setup single-thread dispatches are folded
+// into the last CTA to finish the producing kernel.
+#include "tc_device.cuh"
+#include "tc_kernels.h"
+
+namespace tc {
+
+// launch slots (tickets / done counters / look-back epochs)
+enum
+{
+  SLOT_CLASSIFY    = 0,
+  SLOT_SPLIT0      = 1,  // .. SLOT_SPLIT0 + 14 (splitFactor 2 needs 14 passes)
+  SLOT_INSTANTIATE = 16
+};
+
+__device__ __forceinline__ uint32_t lo32(unsigned long long v) { return uint32_t(v); }
+__device__ __forceinline__ uint32_t hi32(unsigned long long v) { return uint32_t(v >> 32); }
+
+// ============================================================================================================
+// frame setup: rt.cpp:412-419
+// ============================================================================================================
+
+__global__ void k_frame_setup(Params p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter)
+{
+  const uint32_t t = threadIdx.x;
+  // SceneBuilding <- host template (all counters zero), word by word
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(tmpl);
+  uint32_t*       dst = reinterpret_cast<uint32_t*>(p.build);
+  for(uint32_t i = t; i < sizeof(tc_SceneBuilding) / 4; i += blockDim.x)
+    dst[i] = src[i];
+  uint32_t* rb = reinterpret_cast<uint32_t*>(p.readback);
+  for(uint32_t i = t; i < sizeof(tc_Readback) / 4; i += blockDim.x)
+    rb[i] = 0;
+  uint32_t* st = reinterpret_cast<uint32_t*>(p.state);
+  for(uint32_t i = t; i < sizeof(FrameState) / 4; i += blockDim.x)
+    st[i] = 0;
+  __syncthreads();
+  if(t < 3)
+    p.build->viewPos[t] = viewPosOverride ? viewPosOverride[t] : p.view[0].viewPos[t];
+  if(t == 0)
+    *epochCounter += 32;  // 32 launch slots per frame
+}
+
+// ============================================================================================================
+// culling.glsl (EXACT) + instances_classify
+// ============================================================================================================
+
+__device__ __forceinline__ uint32_t cull_bits(F4 h)
+{
+  uint32_t b = 0;
+  b |= h.x < -h.w ? 1 : 0;
+  b |= h.x > h.w ? 2 : 0;
+  b |= h.y < -h.w ? 4 : 0;
+  b |= h.y > h.w ? 8 : 0;
+  b |= h.z < 0 ? 16 : 0;
+  b |= h.z > h.w ? 32 : 0;
+  b |= h.w <= 0 ? 64 : 0;
+  return b;
+}
+
+// ceil(log2(x)) for x > 0, exact (defined like the oracle's frexp formulation)
+__device__ __forceinline__ int ceil_log2_exact(float x)
+{
+  int   e;
+  float m = frexpf(x, &e);
+  return m == 0.5f ? e - 1 : e;
+}
+
+__device__ float sample_hiz_max(const Params& p, float u, float v, float lod)
+{
+  int level = 0;
+  if(lod > 0.0f)
+    level = min(int(lod), int(p.hizMips) - 1);
+  uint32_t size = max(1u, p.hizSize >> level);
+  size_t   base = 0;
+  for(int l = 0; l < level; l++)
+  {
+    size_t s = max(1u, p.hizSize >> l);
+    base += s * s;
+  }
+  float x  = xsub(xmul(u, float(size)), 0.5f);
+  float y  = xsub(xmul(v, float(size)), 0.5f);
+  int   x0 = int(floorf(x)), y0 = int(floorf(y));
+  int   x1 = x0 + 1, y1 = y0 + 1;
+  int   hi = int(size) - 1;
+  x0 = min(max(x0, 0), hi); x1 = min(max(x1, 0), hi);
+  y0 = min(max(y0, 0), hi); y1 = min(max(y1, 0), hi);
+  const float* t = p.hiz + base;
+  float a = t[size_t(y0) * size + x0], b = t[size_t(y0) * size + x1];
+  float d = t[size_t(y1) * size + x0], e = t[size_t(y1) * size + x1];
+  return fmaxf(fmaxf(a, b), fmaxf(d, e));
+}
+
+__global__ void k_instances_classify(Params p)  // instances_classify.comp.glsl:102-128
+{
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= p.numInstances)
+    return;
+  const tc_RenderInstance& inst     = p.instances[i];
+  const tc_FrameConstants& viewLast = p.view[1];
+  // worldViewProj = viewLast.viewProjMatrix * worldMatrix, column by column
+  float wvp[16];
+#pragma unroll
+  for(int c = 0; c < 4; c++)
+  {
+    F4 r = xmat4_mul(viewLast.viewProjMatrix, F4{inst.worldMatrix[c * 4 + 0], inst.worldMatrix[c * 4 + 1], inst.worldMatrix[c * 4 + 2], inst.worldMatrix[c * 4 + 3]});
+    wvp[c * 4 + 0] = r.x; wvp[c * 4 + 1] = r.y; wvp[c * 4 + 2] = r.z; wvp[c * 4 + 3] = r.w;
+  }
+  uint32_t bits     = ~0u;
+  bool     allValid = true;
+  F4       cmin{}, cmax{};
+  const float c_epsilon = 1.2e-07f;
+  for(int n = 0; n < 8; n++)
+  {
+    F4    corner = {(n & 1) ? inst.geoHi[0] : inst.geoLo[0], (n & 2) ? inst.geoHi[1] : inst.geoLo[1], (n & 4) ? inst.geoHi[2] : inst.geoLo[2], 1.0f};
+    F4    h      = xmat4_mul(wvp, corner);
+    bool  valid  = !(-c_epsilon < h.w && h.w < c_epsilon);
+    float aw     = fabsf(h.w);
+    F4    clip   = {xdiv(h.x, aw), xdiv(h.y, aw), xdiv(h.z, aw), h.w};
+    bits &= cull_bits(h);
+    if(n == 0)
+    {
+      cmin = clip;
+      cmax = clip;
+    }
+    else
+    {
+      cmin = {fminf(cmin.x, clip.x), fminf(cmin.y, clip.y), fminf(cmin.z, clip.z), fminf(cmin.w, clip.w)};
+      cmax = {fmaxf(cmax.x, clip.x), fmaxf(cmax.y, clip.y), fmaxf(cmax.z, clip.z), fmaxf(cmax.w, clip.w)};
+    }
+    allValid = allValid && valid;
+  }
+  cmin.x = fminf(fmaxf(cmin.x, -1.0f), 1.0f); cmin.y = fminf(fmaxf(cmin.y, -1.0f), 1.0f);
+  cmax.x = fminf(fmaxf(cmax.x, -1.0f), 1.0f); cmax.y = fminf(fmaxf(cmax.y, -1.0f), 1.0f);
+  bool inFrustum = bits == 0;
+  bool isVisible = false;
+  if(inFrustum)
+  {
+    if(!allValid)
+      isVisible = true;
+    else
+    {
+      // intersectSize (culling.glsl:30-35)
+      float rx = xsub(cmax.x, cmin.x), ry = xsub(cmax.y, cmin.y);
+      bool  sizeOk = rx > xdiv(2.0f, viewLast.viewportf[0]) || ry > xdiv(2.0f, viewLast.viewportf[1]);
+      bool  hizOk  = true;
+      if(sizeOk && p.hizSize != 0)
+      {  // intersectHiz (culling.glsl:94-113)
+        const float* f = viewLast.hizSizeFactors;
+        float minx = xadd(xmul(cmin.x, 0.5f), 0.5f), miny = xadd(xmul(cmin.y, 0.5f), 0.5f);
+        float maxx = xadd(xmul(cmax.x, 0.5f), 0.5f), maxy = xadd(xmul(cmax.y, 0.5f), 0.5f);
+        minx = fminf(xmul(minx, f[0]), f[2]); miny = fminf(xmul(miny, f[1]), f[3]);
+        maxx = fminf(xmul(maxx, f[0]), f[2]); maxy = fminf(xmul(maxy, f[1]), f[3]);
+        float sx = xsub(maxx, minx), sy = xsub(maxy, miny);
+        float maxsize  = xmul(fmaxf(sx, sy), viewLast.hizSizeMax);
+        float miplevel = maxsize > 0.0f ? float(ceil_log2_exact(maxsize)) : 0.0f;
+        float depth    = sample_hiz_max(p, xmul(xadd(minx, maxx), 0.5f), xmul(xadd(miny, maxy), 0.5f), miplevel);
+        hizOk          = cmin.z <= xadd(depth, 2.0f / float(1 << 24));
+      }
+      isVisible = sizeOk && hizOk;
+    }
+  }
+  tc_BlasBuildInfo* blas = reinterpret_cast<tc_BlasBuildInfo*>(p.build->blasBuildInfos);
+  reinterpret_cast<uint32_t*>(p.build->instanceStates)[i] = (inFrustum ? TC_INSTANCE_FRUSTUM_BIT : 0) | (isVisible ? TC_INSTANCE_VISIBLE_BIT : 0);
+  blas[i].clusterReferencesCount = 0;
+}
+
+// ============================================================================================================
+// clusters_cull (ray-tracing build: every cluster is appended) + BUILD_SETUP_CLASSIFY
+// ============================================================================================================
+
+__global__ void k_clusters_cull(Params p)  // clusters_cull.comp.glsl:112-161, build_setup.comp.glsl:105-119
+{
+  uint32_t j     = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t total = p.totalClusters;
+  uint32_t count = min(total, p.maxVisibleClusters);
+  if(j == 0)
+  {
+    p.readback->numVisibleClusters   = total;
+    p.build->visibleClusterCounter   = count;
+    p.build->dispatchClassify.gridX  = count;
+    p.build->dispatchClassify.gridY  = 1;
+    p.build->dispatchClassify.gridZ  = 1;
+  }
+  if(j >= count)
+    return;
+  // instance = last i with prefix[i] <= j
+  uint32_t lo = 0, hi = p.numInstances;
+  while(hi - lo > 1)
+  {
+    uint32_t mid = (lo + hi) >> 1;
+    if(__ldg(&p.instanceClusterPrefix[mid]) <= j)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  tc_ClusterInfo* vis = reinterpret_cast<tc_ClusterInfo*>(p.build->visibleClusters);
+  vis[j]              = tc_ClusterInfo{lo, j - __ldg(&p.instanceClusterPrefix[lo])};
+}
+
+// ============================================================================================================
+// shared device pieces: dual counter (build.glsl), per-vertex generation
+// ============================================================================================================
+
+// build_atomicAdd_partTriangleCounter (build.glsl:68-83) evaluated on known (lo, hi) prefix values
+__device__ __forceinline__ uint32_t dual_front_offset(const Params& p, uint32_t lo, uint32_t hi, uint32_t n)
+{
+  if(!flag_transient(p))
+    return lo;
+  return (lo + hi + n + 1 > p.maxPartTriangles) ? p.maxPartTriangles : lo;
+}
+// build_atomicAdd_partTriangleCounterTransient (build.glsl:54-65)
+__device__ __forceinline__ uint32_t dual_back_offset(const Params& p, uint32_t lo, uint32_t hi, uint32_t n)
+{
+  return (lo + hi + n + 1 > p.maxPartTriangles) ? p.maxPartTriangles : (p.maxPartTriangles - hi - n);
+}
+
+__device__ __forceinline__ DisplacementConsts displacement_consts(const Params& p, const tc_RenderInstance& inst)
+{
+  DisplacementConsts d;
+  d.texture = (p.numTextures > 0 && inst.displacementIndex >= 0) ? inst.displacementIndex : -1;
+  d.scale   = inst.displacementScale * p.view[0].displacementScale;
+  d.offset  = inst.displacementOffset + p.view[0].displacementOffset;
+  return d;
+}
+
+// loads the base triangle of (instance, cluster, local indices) and prepares the per-part constants
+__device__ __forceinline__ void setup_base_triangle(const Params& p, const tc_RenderInstance& inst, uint32_t firstLocalVertex, uint32_t i0, uint32_t i1,
+                                                    uint32_t i2, const uint32_t vtxEncoded[3], BaseTriangle& b)
+{
+  const float* positions = reinterpret_cast<const float*>(inst.positions);
+  const float* normals   = reinterpret_cast<const float*>(inst.normals);
+  const float* texcoords = reinterpret_cast<const float*>(inst.texcoords);
+  uint32_t     gi[3]     = {firstLocalVertex + i0, firstLocalVertex + i1, firstLocalVertex + i2};
+  F3           pos[3];
+#pragma unroll
+  for(int v = 0; v < 3; v++)
+  {
+    b.bu[v]  = float(vtxEncoded[v] & 0xFFFF) * (1.0f / 32768.0f);
+    b.bv[v]  = float(vtxEncoded[v] >> 16) * (1.0f / 32768.0f);
+    pos[v]   = ld_f3(positions, gi[v]);
+    b.nrm[v] = normalize3(ld_f3(normals, gi[v]));
+    b.tu[v]  = __ldg(texcoords + size_t(gi[v]) * 2);
+    b.tv[v]  = __ldg(texcoords + size_t(gi[v]) * 2 + 1);
+  }
+  if(flag_pn(p))
+    setup_pn(b, pos, b.nrm);
+  else
+  {
+    b.pos[0] = pos[0]; b.pos[1] = pos[1]; b.pos[2] = pos[2];
+  }
+}
+
+// one generated vertex (instantiate.comp.glsl:343-371 / cluster_classify.comp.glsl:843-871)
+__device__ __forceinline__ F3 generate_vertex(const Params& p, const BaseTriangle& b, const DisplacementConsts& dc, uint32_t packedVertex, bool flipped,
+                                              uint32_t instanceID, float geoSize)
+{
+  float q1 = float(packedVertex & 0xFFFF) * (1.0f / 32768.0f);
+  float q2 = float(packedVertex >> 16) * (1.0f / 32768.0f);
+  float q0 = 1.0f - q1 - q2;
+  if(flipped)
+  {
+    float t = q0;
+    q0 = q1;
+    q1 = t;
+  }
+  // rebase into the sub-triangle: r = sum_k corner_k * q_k, corner_k = (1-bu-bv, bu, bv)
+  float r1 = fmaf(b.bu[2], q2, fmaf(b.bu[1], q1, b.bu[0] * q0));
+  float r2 = fmaf(b.bv[2], q2, fmaf(b.bv[1], q1, b.bv[0] * q0));
+  float r0 = fmaf(1.0f - b.bu[2] - b.bv[2], q2, fmaf(1.0f - b.bu[1] - b.bv[1], q1, (1.0f - b.bu[0] - b.bv[0]) * q0));
+  F3 pos;
+  if(flag_pn(p))
+    pos = eval_pn(b, r0, r1, r2);
+  else
+    pos = fma3(b.pos[2], r2, fma3(b.pos[1], r1, b.pos[0] * r0));
+  if(dc.texture >= 0)
+  {
+    F3    n  = fma3(b.nrm[2], r2, fma3(b.nrm[1], r1, b.nrm[0] * r0));
+    float tu = fmaf(b.tu[2], r2, fmaf(b.tu[1], r1, b.tu[0] * r0));
+    float tv = fmaf(b.tv[2], r2, fmaf(b.tv[1], r1, b.tv[0] * r0));
+    float h  = fmaf(sample_displacement(p.textures[dc.texture], tu, tv), dc.scale, dc.offset);
+    float s  = h * rsqrtf(dot3(n, n));
+    pos      = fma3(n, s, pos);
+  }
+  if(flag_animation(p))
+    pos = ripple_deform(p.view[0], pos, instanceID, geoSize);
+  return pos;
+}
+
+// ============================================================================================================
+// cluster_classify
+// ============================================================================================================
+
+constexpr int CLASSIFY_WARPS   = 8;
+constexpr int CLASSIFY_THREADS = CLASSIFY_WARPS * 32;
+
+// tuple lanes
+enum { T_SPLIT = 0, T_LO = 1, T_HI = 2, T_TEMP = 3, T_TRANS = 4, T_VERT = 5 };
+
+struct ClassifyShared
+{
+  ScanTuple warpTuple[CLASSIFY_WARPS];
+  ScanTuple warpPrefix[CLASSIFY_WARPS];
+  uint32_t  tile;
+  uint32_t  succTemp, succTrans, totalTris, fullClusters, validParts;
+};
+
+__global__ void __launch_bounds__(CLASSIFY_THREADS) k_cluster_classify(Params p, const uint32_t* epochCounter)
+{
+  extern __shared__ __align__(16) uint8_t smemRaw[];
+  __shared__ ClassifyShared sh;
+
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t maxV = p.clusterVertices, maxT = p.clusterTriangles;
+  // per-warp regions: object positions [maxV*3], world positions + eye distance [maxV*4], factors [maxT*3]
+  const uint32_t warpWords = maxV * 3 + maxV * 4 + maxT * 3;
+  float*    sObj     = reinterpret_cast<float*>(smemRaw) + size_t(warp) * warpWords;
+  float*    sWorld   = sObj + maxV * 3;
+  uint32_t* sFactors = reinterpret_cast<uint32_t*>(sWorld + maxV * 4);
+
+  const uint32_t epoch      = *epochCounter + SLOT_CLASSIFY;
+  const uint32_t numVisible = p.build->visibleClusterCounter;
+  const uint32_t numTiles   = (numVisible + CLASSIFY_WARPS - 1) / CLASSIFY_WARPS;
+  LookbackDesc*  descs      = reinterpret_cast<LookbackDesc*>(p.lookback);
+  const FactorConsts fcst   = load_factor_consts(p);
+  const bool use1X = flag_1x(p), use2X = flag_2x(p);
+  const uint32_t basic32 = use2X ? __ldg(&p.basicClusterSizes[TC_TESS_2X_MINI_BATCHSIZE * TC_TESS_2X_MINI_TRIANGLES]) : 0;
+  const uint32_t miniVertexSize = TC_TESS_2X_MINI_BATCHSIZE * TC_TESS_2X_MINI_VERTICES + (TC_TESS_2X_MINI_BATCHSIZE * TC_TESS_2X_MINI_TRIANGLES * 3 + 11) / 12;  // 56
+  const uint32_t miniPartSize   = (8 + TC_TESS_2X_MINI_BATCHSIZE * TC_TESS_2X_MINI_TRIANGLES * 2 + 24 - 1) / 24;                                              // 3
+
+  tc_ClusterInfo*             visibleClusters = reinterpret_cast<tc_ClusterInfo*>(p.build->visibleClusters);
+  tc_TessTriangleInfo*        splitTriangles  = reinterpret_cast<tc_TessTriangleInfo*>(p.build->splitTriangles);
+  tc_TessTriangleInfo*        partTriangles   = reinterpret_cast<tc_TessTriangleInfo*>(p.build->partTriangles);
+  float*                      genVertices     = reinterpret_cast<float*>(p.build->genVertices);
+  uint8_t*                    transTriIndices = reinterpret_cast<uint8_t*>(p.build->genVertices);
+  uint8_t*                    transTriMappings = reinterpret_cast<uint8_t*>(p.build->partTriangles);
+  tc_TemplateInstantiateInfo* tempInstantiations = reinterpret_cast<tc_TemplateInstantiateInfo*>(p.build->tempInstantiations);
+  uint32_t*                   tempInstanceIDs = reinterpret_cast<uint32_t*>(p.build->tempInstanceIDs);
+  unsigned long long*         tempClusterAddresses = reinterpret_cast<unsigned long long*>(p.build->tempClusterAddresses);
+  uint32_t*                   tempClusterSizes = reinterpret_cast<uint32_t*>(p.build->tempClusterSizes);
+  tc_ClasBuildInfo*           transBuilds = reinterpret_cast<tc_ClasBuildInfo*>(p.build->transBuilds);
+  uint32_t*                   transInstanceIDs = reinterpret_cast<uint32_t*>(p.build->transInstanceIDs);
+  unsigned long long*         transClusterAddresses = reinterpret_cast<unsigned long long*>(p.build->transClusterAddresses);
+  uint32_t*                   transClusterSizes = reinterpret_cast<uint32_t*>(p.build->transClusterSizes);
+  const uint32_t*             instanceStates = reinterpret_cast<const uint32_t*>(p.build->instanceStates);
+  const unsigned long long    genVerticesAddr = p.build->genVertices, genClusterData = p.build->genClusterData;
+  const uint32_t              truncBits = p.build->positionTruncateBitCount;
+
+  if(threadIdx.x == 0)
+  {
+    sh.succTemp = sh.succTrans = sh.totalTris = sh.fullClusters = sh.validParts = 0;
+  }
+
+  while(true)
+  {
+    __syncthreads();
+    if(threadIdx.x == 0)
+      sh.tile = atomicAdd(&p.state->ticket[SLOT_CLASSIFY], 1u);
+    __syncthreads();
+    const uint32_t tile = sh.tile;
+    if(tile >= numTiles)
+      break;
+
+    const uint32_t vi    = tile * CLASSIFY_WARPS + warp;
+    const bool     valid = vi < numVisible;
+
+    // ---------------- phase 1: load, factors, counts (:154-258) ----------------
+    tc_ClusterInfo cinfo{0, 0};
+    uint32_t       numVertices = 0, numTriangles = 0, firstLocalVertex = 0, firstLocalTriangle = 0;
+    const tc_RenderInstance* inst = nullptr;
+    uint32_t       simpleCount = 0;
+    ScanTuple      tup;
+    tup.zero();
+    bool     clusterLevel = false, isFull = false;
+    uint32_t clasDataSize = 0, vertexSize = 0, partSize = 0;
+
+    if(valid)
+    {
+      cinfo = visibleClusters[vi];
+      inst  = &p.instances[cinfo.instanceID];
+      const uint4 ch = __ldg(reinterpret_cast<const uint4*>(inst->clusters) + cinfo.clusterID);
+      numVertices        = ch.x & 0xFFFF;
+      numTriangles       = ch.x >> 16;
+      firstLocalVertex   = ch.z;
+      firstLocalTriangle = ch.w;
+      const float* positions = reinterpret_cast<const float*>(inst->positions);
+      float m[16];
+#pragma unroll
+      for(int k = 0; k < 16; k++)
+        m[k] = inst->worldMatrix[k];
+      for(uint32_t v = lane; v < numVertices; v += 32)
+      {
+        F3 o = ld_f3(positions, firstLocalVertex + v);
+        sObj[v * 3 + 0] = o.x; sObj[v * 3 + 1] = o.y; sObj[v * 3 + 2] = o.z;
+        F3 w = xtransform_point(m, o);
+        float d = xdistance3(w, fcst.eye);
+        reinterpret_cast<float4*>(sWorld)[v] = make_float4(w.x, w.y, w.z, d);
+      }
+      __syncwarp();
+
+      const bool hidden = flag_culling(p) && (instanceStates[cinfo.instanceID] & TC_INSTANCE_VISIBLE_BIT) == 0;
+      if(hidden)
+        simpleCount = numTriangles;
+      else
+      {
+        const uint8_t* localTriangles = reinterpret_cast<const uint8_t*>(inst->clusterLocalTriangles) + firstLocalTriangle;
+        for(uint32_t base = 0; base < numTriangles; base += 32)
+        {
+          uint32_t tri = base + lane;
+          bool     tv  = tri < numTriangles;
+          uint32_t f[3] = {1, 1, 1};
+          if(tv)
+          {
+            uint32_t i0 = __ldg(localTriangles + tri * 3 + 0), i1 = __ldg(localTriangles + tri * 3 + 1), i2 = __ldg(localTriangles + tri * 3 + 2);
+            float4   a = reinterpret_cast<const float4*>(sWorld)[i0], b = reinterpret_cast<const float4*>(sWorld)[i1], c = reinterpret_cast<const float4*>(sWorld)[i2];
+            tess_factors(fcst, F3{a.x, a.y, a.z}, F3{b.x, b.y, b.z}, F3{c.x, c.y, c.z}, a.w, b.w, c.w, f);
+            sFactors[tri * 3 + 0] = f[0] | (i0 << 24);
+            sFactors[tri * 3 + 1] = f[1] | (i1 << 24);
+            sFactors[tri * 3 + 2] = f[2] | (i2 << 24);
+          }
+          uint32_t mx = max(max(f[0], f[1]), f[2]);
+          simpleCount += __popc(__ballot_sync(0xffffffffu, tv && mx == 1));
+        }
+      }
+      __syncwarp();
+
+      // ---- counts in canonical order ----
+      clusterLevel = use1X ? (simpleCount == numTriangles || simpleCount > 1) : (simpleCount == numTriangles);
+      isFull       = simpleCount == numTriangles;
+      if(clusterLevel)
+      {
+        vertexSize = numVertices;
+        if(!use1X || isFull)
+        {
+          clasDataSize = __ldg(reinterpret_cast<const uint32_t*>(inst->clusterTemplateInstantiatonSizes) + cinfo.clusterID);
+          tup.v[T_TEMP] += 1;
+        }
+        else
+        {
+          clasDataSize = __ldg(&p.basicClusterSizes[simpleCount]);
+          vertexSize += (simpleCount * 3 + 11) / 12;
+          partSize = (8 + simpleCount + 24 - 1) / 24;
+          tup.v[T_TRANS] += 1;
+          tup.v[T_HI] += partSize;
+        }
+        tup.v[T_VERT] += vertexSize;
+        tup.d += clasDataSize;
+      }
+      if(simpleCount != numTriangles)
+      {
+        for(uint32_t base = 0; base < numTriangles; base += 32)
+        {
+          uint32_t tri = base + lane;
+          bool     tv  = tri < numTriangles;
+          uint32_t mx  = 0;
+          if(tv)
+            mx = max(max(sFactors[tri * 3] & 0xFFFFFF, sFactors[tri * 3 + 1] & 0xFFFFFF), sFactors[tri * 3 + 2] & 0xFFFFFF);
+          bool noTess = mx == 1, mini = mx <= 2, split = mx > TC_TESSTABLE_SIZE, part = mx <= TC_TESSTABLE_SIZE;
+          if(use1X && simpleCount > 1 && noTess)
+          {
+            part = false;
+            mini = false;
+          }
+          if(use2X)
+            part = part && !mini;
+          if(!tv)
+            mini = split = part = false;
+          uint32_t nSplit = __popc(__ballot_sync(0xffffffffu, split));
+          uint32_t nPart  = __popc(__ballot_sync(0xffffffffu, part));
+          uint32_t nMini  = use2X ? __popc(__ballot_sync(0xffffffffu, mini)) : 0;
+          uint32_t batches = (nMini + TC_TESS_2X_MINI_BATCHSIZE - 1) / TC_TESS_2X_MINI_BATCHSIZE;
+          tup.v[T_SPLIT] += nSplit;
+          tup.v[T_LO] += nPart;
+          tup.v[T_TRANS] += batches;
+          tup.v[T_HI] += batches * miniPartSize;
+          tup.v[T_VERT] += batches * miniVertexSize;
+          tup.d += (unsigned long long)batches * basic32;
+        }
+      }
+    }
+    if(lane == 0)
+      sh.warpTuple[warp] = tup;
+    __syncthreads();
+
+    // ---------------- tile scan + look-back ----------------
+    if(warp == 0)
+    {
+      ScanTuple total;
+      total.zero();
+      if(lane == 0)
+      {
+        for(int w = 0; w < CLASSIFY_WARPS; w++)
+        {
+          sh.warpPrefix[w] = total;
+          total.add(sh.warpTuple[w]);
+        }
+      }
+#pragma unroll
+      for(int i = 0; i < 6; i++)
+        total.v[i] = __shfl_sync(0xffffffffu, total.v[i], 0);
+      total.d = __shfl_sync(0xffffffffu, total.d, 0);
+      ScanTuple excl = lookback_exclusive(descs, tile, total, epoch);
+      if(lane == 0)
+      {
+        for(int w = 0; w < CLASSIFY_WARPS; w++)
+          sh.warpPrefix[w].add(excl);
+        if(tile == numTiles - 1)
+        {  // grand totals for the setup step
+          excl.add(total);
+          st_tuple(reinterpret_cast<ScanTuple*>(&descs[numTiles].aggregate), excl);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2..4: emit in canonical order ----------------
+    if(valid)
+    {
+      ScanTuple run = sh.warpPrefix[warp];
+      uint32_t  succTemp = 0, succTrans = 0, totalTris = 0, validParts = 0;
+      const uint32_t instanceID = cinfo.instanceID, clusterID = cinfo.clusterID;
+      const DisplacementConsts dc = displacement_consts(p, *inst);
+      const float geoSize = inst->geoHi[3];
+
+      if(clusterLevel)
+      {  // :271-538
+        uint32_t genOffset  = run.v[T_TEMP] + run.v[T_TRANS];
+        uint32_t partOffset = 0;
+        const bool transient1X = use1X && !isFull;
+        if(transient1X)
+        {
+          partOffset = dual_back_offset(p, run.v[T_LO], run.v[T_HI], partSize);
+          run.v[T_HI] += partSize;
+        }
+        unsigned long long dataOffset = run.d;
+        run.d += clasDataSize;
+        uint32_t vertexOffset = run.v[T_VERT];
+        run.v[T_VERT] += vertexSize;
+        bool fail = (vertexOffset + vertexSize > p.maxGenVertices) || (genOffset + 1 > p.maxGenClusters) || (dataOffset + clasDataSize > p.maxGenDataBytes)
+                    || (use1X && (partOffset + partSize > p.maxPartTriangles));
+        if(!fail)
+        {
+          const unsigned long long vertexBuffer = genVerticesAddr + (unsigned long long)(uint32_t)(vertexOffset * 4u * 3u);
+          if(!transient1X)
+          {
+            uint32_t tempOffset = run.v[T_TEMP];
+            if(lane == 0)
+            {
+              tc_TemplateInstantiateInfo ti;
+              ti.clusterIdOffset        = 0;
+              ti.geometryIndexOffset    = 0;
+              ti.clusterTemplateAddress = __ldg(reinterpret_cast<const unsigned long long*>(inst->clusterTemplateAdresses) + clusterID);
+              ti.vertexBufferAddress    = vertexBuffer;
+              ti.vertexBufferStride     = 12;
+              tempInstantiations[tempOffset]   = ti;
+              tempInstanceIDs[tempOffset]      = instanceID;
+              tempClusterAddresses[tempOffset] = genClusterData + dataOffset;
+              if(p.driverStandin)
+                tempClusterSizes[tempOffset] = clasDataSize;
+            }
+            succTemp++;
+          }
+          else
+          {
+            uint32_t transOffset = run.v[T_TRANS];
+            if(lane == 0)
+            {
+              tc_ClasBuildInfo bi;
+              bi.clusterID    = (TC_RT_CLUSTER_MODE_1X_SUBSET_CLUSTER << 30) | partOffset;
+              bi.clusterFlags = 0;
+              bi.packed       = simpleCount | (numVertices << 9) | (truncBits << 18) | (1u << 24);
+              bi.baseGeometryIndexAndFlags = TC_CLAS_GEOMETRY_FLAG_OPAQUE;
+              bi.indexBufferStride  = 1;
+              bi.vertexBufferStride = 12;
+              bi.geometryIndexAndFlagsBufferStride = 0;
+              bi.opacityMicromapIndexBufferStride  = 0;
+              bi.vertexBuffer = vertexBuffer;
+              bi.indexBuffer  = vertexBuffer + (unsigned long long)(uint32_t)(numVertices * 4u * 3u);
+              bi.geometryIndexAndFlagsBuffer = 0;
+              bi.opacityMicromapArray        = 0;
+              bi.opacityMicromapIndexBuffer  = 0;
+              transBuilds[transOffset]           = bi;
+              transInstanceIDs[transOffset]      = instanceID;
+              transClusterAddresses[transOffset] = genClusterData + dataOffset;
+              if(p.driverStandin)
+                transClusterSizes[transOffset] = clasDataSize;
+              partTriangles[partOffset].cluster = cinfo;
+            }
+            succTrans++;
+          }
+          totalTris += simpleCount;
+
+          // displaced copy of the cluster vertices (:465-488)
+          const float* normals   = reinterpret_cast<const float*>(inst->normals);
+          const float* texcoords = reinterpret_cast<const float*>(inst->texcoords);
+          for(uint32_t v = lane; v < numVertices; v += 32)
+          {
+            F3 o = {sObj[v * 3 + 0], sObj[v * 3 + 1], sObj[v * 3 + 2]};
+            if(dc.texture >= 0)
+            {
+              uint32_t vertexIndex = firstLocalVertex + v;
+              F3       n  = ld_f3(normals, vertexIndex);
+              float    tu = __ldg(texcoords + size_t(vertexIndex) * 2), tv = __ldg(texcoords + size_t(vertexIndex) * 2 + 1);
+              float    h  = fmaf(sample_displacement(p.textures[dc.texture], tu, tv), dc.scale, dc.offset);
+              o           = fma3(n, h * rsqrtf(dot3(n, n)), o);
+            }
+            if(flag_animation(p))
+              o = ripple_deform(p.view[0], o, instanceID, geoSize);
+            float* dst = genVertices + size_t(vertexOffset + v) * 3;
+            dst[0] = o.x; dst[1] = o.y; dst[2] = o.z;
+          }
+          if(transient1X)
+          {  // ordered export of the simple triangles (:497-534)
+            uint32_t indexOffset      = (vertexOffset + numVertices) * 4u * 3u;
+            uint32_t triMappingOffset = partOffset * 24u + 8u;
+            uint32_t outOffset        = 0;
+            for(uint32_t base = 0; base < numTriangles; base += 32)
+            {
+              uint32_t tri = base + lane;
+              bool     tv  = tri < numTriangles;
+              uint32_t f0 = 0, f1 = 0, f2 = 0;
+              if(tv)
+              {
+                f0 = sFactors[tri * 3]; f1 = sFactors[tri * 3 + 1]; f2 = sFactors[tri * 3 + 2];
+              }
+              bool     isSimple = tv && max(max(f0 & 0xFFFFFF, f1 & 0xFFFFFF), f2 & 0xFFFFFF) == 1;
+              uint32_t vote     = __ballot_sync(0xffffffffu, isSimple);
+              uint32_t triOffset = outOffset + __popc(vote & lanemask_lt());
+              if(isSimple)
+              {
+                transTriMappings[size_t(triMappingOffset) + triOffset] = uint8_t(tri);
+                transTriIndices[size_t(indexOffset) + triOffset * 3 + 0] = uint8_t(f0 >> 24);
+                transTriIndices[size_t(indexOffset) + triOffset * 3 + 1] = uint8_t(f1 >> 24);
+                transTriIndices[size_t(indexOffset) + triOffset * 3 + 2] = uint8_t(f2 >> 24);
+              }
+              outOffset += __popc(vote);
+            }
+          }
+        }
+        if(!transient1X)
+          run.v[T_TEMP] += 1;
+        else
+          run.v[T_TRANS] += 1;
+      }
+
+      if(simpleCount != numTriangles)
+      {  // :543-905
+        for(uint32_t base = 0; base < numTriangles; base += 32)
+        {
+          uint32_t tri = base + lane;
+          bool     tv  = tri < numTriangles;
+          uint32_t f0 = 0, f1 = 0, f2 = 0, i0 = 0, i1 = 0, i2 = 0;
+          if(tv)
+          {
+            f0 = sFactors[tri * 3]; f1 = sFactors[tri * 3 + 1]; f2 = sFactors[tri * 3 + 2];
+            i0 = f0 >> 24; i1 = f1 >> 24; i2 = f2 >> 24;
+            f0 &= 0xFFFFFF; f1 &= 0xFFFFFF; f2 &= 0xFFFFFF;
+          }
+          uint32_t mx = max(max(f0, f1), f2);
+          bool noTess = mx == 1, mini = mx <= 2, split = mx > TC_TESSTABLE_SIZE, part = mx <= TC_TESSTABLE_SIZE;
+          if(use1X && simpleCount > 1 && noTess)
+          {
+            part = false;
+            mini = false;
+          }
+          if(use2X)
+            part = part && !mini;
+          if(!tv)
+            mini = split = part = false;
+          if(!use2X)
+            mini = false;
+
+          uint32_t voteSplit = __ballot_sync(0xffffffffu, split), votePart = __ballot_sync(0xffffffffu, part);
+          uint32_t nSplit = __popc(voteSplit), nPart = __popc(votePart);
+          uint32_t offsetSplit = run.v[T_SPLIT] + __popc(voteSplit & lanemask_lt());
+          uint32_t offsetPart  = dual_front_offset(p, run.v[T_LO], run.v[T_HI], nPart) + __popc(votePart & lanemask_lt());
+          run.v[T_SPLIT] += nSplit;
+          run.v[T_LO] += nPart;
+
+          uint32_t v0 = 0u, v1 = TC_TESSTABLE_COORD_MAX, v2 = TC_TESSTABLE_COORD_MAX << 16;
+          uint32_t cfg = 0;
+          if(split && offsetSplit < p.maxSplitTriangles)
+          {
+            cfg = tess_getConfig(tess_splitFactor(f0, p.splitFactor), tess_splitFactor(f1, p.splitFactor), tess_splitFactor(f2, p.splitFactor), v0, v1, v2);
+            uint2* dst = reinterpret_cast<uint2*>(&splitTriangles[offsetSplit]);
+            dst[0] = make_uint2(instanceID, clusterID);
+            dst[1] = make_uint2(v0, v1);
+            dst[2] = make_uint2(v2, tri | (cfg << 16));
+          }
+          else if(part && offsetPart < p.maxPartTriangles)
+          {
+            cfg = tess_getConfig(f0, f1, f2, v0, v1, v2);
+            uint2* dst = reinterpret_cast<uint2*>(&partTriangles[offsetPart]);
+            dst[0] = make_uint2(instanceID, clusterID);
+            dst[1] = make_uint2(v0, v1);
+            dst[2] = make_uint2(v2, tri | (cfg << 16));
+            validParts = max(validParts, offsetPart + 1);
+          }
+          else if(mini)
+            cfg = tess_getConfig(f0, f1, f2, v0, v1, v2);
+
+          uint32_t voteMini = __ballot_sync(0xffffffffu, mini);
+          if(voteMini == 0)
+            continue;
+
+          // ---- 2X mini batches (:667-905) ----
+          const uint32_t miniBatch = TC_TESS_2X_MINI_BATCHSIZE, miniVertices = TC_TESS_2X_MINI_VERTICES;
+          const uint32_t miniBatchVertices = miniBatch * miniVertices;
+          uint32_t offsetMini = __popc(voteMini & lanemask_lt());
+          uint32_t relMini    = offsetMini & (miniBatch - 1);
+          uint32_t batchIdx   = offsetMini / miniBatch;
+          uint32_t nMini      = __popc(voteMini);
+          uint32_t batches    = (nMini + miniBatch - 1) / miniBatch;
+          tc_TessTableEntry entry{0, 0, 0, 0};
+          if(mini)
+            entry = tess_entry(p, cfg);
+          uint32_t numTris          = mini ? entry.numTriangles : 0;
+          uint32_t numTrisInclusive = warp_inclusive_add(numTris);
+          // first lane of my batch = the mini lane whose offsetMini == batchIdx*8
+          uint32_t miniRankTarget = batchIdx * miniBatch;
+          // lane index of the n-th set bit in voteMini
+          uint32_t startLane = __fns(voteMini, 0, miniRankTarget + 1);
+          uint32_t lastRank  = min(miniRankTarget + miniBatch, nMini) - 1;
+          uint32_t lastLane  = __fns(voteMini, 0, lastRank + 1);
+          if(!mini)
+          {
+            startLane = 0;
+            lastLane  = 0;
+          }
+          uint32_t firstTris     = __shfl_sync(0xffffffffu, numTrisInclusive - numTris, startLane);
+          uint32_t lastBatchTris = __shfl_sync(0xffffffffu, numTrisInclusive, lastLane);
+          uint32_t numBatchTris  = lastBatchTris - firstTris;
+
+          // batch b allocates constant sizes, so offsets are closed-form in b
+          uint32_t transGenOffset  = run.v[T_TEMP] + run.v[T_TRANS] + batchIdx;
+          uint32_t hiBefore        = run.v[T_HI] + batchIdx * miniPartSize;
+          uint32_t transPartOffset = dual_back_offset(p, run.v[T_LO], hiBefore, miniPartSize);
+          unsigned long long transDataOffset = run.d + (unsigned long long)batchIdx * basic32;
+          uint32_t transVertexOffset = run.v[T_VERT] + batchIdx * miniVertexSize;
+          bool     failB = (transVertexOffset + miniVertexSize > p.maxGenVertices) || (transGenOffset + 1 > p.maxGenClusters)
+                       || (transDataOffset + basic32 > p.maxGenDataBytes) || (transPartOffset + miniPartSize > p.maxPartTriangles);
+          uint32_t transOffset = run.v[T_TRANS] + batchIdx;
+
+          if(mini && !failB)
+          {
+            const unsigned long long vertexBuffer = genVerticesAddr + (unsigned long long)(uint32_t)(transVertexOffset * 4u * 3u);
+            if(relMini == 0)
+            {
+              tc_ClasBuildInfo bi;
+              bi.clusterID    = (TC_RT_CLUSTER_MODE_2X_BATCHED_TESSELLATED << 30) | transPartOffset;
+              bi.clusterFlags = 0;
+              bi.packed       = numBatchTris | (miniBatchVertices << 9) | (truncBits << 18) | (1u << 24);
+              bi.baseGeometryIndexAndFlags = TC_CLAS_GEOMETRY_FLAG_OPAQUE;
+              bi.indexBufferStride  = 1;
+              bi.vertexBufferStride = 12;
+              bi.geometryIndexAndFlagsBufferStride = 0;
+              bi.opacityMicromapIndexBufferStride  = 0;
+              bi.vertexBuffer = vertexBuffer;
+              bi.indexBuffer  = vertexBuffer + (unsigned long long)(uint32_t)(miniBatchVertices * 4u * 3u);
+              bi.geometryIndexAndFlagsBuffer = 0;
+              bi.opacityMicromapArray        = 0;
+              bi.opacityMicromapIndexBuffer  = 0;
+              transBuilds[transOffset]           = bi;
+              transInstanceIDs[transOffset]      = instanceID;
+              transClusterAddresses[transOffset] = genClusterData + transDataOffset;
+              if(p.driverStandin)
+                transClusterSizes[transOffset] = basic32;
+              partTriangles[transPartOffset].cluster = cinfo;
+            }
+            uint32_t baseTris      = numTrisInclusive - numTris - firstTris;
+            uint32_t packedFactors = (f0 - 1) | ((f1 - 1) << 1) | ((f2 - 1) << 2);  // un-rotated factors
+            uint32_t vtxEnc[3]     = {v0, v1, v2};
+            BaseTriangle bt;
+            setup_base_triangle(p, *inst, firstLocalVertex, i0, i1, i2, vtxEnc, bt);
+            const bool flipped = (cfg & TC_CONFIG_FLIPPED_BIT) != 0;
+            for(uint32_t vert = 0; vert < entry.numVertices; vert++)
+            {
+              F3 o = generate_vertex(p, bt, dc, __ldg(&p.tblVertices[entry.firstVertex + vert]), flipped, instanceID, geoSize);
+              float* dst = genVertices + size_t(vert + transVertexOffset + relMini * miniVertices) * 3;
+              dst[0] = o.x; dst[1] = o.y; dst[2] = o.z;
+            }
+            uint32_t  indexOffset      = (transVertexOffset + miniBatchVertices) * 4u * 3u;
+            uint32_t  triMappingOffset = transPartOffset * (24u / 2u) + (8u / 2u);
+            uint16_t* mappings         = reinterpret_cast<uint16_t*>(transTriMappings);
+            for(uint32_t i = 0; i < numTris; i++)
+            {
+              uint32_t triOffset = baseTris + i;
+              mappings[size_t(triMappingOffset) + triOffset] = uint16_t(tri | (i << 8) | (packedFactors << 12));
+              uint32_t packedTri = __ldg(&p.tblTriangles[entry.firstTriangle + i]);
+              uint32_t c0 = packedTri & 0xFF, c1 = (packedTri >> 8) & 0xFF, c2 = (packedTri >> 16) & 0xFF;
+              if(flipped)
+              {
+                uint32_t t = c1;
+                c1 = c2;
+                c2 = t;
+              }
+              transTriIndices[size_t(indexOffset) + triOffset * 3 + 0] = uint8_t(c0 + relMini * miniVertices);
+              transTriIndices[size_t(indexOffset) + triOffset * 3 + 1] = uint8_t(c1 + relMini * miniVertices);
+              transTriIndices[size_t(indexOffset) + triOffset * 3 + 2] = uint8_t(c2 + relMini * miniVertices);
+            }
+          }
+          // per-batch success bookkeeping (uniform per batch; count once per batch leader)
+          uint32_t leaderOk = __ballot_sync(0xffffffffu, mini && relMini == 0 && !failB);
+          succTrans += __popc(leaderOk);
+          uint32_t trisOk = (mini && relMini == 0 && !failB) ? numBatchTris : 0;
+          totalTris += warp_sum(trisOk);
+
+          run.v[T_TRANS] += batches;
+          run.v[T_HI] += batches * miniPartSize;
+          run.v[T_VERT] += batches * miniVertexSize;
+          run.d += (unsigned long long)batches * basic32;
+        }
+      }
+
+      validParts = max(validParts, __shfl_xor_sync(0xffffffffu, validParts, 16));
+      validParts = max(validParts, __shfl_xor_sync(0xffffffffu, validParts, 8));
+      validParts = max(validParts, __shfl_xor_sync(0xffffffffu, validParts, 4));
+      validParts = max(validParts, __shfl_xor_sync(0xffffffffu, validParts, 2));
+      validParts = max(validParts, __shfl_xor_sync(0xffffffffu, validParts, 1));
+      if(lane == 0)
+      {
+        if(succTemp) atomicAdd(&sh.succTemp, succTemp);
+        if(succTrans) atomicAdd(&sh.succTrans, succTrans);
+        if(totalTris) atomicAdd(&sh.totalTris, totalTris);
+        if(clusterLevel && isFull) atomicAdd(&sh.fullClusters, 1u);
+        if(validParts) atomicMax(&sh.validParts, validParts);
+      }
+    }
+  }
+
+  // ---------------- CTA epilogue: stats + last-CTA setup (BUILD_SETUP_SPLIT, build_setup.comp.glsl:150-167) ----
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    if(sh.succTemp) atomicAdd(&p.build->tempInstantiateCounter, sh.succTemp);
+    if(sh.succTrans) atomicAdd(&p.build->transBuildCounter, sh.succTrans);
+    if(sh.totalTris) atomicAdd(&p.readback->numTotalTriangles, sh.totalTris);
+    if(sh.fullClusters) atomicAdd(&p.readback->numFullClusters, sh.fullClusters);
+    if(sh.validParts) atomicMax(&p.state->validParts, sh.validParts);
+    __threadfence();
+    uint32_t done = atomicAdd(&p.state->done[SLOT_CLASSIFY], 1u);
+    if(done == gridDim.x - 1)
+    {
+      __threadfence();
+      ScanTuple tot;
+      tot.zero();
+      if(numTiles > 0)
+        tot = ld_tuple(reinterpret_cast<const ScanTuple*>(&descs[numTiles].aggregate));
+      tc_SceneBuilding* b = p.build;
+      b->genClusterCounter     = tot.v[T_TEMP] + tot.v[T_TRANS];
+      b->genClusterDataCounter = tot.d;
+      b->genVertexCounter      = tot.v[T_VERT];
+      uint32_t lo = tot.v[T_LO];
+      if(flag_transient(p))
+        b->dualPartTriangleCounter = (unsigned long long)lo | ((unsigned long long)tot.v[T_HI] << 32);
+      // BUILD_SETUP_SPLIT
+      uint32_t count          = min(tot.v[T_SPLIT], p.maxSplitTriangles);
+      b->splitWriteCounter    = count;
+      b->splitTriangleCounter = int32_t(count);
+      b->partTriangleCounter  = lo;
+      b->splitPassStart       = 0;
+      b->splitPassEnd         = count;
+      b->dispatchTriangleSplit.gridX = (count + 63) / 64;
+      b->dispatchTriangleSplit.gridY = 1;
+      b->dispatchTriangleSplit.gridZ = 1;
+      FrameState* s         = p.state;
+      s->tempAfterClassify  = *(volatile uint32_t*)&b->tempInstantiateCounter;
+      s->transAfterClassify = *(volatile uint32_t*)&b->transBuildCounter;
+      s->hiAfterClassify    = tot.v[T_HI];
+      s->partSegEnd[0]      = min(lo, *(volatile uint32_t*)&s->validParts);
+      s->numPartSegs        = 1;
+    }
+  }
+}
+
+// ============================================================================================================
+// triangle_split (multipass variant), one launch per pass
+// ============================================================================================================
+
+constexpr int SPLIT_WARPS        = 4;
+constexpr int SPLIT_THREADS      = SPLIT_WARPS * 32;
+constexpr int SPLIT_MAX_CHILDREN = 32 * 64;  // per warp: 32 items x <= 64 children (split factors <= 8)
+constexpr int SPLIT_MAX_RUNS     = SPLIT_MAX_CHILDREN / 32;
+
+struct SplitShared
+{
+  // per child: new cfg (bit 15 flip, low 12 bits lookup index) | rotation << 12 (0 none, 1 .yzx, 2 .zxy) | bit 14: split again
+  uint16_t stash[SPLIT_WARPS][SPLIT_MAX_CHILDREN];
+  uint32_t runSplitPref[SPLIT_WARPS][SPLIT_MAX_RUNS + 1], runPartPref[SPLIT_WARPS][SPLIT_MAX_RUNS + 1];
+  uint32_t warpSplit[SPLIT_WARPS], warpPart[SPLIT_WARPS];
+  uint32_t prefSplit[SPLIT_WARPS], prefPart[SPLIT_WARPS];
+  uint32_t tile;
+  uint32_t validParts;
+};
+
+// tess_getConfig that also reports which rotation it applied
+__device__ __forceinline__ uint32_t tess_getConfigRot(uint32_t fx, uint32_t fy, uint32_t fz, uint32_t& rot)
+{
+  uint32_t m = max(max(fx, fy), fz);
+  rot        = 0;
+  if(m == fy)
+  {
+    uint32_t t = fx;
+    fx = fy; fy = fz; fz = t;
+    rot = 1;
+  }
+  else if(m == fz)
+  {
+    uint32_t t = fz;
+    fz = fy; fy = fx; fx = t;
+    rot = 2;
+  }
+  uint32_t idx = fx + fy * 16u + fz * 256u - 273u;
+  if(fz > fy)
+    idx |= TC_CONFIG_FLIPPED_BIT;
+  return idx;
+}
+
+__device__ __forceinline__ F3 xinterp3(const F3 base[3], F3 w)
+{
+  F3 r;
+  r.x = xadd(xadd(xmul(base[0].x, w.x), xmul(base[1].x, w.y)), xmul(base[2].x, w.z));
+  r.y = xadd(xadd(xmul(base[0].y, w.x), xmul(base[1].y, w.y)), xmul(base[2].y, w.z));
+  r.z = xadd(xadd(xmul(base[0].z, w.x), xmul(base[1].z, w.y)), xmul(base[2].z, w.z));
+  return r;
+}
+
+// child corners of pattern triangle `sub` inside the parent sub-triangle (processSubTask :219-247), un-rotated
+__device__ __forceinline__ void split_child_corners(const Params& p, uint32_t cfg, uint32_t firstTriangle, uint32_t firstVertex, uint32_t sub,
+                                                    const uint32_t parentVtx[3], uint32_t out[3])
+{
+  F3 baseBary[3] = {tess_decodeBarycentrics(parentVtx[0]), tess_decodeBarycentrics(parentVtx[1]), tess_decodeBarycentrics(parentVtx[2])};
+  uint32_t packedTri = __ldg(&p.tblTriangles[firstTriangle + sub]);
+  uint32_t vi[3]     = {packedTri & 0xFF, (packedTri >> 8) & 0xFF, (packedTri >> 16) & 0xFF};
+  const bool flipped = (cfg & TC_CONFIG_FLIPPED_BIT) != 0;
+  if(flipped)
+  {
+    uint32_t t = vi[1];
+    vi[1] = vi[2];
+    vi[2] = t;
+  }
+#pragma unroll
+  for(int v = 0; v < 3; v++)
+  {
+    F3 q = tess_decodeBarycentrics(__ldg(&p.tblVertices[firstVertex + vi[v]]));
+    if(flipped)
+    {
+      float t = q.x;
+      q.x = q.y;
+      q.y = t;
+    }
+    out[v] = tess_encodeBarycentrics(xinterp3(baseBary, q));
+  }
+}
+
+// lane index of the item that owns virtual child thread t: first lane whose inclusive end offset exceeds t
+__device__ __forceinline__ uint32_t find_item(uint32_t endOffset, uint32_t t)
+{
+  uint32_t lo = 0;  // answer in [0, 31]
+#pragma unroll
+  for(int step = 16; step > 0; step >>= 1)
+  {
+    uint32_t probe = lo + step - 1;
+    uint32_t e     = __shfl_sync(0xffffffffu, endOffset, probe);
+    if(e <= t)
+      lo += step;
+  }
+  return min(lo, 31u);
+}
+
+__global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, const uint32_t* epochCounter, uint32_t pass, uint32_t lastPass)
+{
+  __shared__ SplitShared sh;
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t slot  = SLOT_SPLIT0 + pass;
+  const uint32_t epoch = *epochCounter + slot;
+  tc_SceneBuilding* b  = p.build;
+  FrameState*       st = p.state;
+  LookbackDesc*     descs = reinterpret_cast<LookbackDesc*>(p.lookback);
+  const uint32_t start = b->splitPassStart, end = b->splitPassEnd;
+  const uint32_t numItems = end > start ? end - start : 0;
+  const uint32_t numTiles = (numItems + SPLIT_THREADS - 1) / SPLIT_THREADS;
+  // bases are constant while the pass runs: only the last CTA to finish writes the counters back
+  const bool     transient = flag_transient(p);
+  const uint32_t baseSplit = b->splitWriteCounter;
+  const uint32_t baseLo    = transient ? lo32(b->dualPartTriangleCounter) : b->partTriangleCounter;
+  const uint32_t hi        = transient ? hi32(b->dualPartTriangleCounter) : 0;
+  const FactorConsts fcst  = load_factor_consts(p);
+  tc_TessTriangleInfo* splitTriangles = reinterpret_cast<tc_TessTriangleInfo*>(b->splitTriangles);
+  tc_TessTriangleInfo* partTriangles  = reinterpret_cast<tc_TessTriangleInfo*>(b->partTriangles);
+
+  if(threadIdx.x == 0)
+    sh.validParts = 0;
+
+  while(true)
+  {
+    __syncthreads();
+    if(threadIdx.x == 0)
+      sh.tile = atomicAdd(&st->ticket[slot], 1u);
+    __syncthreads();
+    const uint32_t tile = sh.tile;
+    if(tile >= numTiles)
+      break;
+
+    const uint32_t readIndex = start + tile * SPLIT_THREADS + threadIdx.x;
+    const bool     runnable  = readIndex < end;
+    uint32_t iInstance = 0, iCluster = 0, iVtx[3] = {0, 0, 0}, iTriCfg = 0;
+    uint32_t firstTriangle = 0, firstVertex = 0, subCount = 0;
+    F3       basePos[3] = {};
+    if(runnable)
+    {
+      const uint2* src = reinterpret_cast<const uint2*>(&splitTriangles[readIndex]);
+      uint2 a = src[0], c = src[1], d = src[2];
+      iInstance = a.x; iCluster = a.y; iVtx[0] = c.x; iVtx[1] = c.y; iVtx[2] = d.x; iTriCfg = d.y;
+      tc_TessTableEntry e = tess_entry(p, iTriCfg >> 16);
+      firstTriangle = e.firstTriangle; firstVertex = e.firstVertex; subCount = e.numTriangles;
+      // fillBaseVertices (:146-174)
+      const tc_RenderInstance& inst = p.instances[iInstance];
+      const uint4 ch = __ldg(reinterpret_cast<const uint4*>(inst.clusters) + iCluster);
+      const uint8_t* lt = reinterpret_cast<const uint8_t*>(inst.clusterLocalTriangles) + ch.w + (iTriCfg & 0xFFFF) * 3;
+      const float* positions = reinterpret_cast<const float*>(inst.positions);
+      float m[16];
+#pragma unroll
+      for(int k = 0; k < 16; k++)
+        m[k] = inst.worldMatrix[k];
+#pragma unroll
+      for(int v = 0; v < 3; v++)
+        basePos[v] = xtransform_point(m, ld_f3(positions, ch.z + __ldg(lt + v)));
+    }
+    const uint32_t endOffset   = warp_inclusive_add(subCount);
+    const uint32_t startOffset = endOffset - subCount;
+    const uint32_t total       = __shfl_sync(0xffffffffu, endOffset, 31);
+    const uint32_t numRuns     = (total + 31) / 32;
+
+    // ---------------- phase 1: classify every child, remember (cfg, rotation, kind) ----------------
+    uint32_t nSplitW = 0, nPartW = 0;
+    for(uint32_t r = 0; r < numRuns; r++)
+    {
+      const uint32_t t     = r * 32 + lane;
+      const bool     valid = t < total;
+      const uint32_t item  = find_item(endOffset, t);
+      const uint32_t sub   = t - __shfl_sync(0xffffffffu, startOffset, item);
+      const uint32_t pcfg  = __shfl_sync(0xffffffffu, iTriCfg, item) >> 16;
+      const uint32_t pFT   = __shfl_sync(0xffffffffu, firstTriangle, item);
+      const uint32_t pFV   = __shfl_sync(0xffffffffu, firstVertex, item);
+      uint32_t pv[3];
+      F3       bp[3];
+#pragma unroll
+      for(int v = 0; v < 3; v++)
+      {
+        pv[v]   = __shfl_sync(0xffffffffu, iVtx[v], item);
+        bp[v].x = __shfl_sync(0xffffffffu, basePos[v].x, item);
+        bp[v].y = __shfl_sync(0xffffffffu, basePos[v].y, item);
+        bp[v].z = __shfl_sync(0xffffffffu, basePos[v].z, item);
+      }
+      bool split = false, part = false;
+      if(valid)
+      {
+        uint32_t enc[3];
+        split_child_corners(p, pcfg, pFT, pFV, sub, pv, enc);
+        F3 w[3];
+        float d[3];
+#pragma unroll
+        for(int v = 0; v < 3; v++)
+        {
+          w[v] = xinterp3(bp, tess_decodeBarycentrics(enc[v]));
+          d[v] = xdistance3(w[v], fcst.eye);
+        }
+        uint32_t f[3];
+        tess_factors(fcst, w[0], w[1], w[2], d[0], d[1], d[2], f);
+        uint32_t mx = max(max(f[0], f[1]), f[2]);
+        split       = mx > TC_TESSTABLE_SIZE;
+        part        = !split;
+        if(split)
+        {
+          f[0] = tess_splitFactor(f[0], p.splitFactor); f[1] = tess_splitFactor(f[1], p.splitFactor); f[2] = tess_splitFactor(f[2], p.splitFactor);
+        }
+        uint32_t rot;
+        uint32_t ncfg = tess_getConfigRot(f[0], f[1], f[2], rot);
+        sh.stash[warp][t] = uint16_t((ncfg & 0x8FFF) | (rot << 12) | (split ? 0x4000u : 0u));
+      }
+      uint32_t cs = __popc(__ballot_sync(0xffffffffu, split)), cp = __popc(__ballot_sync(0xffffffffu, part));
+      if(lane == 0)
+      {
+        sh.runSplitPref[warp][r] = nSplitW;
+        sh.runPartPref[warp][r]  = nPartW;
+      }
+      nSplitW += cs;
+      nPartW += cp;
+    }
+    if(lane == 0)
+    {
+      sh.runSplitPref[warp][numRuns] = nSplitW;
+      sh.runPartPref[warp][numRuns]  = nPartW;
+      sh.warpSplit[warp] = nSplitW;
+      sh.warpPart[warp]  = nPartW;
+    }
+    __syncthreads();
+
+    // ---------------- tile scan + look-back ----------------
+    if(warp == 0)
+    {
+      ScanTuple total2;
+      total2.zero();
+      uint32_t ps = 0, pp = 0;
+      for(int w = 0; w < SPLIT_WARPS; w++)
+      {
+        if(lane == 0)
+        {
+          sh.prefSplit[w] = ps;
+          sh.prefPart[w]  = pp;
+        }
+        ps += sh.warpSplit[w];
+        pp += sh.warpPart[w];
+      }
+      total2.v[0] = ps;
+      total2.v[1] = pp;
+      ScanTuple excl = lookback_exclusive(descs, tile, total2, epoch);
+      if(lane == 0)
+      {
+        for(int w = 0; w < SPLIT_WARPS; w++)
+        {
+          sh.prefSplit[w] += excl.v[0];
+          sh.prefPart[w] += excl.v[1];
+        }
+        if(tile == numTiles - 1)
+        {
+          excl.add(total2);
+          st_tuple(reinterpret_cast<ScanTuple*>(&descs[numTiles].aggregate), excl);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: emit, one allocation per run of 32 children (processSubTask :252-330) ----------------
+    uint32_t validParts = 0;
+    for(uint32_t r = 0; r < numRuns; r++)
+    {
+      const uint32_t t     = r * 32 + lane;
+      const bool     valid = t < total;
+      const uint32_t item  = find_item(endOffset, t);
+      const uint32_t sub   = t - __shfl_sync(0xffffffffu, startOffset, item);
+      const uint32_t ptc   = __shfl_sync(0xffffffffu, iTriCfg, item);
+      const uint32_t pFT   = __shfl_sync(0xffffffffu, firstTriangle, item);
+      const uint32_t pFV   = __shfl_sync(0xffffffffu, firstVertex, item);
+      const uint32_t pInst = __shfl_sync(0xffffffffu, iInstance, item);
+      const uint32_t pClus = __shfl_sync(0xffffffffu, iCluster, item);
+      uint32_t pv[3];
+#pragma unroll
+      for(int v = 0; v < 3; v++)
+        pv[v] = __shfl_sync(0xffffffffu, iVtx[v], item);
+      uint32_t code  = valid ? sh.stash[warp][t] : 0;
+      bool     split = valid && (code & 0x4000u), part = valid && !(code & 0x4000u);
+      uint32_t voteSplit = __ballot_sync(0xffffffffu, split), votePart = __ballot_sync(0xffffffffu, part);
+      uint32_t countPart = __popc(votePart);
+      uint32_t offsetSplit = baseSplit + sh.prefSplit[warp] + sh.runSplitPref[warp][r] + __popc(voteSplit & lanemask_lt());
+      uint32_t loBefore    = baseLo + sh.prefPart[warp] + sh.runPartPref[warp][r];
+      uint32_t offsetPart  = dual_front_offset(p, loBefore, hi, countPart) + __popc(votePart & lanemask_lt());
+      if(valid)
+      {
+        uint32_t enc[3];
+        split_child_corners(p, ptc >> 16, pFT, pFV, sub, pv, enc);
+        uint32_t rot = (code >> 12) & 3u;
+        uint32_t v0 = enc[0], v1 = enc[1], v2 = enc[2];
+        if(rot == 1)
+        {
+          v0 = enc[1]; v1 = enc[2]; v2 = enc[0];
+        }
+        else if(rot == 2)
+        {
+          v0 = enc[2]; v1 = enc[0]; v2 = enc[1];
+        }
+        uint32_t triCfg = (ptc & 0xFFFFu) | ((code & 0x8FFFu) << 16);
+        if(split && offsetSplit < p.maxSplitTriangles)
+        {
+          uint2* dst = reinterpret_cast<uint2*>(&splitTriangles[offsetSplit]);
+          dst[0] = make_uint2(pInst, pClus);
+          dst[1] = make_uint2(v0, v1);
+          dst[2] = make_uint2(v2, triCfg);
+        }
+        else if(part && offsetPart < p.maxPartTriangles)
+        {
+          uint2* dst = reinterpret_cast<uint2*>(&partTriangles[offsetPart]);
+          dst[0] = make_uint2(pInst, pClus);
+          dst[1] = make_uint2(v0, v1);
+          dst[2] = make_uint2(v2, triCfg);
+          validParts = max(validParts, offsetPart + 1);
+        }
+      }
+    }
+#pragma unroll
+    for(int d = 16; d > 0; d >>= 1)
+      validParts = max(validParts, __shfl_xor_sync(0xffffffffu, validParts, d));
+    if(lane == 0 && validParts)
+      atomicMax(&sh.validParts, validParts);
+  }
+
+  // ---------------- epilogue: BUILD_SETUP_SPLIT_PASS (:168-190) or BUILD_SETUP_INSTANTIATE_TESS (:236-264) ----------------
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    if(sh.validParts)
+      atomicMax(&st->validParts, sh.validParts);
+    __threadfence();
+    uint32_t done = atomicAdd(&st->done[slot], 1u);
+    if(done == gridDim.x - 1)
+    {
+      __threadfence();
+      ScanTuple tot;
+      tot.zero();
+      if(numTiles > 0)
+        tot = ld_tuple(reinterpret_cast<const ScanTuple*>(&descs[numTiles].aggregate));
+      const uint32_t validAll = *(volatile uint32_t*)&st->validParts;
+      b->splitWriteCounter = baseSplit + tot.v[0];
+      const uint32_t loNow = baseLo + tot.v[1];
+      if(transient)
+      {
+        b->dualPartTriangleCounter = (unsigned long long)loNow | ((unsigned long long)hi << 32);
+        b->partTriangleCounter     = max(b->partTriangleCounter, validAll);  // atomicMax :323-329 (validAll covers classify too,
+                                                                             // whose written parts never exceed the old value)
+      }
+      else
+        b->partTriangleCounter = loNow;
+      st->partSegEnd[st->numPartSegs] = loNow;
+      st->numPartSegs += 1;
+
+      if(!lastPass)
+      {
+        b->splitPass += 1;
+        uint32_t s2 = min(b->splitPassEnd, p.maxSplitTriangles);
+        uint32_t e2 = min(b->splitWriteCounter, p.maxSplitTriangles);
+        b->splitPassStart = s2;
+        b->splitPassEnd   = e2;
+        b->dispatchTriangleSplit.gridX = (e2 - s2 + 63) / 64;
+        b->dispatchTriangleSplit.gridY = 1;
+        b->dispatchTriangleSplit.gridZ = 1;
+      }
+      else
+      {
+        uint32_t counterPart = loNow;
+        if(transient)
+        {
+          p.readback->numPartTriangles      = counterPart + hi;
+          p.readback->numTransPartTriangles = hi;
+        }
+        else
+          p.readback->numPartTriangles = counterPart;
+        p.readback->numSplitTriangles = b->splitWriteCounter;
+        if(transient)
+          counterPart = b->partTriangleCounter;
+        else
+        {
+          counterPart            = min(counterPart, p.maxPartTriangles);
+          b->partTriangleCounter = counterPart;
+        }
+        b->dispatchTriangleInstantiate.gridX = (counterPart + TC_TESS_INSTANTIATE_BATCHSIZE - 1) / TC_TESS_INSTANTIATE_BATCHSIZE;
+        b->dispatchTriangleInstantiate.gridY = 1;
+        b->dispatchTriangleInstantiate.gridZ = 1;
+        // DESIGN.md deviation: only entries written this frame are visited
+        st->numParts = min(counterPart, validAll);
+      }
+    }
+  }
+}
+
+// ============================================================================================================
+// triangle_tess_template_instantiate + BUILD_SETUP_BUILD_BLAS
+// ============================================================================================================
+
+constexpr int INST_THREADS = 128;               // one part per thread
+constexpr int INST_STAGE_VERTS = 3072;          // staging window (vertices) for coalesced 128-bit stores
+constexpr int INST_STAGE_FLOATS = INST_STAGE_VERTS * 3 + 4;
+
+struct InstShared
+{
+  float    stage[INST_STAGE_FLOATS];
+  uint32_t warpV[INST_THREADS / 32];
+  unsigned long long warpD[INST_THREADS / 32];
+  uint32_t tile;
+  uint32_t tileVertexBase;      // absolute vertex offset of the tile
+  unsigned long long tileDataBase;
+  uint32_t tileWritten;         // vertices of successful parts in the tile (they form a prefix)
+  uint32_t succ, totalTris;
+};
+
+__global__ void __launch_bounds__(INST_THREADS) k_instantiate(Params p, const uint32_t* epochCounter)
+{
+  __shared__ __align__(16) InstShared sh;
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t epoch = *epochCounter + SLOT_INSTANTIATE;
+  tc_SceneBuilding* b  = p.build;
+  FrameState*       st = p.state;
+  LookbackDesc*     descs = reinterpret_cast<LookbackDesc*>(p.lookback);
+  const uint32_t numParts = st->numParts;
+  const uint32_t numTiles = (numParts + INST_THREADS - 1) / INST_THREADS;
+  // bases: constant during the kernel (written back by the last CTA only)
+  const uint32_t baseVertex = b->genVertexCounter, baseGen = b->genClusterCounter, baseTemp = st->tempAfterClassify;
+  const unsigned long long baseData = b->genClusterDataCounter;
+  const unsigned long long genVerticesAddr = b->genVertices, genClusterData = b->genClusterData;
+  const tc_TessTriangleInfo* partTriangles = reinterpret_cast<const tc_TessTriangleInfo*>(b->partTriangles);
+  float*              genVertices          = reinterpret_cast<float*>(b->genVertices);
+  uint4*              tempInstantiations   = reinterpret_cast<uint4*>(b->tempInstantiations);
+  uint32_t*           tempInstanceIDs      = reinterpret_cast<uint32_t*>(b->tempInstanceIDs);
+  unsigned long long* tempClusterAddresses = reinterpret_cast<unsigned long long*>(b->tempClusterAddresses);
+  uint32_t*           tempClusterSizes     = reinterpret_cast<uint32_t*>(b->tempClusterSizes);
+
+  if(threadIdx.x == 0)
+  {
+    sh.succ = 0;
+    sh.totalTris = 0;
+  }
+
+  while(true)
+  {
+    __syncthreads();
+    if(threadIdx.x == 0)
+      sh.tile = atomicAdd(&st->ticket[SLOT_INSTANTIATE], 1u);
+    __syncthreads();
+    const uint32_t tile = sh.tile;
+    if(tile >= numTiles)
+      break;
+
+    const uint32_t partIndex = tile * INST_THREADS + threadIdx.x;
+    const bool     valid     = partIndex < numParts;
+    uint32_t instanceID = 0, clusterID = 0, vtxEnc[3] = {0, 0, 0}, triCfg = 0;
+    uint32_t numVertices = 0, numTriangles = 0, firstVertex = 0, dataSize = 0;
+    if(valid)
+    {
+      const uint2* src = reinterpret_cast<const uint2*>(&partTriangles[partIndex]);
+      uint2 a = src[0], c = src[1], d = src[2];
+      instanceID = a.x; clusterID = a.y; vtxEnc[0] = c.x; vtxEnc[1] = c.y; vtxEnc[2] = d.x; triCfg = d.y;
+      tc_TessTableEntry e = tess_entry(p, triCfg >> 16);
+      numVertices = e.numVertices; numTriangles = e.numTriangles; firstVertex = e.firstVertex;
+      dataSize    = __ldg(&p.tblTemplSize[tess_configIndex(triCfg >> 16) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1)]);
+    }
+    // block scan of (numVertices, dataSize)
+    uint32_t incV = warp_inclusive_add(numVertices);
+    unsigned long long incD = dataSize;
+#pragma unroll
+    for(int dlt = 1; dlt < 32; dlt <<= 1)
+    {
+      unsigned long long n = __shfl_up_sync(0xffffffffu, incD, dlt);
+      if(lane >= dlt)
+        incD += n;
+    }
+    if(lane == 31)
+    {
+      sh.warpV[warp] = incV;
+      sh.warpD[warp] = incD;
+    }
+    __syncthreads();
+    if(warp == 0)
+    {
+      ScanTuple agg;
+      agg.zero();
+      for(int w = 0; w < INST_THREADS / 32; w++)
+      {
+        agg.v[0] += sh.warpV[w];
+        agg.d += sh.warpD[w];
+      }
+      ScanTuple excl = lookback_exclusive(descs, tile, agg, epoch);
+      if(lane == 0)
+      {
+        sh.tileVertexBase = baseVertex + excl.v[0];
+        sh.tileDataBase   = baseData + excl.d;
+        if(tile == numTiles - 1)
+        {
+          excl.add(agg);
+          st_tuple(reinterpret_cast<ScanTuple*>(&descs[numTiles].aggregate), excl);
+        }
+      }
+    }
+    __syncthreads();
+    uint32_t relV = incV - numVertices;
+    unsigned long long relD = incD - dataSize;
+    for(uint32_t w = 0; w < warp; w++)
+    {
+      relV += sh.warpV[w];
+      relD += sh.warpD[w];
+    }
+    const uint32_t tileVertexBase = sh.tileVertexBase;
+    const uint32_t vertexOffset   = tileVertexBase + relV;
+    const unsigned long long dataOffset = sh.tileDataBase + relD;
+    const uint32_t genOffset      = baseGen + partIndex;
+    bool ok = valid && !((vertexOffset + numVertices > p.maxGenVertices) || (genOffset + 1 > p.maxGenClusters) || (dataOffset + dataSize > p.maxGenDataBytes));
+
+    // successful parts are a prefix of the tile: the tile's written vertex count is the end of the last good part
+    if(threadIdx.x == 0)
+      sh.tileWritten = 0;
+    __syncthreads();
+    if(ok)
+      atomicMax(&sh.tileWritten, relV + numVertices);
+    uint32_t okVote = __ballot_sync(0xffffffffu, ok);
+    uint32_t trisW  = warp_sum(ok ? numTriangles : 0);
+    if(lane == 0)
+    {
+      if(okVote) atomicAdd(&sh.succ, __popc(okVote));
+      if(trisW) atomicAdd(&sh.totalTris, trisW);
+    }
+
+    BaseTriangle       bt;
+    DisplacementConsts dc{0.f, 0.f, -1};
+    float              geoSize = 1.0f;
+    const bool         flipped = (triCfg >> 16) & TC_CONFIG_FLIPPED_BIT;
+    if(ok)
+    {  // records (:171-203)
+      const uint32_t cfgIdx     = tess_configIndex(triCfg >> 16) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1);
+      const uint32_t tempOffset = baseTemp + partIndex;
+      const unsigned long long templAddr = __ldg(reinterpret_cast<const unsigned long long*>(p.tblTemplAddr) + cfgIdx);
+      const unsigned long long vaddr     = genVerticesAddr + (unsigned long long)(uint32_t)(vertexOffset * 4u * 3u);
+      tempInstantiations[size_t(tempOffset) * 2 + 0] = make_uint4(partIndex | (TC_RT_CLUSTER_MODE_SINGLE_TESSELLATED << 30), 0u, uint32_t(templAddr), uint32_t(templAddr >> 32));
+      tempInstantiations[size_t(tempOffset) * 2 + 1] = make_uint4(uint32_t(vaddr), uint32_t(vaddr >> 32), 12u, 0u);
+      tempInstanceIDs[tempOffset]      = instanceID;
+      tempClusterAddresses[tempOffset] = genClusterData + dataOffset;
+      if(p.driverStandin)
+        tempClusterSizes[tempOffset] = dataSize;
+
+      const tc_RenderInstance& inst = p.instances[instanceID];
+      const uint4 ch = __ldg(reinterpret_cast<const uint4*>(inst.clusters) + clusterID);
+      const uint8_t* lt = reinterpret_cast<const uint8_t*>(inst.clusterLocalTriangles) + ch.w + (triCfg & 0xFFFF) * 3;
+      setup_base_triangle(p, inst, ch.z, __ldg(lt), __ldg(lt + 1), __ldg(lt + 2), vtxEnc, bt);
+      dc      = displacement_consts(p, inst);
+      geoSize = inst.geoHi[3];
+    }
+    __syncthreads();
+    const uint32_t tileWritten = sh.tileWritten;
+
+    // vertex generation through a shared staging window, flushed with aligned 128-bit stores
+    uint32_t nextVert = 0;
+    const uint32_t myCount = ok ? numVertices : 0;
+    for(uint32_t winStart = 0; winStart < tileWritten; winStart += INST_STAGE_VERTS)
+    {
+      const uint32_t winEnd   = min(winStart + INST_STAGE_VERTS, tileWritten);
+      const size_t   dstFloat = size_t(tileVertexBase + winStart) * 3;  // first float of the window in genVertices
+      const uint32_t shift    = uint32_t(dstFloat & 3);                 // keep smem and global 16-byte phases equal
+      while(nextVert < myCount && relV + nextVert < winEnd)
+      {
+        F3 o = generate_vertex(p, bt, dc, __ldg(&p.tblVertices[firstVertex + nextVert]), flipped, instanceID, geoSize);
+        uint32_t s = shift + (relV + nextVert - winStart) * 3;
+        sh.stage[s + 0] = o.x; sh.stage[s + 1] = o.y; sh.stage[s + 2] = o.z;
+        nextVert++;
+      }
+      __syncthreads();
+      const uint32_t nFloats = (winEnd - winStart) * 3;
+      float*         dst     = genVertices + dstFloat;
+      // head (to 16-byte alignment), body (float4), tail
+      const uint32_t head = min(nFloats, (4u - shift) & 3u);
+      if(threadIdx.x < head)
+        dst[threadIdx.x] = sh.stage[shift + threadIdx.x];
+      const uint32_t bodyVec = (nFloats - head) / 4;
+      const float4*  s4 = reinterpret_cast<const float4*>(&sh.stage[shift + head]);
+      float4*        d4 = reinterpret_cast<float4*>(dst + head);
+      for(uint32_t i = threadIdx.x; i < bodyVec; i += INST_THREADS)
+        __stcs(d4 + i, s4[i]);
+      const uint32_t tailStart = head + bodyVec * 4;
+      if(threadIdx.x < nFloats - tailStart)
+        dst[tailStart + threadIdx.x] = sh.stage[shift + tailStart + threadIdx.x];
+      __syncthreads();
+    }
+  }
+
+  // ---------------- epilogue: counters + BUILD_SETUP_BUILD_BLAS (build_setup.comp.glsl:191-235) ----------------
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    if(sh.succ) atomicAdd(&b->tempInstantiateCounter, sh.succ);
+    if(sh.totalTris) atomicAdd(&p.readback->numTotalTriangles, sh.totalTris);
+    __threadfence();
+    uint32_t done = atomicAdd(&st->done[SLOT_INSTANTIATE], 1u);
+    if(done == gridDim.x - 1)
+    {
+      __threadfence();
+      ScanTuple tot;
+      tot.zero();
+      if(numTiles > 0)
+        tot = ld_tuple(reinterpret_cast<const ScanTuple*>(&descs[numTiles].aggregate));
+      b->genVertexCounter      = baseVertex + tot.v[0];
+      b->genClusterDataCounter = baseData + tot.d;
+      b->genClusterCounter     = baseGen + numParts;
+
+      const bool     transient    = flag_transient(p);
+      const uint32_t maxEntries   = p.maxGenClusters;
+      uint32_t       counterTemp  = *(volatile uint32_t*)&b->tempInstantiateCounter;
+      uint32_t       counterTrans = transient ? b->transBuildCounter : 0;
+      tc_Readback*   rb           = p.readback;
+      rb->numBlasClusters         = counterTemp + counterTrans;
+      if(transient)
+        rb->numTransBuilds = counterTrans;
+      rb->numTempInstantiations = counterTemp;
+      rb->numGenDatas           = b->genClusterDataCounter;
+      rb->numGenVertices        = b->genVertexCounter;
+      rb->numBlasReservedSizes  = b->numBlasReservedSizes;
+      counterTemp               = min(maxEntries, counterTemp);
+      if(transient)
+        counterTrans = min(maxEntries, counterTemp + counterTrans) - counterTemp;
+      b->tempInstantiateCounter       = counterTemp;
+      rb->numActualTempInstantiations = counterTemp;
+      b->dispatchBlasTempInsert.gridX = (counterTemp + 63) / 64;
+      b->dispatchBlasTempInsert.gridY = 1;
+      b->dispatchBlasTempInsert.gridZ = 1;
+      if(transient)
+      {
+        b->transBuildCounter             = counterTrans;
+        rb->numActualTransBuilds         = counterTrans;
+        b->dispatchBlasTransInsert.gridX = (counterTrans + 63) / 64;
+        b->dispatchBlasTransInsert.gridY = 1;
+        b->dispatchBlasTransInsert.gridZ = 1;
+      }
+    }
+  }
+}
+
+// ============================================================================================================
+// blas_setup_insertion + blas_clusters_insert, atomics replaced by sorted-segment ranks
+//
+// Every generated-CLAS list is a concatenation of a few segments that are each sorted by instance id (full
+// clusters; parts appended by classify; parts appended by each split pass; transient builds), because clusters
+// are visited in (instance, cluster) order and all appends are order preserving.  The rank of an element inside
+// its instance's BLAS list is therefore  sum(earlier segments' counts for that instance) + (index - first index
+// of the instance in this segment),  found with binary searches -- no atomics, deterministic order.
+// ============================================================================================================
+
+struct SegmentTable
+{
+  uint32_t begin[TC_MAX_SEGMENTS + 2], end[TC_MAX_SEGMENTS + 2];
+  uint32_t isTrans[TC_MAX_SEGMENTS + 2];
+  uint32_t count;
+};
+
+__device__ __forceinline__ SegmentTable load_segments(const Params& p)
+{
+  SegmentTable      t;
+  const FrameState* st      = p.state;
+  const uint32_t    numTemp = p.build->tempInstantiateCounter, numTrans = flag_transient(p) ? p.build->transBuildCounter : 0;
+  const uint32_t    tA      = min(st->tempAfterClassify, numTemp);
+  uint32_t n = 0;
+  t.begin[n] = 0; t.end[n] = tA; t.isTrans[n] = 0; n++;
+  uint32_t prev = 0;
+  for(uint32_t s = 0; s < st->numPartSegs && s < TC_MAX_SEGMENTS; s++)
+  {
+    uint32_t e = min(min(st->partSegEnd[s], st->numParts) + tA, numTemp);
+    uint32_t bgn = min(prev + tA, numTemp);
+    t.begin[n] = bgn; t.end[n] = max(e, bgn); t.isTrans[n] = 0; n++;
+    prev = min(st->partSegEnd[s], st->numParts);
+  }
+  t.begin[n] = 0; t.end[n] = numTrans; t.isTrans[n] = 1; n++;
+  t.count = n;
+  return t;
+}
+
+// grid: (numInstances + 1) * segments threads.  segLo[s][i] = first index in segment s whose instance id >= i
+__global__ void k_blas_segments(Params p)
+{
+  const SegmentTable segs = load_segments(p);
+  const uint32_t     N    = p.numInstances;
+  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if(gid >= (N + 1) * segs.count)
+    return;
+  uint32_t s = gid / (N + 1), i = gid % (N + 1);
+  const uint32_t* ids = reinterpret_cast<const uint32_t*>(segs.isTrans[s] ? p.build->transInstanceIDs : p.build->tempInstanceIDs);
+  uint32_t lo = segs.begin[s], hi = segs.end[s];
+  while(lo < hi)
+  {
+    uint32_t mid = (lo + hi) >> 1;
+    if(__ldg(&ids[mid]) < i)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  p.segLo[size_t(s) * (N + 1) + i] = lo;
+}
+
+// one CTA: per-instance totals, exclusive scan in instance order, BlasBuildInfo (blas_setup_insertion.comp.glsl:100-115)
+__global__ void __launch_bounds__(1024) k_blas_setup(Params p)
+{
+  __shared__ uint32_t warpSums[32];
+  __shared__ uint32_t carry, sizesSum, blockTotal;
+  const SegmentTable segs = load_segments(p);
+  const uint32_t     N    = p.numInstances;
+  tc_BlasBuildInfo*  blas = reinterpret_cast<tc_BlasBuildInfo*>(p.build->blasBuildInfos);
+  const uint32_t*    blasBuildSizes = reinterpret_cast<const uint32_t*>(p.build->blasBuildSizes);
+  if(threadIdx.x == 0)
+  {
+    carry    = 0;
+    sizesSum = 0;
+  }
+  __syncthreads();
+  uint32_t localSizes = 0;
+  for(uint32_t base = 0; base < N; base += blockDim.x)
+  {
+    uint32_t i = base + threadIdx.x;
+    uint32_t total = 0;
+    if(i < N)
+    {
+      for(uint32_t s = 0; s < segs.count; s++)
+      {
+        p.rankBase[size_t(s) * (N + 1) + i] = total;
+        total += p.segLo[size_t(s) * (N + 1) + i + 1] - p.segLo[size_t(s) * (N + 1) + i];
+      }
+      localSizes += blasBuildSizes[i];
+    }
+    uint32_t inc = warp_inclusive_add(total);
+    if(lane_id() == 31)
+      warpSums[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if(threadIdx.x < 32)
+    {
+      uint32_t v  = threadIdx.x < (blockDim.x >> 5) ? warpSums[threadIdx.x] : 0;
+      uint32_t iv = warp_inclusive_add(v);
+      warpSums[threadIdx.x] = iv - v;
+      if(threadIdx.x == 31)
+        blockTotal = iv;
+    }
+    __syncthreads();
+    uint32_t offset = carry + warpSums[threadIdx.x >> 5] + inc - total;
+    if(i < N)
+    {
+      blas[i].clusterReferencesCount  = total;  // the value blas_clusters_insert re-counts to
+      blas[i].clusterReferencesStride = 8;
+      blas[i].clusterReferences       = p.build->blasClusterAddresses + (unsigned long long)(uint32_t)(offset * 8u);
+    }
+    __syncthreads();
+    if(threadIdx.x == 0)
+      carry += blockTotal;
+    __syncthreads();
+  }
+  localSizes = warp_sum(localSizes);
+  if(lane_id() == 0 && localSizes)
+    atomicAdd(&sizesSum, localSizes);
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    p.build->blasClusterCounter     = carry;
+    p.readback->numBlasActualSizes += sizesSum;
+  }
+}
+
+// thread per generated CLAS (templates first, then transient builds), blas_clusters_insert.comp.glsl:97-135
+__global__ void k_blas_insert(Params p)
+{
+  __shared__ unsigned long long blockSizes;
+  const SegmentTable segs = load_segments(p);
+  const uint32_t     N    = p.numInstances;
+  const uint32_t numTemp  = p.build->tempInstantiateCounter, numTrans = flag_transient(p) ? p.build->transBuildCounter : 0;
+  if(threadIdx.x == 0)
+    blockSizes = 0;
+  __syncthreads();
+  unsigned long long mySize = 0;
+  for(uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < numTemp + numTrans; gid += gridDim.x * blockDim.x)
+  {
+    const bool     isTrans = gid >= numTemp;
+    const uint32_t j       = isTrans ? gid - numTemp : gid;
+    uint32_t s = 0;
+    if(isTrans)
+      s = segs.count - 1;
+    else
+      while(s + 2 < segs.count && j >= segs.end[s])
+        s++;
+    const uint32_t* ids   = reinterpret_cast<const uint32_t*>(isTrans ? p.build->transInstanceIDs : p.build->tempInstanceIDs);
+    const unsigned long long* addrs = reinterpret_cast<const unsigned long long*>(isTrans ? p.build->transClusterAddresses : p.build->tempClusterAddresses);
+    const uint32_t* sizes = reinterpret_cast<const uint32_t*>(isTrans ? p.build->transClusterSizes : p.build->tempClusterSizes);
+    const uint32_t  inst  = ids[j];
+    const uint32_t  idx   = p.rankBase[size_t(s) * (N + 1) + inst] + (j - p.segLo[size_t(s) * (N + 1) + inst]);
+    const tc_BlasBuildInfo* blas = reinterpret_cast<const tc_BlasBuildInfo*>(p.build->blasBuildInfos);
+    unsigned long long* refs = reinterpret_cast<unsigned long long*>(blas[inst].clusterReferences);
+    refs[idx] = addrs[j];
+    mySize += sizes[j];
+  }
+#pragma unroll
+  for(int d = 16; d > 0; d >>= 1)
+    mySize += __shfl_xor_sync(0xffffffffu, mySize, d);
+  if(lane_id() == 0 && mySize)
+    atomicAdd(&blockSizes, mySize);
+  __syncthreads();
+  if(threadIdx.x == 0 && blockSizes)
+    atomicAdd(reinterpret_cast<unsigned long long*>(&p.readback->numGenActualDatas), blockSizes);
+}
+
+// shard summary for the multi-GPU allgather
+__global__ void k_shard_counts(Params p, tc_shard_counts* out)
+{
+  out->tempInstantiateCounter = p.build->tempInstantiateCounter;
+  out->transBuildCounter      = p.build->transBuildCounter;
+  out->genVertexCounter       = p.build->genVertexCounter;
+  out->blasClusterCounter     = p.build->tempInstantiateCounter + (flag_transient(p) ? p.build->transBuildCounter : 0);
+  out->genClusterDataCounter  = p.build->genClusterDataCounter;
+  out->numTotalTriangles      = p.readback->numTotalTriangles;
+  out->numInstances           = p.numInstances;
+}
+
+__global__ void k_flush_l2(float4* buf, size_t n)
+{
+  for(size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ============================================================================================================
+// launch wrappers
+// ============================================================================================================
+
+size_t classify_smem_bytes(uint32_t clusterVertices, uint32_t clusterTriangles)
+{
+  return size_t(CLASSIFY_WARPS) * (size_t(clusterVertices) * 7 + size_t(clusterTriangles) * 3) * 4;
+}
+
+int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, KernelOccupancy* occ)
+{
+  size_t smem = classify_smem_bytes(clusterVertices, clusterTriangles);
+  if(cudaFuncSetAttribute(k_cluster_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    return -1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->classify, k_cluster_classify, CLASSIFY_THREADS, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->split, k_triangle_split, SPLIT_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->instantiate, k_instantiate, INST_THREADS, 0);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+uint32_t lookback_tiles_needed(uint32_t maxVisible, uint32_t maxSplit, uint32_t maxPart)
+{
+  uint32_t a = (maxVisible + CLASSIFY_WARPS - 1) / CLASSIFY_WARPS;
+  uint32_t b = (maxSplit + SPLIT_THREADS - 1) / SPLIT_THREADS;
+  uint32_t c = (maxPart + INST_THREADS - 1) / INST_THREADS;
+  uint32_t m = a > b ? a : b;
+  m          = m > c ? m : c;
+  return m + 2;  // +1: slot that carries the grand total
+}
+
+size_t lookback_desc_bytes() { return sizeof(LookbackDesc); }
+size_t frame_state_bytes() { return sizeof(FrameState); }
+
+void launch_frame_setup(const Params& p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter, cudaStream_t s)
+{
+  k_frame_setup<<<1, 128, 0, s>>>(p, tmpl, viewPosOverride, epochCounter);
+}
+void launch_instances_classify(const Params& p, cudaStream_t s)
+{
+  if(p.numInstances)
+    k_instances_classify<<<(p.numInstances + 63) / 64, 64, 0, s>>>(p);
+}
+void launch_clusters_cull(const Params& p, cudaStream_t s)
+{
+  uint32_t n = p.totalClusters < p.maxVisibleClusters ? p.totalClusters : p.maxVisibleClusters;
+  k_clusters_cull<<<(n + 255) / 256 + (n == 0 ? 1 : 0), 256, 0, s>>>(p);
+}
+void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s)
+{
+  k_cluster_classify<<<grid, CLASSIFY_THREADS, classify_smem_bytes(p.clusterVertices, p.clusterTriangles), s>>>(p, epochCounter);
+}
+void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32_t pass, bool lastPass, uint32_t grid, cudaStream_t s)
+{
+  k_triangle_split<<<grid, SPLIT_THREADS, 0, s>>>(p, epochCounter, pass, lastPass ? 1u : 0u);
+}
+void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s)
+{
+  k_instantiate<<<grid, INST_THREADS, 0, s>>>(p, epochCounter);
+}
+void launch_blas(const Params& p, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s)
+{
+  uint32_t threads = (p.numInstances + 1) * numSegmentsMax;
+  k_blas_segments<<<(threads + 255) / 256, 256, 0, s>>>(p);
+  k_blas_setup<<<1, 1024, 0, s>>>(p);
+  k_blas_insert<<<grid, 256, 0, s>>>(p);
+}
+void launch_shard_counts(const Params& p, tc_shard_counts* out, cudaStream_t s) { k_shard_counts<<<1, 1, 0, s>>>(p, out); }
+void launch_flush_l2(void* buf, size_t bytes, cudaStream_t s) { k_flush_l2<<<1184, 256, 0, s>>>(reinterpret_cast<float4*>(buf), bytes / 16); }
+
+}  // namespace tc

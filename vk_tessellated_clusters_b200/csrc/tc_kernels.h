@@ -1,0 +1,33 @@
+// tc_kernels.h -- host-callable launch wrappers of tc_kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/tess_clusters.h"
+
+namespace tc {
+
+struct Params;
+
+struct KernelOccupancy
+{
+  int classify = 1, split = 1, instantiate = 1;
+};
+
+int      configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, KernelOccupancy* occ);
+uint32_t lookback_tiles_needed(uint32_t maxVisible, uint32_t maxSplit, uint32_t maxPart);
+size_t   lookback_desc_bytes();
+size_t   frame_state_bytes();
+
+void launch_frame_setup(const Params& p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter, cudaStream_t s);
+void launch_instances_classify(const Params& p, cudaStream_t s);
+void launch_clusters_cull(const Params& p, cudaStream_t s);
+void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s);
+void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32_t pass, bool lastPass, uint32_t grid, cudaStream_t s);
+void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s);
+void launch_blas(const Params& p, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s);
+void launch_shard_counts(const Params& p, tc_shard_counts* out, cudaStream_t s);
+void launch_flush_l2(void* buf, size_t bytes, cudaStream_t s);
+
+}  // namespace tc
