@@ -161,6 +161,11 @@ TC_API int tc_download(tc_context* ctx, uint64_t src, void* dst, size_t bytes);
 
 /* CUDA stream the context enqueues on (cudaStream_t as integer), for consumers that chain GPU work. */
 TC_API int tc_stream(tc_context* ctx, uint64_t* stream);
+/* Make the context enqueue on a caller-owned stream (e.g. the stream NCCL collectives are issued on) so that the
+ * frame, the allgather and the insert step are ordered without host synchronisation.  0 restores the own stream. */
+TC_API int tc_set_stream(tc_context* ctx, uint64_t stream);
+/* Asynchronous device-to-device copy on the context stream (moves shard counts / bases to and from NCCL buffers). */
+TC_API int tc_copy_async(tc_context* ctx, uint64_t dstDevice, uint64_t srcDevice, size_t bytes);
 
 /* ---- measurement helpers (bench.py) ------------------------------------------------------------------ */
 enum {
@@ -198,6 +203,14 @@ typedef struct tc_shard_counts {
 TC_API int tc_device_shard_counts(tc_context* ctx, uint64_t* deviceAddress);
 /* Device address of a 2 x u32 block {globalBlasClusterBase, globalInstanceBase} the insert step adds. */
 TC_API int tc_device_shard_base(tc_context* ctx, uint64_t* deviceAddress);
+/* Global BLAS insertion list of this shard, written by the insert step: one record per local instance giving its
+ * global instance id and where its cluster references start in the concatenation over all ranks. */
+typedef struct tc_global_blas_range {
+  uint32_t globalInstanceID;
+  uint32_t clusterReferencesCount;
+  uint64_t globalFirstReference; /* index into the rank-concatenated reference list */
+} tc_global_blas_range;
+TC_API int tc_device_global_blas_ranges(tc_context* ctx, uint64_t* deviceAddress);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -1,0 +1,113 @@
+"""CPU tests of the host-side logic: procedural scenes, frame constants, instance sharding (gloo, world size 2)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+
+from vk_tessellated_clusters_b200 import scenes as S, sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _check_geometry(g, max_v=64, max_t=64):
+    cl = g.clusters
+    assert cl["numVertices"].max() <= max_v and cl["numTriangles"].max() <= max_t
+    assert int(cl["numVertices"].sum()) == g.num_vertices and int(cl["numTriangles"].sum()) == g.num_triangles
+    np.testing.assert_array_equal(cl["firstLocalVertex"], np.concatenate([[0], np.cumsum(cl["numVertices"])[:-1]]))
+    np.testing.assert_array_equal(cl["firstLocalTriangle"], 3 * np.concatenate([[0], np.cumsum(cl["numTriangles"])[:-1]]))
+    cl_of_tri = np.repeat(np.arange(g.num_clusters), cl["numTriangles"])
+    lt = g.local_triangles.reshape(-1, 3)
+    assert (lt < cl["numVertices"][cl_of_tri][:, None]).all()
+    assert (g.bboxes["lo"] <= g.bboxes["hi"]).all() and (g.bboxes["shortestEdge"] <= g.bboxes["longestEdge"]).all()
+    assert np.allclose(np.linalg.norm(g.normals, axis=1), 1.0, atol=1e-5)
+
+
+def test_grid_plane_clusters():
+    g = S.make_grid_plane(256)
+    assert g.num_triangles == 131072 and g.num_clusters == 2048 and g.num_vertices == 2048 * 45
+    _check_geometry(g)
+    r = S.make_grid_plane(37)
+    assert r.num_triangles == 2 * 37 * 37
+    _check_geometry(r)
+    assert len(set(r.clusters["numTriangles"].tolist())) > 1  # ragged tiles exist
+
+
+def test_icosphere_clusters():
+    g = S.make_icosphere(5)
+    assert g.num_triangles == 20 * 4**5 and g.num_clusters == 20 * 4**2
+    _check_geometry(g)
+    assert np.allclose(np.linalg.norm(g.positions, axis=1), 1.0, atol=1e-5)
+    # outward facing (CCW): triangle normal points along the position
+    cl_of_tri = np.repeat(np.arange(g.num_clusters), g.clusters["numTriangles"])
+    idx = g.local_triangles.reshape(-1, 3).astype(np.int64) + g.clusters["firstLocalVertex"][cl_of_tri][:, None]
+    p = g.positions[idx].astype(np.float64)
+    n = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
+    assert (np.einsum("ij,ij->i", n, p.mean(axis=1)) > 0).all()
+
+
+def test_frame_constants_and_hiz_shape():
+    fc = S.make_frame_constants((0, -3, 1), (0, 0, 0), up=(0, 0, 1), near=0.01, far=100.0)
+    assert tuple(fc["viewport"]) == (3840, 2160) and fc["tessRate"] == np.float32(0.25)
+    vp = fc["viewProjMatrix"].reshape(4, 4).T
+    h = vp @ np.array([0, 0, 0, 1.0])
+    assert abs(h[0] / h[3]) < 1e-5 and abs(h[1] / h[3]) < 1e-5 and 0 < h[2] / h[3] < 1  # target at screen centre, RH_ZO depth
+    size, mips, uw, uh, factors, size_max = S.hiz_info(3840, 2160)
+    assert (size, mips, uw, uh) == (2048, 12, 1920, 1080) and size_max == 2048.0
+    pyr, n = S.make_hiz_pyramid(np.ones((8, 8), np.float32))
+    assert n == 4 and pyr.size == 64 + 16 + 4 + 1
+
+
+def test_grid_copies_layout():
+    sh = S.grid_copies(9, (2.0, 2.0, 2.0), grid_config=3)
+    assert sh.shape == (9, 3) and (sh[:, 2] == 0).all()
+    assert sorted(set(np.round(-sh[:, 0]).tolist())) == [0.0, 2.0, 4.0] and sorted(set(np.round(sh[:, 1]).tolist())) == [0.0, 2.0, 4.0]
+
+
+def test_partition_instances_balanced_contiguous():
+    counts = np.array([10, 10, 10, 10, 40, 10, 10, 20])
+    for w in (1, 2, 3, 4, 8):
+        parts = sharding.partition_instances(counts, w)
+        assert parts[0][0] == 0 and parts[-1][1] == len(counts) and len(parts) == w
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        assert all(b > a for a, b in parts)
+    two = sharding.partition_instances(counts, 2)
+    loads = [counts[a:b].sum() for a, b in two]
+    assert abs(loads[0] - loads[1]) <= 40
+
+
+_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["TC_ROOT"])
+from vk_tessellated_clusters_b200 import sharding
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# rank r generated (100 + 10 r) template CLAS, (5 + r) transient, owns (3 + r) instances
+local = torch.tensor([100 + 10 * rank, 5 + rank, 1000 * (rank + 1), 105 + 11 * rank, 4096 * (rank + 1), 0, 7 * (rank + 1), 3 + rank], dtype=torch.int32)
+gathered, base = sharding.exchange_shard_counts(local)
+assert gathered.shape == (world, sharding.SHARD_WORDS)
+want_cluster_base = sum(105 + 11 * r for r in range(rank))
+want_instance_base = sum(3 + r for r in range(rank))
+assert base.tolist() == [want_cluster_base, want_instance_base], (rank, base.tolist())
+tot = sharding.global_totals(gathered)
+assert tot["blasClusters"] == sum(105 + 11 * r for r in range(world)) and tot["instances"] == sum(3 + r for r in range(world))
+assert tot["totalTriangles"] == sum(7 * (r + 1) for r in range(world))
+dist.barrier()
+dist.destroy_process_group()
+open(os.path.join(os.environ["TC_OUT"], f"rank{rank}.ok"), "w").write("ok")
+"""
+
+
+def test_shard_count_exchange_gloo_world2(tmp_path):
+    """The N > 1 path's host logic (allgather of tc_shard_counts -> exclusive bases) over gloo, two processes."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, TC_ROOT=ROOT, TC_OUT=str(tmp_path))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert (tmp_path / "rank0.ok").exists() and (tmp_path / "rank1.ok").exists()

@@ -1,0 +1,121 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on identical seeded inputs.
+Integer / byte / index outputs must be bit-exact (compared WITHOUT order normalisation); displaced vertex positions
+within 1e-5 relative (tests/parity_utils.py:VERTEX_RTOL)."""
+import numpy as np
+import pytest
+
+from tests.parity_utils import compare_frame, make_pair
+from tests.scene_cases import ALL_CASES, case
+from vk_tessellated_clusters_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_parity_case(name, table, oracle_lib):
+    scene, fcs, cfg, hiz = case(name)
+    gpu, orc = make_pair(scene, table, cfg, hiz)
+    try:
+        for _ in range(2):  # second frame exercises the per-frame reset of every counter / scan epoch
+            gpu.frame(fcs)
+            orc.frame(fcs)
+            stats = compare_frame(gpu, orc, scene_scale=scene.radius)
+        assert stats["triangles"] > 0
+    finally:
+        gpu.close()
+        orc.close()
+
+
+def test_moving_camera_sequence(table, oracle_lib):
+    """Several different frames back to back (viewLast = previous frame, as the app does)."""
+    from vk_tessellated_clusters_b200 import scenes as S
+
+    scene, fcs, cfg, _ = case("icosphere")
+    gpu, orc = make_pair(scene, table, cfg)
+    prev = fcs[0]
+    for k, d in enumerate([2.5, 2.0, 1.6, 3.5, 8.0]):
+        _, f = S.config_icosphere(0, tex_size=8, distance=d)
+        pair = S.frame_pair(f[0], prev)
+        gpu.frame(pair)
+        orc.frame(pair)
+        compare_frame(gpu, orc, scene_scale=scene.radius)
+        prev = f[0]
+    gpu.close()
+    orc.close()
+
+
+def test_freeze_culling_view_pos_override(table, oracle_lib):
+    scene, fcs, cfg, _ = case("plane")
+    gpu, orc = make_pair(scene, table, cfg)
+    vp = np.array([0.1, -3.0, 2.0], dtype=np.float32)
+    gpu.frame(fcs, vp)
+    orc.frame(fcs, vp)
+    compare_frame(gpu, orc, scene_scale=scene.radius)
+    _, sb = gpu.readback()
+    np.testing.assert_array_equal(sb["viewPos"], vp)
+    gpu.close()
+    orc.close()
+
+
+def test_graph_replay_and_split_entry_points_match_plain_frame(table, oracle_lib):
+    """tc_frame_graph and tc_frame_build + tc_frame_insert must produce the same bytes as tc_frame."""
+    scene, fcs, cfg, _ = case("split")
+    gpu, orc = make_pair(scene, table, cfg)
+    orc.frame(fcs)
+    for _ in range(3):
+        gpu.frame_graph(fcs)
+    compare_frame(gpu, orc, scene_scale=scene.radius)
+    gpu.frame_build(fcs)
+    gpu.frame_insert()
+    compare_frame(gpu, orc, scene_scale=scene.radius)
+    assert gpu.last_launch_count() >= 10
+    gpu.close()
+    orc.close()
+
+
+def test_idempotent_frames_are_byte_identical(table, oracle_lib):
+    """No atomics decide output order: the same frame twice gives identical bytes in every buffer (the reference's
+    atomic compaction cannot promise this)."""
+    scene, fcs, cfg, _ = case("mini")
+    gpu = api.TessClusters(cfg)
+    gpu.set_tess_table(table)
+    gpu.set_scene(scene)
+    snaps = []
+    for _ in range(2):
+        gpu.frame(fcs)
+        _, sb = gpu.readback()
+        snaps.append({n: gpu.buffer(n, None, sb).tobytes() for n in ["partTriangles", "tempInstantiations", "transBuilds", "blasClusterAddresses", "genVertices"]})
+    assert snaps[0] == snaps[1]
+    gpu.close()
+
+
+def test_device_lookup_table_matches_host_rule(table):
+    scene, fcs, cfg, _ = case("plane")
+    gpu = api.TessClusters(cfg)
+    gpu.set_tess_table(table)
+    import ctypes as C
+
+    class TT(C.Structure):
+        _fields_ = [(n, C.c_uint64) for n in ["vertices", "triangles", "entries", "templateAddresses", "templateInstantiationSizes"]]
+
+    tt = TT()
+    assert gpu.lib.tc_device_tess_table(gpu._ctx, C.byref(tt)) == 0
+    ent = gpu.download(tt.entries, 4096 * 8).view("<u2").reshape(4096, 4)
+    np.testing.assert_array_equal(ent, table.lookup_entries())
+    np.testing.assert_array_equal(gpu.download(tt.vertices, table.vertices.nbytes).view("<u4"), table.vertices)
+    gpu.close()
+
+
+def test_invalid_usage_is_reported(table):
+    gpu = api.TessClusters(api.Config(numVisibleClusterBits=8, numPartTriangleBits=8, numSplitTriangleBits=8, numGeneratedVerticesBits=10))
+    scene, fcs, _, _ = case("plane")
+    with pytest.raises(api.TessError, match="must be called first"):
+        gpu.frame(fcs)
+    gpu.set_tess_table(table)
+    big = api.Config(clusterVertices=32, clusterTriangles=32)
+    g2 = api.TessClusters(big)
+    g2.set_tess_table(table)
+    with pytest.raises(api.TessError, match="cluster exceeds"):
+        g2.set_scene(scene)
+    g2.close()
+    gpu.close()

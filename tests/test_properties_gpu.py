@@ -1,0 +1,97 @@
+"""GPU tests at BASELINE.json sizes, where the oracle would be slow to compare byte-for-byte every time: size-independent
+properties of the outputs (partition of the BLAS lists, contiguous vertex allocation, conservation of triangle counts,
+idempotence), plus one full-size oracle comparison of the integer outputs of the headline workload."""
+import numpy as np
+import pytest
+
+from vk_tessellated_clusters_b200 import api, scenes as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_properties(gpu, table, cfg):
+    rb, sb = gpu.readback()
+    ent = table.lookup_entries()
+    n_temp, n_trans = int(sb["tempInstantiateCounter"]), int(sb["transBuildCounter"])
+    n_parts = int(sb["partTriangleCounter"])
+    assert int(rb["numBlasClusters"]) == n_temp + n_trans == int(sb["blasClusterCounter"])
+    parts = gpu.buffer("partTriangles", n_parts, sb)
+    cfgs = (parts["triangleID_config"] >> 16) & 0x7FFF
+    assert (ent[cfgs, 2] > 0).all()
+    ti = gpu.buffer("tempInstantiations", n_temp, sb)
+    part_mode = (ti["clusterIdOffset"] >> 30) == 1
+    assert int(part_mode.sum()) == n_parts
+    np.testing.assert_array_equal(ti["clusterIdOffset"][part_mode] & 0x3FFFFFFF, np.arange(n_parts, dtype=np.uint32))
+    # vertex allocation of the parts is one contiguous run in part order (scan order), each part getting numVertices(cfg)
+    voff = ((ti["vertexBufferAddress"][part_mode] - sb["genVertices"]) // 12).astype(np.int64)
+    nv = ent[cfgs, 3].astype(np.int64)
+    np.testing.assert_array_equal(np.diff(voff), nv[:-1])
+    assert voff[-1] + nv[-1] == int(sb["genVertexCounter"])
+    # conservation: output triangles = part pattern triangles + transient triangles + full cluster triangles
+    tb = gpu.buffer("transBuilds", n_trans, sb)
+    tris = int(ent[cfgs, 2].astype(np.int64).sum()) + int((tb["packed"] & 0x1FF).astype(np.int64).sum())
+    assert int(rb["numTotalTriangles"]) >= tris
+    # BLAS lists: disjoint regions in instance order, each the multiset of that instance's CLAS addresses
+    N = gpu.num_instances
+    blas = gpu.buffer("blasBuildInfos", N, sb)
+    starts = ((blas["clusterReferences"] - sb["blasClusterAddresses"]) // 8).astype(np.int64)
+    np.testing.assert_array_equal(starts, np.concatenate([[0], np.cumsum(blas["clusterReferencesCount"].astype(np.int64))[:-1]]))
+    refs = gpu.buffer("blasClusterAddresses", n_temp + n_trans, sb)
+    ids = np.concatenate([gpu.buffer("tempInstanceIDs", n_temp, sb), gpu.buffer("transInstanceIDs", n_trans, sb)])
+    addrs = np.concatenate([gpu.buffer("tempClusterAddresses", n_temp, sb), gpu.buffer("transClusterAddresses", n_trans, sb)])
+    order = np.lexsort((addrs, ids))
+    seg = np.repeat(np.arange(N), blas["clusterReferencesCount"].astype(np.int64))
+    order2 = np.lexsort((refs, seg))
+    np.testing.assert_array_equal(addrs[order], refs[order2])
+    np.testing.assert_array_equal(ids[order], seg[order2].astype(ids.dtype))
+    assert np.unique(addrs).size == addrs.size
+    return rb, sb
+
+
+def test_headline_workload_properties_and_integer_parity(table, oracle_lib):
+    """bench.py's N=1 workload at full size: properties + bit-exact integer outputs against the oracle."""
+    import bench
+    from oracle.oracle_binding import Oracle
+    from tests.parity_utils import compare_frame
+
+    scene, fcs, cfg = bench.workload()
+    gpu = api.TessClusters(cfg)
+    gpu.set_tess_table(table)
+    gpu.set_scene(scene)
+    gpu.frame(fcs)
+    rb, sb = _check_properties(gpu, table, cfg)
+    assert int(rb["numTotalTriangles"]) >= 100_000_000  # north_star: >= 100 M displaced output triangles per frame
+    assert int(rb["numSplitTriangles"]) > 0
+    orc = Oracle(cfg)
+    orc.set_tess_table(table)
+    orc.set_scene(scene)
+    orc.set_addresses(sb)
+    orc.frame(fcs)
+    stats = compare_frame(gpu, orc, scene_scale=scene.radius, check_vertices=True)
+    assert stats["max_rel_err"] <= 1e-5
+    # idempotence at full size
+    a = gpu.buffer("blasClusterAddresses", int(sb["blasClusterCounter"]), sb).tobytes()
+    gpu.frame(fcs)
+    _, sb2 = gpu.readback()
+    assert a == gpu.buffer("blasClusterAddresses", int(sb2["blasClusterCounter"]), sb2).tobytes()
+    gpu.close()
+    orc.close()
+
+
+def test_instance_grid_with_culling_properties(table):
+    """BASELINE config 3 shape (instance grid, frustum + HiZ instance culling), 256 instances of a 20 k-triangle mesh."""
+    scene, fcs, pyr, size, mips = S.config_instances(256, subdiv=5, tex_size=256, tess_rate_pixels=2.0)
+    cfg = api.Config(flags=api.FLAG_DEFAULT | api.FLAG_CULLING, numVisibleClusterBits=17, numPartTriangleBits=22, numSplitTriangleBits=20,
+                     numGeneratedVerticesBits=27, numGeneratedClusterMegs=4095)
+    gpu = api.TessClusters(cfg)
+    gpu.set_tess_table(table)
+    gpu.set_scene(scene)
+    gpu.set_hiz(pyr, size, mips)
+    gpu.frame(fcs)
+    rb, sb = gpu.readback()
+    states = gpu.buffer("instanceStates", 256, sb)
+    assert 0 < int(((states & 2) != 0).sum()) < 256  # some instances visible, some culled
+    assert ((states & 2) <= ((states & 1) << 1)).all()  # visible implies in frustum
+    if int(sb["splitWriteCounter"]) <= cfg.max_split_triangles and int(rb["numGenVertices"]) <= cfg.max_generated_vertices:
+        _check_properties(gpu, table, cfg)
+    gpu.close()

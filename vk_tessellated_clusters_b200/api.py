@@ -59,6 +59,11 @@ SCENE_BUILDING_DTYPE = np.dtype(
         ("_padEnd", "<u4"),
     ]
 )
+SHARD_COUNTS_DTYPE = np.dtype(
+    [("tempInstantiateCounter", "<u4"), ("transBuildCounter", "<u4"), ("genVertexCounter", "<u4"), ("blasClusterCounter", "<u4"),
+     ("genClusterDataCounter", "<u8"), ("numTotalTriangles", "<u4"), ("numInstances", "<u4")]
+)
+GLOBAL_BLAS_RANGE_DTYPE = np.dtype([("globalInstanceID", "<u4"), ("clusterReferencesCount", "<u4"), ("globalFirstReference", "<u8")])
 READBACK_DTYPE = np.dtype(
     [
         ("numVisibleClusters", "<u4"), ("numFullClusters", "<u4"), ("numSplitTriangles", "<u4"), ("numPartTriangles", "<u4"), ("numTotalTriangles", "<u4"),
@@ -332,6 +337,17 @@ class TessClusters(Binding):
         s = C.c_uint64()
         self._check(self.lib.tc_stream(self._ctx, C.byref(s)), "stream")
         return int(s.value)
+
+    def set_stream(self, stream: int):
+        self._check(self.lib.tc_set_stream(self._ctx, C.c_uint64(int(stream))), "set_stream")
+
+    def copy_async(self, dst: int, src: int, nbytes: int):
+        self._check(self.lib.tc_copy_async(self._ctx, C.c_uint64(int(dst)), C.c_uint64(int(src)), C.c_size_t(int(nbytes))), "copy_async")
+
+    def device_global_blas_ranges(self) -> int:
+        a = C.c_uint64()
+        self._check(self.lib.tc_device_global_blas_ranges(self._ctx, C.byref(a)), "device_global_blas_ranges")
+        return int(a.value)
 
     def device_shard_counts(self) -> int:
         a = C.c_uint64()

@@ -55,6 +55,7 @@ struct tc_context
   int          device = 0;
   int          numSMs = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t ownStream = nullptr;
   tc::KernelOccupancy occ;
 
   uint32_t maxVisible = 0, maxPart = 0, maxSplit = 0, maxVerts = 0, maxGenClusters = 0;
@@ -81,6 +82,7 @@ struct tc_context
   tc_RenderInstance* dInstances = nullptr;
   uint32_t*          dClusterPrefix = nullptr;
   uint32_t *         segLo = nullptr, *rankBase = nullptr;
+  tc_global_blas_range* globalRanges = nullptr;
   std::vector<DeviceGeometry> geoms;
   std::vector<void*>          textures;
   uint32_t numInstances = 0, totalClusters = 0;
@@ -148,7 +150,8 @@ void free_scene(tc_context* c)
     dfree(t);
   c->textures.clear();
   dfree(c->instanceStates); dfree(c->blasBuildInfos); dfree(c->blasBuildSizes); dfree(c->basicClusterSizes);
-  dfree(c->dInstances); dfree(c->dClusterPrefix); dfree(c->segLo); dfree(c->rankBase);
+  dfree(c->dInstances); dfree(c->dClusterPrefix); dfree(c->segLo); dfree(c->rankBase); dfree(c->globalRanges);
+  c->globalRanges = nullptr;
   c->instanceStates = c->blasBuildInfos = c->blasBuildSizes = c->basicClusterSizes = nullptr;
   c->dInstances = nullptr;
   c->dClusterPrefix = nullptr;
@@ -234,6 +237,7 @@ void fill_params(tc_context* c)
   p.segLo              = c->segLo;
   p.rankBase           = c->rankBase;
   p.shardBase          = c->dShardBase;
+  p.globalRanges       = c->globalRanges;
 }
 
 struct StageScope
@@ -302,10 +306,10 @@ int enqueue_build(tc_context* c)
     StageScope sc(c, TC_STAGE_PREP_INSTANTIATE);
     uint32_t grid = std::max(1u, uint32_t(c->numSMs * c->occ.instantiate));
     tc::launch_instantiate(p, c->dEpoch, grid, s);
-    tc::launch_shard_counts(p, c->dShardCounts, s);
-    launches += 2;
+    launches += 1;
   }
-  c->lastLaunches = launches;
+  tc::launch_shard_counts(p, c->dShardCounts, s);  // summary record for the multi-GPU allgather
+  c->lastLaunches = launches + 1;
   CUDA_TRY(cudaGetLastError());
   return TC_OK;
 }
@@ -382,7 +386,8 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
       return bail(fail(TC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)));                              \
   } while(0)
 
-  TRY_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  TRY_CUDA(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
+  c->stream = c->ownStream;
   if(tc::configure_kernels(config->clusterVertices, config->clusterTriangles, &c->occ) != 0)
     return bail(fail(TC_ERR_CUDA, std::string("kernel configuration failed: ") + cudaGetErrorString(cudaGetLastError())));
 
@@ -465,8 +470,8 @@ TC_API void tc_destroy(tc_context* c)
   if(c->evValid)
     for(int i = 0; i <= TC_STAGE_COUNT; i++)
       cudaEventDestroy(c->ev[i]);
-  if(c->stream)
-    cudaStreamDestroy(c->stream);
+  if(c->ownStream)
+    cudaStreamDestroy(c->ownStream);
   delete c;
 }
 
@@ -582,6 +587,7 @@ TC_API int tc_set_scene(tc_context* c, const tc_geometry* geoms, uint32_t numGeo
   if((rc = dalloc(c->dInstances, size_t(numInstances) * sizeof(tc_RenderInstance))) || (rc = dalloc(c->dClusterPrefix, size_t(numInstances + 1) * 4))
      || (rc = dalloc(c->instanceStates, size_t(numInstances) * 4)) || (rc = dalloc(c->blasBuildInfos, size_t(numInstances) * sizeof(tc_BlasBuildInfo)))
      || (rc = dalloc(c->blasBuildSizes, size_t(numInstances) * 4)) || (rc = dalloc(c->basicClusterSizes, size_t(std::max(numBasicClusterSizes, 1u)) * 4))
+     || (rc = dalloc(c->globalRanges, size_t(numInstances) * sizeof(tc_global_blas_range)))
      || (rc = dalloc(c->segLo, size_t(TC_MAX_SEGMENTS + 2) * (numInstances + 1) * 4)) || (rc = dalloc(c->rankBase, size_t(TC_MAX_SEGMENTS + 2) * (numInstances + 1) * 4)))
     return rc;
   CUDA_TRY(cudaMemcpy(c->dInstances, inst.data(), size_t(numInstances) * sizeof(tc_RenderInstance), cudaMemcpyHostToDevice));
@@ -767,6 +773,34 @@ TC_API int tc_stream(tc_context* c, uint64_t* stream)
   if(!c || !stream)
     return fail(TC_ERR_INVALID_ARG, "null argument");
   *stream = uint64_t(c->stream);
+  return TC_OK;
+}
+
+TC_API int tc_set_stream(tc_context* c, uint64_t stream)
+{
+  if(!c)
+    return fail(TC_ERR_INVALID_ARG, "null context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  drop_graph(c);
+  c->stream = stream ? reinterpret_cast<cudaStream_t>(stream) : c->ownStream;
+  return TC_OK;
+}
+
+TC_API int tc_copy_async(tc_context* c, uint64_t dstDevice, uint64_t srcDevice, size_t bytes)
+{
+  if(!c || !dstDevice || !srcDevice)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<void*>(dstDevice), reinterpret_cast<const void*>(srcDevice), bytes, cudaMemcpyDeviceToDevice, c->stream));
+  return TC_OK;
+}
+
+TC_API int tc_device_global_blas_ranges(tc_context* c, uint64_t* deviceAddress)
+{
+  if(!c || !deviceAddress)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  *deviceAddress = uint64_t(c->globalRanges);
   return TC_OK;
 }
 

@@ -80,6 +80,7 @@ struct Params
   uint32_t* segLo;     // [TC_MAX_SEGMENTS+1][numInstances]
   uint32_t* rankBase;  // [TC_MAX_SEGMENTS+1][numInstances]
   const uint32_t* shardBase;  // {globalBlasClusterBase, globalInstanceBase}
+  tc_global_blas_range* globalRanges;  // [numInstances]
 };
 
 __device__ __forceinline__ bool flag_pn(const Params& p) { return p.flags & TC_FLAG_PN_DISPLACEMENT; }

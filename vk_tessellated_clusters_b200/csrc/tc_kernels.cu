@@ -1632,6 +1632,8 @@ __global__ void __launch_bounds__(1024) k_blas_setup(Params p)
       blas[i].clusterReferencesCount  = total;  // the value blas_clusters_insert re-counts to
       blas[i].clusterReferencesStride = 8;
       blas[i].clusterReferences       = p.build->blasClusterAddresses + (unsigned long long)(uint32_t)(offset * 8u);
+      // multi-GPU: position of this instance's list in the rank-concatenated insertion list
+      p.globalRanges[i] = tc_global_blas_range{p.shardBase[1] + i, total, (unsigned long long)p.shardBase[0] + offset};
     }
     __syncthreads();
     if(threadIdx.x == 0)

@@ -1,0 +1,64 @@
+"""Instance sharding across GPUs.
+
+Every stage of the path is independent per instance; the only cross-instance couplings are allocation counters and
+the BLAS region offsets, all plain prefix sums.  So: each rank owns a contiguous instance range and runs the whole
+chain locally; ONE small allgather per frame (a tc_shard_counts record per rank, 32 bytes) gives every rank the
+exclusive prefix that places its BLAS insertion list in the global one.  No vertex or record data crosses NVLink.
+
+Works with any torch.distributed backend: "nccl" on GPUs (tensors on the rank's device, collective enqueued on the
+current stream, no host sync) and "gloo" on CPU for tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SHARD_WORDS = 8  # tc_shard_counts as 8 x u32: temp, trans, genVertex, blasClusters, dataLo, dataHi, totalTris, numInstances
+
+
+def partition_instances(cluster_counts, world_size: int):
+    """Contiguous instance ranges balanced by cluster count.  Returns list of (first, last_exclusive) per rank."""
+    cluster_counts = np.asarray(cluster_counts, dtype=np.int64)
+    n = cluster_counts.shape[0]
+    if world_size <= 1:
+        return [(0, n)]
+    total = int(cluster_counts.sum())
+    prefix = np.concatenate([[0], np.cumsum(cluster_counts)])
+    bounds = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        i = int(np.searchsorted(prefix, target, side="left"))
+        # keep every rank non-empty while instances remain
+        i = max(i, bounds[-1] + 1) if bounds[-1] + 1 <= n - (world_size - r) else bounds[-1]
+        i = min(i, n - (world_size - r))
+        i = max(i, bounds[-1])
+        bounds.append(i)
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+
+
+def exchange_shard_counts(local_counts, group=None):
+    """local_counts: int32 tensor [SHARD_WORDS] (device of the backend).  Returns (gathered [world, SHARD_WORDS],
+    base [2] int32 = {globalBlasClusterBase, globalInstanceBase}) -- both stay on the tensor's device."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    gathered = torch.empty((world, SHARD_WORDS), dtype=local_counts.dtype, device=local_counts.device)
+    dist.all_gather_into_tensor(gathered, local_counts.reshape(1, SHARD_WORDS), group=group)
+    excl = torch.cumsum(gathered, dim=0) - gathered  # exclusive prefix over ranks
+    base = torch.stack([excl[rank, 3], excl[rank, 7]]).to(local_counts.dtype)
+    return gathered, base
+
+
+def global_totals(gathered) -> dict:
+    g = gathered.to("cpu").numpy().astype(np.int64) & 0xFFFFFFFF
+    return {
+        "tempInstantiations": int(g[:, 0].sum()),
+        "transBuilds": int(g[:, 1].sum()),
+        "genVertices": int(g[:, 2].sum()),
+        "blasClusters": int(g[:, 3].sum()),
+        "genClusterDataBytes": int((g[:, 4] + (g[:, 5] << 32)).sum()),
+        "totalTriangles": int(g[:, 6].sum()),
+        "instances": int(g[:, 7].sum()),
+    }
