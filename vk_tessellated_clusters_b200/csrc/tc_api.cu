@@ -88,6 +88,7 @@ struct tc_context
   uint32_t numInstances = 0, totalClusters = 0;
 
   // table
+  void *tblVerticesF = nullptr;
   void *tblVertices = nullptr, *tblTriangles = nullptr, *tblEntries = nullptr, *tblTemplAddr = nullptr, *tblTemplSize = nullptr;
   // hiz
   float* hiz = nullptr;
@@ -214,6 +215,7 @@ void fill_params(tc_context* c)
   p.instanceClusterPrefix = c->dClusterPrefix;
   p.state       = c->dState;
   p.tblVertices  = reinterpret_cast<const uint32_t*>(c->tblVertices);
+  p.tblVerticesF = reinterpret_cast<const float2*>(c->tblVerticesF);
   p.tblTriangles = reinterpret_cast<const uint32_t*>(c->tblTriangles);
   p.tblEntries   = reinterpret_cast<const tc_TessTableEntry*>(c->tblEntries);
   p.tblTemplAddr = reinterpret_cast<const uint64_t*>(c->tblTemplAddr);
@@ -464,6 +466,7 @@ TC_API void tc_destroy(tc_context* c)
   dfree(c->blasClusterAddresses);
   if(c->cfg.allocClasData)
     dfree(c->genClusterData);
+  dfree(c->tblVerticesF);
   dfree(c->tblVertices); dfree(c->tblTriangles); dfree(c->tblEntries); dfree(c->tblTemplAddr); dfree(c->tblTemplSize);
   dfree(c->hiz);
   dfree(c->flushBuf);
@@ -499,6 +502,8 @@ TC_API int tc_set_tess_table(tc_context* c, const uint32_t* vertices, uint32_t n
         if(z != y && x > 1)
           lookup[idx3(x, z, y)] = e;
       }
+  dfree(c->tblVerticesF);
+  c->tblVerticesF = nullptr;
   dfree(c->tblVertices); dfree(c->tblTriangles); dfree(c->tblEntries); dfree(c->tblTemplAddr); dfree(c->tblTemplSize);
   c->tblVertices = c->tblTriangles = c->tblEntries = c->tblTemplAddr = c->tblTemplSize = nullptr;
   int rc;
@@ -507,6 +512,18 @@ TC_API int tc_set_tess_table(tc_context* c, const uint32_t* vertices, uint32_t n
      || (rc = dalloc(c->tblTemplSize, TC_TESSTABLE_LOOKUP_ENTRIES * 4)))
     return rc;
   CUDA_TRY(cudaMemcpy(c->tblVertices, vertices, size_t(numVertices) * 4, cudaMemcpyHostToDevice));
+  {
+    // pattern vertices pre-converted to floats: u/32768 and v/32768 are exact, identical to the in-kernel decode
+    std::vector<float> vf(size_t(numVertices) * 2);
+    for(uint32_t i = 0; i < numVertices; i++)
+    {
+      vf[2 * i + 0] = float(vertices[i] & 0xFFFF) / 32768.0f;
+      vf[2 * i + 1] = float(vertices[i] >> 16) / 32768.0f;
+    }
+    if((rc = dalloc(c->tblVerticesF, vf.size() * 4)))
+      return rc;
+    CUDA_TRY(cudaMemcpy(c->tblVerticesF, vf.data(), vf.size() * 4, cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(cudaMemcpy(c->tblTriangles, triangles, size_t(numTriangles) * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->tblEntries, lookup.data(), lookup.size() * sizeof(tc_TessTableEntry), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->tblTemplAddr, templAddr4096, TC_TESSTABLE_LOOKUP_ENTRIES * 8, cudaMemcpyHostToDevice));

@@ -55,6 +55,7 @@ struct Params
   FrameState*              state;
   // tessellation table
   const uint32_t*          tblVertices;
+  const float2*            tblVerticesF;  // same vertices pre-converted to (u, v) floats (exact: /32768)
   const uint32_t*          tblTriangles;
   const tc_TessTableEntry* tblEntries;
   const uint64_t*          tblTemplAddr;
@@ -505,6 +506,166 @@ __device__ __forceinline__ F3 eval_pn(const BaseTriangle& b, float u, float v, f
   p    = fma3(b.b012, u * v2, p);
   p    = fma3(b.b111, (w * u) * v, p);
   return p;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FAST instantiate: per-part record (shared memory) + per-vertex evaluation.
+//
+// A part's vertices are a cubic (PN) or linear function of the pattern vertex (q1, q2).  Everything that is constant
+// per part is folded into a 60-word record once:
+//   words 0..5   affine map pattern (q1,q2) -> base-triangle barycentrics (s,t) = (lambda1, lambda2); the "flipped"
+//                pattern handling (tessellation.glsl:179-189, weights .yxz) is folded into the coefficients
+//   word  6      firstVertex of the pattern in the table      word 7   displacement texture index (-1: none)
+//   words 8..37  position polynomial in the power basis, P = sum c_jk s^j t^k (10 x float3), converted from the PN
+//                control net of displacement.glsl:47-79 (9 FMA per component instead of 44 mul/add)
+//   words 38,39  displacement scale / offset
+//   words 40..48 normal n0, n1-n0, n2-n0     words 49..54 texcoord u0,du1,du2,v0,dv1,dv2
+//   word  55     geometry size (ripple)      word 56 instance id (ripple seed)
+// ------------------------------------------------------------------------------------------------------------
+
+#define TC_REC_WORDS 60
+
+__device__ __forceinline__ void st3(float* dst, F3 v)
+{
+  dst[0] = v.x; dst[1] = v.y; dst[2] = v.z;
+}
+
+__device__ __forceinline__ void build_part_record(const Params& p, const tc_RenderInstance& inst, uint32_t instanceID, uint32_t firstLocalVertex,
+                                                  uint32_t i0, uint32_t i1, uint32_t i2, const uint32_t vtxEncoded[3], bool flipped,
+                                                  uint32_t firstPatternVertex, float* rec)
+{
+  const float* positions = reinterpret_cast<const float*>(inst.positions);
+  const float* normals   = reinterpret_cast<const float*>(inst.normals);
+  const float* texcoords = reinterpret_cast<const float*>(inst.texcoords);
+  const uint32_t gi[3]   = {firstLocalVertex + i0, firstLocalVertex + i1, firstLocalVertex + i2};
+  float bu[3], bv[3];
+  F3    pos[3], nrm[3];
+  float tu[3], tv[3];
+#pragma unroll
+  for(int v = 0; v < 3; v++)
+  {
+    bu[v]  = float(vtxEncoded[v] & 0xFFFF) * (1.0f / 32768.0f);
+    bv[v]  = float(vtxEncoded[v] >> 16) * (1.0f / 32768.0f);
+    pos[v] = ld_f3(positions, gi[v]);
+    nrm[v] = normalize3(ld_f3(normals, gi[v]));
+    tu[v]  = __ldg(texcoords + size_t(gi[v]) * 2);
+    tv[v]  = __ldg(texcoords + size_t(gi[v]) * 2 + 1);
+  }
+  // corner k has base barycentrics (1-bu-bv, bu, bv); pattern weights (q0,q1,q2), q0 = 1-q1-q2, flipped: q0 <-> q1
+  const int o = flipped ? 1 : 0, a = flipped ? 0 : 1;  // origin corner, corner multiplied by q1
+  rec[0] = bu[o]; rec[1] = bu[a] - bu[o]; rec[2] = bu[2] - bu[o];
+  rec[3] = bv[o]; rec[4] = bv[a] - bv[o]; rec[5] = bv[2] - bv[o];
+  reinterpret_cast<uint32_t*>(rec)[6] = firstPatternVertex;
+  const int texture = (p.numTextures > 0 && inst.displacementIndex >= 0) ? inst.displacementIndex : -1;
+  reinterpret_cast<int*>(rec)[7] = texture;
+
+  F3 c00, c10, c01, c20, c02, c11, c30, c03, c21, c12;
+  if(flag_pn(p))
+  {
+    // PN control net (displacement.glsl:47-79); b_ijk: i = power of lambda0 (vertex 0), j of lambda1, k of lambda2
+    const float third = 1.0f / 3.0f;
+    F3 b300 = pos[0], b030 = pos[1], b003 = pos[2];
+    F3 e01 = b030 - b300, e12 = b003 - b030, e20 = b300 - b003;
+    F3 b210 = project_to_plane(fma3(e01, third, b300), b300, nrm[0]);         // vB021
+    F3 b120 = project_to_plane(fma3(e01, 2.0f * third, b300), b030, nrm[1]);  // vB012
+    F3 b021 = project_to_plane(fma3(e12, third, b030), b030, nrm[1]);         // vB102
+    F3 b012 = project_to_plane(fma3(e12, 2.0f * third, b030), b003, nrm[2]);  // vB201
+    F3 b102 = project_to_plane(fma3(e20, third, b003), b003, nrm[2]);         // vB210
+    F3 b201 = project_to_plane(fma3(e20, 2.0f * third, b003), b300, nrm[0]);  // vB120
+    F3 center = (b030 + b300 + b003) * third;
+    F3 b111   = (b210 + b120 + b021 + b012 + b102 + b201) * (1.0f / 6.0f);
+    b111      = fma3(b111 - center, 0.5f, b111);
+    // Bernstein -> power basis in (s,t) = (lambda1, lambda2) by forward differences
+    c00 = b300;
+    c10 = (b210 - b300) * 3.0f;
+    c01 = (b201 - b300) * 3.0f;
+    c20 = (b120 - b210 * 2.0f + b300) * 3.0f;
+    c02 = (b102 - b201 * 2.0f + b300) * 3.0f;
+    c11 = (b111 - b210 - b201 + b300) * 6.0f;
+    c30 = b030 - b120 * 3.0f + b210 * 3.0f - b300;
+    c03 = b003 - b102 * 3.0f + b201 * 3.0f - b300;
+    c21 = (b021 - b120 - b111 * 2.0f + b210 * 2.0f + b201 - b300) * 3.0f;
+    c12 = (b012 - b102 - b111 * 2.0f + b201 * 2.0f + b210 - b300) * 3.0f;
+  }
+  else
+  {
+    const F3 z = {0.f, 0.f, 0.f};
+    c00 = pos[0]; c10 = pos[1] - pos[0]; c01 = pos[2] - pos[0];
+    c20 = c02 = c11 = c30 = c03 = c21 = c12 = z;
+  }
+  st3(rec + 8, c00);  st3(rec + 11, c10); st3(rec + 14, c01); st3(rec + 17, c20); st3(rec + 20, c02);
+  st3(rec + 23, c11); st3(rec + 26, c30); st3(rec + 29, c03); st3(rec + 32, c21); st3(rec + 35, c12);
+  rec[38] = inst.displacementScale * p.view[0].displacementScale;
+  rec[39] = inst.displacementOffset + p.view[0].displacementOffset;
+  st3(rec + 40, nrm[0]); st3(rec + 43, nrm[1] - nrm[0]); st3(rec + 46, nrm[2] - nrm[0]);
+  rec[49] = tu[0]; rec[50] = tu[1] - tu[0]; rec[51] = tu[2] - tu[0];
+  rec[52] = tv[0]; rec[53] = tv[1] - tv[0]; rec[54] = tv[2] - tv[0];
+  rec[55] = inst.geoHi[3];
+  reinterpret_cast<uint32_t*>(rec)[56] = instanceID;
+}
+
+// floor() and the matching integer without the XU pipe (valid for |x| < 2^22, which texel coordinates satisfy)
+__device__ __forceinline__ float fast_floor(float x, int& xi)
+{
+  const float M = 12582912.0f;  // 1.5 * 2^23
+  float r = __fadd_rn(__fadd_rn(x, M), -M);
+  r       = r > x ? r - 1.0f : r;
+  xi      = __float_as_int(__fadd_rn(r, M)) - 0x4B400000;
+  return r;
+}
+
+// software sampler, same definition as sample_displacement; power-of-two sizes avoid the integer modulo entirely
+__device__ __forceinline__ float sample_displacement_fast(const DeviceTexture& t, float u, float v)
+{
+  const int w = int(t.width), h = int(t.height);
+  float x = fmaf(u, float(w), -0.5f);
+  float y = fmaf(v, float(h), -0.5f);
+  if(!(fabsf(x) < 4194304.0f && fabsf(y) < 4194304.0f) || (w & (w - 1)) || (h & (h - 1)))
+    return sample_displacement(t, u, v);
+  int   xi, yi;
+  float ax = x - fast_floor(x, xi), ay = y - fast_floor(y, yi);
+  int   x0 = xi & (w - 1), x1 = (xi + 1) & (w - 1);
+  int   y0 = yi & (h - 1), y1 = (yi + 1) & (h - 1);
+  const float* r0 = t.texels + size_t(y0) * w;
+  const float* r1 = t.texels + size_t(y1) * w;
+  float t00 = __ldg(r0 + x0), t10 = __ldg(r0 + x1), t01 = __ldg(r1 + x0), t11 = __ldg(r1 + x1);
+  float top = fmaf(t10 - t00, ax, t00);
+  float bot = fmaf(t11 - t01, ax, t01);
+  return fmaf(bot - top, ay, top);
+}
+
+// one vertex of a part from its record (shared memory, 16-byte aligned) and the pattern vertex (q1, q2)
+__device__ __forceinline__ F3 eval_part_vertex(const Params& p, const float4* rec, float q1, float q2)
+{
+  const float4 r0 = rec[0], r1 = rec[1];
+  const float  s = fmaf(q2, r0.z, fmaf(q1, r0.y, r0.x));
+  const float  t = fmaf(q2, r1.y, fmaf(q1, r1.x, r0.w));
+  const float4 a = rec[2], b = rec[3], c = rec[4], d = rec[5], e = rec[6], f = rec[7], g = rec[8], h = rec[9];
+  // c00 = a.xyz, c10 = (a.w,b.x,b.y), c01 = (b.z,b.w,c.x), c20 = (c.y,c.z,c.w), c02 = d.xyz, c11 = (d.w,e.x,e.y),
+  // c30 = (e.z,e.w,f.x), c03 = (f.y,f.z,f.w), c21 = g.xyz, c12 = (g.w,h.x,h.y), scale = h.z, offset = h.w
+  const float st = s * t;
+  F3 A = {fmaf(s, e.z, c.y), fmaf(s, e.w, c.z), fmaf(s, f.x, c.w)};
+  A    = {fmaf(s, A.x, a.w), fmaf(s, A.y, b.x), fmaf(s, A.z, b.y)};
+  F3 B = {fmaf(t, f.y, d.x), fmaf(t, f.z, d.y), fmaf(t, f.w, d.z)};
+  B    = {fmaf(t, B.x, b.z), fmaf(t, B.y, b.w), fmaf(t, B.z, c.x)};
+  F3 C = {fmaf(s, g.x, d.w), fmaf(s, g.y, e.x), fmaf(s, g.z, e.y)};
+  C    = {fmaf(t, g.w, C.x), fmaf(t, h.x, C.y), fmaf(t, h.y, C.z)};
+  F3 pos = {fmaf(st, C.x, fmaf(t, B.x, fmaf(s, A.x, a.x))), fmaf(st, C.y, fmaf(t, B.y, fmaf(s, A.y, a.y))), fmaf(st, C.z, fmaf(t, B.z, fmaf(s, A.z, a.z)))};
+  const int texture = __float_as_int(r1.w);
+  if(texture >= 0)
+  {
+    const float4 n0 = rec[10], n1 = rec[11], n2 = rec[12], n3 = rec[13];
+    // n0 = n0.xyz, dn1 = (n0.w,n1.x,n1.y), dn2 = (n1.z,n1.w,n2.x), tu = (n2.y,n2.z,n2.w), tv = n3.xyz
+    F3    n  = {fmaf(t, n1.z, fmaf(s, n0.w, n0.x)), fmaf(t, n1.w, fmaf(s, n1.x, n0.y)), fmaf(t, n2.x, fmaf(s, n1.y, n0.z))};
+    float tu = fmaf(t, n2.w, fmaf(s, n2.z, n2.y));
+    float tv = fmaf(t, n3.z, fmaf(s, n3.y, n3.x));
+    float hgt = fmaf(sample_displacement_fast(p.textures[texture], tu, tv), h.z, h.w);
+    float k  = hgt * rsqrtf(dot3(n, n));
+    pos      = fma3(n, k, pos);
+  }
+  if(flag_animation(p))
+    pos = ripple_deform(p.view[0], pos, __float_as_uint(rec[14].x), rec[13].w);
+  return pos;
 }
 
 }  // namespace tc

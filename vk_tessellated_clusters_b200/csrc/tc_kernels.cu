@@ -1279,34 +1279,59 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
 
 // ============================================================================================================
 // triangle_tess_template_instantiate + BUILD_SETUP_BUILD_BLAS
+//
+// Persistent warps; a tile is 32 consecutive parts handled by ONE warp with no CTA-level barrier:
+//   1. lane = part: load record, table entry; warp scan of (numVertices, CLAS bytes); decoupled look-back gives the
+//      tile's base offsets in canonical (part) order; overflow test; instantiate records written with 128-bit stores.
+//   2. lane = part: fold everything constant per part into a 60-word record in shared memory (build_part_record).
+//   3. lane = vertex: the tile's vertices form one contiguous run of genVertices; iteration i generates vertices
+//      [32i, 32i+32) -- perfectly balanced regardless of the parts' sizes.  The owning part of each lane is found with
+//      a start-bit mask + popc (no search).  Records are read with broadcast 128-bit shared loads.
+//   4. vertices are staged in shared memory (4 iterations = 128 vertices) and flushed as aligned 128-bit stores.
 // ============================================================================================================
 
-constexpr int INST_THREADS = 128;               // one part per thread
-constexpr int INST_STAGE_VERTS = 3072;          // staging window (vertices) for coalesced 128-bit stores
-constexpr int INST_STAGE_FLOATS = INST_STAGE_VERTS * 3 + 4;
+constexpr int INST_WARPS       = 8;
+constexpr int INST_THREADS     = INST_WARPS * 32;
+constexpr int INST_STAGE_ITERS = 4;
+constexpr int INST_STAGE_WORDS = INST_STAGE_ITERS * 96 + 4;
+constexpr int INST_WARP_WORDS  = 32 * TC_REC_WORDS + INST_STAGE_WORDS;  // 2308 words = 9232 B per warp
 
-struct InstShared
+__device__ __forceinline__ uint32_t lanemask_le()
 {
-  float    stage[INST_STAGE_FLOATS];
-  uint32_t warpV[INST_THREADS / 32];
-  unsigned long long warpD[INST_THREADS / 32];
-  uint32_t tile;
-  uint32_t tileVertexBase;      // absolute vertex offset of the tile
-  unsigned long long tileDataBase;
-  uint32_t tileWritten;         // vertices of successful parts in the tile (they form a prefix)
-  uint32_t succ, totalTris;
-};
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+  return m;
+}
 
-__global__ void __launch_bounds__(INST_THREADS) k_instantiate(Params p, const uint32_t* epochCounter)
+__device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint32_t shift, uint32_t nFloats, uint32_t lane)
 {
-  __shared__ __align__(16) InstShared sh;
+  const uint32_t head = min(nFloats, (4u - shift) & 3u);
+  if(lane < head)
+    dst[lane] = stage[shift + lane];
+  const uint32_t bodyVec = (nFloats - head) >> 2;
+  const float4*  s4 = reinterpret_cast<const float4*>(stage + shift + head);
+  float4*        d4 = reinterpret_cast<float4*>(dst + head);
+  for(uint32_t i = lane; i < bodyVec; i += 32)
+    __stcs(d4 + i, s4[i]);
+  const uint32_t tailStart = head + (bodyVec << 2);
+  if(lane < nFloats - tailStart)
+    dst[tailStart + lane] = stage[shift + tailStart + lane];
+}
+
+__global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const uint32_t* epochCounter)
+{
+  extern __shared__ __align__(16) float instSmem[];
+  __shared__ uint32_t shSucc, shTris;
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  float* recBase = instSmem + size_t(warp) * INST_WARP_WORDS;
+  float* stage   = recBase + 32 * TC_REC_WORDS;
+
   const uint32_t epoch = *epochCounter + SLOT_INSTANTIATE;
   tc_SceneBuilding* b  = p.build;
   FrameState*       st = p.state;
   LookbackDesc*     descs = reinterpret_cast<LookbackDesc*>(p.lookback);
   const uint32_t numParts = st->numParts;
-  const uint32_t numTiles = (numParts + INST_THREADS - 1) / INST_THREADS;
+  const uint32_t numTiles = (numParts + 31) / 32;
   // bases: constant during the kernel (written back by the last CTA only)
   const uint32_t baseVertex = b->genVertexCounter, baseGen = b->genClusterCounter, baseTemp = st->tempAfterClassify;
   const unsigned long long baseData = b->genClusterDataCounter;
@@ -1320,35 +1345,35 @@ __global__ void __launch_bounds__(INST_THREADS) k_instantiate(Params p, const ui
 
   if(threadIdx.x == 0)
   {
-    sh.succ = 0;
-    sh.totalTris = 0;
+    shSucc = 0;
+    shTris = 0;
   }
+  uint32_t accSucc = 0, accTris = 0;  // per-warp statistics, folded once at the end
 
   while(true)
   {
-    __syncthreads();
-    if(threadIdx.x == 0)
-      sh.tile = atomicAdd(&st->ticket[SLOT_INSTANTIATE], 1u);
-    __syncthreads();
-    const uint32_t tile = sh.tile;
+    uint32_t tile = 0;
+    if(lane == 0)
+      tile = atomicAdd(&st->ticket[SLOT_INSTANTIATE], 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
     if(tile >= numTiles)
       break;
 
-    const uint32_t partIndex = tile * INST_THREADS + threadIdx.x;
+    // ---------------- 1. lane = part ----------------
+    const uint32_t partIndex = tile * 32 + lane;
     const bool     valid     = partIndex < numParts;
     uint32_t instanceID = 0, clusterID = 0, vtxEnc[3] = {0, 0, 0}, triCfg = 0;
     uint32_t numVertices = 0, numTriangles = 0, firstVertex = 0, dataSize = 0;
     if(valid)
     {
       const uint2* src = reinterpret_cast<const uint2*>(&partTriangles[partIndex]);
-      uint2 a = src[0], c = src[1], d = src[2];
+      uint2 a = __ldcs(src), c = __ldcs(src + 1), d = __ldcs(src + 2);
       instanceID = a.x; clusterID = a.y; vtxEnc[0] = c.x; vtxEnc[1] = c.y; vtxEnc[2] = d.x; triCfg = d.y;
       tc_TessTableEntry e = tess_entry(p, triCfg >> 16);
       numVertices = e.numVertices; numTriangles = e.numTriangles; firstVertex = e.firstVertex;
       dataSize    = __ldg(&p.tblTemplSize[tess_configIndex(triCfg >> 16) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1)]);
     }
-    // block scan of (numVertices, dataSize)
-    uint32_t incV = warp_inclusive_add(numVertices);
+    const uint32_t incV = warp_inclusive_add(numVertices);
     unsigned long long incD = dataSize;
 #pragma unroll
     for(int dlt = 1; dlt < 32; dlt <<= 1)
@@ -1357,73 +1382,39 @@ __global__ void __launch_bounds__(INST_THREADS) k_instantiate(Params p, const ui
       if(lane >= dlt)
         incD += n;
     }
-    if(lane == 31)
+    ScanTuple agg;
+    agg.zero();
+    agg.v[0] = __shfl_sync(0xffffffffu, incV, 31);
+    agg.d    = __shfl_sync(0xffffffffu, incD, 31);
+    ScanTuple excl = lookback_exclusive(descs, tile, agg, epoch);
+    if(tile == numTiles - 1 && lane == 0)
     {
-      sh.warpV[warp] = incV;
-      sh.warpD[warp] = incD;
+      ScanTuple tot = excl;
+      tot.add(agg);
+      st_tuple(reinterpret_cast<ScanTuple*>(&descs[numTiles].aggregate), tot);
     }
-    __syncthreads();
-    if(warp == 0)
-    {
-      ScanTuple agg;
-      agg.zero();
-      for(int w = 0; w < INST_THREADS / 32; w++)
-      {
-        agg.v[0] += sh.warpV[w];
-        agg.d += sh.warpD[w];
-      }
-      ScanTuple excl = lookback_exclusive(descs, tile, agg, epoch);
-      if(lane == 0)
-      {
-        sh.tileVertexBase = baseVertex + excl.v[0];
-        sh.tileDataBase   = baseData + excl.d;
-        if(tile == numTiles - 1)
-        {
-          excl.add(agg);
-          st_tuple(reinterpret_cast<ScanTuple*>(&descs[numTiles].aggregate), excl);
-        }
-      }
-    }
-    __syncthreads();
-    uint32_t relV = incV - numVertices;
-    unsigned long long relD = incD - dataSize;
-    for(uint32_t w = 0; w < warp; w++)
-    {
-      relV += sh.warpV[w];
-      relD += sh.warpD[w];
-    }
-    const uint32_t tileVertexBase = sh.tileVertexBase;
-    const uint32_t vertexOffset   = tileVertexBase + relV;
-    const unsigned long long dataOffset = sh.tileDataBase + relD;
+    const uint32_t startV         = incV - numVertices;  // tile-relative first vertex of this part
+    const uint32_t tileVertexBase = baseVertex + excl.v[0];
+    const uint32_t vertexOffset   = tileVertexBase + startV;
+    const unsigned long long dataOffset = baseData + excl.d + (incD - dataSize);
     const uint32_t genOffset      = baseGen + partIndex;
-    bool ok = valid && !((vertexOffset + numVertices > p.maxGenVertices) || (genOffset + 1 > p.maxGenClusters) || (dataOffset + dataSize > p.maxGenDataBytes));
+    const bool ok = valid && !((vertexOffset + numVertices > p.maxGenVertices) || (genOffset + 1 > p.maxGenClusters) || (dataOffset + dataSize > p.maxGenDataBytes));
 
-    // successful parts are a prefix of the tile: the tile's written vertex count is the end of the last good part
-    if(threadIdx.x == 0)
-      sh.tileWritten = 0;
-    __syncthreads();
-    if(ok)
-      atomicMax(&sh.tileWritten, relV + numVertices);
-    uint32_t okVote = __ballot_sync(0xffffffffu, ok);
-    uint32_t trisW  = warp_sum(ok ? numTriangles : 0);
-    if(lane == 0)
-    {
-      if(okVote) atomicAdd(&sh.succ, __popc(okVote));
-      if(trisW) atomicAdd(&sh.totalTris, trisW);
-    }
+    const uint32_t okVote = __ballot_sync(0xffffffffu, ok);
+    accSucc += __popc(okVote);
+    accTris += warp_sum(ok ? numTriangles : 0);
+    // successful parts are a prefix of the part list, hence of the tile
+    const uint32_t numOk   = __popc(okVote);
+    const uint32_t written = numOk ? __shfl_sync(0xffffffffu, incV, numOk - 1) : 0;
 
-    BaseTriangle       bt;
-    DisplacementConsts dc{0.f, 0.f, -1};
-    float              geoSize = 1.0f;
-    const bool         flipped = (triCfg >> 16) & TC_CONFIG_FLIPPED_BIT;
     if(ok)
-    {  // records (:171-203)
+    {  // records (:171-203) + per-part constants
       const uint32_t cfgIdx     = tess_configIndex(triCfg >> 16) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1);
       const uint32_t tempOffset = baseTemp + partIndex;
       const unsigned long long templAddr = __ldg(reinterpret_cast<const unsigned long long*>(p.tblTemplAddr) + cfgIdx);
       const unsigned long long vaddr     = genVerticesAddr + (unsigned long long)(uint32_t)(vertexOffset * 4u * 3u);
-      tempInstantiations[size_t(tempOffset) * 2 + 0] = make_uint4(partIndex | (TC_RT_CLUSTER_MODE_SINGLE_TESSELLATED << 30), 0u, uint32_t(templAddr), uint32_t(templAddr >> 32));
-      tempInstantiations[size_t(tempOffset) * 2 + 1] = make_uint4(uint32_t(vaddr), uint32_t(vaddr >> 32), 12u, 0u);
+      __stcs(&tempInstantiations[size_t(tempOffset) * 2 + 0], make_uint4(partIndex | (TC_RT_CLUSTER_MODE_SINGLE_TESSELLATED << 30), 0u, uint32_t(templAddr), uint32_t(templAddr >> 32)));
+      __stcs(&tempInstantiations[size_t(tempOffset) * 2 + 1], make_uint4(uint32_t(vaddr), uint32_t(vaddr >> 32), 12u, 0u));
       tempInstanceIDs[tempOffset]      = instanceID;
       tempClusterAddresses[tempOffset] = genClusterData + dataOffset;
       if(p.driverStandin)
@@ -1432,53 +1423,58 @@ __global__ void __launch_bounds__(INST_THREADS) k_instantiate(Params p, const ui
       const tc_RenderInstance& inst = p.instances[instanceID];
       const uint4 ch = __ldg(reinterpret_cast<const uint4*>(inst.clusters) + clusterID);
       const uint8_t* lt = reinterpret_cast<const uint8_t*>(inst.clusterLocalTriangles) + ch.w + (triCfg & 0xFFFF) * 3;
-      setup_base_triangle(p, inst, ch.z, __ldg(lt), __ldg(lt + 1), __ldg(lt + 2), vtxEnc, bt);
-      dc      = displacement_consts(p, inst);
-      geoSize = inst.geoHi[3];
+      build_part_record(p, inst, instanceID, ch.z, __ldg(lt), __ldg(lt + 1), __ldg(lt + 2), vtxEnc, ((triCfg >> 16) & TC_CONFIG_FLIPPED_BIT) != 0,
+                        firstVertex, recBase + lane * TC_REC_WORDS);
     }
-    __syncthreads();
-    const uint32_t tileWritten = sh.tileWritten;
+    __syncwarp();
 
-    // vertex generation through a shared staging window, flushed with aligned 128-bit stores
-    uint32_t nextVert = 0;
-    const uint32_t myCount = ok ? numVertices : 0;
-    for(uint32_t winStart = 0; winStart < tileWritten; winStart += INST_STAGE_VERTS)
+    // ---------------- 3./4. lane = vertex ----------------
+    const size_t   tileFloat0 = size_t(tileVertexBase) * 3;
+    const uint32_t shift      = uint32_t(tileFloat0 & 3);  // windows are multiples of 384 floats: same 16-byte phase
+    uint32_t partsBefore = 0;                              // parts whose first vertex lies before the current iteration
+    uint32_t winStart    = 0;                              // first vertex of the current staging window
+    for(uint32_t w0 = 0; w0 < written; w0 += 32)
     {
-      const uint32_t winEnd   = min(winStart + INST_STAGE_VERTS, tileWritten);
-      const size_t   dstFloat = size_t(tileVertexBase + winStart) * 3;  // first float of the window in genVertices
-      const uint32_t shift    = uint32_t(dstFloat & 3);                 // keep smem and global 16-byte phases equal
-      while(nextVert < myCount && relV + nextVert < winEnd)
+      const uint32_t t = w0 + lane;
+      // start-bit mask of the parts that begin inside [w0, w0+32)
+      const uint32_t rel       = startV - w0;
+      const uint32_t startBits = __reduce_or_sync(0xffffffffu, (ok && rel < 32u) ? (1u << rel) : 0u);
+      const uint32_t part      = partsBefore + __popc(startBits & lanemask_le()) - 1u;
+      partsBefore += __popc(startBits);
+      const uint32_t partStart = __shfl_sync(0xffffffffu, startV, part & 31u);
+      if(t < written)
       {
-        F3 o = generate_vertex(p, bt, dc, __ldg(&p.tblVertices[firstVertex + nextVert]), flipped, instanceID, geoSize);
-        uint32_t s = shift + (relV + nextVert - winStart) * 3;
-        sh.stage[s + 0] = o.x; sh.stage[s + 1] = o.y; sh.stage[s + 2] = o.z;
-        nextVert++;
+        const float4*  rec = reinterpret_cast<const float4*>(recBase + part * TC_REC_WORDS);
+        const uint32_t fv  = __float_as_uint(rec[1].z);
+        const float2   q   = __ldg(&p.tblVerticesF[fv + (t - partStart)]);
+        F3 o = eval_part_vertex(p, rec, q.x, q.y);
+        float* sdst = stage + shift + (t - winStart) * 3;
+        sdst[0] = o.x; sdst[1] = o.y; sdst[2] = o.z;
       }
-      __syncthreads();
-      const uint32_t nFloats = (winEnd - winStart) * 3;
-      float*         dst     = genVertices + dstFloat;
-      // head (to 16-byte alignment), body (float4), tail
-      const uint32_t head = min(nFloats, (4u - shift) & 3u);
-      if(threadIdx.x < head)
-        dst[threadIdx.x] = sh.stage[shift + threadIdx.x];
-      const uint32_t bodyVec = (nFloats - head) / 4;
-      const float4*  s4 = reinterpret_cast<const float4*>(&sh.stage[shift + head]);
-      float4*        d4 = reinterpret_cast<float4*>(dst + head);
-      for(uint32_t i = threadIdx.x; i < bodyVec; i += INST_THREADS)
-        __stcs(d4 + i, s4[i]);
-      const uint32_t tailStart = head + bodyVec * 4;
-      if(threadIdx.x < nFloats - tailStart)
-        dst[tailStart + threadIdx.x] = sh.stage[shift + tailStart + threadIdx.x];
-      __syncthreads();
+      const bool windowFull = (w0 + 32 - winStart) == INST_STAGE_ITERS * 32;
+      if(windowFull || w0 + 32 >= written)
+      {
+        __syncwarp();
+        const uint32_t winEnd = min(w0 + 32, written);
+        flush_stage(stage, genVertices + tileFloat0 + size_t(winStart) * 3, shift, (winEnd - winStart) * 3, lane);
+        __syncwarp();
+        winStart = w0 + 32;
+      }
     }
+    __syncwarp();
   }
 
   // ---------------- epilogue: counters + BUILD_SETUP_BUILD_BLAS (build_setup.comp.glsl:191-235) ----------------
+  if(lane == 0)
+  {
+    if(accSucc) atomicAdd(&shSucc, accSucc);
+    if(accTris) atomicAdd(&shTris, accTris);
+  }
   __syncthreads();
   if(threadIdx.x == 0)
   {
-    if(sh.succ) atomicAdd(&b->tempInstantiateCounter, sh.succ);
-    if(sh.totalTris) atomicAdd(&p.readback->numTotalTriangles, sh.totalTris);
+    if(shSucc) atomicAdd(&b->tempInstantiateCounter, shSucc);
+    if(shTris) atomicAdd(&p.readback->numTotalTriangles, shTris);
     __threadfence();
     uint32_t done = atomicAdd(&st->done[SLOT_INSTANTIATE], 1u);
     if(done == gridDim.x - 1)
@@ -1714,6 +1710,8 @@ __global__ void k_flush_l2(float4* buf, size_t n)
 // launch wrappers
 // ============================================================================================================
 
+size_t instantiate_smem_bytes() { return size_t(INST_WARPS) * INST_WARP_WORDS * 4; }
+
 size_t classify_smem_bytes(uint32_t clusterVertices, uint32_t clusterTriangles)
 {
   return size_t(CLASSIFY_WARPS) * (size_t(clusterVertices) * 7 + size_t(clusterTriangles) * 3) * 4;
@@ -1726,7 +1724,9 @@ int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, Kerne
     return -1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->classify, k_cluster_classify, CLASSIFY_THREADS, smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->split, k_triangle_split, SPLIT_THREADS, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->instantiate, k_instantiate, INST_THREADS, 0);
+  if(cudaFuncSetAttribute(k_instantiate, cudaFuncAttributeMaxDynamicSharedMemorySize, int(instantiate_smem_bytes())) != cudaSuccess)
+    return -1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->instantiate, k_instantiate, INST_THREADS, instantiate_smem_bytes());
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1734,7 +1734,7 @@ uint32_t lookback_tiles_needed(uint32_t maxVisible, uint32_t maxSplit, uint32_t 
 {
   uint32_t a = (maxVisible + CLASSIFY_WARPS - 1) / CLASSIFY_WARPS;
   uint32_t b = (maxSplit + SPLIT_THREADS - 1) / SPLIT_THREADS;
-  uint32_t c = (maxPart + INST_THREADS - 1) / INST_THREADS;
+  uint32_t c = (maxPart + 31) / 32;  // instantiate tiles are one warp = 32 parts
   uint32_t m = a > b ? a : b;
   m          = m > c ? m : c;
   return m + 2;  // +1: slot that carries the grand total
@@ -1767,7 +1767,7 @@ void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32
 }
 void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s)
 {
-  k_instantiate<<<grid, INST_THREADS, 0, s>>>(p, epochCounter);
+  k_instantiate<<<grid, INST_THREADS, instantiate_smem_bytes(), s>>>(p, epochCounter);
 }
 void launch_blas(const Params& p, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s)
 {
