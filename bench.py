@@ -198,6 +198,10 @@ def main():
         return gathered
 
     use_graph = (world == 1) and not args.no_graph
+    # clocks are sampled from before the warm-up to the end of the measurements (nvidia-smi takes ~0.5 s to start)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.6)
     # warm-up (also builds the graph)
     for _ in range(args.warmup):
         one_frame(use_graph)
@@ -207,11 +211,9 @@ def main():
     clusters_local = int(rb["numBlasClusters"])
 
     # ---- timed region: K frames, device events, L2 flushed between frames (outside the events) ----
-    sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
-    sampler.start()
     frame_ms = []
     gathered = None
     if world == 1:
@@ -240,7 +242,6 @@ def main():
         total_ms = float(t.item())
         dist.barrier()
         torch.cuda.synchronize()
-    clocks = sampler.stop()
 
     if world > 1:
         tot = shard[0].global_totals(gathered)
@@ -262,6 +263,13 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+
+    # keep the GPU busy a little longer so the 100 ms sampler sees clocks under load, then stop it
+    t_end = time.perf_counter() + 0.5
+    while time.perf_counter() < t_end:
+        one_frame(False)
+    gpu.sync()
+    clocks = sampler.stop()
 
     line = None
     if rank == 0:

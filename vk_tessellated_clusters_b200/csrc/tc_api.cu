@@ -67,6 +67,7 @@ struct tc_context
   tc::FrameState*   dState     = nullptr;
   uint32_t*         dEpoch     = nullptr;
   void*             dLookback  = nullptr;
+  void*             dLookback16 = nullptr;
   FrameStaging*     dFrame     = nullptr;
   FrameStaging*     hFrame     = nullptr;  // pinned
   tc_shard_counts*  dShardCounts = nullptr;
@@ -85,6 +86,8 @@ struct tc_context
   tc_global_blas_range* globalRanges = nullptr;
   std::vector<DeviceGeometry> geoms;
   std::vector<void*>          textures;
+  std::vector<cudaArray_t>    textureArrays;
+  std::vector<cudaTextureObject_t> textureObjects;
   uint32_t numInstances = 0, totalClusters = 0;
 
   // table
@@ -150,6 +153,12 @@ void free_scene(tc_context* c)
   for(void* t : c->textures)
     dfree(t);
   c->textures.clear();
+  for(cudaTextureObject_t t : c->textureObjects)
+    cudaDestroyTextureObject(t);
+  c->textureObjects.clear();
+  for(cudaArray_t a : c->textureArrays)
+    cudaFreeArray(a);
+  c->textureArrays.clear();
   dfree(c->instanceStates); dfree(c->blasBuildInfos); dfree(c->blasBuildSizes); dfree(c->basicClusterSizes);
   dfree(c->dInstances); dfree(c->dClusterPrefix); dfree(c->segLo); dfree(c->rankBase); dfree(c->globalRanges);
   c->globalRanges = nullptr;
@@ -236,6 +245,7 @@ void fill_params(tc_context* c)
   p.totalClusters      = c->totalClusters;
   p.driverStandin      = c->driverStandin;
   p.lookback           = c->dLookback;
+  p.lookback16         = reinterpret_cast<uint4*>(c->dLookback16);
   p.segLo              = c->segLo;
   p.rankBase           = c->rankBase;
   p.shardBase          = c->dShardBase;
@@ -406,6 +416,9 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   size_t lbBytes = size_t(tc::lookback_tiles_needed(c->maxVisible, c->maxSplit, c->maxPart)) * tc::lookback_desc_bytes();
   TRY_RC(dalloc(c->dLookback, lbBytes));
   TRY_CUDA(cudaMemset(c->dLookback, 0, lbBytes));
+  size_t lb16Bytes = size_t(tc::lookback16_tiles_needed(c->maxPart)) * 16;
+  TRY_RC(dalloc(c->dLookback16, lb16Bytes));
+  TRY_CUDA(cudaMemset(c->dLookback16, 0, lb16Bytes));
   TRY_CUDA(cudaMemset(c->dEpoch, 0, 16));
   TRY_CUDA(cudaMemset(c->dShardBase, 0, 16));
   TRY_CUDA(cudaMemset(c->dReadback, 0, sizeof(tc_Readback)));
@@ -456,7 +469,7 @@ TC_API void tc_destroy(tc_context* c)
     cudaStreamSynchronize(c->stream);
   drop_graph(c);
   free_scene(c);
-  dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dFrame);
+  dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dFrame);
   dfree(c->dShardCounts); dfree(c->dShardBase);
   if(c->hFrame)
     cudaFreeHost(c->hFrame);
@@ -626,7 +639,25 @@ TC_API int tc_set_scene(tc_context* c, const tc_geometry* geoms, uint32_t numGeo
       return rc;
     c->textures.push_back(d);
     CUDA_TRY(cudaMemcpy(d, textures[t].texels, bytes, cudaMemcpyHostToDevice));
-    c->params.textures[t] = tc::DeviceTexture{reinterpret_cast<const float*>(d), textures[t].width, textures[t].height};
+    // gather view: same texels in a 2D array, point sampled, repeat addressing, normalised coordinates
+    cudaArray_t           arr  = nullptr;
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+    CUDA_TRY(cudaMallocArray(&arr, &desc, textures[t].width, textures[t].height, cudaArrayTextureGather));
+    c->textureArrays.push_back(arr);
+    CUDA_TRY(cudaMemcpy2DToArray(arr, 0, 0, textures[t].texels, size_t(textures[t].width) * 4, size_t(textures[t].width) * 4, textures[t].height, cudaMemcpyHostToDevice));
+    cudaResourceDesc rd{};
+    rd.resType         = cudaResourceTypeArray;
+    rd.res.array.array = arr;
+    cudaTextureDesc td{};
+    td.addressMode[0]   = cudaAddressModeWrap;
+    td.addressMode[1]   = cudaAddressModeWrap;
+    td.filterMode       = cudaFilterModePoint;
+    td.readMode         = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    cudaTextureObject_t obj = 0;
+    CUDA_TRY(cudaCreateTextureObject(&obj, &rd, &td, nullptr));
+    c->textureObjects.push_back(obj);
+    c->params.textures[t] = tc::DeviceTexture{reinterpret_cast<const float*>(d), obj, textures[t].width, textures[t].height};
   }
   c->sceneSet = true;
   fill_params(c);

@@ -20,8 +20,9 @@ namespace tc {
 
 struct DeviceTexture
 {
-  const float* texels;
-  uint32_t     width, height;
+  const float*        texels;  // linear copy (reference-formulation sampler)
+  cudaTextureObject_t gather;  // same texels as a point-sampled, wrap-addressed 2D array for tex2Dgather
+  uint32_t            width, height;
 };
 
 #define TC_MAX_TEXTURES 16
@@ -40,7 +41,9 @@ struct FrameState
   uint32_t numPartSegs;
   uint32_t splitPassesLeft;
   uint32_t hiAfterClassify;  // transient (back) side of the dual counter, constant during split
-  uint32_t pad[5];
+  uint32_t instTotalV;       // grand totals of the instantiate scan (written by the warp that owns the last tile)
+  uint32_t pad[4];
+  unsigned long long instTotalD;
   // aggregated stats kept as plain counters and folded into Readback by the setup steps
   unsigned long long genActualDatas;
 };
@@ -77,6 +80,7 @@ struct Params
   uint32_t epoch;  // look-back flag epoch of this launch (set per kernel by the host)
   // look-back descriptors
   void*    lookback;
+  uint4*   lookback16;  // 16-byte (flag, value) descriptors of the instantiate scan
   // blas helpers
   uint32_t* segLo;     // [TC_MAX_SEGMENTS+1][numInstances]
   uint32_t* rankBase;  // [TC_MAX_SEGMENTS+1][numInstances]
@@ -394,6 +398,86 @@ __device__ __forceinline__ ScanTuple lookback_exclusive(LookbackDesc* descs, uin
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// 16-byte decoupled look-back: {flag, v, d.lo, d.hi} travels as ONE 128-bit L2 transaction (the CUB "TxnWord"
+// technique), so no acquire/release fences -- and therefore no CCTL.IVALL L1 invalidations -- are needed.
+// flag = epoch << 2 | state (1: value is the tile aggregate, 2: value is the inclusive prefix).
+// ------------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint4 ld_desc16(const uint4* p)
+{
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_desc16(uint4* p, uint4 v)
+{
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Called by one full warp.  Returns the exclusive prefix (v, d) of all earlier tiles in every lane.
+__device__ __forceinline__ void lookback16_exclusive(uint4* descs, uint32_t tile, uint32_t aggV, unsigned long long aggD, uint32_t epoch, uint32_t& exclV,
+                                                     unsigned long long& exclD)
+{
+  const uint32_t lane = lane_id();
+  const uint32_t AGG = (epoch << 2) | 1u, INC = (epoch << 2) | 2u;
+  exclV = 0;
+  exclD = 0;
+  if(tile == 0)
+  {
+    if(lane == 0)
+      st_desc16(&descs[0], make_uint4(INC, aggV, uint32_t(aggD), uint32_t(aggD >> 32)));
+    return;
+  }
+  if(lane == 0)
+    st_desc16(&descs[tile], make_uint4(AGG, aggV, uint32_t(aggD), uint32_t(aggD >> 32)));
+  int32_t base = int32_t(tile) - 1;
+  while(true)
+  {
+    const int32_t t = base - int32_t(lane);
+    uint32_t state = 2, v = 0;
+    unsigned long long d = 0;
+    if(t >= 0)
+    {
+      uint4 w;
+      do
+      {
+        w = ld_desc16(&descs[t]);
+      } while(w.x != AGG && w.x != INC);
+      state = w.x & 3u;
+      v     = w.y;
+      d     = (unsigned long long)w.z | ((unsigned long long)w.w << 32);
+    }
+    const uint32_t incMask  = __ballot_sync(0xffffffffu, state == 2);
+    const uint32_t firstInc = incMask ? (__ffs(incMask) - 1) : 32;
+    if(lane > firstInc)
+    {
+      v = 0;
+      d = 0;
+    }
+    exclV += __reduce_add_sync(0xffffffffu, v);
+#pragma unroll
+    for(int k = 16; k > 0; k >>= 1)
+      d += __shfl_xor_sync(0xffffffffu, d, k);
+    exclD += d;
+    if(incMask)
+      break;
+    base -= 32;
+  }
+  if(lane == 0)
+  {
+    const unsigned long long incD = exclD + aggD;
+    st_desc16(&descs[tile], make_uint4(INC, exclV + aggV, uint32_t(incD), uint32_t(incD >> 32)));
+  }
+}
+
+__device__ __forceinline__ float fast_rsqrt(float x)
+{
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // FAST vertex generation (displacement.glsl + the per-vertex body of instantiate / 2X mini)
 // ------------------------------------------------------------------------------------------------------------
 
@@ -519,8 +603,9 @@ __device__ __forceinline__ F3 eval_pn(const BaseTriangle& b, float u, float v, f
 //   words 8..37  position polynomial in the power basis, P = sum c_jk s^j t^k (10 x float3), converted from the PN
 //                control net of displacement.glsl:47-79 (9 FMA per component instead of 44 mul/add)
 //   words 38,39  displacement scale / offset
-//   words 40..48 normal n0, n1-n0, n2-n0     words 49..54 texcoord u0,du1,du2,v0,dv1,dv2
-//   word  55     geometry size (ripple)      word 56 instance id (ripple seed)
+//   words 40..48 normal n0, n1-n0, n2-n0
+//   words 49..54 texel-space texcoord x = u*W-0.5 and y = v*H-0.5 as affine functions of (s,t): X0,X1,X2,Y0,Y1,Y2
+//   words 55,56  1/W, 1/H      words 57,58 cudaTextureObject_t of the gather view      word 59 part index
 // ------------------------------------------------------------------------------------------------------------
 
 #define TC_REC_WORDS 60
@@ -532,7 +617,7 @@ __device__ __forceinline__ void st3(float* dst, F3 v)
 
 __device__ __forceinline__ void build_part_record(const Params& p, const tc_RenderInstance& inst, uint32_t instanceID, uint32_t firstLocalVertex,
                                                   uint32_t i0, uint32_t i1, uint32_t i2, const uint32_t vtxEncoded[3], bool flipped,
-                                                  uint32_t firstPatternVertex, float* rec)
+                                                  uint32_t firstPatternVertex, uint32_t partIndex, float* rec)
 {
   const float* positions = reinterpret_cast<const float*>(inst.positions);
   const float* normals   = reinterpret_cast<const float*>(inst.normals);
@@ -552,9 +637,10 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
     tv[v]  = __ldg(texcoords + size_t(gi[v]) * 2 + 1);
   }
   // corner k has base barycentrics (1-bu-bv, bu, bv); pattern weights (q0,q1,q2), q0 = 1-q1-q2, flipped: q0 <-> q1
-  const int o = flipped ? 1 : 0, a = flipped ? 0 : 1;  // origin corner, corner multiplied by q1
-  rec[0] = bu[o]; rec[1] = bu[a] - bu[o]; rec[2] = bu[2] - bu[o];
-  rec[3] = bv[o]; rec[4] = bv[a] - bv[o]; rec[5] = bv[2] - bv[o];
+  const float buO = flipped ? bu[1] : bu[0], buA = flipped ? bu[0] : bu[1];  // origin corner, corner multiplied by q1
+  const float bvO = flipped ? bv[1] : bv[0], bvA = flipped ? bv[0] : bv[1];
+  rec[0] = buO; rec[1] = buA - buO; rec[2] = bu[2] - buO;
+  rec[3] = bvO; rec[4] = bvA - bvO; rec[5] = bv[2] - bvO;
   reinterpret_cast<uint32_t*>(rec)[6] = firstPatternVertex;
   const int texture = (p.numTextures > 0 && inst.displacementIndex >= 0) ? inst.displacementIndex : -1;
   reinterpret_cast<int*>(rec)[7] = texture;
@@ -598,73 +684,120 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
   rec[38] = inst.displacementScale * p.view[0].displacementScale;
   rec[39] = inst.displacementOffset + p.view[0].displacementOffset;
   st3(rec + 40, nrm[0]); st3(rec + 43, nrm[1] - nrm[0]); st3(rec + 46, nrm[2] - nrm[0]);
-  rec[49] = tu[0]; rec[50] = tu[1] - tu[0]; rec[51] = tu[2] - tu[0];
-  rec[52] = tv[0]; rec[53] = tv[1] - tv[0]; rec[54] = tv[2] - tv[0];
-  rec[55] = inst.geoHi[3];
-  reinterpret_cast<uint32_t*>(rec)[56] = instanceID;
+  float W = 1.0f, H = 1.0f;
+  unsigned long long texObj = 0;
+  if(texture >= 0)
+  {
+    const DeviceTexture& t = p.textures[texture];
+    W      = float(t.width);
+    H      = float(t.height);
+    texObj = t.gather;
+  }
+  rec[49] = fmaf(tu[0], W, -0.5f); rec[50] = (tu[1] - tu[0]) * W; rec[51] = (tu[2] - tu[0]) * W;
+  rec[52] = fmaf(tv[0], H, -0.5f); rec[53] = (tv[1] - tv[0]) * H; rec[54] = (tv[2] - tv[0]) * H;
+  rec[55] = 1.0f / W;
+  rec[56] = 1.0f / H;
+  reinterpret_cast<uint32_t*>(rec)[57] = uint32_t(texObj);
+  reinterpret_cast<uint32_t*>(rec)[58] = uint32_t(texObj >> 32);
+  reinterpret_cast<uint32_t*>(rec)[59] = partIndex;
 }
 
-// floor() and the matching integer without the XU pipe (valid for |x| < 2^22, which texel coordinates satisfy)
-__device__ __forceinline__ float fast_floor(float x, int& xi)
+// floor(x) for |x| < 2^22 without the XU pipe
+__device__ __forceinline__ float fast_floorf(float x)
 {
   const float M = 12582912.0f;  // 1.5 * 2^23
-  float r = __fadd_rn(__fadd_rn(x, M), -M);
-  r       = r > x ? r - 1.0f : r;
-  xi      = __float_as_int(__fadd_rn(r, M)) - 0x4B400000;
-  return r;
+  const float r = __fadd_rn(__fadd_rn(x, M), -M);
+  return r > x ? r - 1.0f : r;
 }
 
-// software sampler, same definition as sample_displacement; power-of-two sizes avoid the integer modulo entirely
-__device__ __forceinline__ float sample_displacement_fast(const DeviceTexture& t, float u, float v)
+// Register image of a part record.
+struct PartCoeffs
 {
-  const int w = int(t.width), h = int(t.height);
-  float x = fmaf(u, float(w), -0.5f);
-  float y = fmaf(v, float(h), -0.5f);
-  if(!(fabsf(x) < 4194304.0f && fabsf(y) < 4194304.0f) || (w & (w - 1)) || (h & (h - 1)))
-    return sample_displacement(t, u, v);
-  int   xi, yi;
-  float ax = x - fast_floor(x, xi), ay = y - fast_floor(y, yi);
-  int   x0 = xi & (w - 1), x1 = (xi + 1) & (w - 1);
-  int   y0 = yi & (h - 1), y1 = (yi + 1) & (h - 1);
-  const float* r0 = t.texels + size_t(y0) * w;
-  const float* r1 = t.texels + size_t(y1) * w;
+  float4 r0, r1;                  // affine (s,t) map, first pattern vertex, texture index
+  float4 a, b, c, d, e, f, g, h;  // position polynomial + displacement scale/offset
+  float4 n0, n1, n2, n3, m;       // normal, texel-space texcoord, 1/W, 1/H, texture object, part index
+};
+
+__device__ __forceinline__ void load_part_coeffs(const float4* rec, PartCoeffs& k, bool displaced)
+{
+  k.r0 = rec[0]; k.r1 = rec[1];
+  k.a = rec[2]; k.b = rec[3]; k.c = rec[4]; k.d = rec[5]; k.e = rec[6]; k.f = rec[7]; k.g = rec[8]; k.h = rec[9];
+  if(displaced)
+  {
+    k.n0 = rec[10]; k.n1 = rec[11]; k.n2 = rec[12]; k.n3 = rec[13]; k.m = rec[14];
+  }
+}
+
+// reference-formulation bilinear/repeat fetch at texel-space coordinates (rare path: huge coordinates)
+static __device__ __noinline__ float sample_texel_space_slow(const float* texels, int w, int h, float x, float y)
+{
+  float fx = floorf(x), fy = floorf(y);
+  float ax = x - fx, ay = y - fy;
+  long long xl = (long long)fx, yl = (long long)fy;
+  int x0 = int(((xl % w) + w) % w), y0 = int(((yl % h) + h) % h);
+  int x1 = x0 + 1 == w ? 0 : x0 + 1, y1 = y0 + 1 == h ? 0 : y0 + 1;
+  const float* r0 = texels + size_t(y0) * w;
+  const float* r1 = texels + size_t(y1) * w;
   float t00 = __ldg(r0 + x0), t10 = __ldg(r0 + x1), t01 = __ldg(r1 + x0), t11 = __ldg(r1 + x1);
   float top = fmaf(t10 - t00, ax, t00);
   float bot = fmaf(t11 - t01, ax, t01);
   return fmaf(bot - top, ay, top);
 }
 
-// one vertex of a part from its record (shared memory, 16-byte aligned) and the pattern vertex (q1, q2)
-__device__ __forceinline__ F3 eval_part_vertex(const Params& p, const float4* rec, float q1, float q2)
+// (takes plain pointers: passing the by-value kernel parameter block to a non-inlined function would copy it to local memory)
+static __device__ __noinline__ F3 ripple_deform_part(const tc_FrameConstants* view, const tc_SceneBuilding* build, const tc_RenderInstance* instances, F3 pos,
+                                                      uint32_t partIndex)
 {
-  const float4 r0 = rec[0], r1 = rec[1];
-  const float  s = fmaf(q2, r0.z, fmaf(q1, r0.y, r0.x));
-  const float  t = fmaf(q2, r1.y, fmaf(q1, r1.x, r0.w));
-  const float4 a = rec[2], b = rec[3], c = rec[4], d = rec[5], e = rec[6], f = rec[7], g = rec[8], h = rec[9];
+  const tc_TessTriangleInfo* parts = reinterpret_cast<const tc_TessTriangleInfo*>(build->partTriangles);
+  const uint32_t instanceID = parts[partIndex].cluster.instanceID;
+  return ripple_deform(view[0], pos, instanceID, instances[instanceID].geoHi[3]);
+}
+
+// one vertex of a part from its coefficients and the pattern vertex (q1, q2)
+__device__ __forceinline__ F3 eval_part_vertex(const Params& p, const PartCoeffs& k, float q1, float q2, bool displaced)
+{
+  const float s = fmaf(q2, k.r0.z, fmaf(q1, k.r0.y, k.r0.x));
+  const float t = fmaf(q2, k.r1.y, fmaf(q1, k.r1.x, k.r0.w));
   // c00 = a.xyz, c10 = (a.w,b.x,b.y), c01 = (b.z,b.w,c.x), c20 = (c.y,c.z,c.w), c02 = d.xyz, c11 = (d.w,e.x,e.y),
   // c30 = (e.z,e.w,f.x), c03 = (f.y,f.z,f.w), c21 = g.xyz, c12 = (g.w,h.x,h.y), scale = h.z, offset = h.w
   const float st = s * t;
-  F3 A = {fmaf(s, e.z, c.y), fmaf(s, e.w, c.z), fmaf(s, f.x, c.w)};
-  A    = {fmaf(s, A.x, a.w), fmaf(s, A.y, b.x), fmaf(s, A.z, b.y)};
-  F3 B = {fmaf(t, f.y, d.x), fmaf(t, f.z, d.y), fmaf(t, f.w, d.z)};
-  B    = {fmaf(t, B.x, b.z), fmaf(t, B.y, b.w), fmaf(t, B.z, c.x)};
-  F3 C = {fmaf(s, g.x, d.w), fmaf(s, g.y, e.x), fmaf(s, g.z, e.y)};
-  C    = {fmaf(t, g.w, C.x), fmaf(t, h.x, C.y), fmaf(t, h.y, C.z)};
-  F3 pos = {fmaf(st, C.x, fmaf(t, B.x, fmaf(s, A.x, a.x))), fmaf(st, C.y, fmaf(t, B.y, fmaf(s, A.y, a.y))), fmaf(st, C.z, fmaf(t, B.z, fmaf(s, A.z, a.z)))};
-  const int texture = __float_as_int(r1.w);
-  if(texture >= 0)
+  F3 A = {fmaf(s, k.e.z, k.c.y), fmaf(s, k.e.w, k.c.z), fmaf(s, k.f.x, k.c.w)};
+  A    = {fmaf(s, A.x, k.a.w), fmaf(s, A.y, k.b.x), fmaf(s, A.z, k.b.y)};
+  F3 B = {fmaf(t, k.f.y, k.d.x), fmaf(t, k.f.z, k.d.y), fmaf(t, k.f.w, k.d.z)};
+  B    = {fmaf(t, B.x, k.b.z), fmaf(t, B.y, k.b.w), fmaf(t, B.z, k.c.x)};
+  F3 C = {fmaf(s, k.g.x, k.d.w), fmaf(s, k.g.y, k.e.x), fmaf(s, k.g.z, k.e.y)};
+  C    = {fmaf(t, k.g.w, C.x), fmaf(t, k.h.x, C.y), fmaf(t, k.h.y, C.z)};
+  F3 pos = {fmaf(st, C.x, fmaf(t, B.x, fmaf(s, A.x, k.a.x))), fmaf(st, C.y, fmaf(t, B.y, fmaf(s, A.y, k.a.y))), fmaf(st, C.z, fmaf(t, B.z, fmaf(s, A.z, k.a.z)))};
+  if(displaced)
   {
-    const float4 n0 = rec[10], n1 = rec[11], n2 = rec[12], n3 = rec[13];
-    // n0 = n0.xyz, dn1 = (n0.w,n1.x,n1.y), dn2 = (n1.z,n1.w,n2.x), tu = (n2.y,n2.z,n2.w), tv = n3.xyz
-    F3    n  = {fmaf(t, n1.z, fmaf(s, n0.w, n0.x)), fmaf(t, n1.w, fmaf(s, n1.x, n0.y)), fmaf(t, n2.x, fmaf(s, n1.y, n0.z))};
-    float tu = fmaf(t, n2.w, fmaf(s, n2.z, n2.y));
-    float tv = fmaf(t, n3.z, fmaf(s, n3.y, n3.x));
-    float hgt = fmaf(sample_displacement_fast(p.textures[texture], tu, tv), h.z, h.w);
-    float k  = hgt * rsqrtf(dot3(n, n));
-    pos      = fma3(n, k, pos);
+    // n0 = n0.xyz, dn1 = (n0.w,n1.x,n1.y), dn2 = (n1.z,n1.w,n2.x), X = (n2.y,n2.z,n2.w), Y = n3.xyz, 1/W = n3.w, 1/H = m.x
+    const F3    n = {fmaf(t, k.n1.z, fmaf(s, k.n0.w, k.n0.x)), fmaf(t, k.n1.w, fmaf(s, k.n1.x, k.n0.y)), fmaf(t, k.n2.x, fmaf(s, k.n1.y, k.n0.z))};
+    const float x = fmaf(t, k.n2.w, fmaf(s, k.n2.z, k.n2.y));
+    const float y = fmaf(t, k.n3.z, fmaf(s, k.n3.y, k.n3.x));
+    float texel;
+    if(fabsf(x) + fabsf(y) < 4194304.0f)
+    {
+      // 2x2 footprint through the texture unit (exact texel values, hardware repeat addressing), weights in fp32.
+      // The gather is aimed at the corner shared by the four texels, so the footprint choice is unambiguous.
+      const float fx = fast_floorf(x), fy = fast_floorf(y);
+      const float ax = x - fx, ay = y - fy;
+      const cudaTextureObject_t tex = (unsigned long long)__float_as_uint(k.m.y) | ((unsigned long long)__float_as_uint(k.m.z) << 32);
+      const float4 g = tex2Dgather<float4>(tex, (fx + 1.0f) * k.n3.w, (fy + 1.0f) * k.m.x, 0);
+      // g = (t01, t11, t10, t00)
+      const float top = fmaf(g.z - g.w, ax, g.w);
+      const float bot = fmaf(g.y - g.x, ax, g.x);
+      texel = fmaf(bot - top, ay, top);
+    }
+    else
+    {
+      const DeviceTexture& dt = p.textures[__float_as_int(k.r1.w)];
+      texel = sample_texel_space_slow(dt.texels, int(dt.width), int(dt.height), x, y);
+    }
+    const float hgt = fmaf(texel, k.h.z, k.h.w);
+    pos = fma3(n, hgt * fast_rsqrt(dot3(n, n)), pos);
   }
   if(flag_animation(p))
-    pos = ripple_deform(p.view[0], pos, __float_as_uint(rec[14].x), rec[13].w);
+    pos = ripple_deform_part(p.view, p.build, p.instances, pos, __float_as_uint(k.m.w));
   return pos;
 }
 

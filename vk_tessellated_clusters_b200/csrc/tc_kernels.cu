@@ -1292,8 +1292,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
 
 constexpr int INST_WARPS       = 8;
 constexpr int INST_THREADS     = INST_WARPS * 32;
-constexpr int INST_STAGE_ITERS = 4;
-constexpr int INST_STAGE_WORDS = INST_STAGE_ITERS * 96 + 4;
+constexpr int INST_ITER_VERTS  = 64;  // two vertices per lane per iteration
+constexpr int INST_STAGE_WORDS = INST_ITER_VERTS * 3 + 4;
 constexpr int INST_WARP_WORDS  = 32 * TC_REC_WORDS + INST_STAGE_WORDS;  // 2308 words = 9232 B per warp
 
 __device__ __forceinline__ uint32_t lanemask_le()
@@ -1329,7 +1329,6 @@ __global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const
   const uint32_t epoch = *epochCounter + SLOT_INSTANTIATE;
   tc_SceneBuilding* b  = p.build;
   FrameState*       st = p.state;
-  LookbackDesc*     descs = reinterpret_cast<LookbackDesc*>(p.lookback);
   const uint32_t numParts = st->numParts;
   const uint32_t numTiles = (numParts + 31) / 32;
   // bases: constant during the kernel (written back by the last CTA only)
@@ -1382,21 +1381,20 @@ __global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const
       if(lane >= dlt)
         incD += n;
     }
-    ScanTuple agg;
-    agg.zero();
-    agg.v[0] = __shfl_sync(0xffffffffu, incV, 31);
-    agg.d    = __shfl_sync(0xffffffffu, incD, 31);
-    ScanTuple excl = lookback_exclusive(descs, tile, agg, epoch);
+    const uint32_t           aggV = __shfl_sync(0xffffffffu, incV, 31);
+    const unsigned long long aggD = __shfl_sync(0xffffffffu, incD, 31);
+    uint32_t           exclV;
+    unsigned long long exclD;
+    lookback16_exclusive(p.lookback16, tile, aggV, aggD, epoch, exclV, exclD);
     if(tile == numTiles - 1 && lane == 0)
     {
-      ScanTuple tot = excl;
-      tot.add(agg);
-      st_tuple(reinterpret_cast<ScanTuple*>(&descs[numTiles].aggregate), tot);
+      st->instTotalV = exclV + aggV;
+      st->instTotalD = exclD + aggD;
     }
     const uint32_t startV         = incV - numVertices;  // tile-relative first vertex of this part
-    const uint32_t tileVertexBase = baseVertex + excl.v[0];
+    const uint32_t tileVertexBase = baseVertex + exclV;
     const uint32_t vertexOffset   = tileVertexBase + startV;
-    const unsigned long long dataOffset = baseData + excl.d + (incD - dataSize);
+    const unsigned long long dataOffset = baseData + exclD + (incD - dataSize);
     const uint32_t genOffset      = baseGen + partIndex;
     const bool ok = valid && !((vertexOffset + numVertices > p.maxGenVertices) || (genOffset + 1 > p.maxGenClusters) || (dataOffset + dataSize > p.maxGenDataBytes));
 
@@ -1424,44 +1422,60 @@ __global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const
       const uint4 ch = __ldg(reinterpret_cast<const uint4*>(inst.clusters) + clusterID);
       const uint8_t* lt = reinterpret_cast<const uint8_t*>(inst.clusterLocalTriangles) + ch.w + (triCfg & 0xFFFF) * 3;
       build_part_record(p, inst, instanceID, ch.z, __ldg(lt), __ldg(lt + 1), __ldg(lt + 2), vtxEnc, ((triCfg >> 16) & TC_CONFIG_FLIPPED_BIT) != 0,
-                        firstVertex, recBase + lane * TC_REC_WORDS);
+                        firstVertex, partIndex, recBase + lane * TC_REC_WORDS);
     }
     __syncwarp();
 
-    // ---------------- 3./4. lane = vertex ----------------
+    // ---------------- 3./4. lane = one slot = two adjacent vertices of ONE part ----------------
+    // Slots are allotted per part (ceil(numVertices / 2)), so a slot never straddles two parts and the loop body has
+    // a single, divergence-free shape; an odd part wastes half a slot.
+    const uint32_t slotCount  = ok ? (numVertices + 1) >> 1 : 0;
+    const uint32_t incS       = warp_inclusive_add(slotCount);
+    const uint32_t startS     = incS - slotCount;
+    const uint32_t totalSlots = __shfl_sync(0xffffffffu, incS, 31);
     const size_t   tileFloat0 = size_t(tileVertexBase) * 3;
-    const uint32_t shift      = uint32_t(tileFloat0 & 3);  // windows are multiples of 384 floats: same 16-byte phase
-    uint32_t partsBefore = 0;                              // parts whose first vertex lies before the current iteration
-    uint32_t winStart    = 0;                              // first vertex of the current staging window
-    for(uint32_t w0 = 0; w0 < written; w0 += 32)
+    uint32_t partsBefore = 0;  // parts whose first slot lies before the current iteration
+    for(uint32_t w0 = 0; w0 < totalSlots; w0 += 32)
     {
-      const uint32_t t = w0 + lane;
-      // start-bit mask of the parts that begin inside [w0, w0+32)
-      const uint32_t rel       = startV - w0;
-      const uint32_t startBits = __reduce_or_sync(0xffffffffu, (ok && rel < 32u) ? (1u << rel) : 0u);
-      const uint32_t part      = partsBefore + __popc(startBits & lanemask_le()) - 1u;
-      partsBefore += __popc(startBits);
-      const uint32_t partStart = __shfl_sync(0xffffffffu, startV, part & 31u);
-      if(t < written)
+      const uint32_t rel   = startS - w0;
+      const uint32_t bits  = __reduce_or_sync(0xffffffffu, (slotCount != 0 && rel < 32u) ? (1u << rel) : 0u);
+      const uint32_t part  = (partsBefore + __popc(bits & lanemask_le()) - 1u) & 31u;
+      partsBefore += __popc(bits);
+      const bool     active = w0 + lane < totalSlots;
+      const uint32_t pStartS = __shfl_sync(0xffffffffu, startS, part);
+      const uint32_t pStartV = __shfl_sync(0xffffffffu, startV, part);
+      const uint32_t pNV     = __shfl_sync(0xffffffffu, numVertices, part);
+      const uint32_t v0      = (w0 + lane - pStartS) * 2;
+      const bool     two     = v0 + 1 < pNV;
+      const uint32_t t0      = pStartV + v0;  // tile-relative index of the slot's first vertex
+      // contiguous vertex range covered by this iteration
+      const uint32_t lastLane = min(31u, totalSlots - w0 - 1u);
+      const uint32_t itStart  = __shfl_sync(0xffffffffu, t0, 0);
+      const uint32_t itEnd    = __shfl_sync(0xffffffffu, t0 + (two ? 2u : 1u), lastLane);
+      const size_t   itFloat0 = tileFloat0 + size_t(itStart) * 3;
+      const uint32_t shift    = uint32_t(itFloat0 & 3);  // keep shared and global 16-byte phases equal
+      if(active)
       {
-        const float4*  rec = reinterpret_cast<const float4*>(recBase + part * TC_REC_WORDS);
-        const uint32_t fv  = __float_as_uint(rec[1].z);
-        const float2   q   = __ldg(&p.tblVerticesF[fv + (t - partStart)]);
-        F3 o = eval_part_vertex(p, rec, q.x, q.y);
-        float* sdst = stage + shift + (t - winStart) * 3;
-        sdst[0] = o.x; sdst[1] = o.y; sdst[2] = o.z;
+        const float4* rec = reinterpret_cast<const float4*>(recBase + part * TC_REC_WORDS);
+        PartCoeffs k;
+        const bool displaced = __float_as_int(rec[1].w) >= 0;
+        load_part_coeffs(rec, k, displaced);
+        const uint32_t fv = __float_as_uint(k.r1.z) + v0;
+        const float2   qa = __ldg(&p.tblVerticesF[fv]);
+        const float2   qb = __ldg(&p.tblVerticesF[fv + (two ? 1u : 0u)]);
+        const F3 oa = eval_part_vertex(p, k, qa.x, qa.y, displaced);
+        const F3 ob = eval_part_vertex(p, k, qb.x, qb.y, displaced);
+        float* sdst = stage + shift + (t0 - itStart) * 3;
+        sdst[0] = oa.x; sdst[1] = oa.y; sdst[2] = oa.z;
+        if(two)
+        {
+          sdst[3] = ob.x; sdst[4] = ob.y; sdst[5] = ob.z;
+        }
       }
-      const bool windowFull = (w0 + 32 - winStart) == INST_STAGE_ITERS * 32;
-      if(windowFull || w0 + 32 >= written)
-      {
-        __syncwarp();
-        const uint32_t winEnd = min(w0 + 32, written);
-        flush_stage(stage, genVertices + tileFloat0 + size_t(winStart) * 3, shift, (winEnd - winStart) * 3, lane);
-        __syncwarp();
-        winStart = w0 + 32;
-      }
+      __syncwarp();
+      flush_stage(stage, genVertices + itFloat0, shift, (itEnd - itStart) * 3, lane);
+      __syncwarp();
     }
-    __syncwarp();
   }
 
   // ---------------- epilogue: counters + BUILD_SETUP_BUILD_BLAS (build_setup.comp.glsl:191-235) ----------------
@@ -1480,12 +1494,10 @@ __global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const
     if(done == gridDim.x - 1)
     {
       __threadfence();
-      ScanTuple tot;
-      tot.zero();
-      if(numTiles > 0)
-        tot = ld_tuple(reinterpret_cast<const ScanTuple*>(&descs[numTiles].aggregate));
-      b->genVertexCounter      = baseVertex + tot.v[0];
-      b->genClusterDataCounter = baseData + tot.d;
+      const uint32_t           totV = numTiles ? *(volatile uint32_t*)&st->instTotalV : 0u;
+      const unsigned long long totD = numTiles ? *(volatile unsigned long long*)&st->instTotalD : 0ull;
+      b->genVertexCounter      = baseVertex + totV;
+      b->genClusterDataCounter = baseData + totD;
       b->genClusterCounter     = baseGen + numParts;
 
       const bool     transient    = flag_transient(p);
@@ -1734,13 +1746,14 @@ uint32_t lookback_tiles_needed(uint32_t maxVisible, uint32_t maxSplit, uint32_t 
 {
   uint32_t a = (maxVisible + CLASSIFY_WARPS - 1) / CLASSIFY_WARPS;
   uint32_t b = (maxSplit + SPLIT_THREADS - 1) / SPLIT_THREADS;
-  uint32_t c = (maxPart + 31) / 32;  // instantiate tiles are one warp = 32 parts
+  uint32_t c = 0;  // the instantiate scan has its own 16-byte descriptors (lookback16_tiles_needed)
   uint32_t m = a > b ? a : b;
   m          = m > c ? m : c;
   return m + 2;  // +1: slot that carries the grand total
 }
 
 size_t lookback_desc_bytes() { return sizeof(LookbackDesc); }
+uint32_t lookback16_tiles_needed(uint32_t maxPart) { return (maxPart + 31) / 32 + 2; }
 size_t frame_state_bytes() { return sizeof(FrameState); }
 
 void launch_frame_setup(const Params& p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter, cudaStream_t s)
