@@ -681,14 +681,14 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
   }
   st3(rec + 8, c00);  st3(rec + 11, c10); st3(rec + 14, c01); st3(rec + 17, c20); st3(rec + 20, c02);
   st3(rec + 23, c11); st3(rec + 26, c30); st3(rec + 29, c03); st3(rec + 32, c21); st3(rec + 35, c12);
-  rec[38] = inst.displacementScale * p.view[0].displacementScale;
-  rec[39] = inst.displacementOffset + p.view[0].displacementOffset;
+  rec[38] = texture >= 0 ? inst.displacementScale * p.view[0].displacementScale : 0.0f;
+  rec[39] = texture >= 0 ? inst.displacementOffset + p.view[0].displacementOffset : 0.0f;
   st3(rec + 40, nrm[0]); st3(rec + 43, nrm[1] - nrm[0]); st3(rec + 46, nrm[2] - nrm[0]);
   float W = 1.0f, H = 1.0f;
   unsigned long long texObj = 0;
-  if(texture >= 0)
+  if(p.numTextures > 0)
   {
-    const DeviceTexture& t = p.textures[texture];
+    const DeviceTexture& t = p.textures[texture >= 0 ? texture : 0];  // undisplaced parts: any valid texture, scale 0
     W      = float(t.width);
     H      = float(t.height);
     texObj = t.gather;
@@ -728,22 +728,6 @@ __device__ __forceinline__ void load_part_coeffs(const float4* rec, PartCoeffs& 
   }
 }
 
-// reference-formulation bilinear/repeat fetch at texel-space coordinates (rare path: huge coordinates)
-static __device__ __noinline__ float sample_texel_space_slow(const float* texels, int w, int h, float x, float y)
-{
-  float fx = floorf(x), fy = floorf(y);
-  float ax = x - fx, ay = y - fy;
-  long long xl = (long long)fx, yl = (long long)fy;
-  int x0 = int(((xl % w) + w) % w), y0 = int(((yl % h) + h) % h);
-  int x1 = x0 + 1 == w ? 0 : x0 + 1, y1 = y0 + 1 == h ? 0 : y0 + 1;
-  const float* r0 = texels + size_t(y0) * w;
-  const float* r1 = texels + size_t(y1) * w;
-  float t00 = __ldg(r0 + x0), t10 = __ldg(r0 + x1), t01 = __ldg(r1 + x0), t11 = __ldg(r1 + x1);
-  float top = fmaf(t10 - t00, ax, t00);
-  float bot = fmaf(t11 - t01, ax, t01);
-  return fmaf(bot - top, ay, top);
-}
-
 // (takes plain pointers: passing the by-value kernel parameter block to a non-inlined function would copy it to local memory)
 static __device__ __noinline__ F3 ripple_deform_part(const tc_FrameConstants* view, const tc_SceneBuilding* build, const tc_RenderInstance* instances, F3 pos,
                                                       uint32_t partIndex)
@@ -753,11 +737,9 @@ static __device__ __noinline__ F3 ripple_deform_part(const tc_FrameConstants* vi
   return ripple_deform(view[0], pos, instanceID, instances[instanceID].geoHi[3]);
 }
 
-// one vertex of a part from its coefficients and the pattern vertex (q1, q2)
-__device__ __forceinline__ F3 eval_part_vertex(const Params& p, const PartCoeffs& k, float q1, float q2, bool displaced)
+// position polynomial of one vertex
+__device__ __forceinline__ F3 eval_position(const PartCoeffs& k, float s, float t)
 {
-  const float s = fmaf(q2, k.r0.z, fmaf(q1, k.r0.y, k.r0.x));
-  const float t = fmaf(q2, k.r1.y, fmaf(q1, k.r1.x, k.r0.w));
   // c00 = a.xyz, c10 = (a.w,b.x,b.y), c01 = (b.z,b.w,c.x), c20 = (c.y,c.z,c.w), c02 = d.xyz, c11 = (d.w,e.x,e.y),
   // c30 = (e.z,e.w,f.x), c03 = (f.y,f.z,f.w), c21 = g.xyz, c12 = (g.w,h.x,h.y), scale = h.z, offset = h.w
   const float st = s * t;
@@ -767,38 +749,47 @@ __device__ __forceinline__ F3 eval_part_vertex(const Params& p, const PartCoeffs
   B    = {fmaf(t, B.x, k.b.z), fmaf(t, B.y, k.b.w), fmaf(t, B.z, k.c.x)};
   F3 C = {fmaf(s, k.g.x, k.d.w), fmaf(s, k.g.y, k.e.x), fmaf(s, k.g.z, k.e.y)};
   C    = {fmaf(t, k.g.w, C.x), fmaf(t, k.h.x, C.y), fmaf(t, k.h.y, C.z)};
-  F3 pos = {fmaf(st, C.x, fmaf(t, B.x, fmaf(s, A.x, k.a.x))), fmaf(st, C.y, fmaf(t, B.y, fmaf(s, A.y, k.a.y))), fmaf(st, C.z, fmaf(t, B.z, fmaf(s, A.z, k.a.z)))};
-  if(displaced)
+  return {fmaf(st, C.x, fmaf(t, B.x, fmaf(s, A.x, k.a.x))), fmaf(st, C.y, fmaf(t, B.y, fmaf(s, A.y, k.a.y))), fmaf(st, C.z, fmaf(t, B.z, fmaf(s, A.z, k.a.z)))};
+}
+
+// Two vertices of ONE part from its coefficients and the pattern vertices qa, qb.  Written in three phases so that both
+// texture gathers are in flight while the position polynomials are evaluated.  Branch-free: parts without displacement
+// carry scale = offset = 0 and a valid texture object (build_part_record), so the displaced variant needs no test.
+template <bool DISPLACED>
+__device__ __forceinline__ void eval_part_pair(const PartCoeffs& k, float2 qa, float2 qb, F3& oa, F3& ob)
+{
+  const float sa = fmaf(qa.y, k.r0.z, fmaf(qa.x, k.r0.y, k.r0.x)), ta = fmaf(qa.y, k.r1.y, fmaf(qa.x, k.r1.x, k.r0.w));
+  const float sb = fmaf(qb.y, k.r0.z, fmaf(qb.x, k.r0.y, k.r0.x)), tb = fmaf(qb.y, k.r1.y, fmaf(qb.x, k.r1.x, k.r0.w));
+  if(DISPLACED)
   {
-    // n0 = n0.xyz, dn1 = (n0.w,n1.x,n1.y), dn2 = (n1.z,n1.w,n2.x), X = (n2.y,n2.z,n2.w), Y = n3.xyz, 1/W = n3.w, 1/H = m.x
-    const F3    n = {fmaf(t, k.n1.z, fmaf(s, k.n0.w, k.n0.x)), fmaf(t, k.n1.w, fmaf(s, k.n1.x, k.n0.y)), fmaf(t, k.n2.x, fmaf(s, k.n1.y, k.n0.z))};
-    const float x = fmaf(t, k.n2.w, fmaf(s, k.n2.z, k.n2.y));
-    const float y = fmaf(t, k.n3.z, fmaf(s, k.n3.y, k.n3.x));
-    float texel;
-    if(fabsf(x) + fabsf(y) < 4194304.0f)
-    {
-      // 2x2 footprint through the texture unit (exact texel values, hardware repeat addressing), weights in fp32.
-      // The gather is aimed at the corner shared by the four texels, so the footprint choice is unambiguous.
-      const float fx = fast_floorf(x), fy = fast_floorf(y);
-      const float ax = x - fx, ay = y - fy;
-      const cudaTextureObject_t tex = (unsigned long long)__float_as_uint(k.m.y) | ((unsigned long long)__float_as_uint(k.m.z) << 32);
-      const float4 g = tex2Dgather<float4>(tex, (fx + 1.0f) * k.n3.w, (fy + 1.0f) * k.m.x, 0);
-      // g = (t01, t11, t10, t00)
-      const float top = fmaf(g.z - g.w, ax, g.w);
-      const float bot = fmaf(g.y - g.x, ax, g.x);
-      texel = fmaf(bot - top, ay, top);
-    }
-    else
-    {
-      const DeviceTexture& dt = p.textures[__float_as_int(k.r1.w)];
-      texel = sample_texel_space_slow(dt.texels, int(dt.width), int(dt.height), x, y);
-    }
-    const float hgt = fmaf(texel, k.h.z, k.h.w);
-    pos = fma3(n, hgt * fast_rsqrt(dot3(n, n)), pos);
+    // X = (n2.y,n2.z,n2.w), Y = n3.xyz, 1/W = n3.w, 1/H = m.x.  The 2x2 footprint comes through the texture unit (exact
+    // texel values, hardware repeat addressing) aimed at the corner shared by the four texels, so the footprint choice
+    // is unambiguous; the bilinear weights are computed here in fp32 (same definition as the CPU oracle's sampler).
+    const cudaTextureObject_t tex = (unsigned long long)__float_as_uint(k.m.y) | ((unsigned long long)__float_as_uint(k.m.z) << 32);
+    const float xa = fmaf(ta, k.n2.w, fmaf(sa, k.n2.z, k.n2.y)), ya = fmaf(ta, k.n3.z, fmaf(sa, k.n3.y, k.n3.x));
+    const float xb = fmaf(tb, k.n2.w, fmaf(sb, k.n2.z, k.n2.y)), yb = fmaf(tb, k.n3.z, fmaf(sb, k.n3.y, k.n3.x));
+    const float fxa = floorf(xa), fya = floorf(ya), fxb = floorf(xb), fyb = floorf(yb);
+    const float4 ga = tex2Dgather<float4>(tex, (fxa + 1.0f) * k.n3.w, (fya + 1.0f) * k.m.x, 0);  // (t01, t11, t10, t00)
+    const float4 gb = tex2Dgather<float4>(tex, (fxb + 1.0f) * k.n3.w, (fyb + 1.0f) * k.m.x, 0);
+    oa = eval_position(k, sa, ta);
+    ob = eval_position(k, sb, tb);
+    // n0 = n0.xyz, dn1 = (n0.w,n1.x,n1.y), dn2 = (n1.z,n1.w,n2.x)
+    const F3 na = {fmaf(ta, k.n1.z, fmaf(sa, k.n0.w, k.n0.x)), fmaf(ta, k.n1.w, fmaf(sa, k.n1.x, k.n0.y)), fmaf(ta, k.n2.x, fmaf(sa, k.n1.y, k.n0.z))};
+    const F3 nb = {fmaf(tb, k.n1.z, fmaf(sb, k.n0.w, k.n0.x)), fmaf(tb, k.n1.w, fmaf(sb, k.n1.x, k.n0.y)), fmaf(tb, k.n2.x, fmaf(sb, k.n1.y, k.n0.z))};
+    const float ra = fast_rsqrt(dot3(na, na)), rb = fast_rsqrt(dot3(nb, nb));
+    const float axa = xa - fxa, aya = ya - fya, axb = xb - fxb, ayb = yb - fyb;
+    const float topa = fmaf(ga.z - ga.w, axa, ga.w), bota = fmaf(ga.y - ga.x, axa, ga.x);
+    const float topb = fmaf(gb.z - gb.w, axb, gb.w), botb = fmaf(gb.y - gb.x, axb, gb.x);
+    const float ha = fmaf(fmaf(bota - topa, aya, topa), k.h.z, k.h.w) * ra;
+    const float hb = fmaf(fmaf(botb - topb, ayb, topb), k.h.z, k.h.w) * rb;
+    oa = fma3(na, ha, oa);
+    ob = fma3(nb, hb, ob);
   }
-  if(flag_animation(p))
-    pos = ripple_deform_part(p.view, p.build, p.instances, pos, __float_as_uint(k.m.w));
-  return pos;
+  else
+  {
+    oa = eval_position(k, sa, ta);
+    ob = eval_position(k, sb, tb);
+  }
 }
 
 }  // namespace tc

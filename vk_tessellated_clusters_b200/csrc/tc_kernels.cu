@@ -1303,6 +1303,7 @@ __device__ __forceinline__ uint32_t lanemask_le()
   return m;
 }
 
+// nFloats <= 192 (64 vertices): head to 16-byte alignment, at most two rounds of 128-bit stores, tail
 __device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint32_t shift, uint32_t nFloats, uint32_t lane)
 {
   const uint32_t head = min(nFloats, (4u - shift) & 3u);
@@ -1311,13 +1312,16 @@ __device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint
   const uint32_t bodyVec = (nFloats - head) >> 2;
   const float4*  s4 = reinterpret_cast<const float4*>(stage + shift + head);
   float4*        d4 = reinterpret_cast<float4*>(dst + head);
-  for(uint32_t i = lane; i < bodyVec; i += 32)
-    __stcs(d4 + i, s4[i]);
+  if(lane < bodyVec)
+    __stcs(d4 + lane, s4[lane]);
+  if(lane + 32 < bodyVec)
+    __stcs(d4 + lane + 32, s4[lane + 32]);
   const uint32_t tailStart = head + (bodyVec << 2);
   if(lane < nFloats - tailStart)
     dst[tailStart + lane] = stage[shift + tailStart + lane];
 }
 
+template <bool DISPLACED, bool ANIM>
 __global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const uint32_t* epochCounter)
 {
   extern __shared__ __align__(16) float instSmem[];
@@ -1458,13 +1462,19 @@ __global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const
       {
         const float4* rec = reinterpret_cast<const float4*>(recBase + part * TC_REC_WORDS);
         PartCoeffs k;
-        const bool displaced = __float_as_int(rec[1].w) >= 0;
-        load_part_coeffs(rec, k, displaced);
+        load_part_coeffs(rec, k, DISPLACED);
+        if(ANIM && !DISPLACED)
+          k.m = rec[14];
         const uint32_t fv = __float_as_uint(k.r1.z) + v0;
         const float2   qa = __ldg(&p.tblVerticesF[fv]);
         const float2   qb = __ldg(&p.tblVerticesF[fv + (two ? 1u : 0u)]);
-        const F3 oa = eval_part_vertex(p, k, qa.x, qa.y, displaced);
-        const F3 ob = eval_part_vertex(p, k, qb.x, qb.y, displaced);
+        F3 oa, ob;
+        eval_part_pair<DISPLACED>(k, qa, qb, oa, ob);
+        if(ANIM)
+        {
+          oa = ripple_deform_part(p.view, p.build, p.instances, oa, __float_as_uint(k.m.w));
+          ob = ripple_deform_part(p.view, p.build, p.instances, ob, __float_as_uint(k.m.w));
+        }
         float* sdst = stage + shift + (t0 - itStart) * 3;
         sdst[0] = oa.x; sdst[1] = oa.y; sdst[2] = oa.z;
         if(two)
@@ -1736,9 +1746,12 @@ int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, Kerne
     return -1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->classify, k_cluster_classify, CLASSIFY_THREADS, smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->split, k_triangle_split, SPLIT_THREADS, 0);
-  if(cudaFuncSetAttribute(k_instantiate, cudaFuncAttributeMaxDynamicSharedMemorySize, int(instantiate_smem_bytes())) != cudaSuccess)
-    return -1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->instantiate, k_instantiate, INST_THREADS, instantiate_smem_bytes());
+  const void* variants[4] = {(const void*)k_instantiate<false, false>, (const void*)k_instantiate<false, true>, (const void*)k_instantiate<true, false>,
+                             (const void*)k_instantiate<true, true>};
+  for(const void* f : variants)
+    if(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, int(instantiate_smem_bytes())) != cudaSuccess)
+      return -1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->instantiate, k_instantiate<true, false>, INST_THREADS, instantiate_smem_bytes());
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1780,7 +1793,15 @@ void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32
 }
 void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s)
 {
-  k_instantiate<<<grid, INST_THREADS, instantiate_smem_bytes(), s>>>(p, epochCounter);
+  const bool displaced = p.numTextures > 0, anim = (p.flags & TC_FLAG_ANIMATION) != 0;
+  if(displaced && anim)
+    k_instantiate<true, true><<<grid, INST_THREADS, instantiate_smem_bytes(), s>>>(p, epochCounter);
+  else if(displaced)
+    k_instantiate<true, false><<<grid, INST_THREADS, instantiate_smem_bytes(), s>>>(p, epochCounter);
+  else if(anim)
+    k_instantiate<false, true><<<grid, INST_THREADS, instantiate_smem_bytes(), s>>>(p, epochCounter);
+  else
+    k_instantiate<false, false><<<grid, INST_THREADS, instantiate_smem_bytes(), s>>>(p, epochCounter);
 }
 void launch_blas(const Params& p, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s)
 {
