@@ -414,22 +414,24 @@ __device__ __forceinline__ void st_desc16(uint4* p, uint4 v)
   asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// Called by one full warp.  Returns the exclusive prefix (v, d) of all earlier tiles in every lane.
-__device__ __forceinline__ void lookback16_exclusive(uint4* descs, uint32_t tile, uint32_t aggV, unsigned long long aggD, uint32_t epoch, uint32_t& exclV,
-                                                     unsigned long long& exclD)
+// Step 1 (as early as possible): make the tile's aggregate visible to its successors.
+__device__ __forceinline__ void lookback16_publish(uint4* descs, uint32_t tile, uint32_t aggV, unsigned long long aggD, uint32_t epoch)
+{
+  const uint32_t AGG = (epoch << 2) | 1u, INC = (epoch << 2) | 2u;
+  if(lane_id() == 0)
+    st_desc16(&descs[tile], make_uint4(tile == 0 ? INC : AGG, aggV, uint32_t(aggD), uint32_t(aggD >> 32)));
+}
+
+// Step 2 (one full warp): exclusive prefix (v, d) of all earlier tiles in every lane; publishes the inclusive prefix.
+__device__ __forceinline__ void lookback16_resolve(uint4* descs, uint32_t tile, uint32_t aggV, unsigned long long aggD, uint32_t epoch, uint32_t& exclV,
+                                                   unsigned long long& exclD)
 {
   const uint32_t lane = lane_id();
   const uint32_t AGG = (epoch << 2) | 1u, INC = (epoch << 2) | 2u;
   exclV = 0;
   exclD = 0;
   if(tile == 0)
-  {
-    if(lane == 0)
-      st_desc16(&descs[0], make_uint4(INC, aggV, uint32_t(aggD), uint32_t(aggD >> 32)));
     return;
-  }
-  if(lane == 0)
-    st_desc16(&descs[tile], make_uint4(AGG, aggV, uint32_t(aggD), uint32_t(aggD >> 32)));
   int32_t base = int32_t(tile) - 1;
   while(true)
   {

@@ -1353,31 +1353,38 @@ __global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const
   }
   uint32_t accSucc = 0, accTris = 0;  // per-warp statistics, folded once at the end
 
-  while(true)
+  // One tile ahead: while a warp generates the vertices of tile k it already holds the ticket of its next tile, has
+  // loaded those parts, scanned them and published their aggregate -- successors never wait on this warp's heavy work
+  // and the part-record load latency is off the critical path.
+  struct Fetched
   {
+    uint32_t tile, instanceID, clusterID, vtx0, vtx1, vtx2, triCfg;
+    uint32_t numVertices, numTriangles, firstVertex, dataSize, incV;
+    unsigned long long incD;
+  };
+  auto fetch = [&](Fetched& f) {
     uint32_t tile = 0;
     if(lane == 0)
       tile = atomicAdd(&st->ticket[SLOT_INSTANTIATE], 1u);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    if(tile >= numTiles)
-      break;
-
-    // ---------------- 1. lane = part ----------------
-    const uint32_t partIndex = tile * 32 + lane;
-    const bool     valid     = partIndex < numParts;
-    uint32_t instanceID = 0, clusterID = 0, vtxEnc[3] = {0, 0, 0}, triCfg = 0;
-    uint32_t numVertices = 0, numTriangles = 0, firstVertex = 0, dataSize = 0;
-    if(valid)
+    f.tile = __shfl_sync(0xffffffffu, tile, 0);
+    f.instanceID = f.clusterID = f.vtx0 = f.vtx1 = f.vtx2 = f.triCfg = 0;
+    f.numVertices = f.numTriangles = f.firstVertex = f.dataSize = 0;
+    f.incV = 0;
+    f.incD = 0;
+    if(f.tile >= numTiles)
+      return;
+    const uint32_t partIndex = f.tile * 32 + lane;
+    if(partIndex < numParts)
     {
       const uint2* src = reinterpret_cast<const uint2*>(&partTriangles[partIndex]);
       uint2 a = __ldcs(src), c = __ldcs(src + 1), d = __ldcs(src + 2);
-      instanceID = a.x; clusterID = a.y; vtxEnc[0] = c.x; vtxEnc[1] = c.y; vtxEnc[2] = d.x; triCfg = d.y;
-      tc_TessTableEntry e = tess_entry(p, triCfg >> 16);
-      numVertices = e.numVertices; numTriangles = e.numTriangles; firstVertex = e.firstVertex;
-      dataSize    = __ldg(&p.tblTemplSize[tess_configIndex(triCfg >> 16) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1)]);
+      f.instanceID = a.x; f.clusterID = a.y; f.vtx0 = c.x; f.vtx1 = c.y; f.vtx2 = d.x; f.triCfg = d.y;
+      tc_TessTableEntry e = tess_entry(p, f.triCfg >> 16);
+      f.numVertices = e.numVertices; f.numTriangles = e.numTriangles; f.firstVertex = e.firstVertex;
+      f.dataSize    = __ldg(&p.tblTemplSize[tess_configIndex(f.triCfg >> 16) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1)]);
     }
-    const uint32_t incV = warp_inclusive_add(numVertices);
-    unsigned long long incD = dataSize;
+    f.incV = warp_inclusive_add(f.numVertices);
+    unsigned long long incD = f.dataSize;
 #pragma unroll
     for(int dlt = 1; dlt < 32; dlt <<= 1)
     {
@@ -1385,11 +1392,31 @@ __global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const
       if(lane >= dlt)
         incD += n;
     }
+    f.incD = incD;
+    lookback16_publish(p.lookback16, f.tile, __shfl_sync(0xffffffffu, f.incV, 31), __shfl_sync(0xffffffffu, incD, 31), epoch);
+  };
+
+  Fetched nxt;
+  fetch(nxt);
+  while(nxt.tile < numTiles)
+  {
+    const Fetched cur = nxt;
+    fetch(nxt);
+
+    // ---------------- 1. lane = part ----------------
+    const uint32_t tile = cur.tile;
+    const uint32_t partIndex = tile * 32 + lane;
+    const bool     valid     = partIndex < numParts;
+    const uint32_t instanceID = cur.instanceID, clusterID = cur.clusterID, triCfg = cur.triCfg;
+    const uint32_t vtxEnc[3] = {cur.vtx0, cur.vtx1, cur.vtx2};
+    const uint32_t numVertices = cur.numVertices, numTriangles = cur.numTriangles, firstVertex = cur.firstVertex, dataSize = cur.dataSize;
+    const uint32_t incV = cur.incV;
+    const unsigned long long incD = cur.incD;
     const uint32_t           aggV = __shfl_sync(0xffffffffu, incV, 31);
     const unsigned long long aggD = __shfl_sync(0xffffffffu, incD, 31);
     uint32_t           exclV;
     unsigned long long exclD;
-    lookback16_exclusive(p.lookback16, tile, aggV, aggD, epoch, exclV, exclD);
+    lookback16_resolve(p.lookback16, tile, aggV, aggD, epoch, exclV, exclD);
     if(tile == numTiles - 1 && lane == 0)
     {
       st->instTotalV = exclV + aggV;
