@@ -309,9 +309,11 @@ int enqueue_build(tc_context* c)
   {
     StageScope sc(c, TC_STAGE_SPLIT);
     uint32_t passes = split_pass_count(std::max(2u, c->cfg.splitFactor));
-    uint32_t grid   = std::max(1u, uint32_t(c->numSMs * c->occ.split));
+    // pass 0 sees the bulk of the work; deeper levels are usually small or empty
+    uint32_t grid0 = std::max(1u, uint32_t(c->numSMs * c->occ.split));
+    uint32_t gridN = std::max(1u, uint32_t(c->numSMs * std::min(c->occ.split, 2)));
     for(uint32_t k = 0; k < passes; k++)
-      tc::launch_triangle_split(p, c->dEpoch, k, k + 1 == passes, grid, s);
+      tc::launch_triangle_split(p, c->dEpoch, k, k + 1 == passes, k == 0 ? grid0 : gridN, s);
     launches += passes;
   }
   {

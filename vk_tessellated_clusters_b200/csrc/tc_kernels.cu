@@ -305,6 +305,47 @@ __device__ __forceinline__ F3 generate_vertex(const Params& p, const BaseTriangl
 // cluster_classify
 // ============================================================================================================
 
+// cold path of cluster_classify kept out of line (its register footprint must not limit the occupancy of the hot path):
+// the 3..6 displaced vertices of one 2X mini triangle (cluster_classify.comp.glsl:817-875)
+static __device__ __noinline__ void emit_mini_vertices(const tc_RenderInstance* inst, const tc_FrameConstants* view, const DeviceTexture* textures,
+                                                        uint32_t numTextures, uint32_t flags, const uint32_t* tblVertices, uint32_t firstLocalVertex,
+                                                        uint32_t i0, uint32_t i1, uint32_t i2, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t cfg,
+                                                        uint32_t firstPatternVertex, uint32_t numPatternVertices, uint32_t instanceID, float* dst)
+{
+  // rebuild the few Params members the shared helpers need (passing the kernel parameter block by reference would spill it)
+  Params q;
+  q.view        = view;
+  q.numTextures = numTextures;
+  q.flags       = flags;
+  for(uint32_t t = 0; t < numTextures && t < TC_MAX_TEXTURES; t++)
+    q.textures[t] = textures[t];
+  const uint32_t vtxEnc[3] = {v0, v1, v2};
+  BaseTriangle   bt;
+  setup_base_triangle(q, *inst, firstLocalVertex, i0, i1, i2, vtxEnc, bt);
+  const DisplacementConsts dc = displacement_consts(q, *inst);
+  const bool  flipped = (cfg & TC_CONFIG_FLIPPED_BIT) != 0;
+  const float geoSize = inst->geoHi[3];
+  for(uint32_t vert = 0; vert < numPatternVertices; vert++)
+  {
+    F3 o = generate_vertex(q, bt, dc, __ldg(&tblVertices[firstPatternVertex + vert]), flipped, instanceID, geoSize);
+    dst[vert * 3 + 0] = o.x; dst[vert * 3 + 1] = o.y; dst[vert * 3 + 2] = o.z;
+  }
+}
+
+// cold path: displaced (and optionally animated) copy of one original cluster vertex (cluster_classify.comp.glsl:465-488)
+static __device__ __noinline__ F3 displace_cluster_vertex(const tc_FrameConstants* view, const DeviceTexture* texture, float scale, float offset, uint32_t flags,
+                                                          F3 o, F3 n, float tu, float tv, uint32_t instanceID, float geoSize)
+{
+  if(texture)
+  {
+    float h = fmaf(sample_displacement(*texture, tu, tv), scale, offset);
+    o       = fma3(n, h * rsqrtf(dot3(n, n)), o);
+  }
+  if(flags & TC_FLAG_ANIMATION)
+    o = ripple_deform(view[0], o, instanceID, geoSize);
+  return o;
+}
+
 constexpr int CLASSIFY_WARPS   = 8;
 constexpr int CLASSIFY_THREADS = CLASSIFY_WARPS * 32;
 
@@ -319,7 +360,7 @@ struct ClassifyShared
   uint32_t  succTemp, succTrans, totalTris, fullClusters, validParts;
 };
 
-__global__ void __launch_bounds__(CLASSIFY_THREADS) k_cluster_classify(Params p, const uint32_t* epochCounter)
+__global__ void __launch_bounds__(CLASSIFY_THREADS, 2) k_cluster_classify(Params p, const uint32_t* epochCounter)
 {
   extern __shared__ __align__(16) uint8_t smemRaw[];
   __shared__ ClassifyShared sh;
@@ -610,16 +651,13 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_cluster_classify(Params p,
           for(uint32_t v = lane; v < numVertices; v += 32)
           {
             F3 o = {sObj[v * 3 + 0], sObj[v * 3 + 1], sObj[v * 3 + 2]};
-            if(dc.texture >= 0)
+            if(dc.texture >= 0 || flag_animation(p))
             {
               uint32_t vertexIndex = firstLocalVertex + v;
               F3       n  = ld_f3(normals, vertexIndex);
               float    tu = __ldg(texcoords + size_t(vertexIndex) * 2), tv = __ldg(texcoords + size_t(vertexIndex) * 2 + 1);
-              float    h  = fmaf(sample_displacement(p.textures[dc.texture], tu, tv), dc.scale, dc.offset);
-              o           = fma3(n, h * rsqrtf(dot3(n, n)), o);
+              o = displace_cluster_vertex(p.view, dc.texture >= 0 ? &p.textures[dc.texture] : nullptr, dc.scale, dc.offset, p.flags, o, n, tu, tv, instanceID, geoSize);
             }
-            if(flag_animation(p))
-              o = ripple_deform(p.view[0], o, instanceID, geoSize);
             float* dst = genVertices + size_t(vertexOffset + v) * 3;
             dst[0] = o.x; dst[1] = o.y; dst[2] = o.z;
           }
@@ -783,16 +821,9 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_cluster_classify(Params p,
             }
             uint32_t baseTris      = numTrisInclusive - numTris - firstTris;
             uint32_t packedFactors = (f0 - 1) | ((f1 - 1) << 1) | ((f2 - 1) << 2);  // un-rotated factors
-            uint32_t vtxEnc[3]     = {v0, v1, v2};
-            BaseTriangle bt;
-            setup_base_triangle(p, *inst, firstLocalVertex, i0, i1, i2, vtxEnc, bt);
             const bool flipped = (cfg & TC_CONFIG_FLIPPED_BIT) != 0;
-            for(uint32_t vert = 0; vert < entry.numVertices; vert++)
-            {
-              F3 o = generate_vertex(p, bt, dc, __ldg(&p.tblVertices[entry.firstVertex + vert]), flipped, instanceID, geoSize);
-              float* dst = genVertices + size_t(vert + transVertexOffset + relMini * miniVertices) * 3;
-              dst[0] = o.x; dst[1] = o.y; dst[2] = o.z;
-            }
+            emit_mini_vertices(inst, p.view, p.textures, p.numTextures, p.flags, p.tblVertices, firstLocalVertex, i0, i1, i2, v0, v1, v2, cfg, entry.firstVertex,
+                               entry.numVertices, instanceID, genVertices + size_t(transVertexOffset + relMini * miniVertices) * 3);
             uint32_t  indexOffset      = (transVertexOffset + miniBatchVertices) * 4u * 3u;
             uint32_t  triMappingOffset = transPartOffset * (24u / 2u) + (8u / 2u);
             uint16_t* mappings         = reinterpret_cast<uint16_t*>(transTriMappings);
@@ -982,6 +1013,64 @@ __device__ __forceinline__ uint32_t find_item(uint32_t endOffset, uint32_t t)
   return min(lo, 31u);
 }
 
+// BUILD_SETUP_SPLIT_PASS (build_setup.comp.glsl:168-190) or, after the last pass, BUILD_SETUP_INSTANTIATE_TESS (:236-264);
+// executed by exactly one thread after every CTA of the pass has finished
+__device__ void split_pass_epilogue(const Params& p, uint32_t baseSplit, uint32_t baseLo, uint32_t hi, uint32_t totSplit, uint32_t totPart, bool lastPass)
+{
+  tc_SceneBuilding* b  = p.build;
+  FrameState*       st = p.state;
+  const bool     transient = flag_transient(p);
+  const uint32_t validAll  = *(volatile uint32_t*)&st->validParts;
+  b->splitWriteCounter = baseSplit + totSplit;
+  const uint32_t loNow = baseLo + totPart;
+  if(transient)
+  {
+    b->dualPartTriangleCounter = (unsigned long long)loNow | ((unsigned long long)hi << 32);
+    b->partTriangleCounter     = max(b->partTriangleCounter, validAll);  // atomicMax :323-329 (validAll covers classify too,
+                                                                         // whose written parts never exceed the old value)
+  }
+  else
+    b->partTriangleCounter = loNow;
+  st->partSegEnd[st->numPartSegs] = loNow;
+  st->numPartSegs += 1;
+
+  if(!lastPass)
+  {
+    b->splitPass += 1;
+    uint32_t s2 = min(b->splitPassEnd, p.maxSplitTriangles);
+    uint32_t e2 = min(b->splitWriteCounter, p.maxSplitTriangles);
+    b->splitPassStart = s2;
+    b->splitPassEnd   = e2;
+    b->dispatchTriangleSplit.gridX = (e2 - s2 + 63) / 64;
+    b->dispatchTriangleSplit.gridY = 1;
+    b->dispatchTriangleSplit.gridZ = 1;
+  }
+  else
+  {
+    uint32_t counterPart = loNow;
+    if(transient)
+    {
+      p.readback->numPartTriangles      = counterPart + hi;
+      p.readback->numTransPartTriangles = hi;
+    }
+    else
+      p.readback->numPartTriangles = counterPart;
+    p.readback->numSplitTriangles = b->splitWriteCounter;
+    if(transient)
+      counterPart = b->partTriangleCounter;
+    else
+    {
+      counterPart            = min(counterPart, p.maxPartTriangles);
+      b->partTriangleCounter = counterPart;
+    }
+    b->dispatchTriangleInstantiate.gridX = (counterPart + TC_TESS_INSTANTIATE_BATCHSIZE - 1) / TC_TESS_INSTANTIATE_BATCHSIZE;
+    b->dispatchTriangleInstantiate.gridY = 1;
+    b->dispatchTriangleInstantiate.gridZ = 1;
+    // DESIGN.md deviation: only entries written this frame are visited
+    st->numParts = min(counterPart, validAll);
+  }
+}
+
 __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, const uint32_t* epochCounter, uint32_t pass, uint32_t lastPass)
 {
   __shared__ SplitShared sh;
@@ -1003,6 +1092,12 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
   tc_TessTriangleInfo* splitTriangles = reinterpret_cast<tc_TessTriangleInfo*>(b->splitTriangles);
   tc_TessTriangleInfo* partTriangles  = reinterpret_cast<tc_TessTriangleInfo*>(b->partTriangles);
 
+  if(numTiles == 0)
+  {  // nothing to split in this pass: one thread runs the setup step, nobody else touches any state
+    if(blockIdx.x == 0 && threadIdx.x == 0)
+      split_pass_epilogue(p, baseSplit, baseLo, hi, 0u, 0u, lastPass != 0);
+    return;
+  }
   if(threadIdx.x == 0)
     sh.validParts = 0;
 
@@ -1220,59 +1315,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
     if(done == gridDim.x - 1)
     {
       __threadfence();
-      ScanTuple tot;
-      tot.zero();
-      if(numTiles > 0)
-        tot = ld_tuple(reinterpret_cast<const ScanTuple*>(&descs[numTiles].aggregate));
-      const uint32_t validAll = *(volatile uint32_t*)&st->validParts;
-      b->splitWriteCounter = baseSplit + tot.v[0];
-      const uint32_t loNow = baseLo + tot.v[1];
-      if(transient)
-      {
-        b->dualPartTriangleCounter = (unsigned long long)loNow | ((unsigned long long)hi << 32);
-        b->partTriangleCounter     = max(b->partTriangleCounter, validAll);  // atomicMax :323-329 (validAll covers classify too,
-                                                                             // whose written parts never exceed the old value)
-      }
-      else
-        b->partTriangleCounter = loNow;
-      st->partSegEnd[st->numPartSegs] = loNow;
-      st->numPartSegs += 1;
-
-      if(!lastPass)
-      {
-        b->splitPass += 1;
-        uint32_t s2 = min(b->splitPassEnd, p.maxSplitTriangles);
-        uint32_t e2 = min(b->splitWriteCounter, p.maxSplitTriangles);
-        b->splitPassStart = s2;
-        b->splitPassEnd   = e2;
-        b->dispatchTriangleSplit.gridX = (e2 - s2 + 63) / 64;
-        b->dispatchTriangleSplit.gridY = 1;
-        b->dispatchTriangleSplit.gridZ = 1;
-      }
-      else
-      {
-        uint32_t counterPart = loNow;
-        if(transient)
-        {
-          p.readback->numPartTriangles      = counterPart + hi;
-          p.readback->numTransPartTriangles = hi;
-        }
-        else
-          p.readback->numPartTriangles = counterPart;
-        p.readback->numSplitTriangles = b->splitWriteCounter;
-        if(transient)
-          counterPart = b->partTriangleCounter;
-        else
-        {
-          counterPart            = min(counterPart, p.maxPartTriangles);
-          b->partTriangleCounter = counterPart;
-        }
-        b->dispatchTriangleInstantiate.gridX = (counterPart + TC_TESS_INSTANTIATE_BATCHSIZE - 1) / TC_TESS_INSTANTIATE_BATCHSIZE;
-        b->dispatchTriangleInstantiate.gridY = 1;
-        b->dispatchTriangleInstantiate.gridZ = 1;
-        // DESIGN.md deviation: only entries written this frame are visited
-        st->numParts = min(counterPart, validAll);
-      }
+      ScanTuple tot = ld_tuple(reinterpret_cast<const ScanTuple*>(&descs[numTiles].aggregate));
+      split_pass_epilogue(p, baseSplit, baseLo, hi, tot.v[0], tot.v[1], lastPass != 0);
     }
   }
 }
@@ -1607,26 +1651,40 @@ __device__ __forceinline__ SegmentTable load_segments(const Params& p)
   return t;
 }
 
-// grid: (numInstances + 1) * segments threads.  segLo[s][i] = first index in segment s whose instance id >= i
+// one warp per (instance, segment): segLo[s][i] = first index in segment s whose instance id >= i, found with a
+// 32-ary search (5 dependent probes instead of 21 for 2 M entries)
 __global__ void k_blas_segments(Params p)
 {
   const SegmentTable segs = load_segments(p);
   const uint32_t     N    = p.numInstances;
-  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if(gid >= (N + 1) * segs.count)
+  const uint32_t     lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if(gw >= (N + 1) * segs.count)
     return;
-  uint32_t s = gid / (N + 1), i = gid % (N + 1);
+  const uint32_t s = gw / (N + 1), i = gw % (N + 1);
   const uint32_t* ids = reinterpret_cast<const uint32_t*>(segs.isTrans[s] ? p.build->transInstanceIDs : p.build->tempInstanceIDs);
-  uint32_t lo = segs.begin[s], hi = segs.end[s];
-  while(lo < hi)
+  uint32_t lo = segs.begin[s], hi = segs.end[s];  // answer in [lo, hi]
+  while(hi - lo > 32)
   {
-    uint32_t mid = (lo + hi) >> 1;
-    if(__ldg(&ids[mid]) < i)
-      lo = mid + 1;
-    else
-      hi = mid;
+    // probes split [lo, hi) into 33 nearly equal pieces
+    const uint32_t span  = hi - lo;
+    const uint32_t probe = lo + uint32_t((unsigned long long)span * (lane + 1) / 33ull);
+    const bool     less  = __ldg(&ids[probe]) < i;  // probe < hi always
+    const uint32_t mask  = __ballot_sync(0xffffffffu, less);
+    // ids sorted => mask is a prefix of ones; first zero lane bounds the answer from above
+    const uint32_t k     = __popc(mask);
+    const uint32_t newLo = k == 0 ? lo : __shfl_sync(0xffffffffu, probe, k - 1) + 1;
+    const uint32_t newHi = k == 32 ? hi : __shfl_sync(0xffffffffu, probe, k & 31);
+    lo = newLo;
+    hi = newHi;
   }
-  p.segLo[size_t(s) * (N + 1) + i] = lo;
+  {
+    const uint32_t idx  = lo + lane;
+    const bool     less = idx < hi && __ldg(&ids[idx]) < i;
+    lo += __popc(__ballot_sync(0xffffffffu, less));
+  }
+  if(lane == 0)
+    p.segLo[size_t(s) * (N + 1) + i] = lo;
 }
 
 // one CTA: per-instance totals, exclusive scan in instance order, BlasBuildInfo (blas_setup_insertion.comp.glsl:100-115)
@@ -1832,7 +1890,7 @@ void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t 
 }
 void launch_blas(const Params& p, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s)
 {
-  uint32_t threads = (p.numInstances + 1) * numSegmentsMax;
+  uint32_t threads = (p.numInstances + 1) * numSegmentsMax * 32;  // one warp per (instance, segment)
   k_blas_segments<<<(threads + 255) / 256, 256, 0, s>>>(p);
   k_blas_setup<<<1, 1024, 0, s>>>(p);
   k_blas_insert<<<grid, 256, 0, s>>>(p);
