@@ -301,7 +301,7 @@ int enqueue_build(tc_context* c)
   }
   {
     StageScope sc(c, TC_STAGE_CLUSTER_CLASSIFY);
-    uint32_t tiles = (std::min(c->totalClusters, c->maxVisible) + 7) / 8;
+    uint32_t tiles = (std::min(c->totalClusters, c->maxVisible) + tc::classify_tile_clusters() - 1) / tc::classify_tile_clusters();
     uint32_t grid  = std::max(1u, std::min(tiles, uint32_t(c->numSMs * c->occ.classify)));
     tc::launch_cluster_classify(p, c->dEpoch, grid, s);
     launches += 1;

@@ -794,4 +794,63 @@ __device__ __forceinline__ void eval_part_pair(const PartCoeffs& k, float2 qa, f
   }
 }
 
+// N vertices of ONE part (N = 2 or 4).  Phases are ordered so that all texture gathers are in flight while the position
+// polynomials are evaluated; coefficients are read from the shared-memory record right where they are used, which
+// keeps the peak register pressure at one coefficient group at a time.
+template <bool DISPLACED, int N>
+__device__ __forceinline__ void eval_part_n(const float4* rec, const float2 (&q)[N], F3 (&o)[N])
+{
+  float s[N], t[N];
+  {
+    const float4 r0 = rec[0], r1 = rec[1];
+#pragma unroll
+    for(int i = 0; i < N; i++)
+    {
+      s[i] = fmaf(q[i].y, r0.z, fmaf(q[i].x, r0.y, r0.x));
+      t[i] = fmaf(q[i].y, r1.y, fmaf(q[i].x, r1.x, r0.w));
+    }
+  }
+  float  ax[N], ay[N];
+  float4 g[N];
+  if(DISPLACED)
+  {
+    // X = (n2.y,n2.z,n2.w), Y = n3.xyz, 1/W = n3.w, 1/H = m.x, texture object = (m.y, m.z)
+    const float4 n2 = rec[12], n3 = rec[13], m = rec[14];
+    const cudaTextureObject_t tex = (unsigned long long)__float_as_uint(m.y) | ((unsigned long long)__float_as_uint(m.z) << 32);
+#pragma unroll
+    for(int i = 0; i < N; i++)
+    {
+      const float x = fmaf(t[i], n2.w, fmaf(s[i], n2.z, n2.y)), y = fmaf(t[i], n3.z, fmaf(s[i], n3.y, n3.x));
+      const float fx = floorf(x), fy = floorf(y);
+      ax[i] = x - fx;
+      ay[i] = y - fy;
+      g[i]  = tex2Dgather<float4>(tex, (fx + 1.0f) * n3.w, (fy + 1.0f) * m.x, 0);  // (t01, t11, t10, t00)
+    }
+  }
+  float scale = 0.f, offset = 0.f;
+  {
+    PartCoeffs k;
+    k.a = rec[2]; k.b = rec[3]; k.c = rec[4]; k.d = rec[5]; k.e = rec[6]; k.f = rec[7]; k.g = rec[8]; k.h = rec[9];
+    scale  = k.h.z;
+    offset = k.h.w;
+#pragma unroll
+    for(int i = 0; i < N; i++)
+      o[i] = eval_position(k, s[i], t[i]);
+  }
+  if(DISPLACED)
+  {
+    // n0 = n0.xyz, dn1 = (n0.w,n1.x,n1.y), dn2 = (n1.z,n1.w,n2.x)
+    const float4 n0 = rec[10], n1 = rec[11];
+    const float  n2x = rec[12].x;
+#pragma unroll
+    for(int i = 0; i < N; i++)
+    {
+      const F3    n   = {fmaf(t[i], n1.z, fmaf(s[i], n0.w, n0.x)), fmaf(t[i], n1.w, fmaf(s[i], n1.x, n0.y)), fmaf(t[i], n2x, fmaf(s[i], n1.y, n0.z))};
+      const float top = fmaf(g[i].z - g[i].w, ax[i], g[i].w), bot = fmaf(g[i].y - g[i].x, ax[i], g[i].x);
+      const float h   = fmaf(fmaf(bot - top, ay[i], top), scale, offset) * fast_rsqrt(dot3(n, n));
+      o[i] = fma3(n, h, o[i]);
+    }
+  }
+}
+
 }  // namespace tc

@@ -346,7 +346,13 @@ static __device__ __noinline__ F3 displace_cluster_vertex(const tc_FrameConstant
   return o;
 }
 
-constexpr int CLASSIFY_WARPS   = 8;
+#ifndef TC_CLASSIFY_WARPS
+#define TC_CLASSIFY_WARPS 8
+#endif
+#ifndef TC_CLASSIFY_MIN_CTAS
+#define TC_CLASSIFY_MIN_CTAS 2
+#endif
+constexpr int CLASSIFY_WARPS   = TC_CLASSIFY_WARPS;
 constexpr int CLASSIFY_THREADS = CLASSIFY_WARPS * 32;
 
 // tuple lanes
@@ -360,7 +366,7 @@ struct ClassifyShared
   uint32_t  succTemp, succTrans, totalTris, fullClusters, validParts;
 };
 
-__global__ void __launch_bounds__(CLASSIFY_THREADS, 2) k_cluster_classify(Params p, const uint32_t* epochCounter)
+__global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_cluster_classify(Params p, const uint32_t* epochCounter)
 {
   extern __shared__ __align__(16) uint8_t smemRaw[];
   __shared__ ClassifyShared sh;
@@ -1336,7 +1342,11 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
 
 constexpr int INST_WARPS       = 8;
 constexpr int INST_THREADS     = INST_WARPS * 32;
-constexpr int INST_ITER_VERTS  = 64;  // two vertices per lane per iteration
+#ifndef TC_INST_SLOT
+#define TC_INST_SLOT 4
+#endif
+constexpr int INST_SLOT        = TC_INST_SLOT;      // vertices per lane per iteration (all of one part)
+constexpr int INST_ITER_VERTS  = 32 * INST_SLOT;
 constexpr int INST_STAGE_WORDS = INST_ITER_VERTS * 3 + 4;
 constexpr int INST_WARP_WORDS  = 32 * TC_REC_WORDS + INST_STAGE_WORDS;  // 2308 words = 9232 B per warp
 
@@ -1347,7 +1357,7 @@ __device__ __forceinline__ uint32_t lanemask_le()
   return m;
 }
 
-// nFloats <= 192 (64 vertices): head to 16-byte alignment, at most two rounds of 128-bit stores, tail
+// nFloats <= INST_ITER_VERTS * 3: head to 16-byte alignment, predicated rounds of 128-bit stores, tail
 __device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint32_t shift, uint32_t nFloats, uint32_t lane)
 {
   const uint32_t head = min(nFloats, (4u - shift) & 3u);
@@ -1356,10 +1366,10 @@ __device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint
   const uint32_t bodyVec = (nFloats - head) >> 2;
   const float4*  s4 = reinterpret_cast<const float4*>(stage + shift + head);
   float4*        d4 = reinterpret_cast<float4*>(dst + head);
-  if(lane < bodyVec)
-    __stcs(d4 + lane, s4[lane]);
-  if(lane + 32 < bodyVec)
-    __stcs(d4 + lane + 32, s4[lane + 32]);
+#pragma unroll
+  for(int r = 0; r < (INST_ITER_VERTS * 3 / 4 + 31) / 32; r++)
+    if(lane + 32 * r < bodyVec)
+      __stcs(d4 + lane + 32 * r, s4[lane + 32 * r]);
   const uint32_t tailStart = head + (bodyVec << 2);
   if(lane < nFloats - tailStart)
     dst[tailStart + lane] = stage[shift + tailStart + lane];
@@ -1501,10 +1511,10 @@ __global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const
     }
     __syncwarp();
 
-    // ---------------- 3./4. lane = one slot = two adjacent vertices of ONE part ----------------
-    // Slots are allotted per part (ceil(numVertices / 2)), so a slot never straddles two parts and the loop body has
-    // a single, divergence-free shape; an odd part wastes half a slot.
-    const uint32_t slotCount  = ok ? (numVertices + 1) >> 1 : 0;
+    // ---------------- 3./4. lane = one slot = INST_SLOT adjacent vertices of ONE part ----------------
+    // Slots are allotted per part (ceil(numVertices / INST_SLOT)), so a slot never straddles two parts and the loop
+    // body has a single, divergence-free shape; the last slot of a part may be partially filled.
+    const uint32_t slotCount  = ok ? (numVertices + INST_SLOT - 1) / INST_SLOT : 0;
     const uint32_t incS       = warp_inclusive_add(slotCount);
     const uint32_t startS     = incS - slotCount;
     const uint32_t totalSlots = __shfl_sync(0xffffffffu, incS, 31);
@@ -1520,38 +1530,39 @@ __global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const
       const uint32_t pStartS = __shfl_sync(0xffffffffu, startS, part);
       const uint32_t pStartV = __shfl_sync(0xffffffffu, startV, part);
       const uint32_t pNV     = __shfl_sync(0xffffffffu, numVertices, part);
-      const uint32_t v0      = (w0 + lane - pStartS) * 2;
-      const bool     two     = v0 + 1 < pNV;
-      const uint32_t t0      = pStartV + v0;  // tile-relative index of the slot's first vertex
+      const uint32_t v0      = (w0 + lane - pStartS) * INST_SLOT;
+      const uint32_t cnt     = min(uint32_t(INST_SLOT), pNV - v0);  // vertices of this slot (>= 1 when active)
+      const uint32_t t0      = pStartV + v0;                        // tile-relative index of the slot's first vertex
       // contiguous vertex range covered by this iteration
       const uint32_t lastLane = min(31u, totalSlots - w0 - 1u);
       const uint32_t itStart  = __shfl_sync(0xffffffffu, t0, 0);
-      const uint32_t itEnd    = __shfl_sync(0xffffffffu, t0 + (two ? 2u : 1u), lastLane);
+      const uint32_t itEnd    = __shfl_sync(0xffffffffu, t0 + cnt, lastLane);
       const size_t   itFloat0 = tileFloat0 + size_t(itStart) * 3;
       const uint32_t shift    = uint32_t(itFloat0 & 3);  // keep shared and global 16-byte phases equal
       if(active)
       {
-        const float4* rec = reinterpret_cast<const float4*>(recBase + part * TC_REC_WORDS);
-        PartCoeffs k;
-        load_part_coeffs(rec, k, DISPLACED);
-        if(ANIM && !DISPLACED)
-          k.m = rec[14];
-        const uint32_t fv = __float_as_uint(k.r1.z) + v0;
-        const float2   qa = __ldg(&p.tblVerticesF[fv]);
-        const float2   qb = __ldg(&p.tblVerticesF[fv + (two ? 1u : 0u)]);
-        F3 oa, ob;
-        eval_part_pair<DISPLACED>(k, qa, qb, oa, ob);
+        const float4*  rec = reinterpret_cast<const float4*>(recBase + part * TC_REC_WORDS);
+        const uint32_t fv  = __float_as_uint(rec[1].z) + v0;
+        float2 q[INST_SLOT];
+        F3     o[INST_SLOT];
+#pragma unroll
+        for(int i = 0; i < INST_SLOT; i++)
+          q[i] = __ldg(&p.tblVerticesF[fv + min(uint32_t(i), cnt - 1u)]);
+        eval_part_n<DISPLACED, INST_SLOT>(rec, q, o);
         if(ANIM)
         {
-          oa = ripple_deform_part(p.view, p.build, p.instances, oa, __float_as_uint(k.m.w));
-          ob = ripple_deform_part(p.view, p.build, p.instances, ob, __float_as_uint(k.m.w));
+          const uint32_t partIdx = __float_as_uint(rec[14].w);
+#pragma unroll
+          for(int i = 0; i < INST_SLOT; i++)
+            o[i] = ripple_deform_part(p.view, p.build, p.instances, o[i], partIdx);
         }
         float* sdst = stage + shift + (t0 - itStart) * 3;
-        sdst[0] = oa.x; sdst[1] = oa.y; sdst[2] = oa.z;
-        if(two)
-        {
-          sdst[3] = ob.x; sdst[4] = ob.y; sdst[5] = ob.z;
-        }
+#pragma unroll
+        for(int i = 0; i < INST_SLOT; i++)
+          if(uint32_t(i) < cnt)
+          {
+            sdst[i * 3 + 0] = o[i].x; sdst[i * 3 + 1] = o[i].y; sdst[i * 3 + 2] = o[i].z;
+          }
       }
       __syncwarp();
       flush_stage(stage, genVertices + itFloat0, shift, (itEnd - itStart) * 3, lane);
@@ -1851,6 +1862,7 @@ uint32_t lookback_tiles_needed(uint32_t maxVisible, uint32_t maxSplit, uint32_t 
 }
 
 size_t lookback_desc_bytes() { return sizeof(LookbackDesc); }
+uint32_t classify_tile_clusters() { return CLASSIFY_WARPS; }
 uint32_t lookback16_tiles_needed(uint32_t maxPart) { return (maxPart + 31) / 32 + 2; }
 size_t frame_state_bytes() { return sizeof(FrameState); }
 
