@@ -294,6 +294,14 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         inst_avg_ms = float(np.mean(inst_ms))
+        # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/), per launch
+        traffic = None
+        try:
+            raw = {l.split(",")[0]: l.strip().split(",")[1:] for l in open(os.path.join(ROOT, "profiles", "r01_instantiate_ncu_raw.csv"))}
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            traffic = int(sum(float(raw[k][1]) * scale[raw[k][0]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")))
+        except (OSError, KeyError, ValueError):
+            pass
         achieved = alg_bytes / (inst_avg_ms * 1e-3) / 1e9
         frame_alg = api.algorithmic_bytes(rb, sb, scene, tbl)
 
@@ -315,7 +323,7 @@ def main():
             "e2e": {"value": tris_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": gpu.last_launch_count() * args.steps,
             "roofline": {"kernel": "k_instantiate", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": inst_avg_ms,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": inst_avg_ms,
                          "frac_of_8000_nominal": achieved / 8000.0,
                          "frame": {"algorithmic_bytes": frame_alg, "achieved": frame_alg / (ms_per_step * 1e-3) / 1e9, "frac": frame_alg / (ms_per_step * 1e-3) / 1e9 / peak}},
             "stage_ms": {k: float(np.mean(v)) for k, v in stage_acc.items()},
