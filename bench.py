@@ -114,6 +114,10 @@ def run_cpu_reference(args, rank, world):
     scene, fcs, cfg = workload(0, 1, args.small)
     tbl = table.load_tess_table()
     orc = Oracle(cfg)
+    try:
+        orc.set_num_threads(len(os.sched_getaffinity(0)))  # all host cores (torchrun pins OMP_NUM_THREADS=1)
+    except AttributeError:
+        orc.set_num_threads(os.cpu_count() or 1)
     orc.set_tess_table(tbl)
     orc.set_scene(scene)
     orc.set_default_addresses()
@@ -180,7 +184,10 @@ def main():
     if world > 1:
         from vk_tessellated_clusters_b200 import sharding
 
-        stream = torch.cuda.current_stream()
+        # one non-default stream for everything: the frame's kernels, the NCCL allgather and the timing events
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        assert stream.cuda_stream != 0
         gpu.set_stream(stream.cuda_stream)
         counts_t = torch.zeros(sharding.SHARD_WORDS, dtype=torch.int32, device="cuda")
         shard = (sharding, counts_t)

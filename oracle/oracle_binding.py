@@ -59,6 +59,9 @@ class Oracle(api.Binding):
         raw = (C.c_uint8 * nbytes.value).from_address(ptr.value)
         return np.frombuffer(raw, dtype="<u2").reshape(-1, 4).copy()
 
+    def set_num_threads(self, n: int):
+        self.lib.orc_set_num_threads(C.c_int(int(n)))
+
     def num_threads(self) -> int:
         return int(self.lib.orc_num_threads())
 

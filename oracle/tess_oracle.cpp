@@ -1479,6 +1479,17 @@ ORC_API int orc_buffer(orc_context* c, const char* name, const void** ptr, size_
   return TC_ERR_INVALID_ARG;
 }
 
+// torchrun exports OMP_NUM_THREADS=1; the timed CPU baseline asks for all host cores explicitly
+ORC_API void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if(n > 0)
+    omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 ORC_API int orc_num_threads(void)
 {
 #ifdef _OPENMP
