@@ -797,8 +797,11 @@ __device__ __forceinline__ void eval_part_pair(const PartCoeffs& k, float2 qa, f
 // N vertices of ONE part (N = 2 or 4).  Phases are ordered so that all texture gathers are in flight while the position
 // polynomials are evaluated; coefficients are read from the shared-memory record right where they are used, which
 // keeps the peak register pressure at one coefficient group at a time.
+// uniformTex != 0: every part of the scene samples the same texture, so the handle comes from the (warp-uniform) kernel
+// parameter; a per-lane handle makes the compiler wrap every texture instruction in a "waterfall" loop over the distinct
+// handles of the warp, which also stops it from batching the gathers.
 template <bool DISPLACED, int N>
-__device__ __forceinline__ void eval_part_n(const float4* rec, const float2 (&q)[N], F3 (&o)[N])
+__device__ __forceinline__ void eval_part_n(const float4* rec, const float2 (&q)[N], F3 (&o)[N], cudaTextureObject_t uniformTex)
 {
   float s[N], t[N];
   {
@@ -816,7 +819,7 @@ __device__ __forceinline__ void eval_part_n(const float4* rec, const float2 (&q)
   {
     // X = (n2.y,n2.z,n2.w), Y = n3.xyz, 1/W = n3.w, 1/H = m.x, texture object = (m.y, m.z)
     const float4 n2 = rec[12], n3 = rec[13], m = rec[14];
-    const cudaTextureObject_t tex = (unsigned long long)__float_as_uint(m.y) | ((unsigned long long)__float_as_uint(m.z) << 32);
+    float gx[N], gy[N];
 #pragma unroll
     for(int i = 0; i < N; i++)
     {
@@ -824,7 +827,21 @@ __device__ __forceinline__ void eval_part_n(const float4* rec, const float2 (&q)
       const float fx = floorf(x), fy = floorf(y);
       ax[i] = x - fx;
       ay[i] = y - fy;
-      g[i]  = tex2Dgather<float4>(tex, (fx + 1.0f) * n3.w, (fy + 1.0f) * m.x, 0);  // (t01, t11, t10, t00)
+      gx[i] = (fx + 1.0f) * n3.w;
+      gy[i] = (fy + 1.0f) * m.x;
+    }
+    if(uniformTex)
+    {
+#pragma unroll
+      for(int i = 0; i < N; i++)
+        g[i] = tex2Dgather<float4>(uniformTex, gx[i], gy[i], 0);  // (t01, t11, t10, t00)
+    }
+    else
+    {
+      const cudaTextureObject_t tex = (unsigned long long)__float_as_uint(m.y) | ((unsigned long long)__float_as_uint(m.z) << 32);
+#pragma unroll
+      for(int i = 0; i < N; i++)
+        g[i] = tex2Dgather<float4>(tex, gx[i], gy[i], 0);
     }
   }
   float scale = 0.f, offset = 0.f;

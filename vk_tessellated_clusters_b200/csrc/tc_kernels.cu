@@ -1406,6 +1406,7 @@ __global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const
     shTris = 0;
   }
   uint32_t accSucc = 0, accTris = 0;  // per-warp statistics, folded once at the end
+  const cudaTextureObject_t uniformTex = (DISPLACED && p.numTextures == 1) ? p.textures[0].gather : 0;  // warp-uniform handle
 
   // One tile ahead: while a warp generates the vertices of tile k it already holds the ticket of its next tile, has
   // loaded those parts, scanned them and published their aggregate -- successors never wait on this warp's heavy work
@@ -1548,7 +1549,7 @@ __global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const
 #pragma unroll
         for(int i = 0; i < INST_SLOT; i++)
           q[i] = __ldg(&p.tblVerticesF[fv + min(uint32_t(i), cnt - 1u)]);
-        eval_part_n<DISPLACED, INST_SLOT>(rec, q, o);
+        eval_part_n<DISPLACED, INST_SLOT>(rec, q, o, uniformTex);
         if(ANIM)
         {
           const uint32_t partIdx = __float_as_uint(rec[14].w);
