@@ -1340,10 +1340,13 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
 //   4. vertices are staged in shared memory (4 iterations = 128 vertices) and flushed as aligned 128-bit stores.
 // ============================================================================================================
 
-constexpr int INST_WARPS       = 8;
+#ifndef TC_INST_WARPS
+#define TC_INST_WARPS 8
+#endif
+constexpr int INST_WARPS       = TC_INST_WARPS;
 constexpr int INST_THREADS     = INST_WARPS * 32;
 #ifndef TC_INST_SLOT
-#define TC_INST_SLOT 4
+#define TC_INST_SLOT 3
 #endif
 constexpr int INST_SLOT        = TC_INST_SLOT;      // vertices per lane per iteration (all of one part)
 constexpr int INST_ITER_VERTS  = 32 * INST_SLOT;
@@ -1375,8 +1378,11 @@ __device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint
     dst[tailStart + lane] = stage[shift + tailStart + lane];
 }
 
+#ifndef TC_INST_MIN_CTAS
+#define TC_INST_MIN_CTAS 3
+#endif
 template <bool DISPLACED, bool ANIM>
-__global__ void __launch_bounds__(INST_THREADS, 2) k_instantiate(Params p, const uint32_t* epochCounter)
+__global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(Params p, const uint32_t* epochCounter)
 {
   extern __shared__ __align__(16) float instSmem[];
   __shared__ uint32_t shSucc, shTris;
