@@ -641,8 +641,10 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
   // corner k has base barycentrics (1-bu-bv, bu, bv); pattern weights (q0,q1,q2), q0 = 1-q1-q2, flipped: q0 <-> q1
   const float buO = flipped ? bu[1] : bu[0], buA = flipped ? bu[0] : bu[1];  // origin corner, corner multiplied by q1
   const float bvO = flipped ? bv[1] : bv[0], bvA = flipped ? bv[0] : bv[1];
-  rec[0] = buO; rec[1] = buA - buO; rec[2] = bu[2] - buO;
-  rec[3] = bvO; rec[4] = bvA - bvO; rec[5] = bv[2] - bvO;
+  // (q1, q2) enter as the raw 16-bit table integers converted to float: the 1/32768 scale (exact) lives here
+  const float k = 1.0f / 32768.0f;
+  rec[0] = buO; rec[1] = (buA - buO) * k; rec[2] = (bu[2] - buO) * k;
+  rec[3] = bvO; rec[4] = (bvA - bvO) * k; rec[5] = (bv[2] - bvO) * k;
   reinterpret_cast<uint32_t*>(rec)[6] = firstPatternVertex;
   const int texture = (p.numTextures > 0 && inst.displacementIndex >= 0) ? inst.displacementIndex : -1;
   reinterpret_cast<int*>(rec)[7] = texture;

@@ -1554,7 +1554,13 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
         F3     o[INST_SLOT];
 #pragma unroll
         for(int i = 0; i < INST_SLOT; i++)
-          q[i] = __ldg(&p.tblVerticesF[fv + min(uint32_t(i), cnt - 1u)]);
+        {
+          // packed (u | v << 16) pattern vertex: one 32-bit load; u16 -> float without the conversion pipe
+          // (2^23 + n has n in its low mantissa bits); the 1/32768 scale is folded into the record's affine map
+          const uint32_t pk = __ldg(&p.tblVertices[fv + min(uint32_t(i), cnt - 1u)]);
+          q[i].x = __uint_as_float(0x4B000000u | (pk & 0xFFFFu)) - 8388608.0f;
+          q[i].y = __uint_as_float(0x4B000000u | (pk >> 16)) - 8388608.0f;
+        }
         eval_part_n<DISPLACED, INST_SLOT>(rec, q, o, uniformTex);
         if(ANIM)
         {
@@ -1772,36 +1778,59 @@ __global__ void __launch_bounds__(1024) k_blas_setup(Params p)
   }
 }
 
-// thread per generated CLAS (templates first, then transient builds), blas_clusters_insert.comp.glsl:97-135
-__global__ void k_blas_insert(Params p)
+// blas_clusters_insert.comp.glsl:97-135 without atomics: thread = 4 consecutive CLAS of one list (128-bit loads of ids /
+// sizes, 2 x 128-bit of addresses); rank inside the instance's BLAS list from the sorted-segment tables.
+__device__ __forceinline__ void blas_insert_one(const Params& p, const SegmentTable& segs, uint32_t N, bool isTrans, uint32_t j, uint32_t inst,
+                                                unsigned long long addr)
+{
+  uint32_t s = 0;
+  if(isTrans)
+    s = segs.count - 1;
+  else
+    while(s + 2 < segs.count && j >= segs.end[s])
+      s++;
+  const uint32_t idx = p.rankBase[size_t(s) * (N + 1) + inst] + (j - p.segLo[size_t(s) * (N + 1) + inst]);
+  const tc_BlasBuildInfo* blas = reinterpret_cast<const tc_BlasBuildInfo*>(p.build->blasBuildInfos);
+  reinterpret_cast<unsigned long long*>(blas[inst].clusterReferences)[idx] = addr;
+}
+
+__global__ void __launch_bounds__(256) k_blas_insert(Params p)
 {
   __shared__ unsigned long long blockSizes;
   const SegmentTable segs = load_segments(p);
   const uint32_t     N    = p.numInstances;
   const uint32_t numTemp  = p.build->tempInstantiateCounter, numTrans = flag_transient(p) ? p.build->transBuildCounter : 0;
+  const uint32_t quadsTemp = (numTemp + 3) / 4, quadsTrans = (numTrans + 3) / 4;
   if(threadIdx.x == 0)
     blockSizes = 0;
   __syncthreads();
   unsigned long long mySize = 0;
-  for(uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < numTemp + numTrans; gid += gridDim.x * blockDim.x)
+  for(uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < quadsTemp + quadsTrans; gid += gridDim.x * blockDim.x)
   {
-    const bool     isTrans = gid >= numTemp;
-    const uint32_t j       = isTrans ? gid - numTemp : gid;
-    uint32_t s = 0;
-    if(isTrans)
-      s = segs.count - 1;
-    else
-      while(s + 2 < segs.count && j >= segs.end[s])
-        s++;
-    const uint32_t* ids   = reinterpret_cast<const uint32_t*>(isTrans ? p.build->transInstanceIDs : p.build->tempInstanceIDs);
+    const bool     isTrans = gid >= quadsTemp;
+    const uint32_t j0      = (isTrans ? gid - quadsTemp : gid) * 4;
+    const uint32_t count   = isTrans ? numTrans : numTemp;
+    const uint32_t* ids    = reinterpret_cast<const uint32_t*>(isTrans ? p.build->transInstanceIDs : p.build->tempInstanceIDs);
     const unsigned long long* addrs = reinterpret_cast<const unsigned long long*>(isTrans ? p.build->transClusterAddresses : p.build->tempClusterAddresses);
-    const uint32_t* sizes = reinterpret_cast<const uint32_t*>(isTrans ? p.build->transClusterSizes : p.build->tempClusterSizes);
-    const uint32_t  inst  = ids[j];
-    const uint32_t  idx   = p.rankBase[size_t(s) * (N + 1) + inst] + (j - p.segLo[size_t(s) * (N + 1) + inst]);
-    const tc_BlasBuildInfo* blas = reinterpret_cast<const tc_BlasBuildInfo*>(p.build->blasBuildInfos);
-    unsigned long long* refs = reinterpret_cast<unsigned long long*>(blas[inst].clusterReferences);
-    refs[idx] = addrs[j];
-    mySize += sizes[j];
+    const uint32_t* sizes  = reinterpret_cast<const uint32_t*>(isTrans ? p.build->transClusterSizes : p.build->tempClusterSizes);
+    if(j0 + 4 <= count)
+    {
+      const uint4      id4 = __ldcs(reinterpret_cast<const uint4*>(ids + j0));
+      const uint4      sz4 = __ldcs(reinterpret_cast<const uint4*>(sizes + j0));
+      const ulonglong2 a01 = __ldcs(reinterpret_cast<const ulonglong2*>(addrs + j0));
+      const ulonglong2 a23 = __ldcs(reinterpret_cast<const ulonglong2*>(addrs + j0 + 2));
+      blas_insert_one(p, segs, N, isTrans, j0 + 0, id4.x, a01.x);
+      blas_insert_one(p, segs, N, isTrans, j0 + 1, id4.y, a01.y);
+      blas_insert_one(p, segs, N, isTrans, j0 + 2, id4.z, a23.x);
+      blas_insert_one(p, segs, N, isTrans, j0 + 3, id4.w, a23.y);
+      mySize += (unsigned long long)sz4.x + sz4.y + sz4.z + sz4.w;
+    }
+    else
+      for(uint32_t j = j0; j < count; j++)
+      {
+        blas_insert_one(p, segs, N, isTrans, j, ids[j], addrs[j]);
+        mySize += sizes[j];
+      }
   }
 #pragma unroll
   for(int d = 16; d > 0; d >>= 1)
