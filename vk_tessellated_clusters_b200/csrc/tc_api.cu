@@ -68,6 +68,8 @@ struct tc_context
   uint32_t*         dEpoch     = nullptr;
   void*             dLookback  = nullptr;
   void*             dLookback16 = nullptr;
+  void*             dClassTuples = nullptr;
+  uint32_t*         dFactorStash = nullptr;
   FrameStaging*     dFrame     = nullptr;
   FrameStaging*     hFrame     = nullptr;  // pinned
   tc_shard_counts*  dShardCounts = nullptr;
@@ -87,6 +89,8 @@ struct tc_context
   std::vector<DeviceGeometry> geoms;
   std::vector<void*>          textures;
   std::vector<cudaArray_t>    textureArrays;
+  tc::DeviceTexture*          dTextureTable = nullptr;
+  std::vector<tc::DeviceTexture> hTextureTable;
   std::vector<cudaTextureObject_t> textureObjects;
   uint32_t numInstances = 0, totalClusters = 0;
 
@@ -159,6 +163,9 @@ void free_scene(tc_context* c)
   for(cudaArray_t a : c->textureArrays)
     cudaFreeArray(a);
   c->textureArrays.clear();
+  dfree(c->dTextureTable);
+  c->dTextureTable = nullptr;
+  c->hTextureTable.clear();
   dfree(c->instanceStates); dfree(c->blasBuildInfos); dfree(c->blasBuildSizes); dfree(c->basicClusterSizes);
   dfree(c->dInstances); dfree(c->dClusterPrefix); dfree(c->segLo); dfree(c->rankBase); dfree(c->globalRanges);
   c->globalRanges = nullptr;
@@ -246,6 +253,8 @@ void fill_params(tc_context* c)
   p.driverStandin      = c->driverStandin;
   p.lookback           = c->dLookback;
   p.lookback16         = reinterpret_cast<uint4*>(c->dLookback16);
+  p.classTuples        = c->dClassTuples;
+  p.factorStash        = c->dFactorStash;
   p.segLo              = c->segLo;
   p.rankBase           = c->rankBase;
   p.shardBase          = c->dShardBase;
@@ -301,10 +310,10 @@ int enqueue_build(tc_context* c)
   }
   {
     StageScope sc(c, TC_STAGE_CLUSTER_CLASSIFY);
-    uint32_t tiles = (std::min(c->totalClusters, c->maxVisible) + tc::classify_tile_clusters() - 1) / tc::classify_tile_clusters();
-    uint32_t grid  = std::max(1u, std::min(tiles, uint32_t(c->numSMs * c->occ.classify)));
-    tc::launch_cluster_classify(p, c->dEpoch, grid, s);
-    launches += 1;
+    // count / emit have no inter-CTA ordering: one CTA per 8 clusters, the hardware scheduler balances them
+    uint32_t grid = std::max(1u, (std::min(c->totalClusters, c->maxVisible) + tc::classify_tile_clusters() - 1) / tc::classify_tile_clusters());
+    tc::launch_cluster_classify(p, c->dEpoch, grid, s);  // count -> scan -> emit
+    launches += 3;
   }
   {
     StageScope sc(c, TC_STAGE_SPLIT);
@@ -421,6 +430,8 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   size_t lb16Bytes = size_t(tc::lookback16_tiles_needed(c->maxPart)) * 16;
   TRY_RC(dalloc(c->dLookback16, lb16Bytes));
   TRY_CUDA(cudaMemset(c->dLookback16, 0, lb16Bytes));
+  TRY_RC(dalloc(c->dClassTuples, size_t(c->maxVisible) * tc::classify_tuple_bytes()));
+  TRY_RC(dalloc(c->dFactorStash, size_t(c->maxVisible) * config->clusterTriangles * 12));
   TRY_CUDA(cudaMemset(c->dEpoch, 0, 16));
   TRY_CUDA(cudaMemset(c->dShardBase, 0, 16));
   TRY_CUDA(cudaMemset(c->dReadback, 0, sizeof(tc_Readback)));
@@ -471,7 +482,7 @@ TC_API void tc_destroy(tc_context* c)
     cudaStreamSynchronize(c->stream);
   drop_graph(c);
   free_scene(c);
-  dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dFrame);
+  dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dFrame);
   dfree(c->dShardCounts); dfree(c->dShardBase);
   if(c->hFrame)
     cudaFreeHost(c->hFrame);
@@ -659,8 +670,15 @@ TC_API int tc_set_scene(tc_context* c, const tc_geometry* geoms, uint32_t numGeo
     cudaTextureObject_t obj = 0;
     CUDA_TRY(cudaCreateTextureObject(&obj, &rd, &td, nullptr));
     c->textureObjects.push_back(obj);
-    c->params.textures[t] = tc::DeviceTexture{reinterpret_cast<const float*>(d), obj, textures[t].width, textures[t].height};
+    c->hTextureTable.push_back(tc::DeviceTexture{reinterpret_cast<const float*>(d), obj, textures[t].width, textures[t].height});
   }
+  if((rc = dalloc(c->dTextureTable, sizeof(tc::DeviceTexture) * TC_MAX_TEXTURES)))
+    return rc;
+  if(numTextures)
+    CUDA_TRY(cudaMemcpy(c->dTextureTable, c->hTextureTable.data(), sizeof(tc::DeviceTexture) * numTextures, cudaMemcpyHostToDevice));
+  c->params.textures = c->dTextureTable;
+  for(uint32_t t = 0; t < numTextures; t++)
+    c->params.texturesC[t] = c->hTextureTable[t];
   c->sceneSet = true;
   fill_params(c);
   return upload_template(c);

@@ -44,6 +44,7 @@ struct FrameState
   uint32_t instTotalV;       // grand totals of the instantiate scan (written by the warp that owns the last tile)
   uint32_t pad[4];
   unsigned long long instTotalD;
+  uint32_t classTotal[8];    // grand totals of the classify scan: v[0..5], data lo, data hi
   // aggregated stats kept as plain counters and folded into Readback by the setup steps
   unsigned long long genActualDatas;
 };
@@ -67,8 +68,10 @@ struct Params
   // hiz
   const float*             hiz;
   uint32_t                 hizSize, hizMips;
-  // displacement textures
-  DeviceTexture            textures[TC_MAX_TEXTURES];
+  // displacement textures: device array (NOT embedded -- taking the address of a by-value kernel parameter member makes
+  // the compiler copy the whole parameter block to local memory)
+  const DeviceTexture*     textures;
+  DeviceTexture            texturesC[TC_MAX_TEXTURES];  // same table in the parameter block: value reads only (constant bank)
   uint32_t                 numTextures;
   // limits (the reference's shader macros)
   uint32_t maxVisibleClusters, maxPartTriangles, maxSplitTriangles, maxGenVertices, maxGenClusters;
@@ -81,6 +84,9 @@ struct Params
   // look-back descriptors
   void*    lookback;
   uint4*   lookback16;  // 16-byte (flag, value) descriptors of the instantiate scan
+  // classify runs as count -> scan -> emit: per visible cluster an 8-word tuple and the packed per-triangle factors
+  void*     classTuples;   // ScanTuple[maxVisibleClusters]: counts, then (in place) exclusive prefixes
+  uint32_t* factorStash;   // [maxVisibleClusters][clusterTriangles][3]: factor | local vertex index << 24
   // blas helpers
   uint32_t* segLo;     // [TC_MAX_SEGMENTS+1][numInstances]
   uint32_t* rankBase;  // [TC_MAX_SEGMENTS+1][numInstances]
@@ -641,10 +647,8 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
   // corner k has base barycentrics (1-bu-bv, bu, bv); pattern weights (q0,q1,q2), q0 = 1-q1-q2, flipped: q0 <-> q1
   const float buO = flipped ? bu[1] : bu[0], buA = flipped ? bu[0] : bu[1];  // origin corner, corner multiplied by q1
   const float bvO = flipped ? bv[1] : bv[0], bvA = flipped ? bv[0] : bv[1];
-  // (q1, q2) enter as the raw 16-bit table integers converted to float: the 1/32768 scale (exact) lives here
-  const float k = 1.0f / 32768.0f;
-  rec[0] = buO; rec[1] = (buA - buO) * k; rec[2] = (bu[2] - buO) * k;
-  rec[3] = bvO; rec[4] = (bvA - bvO) * k; rec[5] = (bv[2] - bvO) * k;
+  rec[0] = buO; rec[1] = buA - buO; rec[2] = bu[2] - buO;
+  rec[3] = bvO; rec[4] = bvA - bvO; rec[5] = bv[2] - bvO;
   reinterpret_cast<uint32_t*>(rec)[6] = firstPatternVertex;
   const int texture = (p.numTextures > 0 && inst.displacementIndex >= 0) ? inst.displacementIndex : -1;
   reinterpret_cast<int*>(rec)[7] = texture;
@@ -692,10 +696,10 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
   unsigned long long texObj = 0;
   if(p.numTextures > 0)
   {
-    const DeviceTexture& t = p.textures[texture >= 0 ? texture : 0];  // undisplaced parts: any valid texture, scale 0
-    W      = float(t.width);
-    H      = float(t.height);
-    texObj = t.gather;
+    const int ti = texture >= 0 ? texture : 0;  // undisplaced parts: any valid texture, scale 0
+    W      = float(p.texturesC[ti].width);
+    H      = float(p.texturesC[ti].height);
+    texObj = p.texturesC[ti].gather;
   }
   rec[49] = fmaf(tu[0], W, -0.5f); rec[50] = (tu[1] - tu[0]) * W; rec[51] = (tu[2] - tu[0]) * W;
   rec[52] = fmaf(tv[0], H, -0.5f); rec[53] = (tv[1] - tv[0]) * H; rec[54] = (tv[2] - tv[0]) * H;

@@ -317,8 +317,7 @@ static __device__ __noinline__ void emit_mini_vertices(const tc_RenderInstance* 
   q.view        = view;
   q.numTextures = numTextures;
   q.flags       = flags;
-  for(uint32_t t = 0; t < numTextures && t < TC_MAX_TEXTURES; t++)
-    q.textures[t] = textures[t];
+  q.textures    = textures;
   const uint32_t vtxEnc[3] = {v0, v1, v2};
   BaseTriangle   bt;
   setup_base_triangle(q, *inst, firstLocalVertex, i0, i1, i2, vtxEnc, bt);
@@ -358,15 +357,18 @@ constexpr int CLASSIFY_THREADS = CLASSIFY_WARPS * 32;
 // tuple lanes
 enum { T_SPLIT = 0, T_LO = 1, T_HI = 2, T_TEMP = 3, T_TRANS = 4, T_VERT = 5 };
 
-struct ClassifyShared
+struct ClassifyShared  // only the CTA epilogue's statistics: one cluster per warp, no CTA-level exchange in the loop
 {
-  ScanTuple warpTuple[CLASSIFY_WARPS];
-  ScanTuple warpPrefix[CLASSIFY_WARPS];
-  uint32_t  tile;
-  uint32_t  succTemp, succTrans, totalTris, fullClusters, validParts;
+  uint32_t succTemp, succTrans, totalTris, fullClusters, validParts;
 };
 
-__global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_cluster_classify(Params p, const uint32_t* epochCounter)
+// cluster_classify runs as three launches so that no warp ever waits for another one:
+//   MODE 0 (count): per cluster load vertices, compute the per-triangle edge factors (EXACT), stash them packed in global
+//                   memory and write the cluster's 8-word allocation tuple;
+//   k_classify_scan: exclusive prefix of the tuples in canonical (visible-list) order, in place;
+//   MODE 1 (emit):  per cluster read its prefix + stashed factors and write every record / vertex / index byte.
+template <int MODE>
+__global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_cluster_classify(Params p)
 {
   extern __shared__ __align__(16) uint8_t smemRaw[];
   __shared__ ClassifyShared sh;
@@ -379,10 +381,8 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
   float*    sWorld   = sObj + maxV * 3;
   uint32_t* sFactors = reinterpret_cast<uint32_t*>(sWorld + maxV * 4);
 
-  const uint32_t epoch      = *epochCounter + SLOT_CLASSIFY;
   const uint32_t numVisible = p.build->visibleClusterCounter;
-  const uint32_t numTiles   = (numVisible + CLASSIFY_WARPS - 1) / CLASSIFY_WARPS;
-  LookbackDesc*  descs      = reinterpret_cast<LookbackDesc*>(p.lookback);
+  ScanTuple*     tuples     = reinterpret_cast<ScanTuple*>(p.classTuples);
   const FactorConsts fcst   = load_factor_consts(p);
   const bool use1X = flag_1x(p), use2X = flag_2x(p);
   const uint32_t basic32 = use2X ? __ldg(&p.basicClusterSizes[TC_TESS_2X_MINI_BATCHSIZE * TC_TESS_2X_MINI_TRIANGLES]) : 0;
@@ -411,19 +411,13 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
   {
     sh.succTemp = sh.succTrans = sh.totalTris = sh.fullClusters = sh.validParts = 0;
   }
+  __syncthreads();
+  uint32_t accSuccTemp = 0, accSuccTrans = 0, accTris = 0, accFull = 0, accValidParts = 0;  // per warp, folded once at the end
 
-  while(true)
+  for(uint32_t vi = blockIdx.x * CLASSIFY_WARPS + warp; vi < numVisible; vi += gridDim.x * CLASSIFY_WARPS)
   {
-    __syncthreads();
-    if(threadIdx.x == 0)
-      sh.tile = atomicAdd(&p.state->ticket[SLOT_CLASSIFY], 1u);
-    __syncthreads();
-    const uint32_t tile = sh.tile;
-    if(tile >= numTiles)
-      break;
-
-    const uint32_t vi    = tile * CLASSIFY_WARPS + warp;
-    const bool     valid = vi < numVisible;
+    const bool valid = true;
+    uint32_t*  stash = p.factorStash + size_t(vi) * maxT * 3;
 
     // ---------------- phase 1: load, factors, counts (:154-258) ----------------
     tc_ClusterInfo cinfo{0, 0};
@@ -445,42 +439,62 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
       firstLocalVertex   = ch.z;
       firstLocalTriangle = ch.w;
       const float* positions = reinterpret_cast<const float*>(inst->positions);
-      float m[16];
-#pragma unroll
-      for(int k = 0; k < 16; k++)
-        m[k] = inst->worldMatrix[k];
-      for(uint32_t v = lane; v < numVertices; v += 32)
-      {
-        F3 o = ld_f3(positions, firstLocalVertex + v);
-        sObj[v * 3 + 0] = o.x; sObj[v * 3 + 1] = o.y; sObj[v * 3 + 2] = o.z;
-        F3 w = xtransform_point(m, o);
-        float d = xdistance3(w, fcst.eye);
-        reinterpret_cast<float4*>(sWorld)[v] = make_float4(w.x, w.y, w.z, d);
-      }
-      __syncwarp();
-
       const bool hidden = flag_culling(p) && (instanceStates[cinfo.instanceID] & TC_INSTANCE_VISIBLE_BIT) == 0;
-      if(hidden)
-        simpleCount = numTriangles;
+      if(MODE == 0)
+      {
+        float m[16];
+#pragma unroll
+        for(int k = 0; k < 16; k++)
+          m[k] = inst->worldMatrix[k];
+        if(!hidden)
+          for(uint32_t v = lane; v < numVertices; v += 32)
+          {
+            F3 o = ld_f3(positions, firstLocalVertex + v);
+            F3 w = xtransform_point(m, o);
+            float d = xdistance3(w, fcst.eye);
+            reinterpret_cast<float4*>(sWorld)[v] = make_float4(w.x, w.y, w.z, d);
+          }
+        __syncwarp();
+        if(hidden)
+          simpleCount = numTriangles;
+        else
+        {
+          const uint8_t* localTriangles = reinterpret_cast<const uint8_t*>(inst->clusterLocalTriangles) + firstLocalTriangle;
+          for(uint32_t base = 0; base < numTriangles; base += 32)
+          {
+            uint32_t tri = base + lane;
+            bool     tv  = tri < numTriangles;
+            uint32_t f[3] = {1, 1, 1};
+            if(tv)
+            {
+              uint32_t i0 = __ldg(localTriangles + tri * 3 + 0), i1 = __ldg(localTriangles + tri * 3 + 1), i2 = __ldg(localTriangles + tri * 3 + 2);
+              float4   a = reinterpret_cast<const float4*>(sWorld)[i0], b = reinterpret_cast<const float4*>(sWorld)[i1], c = reinterpret_cast<const float4*>(sWorld)[i2];
+              tess_factors(fcst, F3{a.x, a.y, a.z}, F3{b.x, b.y, b.z}, F3{c.x, c.y, c.z}, a.w, b.w, c.w, f);
+              const uint32_t w0 = f[0] | (i0 << 24), w1 = f[1] | (i1 << 24), w2 = f[2] | (i2 << 24);
+              sFactors[tri * 3 + 0] = w0; sFactors[tri * 3 + 1] = w1; sFactors[tri * 3 + 2] = w2;
+              stash[tri * 3 + 0] = w0; stash[tri * 3 + 1] = w1; stash[tri * 3 + 2] = w2;
+            }
+            uint32_t mx = max(max(f[0], f[1]), f[2]);
+            simpleCount += __popc(__ballot_sync(0xffffffffu, tv && mx == 1));
+          }
+        }
+      }
       else
       {
-        const uint8_t* localTriangles = reinterpret_cast<const uint8_t*>(inst->clusterLocalTriangles) + firstLocalTriangle;
-        for(uint32_t base = 0; base < numTriangles; base += 32)
+        if(hidden)
+          simpleCount = numTriangles;
+        else
         {
-          uint32_t tri = base + lane;
-          bool     tv  = tri < numTriangles;
-          uint32_t f[3] = {1, 1, 1};
-          if(tv)
+          for(uint32_t i = lane; i < numTriangles * 3; i += 32)
+            sFactors[i] = __ldcs(stash + i);
+          __syncwarp();
+          for(uint32_t base = 0; base < numTriangles; base += 32)
           {
-            uint32_t i0 = __ldg(localTriangles + tri * 3 + 0), i1 = __ldg(localTriangles + tri * 3 + 1), i2 = __ldg(localTriangles + tri * 3 + 2);
-            float4   a = reinterpret_cast<const float4*>(sWorld)[i0], b = reinterpret_cast<const float4*>(sWorld)[i1], c = reinterpret_cast<const float4*>(sWorld)[i2];
-            tess_factors(fcst, F3{a.x, a.y, a.z}, F3{b.x, b.y, b.z}, F3{c.x, c.y, c.z}, a.w, b.w, c.w, f);
-            sFactors[tri * 3 + 0] = f[0] | (i0 << 24);
-            sFactors[tri * 3 + 1] = f[1] | (i1 << 24);
-            sFactors[tri * 3 + 2] = f[2] | (i2 << 24);
+            uint32_t tri = base + lane;
+            bool     tv  = tri < numTriangles;
+            uint32_t mx  = tv ? max(max(sFactors[tri * 3] & 0xFFFFFF, sFactors[tri * 3 + 1] & 0xFFFFFF), sFactors[tri * 3 + 2] & 0xFFFFFF) : 0;
+            simpleCount += __popc(__ballot_sync(0xffffffffu, tv && mx == 1));
           }
-          uint32_t mx = max(max(f[0], f[1]), f[2]);
-          simpleCount += __popc(__ballot_sync(0xffffffffu, tv && mx == 1));
         }
       }
       __syncwarp();
@@ -507,7 +521,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
         tup.v[T_VERT] += vertexSize;
         tup.d += clasDataSize;
       }
-      if(simpleCount != numTriangles)
+      if(MODE == 0 && simpleCount != numTriangles)
       {
         for(uint32_t base = 0; base < numTriangles; base += 32)
         {
@@ -539,45 +553,18 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
         }
       }
     }
-    if(lane == 0)
-      sh.warpTuple[warp] = tup;
-    __syncthreads();
-
-    // ---------------- tile scan + look-back ----------------
-    if(warp == 0)
+    if(MODE == 0)
     {
-      ScanTuple total;
-      total.zero();
       if(lane == 0)
-      {
-        for(int w = 0; w < CLASSIFY_WARPS; w++)
-        {
-          sh.warpPrefix[w] = total;
-          total.add(sh.warpTuple[w]);
-        }
-      }
-#pragma unroll
-      for(int i = 0; i < 6; i++)
-        total.v[i] = __shfl_sync(0xffffffffu, total.v[i], 0);
-      total.d = __shfl_sync(0xffffffffu, total.d, 0);
-      ScanTuple excl = lookback_exclusive(descs, tile, total, epoch);
-      if(lane == 0)
-      {
-        for(int w = 0; w < CLASSIFY_WARPS; w++)
-          sh.warpPrefix[w].add(excl);
-        if(tile == numTiles - 1)
-        {  // grand totals for the setup step
-          excl.add(total);
-          st_tuple(reinterpret_cast<ScanTuple*>(&descs[numTiles].aggregate), excl);
-        }
-      }
+        st_tuple(&tuples[vi], tup);
+      __syncwarp();
+      continue;
     }
-    __syncthreads();
+    ScanTuple run = ld_tuple(&tuples[vi]);  // exclusive prefix written by k_classify_scan
 
     // ---------------- phase 2..4: emit in canonical order ----------------
     if(valid)
     {
-      ScanTuple run = sh.warpPrefix[warp];
       uint32_t  succTemp = 0, succTrans = 0, totalTris = 0, validParts = 0;
       const uint32_t instanceID = cinfo.instanceID, clusterID = cinfo.clusterID;
       const DisplacementConsts dc = displacement_consts(p, *inst);
@@ -652,6 +639,15 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
           totalTris += simpleCount;
 
           // displaced copy of the cluster vertices (:465-488)
+          {
+            const float* positions = reinterpret_cast<const float*>(inst->positions);
+            for(uint32_t v = lane; v < numVertices; v += 32)
+            {
+              F3 o = ld_f3(positions, firstLocalVertex + v);
+              sObj[v * 3 + 0] = o.x; sObj[v * 3 + 1] = o.y; sObj[v * 3 + 2] = o.z;
+            }
+            __syncwarp();
+          }
           const float* normals   = reinterpret_cast<const float*>(inst->normals);
           const float* texcoords = reinterpret_cast<const float*>(inst->texcoords);
           for(uint32_t v = lane; v < numVertices; v += 32)
@@ -868,15 +864,23 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
       validParts = max(validParts, __shfl_xor_sync(0xffffffffu, validParts, 4));
       validParts = max(validParts, __shfl_xor_sync(0xffffffffu, validParts, 2));
       validParts = max(validParts, __shfl_xor_sync(0xffffffffu, validParts, 1));
-      if(lane == 0)
-      {
-        if(succTemp) atomicAdd(&sh.succTemp, succTemp);
-        if(succTrans) atomicAdd(&sh.succTrans, succTrans);
-        if(totalTris) atomicAdd(&sh.totalTris, totalTris);
-        if(clusterLevel && isFull) atomicAdd(&sh.fullClusters, 1u);
-        if(validParts) atomicMax(&sh.validParts, validParts);
-      }
+      accSuccTemp += succTemp;
+      accSuccTrans += succTrans;
+      accTris += totalTris;
+      accFull += (clusterLevel && isFull) ? 1u : 0u;
+      accValidParts = max(accValidParts, validParts);
     }
+    __syncwarp();  // the per-warp shared staging is reused by the next cluster
+  }
+  if(MODE == 0)
+    return;
+  if(lane == 0)
+  {
+    if(accSuccTemp) atomicAdd(&sh.succTemp, accSuccTemp);
+    if(accSuccTrans) atomicAdd(&sh.succTrans, accSuccTrans);
+    if(accTris) atomicAdd(&sh.totalTris, accTris);
+    if(accFull) atomicAdd(&sh.fullClusters, accFull);
+    if(accValidParts) atomicMax(&sh.validParts, accValidParts);
   }
 
   // ---------------- CTA epilogue: stats + last-CTA setup (BUILD_SETUP_SPLIT, build_setup.comp.glsl:150-167) ----
@@ -895,8 +899,14 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
       __threadfence();
       ScanTuple tot;
       tot.zero();
-      if(numTiles > 0)
-        tot = ld_tuple(reinterpret_cast<const ScanTuple*>(&descs[numTiles].aggregate));
+      if(numVisible > 0)
+      {
+        const volatile uint32_t* ct = p.state->classTotal;
+#pragma unroll
+        for(int i = 0; i < 6; i++)
+          tot.v[i] = ct[i];
+        tot.d = (unsigned long long)ct[6] | ((unsigned long long)ct[7] << 32);
+      }
       tc_SceneBuilding* b = p.build;
       b->genClusterCounter     = tot.v[T_TEMP] + tot.v[T_TRANS];
       b->genClusterDataCounter = tot.d;
@@ -920,6 +930,114 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
       s->hiAfterClassify    = tot.v[T_HI];
       s->partSegEnd[0]      = min(lo, *(volatile uint32_t*)&s->validParts);
       s->numPartSegs        = 1;
+    }
+  }
+}
+
+// exclusive prefix of the classify tuples in canonical order, in place.  Tile = 1024 tuples per CTA (4 per thread),
+// decoupled look-back across tiles (a handful of tiles even for millions of clusters).
+constexpr int CSCAN_THREADS = 256;
+constexpr int CSCAN_PER_THREAD = 4;
+constexpr int CSCAN_TILE = CSCAN_THREADS * CSCAN_PER_THREAD;
+
+__device__ __forceinline__ ScanTuple warp_inclusive_tuple(ScanTuple t)
+{
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for(int d = 1; d < 32; d <<= 1)
+  {
+    ScanTuple o;
+#pragma unroll
+    for(int i = 0; i < 6; i++)
+      o.v[i] = __shfl_up_sync(0xffffffffu, t.v[i], d);
+    o.d = __shfl_up_sync(0xffffffffu, t.d, d);
+    if(lane >= uint32_t(d))
+      t.add(o);
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(CSCAN_THREADS) k_classify_scan(Params p, const uint32_t* epochCounter)
+{
+  __shared__ ScanTuple warpTotals[CSCAN_THREADS / 32];
+  __shared__ ScanTuple tileExclusive;
+  __shared__ uint32_t  shTile;
+  const uint32_t epoch      = *epochCounter + SLOT_CLASSIFY;
+  const uint32_t numVisible = p.build->visibleClusterCounter;
+  const uint32_t numTiles   = (numVisible + CSCAN_TILE - 1) / CSCAN_TILE;
+  ScanTuple*     tuples     = reinterpret_cast<ScanTuple*>(p.classTuples);
+  LookbackDesc*  descs      = reinterpret_cast<LookbackDesc*>(p.lookback);
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  while(true)
+  {
+    __syncthreads();
+    if(threadIdx.x == 0)
+      shTile = atomicAdd(&p.state->ticket[SLOT_CLASSIFY], 1u);
+    __syncthreads();
+    const uint32_t tile = shTile;
+    if(tile >= numTiles)
+      break;
+    const uint32_t first = tile * CSCAN_TILE + threadIdx.x * CSCAN_PER_THREAD;
+    ScanTuple item[CSCAN_PER_THREAD], local;
+    local.zero();
+#pragma unroll
+    for(int k = 0; k < CSCAN_PER_THREAD; k++)
+    {
+      item[k].zero();
+      if(first + k < numVisible)
+        item[k] = ld_tuple(&tuples[first + k]);
+      local.add(item[k]);
+    }
+    ScanTuple inc = warp_inclusive_tuple(local);
+    if(lane == 31)
+      warpTotals[warp] = inc;
+    __syncthreads();
+    if(warp == 0)
+    {
+      ScanTuple total;
+      total.zero();
+      if(lane == 0)
+        for(int w = 0; w < CSCAN_THREADS / 32; w++)
+        {
+          ScanTuple tmp = warpTotals[w];
+          warpTotals[w] = total;  // exclusive over warps
+          total.add(tmp);
+        }
+#pragma unroll
+      for(int i = 0; i < 6; i++)
+        total.v[i] = __shfl_sync(0xffffffffu, total.v[i], 0);
+      total.d = __shfl_sync(0xffffffffu, total.d, 0);
+      ScanTuple excl = lookback_exclusive(descs, tile, total, epoch);
+      if(lane == 0)
+      {
+        tileExclusive = excl;
+        if(tile == numTiles - 1)
+        {
+          excl.add(total);
+          uint32_t* ct = p.state->classTotal;
+#pragma unroll
+          for(int i = 0; i < 6; i++)
+            ct[i] = excl.v[i];
+          ct[6] = uint32_t(excl.d);
+          ct[7] = uint32_t(excl.d >> 32);
+        }
+      }
+    }
+    __syncthreads();
+    ScanTuple run = tileExclusive;
+    run.add(warpTotals[warp]);
+    ScanTuple exclLane = inc;  // inclusive over lanes -> exclusive for this thread
+#pragma unroll
+    for(int i = 0; i < 6; i++)
+      exclLane.v[i] -= local.v[i];
+    exclLane.d -= local.d;
+    run.add(exclLane);
+#pragma unroll
+    for(int k = 0; k < CSCAN_PER_THREAD; k++)
+    {
+      if(first + k < numVisible)
+        st_tuple(&tuples[first + k], run);
+      run.add(item[k]);
     }
   }
 }
@@ -1412,7 +1530,7 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
     shTris = 0;
   }
   uint32_t accSucc = 0, accTris = 0;  // per-warp statistics, folded once at the end
-  const cudaTextureObject_t uniformTex = (DISPLACED && p.numTextures == 1) ? p.textures[0].gather : 0;  // warp-uniform handle
+  const cudaTextureObject_t uniformTex = (DISPLACED && p.numTextures == 1) ? p.texturesC[0].gather : 0;  // warp-uniform handle
 
   // One tile ahead: while a warp generates the vertices of tile k it already holds the ticket of its next tile, has
   // loaded those parts, scanned them and published their aggregate -- successors never wait on this warp's heavy work
@@ -1554,13 +1672,7 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
         F3     o[INST_SLOT];
 #pragma unroll
         for(int i = 0; i < INST_SLOT; i++)
-        {
-          // packed (u | v << 16) pattern vertex: one 32-bit load; u16 -> float without the conversion pipe
-          // (2^23 + n has n in its low mantissa bits); the 1/32768 scale is folded into the record's affine map
-          const uint32_t pk = __ldg(&p.tblVertices[fv + min(uint32_t(i), cnt - 1u)]);
-          q[i].x = __uint_as_float(0x4B000000u | (pk & 0xFFFFu)) - 8388608.0f;
-          q[i].y = __uint_as_float(0x4B000000u | (pk >> 16)) - 8388608.0f;
-        }
+          q[i] = __ldg(&p.tblVerticesF[fv + min(uint32_t(i), cnt - 1u)]);
         eval_part_n<DISPLACED, INST_SLOT>(rec, q, o, uniformTex);
         if(ANIM)
         {
@@ -1874,9 +1986,10 @@ size_t classify_smem_bytes(uint32_t clusterVertices, uint32_t clusterTriangles)
 int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, KernelOccupancy* occ)
 {
   size_t smem = classify_smem_bytes(clusterVertices, clusterTriangles);
-  if(cudaFuncSetAttribute(k_cluster_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+  if(cudaFuncSetAttribute(k_cluster_classify<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess
+     || cudaFuncSetAttribute(k_cluster_classify<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
     return -1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->classify, k_cluster_classify, CLASSIFY_THREADS, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->classify, k_cluster_classify<1>, CLASSIFY_THREADS, smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->split, k_triangle_split, SPLIT_THREADS, 0);
   const void* variants[4] = {(const void*)k_instantiate<false, false>, (const void*)k_instantiate<false, true>, (const void*)k_instantiate<true, false>,
                              (const void*)k_instantiate<true, true>};
@@ -1889,7 +2002,7 @@ int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, Kerne
 
 uint32_t lookback_tiles_needed(uint32_t maxVisible, uint32_t maxSplit, uint32_t maxPart)
 {
-  uint32_t a = (maxVisible + CLASSIFY_WARPS - 1) / CLASSIFY_WARPS;
+  uint32_t a = (maxVisible + CSCAN_TILE - 1) / CSCAN_TILE;
   uint32_t b = (maxSplit + SPLIT_THREADS - 1) / SPLIT_THREADS;
   uint32_t c = 0;  // the instantiate scan has its own 16-byte descriptors (lookback16_tiles_needed)
   uint32_t m = a > b ? a : b;
@@ -1899,6 +2012,7 @@ uint32_t lookback_tiles_needed(uint32_t maxVisible, uint32_t maxSplit, uint32_t 
 
 size_t lookback_desc_bytes() { return sizeof(LookbackDesc); }
 uint32_t classify_tile_clusters() { return CLASSIFY_WARPS; }
+size_t   classify_tuple_bytes() { return sizeof(ScanTuple); }
 uint32_t lookback16_tiles_needed(uint32_t maxPart) { return (maxPart + 31) / 32 + 2; }
 size_t frame_state_bytes() { return sizeof(FrameState); }
 
@@ -1918,7 +2032,10 @@ void launch_clusters_cull(const Params& p, cudaStream_t s)
 }
 void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s)
 {
-  k_cluster_classify<<<grid, CLASSIFY_THREADS, classify_smem_bytes(p.clusterVertices, p.clusterTriangles), s>>>(p, epochCounter);
+  const size_t smem = classify_smem_bytes(p.clusterVertices, p.clusterTriangles);
+  k_cluster_classify<0><<<grid, CLASSIFY_THREADS, smem, s>>>(p);
+  k_classify_scan<<<148, CSCAN_THREADS, 0, s>>>(p, epochCounter);
+  k_cluster_classify<1><<<grid, CLASSIFY_THREADS, smem, s>>>(p);
 }
 void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32_t pass, bool lastPass, uint32_t grid, cudaStream_t s)
 {

@@ -19,6 +19,7 @@ int      configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, 
 uint32_t lookback_tiles_needed(uint32_t maxVisible, uint32_t maxSplit, uint32_t maxPart);
 size_t   lookback_desc_bytes();
 uint32_t classify_tile_clusters();
+size_t   classify_tuple_bytes();
 uint32_t lookback16_tiles_needed(uint32_t maxPart);
 size_t   frame_state_bytes();
 
