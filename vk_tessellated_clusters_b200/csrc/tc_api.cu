@@ -310,8 +310,10 @@ int enqueue_build(tc_context* c)
   }
   {
     StageScope sc(c, TC_STAGE_CLUSTER_CLASSIFY);
-    // count / emit have no inter-CTA ordering: one CTA per 8 clusters, the hardware scheduler balances them
+    // count / emit have no inter-CTA ordering (grid-stride over clusters); cap the grid so that the per-CTA epilogue
+    // (statistics atomics + fence) stays negligible for scenes with millions of clusters
     uint32_t grid = std::max(1u, (std::min(c->totalClusters, c->maxVisible) + tc::classify_tile_clusters() - 1) / tc::classify_tile_clusters());
+    grid          = std::min(grid, uint32_t(c->numSMs) * 32u);
     tc::launch_cluster_classify(p, c->dEpoch, grid, s);  // count -> scan -> emit
     launches += 3;
   }

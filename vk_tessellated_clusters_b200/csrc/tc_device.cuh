@@ -524,6 +524,19 @@ __device__ __forceinline__ float sample_displacement(const DeviceTexture& t, flo
   return fmaf(bot - top, ay, top);
 }
 
+// Same sampler definition through the texture unit: tex2Dgather returns the exact 2x2 texel footprint (aimed at the corner
+// shared by the four texels, so the footprint is unambiguous; hardware repeat addressing), the bilinear weights are fp32.
+__device__ __forceinline__ float sample_displacement_gather(const DeviceTexture& t, float u, float v)
+{
+  const float W = float(t.width), H = float(t.height);
+  const float x = fmaf(u, W, -0.5f), y = fmaf(v, H, -0.5f);
+  const float fx = floorf(x), fy = floorf(y);
+  const float ax = x - fx, ay = y - fy;
+  const float4 g = tex2Dgather<float4>(t.gather, __fdividef(fx + 1.0f, W), __fdividef(fy + 1.0f, H), 0);  // (t01, t11, t10, t00)
+  const float top = fmaf(g.z - g.w, ax, g.w), bot = fmaf(g.y - g.x, ax, g.x);
+  return fmaf(bot - top, ay, top);
+}
+
 struct DisplacementConsts
 {
   float scale;   // inst.displacementScale * view.displacementScale

@@ -292,7 +292,7 @@ __device__ __forceinline__ F3 generate_vertex(const Params& p, const BaseTriangl
     F3    n  = fma3(b.nrm[2], r2, fma3(b.nrm[1], r1, b.nrm[0] * r0));
     float tu = fmaf(b.tu[2], r2, fmaf(b.tu[1], r1, b.tu[0] * r0));
     float tv = fmaf(b.tv[2], r2, fmaf(b.tv[1], r1, b.tv[0] * r0));
-    float h  = fmaf(sample_displacement(p.textures[dc.texture], tu, tv), dc.scale, dc.offset);
+    float h  = fmaf(sample_displacement_gather(p.textures[dc.texture], tu, tv), dc.scale, dc.offset);
     float s  = h * rsqrtf(dot3(n, n));
     pos      = fma3(n, s, pos);
   }
@@ -331,18 +331,27 @@ static __device__ __noinline__ void emit_mini_vertices(const tc_RenderInstance* 
   }
 }
 
-// cold path: displaced (and optionally animated) copy of one original cluster vertex (cluster_classify.comp.glsl:465-488)
-static __device__ __noinline__ F3 displace_cluster_vertex(const tc_FrameConstants* view, const DeviceTexture* texture, float scale, float offset, uint32_t flags,
-                                                          F3 o, F3 n, float tu, float tv, uint32_t instanceID, float geoSize)
+// cold path: procedural ripple of one vertex (displacement.glsl:106-120), kept out of line because of its trig slow paths
+static __device__ __noinline__ F3 ripple_vertex(const tc_FrameConstants* view, F3 o, uint32_t instanceID, float geoSize)
 {
-  if(texture)
-  {
-    float h = fmaf(sample_displacement(*texture, tu, tv), scale, offset);
-    o       = fma3(n, h * rsqrtf(dot3(n, n)), o);
-  }
-  if(flags & TC_FLAG_ANIMATION)
-    o = ripple_deform(view[0], o, instanceID, geoSize);
-  return o;
+  return ripple_deform(view[0], o, instanceID, geoSize);
+}
+
+// warp copy of nFloats staged floats to global memory with aligned 128-bit stores; stage[shift + i] <-> dst[i], where
+// shift = (dst float index) & 3 keeps the 16-byte phases of the shared and global addresses equal
+__device__ __forceinline__ void flush_floats(const float* stage, float* dst, uint32_t shift, uint32_t nFloats, uint32_t lane)
+{
+  const uint32_t head = min(nFloats, (4u - shift) & 3u);
+  if(lane < head)
+    dst[lane] = stage[shift + lane];
+  const uint32_t bodyVec = (nFloats - head) >> 2;
+  const float4*  s4 = reinterpret_cast<const float4*>(stage + shift + head);
+  float4*        d4 = reinterpret_cast<float4*>(dst + head);
+  for(uint32_t i = lane; i < bodyVec; i += 32)
+    __stcs(d4 + i, s4[i]);
+  const uint32_t tailStart = head + (bodyVec << 2);
+  if(lane < nFloats - tailStart)
+    dst[tailStart + lane] = stage[shift + tailStart + lane];
 }
 
 #ifndef TC_CLASSIFY_WARPS
@@ -638,30 +647,32 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
           }
           totalTris += simpleCount;
 
-          // displaced copy of the cluster vertices (:465-488)
+          // displaced copy of the cluster vertices (:465-488): staged in shared memory, flushed with 128-bit stores
           {
             const float* positions = reinterpret_cast<const float*>(inst->positions);
+            const float* normals   = reinterpret_cast<const float*>(inst->normals);
+            const float* texcoords = reinterpret_cast<const float*>(inst->texcoords);
+            const size_t   dstFloat = size_t(vertexOffset) * 3;
+            const uint32_t shift    = uint32_t(dstFloat & 3);
+            float*         sOut     = sWorld;  // unused in emit mode: maxV * 4 floats >= maxV * 3 + 3
             for(uint32_t v = lane; v < numVertices; v += 32)
             {
-              F3 o = ld_f3(positions, firstLocalVertex + v);
-              sObj[v * 3 + 0] = o.x; sObj[v * 3 + 1] = o.y; sObj[v * 3 + 2] = o.z;
+              const uint32_t vertexIndex = firstLocalVertex + v;
+              F3 o = ld_f3(positions, vertexIndex);
+              if(dc.texture >= 0)
+              {
+                const F3    n  = ld_f3(normals, vertexIndex);
+                const float tu = __ldg(texcoords + size_t(vertexIndex) * 2), tv = __ldg(texcoords + size_t(vertexIndex) * 2 + 1);
+                const float h  = fmaf(sample_displacement_gather(p.texturesC[dc.texture], tu, tv), dc.scale, dc.offset);
+                o = fma3(n, h * fast_rsqrt(dot3(n, n)), o);
+              }
+              if(flag_animation(p))
+                o = ripple_vertex(p.view, o, instanceID, geoSize);
+              sOut[shift + v * 3 + 0] = o.x; sOut[shift + v * 3 + 1] = o.y; sOut[shift + v * 3 + 2] = o.z;
             }
             __syncwarp();
-          }
-          const float* normals   = reinterpret_cast<const float*>(inst->normals);
-          const float* texcoords = reinterpret_cast<const float*>(inst->texcoords);
-          for(uint32_t v = lane; v < numVertices; v += 32)
-          {
-            F3 o = {sObj[v * 3 + 0], sObj[v * 3 + 1], sObj[v * 3 + 2]};
-            if(dc.texture >= 0 || flag_animation(p))
-            {
-              uint32_t vertexIndex = firstLocalVertex + v;
-              F3       n  = ld_f3(normals, vertexIndex);
-              float    tu = __ldg(texcoords + size_t(vertexIndex) * 2), tv = __ldg(texcoords + size_t(vertexIndex) * 2 + 1);
-              o = displace_cluster_vertex(p.view, dc.texture >= 0 ? &p.textures[dc.texture] : nullptr, dc.scale, dc.offset, p.flags, o, n, tu, tv, instanceID, geoSize);
-            }
-            float* dst = genVertices + size_t(vertexOffset + v) * 3;
-            dst[0] = o.x; dst[1] = o.y; dst[2] = o.z;
+            flush_floats(sOut, genVertices + dstFloat, shift, numVertices * 3, lane);
+            __syncwarp();
           }
           if(transient1X)
           {  // ordered export of the simple triangles (:497-534)

@@ -616,7 +616,7 @@ def config_instances(num_instances=1024, subdiv=6, tex_size=1024, tess_rate_pixe
     scene = _scene([g], inst, [value_noise_texture(tex_size)])
     r = scene.radius
     c = scene.center
-    eye = c + np.array([0.35 * r, -0.35 * r, 0.12 * r])
+    eye = c + np.array([0.35 * r, -0.35 * r, 0.03 * r])  # low over the grid: near instances tessellate, far ones do not
     target = c + np.array([-0.6 * r, 0.6 * r, 0.0])
     fc = make_frame_constants(eye, target, up=(0, 0, 1), near=0.001 * r, far=100 * r, tess_rate_pixels=tess_rate_pixels)
     size, mips, uw, uh, _, _ = hiz_info(int(fc["viewport"][0]), int(fc["viewport"][1]))
