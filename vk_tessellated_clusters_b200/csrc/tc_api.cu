@@ -70,6 +70,7 @@ struct tc_context
   void*             dLookback16 = nullptr;
   void*             dClassTuples = nullptr;
   uint32_t*         dFactorStash = nullptr;
+  uint32_t*         dClassMeta = nullptr;
   FrameStaging*     dFrame     = nullptr;
   FrameStaging*     hFrame     = nullptr;  // pinned
   tc_shard_counts*  dShardCounts = nullptr;
@@ -255,6 +256,7 @@ void fill_params(tc_context* c)
   p.lookback16         = reinterpret_cast<uint4*>(c->dLookback16);
   p.classTuples        = c->dClassTuples;
   p.factorStash        = c->dFactorStash;
+  p.classMeta          = c->dClassMeta;
   p.segLo              = c->segLo;
   p.rankBase           = c->rankBase;
   p.shardBase          = c->dShardBase;
@@ -314,8 +316,8 @@ int enqueue_build(tc_context* c)
     // (statistics atomics + fence) stays negligible for scenes with millions of clusters
     uint32_t grid = std::max(1u, (std::min(c->totalClusters, c->maxVisible) + tc::classify_tile_clusters() - 1) / tc::classify_tile_clusters());
     grid          = std::min(grid, uint32_t(c->numSMs) * 32u);
-    tc::launch_cluster_classify(p, c->dEpoch, grid, s);  // count -> scan -> emit
-    launches += 3;
+    tc::launch_cluster_classify(p, c->dEpoch, grid, s);  // count -> scan -> emit (cluster level) -> emit (triangle level)
+    launches += 4;
   }
   {
     StageScope sc(c, TC_STAGE_SPLIT);
@@ -434,6 +436,7 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   TRY_CUDA(cudaMemset(c->dLookback16, 0, lb16Bytes));
   TRY_RC(dalloc(c->dClassTuples, size_t(c->maxVisible) * tc::classify_tuple_bytes()));
   TRY_RC(dalloc(c->dFactorStash, size_t(c->maxVisible) * config->clusterTriangles * 12));
+  TRY_RC(dalloc(c->dClassMeta, size_t(c->maxVisible) * 4));
   TRY_CUDA(cudaMemset(c->dEpoch, 0, 16));
   TRY_CUDA(cudaMemset(c->dShardBase, 0, 16));
   TRY_CUDA(cudaMemset(c->dReadback, 0, sizeof(tc_Readback)));
@@ -484,7 +487,7 @@ TC_API void tc_destroy(tc_context* c)
     cudaStreamSynchronize(c->stream);
   drop_graph(c);
   free_scene(c);
-  dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dFrame);
+  dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dFrame);
   dfree(c->dShardCounts); dfree(c->dShardBase);
   if(c->hFrame)
     cudaFreeHost(c->hFrame);

@@ -87,6 +87,7 @@ struct Params
   // classify runs as count -> scan -> emit: per visible cluster an 8-word tuple and the packed per-triangle factors
   void*     classTuples;   // ScanTuple[maxVisibleClusters]: counts, then (in place) exclusive prefixes
   uint32_t* factorStash;   // [maxVisibleClusters][clusterTriangles][3]: factor | local vertex index << 24
+  uint32_t* classMeta;     // [maxVisibleClusters]: number of triangles that need no tessellation (simpleCount)
   // blas helpers
   uint32_t* segLo;     // [TC_MAX_SEGMENTS+1][numInstances]
   uint32_t* rankBase;  // [TC_MAX_SEGMENTS+1][numInstances]

@@ -375,9 +375,13 @@ struct ClassifyShared  // only the CTA epilogue's statistics: one cluster per wa
 //   MODE 0 (count): per cluster load vertices, compute the per-triangle edge factors (EXACT), stash them packed in global
 //                   memory and write the cluster's 8-word allocation tuple;
 //   k_classify_scan: exclusive prefix of the tuples in canonical (visible-list) order, in place;
-//   MODE 1 (emit):  per cluster read its prefix + stashed factors and write every record / vertex / index byte.
+//   MODE 1 (emit, cluster level): full-cluster template instantiations and 1X transient builds: records, displaced copies
+//                   of the cluster vertices, ordered index/mapping bytes.  Clusters without such work are skipped at once.
+//   MODE 2 (emit, triangle level): part / split records and 2X mini batches.  Clusters that are entirely simple are skipped.
+// Splitting the emit step keeps both kernels light (registers -> occupancy): scenes dominated by untessellated clusters
+// (hidden instances, far field) are pure streaming work in MODE 1, tessellated scenes are pure record writing in MODE 2.
 template <int MODE>
-__global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_cluster_classify(Params p)
+__global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_CTAS : 3) k_cluster_classify(Params p)
 {
   extern __shared__ __align__(16) uint8_t smemRaw[];
   __shared__ ClassifyShared sh;
@@ -423,10 +427,41 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
   __syncthreads();
   uint32_t accSuccTemp = 0, accSuccTrans = 0, accTris = 0, accFull = 0, accValidParts = 0;  // per warp, folded once at the end
 
-  for(uint32_t vi = blockIdx.x * CLASSIFY_WARPS + warp; vi < numVisible; vi += gridDim.x * CLASSIFY_WARPS)
+  // A warp takes 32 consecutive visible clusters at a time: the lanes fetch the 32 descriptors (ClusterInfo -> cluster
+  // header -> simple-triangle count) in parallel, so the dependent-load chain is paid once per 32 clusters and clusters
+  // with nothing to do in this pass are skipped without touching their data.
+  // (the chunk shrinks to a power of two >= 1 when there are fewer clusters than 32 per launched warp, so small scenes
+  // still spread over the whole chip)
+  uint32_t chunkSize = 32;
+  while(chunkSize > 1 && numVisible / chunkSize < gridDim.x * CLASSIFY_WARPS)
+    chunkSize >>= 1;
+  for(uint32_t chunk = (blockIdx.x * CLASSIFY_WARPS + warp) * chunkSize; chunk < numVisible; chunk += gridDim.x * CLASSIFY_WARPS * chunkSize)
   {
-    const bool valid = true;
-    uint32_t*  stash = p.factorStash + size_t(vi) * maxT * 3;
+    tc_ClusterInfo cinfoL{0, 0};
+    uint4          chL   = make_uint4(0, 0, 0, 0);
+    uint32_t       metaL = 0;
+    bool           needL = false;
+    if(lane < chunkSize && chunk + lane < numVisible)
+    {
+      cinfoL = visibleClusters[chunk + lane];
+      chL    = __ldg(reinterpret_cast<const uint4*>(p.instances[cinfoL.instanceID].clusters) + cinfoL.clusterID);
+      needL  = true;
+      if(MODE != 0)
+      {
+        metaL = __ldg(&p.classMeta[chunk + lane]);
+        const uint32_t nT = chL.x >> 16;
+        const bool clusterLevelL = use1X ? (metaL == nT || metaL > 1) : (metaL == nT);
+        needL = (MODE == 1) ? clusterLevelL : (metaL != nT);
+      }
+    }
+    uint32_t needMask = __ballot_sync(0xffffffffu, needL);
+  while(needMask)
+  {
+    const uint32_t src = __ffs(needMask) - 1;
+    needMask &= needMask - 1;
+    const uint32_t vi    = chunk + src;
+    const bool     valid = true;
+    uint32_t*      stash = p.factorStash + size_t(vi) * maxT * 3;
 
     // ---------------- phase 1: load, factors, counts (:154-258) ----------------
     tc_ClusterInfo cinfo{0, 0};
@@ -440,9 +475,14 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
 
     if(valid)
     {
-      cinfo = visibleClusters[vi];
+      cinfo.instanceID = __shfl_sync(0xffffffffu, cinfoL.instanceID, src);
+      cinfo.clusterID  = __shfl_sync(0xffffffffu, cinfoL.clusterID, src);
       inst  = &p.instances[cinfo.instanceID];
-      const uint4 ch = __ldg(reinterpret_cast<const uint4*>(inst->clusters) + cinfo.clusterID);
+      uint4 ch;
+      ch.x = __shfl_sync(0xffffffffu, chL.x, src);
+      ch.z = __shfl_sync(0xffffffffu, chL.z, src);
+      ch.w = __shfl_sync(0xffffffffu, chL.w, src);
+      const uint32_t metaSimple = __shfl_sync(0xffffffffu, metaL, src);
       numVertices        = ch.x & 0xFFFF;
       numTriangles       = ch.x >> 16;
       firstLocalVertex   = ch.z;
@@ -490,21 +530,11 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
       }
       else
       {
-        if(hidden)
-          simpleCount = numTriangles;
-        else
-        {
+        simpleCount = metaSimple;  // hidden instances were counted as all-simple by the count pass
+        const bool needFactors = (MODE == 2) ? (simpleCount != numTriangles) : (use1X && simpleCount > 1 && simpleCount != numTriangles);
+        if(needFactors)
           for(uint32_t i = lane; i < numTriangles * 3; i += 32)
             sFactors[i] = __ldcs(stash + i);
-          __syncwarp();
-          for(uint32_t base = 0; base < numTriangles; base += 32)
-          {
-            uint32_t tri = base + lane;
-            bool     tv  = tri < numTriangles;
-            uint32_t mx  = tv ? max(max(sFactors[tri * 3] & 0xFFFFFF, sFactors[tri * 3 + 1] & 0xFFFFFF), sFactors[tri * 3 + 2] & 0xFFFFFF) : 0;
-            simpleCount += __popc(__ballot_sync(0xffffffffu, tv && mx == 1));
-          }
-        }
       }
       __syncwarp();
 
@@ -565,7 +595,15 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
     if(MODE == 0)
     {
       if(lane == 0)
+      {
         st_tuple(&tuples[vi], tup);
+        p.classMeta[vi] = simpleCount;
+      }
+      __syncwarp();
+      continue;
+    }
+    if((MODE == 1 && !clusterLevel) || (MODE == 2 && simpleCount == numTriangles))
+    {
       __syncwarp();
       continue;
     }
@@ -595,7 +633,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
         run.v[T_VERT] += vertexSize;
         bool fail = (vertexOffset + vertexSize > p.maxGenVertices) || (genOffset + 1 > p.maxGenClusters) || (dataOffset + clasDataSize > p.maxGenDataBytes)
                     || (use1X && (partOffset + partSize > p.maxPartTriangles));
-        if(!fail)
+        if(!fail && MODE == 1)
         {
           const unsigned long long vertexBuffer = genVerticesAddr + (unsigned long long)(uint32_t)(vertexOffset * 4u * 3u);
           if(!transient1X)
@@ -708,7 +746,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
           run.v[T_TRANS] += 1;
       }
 
-      if(simpleCount != numTriangles)
+      if(MODE == 2 && simpleCount != numTriangles)
       {  // :543-905
         for(uint32_t base = 0; base < numTriangles; base += 32)
         {
@@ -878,10 +916,11 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
       accSuccTemp += succTemp;
       accSuccTrans += succTrans;
       accTris += totalTris;
-      accFull += (clusterLevel && isFull) ? 1u : 0u;
+      accFull += (MODE == 1 && clusterLevel && isFull) ? 1u : 0u;
       accValidParts = max(accValidParts, validParts);
     }
     __syncwarp();  // the per-warp shared staging is reused by the next cluster
+  }
   }
   if(MODE == 0)
     return;
@@ -903,6 +942,8 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, TC_CLASSIFY_MIN_CTAS) k_clus
     if(sh.totalTris) atomicAdd(&p.readback->numTotalTriangles, sh.totalTris);
     if(sh.fullClusters) atomicAdd(&p.readback->numFullClusters, sh.fullClusters);
     if(sh.validParts) atomicMax(&p.state->validParts, sh.validParts);
+    if(MODE != 2)
+      return;  // the setup step runs once, after the last emit kernel (stream order makes MODE 1's counters visible)
     __threadfence();
     uint32_t done = atomicAdd(&p.state->done[SLOT_CLASSIFY], 1u);
     if(done == gridDim.x - 1)
@@ -1998,7 +2039,8 @@ int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, Kerne
 {
   size_t smem = classify_smem_bytes(clusterVertices, clusterTriangles);
   if(cudaFuncSetAttribute(k_cluster_classify<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess
-     || cudaFuncSetAttribute(k_cluster_classify<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+     || cudaFuncSetAttribute(k_cluster_classify<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess
+     || cudaFuncSetAttribute(k_cluster_classify<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
     return -1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->classify, k_cluster_classify<1>, CLASSIFY_THREADS, smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->split, k_triangle_split, SPLIT_THREADS, 0);
@@ -2047,6 +2089,7 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
   k_cluster_classify<0><<<grid, CLASSIFY_THREADS, smem, s>>>(p);
   k_classify_scan<<<148, CSCAN_THREADS, 0, s>>>(p, epochCounter);
   k_cluster_classify<1><<<grid, CLASSIFY_THREADS, smem, s>>>(p);
+  k_cluster_classify<2><<<grid, CLASSIFY_THREADS, smem, s>>>(p);
 }
 void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32_t pass, bool lastPass, uint32_t grid, cudaStream_t s)
 {
