@@ -197,14 +197,14 @@ def main():
             (gpu.frame_graph if use_graph else gpu.frame)(fcs)
             return None
         sharding_, counts_t_ = shard
-        gpu.frame_build(fcs)
+        (gpu.frame_build_graph if use_graph else gpu.frame_build)(fcs)
         gpu.copy_async(counts_t_.data_ptr(), gpu.device_shard_counts(), 32)
         gathered, base = sharding_.exchange_shard_counts(counts_t_)
         gpu.copy_async(gpu.device_shard_base(), base.data_ptr(), 8)
-        gpu.frame_insert()
+        (gpu.frame_insert_graph if use_graph else gpu.frame_insert)()
         return gathered
 
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
     # clocks are sampled from before the warm-up to the end of the measurements (nvidia-smi takes ~0.5 s to start)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -238,7 +238,7 @@ def main():
             gpu.flush_l2()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            gathered = one_frame(False)
+            gathered = one_frame(use_graph)
             e1.record()
             e1.synchronize()
             frame_ms.append(e0.elapsed_time(e1))

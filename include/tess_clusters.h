@@ -143,6 +143,11 @@ TC_API int tc_frame_insert(tc_context* ctx);               /* :661-686  blas_set
 /* Same frame replayed from a captured CUDA graph (frame constants re-read from a pinned staging copy). */
 TC_API int tc_frame_graph(tc_context* ctx, const void* frameConstants, size_t strideBytes,
                           const float* viewPosOverride);
+/* The two halves as separately captured graphs, for callers that put work (driver CLAS builds, the multi-GPU
+ * allgather) between them. */
+TC_API int tc_frame_build_graph(tc_context* ctx, const void* frameConstants, size_t strideBytes,
+                                const float* viewPosOverride);
+TC_API int tc_frame_insert_graph(tc_context* ctx);
 
 TC_API int tc_sync(tc_context* ctx);
 

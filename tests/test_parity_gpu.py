@@ -68,6 +68,10 @@ def test_graph_replay_and_split_entry_points_match_plain_frame(table, oracle_lib
     gpu.frame_build(fcs)
     gpu.frame_insert()
     compare_frame(gpu, orc, scene_scale=scene.radius)
+    for _ in range(2):  # the two halves as separately captured graphs (multi-GPU path)
+        gpu.frame_build_graph(fcs)
+        gpu.frame_insert_graph()
+    compare_frame(gpu, orc, scene_scale=scene.radius)
     assert gpu.last_launch_count() >= 10
     gpu.close()
     orc.close()

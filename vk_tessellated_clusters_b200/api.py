@@ -299,6 +299,12 @@ class TessClusters(Binding):
     def frame_graph(self, frame_constants, view_pos=None):
         self._check(self.lib.tc_frame_graph(self._ctx, *self._fc_args(frame_constants, view_pos)), "frame_graph")
 
+    def frame_build_graph(self, frame_constants, view_pos=None):
+        self._check(self.lib.tc_frame_build_graph(self._ctx, *self._fc_args(frame_constants, view_pos)), "frame_build_graph")
+
+    def frame_insert_graph(self):
+        self._check(self.lib.tc_frame_insert_graph(self._ctx), "frame_insert_graph")
+
     def sync(self):
         self._check(self.lib.tc_sync(self._ctx), "sync")
 

@@ -116,7 +116,7 @@ struct tc_context
   uint32_t    lastLaunches = 0;
 
   // graph
-  cudaGraphExec_t graphExec = nullptr;
+  cudaGraphExec_t graphExec = nullptr, graphBuild = nullptr, graphInsert = nullptr;
 };
 
 namespace {
@@ -179,11 +179,12 @@ void free_scene(tc_context* c)
 
 void drop_graph(tc_context* c)
 {
-  if(c->graphExec)
-  {
-    cudaGraphExecDestroy(c->graphExec);
-    c->graphExec = nullptr;
-  }
+  for(cudaGraphExec_t* g : {&c->graphExec, &c->graphBuild, &c->graphInsert})
+    if(*g)
+    {
+      cudaGraphExecDestroy(*g);
+      *g = nullptr;
+    }
 }
 
 int upload_template(tc_context* c)
@@ -779,6 +780,51 @@ TC_API int tc_frame_graph(tc_context* c, const void* frameConstants, size_t stri
   }
   CUDA_TRY(cudaGraphLaunch(c->graphExec, c->stream));
   return TC_OK;
+}
+
+namespace {
+// capture `what` (0: build half, 1: insert half) once and replay it
+int replay_half(tc_context* c, cudaGraphExec_t& exec, int what)
+{
+  if(!exec)
+  {
+    bool savedTimers = c->timers;
+    c->timers        = false;
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int         rc = what == 0 ? enqueue_build(c) : enqueue_insert(c);
+    cudaError_t e  = cudaStreamEndCapture(c->stream, &graph);
+    c->timers      = savedTimers;
+    if(rc != TC_OK)
+      return rc;
+    if(e != cudaSuccess)
+      return fail(TC_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if(e != cudaSuccess)
+      return fail(TC_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+  }
+  CUDA_TRY(cudaGraphLaunch(exec, c->stream));
+  return TC_OK;
+}
+}  // namespace
+
+TC_API int tc_frame_build_graph(tc_context* c, const void* frameConstants, size_t strideBytes, const float* viewPosOverride)
+{
+  int rc = check_ready(c);
+  if(rc)
+    return rc;
+  if((rc = stage_frame_inputs(c, frameConstants, strideBytes, viewPosOverride)))
+    return rc;
+  return replay_half(c, c->graphBuild, 0);
+}
+
+TC_API int tc_frame_insert_graph(tc_context* c)
+{
+  int rc = check_ready(c);
+  if(rc)
+    return rc;
+  return replay_half(c, c->graphInsert, 1);
 }
 
 TC_API int tc_sync(tc_context* c)
