@@ -1516,7 +1516,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
 constexpr int INST_WARPS       = TC_INST_WARPS;
 constexpr int INST_THREADS     = INST_WARPS * 32;
 #ifndef TC_INST_SLOT
-#define TC_INST_SLOT 3
+#define TC_INST_SLOT 6
 #endif
 constexpr int INST_SLOT        = TC_INST_SLOT;      // vertices per lane per iteration (all of one part)
 constexpr int INST_ITER_VERTS  = 32 * INST_SLOT;
@@ -1549,7 +1549,7 @@ __device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint
 }
 
 #ifndef TC_INST_MIN_CTAS
-#define TC_INST_MIN_CTAS 3
+#define TC_INST_MIN_CTAS 2
 #endif
 template <bool DISPLACED, bool ANIM>
 __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(Params p, const uint32_t* epochCounter)
