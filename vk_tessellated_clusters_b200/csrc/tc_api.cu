@@ -96,7 +96,7 @@ struct tc_context
   uint32_t numInstances = 0, totalClusters = 0;
 
   // table
-  void *tblVerticesF = nullptr;
+  void *tblVerticesF = nullptr, *tblSlots = nullptr, *tblSlotBase = nullptr;
   void *tblVertices = nullptr, *tblTriangles = nullptr, *tblEntries = nullptr, *tblTemplAddr = nullptr, *tblTemplSize = nullptr;
   // hiz
   float* hiz = nullptr;
@@ -234,6 +234,8 @@ void fill_params(tc_context* c)
   p.state       = c->dState;
   p.tblVertices  = reinterpret_cast<const uint32_t*>(c->tblVertices);
   p.tblVerticesF = reinterpret_cast<const float2*>(c->tblVerticesF);
+  p.tblSlots     = reinterpret_cast<const float4*>(c->tblSlots);
+  p.tblSlotBase  = reinterpret_cast<const uint32_t*>(c->tblSlotBase);
   p.tblTriangles = reinterpret_cast<const uint32_t*>(c->tblTriangles);
   p.tblEntries   = reinterpret_cast<const tc_TessTableEntry*>(c->tblEntries);
   p.tblTemplAddr = reinterpret_cast<const uint64_t*>(c->tblTemplAddr);
@@ -498,7 +500,7 @@ TC_API void tc_destroy(tc_context* c)
   dfree(c->blasClusterAddresses);
   if(c->cfg.allocClasData)
     dfree(c->genClusterData);
-  dfree(c->tblVerticesF);
+  dfree(c->tblVerticesF); dfree(c->tblSlots); dfree(c->tblSlotBase);
   dfree(c->tblVertices); dfree(c->tblTriangles); dfree(c->tblEntries); dfree(c->tblTemplAddr); dfree(c->tblTemplSize);
   dfree(c->hiz);
   dfree(c->flushBuf);
@@ -534,8 +536,8 @@ TC_API int tc_set_tess_table(tc_context* c, const uint32_t* vertices, uint32_t n
         if(z != y && x > 1)
           lookup[idx3(x, z, y)] = e;
       }
-  dfree(c->tblVerticesF);
-  c->tblVerticesF = nullptr;
+  dfree(c->tblVerticesF); dfree(c->tblSlots); dfree(c->tblSlotBase);
+  c->tblVerticesF = c->tblSlots = c->tblSlotBase = nullptr;
   dfree(c->tblVertices); dfree(c->tblTriangles); dfree(c->tblEntries); dfree(c->tblTemplAddr); dfree(c->tblTemplSize);
   c->tblVertices = c->tblTriangles = c->tblEntries = c->tblTemplAddr = c->tblTemplSize = nullptr;
   int rc;
@@ -555,6 +557,42 @@ TC_API int tc_set_tess_table(tc_context* c, const uint32_t* vertices, uint32_t n
     if((rc = dalloc(c->tblVerticesF, vf.size() * 4)))
       return rc;
     CUDA_TRY(cudaMemcpy(c->tblVerticesF, vf.data(), vf.size() * 4, cudaMemcpyHostToDevice));
+    // Instantiate view of the same vertices: a lane generates TC_INST_SLOT consecutive vertices of one pattern.  Per
+    // pattern the slots are laid out as SLOT/2 planes of numSlots float4, float4 (k, j) = vertices 6j+2k and 6j+2k+1 as
+    // (u_a, u_b, v_a, v_b): the lanes of a part read consecutive float4 (coalesced) and the halves are ready-made
+    // operands of the packed fp32 arithmetic.  The tail of the last slot repeats the last vertex.
+    constexpr uint32_t SLOT = tc::kInstantiateSlot;
+    std::vector<uint32_t> slotBase(TC_TESSTABLE_LOOKUP_ENTRIES, 0);
+    std::vector<float>    slots;
+    for(uint32_t li = 0; li < TC_TESSTABLE_LOOKUP_ENTRIES; li++)
+    {
+      const tc_TessTableEntry& e = lookup[li];
+      if(e.numVertices == 0)
+        continue;
+      // mirrored lookups share their pattern: reuse the block of an earlier identical entry
+      bool shared = false;
+      for(uint32_t lj = 0; lj < li && !shared; lj++)
+        if(lookup[lj].numVertices == e.numVertices && lookup[lj].firstVertex == e.firstVertex)
+        {
+          slotBase[li] = slotBase[lj];
+          shared       = true;
+        }
+      if(shared)
+        continue;
+      const uint32_t numSlots = (e.numVertices + SLOT - 1) / SLOT;
+      slotBase[li]            = uint32_t(slots.size() / 4);
+      for(uint32_t k = 0; k < SLOT / 2; k++)
+        for(uint32_t j = 0; j < numSlots; j++)
+        {
+          const uint32_t va = e.firstVertex + std::min<uint32_t>(j * SLOT + 2 * k, e.numVertices - 1u);
+          const uint32_t vb = e.firstVertex + std::min<uint32_t>(j * SLOT + 2 * k + 1, e.numVertices - 1u);
+          slots.push_back(vf[2 * va]); slots.push_back(vf[2 * vb]); slots.push_back(vf[2 * va + 1]); slots.push_back(vf[2 * vb + 1]);
+        }
+    }
+    if((rc = dalloc(c->tblSlots, slots.size() * 4)) || (rc = dalloc(c->tblSlotBase, slotBase.size() * 4)))
+      return rc;
+    CUDA_TRY(cudaMemcpy(c->tblSlots, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->tblSlotBase, slotBase.data(), slotBase.size() * 4, cudaMemcpyHostToDevice));
   }
   CUDA_TRY(cudaMemcpy(c->tblTriangles, triangles, size_t(numTriangles) * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->tblEntries, lookup.data(), lookup.size() * sizeof(tc_TessTableEntry), cudaMemcpyHostToDevice));

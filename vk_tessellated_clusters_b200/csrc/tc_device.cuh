@@ -60,6 +60,8 @@ struct Params
   // tessellation table
   const uint32_t*          tblVertices;
   const float2*            tblVerticesF;  // same vertices pre-converted to (u, v) floats (exact: /32768)
+  const float4*            tblSlots;      // pattern vertices regrouped for instantiate (TC_INST_SLOT vertices per slot, see tc_api.cu)
+  const uint32_t*          tblSlotBase;   // [lookup index] first float4 of the config in tblSlots
   const uint32_t*          tblTriangles;
   const tc_TessTableEntry* tblEntries;
   const uint64_t*          tblTemplAddr;
@@ -621,13 +623,14 @@ __device__ __forceinline__ F3 eval_pn(const BaseTriangle& b, float u, float v, f
 // per part is folded into a 60-word record once:
 //   words 0..5   affine map pattern (q1,q2) -> base-triangle barycentrics (s,t) = (lambda1, lambda2); the "flipped"
 //                pattern handling (tessellation.glsl:179-189, weights .yxz) is folded into the coefficients
-//   word  6      firstVertex of the pattern in the table      word 7   displacement texture index (-1: none)
+//   word  6      first float4 of the pattern in tblSlots      word 7   number of slots of the pattern
 //   words 8..37  position polynomial in the power basis, P = sum c_jk s^j t^k (10 x float3), converted from the PN
 //                control net of displacement.glsl:47-79 (9 FMA per component instead of 44 mul/add)
 //   words 38,39  displacement scale / offset
-//   words 40..48 normal n0, n1-n0, n2-n0
-//   words 49..54 texel-space texcoord x = u*W-0.5 and y = v*H-0.5 as affine functions of (s,t): X0,X1,X2,Y0,Y1,Y2
-//   words 55,56  1/W, 1/H      words 57,58 cudaTextureObject_t of the gather view      word 59 part index
+//   words 40..47, 56 normal n0, n1-n0, n2-n0 (the last component sits in word 56)
+//   words 48..53 texel-space texcoord x = u*W-0.5 and y = v*H-0.5 as affine functions of (s,t), interleaved for packed
+//                (x,y) arithmetic: X0,Y0,X1,Y1,X2,Y2      words 54,55  1/W, 1/H
+//   words 57,58  cudaTextureObject_t of the gather view      word 59 part index
 // ------------------------------------------------------------------------------------------------------------
 
 #define TC_REC_WORDS 60
@@ -639,7 +642,7 @@ __device__ __forceinline__ void st3(float* dst, F3 v)
 
 __device__ __forceinline__ void build_part_record(const Params& p, const tc_RenderInstance& inst, uint32_t instanceID, uint32_t firstLocalVertex,
                                                   uint32_t i0, uint32_t i1, uint32_t i2, const uint32_t vtxEncoded[3], bool flipped,
-                                                  uint32_t firstPatternVertex, uint32_t partIndex, float* rec)
+                                                  uint32_t slotBase, uint32_t numSlots, uint32_t partIndex, float* rec)
 {
   const float* positions = reinterpret_cast<const float*>(inst.positions);
   const float* normals   = reinterpret_cast<const float*>(inst.normals);
@@ -663,9 +666,9 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
   const float bvO = flipped ? bv[1] : bv[0], bvA = flipped ? bv[0] : bv[1];
   rec[0] = buO; rec[1] = buA - buO; rec[2] = bu[2] - buO;
   rec[3] = bvO; rec[4] = bvA - bvO; rec[5] = bv[2] - bvO;
-  reinterpret_cast<uint32_t*>(rec)[6] = firstPatternVertex;
+  reinterpret_cast<uint32_t*>(rec)[6] = slotBase;
+  reinterpret_cast<uint32_t*>(rec)[7] = numSlots;
   const int texture = (p.numTextures > 0 && inst.displacementIndex >= 0) ? inst.displacementIndex : -1;
-  reinterpret_cast<int*>(rec)[7] = texture;
 
   F3 c00, c10, c01, c20, c02, c11, c30, c03, c21, c12;
   if(flag_pn(p))
@@ -705,7 +708,8 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
   st3(rec + 23, c11); st3(rec + 26, c30); st3(rec + 29, c03); st3(rec + 32, c21); st3(rec + 35, c12);
   rec[38] = texture >= 0 ? inst.displacementScale * p.view[0].displacementScale : 0.0f;
   rec[39] = texture >= 0 ? inst.displacementOffset + p.view[0].displacementOffset : 0.0f;
-  st3(rec + 40, nrm[0]); st3(rec + 43, nrm[1] - nrm[0]); st3(rec + 46, nrm[2] - nrm[0]);
+  st3(rec + 40, nrm[0]); st3(rec + 43, nrm[1] - nrm[0]);
+  rec[46] = nrm[2].x - nrm[0].x; rec[47] = nrm[2].y - nrm[0].y; rec[56] = nrm[2].z - nrm[0].z;
   float W = 1.0f, H = 1.0f;
   unsigned long long texObj = 0;
   if(p.numTextures > 0)
@@ -715,39 +719,13 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
     H      = float(p.texturesC[ti].height);
     texObj = p.texturesC[ti].gather;
   }
-  rec[49] = fmaf(tu[0], W, -0.5f); rec[50] = (tu[1] - tu[0]) * W; rec[51] = (tu[2] - tu[0]) * W;
-  rec[52] = fmaf(tv[0], H, -0.5f); rec[53] = (tv[1] - tv[0]) * H; rec[54] = (tv[2] - tv[0]) * H;
-  rec[55] = 1.0f / W;
-  rec[56] = 1.0f / H;
+  rec[48] = fmaf(tu[0], W, -0.5f); rec[50] = (tu[1] - tu[0]) * W; rec[52] = (tu[2] - tu[0]) * W;
+  rec[49] = fmaf(tv[0], H, -0.5f); rec[51] = (tv[1] - tv[0]) * H; rec[53] = (tv[2] - tv[0]) * H;
+  rec[54] = 1.0f / W;
+  rec[55] = 1.0f / H;
   reinterpret_cast<uint32_t*>(rec)[57] = uint32_t(texObj);
   reinterpret_cast<uint32_t*>(rec)[58] = uint32_t(texObj >> 32);
   reinterpret_cast<uint32_t*>(rec)[59] = partIndex;
-}
-
-// floor(x) for |x| < 2^22 without the XU pipe
-__device__ __forceinline__ float fast_floorf(float x)
-{
-  const float M = 12582912.0f;  // 1.5 * 2^23
-  const float r = __fadd_rn(__fadd_rn(x, M), -M);
-  return r > x ? r - 1.0f : r;
-}
-
-// Register image of a part record.
-struct PartCoeffs
-{
-  float4 r0, r1;                  // affine (s,t) map, first pattern vertex, texture index
-  float4 a, b, c, d, e, f, g, h;  // position polynomial + displacement scale/offset
-  float4 n0, n1, n2, n3, m;       // normal, texel-space texcoord, 1/W, 1/H, texture object, part index
-};
-
-__device__ __forceinline__ void load_part_coeffs(const float4* rec, PartCoeffs& k, bool displaced)
-{
-  k.r0 = rec[0]; k.r1 = rec[1];
-  k.a = rec[2]; k.b = rec[3]; k.c = rec[4]; k.d = rec[5]; k.e = rec[6]; k.f = rec[7]; k.g = rec[8]; k.h = rec[9];
-  if(displaced)
-  {
-    k.n0 = rec[10]; k.n1 = rec[11]; k.n2 = rec[12]; k.n3 = rec[13]; k.m = rec[14];
-  }
 }
 
 // (takes plain pointers: passing the by-value kernel parameter block to a non-inlined function would copy it to local memory)
@@ -759,133 +737,150 @@ static __device__ __noinline__ F3 ripple_deform_part(const tc_FrameConstants* vi
   return ripple_deform(view[0], pos, instanceID, instances[instanceID].geoHi[3]);
 }
 
-// position polynomial of one vertex
-__device__ __forceinline__ F3 eval_position(const PartCoeffs& k, float s, float t)
+// ------------------------------------------------------------------------------------------------------------
+// Packed fp32 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2): one issue slot performs the operation on a 64-bit register
+// pair.  Operands are handed over as plain floats; ptxas allocates the aligned pairs, and a pair built from twice
+// the same scalar becomes a broadcast operand of the instruction (no move).
+// ------------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
 {
-  // c00 = a.xyz, c10 = (a.w,b.x,b.y), c01 = (b.z,b.w,c.x), c20 = (c.y,c.z,c.w), c02 = d.xyz, c11 = (d.w,e.x,e.y),
-  // c30 = (e.z,e.w,f.x), c03 = (f.y,f.z,f.w), c21 = g.xyz, c12 = (g.w,h.x,h.y), scale = h.z, offset = h.w
-  const float st = s * t;
-  F3 A = {fmaf(s, k.e.z, k.c.y), fmaf(s, k.e.w, k.c.z), fmaf(s, k.f.x, k.c.w)};
-  A    = {fmaf(s, A.x, k.a.w), fmaf(s, A.y, k.b.x), fmaf(s, A.z, k.b.y)};
-  F3 B = {fmaf(t, k.f.y, k.d.x), fmaf(t, k.f.z, k.d.y), fmaf(t, k.f.w, k.d.z)};
-  B    = {fmaf(t, B.x, k.b.z), fmaf(t, B.y, k.b.w), fmaf(t, B.z, k.c.x)};
-  F3 C = {fmaf(s, k.g.x, k.d.w), fmaf(s, k.g.y, k.e.x), fmaf(s, k.g.z, k.e.y)};
-  C    = {fmaf(t, k.g.w, C.x), fmaf(t, k.h.x, C.y), fmaf(t, k.h.y, C.z)};
-  return {fmaf(st, C.x, fmaf(t, B.x, fmaf(s, A.x, k.a.x))), fmaf(st, C.y, fmaf(t, B.y, fmaf(s, A.y, k.a.y))), fmaf(st, C.z, fmaf(t, B.z, fmaf(s, A.z, k.a.z)))};
+  float2 d;
+  asm("{\n .reg .b64 a, b, c, d;\n mov.b64 a, {%2, %3};\n mov.b64 b, {%4, %5};\n mov.b64 c, {%6, %7};\n fma.rn.f32x2 d, a, b, c;\n mov.b64 {%0, %1}, d;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+  float2 d;
+  asm("{\n .reg .b64 a, b, d;\n mov.b64 a, {%2, %3};\n mov.b64 b, {%4, %5};\n mul.rn.f32x2 d, a, b;\n mov.b64 {%0, %1}, d;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b)
+{
+  float2 d;
+  asm("{\n .reg .b64 a, b, d;\n mov.b64 a, {%2, %3};\n mov.b64 b, {%4, %5};\n add.rn.f32x2 d, a, b;\n mov.b64 {%0, %1}, d;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+
+// Position polynomial of TWO vertices of one part: (s, t) hold the pair, the coefficients are broadcast scalars.
+// c00 = a.xyz, c10 = (a.w,b.x,b.y), c01 = (b.z,b.w,c.x), c20 = (c.y,c.z,c.w), c02 = d.xyz, c11 = (d.w,e.x,e.y),
+// c30 = (e.z,e.w,f.x), c03 = (f.y,f.z,f.w), c21 = g.xyz, c12 = (g.w,h.x,h.y), scale = h.z, offset = h.w
+struct PositionCoeffs
+{
+  float4 a, b, c, d, e, f, g, h;
+};
+__device__ __forceinline__ void eval_position2(const PositionCoeffs& k, float2 s, float2 t, float2& X, float2& Y, float2& Z)
+{
+  const float2 st = mul2(s, t);
+  float2 Ax = fma2(s, bc2(k.e.z), bc2(k.c.y)), Ay = fma2(s, bc2(k.e.w), bc2(k.c.z)), Az = fma2(s, bc2(k.f.x), bc2(k.c.w));
+  Ax = fma2(s, Ax, bc2(k.a.w)); Ay = fma2(s, Ay, bc2(k.b.x)); Az = fma2(s, Az, bc2(k.b.y));
+  float2 Bx = fma2(t, bc2(k.f.y), bc2(k.d.x)), By = fma2(t, bc2(k.f.z), bc2(k.d.y)), Bz = fma2(t, bc2(k.f.w), bc2(k.d.z));
+  Bx = fma2(t, Bx, bc2(k.b.z)); By = fma2(t, By, bc2(k.b.w)); Bz = fma2(t, Bz, bc2(k.c.x));
+  float2 Cx = fma2(s, bc2(k.g.x), bc2(k.d.w)), Cy = fma2(s, bc2(k.g.y), bc2(k.e.x)), Cz = fma2(s, bc2(k.g.z), bc2(k.e.y));
+  Cx = fma2(t, bc2(k.g.w), Cx); Cy = fma2(t, bc2(k.h.x), Cy); Cz = fma2(t, bc2(k.h.y), Cz);
+  X = fma2(st, Cx, fma2(t, Bx, fma2(s, Ax, bc2(k.a.x))));
+  Y = fma2(st, Cy, fma2(t, By, fma2(s, Ay, bc2(k.a.y))));
+  Z = fma2(st, Cz, fma2(t, Bz, fma2(s, Az, bc2(k.a.z))));
 }
 
-// Two vertices of ONE part from its coefficients and the pattern vertices qa, qb.  Written in three phases so that both
-// texture gathers are in flight while the position polynomials are evaluated.  Branch-free: parts without displacement
-// carry scale = offset = 0 and a valid texture object (build_part_record), so the displaced variant needs no test.
-template <bool DISPLACED>
-__device__ __forceinline__ void eval_part_pair(const PartCoeffs& k, float2 qa, float2 qb, F3& oa, F3& ob)
+// 2*NP vertices of ONE part.  q[i] = (q1 of vertex 2i, q1 of vertex 2i+1, q2 of vertex 2i, q2 of vertex 2i+1); the
+// outputs are (X, Y, Z) pairs per vertex pair.  Everything but the texture-footprint blend runs as packed fp32: vertex
+// pairs share a broadcast coefficient; texel-space coordinates pair (x, y) of one vertex so that the gather coordinates
+// come out in adjacent registers.  Phases are ordered so that all gathers are in flight while the position polynomials
+// are evaluated; coefficient groups are read from the shared-memory record right where they are used.
+// Branch-free: parts without displacement carry scale = offset = 0 and a valid texture object (build_part_record).
+// The footprint origin is rint(x - 0.5): it equals floor(x) except where x is an exact integer and the tie rounds down,
+// where the weight becomes exactly 1 on the same texel -- the same bilinear value (the filter is continuous).
+// TEX == 1: every part of the scene samples the same texture, so the handle comes from the (warp-uniform) kernel
+// parameter; a per-lane handle (TEX == 2) makes the compiler wrap every texture instruction in a "waterfall" loop over
+// the distinct handles of the warp, which also stops it from batching the gathers.
+template <int TEX, int NP>
+__device__ __forceinline__ void eval_part_pairs(const float4* rec, const float4 (&q)[NP], float2 (&X)[NP], float2 (&Y)[NP], float2 (&Z)[NP],
+                                                cudaTextureObject_t uniformTex)
 {
-  const float sa = fmaf(qa.y, k.r0.z, fmaf(qa.x, k.r0.y, k.r0.x)), ta = fmaf(qa.y, k.r1.y, fmaf(qa.x, k.r1.x, k.r0.w));
-  const float sb = fmaf(qb.y, k.r0.z, fmaf(qb.x, k.r0.y, k.r0.x)), tb = fmaf(qb.y, k.r1.y, fmaf(qb.x, k.r1.x, k.r0.w));
-  if(DISPLACED)
-  {
-    // X = (n2.y,n2.z,n2.w), Y = n3.xyz, 1/W = n3.w, 1/H = m.x.  The 2x2 footprint comes through the texture unit (exact
-    // texel values, hardware repeat addressing) aimed at the corner shared by the four texels, so the footprint choice
-    // is unambiguous; the bilinear weights are computed here in fp32 (same definition as the CPU oracle's sampler).
-    const cudaTextureObject_t tex = (unsigned long long)__float_as_uint(k.m.y) | ((unsigned long long)__float_as_uint(k.m.z) << 32);
-    const float xa = fmaf(ta, k.n2.w, fmaf(sa, k.n2.z, k.n2.y)), ya = fmaf(ta, k.n3.z, fmaf(sa, k.n3.y, k.n3.x));
-    const float xb = fmaf(tb, k.n2.w, fmaf(sb, k.n2.z, k.n2.y)), yb = fmaf(tb, k.n3.z, fmaf(sb, k.n3.y, k.n3.x));
-    const float fxa = floorf(xa), fya = floorf(ya), fxb = floorf(xb), fyb = floorf(yb);
-    const float4 ga = tex2Dgather<float4>(tex, (fxa + 1.0f) * k.n3.w, (fya + 1.0f) * k.m.x, 0);  // (t01, t11, t10, t00)
-    const float4 gb = tex2Dgather<float4>(tex, (fxb + 1.0f) * k.n3.w, (fyb + 1.0f) * k.m.x, 0);
-    oa = eval_position(k, sa, ta);
-    ob = eval_position(k, sb, tb);
-    // n0 = n0.xyz, dn1 = (n0.w,n1.x,n1.y), dn2 = (n1.z,n1.w,n2.x)
-    const F3 na = {fmaf(ta, k.n1.z, fmaf(sa, k.n0.w, k.n0.x)), fmaf(ta, k.n1.w, fmaf(sa, k.n1.x, k.n0.y)), fmaf(ta, k.n2.x, fmaf(sa, k.n1.y, k.n0.z))};
-    const F3 nb = {fmaf(tb, k.n1.z, fmaf(sb, k.n0.w, k.n0.x)), fmaf(tb, k.n1.w, fmaf(sb, k.n1.x, k.n0.y)), fmaf(tb, k.n2.x, fmaf(sb, k.n1.y, k.n0.z))};
-    const float ra = fast_rsqrt(dot3(na, na)), rb = fast_rsqrt(dot3(nb, nb));
-    const float axa = xa - fxa, aya = ya - fya, axb = xb - fxb, ayb = yb - fyb;
-    const float topa = fmaf(ga.z - ga.w, axa, ga.w), bota = fmaf(ga.y - ga.x, axa, ga.x);
-    const float topb = fmaf(gb.z - gb.w, axb, gb.w), botb = fmaf(gb.y - gb.x, axb, gb.x);
-    const float ha = fmaf(fmaf(bota - topa, aya, topa), k.h.z, k.h.w) * ra;
-    const float hb = fmaf(fmaf(botb - topb, ayb, topb), k.h.z, k.h.w) * rb;
-    oa = fma3(na, ha, oa);
-    ob = fma3(nb, hb, ob);
-  }
-  else
-  {
-    oa = eval_position(k, sa, ta);
-    ob = eval_position(k, sb, tb);
-  }
-}
-
-// N vertices of ONE part (N = 2 or 4).  Phases are ordered so that all texture gathers are in flight while the position
-// polynomials are evaluated; coefficients are read from the shared-memory record right where they are used, which
-// keeps the peak register pressure at one coefficient group at a time.
-// uniformTex != 0: every part of the scene samples the same texture, so the handle comes from the (warp-uniform) kernel
-// parameter; a per-lane handle makes the compiler wrap every texture instruction in a "waterfall" loop over the distinct
-// handles of the warp, which also stops it from batching the gathers.
-template <bool DISPLACED, int N>
-__device__ __forceinline__ void eval_part_n(const float4* rec, const float2 (&q)[N], F3 (&o)[N], cudaTextureObject_t uniformTex)
-{
-  float s[N], t[N];
+  float2 s[NP], t[NP];
   {
     const float4 r0 = rec[0], r1 = rec[1];
 #pragma unroll
-    for(int i = 0; i < N; i++)
+    for(int i = 0; i < NP; i++)
     {
-      s[i] = fmaf(q[i].y, r0.z, fmaf(q[i].x, r0.y, r0.x));
-      t[i] = fmaf(q[i].y, r1.y, fmaf(q[i].x, r1.x, r0.w));
+      const float2 q1 = make_float2(q[i].x, q[i].y), q2 = make_float2(q[i].z, q[i].w);
+      s[i] = fma2(q2, bc2(r0.z), fma2(q1, bc2(r0.y), bc2(r0.x)));
+      t[i] = fma2(q2, bc2(r1.y), fma2(q1, bc2(r1.x), bc2(r0.w)));
     }
   }
-  float  ax[N], ay[N];
-  float4 g[N];
+  constexpr bool DISPLACED = TEX != 0;
+  float2 axy[2 * NP];
+  float4 g[2 * NP];
   if(DISPLACED)
   {
-    // X = (n2.y,n2.z,n2.w), Y = n3.xyz, 1/W = n3.w, 1/H = m.x, texture object = (m.y, m.z)
-    const float4 n2 = rec[12], n3 = rec[13], m = rec[14];
-    float gx[N], gy[N];
+    // c0 = (X0, Y0, X1, Y1), c1 = (X2, Y2, 1/W, 1/H), texture object = (m.y, m.z)
+    const float4 c0 = rec[12], c1 = rec[13];
+    const float  M  = 12582912.0f;  // 1.5 * 2^23: (v + M) - M = rint(v) for |v| < 2^22, on the FMA pipe
+    float2       gc[2 * NP];
 #pragma unroll
-    for(int i = 0; i < N; i++)
+    for(int i = 0; i < 2 * NP; i++)
     {
-      const float x = fmaf(t[i], n2.w, fmaf(s[i], n2.z, n2.y)), y = fmaf(t[i], n3.z, fmaf(s[i], n3.y, n3.x));
-      const float fx = floorf(x), fy = floorf(y);
-      ax[i] = x - fx;
-      ay[i] = y - fy;
-      gx[i] = (fx + 1.0f) * n3.w;
-      gy[i] = (fy + 1.0f) * m.x;
+      const float  sv = (i & 1) ? s[i >> 1].y : s[i >> 1].x, tv = (i & 1) ? t[i >> 1].y : t[i >> 1].x;
+      const float2 xy = fma2(bc2(tv), make_float2(c1.x, c1.y), fma2(bc2(sv), make_float2(c0.z, c0.w), make_float2(c0.x, c0.y)));
+      const float2 f  = add2(add2(add2(xy, bc2(-0.5f)), bc2(M)), bc2(-M));
+      axy[i] = fma2(f, bc2(-1.0f), xy);
+      gc[i]  = fma2(f, make_float2(c1.z, c1.w), make_float2(c1.z, c1.w));
     }
-    if(uniformTex)
+    if(TEX == 1)
     {
 #pragma unroll
-      for(int i = 0; i < N; i++)
-        g[i] = tex2Dgather<float4>(uniformTex, gx[i], gy[i], 0);  // (t01, t11, t10, t00)
+      for(int i = 0; i < 2 * NP; i++)
+        g[i] = tex2Dgather<float4>(uniformTex, gc[i].x, gc[i].y, 0);  // (t01, t11, t10, t00)
     }
     else
     {
+      const float4 m = rec[14];
       const cudaTextureObject_t tex = (unsigned long long)__float_as_uint(m.y) | ((unsigned long long)__float_as_uint(m.z) << 32);
 #pragma unroll
-      for(int i = 0; i < N; i++)
-        g[i] = tex2Dgather<float4>(tex, gx[i], gy[i], 0);
+      for(int i = 0; i < 2 * NP; i++)
+        g[i] = tex2Dgather<float4>(tex, gc[i].x, gc[i].y, 0);
     }
   }
   float scale = 0.f, offset = 0.f;
   {
-    PartCoeffs k;
+    PositionCoeffs k;
     k.a = rec[2]; k.b = rec[3]; k.c = rec[4]; k.d = rec[5]; k.e = rec[6]; k.f = rec[7]; k.g = rec[8]; k.h = rec[9];
     scale  = k.h.z;
     offset = k.h.w;
 #pragma unroll
-    for(int i = 0; i < N; i++)
-      o[i] = eval_position(k, s[i], t[i]);
+    for(int i = 0; i < NP; i++)
+      eval_position2(k, s[i], t[i], X[i], Y[i], Z[i]);
   }
   if(DISPLACED)
   {
-    // n0 = n0.xyz, dn1 = (n0.w,n1.x,n1.y), dn2 = (n1.z,n1.w,n2.x)
+    // n0 = n0.xyz, dn1 = (n0.w,n1.x,n1.y), dn2 = (n1.z,n1.w,rec[14].x)
     const float4 n0 = rec[10], n1 = rec[11];
-    const float  n2x = rec[12].x;
+    const float  n2z = rec[14].x;
 #pragma unroll
-    for(int i = 0; i < N; i++)
+    for(int i = 0; i < NP; i++)
     {
-      const F3    n   = {fmaf(t[i], n1.z, fmaf(s[i], n0.w, n0.x)), fmaf(t[i], n1.w, fmaf(s[i], n1.x, n0.y)), fmaf(t[i], n2x, fmaf(s[i], n1.y, n0.z))};
-      const float top = fmaf(g[i].z - g[i].w, ax[i], g[i].w), bot = fmaf(g[i].y - g[i].x, ax[i], g[i].x);
-      const float h   = fmaf(fmaf(bot - top, ay[i], top), scale, offset) * fast_rsqrt(dot3(n, n));
-      o[i] = fma3(n, h, o[i]);
+      const float2 nx = fma2(t[i], bc2(n1.z), fma2(s[i], bc2(n0.w), bc2(n0.x)));
+      const float2 ny = fma2(t[i], bc2(n1.w), fma2(s[i], bc2(n1.x), bc2(n0.y)));
+      const float2 nz = fma2(t[i], bc2(n2z), fma2(s[i], bc2(n1.y), bc2(n0.z)));
+      const float2 d  = fma2(nz, nz, fma2(ny, ny, mul2(nx, nx)));
+      const float2 r  = make_float2(fast_rsqrt(d.x), fast_rsqrt(d.y));
+      const float4 ga = g[2 * i], gb = g[2 * i + 1];
+      const float2 aa = axy[2 * i], ab = axy[2 * i + 1];
+      const float  topa = fmaf(ga.z - ga.w, aa.x, ga.w), bota = fmaf(ga.y - ga.x, aa.x, ga.x);
+      const float  topb = fmaf(gb.z - gb.w, ab.x, gb.w), botb = fmaf(gb.y - gb.x, ab.x, gb.x);
+      const float2 hr   = make_float2(fmaf(bota - topa, aa.y, topa), fmaf(botb - topb, ab.y, topb));
+      const float2 h    = mul2(fma2(hr, bc2(scale), bc2(offset)), r);
+      X[i] = fma2(nx, h, X[i]);
+      Y[i] = fma2(ny, h, Y[i]);
+      Z[i] = fma2(nz, h, Z[i]);
     }
   }
 }

@@ -1515,10 +1515,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
 #endif
 constexpr int INST_WARPS       = TC_INST_WARPS;
 constexpr int INST_THREADS     = INST_WARPS * 32;
-#ifndef TC_INST_SLOT
-#define TC_INST_SLOT 6
-#endif
-constexpr int INST_SLOT        = TC_INST_SLOT;      // vertices per lane per iteration (all of one part)
+constexpr int INST_SLOT        = TC_INST_SLOT;      // vertices per lane per iteration (all of one part); even, see tc_set_tess_table
+static_assert(INST_SLOT % 2 == 0, "vertex pairs");
 constexpr int INST_ITER_VERTS  = 32 * INST_SLOT;
 constexpr int INST_STAGE_WORDS = INST_ITER_VERTS * 3 + 4;
 constexpr int INST_WARP_WORDS  = 32 * TC_REC_WORDS + INST_STAGE_WORDS;  // 2308 words = 9232 B per warp
@@ -1551,7 +1549,11 @@ __device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint
 #ifndef TC_INST_MIN_CTAS
 #define TC_INST_MIN_CTAS 2
 #endif
-template <bool DISPLACED, bool ANIM>
+// TEX: 0 = no displacement textures, 1 = the scene has ONE texture (warp-uniform handle from the parameter block),
+// 2 = per-part handles.  Compile-time, because the compiler if-converts a run-time choice: the per-lane-handle
+// "waterfall" then runs predicated off after the uniform gathers and its write-after-write dependency on the gather
+// registers exposes the full texture latency before the position polynomials (measured: 12 % of all stall samples).
+template <int TEX, bool ANIM>
 __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(Params p, const uint32_t* epochCounter)
 {
   extern __shared__ __align__(16) float instSmem[];
@@ -1582,7 +1584,7 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
     shTris = 0;
   }
   uint32_t accSucc = 0, accTris = 0;  // per-warp statistics, folded once at the end
-  const cudaTextureObject_t uniformTex = (DISPLACED && p.numTextures == 1) ? p.texturesC[0].gather : 0;  // warp-uniform handle
+  const cudaTextureObject_t uniformTex = TEX == 1 ? p.texturesC[0].gather : 0;  // warp-uniform handle
 
   // One tile ahead: while a warp generates the vertices of tile k it already holds the ticket of its next tile, has
   // loaded those parts, scanned them and published their aggregate -- successors never wait on this warp's heavy work
@@ -1590,7 +1592,7 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
   struct Fetched
   {
     uint32_t tile, instanceID, clusterID, vtx0, vtx1, vtx2, triCfg;
-    uint32_t numVertices, numTriangles, firstVertex, dataSize, incV;
+    uint32_t numVertices, numTriangles, slotBase, dataSize, incV;
     unsigned long long incD;
   };
   auto fetch = [&](Fetched& f) {
@@ -1599,7 +1601,7 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
       tile = atomicAdd(&st->ticket[SLOT_INSTANTIATE], 1u);
     f.tile = __shfl_sync(0xffffffffu, tile, 0);
     f.instanceID = f.clusterID = f.vtx0 = f.vtx1 = f.vtx2 = f.triCfg = 0;
-    f.numVertices = f.numTriangles = f.firstVertex = f.dataSize = 0;
+    f.numVertices = f.numTriangles = f.slotBase = f.dataSize = 0;
     f.incV = 0;
     f.incD = 0;
     if(f.tile >= numTiles)
@@ -1611,8 +1613,10 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
       uint2 a = __ldcs(src), c = __ldcs(src + 1), d = __ldcs(src + 2);
       f.instanceID = a.x; f.clusterID = a.y; f.vtx0 = c.x; f.vtx1 = c.y; f.vtx2 = d.x; f.triCfg = d.y;
       tc_TessTableEntry e = tess_entry(p, f.triCfg >> 16);
-      f.numVertices = e.numVertices; f.numTriangles = e.numTriangles; f.firstVertex = e.firstVertex;
-      f.dataSize    = __ldg(&p.tblTemplSize[tess_configIndex(f.triCfg >> 16) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1)]);
+      const uint32_t cfgIdx = tess_configIndex(f.triCfg >> 16) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1);
+      f.numVertices = e.numVertices; f.numTriangles = e.numTriangles;
+      f.slotBase    = __ldg(&p.tblSlotBase[cfgIdx]);
+      f.dataSize    = __ldg(&p.tblTemplSize[cfgIdx]);
     }
     f.incV = warp_inclusive_add(f.numVertices);
     unsigned long long incD = f.dataSize;
@@ -1640,7 +1644,7 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
     const bool     valid     = partIndex < numParts;
     const uint32_t instanceID = cur.instanceID, clusterID = cur.clusterID, triCfg = cur.triCfg;
     const uint32_t vtxEnc[3] = {cur.vtx0, cur.vtx1, cur.vtx2};
-    const uint32_t numVertices = cur.numVertices, numTriangles = cur.numTriangles, firstVertex = cur.firstVertex, dataSize = cur.dataSize;
+    const uint32_t numVertices = cur.numVertices, numTriangles = cur.numTriangles, slotBase = cur.slotBase, dataSize = cur.dataSize;
     const uint32_t incV = cur.incV;
     const unsigned long long incD = cur.incD;
     const uint32_t           aggV = __shfl_sync(0xffffffffu, incV, 31);
@@ -1684,7 +1688,7 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
       const uint4 ch = __ldg(reinterpret_cast<const uint4*>(inst.clusters) + clusterID);
       const uint8_t* lt = reinterpret_cast<const uint8_t*>(inst.clusterLocalTriangles) + ch.w + (triCfg & 0xFFFF) * 3;
       build_part_record(p, inst, instanceID, ch.z, __ldg(lt), __ldg(lt + 1), __ldg(lt + 2), vtxEnc, ((triCfg >> 16) & TC_CONFIG_FLIPPED_BIT) != 0,
-                        firstVertex, partIndex, recBase + lane * TC_REC_WORDS);
+                        slotBase, (numVertices + INST_SLOT - 1) / INST_SLOT, partIndex, recBase + lane * TC_REC_WORDS);
     }
     __syncwarp();
 
@@ -1718,14 +1722,23 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
       const uint32_t shift    = uint32_t(itFloat0 & 3);  // keep shared and global 16-byte phases equal
       if(active)
       {
-        const float4*  rec = reinterpret_cast<const float4*>(recBase + part * TC_REC_WORDS);
-        const uint32_t fv  = __float_as_uint(rec[1].z) + v0;
-        float2 q[INST_SLOT];
-        F3     o[INST_SLOT];
+        const float4*  rec  = reinterpret_cast<const float4*>(recBase + part * TC_REC_WORDS);
+        const float4   r1   = rec[1];
+        const uint32_t nS   = __float_as_uint(r1.w);
+        const float4*  qsrc = p.tblSlots + (__float_as_uint(r1.z) + (w0 + lane - pStartS));  // coalesced across the lanes of a part
+        float4 q[INST_SLOT / 2];
 #pragma unroll
-        for(int i = 0; i < INST_SLOT; i++)
-          q[i] = __ldg(&p.tblVerticesF[fv + min(uint32_t(i), cnt - 1u)]);
-        eval_part_n<DISPLACED, INST_SLOT>(rec, q, o, uniformTex);
+        for(int i = 0; i < INST_SLOT / 2; i++)
+          q[i] = __ldg(qsrc + i * nS);
+        float2 X[INST_SLOT / 2], Y[INST_SLOT / 2], Z[INST_SLOT / 2];
+        eval_part_pairs<TEX, INST_SLOT / 2>(rec, q, X, Y, Z, uniformTex);
+        F3 o[INST_SLOT];
+#pragma unroll
+        for(int i = 0; i < INST_SLOT / 2; i++)
+        {
+          o[2 * i]     = {X[i].x, Y[i].x, Z[i].x};
+          o[2 * i + 1] = {X[i].y, Y[i].y, Z[i].y};
+        }
         if(ANIM)
         {
           const uint32_t partIdx = __float_as_uint(rec[14].w);
@@ -2044,12 +2057,12 @@ int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, Kerne
     return -1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->classify, k_cluster_classify<1>, CLASSIFY_THREADS, smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->split, k_triangle_split, SPLIT_THREADS, 0);
-  const void* variants[4] = {(const void*)k_instantiate<false, false>, (const void*)k_instantiate<false, true>, (const void*)k_instantiate<true, false>,
-                             (const void*)k_instantiate<true, true>};
+  const void* variants[6] = {(const void*)k_instantiate<0, false>, (const void*)k_instantiate<0, true>, (const void*)k_instantiate<1, false>,
+                             (const void*)k_instantiate<1, true>,  (const void*)k_instantiate<2, false>, (const void*)k_instantiate<2, true>};
   for(const void* f : variants)
     if(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, int(instantiate_smem_bytes())) != cudaSuccess)
       return -1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->instantiate, k_instantiate<true, false>, INST_THREADS, instantiate_smem_bytes());
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->instantiate, k_instantiate<1, false>, INST_THREADS, instantiate_smem_bytes());
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -2097,15 +2110,18 @@ void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32
 }
 void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s)
 {
-  const bool displaced = p.numTextures > 0, anim = (p.flags & TC_FLAG_ANIMATION) != 0;
-  if(displaced && anim)
-    k_instantiate<true, true><<<grid, INST_THREADS, instantiate_smem_bytes(), s>>>(p, epochCounter);
-  else if(displaced)
-    k_instantiate<true, false><<<grid, INST_THREADS, instantiate_smem_bytes(), s>>>(p, epochCounter);
-  else if(anim)
-    k_instantiate<false, true><<<grid, INST_THREADS, instantiate_smem_bytes(), s>>>(p, epochCounter);
-  else
-    k_instantiate<false, false><<<grid, INST_THREADS, instantiate_smem_bytes(), s>>>(p, epochCounter);
+  const int  tex  = p.numTextures == 0 ? 0 : (p.numTextures == 1 ? 1 : 2);
+  const bool anim = (p.flags & TC_FLAG_ANIMATION) != 0;
+  const size_t smem = instantiate_smem_bytes();
+  switch(tex * 2 + int(anim))
+  {
+    case 0: k_instantiate<0, false><<<grid, INST_THREADS, smem, s>>>(p, epochCounter); break;
+    case 1: k_instantiate<0, true><<<grid, INST_THREADS, smem, s>>>(p, epochCounter); break;
+    case 2: k_instantiate<1, false><<<grid, INST_THREADS, smem, s>>>(p, epochCounter); break;
+    case 3: k_instantiate<1, true><<<grid, INST_THREADS, smem, s>>>(p, epochCounter); break;
+    case 4: k_instantiate<2, false><<<grid, INST_THREADS, smem, s>>>(p, epochCounter); break;
+    default: k_instantiate<2, true><<<grid, INST_THREADS, smem, s>>>(p, epochCounter); break;
+  }
 }
 void launch_blas(const Params& p, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s)
 {

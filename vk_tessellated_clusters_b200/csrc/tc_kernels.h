@@ -10,6 +10,12 @@ namespace tc {
 
 struct Params;
 
+// vertices a lane generates per iteration of k_instantiate; also the granularity of the slotted pattern-vertex table
+#ifndef TC_INST_SLOT
+#define TC_INST_SLOT 6
+#endif
+constexpr uint32_t kInstantiateSlot = TC_INST_SLOT;
+
 struct KernelOccupancy
 {
   int classify = 1, split = 1, instantiate = 1;
