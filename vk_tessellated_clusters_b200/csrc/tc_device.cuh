@@ -658,17 +658,19 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
     bv[v]  = float(vtxEncoded[v] >> 16) * (1.0f / 32768.0f);
     pos[v] = ld_f3(positions, gi[v]);
     nrm[v] = normalize3(ld_f3(normals, gi[v]));
-    tu[v]  = __ldg(texcoords + size_t(gi[v]) * 2);
-    tv[v]  = __ldg(texcoords + size_t(gi[v]) * 2 + 1);
+    const float2 tc = __ldg(reinterpret_cast<const float2*>(texcoords) + gi[v]);
+    tu[v] = tc.x;
+    tv[v] = tc.y;
   }
   // corner k has base barycentrics (1-bu-bv, bu, bv); pattern weights (q0,q1,q2), q0 = 1-q1-q2, flipped: q0 <-> q1
   const float buO = flipped ? bu[1] : bu[0], buA = flipped ? bu[0] : bu[1];  // origin corner, corner multiplied by q1
   const float bvO = flipped ? bv[1] : bv[0], bvA = flipped ? bv[0] : bv[1];
-  rec[0] = buO; rec[1] = buA - buO; rec[2] = bu[2] - buO;
-  rec[3] = bvO; rec[4] = bvA - bvO; rec[5] = bv[2] - bvO;
-  reinterpret_cast<uint32_t*>(rec)[6] = slotBase;
-  reinterpret_cast<uint32_t*>(rec)[7] = numSlots;
   const int texture = (p.numTextures > 0 && inst.displacementIndex >= 0) ? inst.displacementIndex : -1;
+  // the record is written as 15 float4: 128-bit shared stores of 8 lanes at a 60-word stride touch 32 distinct banks
+  // (scalar stores at that stride are 4-way conflicted)
+  float4* rec4 = reinterpret_cast<float4*>(rec);
+  rec4[0] = make_float4(buO, buA - buO, bu[2] - buO, bvO);
+  rec4[1] = make_float4(bvA - bvO, bv[2] - bvO, __uint_as_float(slotBase), __uint_as_float(numSlots));
 
   F3 c00, c10, c01, c20, c02, c11, c30, c03, c21, c12;
   if(flag_pn(p))
@@ -704,12 +706,19 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
     c00 = pos[0]; c10 = pos[1] - pos[0]; c01 = pos[2] - pos[0];
     c20 = c02 = c11 = c30 = c03 = c21 = c12 = z;
   }
-  st3(rec + 8, c00);  st3(rec + 11, c10); st3(rec + 14, c01); st3(rec + 17, c20); st3(rec + 20, c02);
-  st3(rec + 23, c11); st3(rec + 26, c30); st3(rec + 29, c03); st3(rec + 32, c21); st3(rec + 35, c12);
-  rec[38] = texture >= 0 ? inst.displacementScale * p.view[0].displacementScale : 0.0f;
-  rec[39] = texture >= 0 ? inst.displacementOffset + p.view[0].displacementOffset : 0.0f;
-  st3(rec + 40, nrm[0]); st3(rec + 43, nrm[1] - nrm[0]);
-  rec[46] = nrm[2].x - nrm[0].x; rec[47] = nrm[2].y - nrm[0].y; rec[56] = nrm[2].z - nrm[0].z;
+  const float scale  = texture >= 0 ? inst.displacementScale * p.view[0].displacementScale : 0.0f;
+  const float offset = texture >= 0 ? inst.displacementOffset + p.view[0].displacementOffset : 0.0f;
+  rec4[2] = make_float4(c00.x, c00.y, c00.z, c10.x);
+  rec4[3] = make_float4(c10.y, c10.z, c01.x, c01.y);
+  rec4[4] = make_float4(c01.z, c20.x, c20.y, c20.z);
+  rec4[5] = make_float4(c02.x, c02.y, c02.z, c11.x);
+  rec4[6] = make_float4(c11.y, c11.z, c30.x, c30.y);
+  rec4[7] = make_float4(c30.z, c03.x, c03.y, c03.z);
+  rec4[8] = make_float4(c21.x, c21.y, c21.z, c12.x);
+  rec4[9] = make_float4(c12.y, c12.z, scale, offset);
+  const F3 dn1 = nrm[1] - nrm[0], dn2 = nrm[2] - nrm[0];
+  rec4[10] = make_float4(nrm[0].x, nrm[0].y, nrm[0].z, dn1.x);
+  rec4[11] = make_float4(dn1.y, dn1.z, dn2.x, dn2.y);
   float W = 1.0f, H = 1.0f;
   unsigned long long texObj = 0;
   if(p.numTextures > 0)
@@ -719,13 +728,9 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
     H      = float(p.texturesC[ti].height);
     texObj = p.texturesC[ti].gather;
   }
-  rec[48] = fmaf(tu[0], W, -0.5f); rec[50] = (tu[1] - tu[0]) * W; rec[52] = (tu[2] - tu[0]) * W;
-  rec[49] = fmaf(tv[0], H, -0.5f); rec[51] = (tv[1] - tv[0]) * H; rec[53] = (tv[2] - tv[0]) * H;
-  rec[54] = 1.0f / W;
-  rec[55] = 1.0f / H;
-  reinterpret_cast<uint32_t*>(rec)[57] = uint32_t(texObj);
-  reinterpret_cast<uint32_t*>(rec)[58] = uint32_t(texObj >> 32);
-  reinterpret_cast<uint32_t*>(rec)[59] = partIndex;
+  rec4[12] = make_float4(fmaf(tu[0], W, -0.5f), fmaf(tv[0], H, -0.5f), (tu[1] - tu[0]) * W, (tv[1] - tv[0]) * H);
+  rec4[13] = make_float4((tu[2] - tu[0]) * W, (tv[2] - tv[0]) * H, 1.0f / W, 1.0f / H);
+  rec4[14] = make_float4(dn2.z, __uint_as_float(uint32_t(texObj)), __uint_as_float(uint32_t(texObj >> 32)), __uint_as_float(partIndex));
 }
 
 // (takes plain pointers: passing the by-value kernel parameter block to a non-inlined function would copy it to local memory)

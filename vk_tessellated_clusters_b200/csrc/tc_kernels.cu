@@ -1519,7 +1519,7 @@ constexpr int INST_SLOT        = TC_INST_SLOT;      // vertices per lane per ite
 static_assert(INST_SLOT % 2 == 0, "vertex pairs");
 constexpr int INST_ITER_VERTS  = 32 * INST_SLOT;
 constexpr int INST_STAGE_WORDS = INST_ITER_VERTS * 3 + 4;
-constexpr int INST_WARP_WORDS  = 32 * TC_REC_WORDS + INST_STAGE_WORDS;  // 2308 words = 9232 B per warp
+constexpr int INST_WARP_WORDS  = 32 * TC_REC_WORDS + 2 * INST_STAGE_WORDS;  // records + double-buffered staging: 3080 words = 12320 B per warp
 
 __device__ __forceinline__ uint32_t lanemask_le()
 {
@@ -1528,22 +1528,46 @@ __device__ __forceinline__ uint32_t lanemask_le()
   return m;
 }
 
-// nFloats <= INST_ITER_VERTS * 3: head to 16-byte alignment, predicated rounds of 128-bit stores, tail
-__device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint32_t shift, uint32_t nFloats, uint32_t lane)
+// Bulk (TMA engine) copy shared -> global: the staged vertices leave the SM without LDS/STG instructions, i.e. without
+// wavefronts on the LSU data pipe (the kernel's busiest unit).
+__device__ __forceinline__ void bulk_store(float* gdst, const float* ssrc, uint32_t bytes, uint64_t policy)
+{
+  const uint32_t s = uint32_t(__cvta_generic_to_shared(ssrc));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(s), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()  // at most N committed groups still reading their shared-memory source
+{
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+// nFloats <= INST_ITER_VERTS * 3 staged floats -> global: head to 16-byte alignment and tail as scalar stores, the
+// 16-byte aligned body as ONE bulk copy issued by lane 0 (shared and global addresses have the same 16-byte phase).
+// Every call commits exactly one bulk group (possibly empty), which is what the double-buffer wait counts.
+__device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint32_t shift, uint32_t nFloats, uint32_t lane, uint64_t policy)
 {
   const uint32_t head = min(nFloats, (4u - shift) & 3u);
   if(lane < head)
     dst[lane] = stage[shift + lane];
-  const uint32_t bodyVec = (nFloats - head) >> 2;
-  const float4*  s4 = reinterpret_cast<const float4*>(stage + shift + head);
-  float4*        d4 = reinterpret_cast<float4*>(dst + head);
-#pragma unroll
-  for(int r = 0; r < (INST_ITER_VERTS * 3 / 4 + 31) / 32; r++)
-    if(lane + 32 * r < bodyVec)
-      __stcs(d4 + lane + 32 * r, s4[lane + 32 * r]);
+  const uint32_t bodyVec   = (nFloats - head) >> 2;
   const uint32_t tailStart = head + (bodyVec << 2);
   if(lane < nFloats - tailStart)
     dst[tailStart + lane] = stage[shift + tailStart + lane];
+  if(lane == 0)
+  {
+    if(bodyVec)
+      bulk_store(dst + head, stage + shift + head, bodyVec << 4, policy);
+    bulk_commit();
+  }
 }
 
 #ifndef TC_INST_MIN_CTAS
@@ -1560,7 +1584,9 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
   __shared__ uint32_t shSucc, shTris;
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   float* recBase = instSmem + size_t(warp) * INST_WARP_WORDS;
-  float* stage   = recBase + 32 * TC_REC_WORDS;
+  float* stageBase = recBase + 32 * TC_REC_WORDS;
+  uint32_t stageSel = 0;  // double-buffered staging: a buffer is rewritten only after the bulk copy issued from it has read it
+  const uint64_t streamPolicy = policy_evict_first();
 
   const uint32_t epoch = *epochCounter + SLOT_INSTANTIATE;
   tc_SceneBuilding* b  = p.build;
@@ -1591,19 +1617,19 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
   // and the part-record load latency is off the critical path.
   struct Fetched
   {
-    uint32_t tile, instanceID, clusterID, vtx0, vtx1, vtx2, triCfg;
-    uint32_t numVertices, numTriangles, slotBase, dataSize, incV;
-    unsigned long long incD;
+    uint32_t tile, instanceID, firstLocalVertex, vtx0, vtx1, vtx2, triCfg;
+    uint8_t  lt0, lt1, lt2;  // the base triangle's local vertex indices (kept apart: packing them would wait for the loads)
+    uint32_t numVertices, numTriangles, incV, incD;  // incD: tile-relative (32 CLAS sizes fit 32 bits)
   };
   auto fetch = [&](Fetched& f) {
     uint32_t tile = 0;
     if(lane == 0)
       tile = atomicAdd(&st->ticket[SLOT_INSTANTIATE], 1u);
     f.tile = __shfl_sync(0xffffffffu, tile, 0);
-    f.instanceID = f.clusterID = f.vtx0 = f.vtx1 = f.vtx2 = f.triCfg = 0;
-    f.numVertices = f.numTriangles = f.slotBase = f.dataSize = 0;
-    f.incV = 0;
-    f.incD = 0;
+    f.instanceID = f.firstLocalVertex = f.vtx0 = f.vtx1 = f.vtx2 = f.triCfg = 0;
+    f.lt0 = f.lt1 = f.lt2 = 0;
+    f.numVertices = f.numTriangles = 0;
+    uint32_t dataSize = 0;
     if(f.tile >= numTiles)
       return;
     const uint32_t partIndex = f.tile * 32 + lane;
@@ -1611,24 +1637,21 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
     {
       const uint2* src = reinterpret_cast<const uint2*>(&partTriangles[partIndex]);
       uint2 a = __ldcs(src), c = __ldcs(src + 1), d = __ldcs(src + 2);
-      f.instanceID = a.x; f.clusterID = a.y; f.vtx0 = c.x; f.vtx1 = c.y; f.vtx2 = d.x; f.triCfg = d.y;
+      f.instanceID = a.x; f.vtx0 = c.x; f.vtx1 = c.y; f.vtx2 = d.x; f.triCfg = d.y;
+      // the dependent chain instance -> cluster header -> local triangle is started a whole tile ahead of its use
+      const tc_RenderInstance& inst = p.instances[a.x];
+      const uint4    ch = __ldg(reinterpret_cast<const uint4*>(inst.clusters) + a.y);
+      const uint8_t* lt = reinterpret_cast<const uint8_t*>(inst.clusterLocalTriangles) + ch.w + (d.y & 0xFFFF) * 3;
+      f.firstLocalVertex = ch.z;
+      f.lt0 = __ldg(lt); f.lt1 = __ldg(lt + 1); f.lt2 = __ldg(lt + 2);
       tc_TessTableEntry e = tess_entry(p, f.triCfg >> 16);
       const uint32_t cfgIdx = tess_configIndex(f.triCfg >> 16) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1);
       f.numVertices = e.numVertices; f.numTriangles = e.numTriangles;
-      f.slotBase    = __ldg(&p.tblSlotBase[cfgIdx]);
-      f.dataSize    = __ldg(&p.tblTemplSize[cfgIdx]);
+      dataSize      = __ldg(&p.tblTemplSize[cfgIdx]);
     }
     f.incV = warp_inclusive_add(f.numVertices);
-    unsigned long long incD = f.dataSize;
-#pragma unroll
-    for(int dlt = 1; dlt < 32; dlt <<= 1)
-    {
-      unsigned long long n = __shfl_up_sync(0xffffffffu, incD, dlt);
-      if(lane >= dlt)
-        incD += n;
-    }
-    f.incD = incD;
-    lookback16_publish(p.lookback16, f.tile, __shfl_sync(0xffffffffu, f.incV, 31), __shfl_sync(0xffffffffu, incD, 31), epoch);
+    f.incD = warp_inclusive_add(dataSize);
+    lookback16_publish(p.lookback16, f.tile, __shfl_sync(0xffffffffu, f.incV, 31), __shfl_sync(0xffffffffu, f.incD, 31), epoch);
   };
 
   Fetched nxt;
@@ -1642,11 +1665,13 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
     const uint32_t tile = cur.tile;
     const uint32_t partIndex = tile * 32 + lane;
     const bool     valid     = partIndex < numParts;
-    const uint32_t instanceID = cur.instanceID, clusterID = cur.clusterID, triCfg = cur.triCfg;
+    const uint32_t instanceID = cur.instanceID, triCfg = cur.triCfg;
     const uint32_t vtxEnc[3] = {cur.vtx0, cur.vtx1, cur.vtx2};
-    const uint32_t numVertices = cur.numVertices, numTriangles = cur.numTriangles, slotBase = cur.slotBase, dataSize = cur.dataSize;
-    const uint32_t incV = cur.incV;
-    const unsigned long long incD = cur.incD;
+    const uint32_t numVertices = cur.numVertices, numTriangles = cur.numTriangles;
+    const uint32_t cfgIdx   = tess_configIndex(triCfg >> 16) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1);
+    const uint32_t dataSize = valid ? __ldg(&p.tblTemplSize[cfgIdx]) : 0u;  // cache hits: fetch() read them a tile ago
+    const uint32_t slotBase = __ldg(&p.tblSlotBase[cfgIdx]);
+    const uint32_t incV = cur.incV, incD = cur.incD;
     const uint32_t           aggV = __shfl_sync(0xffffffffu, incV, 31);
     const unsigned long long aggD = __shfl_sync(0xffffffffu, incD, 31);
     uint32_t           exclV;
@@ -1673,7 +1698,6 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
 
     if(ok)
     {  // records (:171-203) + per-part constants
-      const uint32_t cfgIdx     = tess_configIndex(triCfg >> 16) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1);
       const uint32_t tempOffset = baseTemp + partIndex;
       const unsigned long long templAddr = __ldg(reinterpret_cast<const unsigned long long*>(p.tblTemplAddr) + cfgIdx);
       const unsigned long long vaddr     = genVerticesAddr + (unsigned long long)(uint32_t)(vertexOffset * 4u * 3u);
@@ -1685,9 +1709,8 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
         tempClusterSizes[tempOffset] = dataSize;
 
       const tc_RenderInstance& inst = p.instances[instanceID];
-      const uint4 ch = __ldg(reinterpret_cast<const uint4*>(inst.clusters) + clusterID);
-      const uint8_t* lt = reinterpret_cast<const uint8_t*>(inst.clusterLocalTriangles) + ch.w + (triCfg & 0xFFFF) * 3;
-      build_part_record(p, inst, instanceID, ch.z, __ldg(lt), __ldg(lt + 1), __ldg(lt + 2), vtxEnc, ((triCfg >> 16) & TC_CONFIG_FLIPPED_BIT) != 0,
+      build_part_record(p, inst, instanceID, cur.firstLocalVertex, cur.lt0, cur.lt1, cur.lt2, vtxEnc,
+                        ((triCfg >> 16) & TC_CONFIG_FLIPPED_BIT) != 0,
                         slotBase, (numVertices + INST_SLOT - 1) / INST_SLOT, partIndex, recBase + lane * TC_REC_WORDS);
     }
     __syncwarp();
@@ -1720,6 +1743,8 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
       const uint32_t itEnd    = __shfl_sync(0xffffffffu, t0 + cnt, lastLane);
       const size_t   itFloat0 = tileFloat0 + size_t(itStart) * 3;
       const uint32_t shift    = uint32_t(itFloat0 & 3);  // keep shared and global 16-byte phases equal
+      static_assert(INST_SLOT == 6, "the slot outputs below are spelled out for 6 vertices");
+      F3 o0, o1, o2, o3, o4, o5;
       if(active)
       {
         const float4*  rec  = reinterpret_cast<const float4*>(recBase + part * TC_REC_WORDS);
@@ -1746,6 +1771,16 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
           for(int i = 0; i < INST_SLOT; i++)
             o[i] = ripple_deform_part(p.view, p.build, p.instances, o[i], partIdx);
         }
+        o0 = o[0]; o1 = o[1]; o2 = o[2]; o3 = o[3]; o4 = o[4]; o5 = o[5];
+      }
+      float* stage = stageBase + stageSel * INST_STAGE_WORDS;
+      stageSel ^= 1u;
+      if(lane == 0)
+        bulk_wait_read<1>();  // the copy issued two iterations ago (same buffer) has finished reading
+      __syncwarp();
+      if(active)
+      {
+        const F3 o[INST_SLOT] = {o0, o1, o2, o3, o4, o5};
         float* sdst = stage + shift + (t0 - itStart) * 3;
 #pragma unroll
         for(int i = 0; i < INST_SLOT; i++)
@@ -1754,15 +1789,16 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
             sdst[i * 3 + 0] = o[i].x; sdst[i * 3 + 1] = o[i].y; sdst[i * 3 + 2] = o[i].z;
           }
       }
+      fence_async_shared();  // generic-proxy writes above -> visible to the async proxy that executes the bulk copy
       __syncwarp();
-      flush_stage(stage, genVertices + itFloat0, shift, (itEnd - itStart) * 3, lane);
-      __syncwarp();
+      flush_stage(stage, genVertices + itFloat0, shift, (itEnd - itStart) * 3, lane, streamPolicy);
     }
   }
 
   // ---------------- epilogue: counters + BUILD_SETUP_BUILD_BLAS (build_setup.comp.glsl:191-235) ----------------
   if(lane == 0)
   {
+    bulk_wait_all();  // this warp's outstanding vertex copies are complete (shared memory no longer read, data written)
     if(accSucc) atomicAdd(&shSucc, accSucc);
     if(accTris) atomicAdd(&shTris, accTris);
   }
