@@ -1511,7 +1511,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
 // ============================================================================================================
 
 #ifndef TC_INST_WARPS
-#define TC_INST_WARPS 8
+#define TC_INST_WARPS 4
 #endif
 constexpr int INST_WARPS       = TC_INST_WARPS;
 constexpr int INST_THREADS     = INST_WARPS * 32;
@@ -1519,7 +1519,13 @@ constexpr int INST_SLOT        = TC_INST_SLOT;      // vertices per lane per ite
 static_assert(INST_SLOT % 2 == 0, "vertex pairs");
 constexpr int INST_ITER_VERTS  = 32 * INST_SLOT;
 constexpr int INST_STAGE_WORDS = INST_ITER_VERTS * 3 + 4;
-constexpr int INST_WARP_WORDS  = 32 * TC_REC_WORDS + 2 * INST_STAGE_WORDS;  // records + double-buffered staging: 3080 words = 12320 B per warp
+#ifndef TC_INST_STAGES
+#define TC_INST_STAGES 1
+#endif
+// staging buffers per warp.  1: the bulk copy of iteration i has the whole evaluation phase of iteration i+1 to finish
+// reading before the buffer is rewritten (measured faster than 2, and 2.3 KB less shared memory per warp)
+constexpr int INST_STAGES      = TC_INST_STAGES;
+constexpr int INST_WARP_WORDS  = 32 * TC_REC_WORDS + INST_STAGES * INST_STAGE_WORDS;  // 2 stages: 3080 words = 12320 B per warp
 
 __device__ __forceinline__ uint32_t lanemask_le()
 {
@@ -1570,8 +1576,9 @@ __device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint
   }
 }
 
+// 5 CTAs x 4 warps = 20 warps/SM at 96 registers (measured: 16 warps at 128 registers 0.467 ms, 20 warps 0.444 ms)
 #ifndef TC_INST_MIN_CTAS
-#define TC_INST_MIN_CTAS 2
+#define TC_INST_MIN_CTAS 5
 #endif
 // TEX: 0 = no displacement textures, 1 = the scene has ONE texture (warp-uniform handle from the parameter block),
 // 2 = per-part handles.  Compile-time, because the compiler if-converts a run-time choice: the per-lane-handle
@@ -1585,7 +1592,7 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   float* recBase = instSmem + size_t(warp) * INST_WARP_WORDS;
   float* stageBase = recBase + 32 * TC_REC_WORDS;
-  uint32_t stageSel = 0;  // double-buffered staging: a buffer is rewritten only after the bulk copy issued from it has read it
+  uint32_t stageSel = 0;  // a staging buffer is rewritten only after the bulk copy issued from it has read it
   const uint64_t streamPolicy = policy_evict_first();
 
   const uint32_t epoch = *epochCounter + SLOT_INSTANTIATE;
@@ -1614,7 +1621,8 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
 
   // One tile ahead: while a warp generates the vertices of tile k it already holds the ticket of its next tile, has
   // loaded those parts, scanned them and published their aggregate -- successors never wait on this warp's heavy work
-  // and the part-record load latency is off the critical path.
+  // and the part-record load latency is off the critical path.  (Interleaving the three dependent round trips of the
+  // fetch with the current tile's per-part work was measured slower: 7 more live registers spill at 96.)
   struct Fetched
   {
     uint32_t tile, instanceID, firstLocalVertex, vtx0, vtx1, vtx2, triCfg;
@@ -1692,10 +1700,6 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
     const uint32_t okVote = __ballot_sync(0xffffffffu, ok);
     accSucc += __popc(okVote);
     accTris += warp_sum(ok ? numTriangles : 0);
-    // successful parts are a prefix of the part list, hence of the tile
-    const uint32_t numOk   = __popc(okVote);
-    const uint32_t written = numOk ? __shfl_sync(0xffffffffu, incV, numOk - 1) : 0;
-
     if(ok)
     {  // records (:171-203) + per-part constants
       const uint32_t tempOffset = baseTemp + partIndex;
@@ -1774,9 +1778,9 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
         o0 = o[0]; o1 = o[1]; o2 = o[2]; o3 = o[3]; o4 = o[4]; o5 = o[5];
       }
       float* stage = stageBase + stageSel * INST_STAGE_WORDS;
-      stageSel ^= 1u;
+      stageSel = (stageSel + 1u) % INST_STAGES;
       if(lane == 0)
-        bulk_wait_read<1>();  // the copy issued two iterations ago (same buffer) has finished reading
+        bulk_wait_read<INST_STAGES - 1>();  // the copy that last read this buffer has finished reading
       __syncwarp();
       if(active)
       {
