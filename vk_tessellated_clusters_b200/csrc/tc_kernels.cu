@@ -1561,13 +1561,14 @@ __device__ __forceinline__ uint64_t policy_evict_first()
 // Every call commits exactly one bulk group (possibly empty), which is what the double-buffer wait counts.
 __device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint32_t shift, uint32_t nFloats, uint32_t lane, uint64_t policy)
 {
-  const uint32_t head = min(nFloats, (4u - shift) & 3u);
-  if(lane < head)
-    dst[lane] = stage[shift + lane];
+  const uint32_t head      = min(nFloats, (4u - shift) & 3u);
   const uint32_t bodyVec   = (nFloats - head) >> 2;
   const uint32_t tailStart = head + (bodyVec << 2);
-  if(lane < nFloats - tailStart)
-    dst[tailStart + lane] = stage[shift + tailStart + lane];
+  // lanes 0..2: head floats, lanes 4..6: tail floats (one predicated copy for both)
+  const uint32_t k   = lane & 3u;
+  const uint32_t idx = lane < 4u ? k : tailStart + k;
+  if(lane < 8u && k < (lane < 4u ? head : nFloats - tailStart))
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(dst + idx), "f"(stage[shift + idx]) : "memory");
   if(lane == 0)
   {
     if(bodyVec)
@@ -1589,7 +1590,9 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
 {
   extern __shared__ __align__(16) float instSmem[];
   __shared__ uint32_t shSucc, shTris;
-  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  // the warp index as a warp-UNIFORM value (REDUX writes a uniform register): shared-memory bases and the bulk-copy
+  // operands are then computed on the uniform datapath instead of per lane
+  const uint32_t warp = __reduce_max_sync(0xffffffffu, threadIdx.x >> 5), lane = lane_id();
   float* recBase = instSmem + size_t(warp) * INST_WARP_WORDS;
   float* stageBase = recBase + 32 * TC_REC_WORDS;
   uint32_t stageSel = 0;  // a staging buffer is rewritten only after the bulk copy issued from it has read it
