@@ -42,7 +42,9 @@ struct FrameState
   uint32_t splitPassesLeft;
   uint32_t hiAfterClassify;  // transient (back) side of the dual counter, constant during split
   uint32_t instTotalV;       // grand totals of the instantiate scan (written by the warp that owns the last tile)
-  uint32_t pad[4];
+  uint32_t clusterLevelWork;   // visible clusters the cluster-level emit kernel has to touch (counted by the count pass)
+  uint32_t triangleLevelWork;  // ... and the triangle-level emit kernel
+  uint32_t pad[2];
   unsigned long long instTotalD;
   uint32_t classTotal[8];    // grand totals of the classify scan: v[0..5], data lo, data hi
   // aggregated stats kept as plain counters and folded into Readback by the setup steps
