@@ -434,7 +434,7 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   size_t lbBytes = size_t(tc::lookback_tiles_needed(c->maxVisible, c->maxSplit, c->maxPart)) * tc::lookback_desc_bytes();
   TRY_RC(dalloc(c->dLookback, lbBytes));
   TRY_CUDA(cudaMemset(c->dLookback, 0, lbBytes));
-  size_t lb16Bytes = size_t(tc::lookback16_tiles_needed(c->maxPart)) * 16;
+  size_t lb16Bytes = size_t(tc::lookback16_tiles_needed(std::max(c->maxPart, c->maxSplit))) * 16;
   TRY_RC(dalloc(c->dLookback16, lb16Bytes));
   TRY_CUDA(cudaMemset(c->dLookback16, 0, lb16Bytes));
   TRY_RC(dalloc(c->dClassTuples, size_t(c->maxVisible) * tc::classify_tuple_bytes()));

@@ -44,7 +44,7 @@ struct FrameState
   uint32_t instTotalV;       // grand totals of the instantiate scan (written by the warp that owns the last tile)
   uint32_t clusterLevelWork;   // visible clusters the cluster-level emit kernel has to touch (counted by the count pass)
   uint32_t triangleLevelWork;  // ... and the triangle-level emit kernel
-  uint32_t pad[2];
+  uint32_t splitTotal[2];      // grand totals (split, part) of the current split pass (written by the warp that owns the last tile)
   unsigned long long instTotalD;
   uint32_t classTotal[8];    // grand totals of the classify scan: v[0..5], data lo, data hi
   // aggregated stats kept as plain counters and folded into Readback by the setup steps

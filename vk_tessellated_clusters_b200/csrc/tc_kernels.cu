@@ -1149,20 +1149,32 @@ __global__ void __launch_bounds__(CSCAN_THREADS) k_classify_scan(Params p, const
 // triangle_split (multipass variant), one launch per pass
 // ============================================================================================================
 
+// Warps are independent (no CTA barrier in the tile loop): a tile is 32 consecutive items handled by ONE warp --
+// the reference's subgroup -- with its own ticket and a 16-byte decoupled look-back over (split, part) counts.
+//   V. lane = (item, pattern vertex): every vertex of the items' split patterns is evaluated ONCE (barycentric
+//      encode, world position, eye distance) into a per-warp shared-memory cache; a (3,3,3) pattern has 9 children
+//      but only 10 distinct vertices, the child-level formulation evaluated 27 corners -- twice.
+//   C. lane = child, runs of 32 virtual threads exactly like processAllSubTasks: factors from the cached vertices,
+//      split / part decision, (cfg, rotation, kind) remembered as a 16-bit code; per-run counts.
+//   look-back: publish the tile's (split, part) counts, resolve the exclusive prefix.
+//   E. lane = child: records written from the cached encodings and codes, one allocation per run.
+// Tiles whose patterns do not fit the caches (split factors beyond (3,3,3) on every item) take the same steps with
+// the per-child evaluation of the reference in C and again in E -- identical results, no cache.
 constexpr int SPLIT_WARPS        = 4;
 constexpr int SPLIT_THREADS      = SPLIT_WARPS * 32;
+constexpr int SPLIT_TILE         = 32;       // items per tile
 constexpr int SPLIT_MAX_CHILDREN = 32 * 64;  // per warp: 32 items x <= 64 children (split factors <= 8)
 constexpr int SPLIT_MAX_RUNS     = SPLIT_MAX_CHILDREN / 32;
+constexpr int SPLIT_VCACHE       = 384;      // cached pattern vertices per warp: 32 x (3,3,3) = 320
+constexpr int SPLIT_CCACHE       = 512;      // cached child codes per warp
 
-struct SplitShared
+struct SplitWarpShared
 {
+  float4   vWorld[SPLIT_VCACHE];  // world position, eye distance
+  uint32_t vEnc[SPLIT_VCACHE];    // encoded barycentrics inside the base triangle
   // per child: new cfg (bit 15 flip, low 12 bits lookup index) | rotation << 12 (0 none, 1 .yzx, 2 .zxy) | bit 14: split again
-  uint16_t stash[SPLIT_WARPS][SPLIT_MAX_CHILDREN];
-  uint32_t runSplitPref[SPLIT_WARPS][SPLIT_MAX_RUNS + 1], runPartPref[SPLIT_WARPS][SPLIT_MAX_RUNS + 1];
-  uint32_t warpSplit[SPLIT_WARPS], warpPart[SPLIT_WARPS];
-  uint32_t prefSplit[SPLIT_WARPS], prefPart[SPLIT_WARPS];
-  uint32_t tile;
-  uint32_t validParts;
+  uint16_t code[SPLIT_CCACHE];
+  uint32_t runSplitPref[SPLIT_MAX_RUNS + 1], runPartPref[SPLIT_MAX_RUNS + 1];
 };
 
 // tess_getConfig that also reports which rotation it applied
@@ -1298,19 +1310,35 @@ __device__ void split_pass_epilogue(const Params& p, uint32_t baseSplit, uint32_
   }
 }
 
+// factors of one child from its world-space corners -> code (see SplitWarpShared::code)
+__device__ __forceinline__ uint32_t split_child_code(const FactorConsts& fcst, uint32_t splitFactor, const F3 w[3], const float d[3])
+{
+  uint32_t f[3];
+  tess_factors(fcst, w[0], w[1], w[2], d[0], d[1], d[2], f);
+  const bool split = max(max(f[0], f[1]), f[2]) > TC_TESSTABLE_SIZE;
+  if(split)
+  {
+    f[0] = tess_splitFactor(f[0], splitFactor); f[1] = tess_splitFactor(f[1], splitFactor); f[2] = tess_splitFactor(f[2], splitFactor);
+  }
+  uint32_t rot;
+  const uint32_t ncfg = tess_getConfigRot(f[0], f[1], f[2], rot);
+  return (ncfg & 0x8FFFu) | (rot << 12) | (split ? 0x4000u : 0u);
+}
+
 __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, const uint32_t* epochCounter, uint32_t pass, uint32_t lastPass)
 {
   pdl_prologue();
-  __shared__ SplitShared sh;
+  __shared__ SplitWarpShared shAll[SPLIT_WARPS];
+  __shared__ uint32_t        shValidParts;
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  SplitWarpShared& sh = shAll[warp];
   const uint32_t slot  = SLOT_SPLIT0 + pass;
   const uint32_t epoch = *epochCounter + slot;
   tc_SceneBuilding* b  = p.build;
   FrameState*       st = p.state;
-  LookbackDesc*     descs = reinterpret_cast<LookbackDesc*>(p.lookback);
   const uint32_t start = b->splitPassStart, end = b->splitPassEnd;
   const uint32_t numItems = end > start ? end - start : 0;
-  const uint32_t numTiles = (numItems + SPLIT_THREADS - 1) / SPLIT_THREADS;
+  const uint32_t numTiles = (numItems + SPLIT_TILE - 1) / SPLIT_TILE;
   // bases are constant while the pass runs: only the last CTA to finish writes the counters back
   const bool     transient = flag_transient(p);
   const uint32_t baseSplit = b->splitWriteCounter;
@@ -1327,22 +1355,24 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
     return;
   }
   if(threadIdx.x == 0)
-    sh.validParts = 0;
+    shValidParts = 0;
+  __syncthreads();
 
+  uint32_t validParts = 0;
   while(true)
   {
-    __syncthreads();
-    if(threadIdx.x == 0)
-      sh.tile = atomicAdd(&st->ticket[slot], 1u);
-    __syncthreads();
-    const uint32_t tile = sh.tile;
+    uint32_t tile = 0;
+    if(lane == 0)
+      tile = atomicAdd(&st->ticket[slot], 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
     if(tile >= numTiles)
       break;
 
-    const uint32_t readIndex = start + tile * SPLIT_THREADS + threadIdx.x;
+    // ---------------- lane = item ----------------
+    const uint32_t readIndex = start + tile * SPLIT_TILE + lane;
     const bool     runnable  = readIndex < end;
     uint32_t iInstance = 0, iCluster = 0, iVtx[3] = {0, 0, 0}, iTriCfg = 0;
-    uint32_t firstTriangle = 0, firstVertex = 0, subCount = 0;
+    uint32_t firstTriangle = 0, firstVertex = 0, subCount = 0, vtxCount = 0;
     F3       basePos[3] = {};
     if(runnable)
     {
@@ -1350,7 +1380,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
       uint2 a = src[0], c = src[1], d = src[2];
       iInstance = a.x; iCluster = a.y; iVtx[0] = c.x; iVtx[1] = c.y; iVtx[2] = d.x; iTriCfg = d.y;
       tc_TessTableEntry e = tess_entry(p, iTriCfg >> 16);
-      firstTriangle = e.firstTriangle; firstVertex = e.firstVertex; subCount = e.numTriangles;
+      firstTriangle = e.firstTriangle; firstVertex = e.firstVertex; subCount = e.numTriangles; vtxCount = e.numVertices;
       // fillBaseVertices (:146-174)
       const tc_RenderInstance& inst = p.instances[iInstance];
       const uint4 ch = __ldg(reinterpret_cast<const uint4*>(inst.clusters) + iCluster);
@@ -1368,8 +1398,51 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
     const uint32_t startOffset = endOffset - subCount;
     const uint32_t total       = __shfl_sync(0xffffffffu, endOffset, 31);
     const uint32_t numRuns     = (total + 31) / 32;
+    const uint32_t endVtx      = warp_inclusive_add(vtxCount);
+    const uint32_t startVtx    = endVtx - vtxCount;
+    const uint32_t totalVtx    = __shfl_sync(0xffffffffu, endVtx, 31);
+    const bool     cached      = totalVtx <= SPLIT_VCACHE && total <= SPLIT_CCACHE;  // warp-uniform
 
-    // ---------------- phase 1: classify every child, remember (cfg, rotation, kind) ----------------
+    // ---------------- V: every pattern vertex of the tile once ----------------
+    if(cached)
+    {
+      for(uint32_t t0 = 0; t0 < totalVtx; t0 += 32)
+      {
+        const uint32_t t     = t0 + lane;
+        const uint32_t item  = find_item(endVtx, t);
+        const uint32_t v     = t - __shfl_sync(0xffffffffu, startVtx, item);
+        const uint32_t pcfg  = __shfl_sync(0xffffffffu, iTriCfg, item) >> 16;
+        const uint32_t pFV   = __shfl_sync(0xffffffffu, firstVertex, item);
+        uint32_t pv[3];
+        F3       bp[3];
+#pragma unroll
+        for(int k = 0; k < 3; k++)
+        {
+          pv[k]   = __shfl_sync(0xffffffffu, iVtx[k], item);
+          bp[k].x = __shfl_sync(0xffffffffu, basePos[k].x, item);
+          bp[k].y = __shfl_sync(0xffffffffu, basePos[k].y, item);
+          bp[k].z = __shfl_sync(0xffffffffu, basePos[k].z, item);
+        }
+        if(t < totalVtx)
+        {
+          const F3 baseBary[3] = {tess_decodeBarycentrics(pv[0]), tess_decodeBarycentrics(pv[1]), tess_decodeBarycentrics(pv[2])};
+          F3 q = tess_decodeBarycentrics(__ldg(&p.tblVertices[pFV + v]));
+          if(pcfg & TC_CONFIG_FLIPPED_BIT)
+          {
+            const float tmp = q.x;
+            q.x = q.y;
+            q.y = tmp;
+          }
+          const uint32_t enc = tess_encodeBarycentrics(xinterp3(baseBary, q));
+          const F3       w   = xinterp3(bp, tess_decodeBarycentrics(enc));
+          sh.vEnc[t]   = enc;
+          sh.vWorld[t] = make_float4(w.x, w.y, w.z, xdistance3(w, fcst.eye));
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---------------- C: classify every child, per-run counts ----------------
     uint32_t nSplitW = 0, nPartW = 0;
     for(uint32_t r = 0; r < numRuns; r++)
     {
@@ -1379,98 +1452,81 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
       const uint32_t sub   = t - __shfl_sync(0xffffffffu, startOffset, item);
       const uint32_t pcfg  = __shfl_sync(0xffffffffu, iTriCfg, item) >> 16;
       const uint32_t pFT   = __shfl_sync(0xffffffffu, firstTriangle, item);
-      const uint32_t pFV   = __shfl_sync(0xffffffffu, firstVertex, item);
-      uint32_t pv[3];
-      F3       bp[3];
-#pragma unroll
-      for(int v = 0; v < 3; v++)
+      uint32_t code = 0;
+      if(cached)
       {
-        pv[v]   = __shfl_sync(0xffffffffu, iVtx[v], item);
-        bp[v].x = __shfl_sync(0xffffffffu, basePos[v].x, item);
-        bp[v].y = __shfl_sync(0xffffffffu, basePos[v].y, item);
-        bp[v].z = __shfl_sync(0xffffffffu, basePos[v].z, item);
-      }
-      bool split = false, part = false;
-      if(valid)
-      {
-        uint32_t enc[3];
-        split_child_corners(p, pcfg, pFT, pFV, sub, pv, enc);
-        F3 w[3];
-        float d[3];
+        const uint32_t vbase = __shfl_sync(0xffffffffu, startVtx, item);
+        if(valid)
+        {
+          const uint32_t packedTri = __ldg(&p.tblTriangles[pFT + sub]);
+          const bool     flipped   = (pcfg & TC_CONFIG_FLIPPED_BIT) != 0;
+          const uint32_t vi[3]     = {packedTri & 0xFF, (packedTri >> (flipped ? 16 : 8)) & 0xFF, (packedTri >> (flipped ? 8 : 16)) & 0xFF};
+          F3    w[3];
+          float d[3];
 #pragma unroll
-        for(int v = 0; v < 3; v++)
-        {
-          w[v] = xinterp3(bp, tess_decodeBarycentrics(enc[v]));
-          d[v] = xdistance3(w[v], fcst.eye);
+          for(int k = 0; k < 3; k++)
+          {
+            const float4 c = sh.vWorld[vbase + vi[k]];
+            w[k] = {c.x, c.y, c.z};
+            d[k] = c.w;
+          }
+          code       = split_child_code(fcst, p.splitFactor, w, d);
+          sh.code[t] = uint16_t(code);
         }
-        uint32_t f[3];
-        tess_factors(fcst, w[0], w[1], w[2], d[0], d[1], d[2], f);
-        uint32_t mx = max(max(f[0], f[1]), f[2]);
-        split       = mx > TC_TESSTABLE_SIZE;
-        part        = !split;
-        if(split)
-        {
-          f[0] = tess_splitFactor(f[0], p.splitFactor); f[1] = tess_splitFactor(f[1], p.splitFactor); f[2] = tess_splitFactor(f[2], p.splitFactor);
-        }
-        uint32_t rot;
-        uint32_t ncfg = tess_getConfigRot(f[0], f[1], f[2], rot);
-        sh.stash[warp][t] = uint16_t((ncfg & 0x8FFF) | (rot << 12) | (split ? 0x4000u : 0u));
       }
-      uint32_t cs = __popc(__ballot_sync(0xffffffffu, split)), cp = __popc(__ballot_sync(0xffffffffu, part));
+      else
+      {
+        const uint32_t pFV = __shfl_sync(0xffffffffu, firstVertex, item);
+        uint32_t pv[3];
+        F3       bp[3];
+#pragma unroll
+        for(int k = 0; k < 3; k++)
+        {
+          pv[k]   = __shfl_sync(0xffffffffu, iVtx[k], item);
+          bp[k].x = __shfl_sync(0xffffffffu, basePos[k].x, item);
+          bp[k].y = __shfl_sync(0xffffffffu, basePos[k].y, item);
+          bp[k].z = __shfl_sync(0xffffffffu, basePos[k].z, item);
+        }
+        if(valid)
+        {
+          uint32_t enc[3];
+          split_child_corners(p, pcfg, pFT, pFV, sub, pv, enc);
+          F3    w[3];
+          float d[3];
+#pragma unroll
+          for(int k = 0; k < 3; k++)
+          {
+            w[k] = xinterp3(bp, tess_decodeBarycentrics(enc[k]));
+            d[k] = xdistance3(w[k], fcst.eye);
+          }
+          code = split_child_code(fcst, p.splitFactor, w, d);
+        }
+      }
+      const bool     split = valid && (code & 0x4000u), part = valid && !(code & 0x4000u);
+      const uint32_t cs = __popc(__ballot_sync(0xffffffffu, split)), cp = __popc(__ballot_sync(0xffffffffu, part));
       if(lane == 0)
       {
-        sh.runSplitPref[warp][r] = nSplitW;
-        sh.runPartPref[warp][r]  = nPartW;
+        sh.runSplitPref[r] = nSplitW;
+        sh.runPartPref[r]  = nPartW;
       }
       nSplitW += cs;
       nPartW += cp;
     }
-    if(lane == 0)
-    {
-      sh.runSplitPref[warp][numRuns] = nSplitW;
-      sh.runPartPref[warp][numRuns]  = nPartW;
-      sh.warpSplit[warp] = nSplitW;
-      sh.warpPart[warp]  = nPartW;
-    }
-    __syncthreads();
+    __syncwarp();
 
-    // ---------------- tile scan + look-back ----------------
-    if(warp == 0)
+    // ---------------- look-back over (split, part) counts ----------------
+    lookback16_publish(p.lookback16, tile, nSplitW, nPartW, epoch);
+    uint32_t           exclSplit;
+    unsigned long long exclPart64;
+    lookback16_resolve(p.lookback16, tile, nSplitW, nPartW, epoch, exclSplit, exclPart64);
+    const uint32_t exclPart = uint32_t(exclPart64);
+    if(tile == numTiles - 1 && lane == 0)
     {
-      ScanTuple total2;
-      total2.zero();
-      uint32_t ps = 0, pp = 0;
-      for(int w = 0; w < SPLIT_WARPS; w++)
-      {
-        if(lane == 0)
-        {
-          sh.prefSplit[w] = ps;
-          sh.prefPart[w]  = pp;
-        }
-        ps += sh.warpSplit[w];
-        pp += sh.warpPart[w];
-      }
-      total2.v[0] = ps;
-      total2.v[1] = pp;
-      ScanTuple excl = lookback_exclusive(descs, tile, total2, epoch);
-      if(lane == 0)
-      {
-        for(int w = 0; w < SPLIT_WARPS; w++)
-        {
-          sh.prefSplit[w] += excl.v[0];
-          sh.prefPart[w] += excl.v[1];
-        }
-        if(tile == numTiles - 1)
-        {
-          excl.add(total2);
-          st_tuple(reinterpret_cast<ScanTuple*>(&descs[numTiles].aggregate), excl);
-        }
-      }
+      st->splitTotal[0] = exclSplit + nSplitW;
+      st->splitTotal[1] = exclPart + nPartW;
     }
-    __syncthreads();
 
-    // ---------------- phase 2: emit, one allocation per run of 32 children (processSubTask :252-330) ----------------
-    uint32_t validParts = 0;
+    // ---------------- E: emit, one allocation per run of 32 children (processSubTask :252-330) ----------------
     for(uint32_t r = 0; r < numRuns; r++)
     {
       const uint32_t t     = r * 32 + lane;
@@ -1479,25 +1535,58 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
       const uint32_t sub   = t - __shfl_sync(0xffffffffu, startOffset, item);
       const uint32_t ptc   = __shfl_sync(0xffffffffu, iTriCfg, item);
       const uint32_t pFT   = __shfl_sync(0xffffffffu, firstTriangle, item);
-      const uint32_t pFV   = __shfl_sync(0xffffffffu, firstVertex, item);
       const uint32_t pInst = __shfl_sync(0xffffffffu, iInstance, item);
       const uint32_t pClus = __shfl_sync(0xffffffffu, iCluster, item);
-      uint32_t pv[3];
+      uint32_t code = 0, enc[3] = {0, 0, 0};
+      if(cached)
+      {
+        const uint32_t vbase = __shfl_sync(0xffffffffu, startVtx, item);
+        if(valid)
+        {
+          const uint32_t packedTri = __ldg(&p.tblTriangles[pFT + sub]);
+          const bool     flipped   = ((ptc >> 16) & TC_CONFIG_FLIPPED_BIT) != 0;
+          enc[0] = sh.vEnc[vbase + (packedTri & 0xFF)];
+          enc[1] = sh.vEnc[vbase + ((packedTri >> (flipped ? 16 : 8)) & 0xFF)];
+          enc[2] = sh.vEnc[vbase + ((packedTri >> (flipped ? 8 : 16)) & 0xFF)];
+          code   = sh.code[t];
+        }
+      }
+      else
+      {
+        const uint32_t pFV = __shfl_sync(0xffffffffu, firstVertex, item);
+        uint32_t pv[3];
+        F3       bp[3];
 #pragma unroll
-      for(int v = 0; v < 3; v++)
-        pv[v] = __shfl_sync(0xffffffffu, iVtx[v], item);
-      uint32_t code  = valid ? sh.stash[warp][t] : 0;
-      bool     split = valid && (code & 0x4000u), part = valid && !(code & 0x4000u);
-      uint32_t voteSplit = __ballot_sync(0xffffffffu, split), votePart = __ballot_sync(0xffffffffu, part);
-      uint32_t countPart = __popc(votePart);
-      uint32_t offsetSplit = baseSplit + sh.prefSplit[warp] + sh.runSplitPref[warp][r] + __popc(voteSplit & lanemask_lt());
-      uint32_t loBefore    = baseLo + sh.prefPart[warp] + sh.runPartPref[warp][r];
-      uint32_t offsetPart  = dual_front_offset(p, loBefore, hi, countPart) + __popc(votePart & lanemask_lt());
+        for(int k = 0; k < 3; k++)
+        {
+          pv[k]   = __shfl_sync(0xffffffffu, iVtx[k], item);
+          bp[k].x = __shfl_sync(0xffffffffu, basePos[k].x, item);
+          bp[k].y = __shfl_sync(0xffffffffu, basePos[k].y, item);
+          bp[k].z = __shfl_sync(0xffffffffu, basePos[k].z, item);
+        }
+        if(valid)
+        {
+          split_child_corners(p, ptc >> 16, pFT, pFV, sub, pv, enc);
+          F3    w[3];
+          float d[3];
+#pragma unroll
+          for(int k = 0; k < 3; k++)
+          {
+            w[k] = xinterp3(bp, tess_decodeBarycentrics(enc[k]));
+            d[k] = xdistance3(w[k], fcst.eye);
+          }
+          code = split_child_code(fcst, p.splitFactor, w, d);
+        }
+      }
+      const bool     split = valid && (code & 0x4000u), part = valid && !(code & 0x4000u);
+      const uint32_t voteSplit = __ballot_sync(0xffffffffu, split), votePart = __ballot_sync(0xffffffffu, part);
+      const uint32_t countPart = __popc(votePart);
+      const uint32_t offsetSplit = baseSplit + exclSplit + sh.runSplitPref[r] + __popc(voteSplit & lanemask_lt());
+      const uint32_t loBefore    = baseLo + exclPart + sh.runPartPref[r];
+      const uint32_t offsetPart  = dual_front_offset(p, loBefore, hi, countPart) + __popc(votePart & lanemask_lt());
       if(valid)
       {
-        uint32_t enc[3];
-        split_child_corners(p, ptc >> 16, pFT, pFV, sub, pv, enc);
-        uint32_t rot = (code >> 12) & 3u;
+        const uint32_t rot = (code >> 12) & 3u;
         uint32_t v0 = enc[0], v1 = enc[1], v2 = enc[2];
         if(rot == 1)
         {
@@ -1507,7 +1596,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
         {
           v0 = enc[2]; v1 = enc[0]; v2 = enc[1];
         }
-        uint32_t triCfg = (ptc & 0xFFFFu) | ((code & 0x8FFFu) << 16);
+        const uint32_t triCfg = (ptc & 0xFFFFu) | ((code & 0x8FFFu) << 16);
         if(split && offsetSplit < p.maxSplitTriangles)
         {
           uint2* dst = reinterpret_cast<uint2*>(&splitTriangles[offsetSplit]);
@@ -1525,26 +1614,27 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
         }
       }
     }
-#pragma unroll
-    for(int d = 16; d > 0; d >>= 1)
-      validParts = max(validParts, __shfl_xor_sync(0xffffffffu, validParts, d));
-    if(lane == 0 && validParts)
-      atomicMax(&sh.validParts, validParts);
+    __syncwarp();  // the per-warp caches are rewritten by the next tile
   }
+#pragma unroll
+  for(int d = 16; d > 0; d >>= 1)
+    validParts = max(validParts, __shfl_xor_sync(0xffffffffu, validParts, d));
+  if(lane == 0 && validParts)
+    atomicMax(&shValidParts, validParts);
 
   // ---------------- epilogue: BUILD_SETUP_SPLIT_PASS (:168-190) or BUILD_SETUP_INSTANTIATE_TESS (:236-264) ----------------
   __syncthreads();
   if(threadIdx.x == 0)
   {
-    if(sh.validParts)
-      atomicMax(&st->validParts, sh.validParts);
+    if(shValidParts)
+      atomicMax(&st->validParts, shValidParts);
     __threadfence();
     uint32_t done = atomicAdd(&st->done[slot], 1u);
     if(done == gridDim.x - 1)
     {
       __threadfence();
-      ScanTuple tot = ld_tuple(reinterpret_cast<const ScanTuple*>(&descs[numTiles].aggregate));
-      split_pass_epilogue(p, baseSplit, baseLo, hi, tot.v[0], tot.v[1], lastPass != 0);
+      const uint32_t totSplit = *(volatile uint32_t*)&st->splitTotal[0], totPart = *(volatile uint32_t*)&st->splitTotal[1];
+      split_pass_epilogue(p, baseSplit, baseLo, hi, totSplit, totPart, lastPass != 0);
     }
   }
 }
@@ -2169,7 +2259,8 @@ int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, Kerne
 uint32_t lookback_tiles_needed(uint32_t maxVisible, uint32_t maxSplit, uint32_t maxPart)
 {
   uint32_t a = (maxVisible + CSCAN_TILE - 1) / CSCAN_TILE;
-  uint32_t b = (maxSplit + SPLIT_THREADS - 1) / SPLIT_THREADS;
+  uint32_t b = 0;  // the split passes use the 16-byte descriptors too
+  (void)maxSplit;
   uint32_t c = 0;  // the instantiate scan has its own 16-byte descriptors (lookback16_tiles_needed)
   uint32_t m = a > b ? a : b;
   m          = m > c ? m : c;
@@ -2179,7 +2270,7 @@ uint32_t lookback_tiles_needed(uint32_t maxVisible, uint32_t maxSplit, uint32_t 
 size_t lookback_desc_bytes() { return sizeof(LookbackDesc); }
 uint32_t classify_tile_clusters() { return CLASSIFY_WARPS; }
 size_t   classify_tuple_bytes() { return sizeof(ScanTuple); }
-uint32_t lookback16_tiles_needed(uint32_t maxPart) { return (maxPart + 31) / 32 + 2; }
+uint32_t lookback16_tiles_needed(uint32_t maxItems) { return (maxItems + 31) / 32 + 2; }
 size_t frame_state_bytes() { return sizeof(FrameState); }
 
 void launch_frame_setup(const Params& p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter, cudaStream_t s)
