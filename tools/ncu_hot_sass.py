@@ -4,7 +4,12 @@ import csv, subprocess, sys
 rep = sys.argv[1]; n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hdr = rows[1]; body = rows[2:]
+# the page holds one block per captured kernel ("Kernel Name" row, header row, body); take block K (argv[3], default 0)
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+K = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+lo = starts[K]; hi = starts[K + 1] if K + 1 < len(starts) else len(rows)
+print(rows[lo][1][:100])
+hdr = rows[lo + 1]; body = [r for r in rows[lo + 2:hi] if len(r) == len(hdr)]
 ia, isrc, isamp, iex = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 tot = sum(int(r[isamp]) for r in body)

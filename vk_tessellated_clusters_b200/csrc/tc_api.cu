@@ -326,8 +326,14 @@ int enqueue_build(tc_context* c)
     StageScope sc(c, TC_STAGE_SPLIT);
     uint32_t passes = split_pass_count(std::max(2u, c->cfg.splitFactor));
     // pass 0 sees the bulk of the work; deeper levels are usually small or empty
-    uint32_t grid0 = std::max(1u, uint32_t(c->numSMs * c->occ.split));
-    uint32_t gridN = std::max(1u, uint32_t(c->numSMs * std::min(c->occ.split, 2)));
+#ifndef TC_SPLIT_CTAS0
+#define TC_SPLIT_CTAS0 8
+#endif
+#ifndef TC_SPLIT_CTASN
+#define TC_SPLIT_CTASN 2
+#endif
+    uint32_t grid0 = std::max(1u, uint32_t(c->numSMs * std::min(c->occ.split, TC_SPLIT_CTAS0)));
+    uint32_t gridN = std::max(1u, uint32_t(c->numSMs * std::min(c->occ.split, TC_SPLIT_CTASN)));
     for(uint32_t k = 0; k < passes; k++)
       tc::launch_triangle_split(p, c->dEpoch, k, k + 1 == passes, k == 0 ? grid0 : gridN, s);
     launches += passes;

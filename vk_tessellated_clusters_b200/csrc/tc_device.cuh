@@ -483,6 +483,69 @@ __device__ __forceinline__ void lookback16_resolve(uint4* descs, uint32_t tile, 
   }
 }
 
+// Same, W descriptors per lane and step (window of 32*W tiles).  The inclusive prefix travels backwards-looking
+// warp by warp: when thousands of short tiles are in flight at once (split passes), a tile far from the last resolved
+// one needs (distance / window) dependent L2 round trips, so the window width sets how fast the prefix propagates.
+template <int W>
+__device__ __forceinline__ void lookback16_resolve_wide(uint4* descs, uint32_t tile, uint32_t aggV, unsigned long long aggD, uint32_t epoch,
+                                                        uint32_t& exclV, unsigned long long& exclD)
+{
+  const uint32_t lane = lane_id();
+  const uint32_t AGG = (epoch << 2) | 1u, INC = (epoch << 2) | 2u;
+  exclV = 0;
+  exclD = 0;
+  if(tile == 0)
+    return;
+  int32_t base = int32_t(tile) - 1;
+  while(true)
+  {
+    // lane l owns tiles base - l*W - k, k = 0..W-1 (nearest first); all W loads are issued before any is examined
+    uint4 w[W];
+#pragma unroll
+    for(int k = 0; k < W; k++)
+    {
+      const int32_t t = base - int32_t(lane) * W - k;
+      w[k] = t >= 0 ? ld_desc16(&descs[t]) : make_uint4(INC, 0u, 0u, 0u);
+    }
+    uint32_t           v = 0;
+    unsigned long long d = 0;
+    bool               inc = false;
+#pragma unroll
+    for(int k = 0; k < W; k++)
+    {
+      const int32_t t = base - int32_t(lane) * W - k;
+      while(w[k].x != AGG && w[k].x != INC)
+        w[k] = ld_desc16(&descs[t]);
+      if(!inc)
+      {
+        v += w[k].y;
+        d += (unsigned long long)w[k].z | ((unsigned long long)w[k].w << 32);
+        inc = (w[k].x & 3u) == 2u;
+      }
+    }
+    const uint32_t incMask  = __ballot_sync(0xffffffffu, inc);
+    const uint32_t firstInc = incMask ? (__ffs(incMask) - 1) : 32;
+    if(lane > firstInc)
+    {
+      v = 0;
+      d = 0;
+    }
+    exclV += __reduce_add_sync(0xffffffffu, v);
+#pragma unroll
+    for(int k = 16; k > 0; k >>= 1)
+      d += __shfl_xor_sync(0xffffffffu, d, k);
+    exclD += d;
+    if(incMask)
+      break;
+    base -= 32 * W;
+  }
+  if(lane == 0)
+  {
+    const unsigned long long incD = exclD + aggD;
+    st_desc16(&descs[tile], make_uint4(INC, exclV + aggV, uint32_t(incD), uint32_t(incD >> 32)));
+  }
+}
+
 __device__ __forceinline__ float fast_rsqrt(float x)
 {
   float r;

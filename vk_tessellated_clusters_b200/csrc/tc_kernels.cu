@@ -1160,6 +1160,9 @@ __global__ void __launch_bounds__(CSCAN_THREADS) k_classify_scan(Params p, const
 //   E. lane = child: records written from the cached encodings and codes, one allocation per run.
 // Tiles whose patterns do not fit the caches (split factors beyond (3,3,3) on every item) take the same steps with
 // the per-child evaluation of the reference in C and again in E -- identical results, no cache.
+#ifndef TC_SPLIT_LOOKBACK_W
+#define TC_SPLIT_LOOKBACK_W 1
+#endif
 constexpr int SPLIT_WARPS        = 4;
 constexpr int SPLIT_THREADS      = SPLIT_WARPS * 32;
 constexpr int SPLIT_TILE         = 32;       // items per tile
@@ -1518,7 +1521,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
     lookback16_publish(p.lookback16, tile, nSplitW, nPartW, epoch);
     uint32_t           exclSplit;
     unsigned long long exclPart64;
-    lookback16_resolve(p.lookback16, tile, nSplitW, nPartW, epoch, exclSplit, exclPart64);
+    lookback16_resolve_wide<TC_SPLIT_LOOKBACK_W>(p.lookback16, tile, nSplitW, nPartW, epoch, exclSplit, exclPart64);
     const uint32_t exclPart = uint32_t(exclPart64);
     if(tile == numTiles - 1 && lane == 0)
     {
