@@ -122,6 +122,18 @@ TC_API int tc_set_scene(tc_context* ctx, const tc_geometry* geoms, uint32_t numG
  * clamp-to-edge (src/nvhiz_vk.cpp:83-115).  Only read when TC_FLAG_CULLING is set. */
 TC_API int tc_set_hiz(tc_context* ctx, const float* mips, uint32_t size, uint32_t mipLevels);
 
+/* Far-HiZ pyramid BUILDER: NVHizVK::cmdUpdateHiz (src/nvhiz_vk.cpp:484-594) running
+ * shaders/nvhiz-update.comp.glsl:109-221 with NV_HIZ_LEVELS 3, hizFarLevel 0, no MSAA, reversedZ off
+ * (src/resources.cpp:181).  `depth` is last frame's depth image, width*height floats, row-major, on the device
+ * (depthIsDevice != 0, enqueued on the context stream without a copy) or on the host.  Replaces the pyramid that
+ * tc_set_hiz installed; texels the reference's dispatches never write read as zero.  tc_hiz_info is
+ * NVHizVK::setupUpdateInfos + TextureInfo::getShaderFactors (src/nvhiz_vk.cpp:29-40, :278-309): the pyramid shape and the
+ * FrameConstants::hizSizeFactors / hizSizeMax values that go with it.  tc_get_hiz downloads the packed pyramid
+ * (out == NULL: only size/mipLevels). */
+TC_API int tc_hiz_info(uint32_t width, uint32_t height, uint32_t* size, uint32_t* mipLevels, float factors[4], float* sizeMax);
+TC_API int tc_update_hiz(tc_context* ctx, const float* depth, uint32_t width, uint32_t height, uint32_t depthIsDevice);
+TC_API int tc_get_hiz(tc_context* ctx, float* out, size_t capacityFloats, uint32_t* size, uint32_t* mipLevels);
+
 /* Driver stand-in for parity/bench runs: the reference's tempClusterSizes / transClusterSizes / blasBuildSizes
  * are written by the CLAS/BLAS builds.  mode 0: leave whatever the consumer wrote; mode 1 (default): the
  * library fills tempClusterSizes/transClusterSizes with each CLAS' reserved size before the insert step. */

@@ -93,6 +93,8 @@ public:
 
   /* Renderer::updatedFrameBuffer equivalent for the path: a new far-HiZ pyramid (last frame's depth) */
   bool updatedHiz(const float* mips, uint32_t size, uint32_t mipLevels) { return tc_set_hiz(m_ctx, mips, size, mipLevels) == TC_OK || failed(); }
+  // NVHizVK::cmdUpdateHiz: build the far pyramid from last frame's depth image (device pointer)
+  bool updateHiz(const float* depthDevice, uint32_t width, uint32_t height) { return tc_update_hiz(m_ctx, depthDevice, width, height, 1) == TC_OK || failed(); }
 
   /* Renderer::render: frame.frameConstants / frameConstantsLast are consecutive in FrameConfig (stride = sizeof one) */
   void render(const void* frameConstantsPair, size_t strideBytes, bool freezeCulling = false)

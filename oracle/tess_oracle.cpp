@@ -1395,6 +1395,143 @@ ORC_API int orc_set_hiz(orc_context* c, const float* mips, uint32_t size, uint32
   return TC_OK;
 }
 
+// ---- far-HiZ pyramid builder -------------------------------------------------------------------------------
+// NVHizVK::setupUpdateInfos + TextureInfo::getShaderFactors (src/nvhiz_vk.cpp:29-40, :278-309), hizFarLevel 0
+ORC_API int orc_hiz_info(uint32_t width, uint32_t height, uint32_t* size, uint32_t* mipLevels, float factors[4], float* sizeMax)
+{
+  if(width < 2 || height < 2)
+    return TC_ERR_INVALID_ARG;
+  const uint32_t divisor = 2u << 0;
+  uint32_t dim = (width > height ? width : height) / divisor, hiz = 1, mips = 1;
+  while(hiz < dim)
+  {
+    hiz *= 2;
+    mips++;
+  }
+  const uint32_t usedW = width / divisor, usedH = height / divisor;
+  if(size) *size = hiz;
+  if(mipLevels) *mipLevels = mips;
+  if(factors)
+  {
+    factors[0] = float(usedW) / float(hiz);
+    factors[1] = float(usedH) / float(hiz);
+    factors[2] = float(usedW - 2) / float(hiz);
+    factors[3] = float(usedH - 2) / float(hiz);
+  }
+  if(sizeMax) *sizeMax = float(hiz);
+  return TC_OK;
+}
+
+// NVHizVK::cmdUpdateHiz (src/nvhiz_vk.cpp:484-594) executing shaders/nvhiz-update.comp.glsl:109-221 invocation by
+// invocation: NV_HIZ_LEVELS 3, far output only, reversedZ off (maxOp = max).  Every dispatch is walked workgroup by
+// workgroup and lane by lane with the shader's own lane -> texel map and shuffle pattern.
+ORC_API int orc_update_hiz(orc_context* c, const float* depth, uint32_t width, uint32_t height, uint32_t /*depthIsDevice*/)
+{
+  uint32_t size = 0, mips = 0;
+  if(!c || !depth || orc_hiz_info(width, height, &size, &mips, nullptr, nullptr) != TC_OK)
+    return TC_ERR_INVALID_ARG;
+  std::vector<size_t> levelOffset(mips);
+  size_t total = 0;
+  for(uint32_t l = 0; l < mips; l++)
+  {
+    levelOffset[l] = total;
+    size_t s = std::max(1u, size >> l);
+    total += s * s;
+  }
+  if(c->hiz.size() != total || c->hizSize != size || c->hizMips != mips)
+    c->hiz.assign(total, 0.0f);
+  c->hizSize = size;
+  c->hizMips = mips;
+
+  const uint32_t hizLevels = 3, align = 8;
+  uint32_t inputW = width, inputH = height;                    // :486-487
+  uint32_t subW = (inputW + 1) / 2, subH = (inputH + 1) / 2;   // :492-493
+  for(uint32_t i = 0; i < mips; i += hizLevels)                // :539
+  {
+    const uint32_t inputLod = (i == 0) ? 0 : i - 1;            // :541
+    bool levelActive[3];
+    for(uint32_t level = 0; level < hizLevels; level++)
+      levelActive[level] = level + i < mips;                   // :558-562
+    subW = ((subW + align - 1) / align) * align;               // :564-565
+    subH = ((subH + align - 1) / align) * align;
+    const int srcSizeZ = int(inputW) - 2, srcSizeW = int(inputH) - 2;  // :567-570
+    const float*   src      = (i == 0) ? depth : c->hiz.data() + levelOffset[inputLod];
+    const uint32_t srcPitch = (i == 0) ? width : std::max(1u, size >> inputLod);
+    const uint32_t srcW = srcPitch, srcH = (i == 0) ? height : srcPitch;
+    // texelFetch outside the level is undefined in the reference (only reachable for odd sizes just above 2*2^k);
+    // defined here as the robust-access result 0
+    auto fetch = [&](int x, int y) { return (uint32_t(x) < srcW && uint32_t(y) < srcH) ? src[size_t(y) * srcPitch + x] : 0.0f; };
+    auto store = [&](uint32_t level, int x, int y, float v) {  // imageStore: out-of-bounds writes are dropped
+      const uint32_t n = std::max(1u, size >> level);
+      if(x >= 0 && y >= 0 && uint32_t(x) < n && uint32_t(y) < n)
+        c->hiz[levelOffset[level] + size_t(y) * n + x] = v;
+    };
+    const uint32_t groupsX = (subW + 7) / 8, groupsY = (subH + 7) / 8;  // :580
+    for(uint32_t gy = 0; gy < groupsY; gy++)
+      for(uint32_t gx = 0; gx < groupsX; gx++)
+        for(uint32_t ly = 0; ly < 2; ly++)  // local_size_y = 2: one 32-wide subgroup each
+        {
+          float zMax[32];
+          int   ocx[32], ocy[32];
+          for(uint32_t lane = 0; lane < 32; lane++)
+          {
+            int sx = int(lane & 1), sy = int(lane / 2);  // :111-114
+            if(lane >= 16)
+            {
+              sx += 2;
+              sy -= 8;
+            }
+            sx += int(ly * 4);
+            ocx[lane] = int(gx * 8) + sx;
+            ocy[lane] = int(gy * 8) + sy;
+            const int cx = std::min(ocx[lane] * 2, srcSizeZ), cy = std::min(ocy[lane] * 2, srcSizeW);  // :150
+            const float z0 = fetch(cx, cy), z1 = fetch(cx + 1, cy), z2 = fetch(cx, cy + 1), z3 = fetch(cx + 1, cy + 1);
+            zMax[lane] = std::max(std::max(std::max(z0, z1), z2), z3);  // :156
+            store(i, ocx[lane], ocy[lane], zMax[lane]);                 // :162
+          }
+          if(!(levelActive[1] || levelActive[2]))
+            continue;
+          float zMax1[32] = {};
+          for(uint32_t lane = 0; lane < 32; lane += 4)  // (laneID & 3) == 0, :185
+          {
+            zMax1[lane] = std::max(std::max(std::max(zMax[lane], zMax[lane + 1]), zMax[lane + 2]), zMax[lane + 3]);
+            store(i + 1, ocx[lane] / 2, ocy[lane] / 2, zMax1[lane]);  // :190
+          }
+          if(!levelActive[2])
+            continue;
+          for(uint32_t lane : {0u, 8u})  // :212
+          {
+            const float z = std::max(std::max(std::max(zMax1[lane], zMax1[lane + 4]), zMax1[lane + 16]), zMax1[lane + 20]);
+            store(i + 2, ocx[lane] / 4, ocy[lane] / 4, z);  // :214
+          }
+        }
+    for(uint32_t level = 0; level < hizLevels; level++)  // :583-587
+    {
+      subW = (subW + 1) / 2;
+      subH = (subH + 1) / 2;
+    }
+    subW   = subW ? subW : 1;
+    subH   = subH ? subH : 1;
+    inputW = subW * 2;  // :592-593
+    inputH = subH * 2;
+  }
+  return TC_OK;
+}
+
+ORC_API int orc_get_hiz(orc_context* c, float* out, size_t capacityFloats, uint32_t* size, uint32_t* mipLevels)
+{
+  if(!c)
+    return TC_ERR_INVALID_ARG;
+  if(size) *size = c->hizSize;
+  if(mipLevels) *mipLevels = c->hizMips;
+  if(!out)
+    return TC_OK;
+  if(capacityFloats < c->hiz.size())
+    return TC_ERR_INVALID_ARG;
+  std::copy(c->hiz.begin(), c->hiz.end(), out);
+  return TC_OK;
+}
+
 // base addresses embedded into records (pass the CUDA context's tc_SceneBuilding to compare bytes)
 ORC_API int orc_set_addresses(orc_context* c, const tc_SceneBuilding* addresses)
 {

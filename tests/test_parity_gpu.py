@@ -123,3 +123,71 @@ def test_invalid_usage_is_reported(table):
         g2.set_scene(scene)
     g2.close()
     gpu.close()
+
+
+# ---- far-HiZ builder: tc_update_hiz vs the oracle's lane-by-lane walk of nvhiz-update ----
+from oracle.oracle_binding import Oracle  # noqa: E402
+
+HIZ_SIZES = [(2, 2), (16, 16), (37, 23), (23, 37), (255, 257), (640, 360), (1000, 1000), (1920, 1080), (3840, 2160)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h", HIZ_SIZES)
+def test_hiz_builder_bit_exact(w, h, oracle_lib):
+    rng = np.random.default_rng(2342 + w * 7 + h)
+    depth = rng.random((h, w), dtype=np.float32)
+    gpu, orc = api.TessClusters(), Oracle()
+    gpu.update_hiz(depth)
+    orc.update_hiz(depth)
+    g, gs, gm = gpu.get_hiz()
+    o, os_, om = orc.get_hiz()
+    assert (gs, gm) == (os_, om)
+    assert g.tobytes() == o.tobytes()
+    # a second update with another image reuses the allocation and must not keep stale texels in the written region
+    depth2 = rng.random((h, w), dtype=np.float32)
+    gpu.update_hiz(depth2)
+    orc.update_hiz(depth2)
+    assert gpu.get_hiz()[0].tobytes() == orc.get_hiz()[0].tobytes()
+    gpu.close()
+    orc.close()
+
+
+@pytest.mark.gpu
+def test_hiz_builder_device_pointer_path(oracle_lib):
+    import torch
+
+    depth = torch.rand((1080, 1920), dtype=torch.float32, device="cuda:0")
+    torch.cuda.synchronize()
+    gpu, orc = api.TessClusters(), Oracle()
+    gpu.update_hiz(None, device_ptr=depth.data_ptr(), width=1920, height=1080)
+    orc.update_hiz(depth.cpu().numpy())
+    assert gpu.get_hiz()[0].tobytes() == orc.get_hiz()[0].tobytes()
+    gpu.close()
+    orc.close()
+
+
+@pytest.mark.gpu
+def test_culling_frame_with_built_hiz_matches_oracle(table, oracle_lib):
+    """The culling case again, but the pyramid is BUILT on each side from a depth image instead of being uploaded."""
+    scene, fcs, cfg, hiz = case("culling")
+    w, h = int(fcs[0]["viewport"][0]), int(fcs[0]["viewport"][1])
+    yy, xx = np.mgrid[0:h, 0:w]
+    depth = np.where((xx > w * 0.3) & (xx < w * 0.7), 0.35, 1.0).astype(np.float32)  # a wall in the middle of the screen
+    depth += (np.sin(xx * 0.01) * 0.01).astype(np.float32)
+    tbl = table
+    gpu, orc = api.TessClusters(cfg), Oracle(cfg)
+    for b in (gpu, orc):
+        b.set_tess_table(tbl)
+        b.set_scene(scene)
+        b.update_hiz(depth)
+    gpu.frame(fcs)
+    rb, sb = gpu.readback()
+    orc.set_addresses(sb)
+    orc.frame(fcs)
+    rbo, sbo = orc.readback()
+    for f in ["numVisibleClusters", "numFullClusters", "numPartTriangles", "numTotalTriangles", "numBlasClusters", "numGenVertices"]:
+        assert int(rb[f]) == int(rbo[f]), f
+    n = int(sb["blasClusterCounter"])
+    assert gpu.buffer("blasClusterAddresses", n, sb).tobytes() == orc.buffer("blasClusterAddresses", n).tobytes()
+    gpu.close()
+    orc.close()

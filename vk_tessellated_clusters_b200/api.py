@@ -257,6 +257,32 @@ class Binding:
         p = np.ascontiguousarray(pyramid, np.float32)
         self._check(self._fn("set_hiz")(self._ctx, _ptr(p), C.c_uint32(size), C.c_uint32(mips)), "set_hiz")
 
+    def update_hiz(self, depth: np.ndarray, device_ptr: int | None = None, width: int | None = None, height: int | None = None):
+        """NVHizVK::cmdUpdateHiz: far pyramid from a depth image (host array, or a device pointer with explicit size)."""
+        if device_ptr is not None:
+            self._check(self._fn("update_hiz")(self._ctx, C.c_void_p(device_ptr), C.c_uint32(width), C.c_uint32(height), C.c_uint32(1)), "update_hiz")
+            return
+        d = np.ascontiguousarray(depth, np.float32)
+        assert d.ndim == 2
+        self._keep_depth = d
+        self._check(self._fn("update_hiz")(self._ctx, _ptr(d), C.c_uint32(d.shape[1]), C.c_uint32(d.shape[0]), C.c_uint32(0)), "update_hiz")
+
+    def get_hiz(self):
+        """-> (packed pyramid float32, size, mips)"""
+        size, mips = C.c_uint32(), C.c_uint32()
+        self._check(self._fn("get_hiz")(self._ctx, None, C.c_size_t(0), C.byref(size), C.byref(mips)), "get_hiz")
+        total = sum(max(1, size.value >> l) ** 2 for l in range(mips.value))
+        out = np.zeros(total, np.float32)
+        self._check(self._fn("get_hiz")(self._ctx, _ptr(out), C.c_size_t(total), C.byref(size), C.byref(mips)), "get_hiz")
+        return out, size.value, mips.value
+
+    def hiz_info(self, width: int, height: int):
+        """-> (size, mips, factors[4], sizeMax) of the far pyramid for a width x height depth buffer"""
+        size, mips, smax = C.c_uint32(), C.c_uint32(), C.c_float()
+        f = (C.c_float * 4)()
+        self._check(self._fn("hiz_info")(C.c_uint32(width), C.c_uint32(height), C.byref(size), C.byref(mips), f, C.byref(smax)), "hiz_info")
+        return size.value, mips.value, np.array(list(f), np.float32), float(smax.value)
+
     def set_driver_standin(self, mode: int):
         self._check(self._fn("set_driver_standin")(self._ctx, C.c_uint32(mode)), "set_driver_standin")
 

@@ -100,6 +100,9 @@ struct tc_context
   void *tblVertices = nullptr, *tblTriangles = nullptr, *tblEntries = nullptr, *tblTemplAddr = nullptr, *tblTemplSize = nullptr;
   // hiz
   float* hiz = nullptr;
+  size_t hizFloats = 0;         // capacity of `hiz`
+  float* hizDepth = nullptr;    // staging copy of a host depth image (tc_update_hiz)
+  size_t hizDepthFloats = 0;
 
   void*  flushBuf   = nullptr;
   size_t flushBytes = 0;
@@ -509,6 +512,7 @@ TC_API void tc_destroy(tc_context* c)
   dfree(c->tblVerticesF); dfree(c->tblSlots); dfree(c->tblSlotBase);
   dfree(c->tblVertices); dfree(c->tblTriangles); dfree(c->tblEntries); dfree(c->tblTemplAddr); dfree(c->tblTemplSize);
   dfree(c->hiz);
+  dfree(c->hizDepth);
   dfree(c->flushBuf);
   if(c->evValid)
     for(int i = 0; i <= TC_STAGE_COUNT; i++)
@@ -748,14 +752,156 @@ TC_API int tc_set_hiz(tc_context* c, const float* mips, uint32_t size, uint32_t 
   }
   dfree(c->hiz);
   c->hiz = nullptr;
+  c->hizFloats = 0;
   int rc = dalloc(c->hiz, total * 4);
   if(rc)
     return rc;
+  c->hizFloats = total;
   CUDA_TRY(cudaMemcpy(c->hiz, mips, total * 4, cudaMemcpyHostToDevice));
   c->params.hizSize = size;
   c->params.hizMips = mipLevels;
   drop_graph(c);
   fill_params(c);
+  return TC_OK;
+}
+
+// NVHizVK::TextureInfo of the far pyramid for a width x height depth buffer (setupUpdateInfos, nvhiz_vk.cpp:278-309, hizFarLevel 0)
+TC_API int tc_hiz_info(uint32_t width, uint32_t height, uint32_t* size, uint32_t* mipLevels, float factors[4], float* sizeMax)
+{
+  if(width < 2 || height < 2)
+    return fail(TC_ERR_INVALID_ARG, "depth image must be at least 2x2");
+  const uint32_t divisor = 2;
+  uint32_t dim = std::max(width, height) / divisor, hiz = 1, mips = 1;
+  while(hiz < dim)
+  {
+    hiz *= 2;
+    mips++;
+  }
+  const uint32_t usedW = width / divisor, usedH = height / divisor;
+  if(size) *size = hiz;
+  if(mipLevels) *mipLevels = mips;
+  if(factors)
+  {  // TextureInfo::getShaderFactors (nvhiz_vk.cpp:29-35)
+    factors[0] = float(usedW) / float(hiz);
+    factors[1] = float(usedH) / float(hiz);
+    factors[2] = float(usedW - 2) / float(hiz);
+    factors[3] = float(usedH - 2) / float(hiz);
+  }
+  if(sizeMax) *sizeMax = float(hiz);
+  return TC_OK;
+}
+
+// NVHizVK::cmdUpdateHiz (nvhiz_vk.cpp:484-594): far pyramid of a depth image, three levels per dispatch
+TC_API int tc_update_hiz(tc_context* c, const float* depth, uint32_t width, uint32_t height, uint32_t depthIsDevice)
+{
+  if(!c || !depth)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  uint32_t size = 0, mips = 0;
+  int rc = tc_hiz_info(width, height, &size, &mips, nullptr, nullptr);
+  if(rc)
+    return rc;
+  CUDA_TRY(cudaSetDevice(c->device));
+  size_t total = 0;
+  std::vector<size_t> levelOffset(mips);
+  for(uint32_t l = 0; l < mips; l++)
+  {
+    levelOffset[l] = total;
+    size_t s = std::max(1u, size >> l);
+    total += s * s;
+  }
+  if(c->hizFloats != total || c->params.hizSize != size || c->params.hizMips != mips)
+  {  // new shape: texels the update never writes read as zero
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    dfree(c->hiz);
+    c->hiz = nullptr;
+    c->hizFloats = 0;
+    if((rc = dalloc(c->hiz, total * 4)))
+      return rc;
+    c->hizFloats = total;
+    CUDA_TRY(cudaMemset(c->hiz, 0, total * 4));
+    c->params.hizSize = size;
+    c->params.hizMips = mips;
+    drop_graph(c);
+    fill_params(c);
+  }
+  const float* src = depth;
+  if(!depthIsDevice)
+  {
+    const size_t n = size_t(width) * height;
+    if(c->hizDepthFloats < n)
+    {
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      dfree(c->hizDepth);
+      c->hizDepth = nullptr;
+      c->hizDepthFloats = 0;
+      if((rc = dalloc(c->hizDepth, n * 4)))
+        return rc;
+      c->hizDepthFloats = n;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->hizDepth, depth, n * 4, cudaMemcpyHostToDevice, c->stream));
+    src = c->hizDepth;
+  }
+  const uint32_t hizLevels = 3, align = 8;
+  uint32_t inputW = width, inputH = height;
+  uint32_t subW = (inputW + 1) / 2, subH = (inputH + 1) / 2;
+  for(uint32_t i = 0; i < mips; i += hizLevels)
+  {
+    const uint32_t inputLod = i == 0 ? 0 : i - 1;
+    subW = ((subW + align - 1) / align) * align;
+    subH = ((subH + align - 1) / align) * align;
+    tc::HizPass q{};
+    if(i == 0)
+    {
+      q.src      = src;
+      q.srcPitch = width;
+      q.srcW     = width;
+      q.srcH     = height;
+    }
+    else
+    {
+      q.src      = c->hiz + levelOffset[inputLod];
+      q.srcPitch = std::max(1u, size >> inputLod);
+      q.srcW = q.srcH = q.srcPitch;
+    }
+    q.clampX     = int32_t(inputW) - 2;
+    q.clampY     = int32_t(inputH) - 2;
+    q.vectorRows = (q.srcPitch % 4 == 0 && (reinterpret_cast<uintptr_t>(q.src) & 15) == 0) ? 1u : 0u;
+    for(uint32_t l = 0; l < hizLevels; l++)
+    {
+      const bool active = l + i < mips;
+      q.dst[l]     = active ? c->hiz + levelOffset[i + l] : nullptr;
+      q.dstSize[l] = active ? std::max(1u, size >> (i + l)) : 0;
+    }
+    q.outW = ((subW + 7) / 8) * 8;
+    q.outH = ((subH + 7) / 8) * 8;
+    tc::launch_hiz_update(q, c->stream);
+    for(uint32_t l = 0; l < hizLevels; l++)
+    {
+      subW = (subW + 1) / 2;
+      subH = (subH + 1) / 2;
+    }
+    subW   = subW ? subW : 1;
+    subH   = subH ? subH : 1;
+    inputW = subW * 2;
+    inputH = subH * 2;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return TC_OK;
+}
+
+TC_API int tc_get_hiz(tc_context* c, float* out, size_t capacityFloats, uint32_t* size, uint32_t* mipLevels)
+{
+  if(!c)
+    return fail(TC_ERR_INVALID_ARG, "null context");
+  if(size) *size = c->params.hizSize;
+  if(mipLevels) *mipLevels = c->params.hizMips;
+  if(!out)
+    return TC_OK;
+  if(!c->hiz || capacityFloats < c->hizFloats)
+    return fail(TC_ERR_INVALID_ARG, "no pyramid or output too small");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(out, c->hiz, c->hizFloats * 4, cudaMemcpyDeviceToHost));
   return TC_OK;
 }
 

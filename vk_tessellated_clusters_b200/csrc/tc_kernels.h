@@ -16,6 +16,19 @@ struct Params;
 #endif
 constexpr uint32_t kInstantiateSlot = TC_INST_SLOT;
 
+// one dispatch of nvhiz-update: three consecutive far-pyramid levels from `src`
+struct HizPass
+{
+  const float* src;
+  uint32_t     srcPitch;        // floats per source row
+  uint32_t     srcW, srcH;      // real extent of the source; fetches outside read 0 (robust texelFetch; only reached for odd sizes just above 2*2^k)
+  int32_t      clampX, clampY;  // srcSize.zw = source extent - 2 (nvhiz_vk.cpp:567-570)
+  uint32_t     vectorRows;      // source rows can be read with aligned 128-bit loads
+  float*       dst[3];          // levels writeLod .. writeLod+2 (nullptr: level not active)
+  uint32_t     dstSize[3];      // their (square) sizes
+  uint32_t     outW, outH;      // dispatch extent in texels of level writeLod (multiples of 8)
+};
+
 struct KernelOccupancy
 {
   int classify = 1, split = 1, instantiate = 1;
@@ -36,6 +49,7 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
 void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32_t pass, bool lastPass, uint32_t grid, cudaStream_t s);
 void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s);
 void launch_blas(const Params& p, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s);
+void launch_hiz_update(const HizPass& q, cudaStream_t s);
 void launch_shard_counts(const Params& p, tc_shard_counts* out, cudaStream_t s);
 void launch_flush_l2(void* buf, size_t bytes, cudaStream_t s);
 
