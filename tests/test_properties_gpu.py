@@ -95,3 +95,32 @@ def test_instance_grid_with_culling_properties(table):
     if int(sb["splitWriteCounter"]) <= cfg.max_split_triangles and int(rb["numGenVertices"]) <= cfg.max_generated_vertices:
         _check_properties(gpu, table, cfg)
     gpu.close()
+
+
+def test_shard_summary_record_matches_readback(table):
+    """tc_shard_counts (the 32-byte record each rank contributes to the allgather) is written on the device by the last
+    CTA of k_instantiate: it must agree with the frame's own counters."""
+    import ctypes as C
+
+    from tests.scene_cases import case
+    from vk_tessellated_clusters_b200 import sharding
+
+    scene, fcs, cfg, _ = case("mini")
+    gpu = api.TessClusters(cfg)
+    gpu.set_tess_table(table)
+    gpu.set_scene(scene)
+    gpu.frame(fcs)
+    rb, sb = gpu.readback()
+    rt = C.CDLL("libcudart.so.12")
+    host = np.zeros(sharding.SHARD_WORDS, np.uint32)
+    assert rt.cudaMemcpy(host.ctypes.data_as(C.c_void_p), C.c_void_p(gpu.device_shard_counts()), C.c_size_t(host.nbytes), C.c_int(2)) == 0
+    rec = sharding.unpack_shard_counts(host)
+    assert rec["tempInstantiateCounter"] == int(sb["tempInstantiateCounter"])
+    assert rec["transBuildCounter"] == int(sb["transBuildCounter"])
+    assert rec["genVertexCounter"] == int(sb["genVertexCounter"])
+    assert rec["blasClusterCounter"] == int(sb["tempInstantiateCounter"]) + int(sb["transBuildCounter"])
+    assert rec["genClusterDataCounter"] == int(sb["genClusterDataCounter"])
+    assert rec["numTotalTriangles"] == int(rb["numTotalTriangles"])
+    assert rec["numInstances"] == len(scene.instances)
+    assert rec["transBuildCounter"] > 0 and rec["tempInstantiateCounter"] > 0
+    gpu.close()

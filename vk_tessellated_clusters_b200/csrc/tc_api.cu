@@ -266,6 +266,7 @@ void fill_params(tc_context* c)
   p.segLo              = c->segLo;
   p.rankBase           = c->rankBase;
   p.shardBase          = c->dShardBase;
+  p.shardCounts        = c->dShardCounts;
   p.globalRanges       = c->globalRanges;
 }
 
@@ -347,8 +348,7 @@ int enqueue_build(tc_context* c)
     tc::launch_instantiate(p, c->dEpoch, grid, s);
     launches += 1;
   }
-  tc::launch_shard_counts(p, c->dShardCounts, s);  // summary record for the multi-GPU allgather
-  c->lastLaunches = launches + 1;
+  c->lastLaunches = launches;  // (the shard summary for the multi-GPU allgather is written by k_instantiate's last CTA)
   CUDA_TRY(cudaGetLastError());
   return TC_OK;
 }

@@ -97,6 +97,7 @@ struct Params
   uint32_t* rankBase;  // [TC_MAX_SEGMENTS+1][numInstances]
   const uint32_t* shardBase;  // {globalBlasClusterBase, globalInstanceBase}
   tc_global_blas_range* globalRanges;  // [numInstances]
+  tc_shard_counts*      shardCounts;   // summary record for the multi-GPU allgather, written by the last CTA of k_instantiate
 };
 
 __device__ __forceinline__ bool flag_pn(const Params& p) { return p.flags & TC_FLAG_PN_DISPLACEMENT; }

@@ -2100,6 +2100,15 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
         b->dispatchBlasTransInsert.gridY = 1;
         b->dispatchBlasTransInsert.gridZ = 1;
       }
+      // shard summary for the multi-GPU allgather; all CTAs' atomics are visible after the fence above
+      tc_shard_counts* sc = p.shardCounts;
+      sc->tempInstantiateCounter = b->tempInstantiateCounter;
+      sc->transBuildCounter      = b->transBuildCounter;
+      sc->genVertexCounter       = b->genVertexCounter;
+      sc->blasClusterCounter     = b->tempInstantiateCounter + (transient ? b->transBuildCounter : 0);
+      sc->genClusterDataCounter  = b->genClusterDataCounter;
+      sc->numTotalTriangles      = *(volatile uint32_t*)&p.readback->numTotalTriangles;
+      sc->numInstances           = p.numInstances;
     }
   }
 }
@@ -2312,19 +2321,6 @@ __global__ void __launch_bounds__(256) k_blas_insert(Params p)
     atomicAdd(reinterpret_cast<unsigned long long*>(&p.readback->numGenActualDatas), blockSizes);
 }
 
-// shard summary for the multi-GPU allgather
-__global__ void k_shard_counts(Params p, tc_shard_counts* out)
-{
-  pdl_prologue();
-  out->tempInstantiateCounter = p.build->tempInstantiateCounter;
-  out->transBuildCounter      = p.build->transBuildCounter;
-  out->genVertexCounter       = p.build->genVertexCounter;
-  out->blasClusterCounter     = p.build->tempInstantiateCounter + (flag_transient(p) ? p.build->transBuildCounter : 0);
-  out->genClusterDataCounter  = p.build->genClusterDataCounter;
-  out->numTotalTriangles      = p.readback->numTotalTriangles;
-  out->numInstances           = p.numInstances;
-}
-
 __global__ void k_flush_l2(float4* buf, size_t n)
 {
   for(size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
@@ -2432,7 +2428,6 @@ void launch_hiz_update(const HizPass& q, cudaStream_t s)
   launch_pdl(k_hiz_update, grid, block, 0, s, q);
 }
 
-void launch_shard_counts(const Params& p, tc_shard_counts* out, cudaStream_t s) { launch_pdl(k_shard_counts, 1, 1, 0, s, p, out); }
 void launch_flush_l2(void* buf, size_t bytes, cudaStream_t s) { k_flush_l2<<<1184, 256, 0, s>>>(reinterpret_cast<float4*>(buf), bytes / 16); }
 
 }  // namespace tc

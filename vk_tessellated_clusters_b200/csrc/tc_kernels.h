@@ -50,7 +50,6 @@ void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32
 void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s);
 void launch_blas(const Params& p, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s);
 void launch_hiz_update(const HizPass& q, cudaStream_t s);
-void launch_shard_counts(const Params& p, tc_shard_counts* out, cudaStream_t s);
 void launch_flush_l2(void* buf, size_t bytes, cudaStream_t s);
 
 }  // namespace tc

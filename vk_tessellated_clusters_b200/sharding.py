@@ -15,6 +15,13 @@ import numpy as np
 SHARD_WORDS = 8  # tc_shard_counts as 8 x u32: temp, trans, genVertex, blasClusters, dataLo, dataHi, totalTris, numInstances
 
 
+def unpack_shard_counts(words) -> dict:
+    """One tc_shard_counts record (8 x u32, include/tess_clusters.h) as a dict."""
+    w = [int(x) for x in np.asarray(words, dtype=np.uint32).reshape(SHARD_WORDS)]
+    return {"tempInstantiateCounter": w[0], "transBuildCounter": w[1], "genVertexCounter": w[2], "blasClusterCounter": w[3],
+            "genClusterDataCounter": w[4] | (w[5] << 32), "numTotalTriangles": w[6], "numInstances": w[7]}
+
+
 def partition_instances(cluster_counts, world_size: int):
     """Contiguous instance ranges balanced by cluster count.  Returns list of (first, last_exclusive) per rank."""
     cluster_counts = np.asarray(cluster_counts, dtype=np.int64)
