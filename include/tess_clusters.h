@@ -139,6 +139,45 @@ TC_API int tc_get_hiz(tc_context* ctx, float* out, size_t capacityFloats, uint32
  * library fills tempClusterSizes/transClusterSizes with each CLAS' reserved size before the insert step. */
 TC_API int tc_set_driver_standin(tc_context* ctx, uint32_t mode);
 
+/* ---- explicit triangles of the instantiated parts + hit-side decode ---------------------
+ * The path's outputs are consumed by the CLAS driver and, at hit time, by the closest-hit shader, which turns
+ * (gl_InstanceID, gl_ClusterIDNV, gl_PrimitiveID, barycentrics) back into a base triangle and base barycentrics
+ * using the tags the path wrote (shaders/render_raytrace_clusters.rchit.glsl:131-236).  These two calls make that
+ * contract checkable without the driver:
+ *  - tc_emit_part_triangles lists, for every successfully instantiated part of the last frame in instantiate
+ *    order, its triangles: three indices into genVertices per triangle (pattern triangle of the config, second and
+ *    third index swapped for flipped configs: tess_getConfigTriangleVertices, shaders/tessellation.glsl:162-173,
+ *    the same triples the CLAS template holds) and a tag pair (clusterID word of the instantiate record,
+ *    primitive id) - exactly what a hit on that triangle reports.
+ *  - tc_resolve_hits runs the shader's decode on a batch of hits, for all four cluster modes (full cluster,
+ *    template-instantiated part, 1X subset cluster, 2X mini batch).
+ * Pointers are host pointers unless TC_HIT_DEVICE_POINTERS is set.  TC_HIT_REFERENCE_2X_QUIRK reproduces the
+ * reference's `(packed >> 8) & 4` (rchit:151: always 0, the writer stored i << 8 with i in 0..3,
+ * cluster_classify.comp.glsl:892); without it the mask is 3. */
+typedef struct tc_hit {
+  uint32_t instanceID;      /* gl_InstanceID */
+  uint32_t clusterID;       /* gl_ClusterIDNV: mode in the top two bits */
+  uint32_t primitiveID;     /* gl_PrimitiveID */
+  float    barycentrics[2]; /* hitAttributeEXT */
+} tc_hit;
+typedef struct tc_hit_base {
+  uint32_t mode;            /* clusterID >> 30 (TC_RT_CLUSTER_MODE_*) */
+  uint32_t clusterID;       /* cluster of the instance */
+  uint32_t triangleID;      /* base triangle inside the cluster */
+  uint32_t subTriangleID;   /* triangle of the tessellation pattern */
+  uint32_t cfg;             /* tessellation config, 0 when the hit is not on a tessellated triangle */
+  uint32_t baseIndices[3];  /* vertices of the base triangle in the instance's vertex arrays */
+  uint32_t partID;          /* the shader's visualisation id (rchit:203-226, visualize != TRIANGLES) */
+  float    baryWeightBase[3]; /* hit point in base-triangle barycentrics */
+} tc_hit_base;
+#define TC_HIT_DEVICE_POINTERS 1u
+#define TC_HIT_REFERENCE_2X_QUIRK 2u
+TC_API int tc_resolve_hits(tc_context* ctx, const tc_hit* hits, uint32_t count, tc_hit_base* out, uint32_t flags);
+/* indices: 3 x u32 per triangle, tags: 2 x u32 per triangle; either may be NULL (count only).  numTriangles
+ * receives the total even when it exceeds the capacity (nothing is written beyond it). */
+TC_API int tc_emit_part_triangles(tc_context* ctx, uint32_t* indices, uint32_t* tags, uint64_t capacityTriangles,
+                                  uint64_t* numTriangles, uint32_t flags);
+
 /* ---- Renderer::render ---------------------------------------------------------------------------------
  * frameConstants points at two consecutive FrameConstants (current, last) `strideBytes` apart
  * (sizeof(shaderio::FrameConstants) for a reference caller, sizeof(tc_FrameConstants) otherwise).

@@ -1395,6 +1395,122 @@ ORC_API int orc_set_hiz(orc_context* c, const float* mips, uint32_t size, uint32
   return TC_OK;
 }
 
+// ---- hit-side decode + explicit part triangles ---------------------------------------------
+// main() of shaders/render_raytrace_clusters.rchit.glsl:131-236 (TESS_ACTIVE, 1X and 2X transient builds on,
+// view.visualize != VISUALIZE_TRIANGLES), one hit at a time
+ORC_API int orc_resolve_hits(orc_context* c, const tc_hit* hits, uint32_t count, tc_hit_base* out, uint32_t flags)
+{
+  if(!c || (count && (!hits || !out)))
+    return TC_ERR_INVALID_ARG;
+  const uint8_t*  map8  = reinterpret_cast<const uint8_t*>(c->partTriangles.data());   // transTriMappings aliases partTriangles
+  const uint16_t* map16 = reinterpret_cast<const uint16_t*>(c->partTriangles.data());
+  for(uint32_t i = 0; i < count; i++)
+  {
+    const tc_hit& h = hits[i];
+    uint32_t clusterID = h.clusterID, triangleID = h.primitiveID;  // :134-135
+    const uint32_t mode = clusterID >> 30;                          // :138
+    const bool isSpecial = mode != TC_RT_CLUSTER_MODE_FULL_CLUSTER;
+    bool isTessTriangle  = mode == TC_RT_CLUSTER_MODE_SINGLE_TESSELLATED;
+    clusterID &= 0x3FFFFFFFu;                                       // :145
+    tc_TessTriangleInfo tessInfo{};
+    uint32_t partID = 0, subTriangleID = triangleID, cfg = 0;       // :148-150
+    if(isSpecial)
+    {
+      tessInfo = c->partTriangles[clusterID];                       // :153
+      if(mode == TC_RT_CLUSTER_MODE_2X_BATCHED_TESSELLATED)
+      {
+        const uint32_t packedTriangleID = map16[size_t(clusterID) * (sizeof(tc_TessTriangleInfo) / 2) + sizeof(tc_ClusterInfo) / 2 + triangleID];  // :159
+        triangleID    = packedTriangleID & 0xff;                    // :161
+        subTriangleID = (packedTriangleID >> 8) & ((flags & TC_HIT_REFERENCE_2X_QUIRK) ? 4u : 3u);  // :163 (the reference masks with 4)
+        tessInfo.subTriangle.vtxEncoded[0] = 0u;                               // tess_encodeBarycentrics(0,0)            :165-167
+        tessInfo.subTriangle.vtxEncoded[1] = TC_TESSTABLE_COORD_MAX;           // (COORD_MAX, 0)
+        tessInfo.subTriangle.vtxEncoded[2] = TC_TESSTABLE_COORD_MAX << 16;     // (0, COORD_MAX)
+        const uint32_t intFactors[3] = {1 + ((packedTriangleID >> 12) & 1), 1 + ((packedTriangleID >> 13) & 1), 1 + (packedTriangleID >> 14)};  // :169
+        cfg = tess_getConfig(intFactors, tessInfo.subTriangle.vtxEncoded);     // :171
+        isTessTriangle = true;
+      }
+      else if(mode == TC_RT_CLUSTER_MODE_1X_SUBSET_CLUSTER)
+        triangleID = map8[size_t(clusterID) * sizeof(tc_TessTriangleInfo) + sizeof(tc_ClusterInfo) + triangleID];  // :181
+      else
+      {
+        triangleID = tessInfo.subTriangle.triangleID_config & 0xFFFF;  // :186-187
+        cfg        = tessInfo.subTriangle.triangleID_config >> 16;
+      }
+      clusterID = tessInfo.cluster.clusterID;                       // :189
+    }
+    const tc_RenderInstance& inst = c->instances[h.instanceID];
+    const GeometryHost&      g    = c->geoms[inst.geometryID];
+    const tc_Cluster&        cl   = g.clusters[clusterID];          // :194
+    tc_hit_base r{};
+    for(int k = 0; k < 3; k++)
+      r.baseIndices[k] = uint32_t(g.localTriangles[size_t(triangleID) * 3 + k + cl.firstLocalTriangle]) + cl.firstLocalVertex;  // :201-204
+    const V3 baryWeight = {(1.0f - h.barycentrics[0]) - h.barycentrics[1], h.barycentrics[0], h.barycentrics[1]};  // :206
+    V3 baryWeightBase = baryWeight;
+    if(isTessTriangle)
+    {
+      V3 baseBarycentrics[3];
+      partID = 0;
+      for(uint32_t v = 0; v < 3; v++)
+      {
+        const uint32_t vtxEncoded = tessInfo.subTriangle.vtxEncoded[v];
+        partID ^= (vtxEncoded >> 20) | ((vtxEncoded >> 4) & 0xFFF);  // :216
+        baseBarycentrics[v] = tess_decodeBarycentrics(vtxEncoded);
+      }
+      uint32_t tessTriIndices[3];
+      tess_getConfigTriangleVertices(*c, cfg, subTriangleID, tessTriIndices);  // :220
+      const V3 b0 = tess_getConfigVertexBarycentrics(*c, cfg, tessTriIndices[0]), b1 = tess_getConfigVertexBarycentrics(*c, cfg, tessTriIndices[1]),
+               b2 = tess_getConfigVertexBarycentrics(*c, cfg, tessTriIndices[2]);
+      const V3 nb = {(b0.x * baryWeight.x + b1.x * baryWeight.y) + b2.x * baryWeight.z, (b0.y * baryWeight.x + b1.y * baryWeight.y) + b2.y * baryWeight.z,
+                     (b0.z * baryWeight.x + b1.z * baryWeight.y) + b2.z * baryWeight.z};  // :223-226
+      baryWeightBase = {(baseBarycentrics[0].x * nb.x + baseBarycentrics[1].x * nb.y) + baseBarycentrics[2].x * nb.z,
+                        (baseBarycentrics[0].y * nb.x + baseBarycentrics[1].y * nb.y) + baseBarycentrics[2].y * nb.z,
+                        (baseBarycentrics[0].z * nb.x + baseBarycentrics[1].z * nb.y) + baseBarycentrics[2].z * nb.z};  // :229-232
+      partID = triangleID | ((partID | 1) << 8);  // :236
+    }
+    r.mode = mode; r.clusterID = clusterID; r.triangleID = triangleID; r.subTriangleID = subTriangleID; r.cfg = cfg; r.partID = partID;
+    r.baryWeightBase[0] = baryWeightBase.x; r.baryWeightBase[1] = baryWeightBase.y; r.baryWeightBase[2] = baryWeightBase.z;
+    out[i] = r;
+  }
+  return TC_OK;
+}
+
+// every triangle of every template-instantiated part, in instantiate-record order (the index triples a CLAS template
+// holds: tess_getConfigTriangleVertices) with the (clusterID word, primitive id) pair a hit on it reports
+ORC_API int orc_emit_part_triangles(orc_context* c, uint32_t* indices, uint32_t* tags, uint64_t capacityTriangles, uint64_t* numTriangles, uint32_t /*flags*/)
+{
+  if(!c)
+    return TC_ERR_INVALID_ARG;
+  uint64_t n = 0;
+  for(uint32_t j = 0; j < c->build.tempInstantiateCounter; j++)
+  {
+    const tc_TemplateInstantiateInfo& r = c->tempInstantiations[j];
+    if((r.clusterIdOffset >> 30) != TC_RT_CLUSTER_MODE_SINGLE_TESSELLATED)
+      continue;
+    const uint32_t partIndex    = r.clusterIdOffset & 0x3FFFFFFFu;
+    const uint32_t cfg          = c->partTriangles[partIndex].subTriangle.triangleID_config >> 16;
+    const uint32_t vertexOffset = uint32_t((r.vertexBufferAddress - c->build.genVertices) / 12);
+    const uint32_t numTris      = tess_getConfigTriangleCount(*c, cfg);
+    for(uint32_t tri = 0; tri < numTris; tri++, n++)
+    {
+      if(n >= capacityTriangles)
+        continue;
+      uint32_t v[3];
+      tess_getConfigTriangleVertices(*c, cfg, tri, v);
+      if(indices)
+      {
+        indices[n * 3 + 0] = vertexOffset + v[0]; indices[n * 3 + 1] = vertexOffset + v[1]; indices[n * 3 + 2] = vertexOffset + v[2];
+      }
+      if(tags)
+      {
+        tags[n * 2 + 0] = r.clusterIdOffset; tags[n * 2 + 1] = tri;
+      }
+    }
+  }
+  if(numTriangles)
+    *numTriangles = n;
+  return TC_OK;
+}
+
 // ---- far-HiZ pyramid builder -------------------------------------------------------------------------------
 // NVHizVK::setupUpdateInfos + TextureInfo::getShaderFactors (src/nvhiz_vk.cpp:29-40, :278-309), hizFarLevel 0
 ORC_API int orc_hiz_info(uint32_t width, uint32_t height, uint32_t* size, uint32_t* mipLevels, float factors[4], float* sizeMax)

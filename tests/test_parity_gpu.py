@@ -191,3 +191,53 @@ def test_culling_frame_with_built_hiz_matches_oracle(table, oracle_lib):
     assert gpu.buffer("blasClusterAddresses", n, sb).tobytes() == orc.buffer("blasClusterAddresses", n).tobytes()
     gpu.close()
     orc.close()
+
+
+# ---- explicit part triangles + hit-side decode, CUDA vs oracle, bit-exact ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["plane", "split", "deep_split", "mini", "icosphere", "culling", "overflow_vertices", "linear_no_transient"])
+def test_part_triangles_and_hit_decode_bit_exact(name, table, oracle_lib):
+    scene, fcs, cfg, hiz = case(name)
+    gpu, orc = make_pair(scene, table, cfg, hiz)
+    try:
+        gpu.frame(fcs)
+        orc.frame(fcs)
+        rb, sb = gpu.readback()
+        gi, gt, gn = gpu.emit_part_triangles()
+        oi, ot, on = orc.emit_part_triangles()
+        assert gn == on and gi.tobytes() == oi.tobytes() and gt.tobytes() == ot.tobytes()
+        # a second call (fresh look-back epoch) and a truncated one give the same prefix
+        gi2, gt2, gn2 = gpu.emit_part_triangles(capacity=max(1, gn // 3))
+        assert gn2 == gn and gi2.tobytes() == gi[: gi2.shape[0]].tobytes() and gt2.tobytes() == gt[: gt2.shape[0]].tobytes()
+        # hits: every 7th part triangle + every primitive of every transient build + one per full cluster
+        rng = np.random.default_rng(11)
+        hits = []
+        if gn:
+            sel = np.arange(0, gn, 7)
+            h = np.zeros(sel.shape[0], api.HIT_DTYPE)
+            part = gpu.buffer("partTriangles", None, sb)[gt[sel, 0] & 0x3FFFFFFF]
+            h["instanceID"], h["clusterID"], h["primitiveID"] = part["instanceID"], gt[sel, 0], gt[sel, 1]
+            hits.append(h)
+        n_trans = int(sb["transBuildCounter"])
+        if n_trans:
+            tb, ti = gpu.buffer("transBuilds", n_trans, sb), gpu.buffer("transInstanceIDs", n_trans, sb)
+            counts = (tb["packed"] & 0x1FF).astype(np.int64)
+            h = np.zeros(int(counts.sum()), api.HIT_DTYPE)
+            h["instanceID"], h["clusterID"] = np.repeat(ti, counts), np.repeat(tb["clusterID"], counts)
+            h["primitiveID"] = np.concatenate([np.arange(c) for c in counts]) if counts.sum() else []
+            hits.append(h)
+        n_temp = int(sb["tempInstantiateCounter"])
+        if n_temp:
+            recs, ids = gpu.buffer("tempInstantiations", n_temp, sb), gpu.buffer("tempInstanceIDs", n_temp, sb)
+            full = (recs["clusterIdOffset"] >> 30) == 0
+            h = np.zeros(int(full.sum()), api.HIT_DTYPE)
+            h["instanceID"], h["clusterID"], h["primitiveID"] = ids[full], recs["clusterIdOffset"][full], 0
+            hits.append(h)
+        hits = np.concatenate(hits)
+        b = rng.dirichlet((1.0, 1.0, 1.0), size=hits.shape[0]).astype(np.float32)
+        hits["barycentrics"] = b[:, 1:]
+        for quirk in (False, True):
+            assert gpu.resolve_hits(hits, reference_quirk=quirk).tobytes() == orc.resolve_hits(hits, reference_quirk=quirk).tobytes()
+    finally:
+        gpu.close()
+        orc.close()

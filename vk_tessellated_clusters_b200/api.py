@@ -177,6 +177,12 @@ class TessError(RuntimeError):
     pass
 
 
+HIT_DTYPE = np.dtype([("instanceID", "<u4"), ("clusterID", "<u4"), ("primitiveID", "<u4"), ("barycentrics", "<f4", 2)])
+HIT_BASE_DTYPE = np.dtype([("mode", "<u4"), ("clusterID", "<u4"), ("triangleID", "<u4"), ("subTriangleID", "<u4"), ("cfg", "<u4"), ("baseIndices", "<u4", 3),
+                           ("partID", "<u4"), ("baryWeightBase", "<f4", 3)])
+assert HIT_DTYPE.itemsize == 20 and HIT_BASE_DTYPE.itemsize == 48
+
+
 class Binding:
     """Drives any library exporting the tc_* call set under a symbol prefix.  The product uses ``tc_``."""
 
@@ -282,6 +288,25 @@ class Binding:
         f = (C.c_float * 4)()
         self._check(self._fn("hiz_info")(C.c_uint32(width), C.c_uint32(height), C.byref(size), C.byref(mips), f, C.byref(smax)), "hiz_info")
         return size.value, mips.value, np.array(list(f), np.float32), float(smax.value)
+
+    def resolve_hits(self, hits: np.ndarray, reference_quirk: bool = False) -> np.ndarray:
+        """rchit decode of a batch of hits (HIT_DTYPE) -> HIT_BASE_DTYPE records."""
+        h = np.ascontiguousarray(hits, dtype=HIT_DTYPE)
+        out = np.zeros(h.shape[0], dtype=HIT_BASE_DTYPE)
+        self._check(self._fn("resolve_hits")(self._ctx, _ptr(h), C.c_uint32(h.shape[0]), _ptr(out), C.c_uint32(2 if reference_quirk else 0)), "resolve_hits")
+        return out
+
+    def emit_part_triangles(self, capacity: int | None = None):
+        """-> (indices [n,3] u32 into genVertices, tags [n,2] u32 (clusterID word, primitive id), total count)"""
+        total = C.c_uint64()
+        if capacity is None:
+            self._check(self._fn("emit_part_triangles")(self._ctx, None, None, C.c_uint64(0), C.byref(total), C.c_uint32(0)), "emit_part_triangles")
+            capacity = total.value
+        idx = np.zeros((max(capacity, 1), 3), np.uint32)
+        tags = np.zeros((max(capacity, 1), 2), np.uint32)
+        self._check(self._fn("emit_part_triangles")(self._ctx, _ptr(idx), _ptr(tags), C.c_uint64(capacity), C.byref(total), C.c_uint32(0)), "emit_part_triangles")
+        n = min(capacity, total.value)
+        return idx[:n], tags[:n], total.value
 
     def set_driver_standin(self, mode: int):
         self._check(self._fn("set_driver_standin")(self._ctx, C.c_uint32(mode)), "set_driver_standin")

@@ -74,6 +74,8 @@ struct tc_context
   FrameStaging*     dFrame     = nullptr;
   FrameStaging*     hFrame     = nullptr;  // pinned
   tc_shard_counts*  dShardCounts = nullptr;
+  uint32_t*         dEmitState = nullptr;  // tc_emit_part_triangles: ticket, pad, total (u64)
+  uint32_t          emitCalls = 0;
   uint32_t*         dShardBase   = nullptr;
 
   // path buffers
@@ -437,6 +439,7 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   TRY_RC(dalloc(c->dEpoch, 16));
   TRY_RC(dalloc(c->dFrame, sizeof(FrameStaging)));
   TRY_RC(dalloc(c->dShardCounts, sizeof(tc_shard_counts)));
+  TRY_RC(dalloc(c->dEmitState, 16));
   TRY_RC(dalloc(c->dShardBase, 16));
   TRY_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->hFrame), sizeof(FrameStaging)));
   memset(c->hFrame, 0, sizeof(FrameStaging));
@@ -500,7 +503,7 @@ TC_API void tc_destroy(tc_context* c)
   drop_graph(c);
   free_scene(c);
   dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dFrame);
-  dfree(c->dShardCounts); dfree(c->dShardBase);
+  dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState);
   if(c->hFrame)
     cudaFreeHost(c->hFrame);
   dfree(c->visibleClusters); dfree(c->splitTriangles); dfree(c->partTriangles); dfree(c->genVertices);
@@ -1036,6 +1039,100 @@ TC_API int tc_readback(tc_context* c, tc_Readback* readback, tc_SceneBuilding* b
   if(building)
     CUDA_TRY(cudaMemcpyAsync(building, c->dBuild, sizeof(tc_SceneBuilding), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return TC_OK;
+}
+
+// render_raytrace_clusters.rchit.glsl:131-236 on a batch of hits
+TC_API int tc_resolve_hits(tc_context* c, const tc_hit* hits, uint32_t count, tc_hit_base* out, uint32_t flags)
+{
+  int rc = check_ready(c);
+  if(rc)
+    return rc;
+  if(count == 0)
+    return TC_OK;
+  if(!hits || !out)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const bool quirk = (flags & TC_HIT_REFERENCE_2X_QUIRK) != 0;
+  if(flags & TC_HIT_DEVICE_POINTERS)
+  {
+    tc::launch_resolve_hits(c->params, hits, count, out, quirk, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    return TC_OK;
+  }
+  tc_hit*      dHits = nullptr;
+  tc_hit_base* dOut  = nullptr;
+  if((rc = dalloc(dHits, size_t(count) * sizeof(tc_hit))) || (rc = dalloc(dOut, size_t(count) * sizeof(tc_hit_base))))
+  {
+    dfree(dHits);
+    return rc;
+  }
+  cudaError_t e = cudaMemcpyAsync(dHits, hits, size_t(count) * sizeof(tc_hit), cudaMemcpyHostToDevice, c->stream);
+  if(e == cudaSuccess)
+  {
+    tc::launch_resolve_hits(c->params, dHits, count, dOut, quirk, c->stream);
+    e = cudaMemcpyAsync(out, dOut, size_t(count) * sizeof(tc_hit_base), cudaMemcpyDeviceToHost, c->stream);
+  }
+  if(e == cudaSuccess)
+    e = cudaStreamSynchronize(c->stream);
+  dfree(dHits);
+  dfree(dOut);
+  if(e != cudaSuccess)
+    return fail(TC_ERR_CUDA, cudaGetErrorString(e));
+  return TC_OK;
+}
+
+TC_API int tc_emit_part_triangles(tc_context* c, uint32_t* indices, uint32_t* tags, uint64_t capacityTriangles, uint64_t* numTriangles, uint32_t flags)
+{
+  int rc = check_ready(c);
+  if(rc)
+    return rc;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const bool onDevice = (flags & TC_HIT_DEVICE_POINTERS) != 0;
+  uint32_t *dIdx = indices, *dTags = tags;
+  if(!onDevice)
+  {
+    dIdx = dTags = nullptr;
+    if(indices && capacityTriangles && (rc = dalloc(dIdx, capacityTriangles * 12)))
+      return rc;
+    if(tags && capacityTriangles && (rc = dalloc(dTags, capacityTriangles * 8)))
+    {
+      dfree(dIdx);
+      return rc;
+    }
+  }
+  // the look-back flags of this launch must differ from every earlier launch: own epoch range, one per call
+  const uint32_t epoch = 0x20000000u + (++c->emitCalls & 0x0FFFFFFFu);
+  cudaError_t e = cudaMemsetAsync(c->dEmitState, 0, 16, c->stream);
+  if(e == cudaSuccess)
+  {
+    tc::launch_emit_part_triangles(c->params, dIdx, dTags, capacityTriangles, c->dEmitState, epoch, uint32_t(c->numSMs * 8), c->stream);
+    e = cudaGetLastError();
+  }
+  uint64_t total = 0;
+  if(e == cudaSuccess && (numTriangles || !onDevice))
+  {
+    e = cudaMemcpyAsync(&total, c->dEmitState + 2, 8, cudaMemcpyDeviceToHost, c->stream);
+    if(e == cudaSuccess)
+      e = cudaStreamSynchronize(c->stream);
+  }
+  if(e == cudaSuccess && !onDevice)
+  {
+    const uint64_t n = std::min<uint64_t>(total, capacityTriangles);
+    if(dIdx && n)
+      e = cudaMemcpy(indices, dIdx, n * 12, cudaMemcpyDeviceToHost);
+    if(e == cudaSuccess && dTags && n)
+      e = cudaMemcpy(tags, dTags, n * 8, cudaMemcpyDeviceToHost);
+  }
+  if(!onDevice)
+  {
+    dfree(dIdx);
+    dfree(dTags);
+  }
+  if(e != cudaSuccess)
+    return fail(TC_ERR_CUDA, cudaGetErrorString(e));
+  if(numTriangles)
+    *numTriangles = total;
   return TC_OK;
 }
 

@@ -2321,6 +2321,205 @@ __global__ void __launch_bounds__(256) k_blas_insert(Params p)
     atomicAdd(reinterpret_cast<unsigned long long*>(&p.readback->numGenActualDatas), blockSizes);
 }
 
+// ============================================================================================================
+// hit-side decode (render_raytrace_clusters.rchit.glsl:131-236) and explicit part triangles
+// ============================================================================================================
+
+__device__ __forceinline__ F3 xscale3(F3 a, float s) { return {xmul(a.x, s), xmul(a.y, s), xmul(a.z, s)}; }
+__device__ __forceinline__ F3 xadd3(F3 a, F3 b) { return {xadd(a.x, b.x), xadd(a.y, b.y), xadd(a.z, b.z)}; }
+
+// tess_getConfigVertexBarycentrics (tessellation.glsl:175-187)
+__device__ __forceinline__ F3 tess_configVertexBarycentrics(const Params& p, uint32_t cfg, uint32_t vert)
+{
+  const tc_TessTableEntry e = tess_entry(p, cfg);
+  F3 wuv = tess_decodeBarycentrics(__ldg(&p.tblVertices[e.firstVertex + vert]));
+  if(cfg & TC_CONFIG_FLIPPED_BIT)
+  {
+    const float t = wuv.x;
+    wuv.x = wuv.y;
+    wuv.y = t;
+  }
+  return wuv;
+}
+// tess_getConfigTriangleVertices (tessellation.glsl:162-173)
+__device__ __forceinline__ void tess_configTriangleVertices(const Params& p, uint32_t cfg, uint32_t tri, uint32_t out[3])
+{
+  const tc_TessTableEntry e = tess_entry(p, cfg);
+  const uint32_t packedTri = __ldg(&p.tblTriangles[e.firstTriangle + tri]);
+  const bool     flipped   = (cfg & TC_CONFIG_FLIPPED_BIT) != 0;
+  out[0] = packedTri & 0xFF;
+  out[1] = (packedTri >> (flipped ? 16 : 8)) & 0xFF;
+  out[2] = (packedTri >> (flipped ? 8 : 16)) & 0xFF;
+}
+
+// thread per hit; the 20-byte hit records and the 48-byte results pass through shared memory so that global memory
+// only sees 128-bit accesses of consecutive lanes (as scalar records they were the kernel's limiter: 26 % -> of peak)
+__global__ void __launch_bounds__(128) k_resolve_hits(Params p, const tc_hit* hits, uint32_t count, tc_hit_base* out, uint32_t referenceQuirk)
+{
+  static_assert(sizeof(tc_hit) == 20 && sizeof(tc_hit_base) == 48, "record sizes");
+  __shared__ __align__(16) uint32_t shIn[128 * 5];
+  __shared__ __align__(16) uint32_t shOut[128 * 12];
+  const uint32_t base = blockIdx.x * blockDim.x;
+  const uint32_t nBlk = min(blockDim.x, count - base);
+  {  // cooperative load of nBlk * 5 words (block start is 128 * 20 B = 16-byte aligned)
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(hits) + size_t(base) * 5);
+    const uint32_t words = nBlk * 5, vec = words / 4;
+    for(uint32_t v = threadIdx.x; v < vec; v += blockDim.x)
+      reinterpret_cast<uint4*>(shIn)[v] = __ldcs(src + v);
+    for(uint32_t w = vec * 4 + threadIdx.x; w < words; w += blockDim.x)
+      shIn[w] = reinterpret_cast<const uint32_t*>(src)[w];
+  }
+  __syncthreads();
+  const uint32_t i = base + threadIdx.x;
+  if(threadIdx.x < nBlk)
+  {
+  tc_hit h;
+  h.instanceID = shIn[threadIdx.x * 5 + 0]; h.clusterID = shIn[threadIdx.x * 5 + 1]; h.primitiveID = shIn[threadIdx.x * 5 + 2];
+  h.barycentrics[0] = __uint_as_float(shIn[threadIdx.x * 5 + 3]); h.barycentrics[1] = __uint_as_float(shIn[threadIdx.x * 5 + 4]);
+  uint32_t clusterID = h.clusterID, triangleID = h.primitiveID;
+  const uint32_t mode = clusterID >> 30;  // :136-140
+  const bool isSpecial = mode != TC_RT_CLUSTER_MODE_FULL_CLUSTER;
+  bool       isTessTriangle = mode == TC_RT_CLUSTER_MODE_SINGLE_TESSELLATED;
+  clusterID &= 0x3FFFFFFFu;
+  uint32_t subTriangleID = triangleID, cfg = 0, partID = 0;
+  uint32_t vtxEncoded[3] = {0, 0, 0};
+  if(isSpecial)
+  {
+    const tc_TessTriangleInfo* parts = reinterpret_cast<const tc_TessTriangleInfo*>(p.build->partTriangles);
+    const tc_TessTriangleInfo  info  = parts[clusterID];  // :148
+    vtxEncoded[0] = info.subTriangle.vtxEncoded[0]; vtxEncoded[1] = info.subTriangle.vtxEncoded[1]; vtxEncoded[2] = info.subTriangle.vtxEncoded[2];
+    if(mode == TC_RT_CLUSTER_MODE_2X_BATCHED_TESSELLATED)
+    {  // :151-171
+      const uint16_t* map16 = reinterpret_cast<const uint16_t*>(p.build->transTriMappings);
+      const uint32_t  packedTriangleID = map16[size_t(clusterID) * (sizeof(tc_TessTriangleInfo) / 2) + sizeof(tc_ClusterInfo) / 2 + triangleID];
+      triangleID    = packedTriangleID & 0xFF;
+      subTriangleID = (packedTriangleID >> 8) & (referenceQuirk ? 4u : 3u);
+      vtxEncoded[0] = 0u;
+      vtxEncoded[1] = TC_TESSTABLE_COORD_MAX;
+      vtxEncoded[2] = TC_TESSTABLE_COORD_MAX << 16;
+      const uint32_t f0 = 1 + ((packedTriangleID >> 12) & 1), f1 = 1 + ((packedTriangleID >> 13) & 1), f2 = 1 + (packedTriangleID >> 14);
+      cfg = tess_getConfig(f0, f1, f2, vtxEncoded[0], vtxEncoded[1], vtxEncoded[2]);
+      isTessTriangle = true;
+    }
+    else if(mode == TC_RT_CLUSTER_MODE_1X_SUBSET_CLUSTER)
+    {  // :175-179
+      const uint8_t* map8 = reinterpret_cast<const uint8_t*>(p.build->transTriMappings);
+      triangleID = map8[size_t(clusterID) * sizeof(tc_TessTriangleInfo) + sizeof(tc_ClusterInfo) + triangleID];
+    }
+    else
+    {  // :182-185
+      triangleID = info.subTriangle.triangleID_config & 0xFFFF;
+      cfg        = info.subTriangle.triangleID_config >> 16;
+    }
+    clusterID = info.cluster.clusterID;  // :186
+  }
+  const tc_RenderInstance& inst = p.instances[h.instanceID];
+  const uint4 ch = __ldg(reinterpret_cast<const uint4*>(inst.clusters) + clusterID);  // :191
+  const uint8_t* lt = reinterpret_cast<const uint8_t*>(inst.clusterLocalTriangles) + ch.w + triangleID * 3;
+  tc_hit_base r;
+  r.baseIndices[0] = ch.z + lt[0]; r.baseIndices[1] = ch.z + lt[1]; r.baseIndices[2] = ch.z + lt[2];  // :198-201
+  F3 baryWeight = {xsub(xsub(1.0f, h.barycentrics[0]), h.barycentrics[1]), h.barycentrics[0], h.barycentrics[1]};  // :203
+  F3 baryWeightBase = baryWeight;
+  if(isTessTriangle)
+  {  // :208-232
+    F3 baseBary[3];
+#pragma unroll
+    for(int v = 0; v < 3; v++)
+    {
+      partID ^= (vtxEncoded[v] >> 20) | ((vtxEncoded[v] >> 4) & 0xFFF);
+      baseBary[v] = tess_decodeBarycentrics(vtxEncoded[v]);
+    }
+    uint32_t ti[3];
+    tess_configTriangleVertices(p, cfg, subTriangleID, ti);
+    const F3 nb = xadd3(xadd3(xscale3(tess_configVertexBarycentrics(p, cfg, ti[0]), baryWeight.x), xscale3(tess_configVertexBarycentrics(p, cfg, ti[1]), baryWeight.y)),
+                        xscale3(tess_configVertexBarycentrics(p, cfg, ti[2]), baryWeight.z));
+    baryWeightBase = xadd3(xadd3(xscale3(baseBary[0], nb.x), xscale3(baseBary[1], nb.y)), xscale3(baseBary[2], nb.z));
+    partID = triangleID | ((partID | 1) << 8);
+  }
+  r.mode = mode; r.clusterID = clusterID; r.triangleID = triangleID; r.subTriangleID = subTriangleID; r.cfg = cfg; r.partID = partID;
+  r.baryWeightBase[0] = baryWeightBase.x; r.baryWeightBase[1] = baryWeightBase.y; r.baryWeightBase[2] = baryWeightBase.z;
+  uint4* so = reinterpret_cast<uint4*>(shOut + threadIdx.x * 12);  // 48-byte stride: 128-bit shared stores are conflict free
+  so[0] = make_uint4(r.mode, r.clusterID, r.triangleID, r.subTriangleID);
+  so[1] = make_uint4(r.cfg, r.baseIndices[0], r.baseIndices[1], r.baseIndices[2]);
+  so[2] = make_uint4(r.partID, __float_as_uint(r.baryWeightBase[0]), __float_as_uint(r.baryWeightBase[1]), __float_as_uint(r.baryWeightBase[2]));
+  (void)i;
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(out + base);
+  for(uint32_t v = threadIdx.x; v < nBlk * 3; v += blockDim.x)
+    __stcs(dst + v, reinterpret_cast<const uint4*>(shOut)[v]);
+}
+
+// Explicit triangles of the template-instantiated parts.  Persistent warps, tile = 32 consecutive instantiate
+// records; the triangle offsets come from a 16-byte decoupled look-back in record order (canonical, like the frame).
+// state[0] = tile ticket, state[2..3] = total triangle count (u64)
+__global__ void __launch_bounds__(128) k_emit_part_triangles(Params p, uint32_t* indices, uint32_t* tags, unsigned long long capacity, uint32_t* state,
+                                                            uint32_t epoch)
+{
+  const uint32_t lane = lane_id();
+  const tc_SceneBuilding* b = p.build;
+  const uint32_t first = p.state->tempAfterClassify, end = b->tempInstantiateCounter;
+  const uint32_t count = end > first ? end - first : 0, numTiles = (count + 31) / 32;
+  const tc_TemplateInstantiateInfo* recs  = reinterpret_cast<const tc_TemplateInstantiateInfo*>(b->tempInstantiations);
+  const tc_TessTriangleInfo*        parts = reinterpret_cast<const tc_TessTriangleInfo*>(b->partTriangles);
+  const unsigned long long genVerticesAddr = b->genVertices;
+  if(numTiles == 0)
+  {
+    if(blockIdx.x == 0 && threadIdx.x == 0)
+      *reinterpret_cast<unsigned long long*>(state + 2) = 0ull;
+    return;
+  }
+  while(true)
+  {
+    uint32_t tile = 0;
+    if(lane == 0)
+      tile = atomicAdd(&state[0], 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if(tile >= numTiles)
+      break;
+    const uint32_t j = first + tile * 32 + lane;
+    uint32_t clusterWord = 0, cfg = 0, numTris = 0, firstTriangle = 0, vertexOffset = 0;
+    if(j < end)
+    {
+      const tc_TemplateInstantiateInfo r = recs[j];
+      clusterWord  = r.clusterIdOffset;
+      vertexOffset = uint32_t((r.vertexBufferAddress - genVerticesAddr) / 12ull);
+      cfg          = parts[clusterWord & 0x3FFFFFFFu].subTriangle.triangleID_config >> 16;
+      const tc_TessTableEntry e = tess_entry(p, cfg);
+      numTris = e.numTriangles; firstTriangle = e.firstTriangle;
+    }
+    const uint32_t endT = warp_inclusive_add(numTris), startT = endT - numTris, total = __shfl_sync(0xffffffffu, endT, 31);
+    lookback16_publish(p.lookback16, tile, 0u, total, epoch);
+    uint32_t           dummy;
+    unsigned long long excl;
+    lookback16_resolve(p.lookback16, tile, 0u, total, epoch, dummy, excl);
+    if(tile == numTiles - 1 && lane == 0)
+      *reinterpret_cast<unsigned long long*>(state + 2) = excl + total;
+    for(uint32_t t0 = 0; t0 < total; t0 += 32)
+    {
+      const uint32_t t = t0 + lane;
+      const uint32_t item = find_item(endT, t);
+      const uint32_t tri  = t - __shfl_sync(0xffffffffu, startT, item);
+      const uint32_t iCfg = __shfl_sync(0xffffffffu, cfg, item), iFT = __shfl_sync(0xffffffffu, firstTriangle, item);
+      const uint32_t iVO  = __shfl_sync(0xffffffffu, vertexOffset, item), iCW = __shfl_sync(0xffffffffu, clusterWord, item);
+      const unsigned long long g = excl + t;
+      if(t < total && g < capacity)
+      {
+        const uint32_t packedTri = __ldg(&p.tblTriangles[iFT + tri]);
+        const bool     flipped   = (iCfg & TC_CONFIG_FLIPPED_BIT) != 0;
+        if(indices)
+        {
+          indices[g * 3 + 0] = iVO + (packedTri & 0xFF);
+          indices[g * 3 + 1] = iVO + ((packedTri >> (flipped ? 16 : 8)) & 0xFF);
+          indices[g * 3 + 2] = iVO + ((packedTri >> (flipped ? 8 : 16)) & 0xFF);
+        }
+        if(tags)
+          *reinterpret_cast<uint2*>(tags + g * 2) = make_uint2(iCW, tri);
+      }
+    }
+  }
+}
+
 __global__ void k_flush_l2(float4* buf, size_t n)
 {
   for(size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
@@ -2428,6 +2627,15 @@ void launch_hiz_update(const HizPass& q, cudaStream_t s)
   launch_pdl(k_hiz_update, grid, block, 0, s, q);
 }
 
+void launch_resolve_hits(const Params& p, const tc_hit* hits, uint32_t count, tc_hit_base* out, bool referenceQuirk, cudaStream_t s)
+{
+  if(count)
+    k_resolve_hits<<<(count + 127) / 128, 128, 0, s>>>(p, hits, count, out, referenceQuirk ? 1u : 0u);
+}
+void launch_emit_part_triangles(const Params& p, uint32_t* indices, uint32_t* tags, unsigned long long capacity, uint32_t* state, uint32_t epoch, uint32_t grid, cudaStream_t s)
+{
+  k_emit_part_triangles<<<grid, 128, 0, s>>>(p, indices, tags, capacity, state, epoch);
+}
 void launch_flush_l2(void* buf, size_t bytes, cudaStream_t s) { k_flush_l2<<<1184, 256, 0, s>>>(reinterpret_cast<float4*>(buf), bytes / 16); }
 
 }  // namespace tc
