@@ -151,6 +151,9 @@ def main():
     ap.add_argument("--small", action="store_true", help="debug-size workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the ranks' counts meet -- 'peer': stores into peer mailboxes from inside the frame's own kernels (default), "
+                         "'nccl': an allgather between the two halves of the frame")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -191,12 +194,17 @@ def main():
         gpu.set_stream(stream.cuda_stream)
         counts_t = torch.zeros(sharding.SHARD_WORDS, dtype=torch.int32, device="cuda")
         shard = (sharding, counts_t)
+        if args.exchange == "peer":
+            sharding.connect_peer_mailboxes(gpu, rank, world)
 
     def one_frame(use_graph: bool):
         if world == 1:
             (gpu.frame_graph if use_graph else gpu.frame)(fcs)
             return None
         sharding_, counts_t_ = shard
+        if args.exchange == "peer":  # the whole frame incl. the exchange is one stream-ordered sequence (one graph)
+            (gpu.frame_graph if use_graph else gpu.frame)(fcs)
+            return None
         (gpu.frame_build_graph if use_graph else gpu.frame_build)(fcs)
         gpu.copy_async(counts_t_.data_ptr(), gpu.device_shard_counts(), 32)
         gathered, base = sharding_.exchange_shard_counts(counts_t_)
@@ -251,6 +259,10 @@ def main():
         torch.cuda.synchronize()
 
     if world > 1:
+        if args.exchange == "peer":
+            recs, timed_out = gpu.shard_gathered()
+            assert not timed_out, "a peer's counts never arrived"
+            gathered = torch.from_numpy(recs.astype(np.int64).astype(np.int32, casting="unsafe").reshape(world, -1))
         tot = shard[0].global_totals(gathered)
         tris_total, clusters_total = tot["totalTriangles"], tot["blasClusters"]
     else:
@@ -321,7 +333,7 @@ def main():
         line = {
             "metric": METRIC, "value": tris_total * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if not args.small else "small icosphere (debug)", "parallelism": f"instance-sharded x{world}",
+            "config": {"workload": WORKLOAD if not args.small else "small icosphere (debug)", "parallelism": f"instance-sharded x{world}" + ("" if world == 1 else (", counts exchanged by peer-mailbox stores inside the frame's kernels (no collective call)" if args.exchange == "peer" else ", NCCL allgather of the counts between the frame's halves")),
                        "l2": "flushed between timed frames (256 MiB write)", "launch": "cuda graph" if use_graph else "stream launches",
                        "triangles_per_frame": tris_total, "clusters_per_frame": clusters_total, "parts_per_frame_rank0": n_parts,
                        "generated_vertices_rank0": n_verts},

@@ -255,6 +255,31 @@ typedef struct tc_shard_counts {
   uint32_t numTotalTriangles;
   uint32_t numInstances;
 } tc_shard_counts;
+/* ---- exchange fused into the frame: peer mailboxes over NVLink/NVSwitch ------------------------------------
+ * Instead of a collective between the two halves, the last CTA of the instantiate kernel STORES the rank's
+ * tc_shard_counts straight into a mailbox slot on every peer GPU (peer memory: cudaIpcOpenMemHandle across
+ * processes, plain device pointers inside one process), and the BLAS setup kernel waits for the world's slots of
+ * the current frame and forms its own exclusive prefix.  The whole frame (tc_frame / tc_frame_graph) then is ONE
+ * stream-ordered sequence per rank with no collective call, no host round trip and no second graph.
+ * A mailbox is tc_shard_mailbox_slot[2][TC_MAX_SHARDS] (two frame parities: a rank can run at most one frame
+ * ahead of a peer, because its own insert half waits for every peer's counts).  A rank that never shows up makes
+ * the wait give up after about a second: bases are then 0 and tc_shard_gathered reports timedOut. */
+#define TC_MAX_SHARDS 16
+typedef struct tc_shard_mailbox_slot {
+  tc_shard_counts counts;
+  uint32_t        frame;   /* frame number the counts belong to (written last, release order) */
+  uint32_t        pad[3];
+} tc_shard_mailbox_slot;
+/* this context's own mailbox: a separate cudaMalloc allocation (IPC-exportable), tc_shard_mailbox_bytes() large */
+TC_API size_t tc_shard_mailbox_bytes(void);
+TC_API int tc_device_shard_mailbox(tc_context* ctx, uint64_t* deviceAddress);
+/* mailboxAddresses[r] = rank r's mailbox as seen from THIS process (own address at [rank]); world <= 1 switches the
+ * exchange off again (tc_device_shard_base is then the caller's to fill, as before).  Frame tags restart with this
+ * call: every rank makes it, then a barrier, then frames in lockstep (each rank the same number of tc_frame calls). */
+TC_API int tc_set_shard_peers(tc_context* ctx, uint32_t rank, uint32_t world, const uint64_t* mailboxAddresses);
+/* the records of the last completed frame as this rank received them (synchronises the stream) */
+TC_API int tc_shard_gathered(tc_context* ctx, tc_shard_counts* out, uint32_t capacity, uint32_t* timedOut);
+
 /* Device address of the rank's tc_shard_counts block, valid after tc_frame_build (no sync). */
 TC_API int tc_device_shard_counts(tc_context* ctx, uint64_t* deviceAddress);
 /* Device address of a 2 x u32 block {globalBlasClusterBase, globalInstanceBase} the insert step adds. */

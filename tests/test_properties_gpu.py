@@ -124,3 +124,47 @@ def test_shard_summary_record_matches_readback(table):
     assert rec["numInstances"] == len(scene.instances)
     assert rec["transBuildCounter"] > 0 and rec["tempInstantiateCounter"] > 0
     gpu.close()
+
+
+def test_peer_mailbox_exchange_two_ranks_one_gpu(table):
+    """The exchange fused into the frame, with two contexts (= two ranks) in one process on one GPU: each rank's
+    instantiate kernel stores its counts into both mailboxes, each rank's BLAS setup kernel waits for both and forms
+    its own base.  The global insertion list must be the concatenation of the ranks' lists."""
+    from tests.scene_cases import case
+    from vk_tessellated_clusters_b200 import sharding
+
+    scene_a, fcs, cfg, _ = case("mini")
+    scene_b, _, _, _ = case("split")
+    gpus = []
+    for scene in (scene_a, scene_b):
+        g = api.TessClusters(cfg)
+        g.set_tess_table(table)
+        g.set_scene(scene)
+        gpus.append(g)
+    boxes = [g.device_shard_mailbox() for g in gpus]
+    for r, g in enumerate(gpus):
+        g.set_shard_peers(r, 2, boxes)
+    for frame in range(3):  # several frames: both mailbox parities, tags advance in lockstep
+        for g in gpus:
+            g.frame(fcs)  # asynchronous: rank 0's setup kernel waits on the GPU for rank 1's instantiate
+        recs = []
+        for r, g in enumerate(gpus):
+            got, timed_out = g.shard_gathered()
+            assert not timed_out
+            recs.append(got)
+        assert np.array_equal(recs[0], recs[1])  # both ranks received the same two records
+        cnt = [sharding.unpack_shard_counts(w) for w in recs[0]]
+        for r, g in enumerate(gpus):
+            rb, sb = g.readback()
+            assert cnt[r]["blasClusterCounter"] == int(sb["tempInstantiateCounter"]) + int(sb["transBuildCounter"])
+            ranges = g.global_blas_ranges()
+            base_c = sum(c["blasClusterCounter"] for c in cnt[:r])
+            base_i = sum(c["numInstances"] for c in cnt[:r])
+            assert int(ranges["globalInstanceID"][0]) == base_i
+            assert int(ranges["globalFirstReference"][0]) == base_c
+    # a rank that never shows up must not hang the GPU: the wait gives up and reports it
+    gpus[0].frame(fcs)
+    got, timed_out = gpus[0].shard_gathered()
+    assert timed_out
+    for g in gpus:
+        g.close()

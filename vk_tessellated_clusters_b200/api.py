@@ -406,10 +406,38 @@ class TessClusters(Binding):
         self._check(self.lib.tc_device_global_blas_ranges(self._ctx, C.byref(a)), "device_global_blas_ranges")
         return int(a.value)
 
+    def global_blas_ranges(self, count: int | None = None) -> np.ndarray:
+        """tc_global_blas_range records of the local instances (after the insert half)."""
+        n = self.num_instances if count is None else count
+        raw = self.download(self.device_global_blas_ranges(), n * GLOBAL_BLAS_RANGE_DTYPE.itemsize)
+        return raw.view(GLOBAL_BLAS_RANGE_DTYPE)
+
     def device_shard_counts(self) -> int:
         a = C.c_uint64()
         self._check(self.lib.tc_device_shard_counts(self._ctx, C.byref(a)), "device_shard_counts")
         return int(a.value)
+
+    def device_shard_mailbox(self) -> int:
+        a = C.c_uint64()
+        self._check(self.lib.tc_device_shard_mailbox(self._ctx, C.byref(a)), "device_shard_mailbox")
+        return a.value
+
+    def shard_mailbox_bytes(self) -> int:
+        self.lib.tc_shard_mailbox_bytes.restype = C.c_size_t
+        return int(self.lib.tc_shard_mailbox_bytes())
+
+    def set_shard_peers(self, rank: int, world: int, mailbox_addresses):
+        arr = (C.c_uint64 * max(1, world))(*[int(a) for a in mailbox_addresses])
+        self._check(self.lib.tc_set_shard_peers(self._ctx, C.c_uint32(rank), C.c_uint32(world), arr), "set_shard_peers")
+        self.shard_world = world
+
+    def shard_gathered(self):
+        """-> (records [world, SHARD_WORDS] u32 of the last frame as received by this rank, timed_out)"""
+        world = getattr(self, "shard_world", 0)
+        out = np.zeros((max(world, 1), 8), np.uint32)
+        t = C.c_uint32()
+        self._check(self.lib.tc_shard_gathered(self._ctx, _ptr(out), C.c_uint32(out.shape[0]), C.byref(t)), "shard_gathered")
+        return out[:world], bool(t.value)
 
     def device_shard_base(self) -> int:
         a = C.c_uint64()

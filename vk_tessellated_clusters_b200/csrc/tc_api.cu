@@ -74,6 +74,10 @@ struct tc_context
   FrameStaging*     dFrame     = nullptr;
   FrameStaging*     hFrame     = nullptr;  // pinned
   tc_shard_counts*  dShardCounts = nullptr;
+  tc_shard_mailbox_slot* dMailbox = nullptr;  // own mailbox: its own allocation so that it can be IPC-exported
+  uint32_t*         dShardStatus = nullptr;
+  uint32_t          shardRank = 0, shardWorld = 0, shardFrameBase = 0;
+  uint64_t          peerMailbox[TC_MAX_SHARDS] = {};
   uint32_t*         dEmitState = nullptr;  // tc_emit_part_triangles: ticket, pad, total (u64)
   uint32_t          emitCalls = 0;
   uint32_t*         dShardBase   = nullptr;
@@ -269,6 +273,12 @@ void fill_params(tc_context* c)
   p.rankBase           = c->rankBase;
   p.shardBase          = c->dShardBase;
   p.shardCounts        = c->dShardCounts;
+  p.shardRank          = c->shardRank;
+  p.shardWorld         = c->shardWorld;
+  p.shardFrameBase     = c->shardFrameBase;
+  for(uint32_t r = 0; r < TC_MAX_SHARDS; r++)
+    p.peerMailbox[r] = reinterpret_cast<tc_shard_mailbox_slot*>(c->peerMailbox[r]);
+  p.shardStatus        = c->dShardStatus;
   p.globalRanges       = c->globalRanges;
 }
 
@@ -360,7 +370,7 @@ int enqueue_insert(tc_context* c)
 {
   StageScope sc(c, TC_STAGE_INSERT);
   uint32_t passes = split_pass_count(std::max(2u, c->cfg.splitFactor));
-  tc::launch_blas(c->params, passes + 3, uint32_t(c->numSMs * 4), c->stream);
+  tc::launch_blas(c->params, c->dEpoch, passes + 3, uint32_t(c->numSMs * 4), c->stream);
   c->lastLaunches += 3;
   CUDA_TRY(cudaGetLastError());
   return TC_OK;
@@ -440,6 +450,10 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   TRY_RC(dalloc(c->dFrame, sizeof(FrameStaging)));
   TRY_RC(dalloc(c->dShardCounts, sizeof(tc_shard_counts)));
   TRY_RC(dalloc(c->dEmitState, 16));
+  TRY_RC(dalloc(c->dMailbox, tc_shard_mailbox_bytes()));
+  CUDA_TRY(cudaMemset(c->dMailbox, 0xFF, tc_shard_mailbox_bytes()));  // no slot carries a valid frame number yet
+  TRY_RC(dalloc(c->dShardStatus, 16));
+  CUDA_TRY(cudaMemset(c->dShardStatus, 0, 16));
   TRY_RC(dalloc(c->dShardBase, 16));
   TRY_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->hFrame), sizeof(FrameStaging)));
   memset(c->hFrame, 0, sizeof(FrameStaging));
@@ -503,7 +517,7 @@ TC_API void tc_destroy(tc_context* c)
   drop_graph(c);
   free_scene(c);
   dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dFrame);
-  dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState);
+  dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState); dfree(c->dMailbox); dfree(c->dShardStatus);
   if(c->hFrame)
     cudaFreeHost(c->hFrame);
   dfree(c->visibleClusters); dfree(c->splitTriangles); dfree(c->partTriangles); dfree(c->genVertices);
@@ -1266,6 +1280,60 @@ TC_API int tc_device_shard_counts(tc_context* c, uint64_t* deviceAddress)
   if(!c || !deviceAddress)
     return fail(TC_ERR_INVALID_ARG, "null argument");
   *deviceAddress = uint64_t(c->dShardCounts);
+  return TC_OK;
+}
+
+TC_API size_t tc_shard_mailbox_bytes(void) { return sizeof(tc_shard_mailbox_slot) * 2 * TC_MAX_SHARDS; }
+
+TC_API int tc_device_shard_mailbox(tc_context* c, uint64_t* deviceAddress)
+{
+  if(!c || !deviceAddress)
+    return fail(TC_ERR_INVALID_ARG, "null argument");
+  *deviceAddress = uint64_t(c->dMailbox);
+  return TC_OK;
+}
+
+TC_API int tc_set_shard_peers(tc_context* c, uint32_t rank, uint32_t world, const uint64_t* mailboxAddresses)
+{
+  if(!c)
+    return fail(TC_ERR_INVALID_ARG, "null context");
+  if(world > TC_MAX_SHARDS || (world > 1 && (!mailboxAddresses || rank >= world)))
+    return fail(TC_ERR_INVALID_ARG, "bad rank / world / addresses");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->shardRank  = world > 1 ? rank : 0;
+  c->shardWorld = world > 1 ? world : 0;
+  for(uint32_t r = 0; r < TC_MAX_SHARDS; r++)
+    c->peerMailbox[r] = (world > 1 && r < world) ? mailboxAddresses[r] : 0;
+  if(world > 1 && c->peerMailbox[rank] != uint64_t(c->dMailbox))
+    return fail(TC_ERR_INVALID_ARG, "mailboxAddresses[rank] must be this context's own mailbox");
+  // frame tags restart at 1; the caller separates this call from the first frame of ANY rank by a barrier
+  uint32_t epoch = 0;
+  CUDA_TRY(cudaMemcpy(&epoch, c->dEpoch, 4, cudaMemcpyDeviceToHost));
+  c->shardFrameBase = epoch >> 5;
+  CUDA_TRY(cudaMemset(c->dMailbox, 0xFF, tc_shard_mailbox_bytes()));
+  CUDA_TRY(cudaMemset(c->dShardStatus, 0, 16));
+  drop_graph(c);
+  fill_params(c);
+  return TC_OK;
+}
+
+TC_API int tc_shard_gathered(tc_context* c, tc_shard_counts* out, uint32_t capacity, uint32_t* timedOut)
+{
+  if(!c || !out || capacity < c->shardWorld)
+    return fail(TC_ERR_INVALID_ARG, "null argument or capacity below the world size");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  uint32_t epoch = 0, status = 0;
+  CUDA_TRY(cudaMemcpy(&epoch, c->dEpoch, 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(&status, c->dShardStatus, 4, cudaMemcpyDeviceToHost));
+  std::vector<tc_shard_mailbox_slot> slots(2 * TC_MAX_SHARDS);
+  CUDA_TRY(cudaMemcpy(slots.data(), c->dMailbox, tc_shard_mailbox_bytes(), cudaMemcpyDeviceToHost));
+  const uint32_t frame = (epoch >> 5) - c->shardFrameBase;
+  for(uint32_t r = 0; r < c->shardWorld; r++)
+    out[r] = slots[(frame & 1u) * TC_MAX_SHARDS + r].counts;
+  if(timedOut)
+    *timedOut = status;
   return TC_OK;
 }
 

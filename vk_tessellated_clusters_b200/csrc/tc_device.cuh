@@ -98,6 +98,11 @@ struct Params
   const uint32_t* shardBase;  // {globalBlasClusterBase, globalInstanceBase}
   tc_global_blas_range* globalRanges;  // [numInstances]
   tc_shard_counts*      shardCounts;   // summary record for the multi-GPU allgather, written by the last CTA of k_instantiate
+  // peer-mailbox exchange (tess_clusters.h): world <= 1 = off
+  uint32_t               shardRank, shardWorld;
+  uint32_t               shardFrameBase;  // frame number (epoch / 32) at tc_set_shard_peers: tags count frames since then
+  tc_shard_mailbox_slot* peerMailbox[TC_MAX_SHARDS];  // [r] = rank r's mailbox (own at [shardRank])
+  uint32_t*              shardStatus;   // [0] = 1 when the wait for the peers timed out this frame
 };
 
 __device__ __forceinline__ bool flag_pn(const Params& p) { return p.flags & TC_FLAG_PN_DISPLACEMENT; }

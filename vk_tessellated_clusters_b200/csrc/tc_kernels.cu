@@ -2109,6 +2109,24 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
       sc->genClusterDataCounter  = b->genClusterDataCounter;
       sc->numTotalTriangles      = *(volatile uint32_t*)&p.readback->numTotalTriangles;
       sc->numInstances           = p.numInstances;
+      if(p.shardWorld > 1)
+      {  // exchange fused into the frame: the record goes straight into this rank's slot on every peer (NVLink stores)
+        const uint32_t frame = (*epochCounter >> 5) - p.shardFrameBase;  // frames since tc_set_shard_peers, the same number on every rank
+        const uint4 c0 = make_uint4(sc->tempInstantiateCounter, sc->transBuildCounter, sc->genVertexCounter, sc->blasClusterCounter);
+        const uint4 c1 = make_uint4(uint32_t(sc->genClusterDataCounter), uint32_t(sc->genClusterDataCounter >> 32), sc->numTotalTriangles, sc->numInstances);
+        for(uint32_t r = 0; r < p.shardWorld; r++)
+        {
+          uint4* slot = reinterpret_cast<uint4*>(&p.peerMailbox[r][(frame & 1u) * TC_MAX_SHARDS + p.shardRank]);
+          slot[0] = c0;
+          slot[1] = c1;
+        }
+        __threadfence_system();  // counts before the frame tags, system wide
+        for(uint32_t r = 0; r < p.shardWorld; r++)
+        {
+          uint32_t* tag = &p.peerMailbox[r][(frame & 1u) * TC_MAX_SHARDS + p.shardRank].frame;
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(tag), "r"(frame) : "memory");
+        }
+      }
     }
   }
 }
@@ -2189,11 +2207,63 @@ __global__ void k_blas_segments(Params p)
 }
 
 // one CTA: per-instance totals, exclusive scan in instance order, BlasBuildInfo (blas_setup_insertion.comp.glsl:100-115)
-__global__ void __launch_bounds__(1024) k_blas_setup(Params p)
+__global__ void __launch_bounds__(1024) k_blas_setup(Params p, const uint32_t* epochCounter)
 {
   pdl_prologue();
   __shared__ uint32_t warpSums[32];
   __shared__ uint32_t carry, sizesSum, blockTotal;
+  __shared__ uint32_t shardClusters[TC_MAX_SHARDS], shardInstances[TC_MAX_SHARDS], shardBaseS[2], shardTimedOut;
+  if(p.shardWorld > 1)
+  {  // peer-mailbox exchange: wait for every rank's counts of THIS frame, exclusive prefix over the ranks before ours
+    const uint32_t frame = (*epochCounter >> 5) - p.shardFrameBase;
+    if(threadIdx.x == 0)
+      shardTimedOut = 0;
+    __syncthreads();
+    if(threadIdx.x < p.shardWorld)
+    {
+      const tc_shard_mailbox_slot* slot = &p.peerMailbox[p.shardRank][(frame & 1u) * TC_MAX_SHARDS + threadIdx.x];
+      unsigned long long t0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      uint32_t tag;
+      bool     ok = true;
+      while(true)
+      {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(tag) : "l"(&slot->frame) : "memory");
+        if(tag == frame)
+          break;
+        __nanosleep(200);
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if(t1 - t0 > 1000000000ull)
+        {  // a peer never showed up: give up instead of hanging the GPU
+          ok = false;
+          break;
+        }
+      }
+      shardClusters[threadIdx.x]  = ok ? slot->counts.blasClusterCounter : 0u;
+      shardInstances[threadIdx.x] = ok ? slot->counts.numInstances : 0u;
+      if(!ok)
+        shardTimedOut = 1;
+    }
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+      uint32_t bc = 0, bi = 0;
+      for(uint32_t r = 0; r < p.shardRank; r++)
+      {
+        bc += shardClusters[r];
+        bi += shardInstances[r];
+      }
+      shardBaseS[0] = shardTimedOut ? 0u : bc;
+      shardBaseS[1] = shardTimedOut ? 0u : bi;
+      p.shardStatus[0] = shardTimedOut;
+    }
+  }
+  else if(threadIdx.x == 0)
+  {
+    shardBaseS[0] = p.shardBase[0];
+    shardBaseS[1] = p.shardBase[1];
+  }
   const SegmentTable segs = load_segments(p);
   const uint32_t     N    = p.numInstances;
   tc_BlasBuildInfo*  blas = reinterpret_cast<tc_BlasBuildInfo*>(p.build->blasBuildInfos);
@@ -2238,7 +2308,7 @@ __global__ void __launch_bounds__(1024) k_blas_setup(Params p)
       blas[i].clusterReferencesStride = 8;
       blas[i].clusterReferences       = p.build->blasClusterAddresses + (unsigned long long)(uint32_t)(offset * 8u);
       // multi-GPU: position of this instance's list in the rank-concatenated insertion list
-      p.globalRanges[i] = tc_global_blas_range{p.shardBase[1] + i, total, (unsigned long long)p.shardBase[0] + offset};
+      p.globalRanges[i] = tc_global_blas_range{shardBaseS[1] + i, total, (unsigned long long)shardBaseS[0] + offset};
     }
     __syncthreads();
     if(threadIdx.x == 0)
@@ -2613,11 +2683,11 @@ void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t 
     default: launch_pdl(k_instantiate<2, true>, grid, INST_THREADS, smem, s, p, epochCounter); break;
   }
 }
-void launch_blas(const Params& p, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s)
+void launch_blas(const Params& p, const uint32_t* epochCounter, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s)
 {
   uint32_t threads = (p.numInstances + 1) * numSegmentsMax * 32;  // one warp per (instance, segment)
   launch_pdl(k_blas_segments, (threads + 255) / 256, 256, 0, s, p);
-  launch_pdl(k_blas_setup, 1, 1024, 0, s, p);
+  launch_pdl(k_blas_setup, 1, 1024, 0, s, p, epochCounter);
   launch_pdl(k_blas_insert, grid, 256, 0, s, p);
 }
 void launch_hiz_update(const HizPass& q, cudaStream_t s)

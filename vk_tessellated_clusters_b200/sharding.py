@@ -69,3 +69,49 @@ def global_totals(gathered) -> dict:
         "totalTriangles": int(g[:, 6].sum()),
         "instances": int(g[:, 7].sum()),
     }
+
+
+def connect_peer_mailboxes(gpu, rank: int, world: int, group=None):
+    """Exchange fused into the frame (include/tess_clusters.h, tc_set_shard_peers): every rank exports its mailbox
+    allocation as a CUDA IPC handle, the handles are allgathered ONCE at setup, each rank maps its peers' mailboxes
+    (peer access over NVLink/NVSwitch) and hands the addresses to the library.  After this no collective runs per frame:
+    the instantiate kernel stores the rank's counts into every mailbox, the BLAS setup kernel waits for them.
+    One process per GPU, the rank's device current.  Ends with a barrier (frame tags restart on every rank)."""
+    import ctypes as C
+
+    import torch.distributed as dist
+
+    class IpcHandle(C.Structure):
+        _fields_ = [("reserved", C.c_char * 64)]
+
+    rt = None
+    for name in ("libcudart.so.12", "libcudart.so", "/usr/local/cuda/lib64/libcudart.so"):
+        try:
+            rt = C.CDLL(name)
+            break
+        except OSError:
+            continue
+    if rt is None:
+        raise RuntimeError("libcudart not found")
+    own = gpu.device_shard_mailbox()
+    handle = IpcHandle()
+    rc = rt.cudaIpcGetMemHandle(C.byref(handle), C.c_void_p(own))
+    if rc != 0:
+        raise RuntimeError(f"cudaIpcGetMemHandle failed with {rc}")
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(bytearray(handle)), group=group)
+    addrs = []
+    rt.cudaIpcOpenMemHandle.argtypes = [C.POINTER(C.c_void_p), IpcHandle, C.c_uint]
+    for r in range(world):
+        if r == rank:
+            addrs.append(own)
+            continue
+        peer = IpcHandle.from_buffer_copy(handles[r])
+        ptr = C.c_void_p()
+        rc = rt.cudaIpcOpenMemHandle(C.byref(ptr), peer, C.c_uint(1))  # cudaIpcMemLazyEnablePeerAccess
+        if rc != 0:
+            raise RuntimeError(f"cudaIpcOpenMemHandle(rank {r}) failed with {rc}")
+        addrs.append(ptr.value)
+    gpu.set_shard_peers(rank, world, addrs)
+    dist.barrier(group=group)
+    return addrs
