@@ -78,6 +78,8 @@ struct tc_context
   uint32_t*         dShardStatus = nullptr;
   uint32_t          shardRank = 0, shardWorld = 0, shardFrameBase = 0;
   uint64_t          peerMailbox[TC_MAX_SHARDS] = {};
+  void*             dMiniList = nullptr;
+  uint32_t          maxMini = 0;
   uint32_t*         dEmitState = nullptr;  // tc_emit_part_triangles: ticket, pad, total (u64)
   uint32_t          emitCalls = 0;
   uint32_t*         dShardBase   = nullptr;
@@ -272,6 +274,8 @@ void fill_params(tc_context* c)
   p.segLo              = c->segLo;
   p.rankBase           = c->rankBase;
   p.shardBase          = c->dShardBase;
+  p.miniList           = reinterpret_cast<uint4*>(c->dMiniList);
+  p.maxMini            = c->maxMini;
   p.shardCounts        = c->dShardCounts;
   p.shardRank          = c->shardRank;
   p.shardWorld         = c->shardWorld;
@@ -335,8 +339,8 @@ int enqueue_build(tc_context* c)
     // (statistics atomics + fence) stays negligible for scenes with millions of clusters
     uint32_t grid = std::max(1u, (std::min(c->totalClusters, c->maxVisible) + tc::classify_tile_clusters() - 1) / tc::classify_tile_clusters());
     grid          = std::min(grid, uint32_t(c->numSMs) * 32u);
-    tc::launch_cluster_classify(p, c->dEpoch, grid, s);  // count -> scan -> emit (cluster level) -> emit (triangle level)
-    launches += 4;
+    tc::launch_cluster_classify(p, c->dEpoch, grid, uint32_t(c->numSMs * 5), s);  // count -> scan -> emit (cluster level) -> emit (triangle level) -> 2X mini vertices
+    launches += (c->cfg.flags & TC_FLAG_TRANSIENT_2X) ? 5 : 4;
   }
   {
     StageScope sc(c, TC_STAGE_SPLIT);
@@ -466,6 +470,10 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   TRY_RC(dalloc(c->dClassTuples, size_t(c->maxVisible) * tc::classify_tuple_bytes()));
   TRY_RC(dalloc(c->dFactorStash, size_t(c->maxVisible) * config->clusterTriangles * 12));
   TRY_RC(dalloc(c->dClassMeta, size_t(c->maxVisible) * 4));
+  // one 32-byte record per 2X mini triangle: a batch of 8 occupies 56 vertex slots of genVertices
+  c->maxMini = (config->flags & TC_FLAG_TRANSIENT_2X) ? uint32_t(std::min<uint64_t>(uint64_t(c->maxVerts) / 7 + 64, 0xFFFFFFF0ull)) : 0u;
+  if(c->maxMini)
+    TRY_RC(dalloc(c->dMiniList, size_t(c->maxMini) * 32));
   TRY_CUDA(cudaMemset(c->dEpoch, 0, 16));
   TRY_CUDA(cudaMemset(c->dShardBase, 0, 16));
   TRY_CUDA(cudaMemset(c->dReadback, 0, sizeof(tc_Readback)));
@@ -517,7 +525,7 @@ TC_API void tc_destroy(tc_context* c)
   drop_graph(c);
   free_scene(c);
   dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dFrame);
-  dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState); dfree(c->dMailbox); dfree(c->dShardStatus);
+  dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState); dfree(c->dMiniList); dfree(c->dMailbox); dfree(c->dShardStatus);
   if(c->hFrame)
     cudaFreeHost(c->hFrame);
   dfree(c->visibleClusters); dfree(c->splitTriangles); dfree(c->partTriangles); dfree(c->genVertices);

@@ -45,6 +45,8 @@ struct FrameState
   uint32_t clusterLevelWork;   // visible clusters the cluster-level emit kernel has to touch (counted by the count pass)
   uint32_t triangleLevelWork;  // ... and the triangle-level emit kernel
   uint32_t splitTotal[2];      // grand totals (split, part) of the current split pass (written by the warp that owns the last tile)
+  uint32_t miniCount;          // 2X mini triangles whose vertices k_mini_vertices has to generate (records in Params::miniList)
+  uint32_t pad2;
   unsigned long long instTotalD;
   uint32_t classTotal[8];    // grand totals of the classify scan: v[0..5], data lo, data hi
   // aggregated stats kept as plain counters and folded into Readback by the setup steps
@@ -92,6 +94,9 @@ struct Params
   void*     classTuples;   // ScanTuple[maxVisibleClusters]: counts, then (in place) exclusive prefixes
   uint32_t* factorStash;   // [maxVisibleClusters][clusterTriangles][3]: factor | local vertex index << 24
   uint32_t* classMeta;     // [maxVisibleClusters]: number of triangles that need no tessellation (simpleCount)
+  // 2X mini triangles: classify only writes one 32-byte record per mini triangle, k_mini_vertices generates the vertices
+  uint4*    miniList;   // [maxMini][2]: {instanceID, firstLocalVertex, i0|i1<<8|i2<<16, v0} {v1, v2, cfg, first vertex in genVertices}
+  uint32_t  maxMini;
   // blas helpers
   uint32_t* segLo;     // [TC_MAX_SEGMENTS+1][numInstances]
   uint32_t* rankBase;  // [TC_MAX_SEGMENTS+1][numInstances]

@@ -439,32 +439,6 @@ __device__ __forceinline__ F3 generate_vertex(const Params& p, const BaseTriangl
 // cluster_classify
 // ============================================================================================================
 
-// cold path of cluster_classify kept out of line (its register footprint must not limit the occupancy of the hot path):
-// the 3..6 displaced vertices of one 2X mini triangle (cluster_classify.comp.glsl:817-875)
-static __device__ __noinline__ void emit_mini_vertices(const tc_RenderInstance* inst, const tc_FrameConstants* view, const DeviceTexture* textures,
-                                                        uint32_t numTextures, uint32_t flags, const uint32_t* tblVertices, uint32_t firstLocalVertex,
-                                                        uint32_t i0, uint32_t i1, uint32_t i2, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t cfg,
-                                                        uint32_t firstPatternVertex, uint32_t numPatternVertices, uint32_t instanceID, float* dst)
-{
-  // rebuild the few Params members the shared helpers need (passing the kernel parameter block by reference would spill it)
-  Params q;
-  q.view        = view;
-  q.numTextures = numTextures;
-  q.flags       = flags;
-  q.textures    = textures;
-  const uint32_t vtxEnc[3] = {v0, v1, v2};
-  BaseTriangle   bt;
-  setup_base_triangle(q, *inst, firstLocalVertex, i0, i1, i2, vtxEnc, bt);
-  const DisplacementConsts dc = displacement_consts(q, *inst);
-  const bool  flipped = (cfg & TC_CONFIG_FLIPPED_BIT) != 0;
-  const float geoSize = inst->geoHi[3];
-  for(uint32_t vert = 0; vert < numPatternVertices; vert++)
-  {
-    F3 o = generate_vertex(q, bt, dc, __ldg(&tblVertices[firstPatternVertex + vert]), flipped, instanceID, geoSize);
-    dst[vert * 3 + 0] = o.x; dst[vert * 3 + 1] = o.y; dst[vert * 3 + 2] = o.z;
-  }
-}
-
 // cold path: procedural ripple of one vertex (displacement.glsl:106-120), kept out of line because of its trig slow paths
 static __device__ __noinline__ F3 ripple_vertex(const tc_FrameConstants* view, F3 o, uint32_t instanceID, float geoSize)
 {
@@ -988,6 +962,24 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
                        || (transDataOffset + basic32 > p.maxGenDataBytes) || (transPartOffset + miniPartSize > p.maxPartTriangles);
           uint32_t transOffset = run.v[T_TRANS] + batchIdx;
 
+          {  // vertices are generated by k_mini_vertices from one 32-byte record per mini triangle (any order: the record
+             // carries its destination); one counter increment per 32-triangle iteration
+            const bool     emitV    = mini && !failB;
+            const uint32_t voteEmit = __ballot_sync(0xffffffffu, emitV);
+            if(voteEmit)
+            {
+              uint32_t baseIdx = 0;
+              if(lane == uint32_t(__ffs(voteEmit) - 1))
+                baseIdx = atomicAdd(&p.state->miniCount, uint32_t(__popc(voteEmit)));
+              baseIdx = __shfl_sync(0xffffffffu, baseIdx, __ffs(voteEmit) - 1);
+              const uint32_t idx = baseIdx + __popc(voteEmit & lanemask_lt());
+              if(emitV && idx < p.maxMini)
+              {
+                p.miniList[size_t(idx) * 2 + 0] = make_uint4(instanceID, firstLocalVertex, i0 | (i1 << 8) | (i2 << 16), v0);
+                p.miniList[size_t(idx) * 2 + 1] = make_uint4(v1, v2, cfg, transVertexOffset + relMini * miniVertices);
+              }
+            }
+          }
           if(mini && !failB)
           {
             const unsigned long long vertexBuffer = genVerticesAddr + (unsigned long long)(uint32_t)(transVertexOffset * 4u * 3u);
@@ -1017,8 +1009,6 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
             uint32_t baseTris      = numTrisInclusive - numTris - firstTris;
             uint32_t packedFactors = (f0 - 1) | ((f1 - 1) << 1) | ((f2 - 1) << 2);  // un-rotated factors
             const bool flipped = (cfg & TC_CONFIG_FLIPPED_BIT) != 0;
-            emit_mini_vertices(inst, p.view, p.textures, p.numTextures, p.flags, p.tblVertices, firstLocalVertex, i0, i1, i2, v0, v1, v2, cfg, entry.firstVertex,
-                               entry.numVertices, instanceID, genVertices + size_t(transVertexOffset + relMini * miniVertices) * 3);
             uint32_t  indexOffset      = (transVertexOffset + miniBatchVertices) * 4u * 3u;
             uint32_t  triMappingOffset = transPartOffset * (24u / 2u) + (8u / 2u);
             uint16_t* mappings         = reinterpret_cast<uint16_t*>(transTriMappings);
@@ -1158,6 +1148,72 @@ __device__ __forceinline__ ScanTuple warp_inclusive_tuple(ScanTuple t)
       t.add(o);
   }
   return t;
+}
+
+// ============================================================================================================
+// Vertices of the 2X mini triangles (cluster_classify.comp.glsl:817-875), deferred out of cluster_classify.
+// A mini triangle has at most 6 pattern vertices = exactly ONE slot of the instantiate evaluator: lane = mini triangle,
+// the lane builds the 60-word record (power-basis PN, folded affine maps) in its private shared-memory slot and
+// evaluates it with packed fp32 arithmetic and batched texture gathers.  Inside cluster_classify the same work ran at
+// 16 warps/SM behind a serial per-vertex gather chain and made up 2.6 of the 2.9 ms of BASELINE config 5.
+// ============================================================================================================
+
+constexpr int MINI_WARPS = 4;
+
+template <int TEX, bool ANIM>
+__global__ void __launch_bounds__(MINI_WARPS * 32, 5) k_mini_vertices(Params p)
+{
+  pdl_prologue();
+  extern __shared__ __align__(16) float miniSmem[];
+  static_assert(TC_TESS_2X_MINI_VERTICES == kInstantiateSlot, "a 2X mini triangle is one slot of the slotted pattern table");
+  const uint32_t warp = __reduce_max_sync(0xffffffffu, threadIdx.x >> 5), lane = lane_id();
+  float* rec = miniSmem + size_t(warp) * 32 * TC_REC_WORDS + lane * TC_REC_WORDS;
+  const uint32_t count = min(p.state->miniCount, p.maxMini);
+  float* genVertices = reinterpret_cast<float*>(p.build->genVertices);
+  const cudaTextureObject_t uniformTex = TEX == 1 ? p.texturesC[0].gather : 0;
+  const uint32_t warpsTotal = gridDim.x * MINI_WARPS;
+  for(uint32_t base = (blockIdx.x * MINI_WARPS + warp) * 32; base < count; base += warpsTotal * 32)
+  {
+    const uint32_t idx = base + lane;
+    if(idx < count)
+    {
+      const uint4 a = __ldcs(&p.miniList[size_t(idx) * 2]), b = __ldcs(&p.miniList[size_t(idx) * 2 + 1]);
+      const uint32_t instanceID = a.x, cfg = b.z;
+      const uint32_t vtxEnc[3] = {a.w, b.x, b.y};
+      const uint32_t cfgIdx   = tess_configIndex(cfg) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1);
+      const uint32_t slotBase = __ldg(&p.tblSlotBase[cfgIdx]);
+      const uint32_t numV     = tess_entry(p, cfg).numVertices;
+      const tc_RenderInstance& inst = p.instances[instanceID];
+      build_part_record(p, inst, instanceID, a.y, a.z & 0xFF, (a.z >> 8) & 0xFF, (a.z >> 16) & 0xFF, vtxEnc, (cfg & TC_CONFIG_FLIPPED_BIT) != 0, slotBase, 1u, 0u, rec);
+      float4 q[3];
+#pragma unroll
+      for(int k = 0; k < 3; k++)
+        q[k] = __ldg(p.tblSlots + slotBase + k);  // one slot: the three planes are adjacent
+      float2 X[3], Y[3], Z[3];
+      eval_part_pairs<TEX, 3>(reinterpret_cast<const float4*>(rec), q, X, Y, Z, uniformTex);  // (reads only this lane's own record)
+      F3 o[6];
+#pragma unroll
+      for(int i = 0; i < 3; i++)
+      {
+        o[2 * i]     = {X[i].x, Y[i].x, Z[i].x};
+        o[2 * i + 1] = {X[i].y, Y[i].y, Z[i].y};
+      }
+      if(ANIM)
+      {
+        const float geoSize = inst.geoHi[3];
+#pragma unroll
+        for(int i = 0; i < 6; i++)
+          o[i] = ripple_deform(p.view[0], o[i], instanceID, geoSize);
+      }
+      float* dst = genVertices + size_t(b.w) * 3;
+#pragma unroll
+      for(int i = 0; i < 6; i++)
+        if(uint32_t(i) < numV)
+        {
+          __stcs(dst + i * 3 + 0, o[i].x); __stcs(dst + i * 3 + 1, o[i].y); __stcs(dst + i * 3 + 2, o[i].z);
+        }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(CSCAN_THREADS) k_classify_scan(Params p, const uint32_t* epochCounter)
@@ -2656,13 +2712,30 @@ void launch_clusters_cull(const Params& p, cudaStream_t s)
   uint32_t n = p.totalClusters < p.maxVisibleClusters ? p.totalClusters : p.maxVisibleClusters;
   launch_pdl(k_clusters_cull, (n + 255) / 256 + (n == 0 ? 1 : 0), 256, 0, s, p);
 }
-void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s)
+size_t mini_smem_bytes() { return size_t(MINI_WARPS) * 32 * TC_REC_WORDS * 4; }
+
+void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, uint32_t miniGrid, cudaStream_t s)
 {
   const size_t smem = classify_smem_bytes(p.clusterVertices, p.clusterTriangles);
   launch_pdl(k_cluster_classify<0>, grid, CLASSIFY_THREADS, smem, s, p);
   launch_pdl(k_classify_scan, 148, CSCAN_THREADS, 0, s, p, epochCounter);
   launch_pdl(k_cluster_classify<1>, grid, CLASSIFY_THREADS, smem, s, p);
   launch_pdl(k_cluster_classify<2>, grid, CLASSIFY_THREADS, smem, s, p);
+  if(p.flags & TC_FLAG_TRANSIENT_2X)
+  {  // vertices of the 2X mini triangles recorded by the kernel above
+    const int    tex  = p.numTextures == 0 ? 0 : (p.numTextures == 1 ? 1 : 2);
+    const bool   anim = (p.flags & TC_FLAG_ANIMATION) != 0;
+    const size_t ms   = mini_smem_bytes();
+    switch(tex * 2 + int(anim))
+    {
+      case 0: launch_pdl(k_mini_vertices<0, false>, miniGrid, MINI_WARPS * 32, ms, s, p); break;
+      case 1: launch_pdl(k_mini_vertices<0, true>, miniGrid, MINI_WARPS * 32, ms, s, p); break;
+      case 2: launch_pdl(k_mini_vertices<1, false>, miniGrid, MINI_WARPS * 32, ms, s, p); break;
+      case 3: launch_pdl(k_mini_vertices<1, true>, miniGrid, MINI_WARPS * 32, ms, s, p); break;
+      case 4: launch_pdl(k_mini_vertices<2, false>, miniGrid, MINI_WARPS * 32, ms, s, p); break;
+      default: launch_pdl(k_mini_vertices<2, true>, miniGrid, MINI_WARPS * 32, ms, s, p); break;
+    }
+  }
 }
 void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32_t pass, bool lastPass, uint32_t grid, cudaStream_t s)
 {

@@ -45,7 +45,7 @@ size_t   frame_state_bytes();
 void launch_frame_setup(const Params& p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter, cudaStream_t s);
 void launch_instances_classify(const Params& p, cudaStream_t s);
 void launch_clusters_cull(const Params& p, cudaStream_t s);
-void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s);
+void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, uint32_t miniGrid, cudaStream_t s);
 void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32_t pass, bool lastPass, uint32_t grid, cudaStream_t s);
 void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s);
 void launch_blas(const Params& p, const uint32_t* epochCounter, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s);
