@@ -71,6 +71,7 @@ struct tc_context
   void*             dClassTuples = nullptr;
   uint32_t*         dFactorStash = nullptr;
   uint32_t*         dClassMeta = nullptr;
+  uint32_t*         dClusterVertexDst = nullptr;
   FrameStaging*     dFrame     = nullptr;
   FrameStaging*     hFrame     = nullptr;  // pinned
   tc_shard_counts*  dShardCounts = nullptr;
@@ -271,6 +272,7 @@ void fill_params(tc_context* c)
   p.classTuples        = c->dClassTuples;
   p.factorStash        = c->dFactorStash;
   p.classMeta          = c->dClassMeta;
+  p.clusterVertexDst   = c->dClusterVertexDst;
   p.segLo              = c->segLo;
   p.rankBase           = c->rankBase;
   p.shardBase          = c->dShardBase;
@@ -340,7 +342,7 @@ int enqueue_build(tc_context* c)
     uint32_t grid = std::max(1u, (std::min(c->totalClusters, c->maxVisible) + tc::classify_tile_clusters() - 1) / tc::classify_tile_clusters());
     grid          = std::min(grid, uint32_t(c->numSMs) * 32u);
     tc::launch_cluster_classify(p, c->dEpoch, grid, uint32_t(c->numSMs * 5), s);  // count -> scan -> emit (cluster level) -> emit (triangle level) -> 2X mini vertices
-    launches += (c->cfg.flags & TC_FLAG_TRANSIENT_2X) ? 5 : 4;
+    launches += (c->cfg.flags & TC_FLAG_TRANSIENT_2X) ? 6 : 5;
   }
   {
     StageScope sc(c, TC_STAGE_SPLIT);
@@ -470,6 +472,7 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   TRY_RC(dalloc(c->dClassTuples, size_t(c->maxVisible) * tc::classify_tuple_bytes()));
   TRY_RC(dalloc(c->dFactorStash, size_t(c->maxVisible) * config->clusterTriangles * 12));
   TRY_RC(dalloc(c->dClassMeta, size_t(c->maxVisible) * 4));
+  TRY_RC(dalloc(c->dClusterVertexDst, size_t(c->maxVisible) * 4));
   // one 32-byte record per 2X mini triangle: a batch of 8 occupies 56 vertex slots of genVertices
   c->maxMini = (config->flags & TC_FLAG_TRANSIENT_2X) ? uint32_t(std::min<uint64_t>(uint64_t(c->maxVerts) / 7 + 64, 0xFFFFFFF0ull)) : 0u;
   if(c->maxMini)
@@ -524,7 +527,7 @@ TC_API void tc_destroy(tc_context* c)
     cudaStreamSynchronize(c->stream);
   drop_graph(c);
   free_scene(c);
-  dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dFrame);
+  dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dClusterVertexDst); dfree(c->dFrame);
   dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState); dfree(c->dMiniList); dfree(c->dMailbox); dfree(c->dShardStatus);
   if(c->hFrame)
     cudaFreeHost(c->hFrame);

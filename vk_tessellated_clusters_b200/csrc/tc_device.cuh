@@ -94,6 +94,7 @@ struct Params
   void*     classTuples;   // ScanTuple[maxVisibleClusters]: counts, then (in place) exclusive prefixes
   uint32_t* factorStash;   // [maxVisibleClusters][clusterTriangles][3]: factor | local vertex index << 24
   uint32_t* classMeta;     // [maxVisibleClusters]: number of triangles that need no tessellation (simpleCount)
+  uint32_t* clusterVertexDst;  // [maxVisibleClusters]: first vertex in genVertices of the cluster's displaced vertex copy, ~0u: none
   // 2X mini triangles: classify only writes one 32-byte record per mini triangle, k_mini_vertices generates the vertices
   uint4*    miniList;   // [maxMini][2]: {instanceID, firstLocalVertex, i0|i1<<8|i2<<16, v0} {v1, v2, cfg, first vertex in genVertices}
   uint32_t  maxMini;

@@ -465,8 +465,10 @@ __device__ __forceinline__ void flush_floats(const float* stage, float* dst, uin
 #ifndef TC_CLASSIFY_WARPS
 #define TC_CLASSIFY_WARPS 8
 #endif
+// triangle-level emit: 4 CTAs/SM at 64 registers since the 2X mini vertices moved to their own kernel
+// (measured config 2 / 5 / 3: 0.633 / 2.82 / 2.61 ms at 2 CTAs -> 0.622 / 2.68 / 2.39 ms at 4)
 #ifndef TC_CLASSIFY_MIN_CTAS
-#define TC_CLASSIFY_MIN_CTAS 2
+#define TC_CLASSIFY_MIN_CTAS 4
 #endif
 constexpr int CLASSIFY_WARPS   = TC_CLASSIFY_WARPS;
 constexpr int CLASSIFY_THREADS = CLASSIFY_WARPS * 32;
@@ -514,7 +516,6 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
   tc_ClusterInfo*             visibleClusters = reinterpret_cast<tc_ClusterInfo*>(p.build->visibleClusters);
   tc_TessTriangleInfo*        splitTriangles  = reinterpret_cast<tc_TessTriangleInfo*>(p.build->splitTriangles);
   tc_TessTriangleInfo*        partTriangles   = reinterpret_cast<tc_TessTriangleInfo*>(p.build->partTriangles);
-  float*                      genVertices     = reinterpret_cast<float*>(p.build->genVertices);
   uint8_t*                    transTriIndices = reinterpret_cast<uint8_t*>(p.build->genVertices);
   uint8_t*                    transTriMappings = reinterpret_cast<uint8_t*>(p.build->partTriangles);
   tc_TemplateInstantiateInfo* tempInstantiations = reinterpret_cast<tc_TemplateInstantiateInfo*>(p.build->tempInstantiations);
@@ -714,6 +715,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
       {
         st_tuple(&tuples[vi], tup);
         p.classMeta[vi] = simpleCount;
+        p.clusterVertexDst[vi] = ~0u;  // set by the cluster-level emit kernel when the cluster gets a displaced vertex copy
       }
       accClusterLevel += clusterLevel ? 1u : 0u;
       accTriangleLevel += (simpleCount != numTriangles) ? 1u : 0u;
@@ -733,7 +735,6 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
       uint32_t  succTemp = 0, succTrans = 0, totalTris = 0, validParts = 0;
       const uint32_t instanceID = cinfo.instanceID, clusterID = cinfo.clusterID;
       const DisplacementConsts dc = displacement_consts(p, *inst);
-      const float geoSize = inst->geoHi[3];
 
       if(clusterLevel)
       {  // :271-538
@@ -803,33 +804,9 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
           }
           totalTris += simpleCount;
 
-          // displaced copy of the cluster vertices (:465-488): staged in shared memory, flushed with 128-bit stores
-          {
-            const float* positions = reinterpret_cast<const float*>(inst->positions);
-            const float* normals   = reinterpret_cast<const float*>(inst->normals);
-            const float* texcoords = reinterpret_cast<const float*>(inst->texcoords);
-            const size_t   dstFloat = size_t(vertexOffset) * 3;
-            const uint32_t shift    = uint32_t(dstFloat & 3);
-            float*         sOut     = sWorld;  // unused in emit mode: maxV * 4 floats >= maxV * 3 + 3
-            for(uint32_t v = lane; v < numVertices; v += 32)
-            {
-              const uint32_t vertexIndex = firstLocalVertex + v;
-              F3 o = ld_f3(positions, vertexIndex);
-              if(dc.texture >= 0)
-              {
-                const F3    n  = ld_f3(normals, vertexIndex);
-                const float tu = __ldg(texcoords + size_t(vertexIndex) * 2), tv = __ldg(texcoords + size_t(vertexIndex) * 2 + 1);
-                const float h  = fmaf(sample_displacement_gather(p.texturesC[dc.texture], tu, tv), dc.scale, dc.offset);
-                o = fma3(n, h * fast_rsqrt(dot3(n, n)), o);
-              }
-              if(flag_animation(p))
-                o = ripple_vertex(p.view, o, instanceID, geoSize);
-              sOut[shift + v * 3 + 0] = o.x; sOut[shift + v * 3 + 1] = o.y; sOut[shift + v * 3 + 2] = o.z;
-            }
-            __syncwarp();
-            flush_floats(sOut, genVertices + dstFloat, shift, numVertices * 3, lane);
-            __syncwarp();
-          }
+          // displaced copy of the cluster vertices (:465-488): generated by k_cluster_vertices, here only its destination
+          if(lane == 0)
+            p.clusterVertexDst[vi] = vertexOffset;
           if(transient1X)
           {  // ordered export of the simple triangles (:497-534)
             uint32_t indexOffset      = (vertexOffset + numVertices) * 4u * 3u;
@@ -1148,6 +1125,88 @@ __device__ __forceinline__ ScanTuple warp_inclusive_tuple(ScanTuple t)
       t.add(o);
   }
   return t;
+}
+
+// ============================================================================================================
+// Displaced copies of cluster vertices (cluster_classify.comp.glsl:465-488: full clusters of tessellation-free or
+// hidden instances, 1X subset clusters), deferred out of cluster_classify.  A warp takes 32 consecutive visible
+// clusters, fetches their destinations and descriptors lane-parallel and then generates the vertices of every
+// cluster that has a copy: lane = vertex, both vertices of a lane (clusters hold <= 64) in flight together.  Plain
+// streaming work at high occupancy instead of a serial per-vertex gather chain inside the 80-register emit kernel.
+// ============================================================================================================
+
+__global__ void __launch_bounds__(256) k_cluster_vertices(Params p)
+{
+  pdl_prologue();
+  if(p.state->clusterLevelWork == 0)
+    return;
+  const uint32_t lane = lane_id(), warpsTotal = gridDim.x * (blockDim.x >> 5);
+  const uint32_t numVisible = p.build->visibleClusterCounter;
+  const tc_ClusterInfo* visibleClusters = reinterpret_cast<const tc_ClusterInfo*>(p.build->visibleClusters);
+  float* genVertices = reinterpret_cast<float*>(p.build->genVertices);
+  const bool anim = flag_animation(p);
+  for(uint32_t chunk = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; chunk < numVisible; chunk += warpsTotal * 32)
+  {
+    uint32_t dstL = ~0u, instL = 0, firstL = 0, numL = 0;
+    if(chunk + lane < numVisible)
+    {
+      dstL = __ldcs(&p.clusterVertexDst[chunk + lane]);
+      if(dstL != ~0u)
+      {
+        const tc_ClusterInfo ci = visibleClusters[chunk + lane];
+        const uint4 ch = __ldg(reinterpret_cast<const uint4*>(p.instances[ci.instanceID].clusters) + ci.clusterID);
+        instL = ci.instanceID; firstL = ch.z; numL = ch.x & 0xFFFF;
+      }
+    }
+    uint32_t mask = __ballot_sync(0xffffffffu, dstL != ~0u);
+    while(mask)
+    {
+      const uint32_t src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const uint32_t dst = __shfl_sync(0xffffffffu, dstL, src), instanceID = __shfl_sync(0xffffffffu, instL, src);
+      const uint32_t first = __shfl_sync(0xffffffffu, firstL, src), numVertices = __shfl_sync(0xffffffffu, numL, src);
+      const tc_RenderInstance* inst = &p.instances[instanceID];
+      const DisplacementConsts dc = displacement_consts(p, *inst);
+      const float* positions = reinterpret_cast<const float*>(inst->positions);
+      const float* normals   = reinterpret_cast<const float*>(inst->normals);
+      const float2* texcoords = reinterpret_cast<const float2*>(inst->texcoords);
+      for(uint32_t v0 = 0; v0 < numVertices; v0 += 64)
+      {
+        F3     o[2], n[2];
+        float2 tc[2];
+        bool   ok[2];
+#pragma unroll
+        for(int k = 0; k < 2; k++)
+        {
+          const uint32_t v = v0 + lane + 32 * k;
+          ok[k] = v < numVertices;
+          if(ok[k])
+          {
+            o[k] = ld_f3(positions, first + v);
+            if(dc.texture >= 0)
+            {
+              n[k]  = ld_f3(normals, first + v);
+              tc[k] = __ldg(texcoords + first + v);
+            }
+          }
+        }
+#pragma unroll
+        for(int k = 0; k < 2; k++)
+          if(ok[k])
+          {
+            if(dc.texture >= 0)
+            {
+              const float h = fmaf(sample_displacement_gather(p.textures[dc.texture], tc[k].x, tc[k].y), dc.scale, dc.offset);
+              o[k] = fma3(n[k], h * fast_rsqrt(dot3(n[k], n[k])), o[k]);
+            }
+            if(anim)
+              o[k] = ripple_vertex(p.view, o[k], instanceID, inst->geoHi[3]);
+            float* d = genVertices + size_t(dst + v0 + lane + 32 * k) * 3;
+            __stcs(d + 0, o[k].x); __stcs(d + 1, o[k].y); __stcs(d + 2, o[k].z);
+          }
+      }
+    }
+  }
 }
 
 // ============================================================================================================
@@ -2721,6 +2780,7 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
   launch_pdl(k_classify_scan, 148, CSCAN_THREADS, 0, s, p, epochCounter);
   launch_pdl(k_cluster_classify<1>, grid, CLASSIFY_THREADS, smem, s, p);
   launch_pdl(k_cluster_classify<2>, grid, CLASSIFY_THREADS, smem, s, p);
+  launch_pdl(k_cluster_vertices, miniGrid, 256, 0, s, p);  // displaced cluster-vertex copies recorded by the cluster-level emit kernel
   if(p.flags & TC_FLAG_TRANSIENT_2X)
   {  // vertices of the 2X mini triangles recorded by the kernel above
     const int    tex  = p.numTextures == 0 ? 0 : (p.numTextures == 1 ? 1 : 2);
