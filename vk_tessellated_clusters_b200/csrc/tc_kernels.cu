@@ -1127,6 +1127,21 @@ __device__ __forceinline__ ScanTuple warp_inclusive_tuple(ScanTuple t)
   return t;
 }
 
+// lane index of the item that owns virtual child thread t: first lane whose inclusive end offset exceeds t
+__device__ __forceinline__ uint32_t find_item(uint32_t endOffset, uint32_t t)
+{
+  uint32_t lo = 0;  // answer in [0, 31]
+#pragma unroll
+  for(int step = 16; step > 0; step >>= 1)
+  {
+    uint32_t probe = lo + step - 1;
+    uint32_t e     = __shfl_sync(0xffffffffu, endOffset, probe);
+    if(e <= t)
+      lo += step;
+  }
+  return min(lo, 31u);
+}
+
 // ============================================================================================================
 // Displaced copies of cluster vertices (cluster_classify.comp.glsl:465-488: full clusters of tessellation-free or
 // hidden instances, 1X subset clusters), deferred out of cluster_classify.  A warp takes 32 consecutive visible
@@ -1135,76 +1150,110 @@ __device__ __forceinline__ ScanTuple warp_inclusive_tuple(ScanTuple t)
 // streaming work at high occupancy instead of a serial per-vertex gather chain inside the 80-register emit kernel.
 // ============================================================================================================
 
-__global__ void __launch_bounds__(256) k_cluster_vertices(Params p)
+// TEX: 0 no textures, 1 one texture (warp-uniform handle from the parameter block), 2 per-instance handles
+template <int TEX>
+__global__ void __launch_bounds__(256, 2) k_cluster_vertices(Params p)
 {
   pdl_prologue();
   if(p.state->clusterLevelWork == 0)
     return;
+  constexpr int U = 4;  // independent vertices per lane and step: their loads, then their gathers, are in flight together
   const uint32_t lane = lane_id(), warpsTotal = gridDim.x * (blockDim.x >> 5);
   const uint32_t numVisible = p.build->visibleClusterCounter;
   const tc_ClusterInfo* visibleClusters = reinterpret_cast<const tc_ClusterInfo*>(p.build->visibleClusters);
   float* genVertices = reinterpret_cast<float*>(p.build->genVertices);
   const bool anim = flag_animation(p);
+  const cudaTextureObject_t uniformTex = TEX == 1 ? p.texturesC[0].gather : 0;
+  const float uniW = TEX == 1 ? float(p.texturesC[0].width) : 1.0f, uniH = TEX == 1 ? float(p.texturesC[0].height) : 1.0f;
+  const float viewScale = p.view[0].displacementScale, viewOffset = p.view[0].displacementOffset;
   for(uint32_t chunk = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; chunk < numVisible; chunk += warpsTotal * 32)
   {
-    uint32_t dstL = ~0u, instL = 0, firstL = 0, numL = 0;
+    // lane = cluster: destination and descriptor of 32 consecutive visible clusters
+    uint32_t dstL = 0, instL = 0, firstL = 0, numL = 0;
     if(chunk + lane < numVisible)
     {
-      dstL = __ldcs(&p.clusterVertexDst[chunk + lane]);
-      if(dstL != ~0u)
+      const uint32_t d = __ldcs(&p.clusterVertexDst[chunk + lane]);
+      if(d != ~0u)
       {
         const tc_ClusterInfo ci = visibleClusters[chunk + lane];
         const uint4 ch = __ldg(reinterpret_cast<const uint4*>(p.instances[ci.instanceID].clusters) + ci.clusterID);
-        instL = ci.instanceID; firstL = ch.z; numL = ch.x & 0xFFFF;
+        dstL = d; instL = ci.instanceID; firstL = ch.z; numL = ch.x & 0xFFFF;
       }
     }
-    uint32_t mask = __ballot_sync(0xffffffffu, dstL != ~0u);
-    while(mask)
+    const uint32_t endV = warp_inclusive_add(numL), startV = endV - numL, total = __shfl_sync(0xffffffffu, endV, 31);
+    // lane = vertex of the chunk's flat vertex list
+    for(uint32_t t0 = 0; t0 < total; t0 += 32 * U)
     {
-      const uint32_t src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const uint32_t dst = __shfl_sync(0xffffffffu, dstL, src), instanceID = __shfl_sync(0xffffffffu, instL, src);
-      const uint32_t first = __shfl_sync(0xffffffffu, firstL, src), numVertices = __shfl_sync(0xffffffffu, numL, src);
-      const tc_RenderInstance* inst = &p.instances[instanceID];
-      const DisplacementConsts dc = displacement_consts(p, *inst);
-      const float* positions = reinterpret_cast<const float*>(inst->positions);
-      const float* normals   = reinterpret_cast<const float*>(inst->normals);
-      const float2* texcoords = reinterpret_cast<const float2*>(inst->texcoords);
-      for(uint32_t v0 = 0; v0 < numVertices; v0 += 64)
-      {
-        F3     o[2], n[2];
-        float2 tc[2];
-        bool   ok[2];
+      bool     ok[U];
+      uint32_t instanceID[U], dstVertex[U];
+      F3       o[U], n[U];
+      float2   tc[U];
 #pragma unroll
-        for(int k = 0; k < 2; k++)
+      for(int k = 0; k < U; k++)
+      {
+        const uint32_t t    = t0 + k * 32 + lane;
+        const uint32_t item = find_item(endV, t);
+        const uint32_t v    = t - __shfl_sync(0xffffffffu, startV, item);
+        instanceID[k] = __shfl_sync(0xffffffffu, instL, item);
+        const uint32_t first = __shfl_sync(0xffffffffu, firstL, item);
+        dstVertex[k]  = __shfl_sync(0xffffffffu, dstL, item) + v;
+        ok[k]         = t < total;
+        if(ok[k])
         {
-          const uint32_t v = v0 + lane + 32 * k;
-          ok[k] = v < numVertices;
+          const tc_RenderInstance& inst = p.instances[instanceID[k]];
+          o[k] = ld_f3(reinterpret_cast<const float*>(inst.positions), first + v);
+          if(TEX != 0)
+          {
+            n[k]  = ld_f3(reinterpret_cast<const float*>(inst.normals), first + v);
+            tc[k] = __ldg(reinterpret_cast<const float2*>(inst.texcoords) + first + v);
+          }
+        }
+      }
+      float4 g[U];
+      float  ax[U], ay[U], scale[U], offset[U];
+      if(TEX != 0)
+      {
+#pragma unroll
+        for(int k = 0; k < U; k++)
+        {
+          scale[k] = offset[k] = ax[k] = ay[k] = 0.0f;
+          g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
           if(ok[k])
           {
-            o[k] = ld_f3(positions, first + v);
-            if(dc.texture >= 0)
-            {
-              n[k]  = ld_f3(normals, first + v);
-              tc[k] = __ldg(texcoords + first + v);
+            const tc_RenderInstance& inst = p.instances[instanceID[k]];
+            const int ti = inst.displacementIndex;
+            if(ti >= 0)
+            {  // sample_displacement_gather (same arithmetic), texture state per TEX mode
+              scale[k]  = inst.displacementScale * viewScale;
+              offset[k] = inst.displacementOffset + viewOffset;
+              const float W = TEX == 1 ? uniW : float(p.textures[ti].width), H = TEX == 1 ? uniH : float(p.textures[ti].height);
+              const float x = fmaf(tc[k].x, W, -0.5f), y = fmaf(tc[k].y, H, -0.5f);
+              const float fx = floorf(x), fy = floorf(y);
+              ax[k] = x - fx;
+              ay[k] = y - fy;
+              const float gx = __fdividef(fx + 1.0f, W), gy = __fdividef(fy + 1.0f, H);
+              g[k] = TEX == 1 ? tex2Dgather<float4>(uniformTex, gx, gy, 0) : tex2Dgather<float4>(p.textures[ti].gather, gx, gy, 0);  // (t01, t11, t10, t00)
             }
           }
         }
-#pragma unroll
-        for(int k = 0; k < 2; k++)
-          if(ok[k])
-          {
-            if(dc.texture >= 0)
-            {
-              const float h = fmaf(sample_displacement_gather(p.textures[dc.texture], tc[k].x, tc[k].y), dc.scale, dc.offset);
-              o[k] = fma3(n[k], h * fast_rsqrt(dot3(n[k], n[k])), o[k]);
-            }
-            if(anim)
-              o[k] = ripple_vertex(p.view, o[k], instanceID, inst->geoHi[3]);
-            float* d = genVertices + size_t(dst + v0 + lane + 32 * k) * 3;
-            __stcs(d + 0, o[k].x); __stcs(d + 1, o[k].y); __stcs(d + 2, o[k].z);
-          }
       }
+#pragma unroll
+      for(int k = 0; k < U; k++)
+        if(ok[k])
+        {
+          if(TEX != 0)
+          {
+            const float top = fmaf(g[k].z - g[k].w, ax[k], g[k].w), bot = fmaf(g[k].y - g[k].x, ax[k], g[k].x);
+            const float h   = fmaf(fmaf(bot - top, ay[k], top), scale[k], offset[k]);
+            const tc_RenderInstance& inst = p.instances[instanceID[k]];
+            if(inst.displacementIndex >= 0)
+              o[k] = fma3(n[k], h * fast_rsqrt(dot3(n[k], n[k])), o[k]);
+          }
+          if(anim)
+            o[k] = ripple_vertex(p.view, o[k], instanceID[k], p.instances[instanceID[k]].geoHi[3]);
+          float* d = genVertices + size_t(dstVertex[k]) * 3;
+          __stcs(d + 0, o[k].x); __stcs(d + 1, o[k].y); __stcs(d + 2, o[k].z);
+        }
     }
   }
 }
@@ -1456,20 +1505,6 @@ __device__ __forceinline__ void split_child_corners(const Params& p, uint32_t cf
   }
 }
 
-// lane index of the item that owns virtual child thread t: first lane whose inclusive end offset exceeds t
-__device__ __forceinline__ uint32_t find_item(uint32_t endOffset, uint32_t t)
-{
-  uint32_t lo = 0;  // answer in [0, 31]
-#pragma unroll
-  for(int step = 16; step > 0; step >>= 1)
-  {
-    uint32_t probe = lo + step - 1;
-    uint32_t e     = __shfl_sync(0xffffffffu, endOffset, probe);
-    if(e <= t)
-      lo += step;
-  }
-  return min(lo, 31u);
-}
 
 // BUILD_SETUP_SPLIT_PASS (build_setup.comp.glsl:168-190) or, after the last pass, BUILD_SETUP_INSTANTIATE_TESS (:236-264);
 // executed by exactly one thread after every CTA of the pass has finished
@@ -2780,7 +2815,15 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
   launch_pdl(k_classify_scan, 148, CSCAN_THREADS, 0, s, p, epochCounter);
   launch_pdl(k_cluster_classify<1>, grid, CLASSIFY_THREADS, smem, s, p);
   launch_pdl(k_cluster_classify<2>, grid, CLASSIFY_THREADS, smem, s, p);
-  launch_pdl(k_cluster_vertices, miniGrid, 256, 0, s, p);  // displaced cluster-vertex copies recorded by the cluster-level emit kernel
+  {  // displaced cluster-vertex copies recorded by the cluster-level emit kernel
+    const uint32_t cvGrid = miniGrid / 5 * 2;  // 2 CTAs of 256 threads per SM
+    if(p.numTextures == 0)
+      launch_pdl(k_cluster_vertices<0>, cvGrid, 256, 0, s, p);
+    else if(p.numTextures == 1)
+      launch_pdl(k_cluster_vertices<1>, cvGrid, 256, 0, s, p);
+    else
+      launch_pdl(k_cluster_vertices<2>, cvGrid, 256, 0, s, p);
+  }
   if(p.flags & TC_FLAG_TRANSIENT_2X)
   {  // vertices of the 2X mini triangles recorded by the kernel above
     const int    tex  = p.numTextures == 0 ? 0 : (p.numTextures == 1 ? 1 : 2);
