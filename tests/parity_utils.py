@@ -139,3 +139,45 @@ def make_pair(scene, table, config=None, hiz=None):
     _, sb = gpu.readback()
     orc.set_addresses(sb)
     return gpu, orc
+
+
+class RebasedReference:
+    """oracle/_ref -- the reference's own shaders executed on the host (oracle/ref_binding.py) -- presented with the CUDA
+    context's device addresses, so compare_frame() can check the CUDA path against the reference's code directly.
+    The shaders dereference real host pointers, so the records they write hold host addresses; every address field is
+    moved from the host buffer's base to the corresponding device buffer's base."""
+
+    _REBASE = {  # buffer -> [(field or None, SceneBuilding base field)]
+        "tempInstantiations": [("vertexBufferAddress", "genVertices")],
+        "tempClusterAddresses": [(None, "genClusterData")],
+        "transBuilds": [("vertexBuffer", "genVertices"), ("indexBuffer", "genVertices")],
+        "transClusterAddresses": [(None, "genClusterData")],
+        "blasBuildInfos": [("clusterReferences", "blasClusterAddresses")],
+        "blasClusterAddresses": [(None, "genClusterData")],
+    }
+
+    def __init__(self, ref, gpu_building):
+        self.ref, self.gpu_sb = ref, gpu_building
+        self.config, self.num_instances = ref.config, ref.num_instances
+
+    def readback(self):
+        rb, sb = self.ref.readback()
+        sb = sb.copy()
+        for _, (_, fld) in api.BUFFERS.items():
+            sb[fld] = self.gpu_sb[fld]
+        for fld in ("genClusterData", "transTriMappings", "transTriIndices", "basicClusterSizes", "blasBuildData", "fullClusters"):
+            sb[fld] = self.gpu_sb[fld]
+        return rb, sb
+
+    def buffer(self, name, count=None, building=None):
+        a = self.ref.buffer(name, count)
+        if name in self._REBASE and len(a):
+            _, rsb = self.ref.readback()
+            for fld, base in self._REBASE[name]:
+                delta = np.uint64((int(self.gpu_sb[base]) - int(rsb[base])) % (1 << 64))  # modulo 2^64, like the addition below
+                with np.errstate(over="ignore"):
+                    if fld is None:
+                        a = a + delta
+                    else:
+                        a[fld] = a[fld] + delta
+        return a

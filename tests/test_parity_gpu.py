@@ -26,6 +26,41 @@ def test_parity_case(name, table, oracle_lib):
         orc.close()
 
 
+# cases whose reference-shader library (oracle/_ref, built by oracle/ref/translate.py where /root/reference exists) is checked
+# against the CUDA path DIRECTLY: no oracle in between
+REFERENCE_SHADER_CASES = ["plane", "split", "mini", "only_1x", "linear_no_transient", "icosphere", "far_field", "culling", "overflow_vertices", "overflow_split"]
+
+
+@pytest.mark.parametrize("name", REFERENCE_SHADER_CASES)
+def test_parity_against_reference_shaders(name, table):
+    """CUDA path vs the reference's own compute shaders run by the host SIMT emulator: counters, every record buffer byte
+    for byte (addresses rebased), vertices within 1e-5 relative."""
+    from oracle import ref_binding
+    from tests.parity_utils import RebasedReference
+
+    scene, fcs, cfg, hiz = case(name)
+    try:
+        ref = ref_binding.ReferenceShaders(cfg, len(scene.textures) > 0)
+    except SystemExit as e:
+        pytest.skip(f"oracle/_ref variant not prebuilt: {e}")
+    gpu = api.TessClusters(cfg)
+    try:
+        for b in (gpu, ref):
+            b.set_tess_table(table)
+            b.set_scene(scene)
+            if hiz is not None:
+                b.set_hiz(*hiz)
+        gpu.set_driver_standin(0)  # CLAS sizes come from the driver, which the reference shaders do not run either
+        gpu.frame(fcs)
+        ref.frame(fcs)
+        _, sb = gpu.readback()
+        stats = compare_frame(gpu, RebasedReference(ref, sb), scene_scale=scene.radius)
+        assert stats["triangles"] > 0
+    finally:
+        gpu.close()
+        ref.close()
+
+
 def test_moving_camera_sequence(table, oracle_lib):
     """Several different frames back to back (viewLast = previous frame, as the app does)."""
     from vk_tessellated_clusters_b200 import scenes as S
