@@ -5,10 +5,16 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  The product path
  * (vk_tessellated_clusters_b200/csrc) never includes, links or calls anything in this directory.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path, and its own
- * implementation is GLSL executed by a Vulkan driver (not runnable here: no glslang/shaderc/Vulkan/GPU).
- * The pins that exist are (a) the README's documented encodings, (b) the static_assert'ed struct sizes and
- * (c) structural invariants of the tessellation table -- all checked in tests/test_oracle_table.py.
+ * PARITY PINNED AGAINST THE REFERENCE'S OWN SHADERS.  The reference ships no tests, golden vectors or fixtures for this
+ * path and its implementation is GLSL executed by a Vulkan driver -- but the eight compute shaders of the path DO run
+ * here: oracle/ref/translate.py compiles /root/reference/shaders/*.comp.glsl (read where they lie) with g++ on top of a
+ * GLSL run-time + SIMT emulator (oracle/ref/glsl_shim.hpp) into oracle/_ref/, and tests/test_reference_shaders.py
+ * checks this file against them on 19 scene cases: all counters equal, every record buffer identical byte for byte
+ * (stronger than the order-normalised multiset north_star asks for), generated vertices within 2.4e-7.  What stays
+ * DEFINED rather than pinned: round() ties (to even), the displacement / HiZ samplers (software, see below), and the two
+ * overflow cases where the reference itself reads unwritten memory (DESIGN.md section 3 "Deviation").  Further pins:
+ * (a) the README's documented encodings, (b) the static_assert'ed struct sizes, (c) structural invariants of the
+ * tessellation table -- tests/test_oracle_table.py.
  *
  * What it follows, function by function (paths relative to /root/reference):
  *   shaders/tessellation.glsl                     -> enc/dec barycentrics, factors, config, table reads
