@@ -1260,67 +1260,191 @@ __global__ void __launch_bounds__(256, 2) k_cluster_vertices(Params p)
 
 // ============================================================================================================
 // Vertices of the 2X mini triangles (cluster_classify.comp.glsl:817-875), deferred out of cluster_classify.
-// A mini triangle has at most 6 pattern vertices = exactly ONE slot of the instantiate evaluator: lane = mini triangle,
-// the lane builds the 60-word record (power-basis PN, folded affine maps) in its private shared-memory slot and
-// evaluates it with packed fp32 arithmetic and batched texture gathers.  Inside cluster_classify the same work ran at
-// 16 warps/SM behind a serial per-vertex gather chain and made up 2.6 of the 2.9 ms of BASELINE config 5.
+// A mini triangle is a WHOLE base triangle with edge factors <= 2, so every pattern vertex is either a base corner or
+// the midpoint of a base edge, and the general evaluator (PN control net -> power basis -> cubic per vertex) collapses
+// to a closed form:  corner: the base vertex itself;  midpoint of the edge P->Q with unit normals Np, Nq:
+//     b(1/2,1/2) = (P + Q + 3 C1 + 3 C2) / 8,  C1 = proj(P + e/3 | plane P,Np),  C2 = proj(P + 2e/3 | plane Q,Nq),  e = Q - P
+//                = (P + Q)/2 + (dot(e,Nq) Nq - dot(e,Np) Np) / 8          (displacement.glsl:47-104 at u = v = 1/2)
+// (linear: (P+Q)/2), then the usual displacement along normalize(Np + Nq) with the texel at (uvP + uvQ)/2.
+// lane = mini triangle: three corners always, a midpoint per edge of factor 2; every candidate knows its pattern index
+// (a nibble per candidate, found by scanning the <= 6 pattern vertices), so all register indexing is static and the
+// <= 6 texture gathers of a lane are in flight together.  The general evaluator took 703 warp instructions per 32 mini
+// triangles for the record build alone (profiles/r01_summary.md).
 // ============================================================================================================
 
 constexpr int MINI_WARPS = 4;
 
 template <int TEX, bool ANIM>
-__global__ void __launch_bounds__(MINI_WARPS * 32, 5) k_mini_vertices(Params p)
+__global__ void __launch_bounds__(MINI_WARPS * 32, 6) k_mini_vertices(Params p)
 {
   pdl_prologue();
-  extern __shared__ __align__(16) float miniSmem[];
-  static_assert(TC_TESS_2X_MINI_VERTICES == kInstantiateSlot, "a 2X mini triangle is one slot of the slotted pattern table");
-  const uint32_t warp = __reduce_max_sync(0xffffffffu, threadIdx.x >> 5), lane = lane_id();
-  float* rec = miniSmem + size_t(warp) * 32 * TC_REC_WORDS + lane * TC_REC_WORDS;
+  constexpr uint32_t kMiniFloats = TC_TESS_2X_MINI_VERTICES * 3;
+  __shared__ float stageAll[MINI_WARPS][32 * kMiniFloats];
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  __shared__ uint2 hdrAll[MINI_WARPS][32];  // per mini triangle: destination float index, floats to write
+  float* stage = stageAll[warp];
+  uint2* hdr   = hdrAll[warp];
   const uint32_t count = min(p.state->miniCount, p.maxMini);
   float* genVertices = reinterpret_cast<float*>(p.build->genVertices);
   const cudaTextureObject_t uniformTex = TEX == 1 ? p.texturesC[0].gather : 0;
+  const float uniW = TEX == 1 ? float(p.texturesC[0].width) : 0.0f, uniH = TEX == 1 ? float(p.texturesC[0].height) : 0.0f;
+  const float viewScale = p.view[0].displacementScale, viewOffset = p.view[0].displacementOffset;
+  const bool  pn = flag_pn(p);
   const uint32_t warpsTotal = gridDim.x * MINI_WARPS;
   for(uint32_t base = (blockIdx.x * MINI_WARPS + warp) * 32; base < count; base += warpsTotal * 32)
   {
     const uint32_t idx = base + lane;
+    hdr[lane] = make_uint2(0u, 0u);  // .y = 0: this lane has no mini triangle
     if(idx < count)
     {
-      const uint4 a = __ldcs(&p.miniList[size_t(idx) * 2]), b = __ldcs(&p.miniList[size_t(idx) * 2 + 1]);
-      const uint32_t instanceID = a.x, cfg = b.z;
-      const uint32_t vtxEnc[3] = {a.w, b.x, b.y};
-      const uint32_t cfgIdx   = tess_configIndex(cfg) & (TC_TESSTABLE_LOOKUP_ENTRIES - 1);
-      const uint32_t slotBase = __ldg(&p.tblSlotBase[cfgIdx]);
-      const uint32_t numV     = tess_entry(p, cfg).numVertices;
-      const tc_RenderInstance& inst = p.instances[instanceID];
-      build_part_record(p, inst, instanceID, a.y, a.z & 0xFF, (a.z >> 8) & 0xFF, (a.z >> 16) & 0xFF, vtxEnc, (cfg & TC_CONFIG_FLIPPED_BIT) != 0, slotBase, 1u, 0u, rec);
-      float4 q[3];
+    const uint4 a = __ldcs(&p.miniList[size_t(idx) * 2]), b = __ldcs(&p.miniList[size_t(idx) * 2 + 1]);
+    const uint32_t instanceID = a.x, cfg = b.z;
+    const tc_RenderInstance& inst = p.instances[instanceID];
+    const tc_TessTableEntry  e    = tess_entry(p, cfg);
+    const bool flipped = (cfg & TC_CONFIG_FLIPPED_BIT) != 0;
+    // base vertex behind each corner of the (rotated) sub-triangle: vtxEncoded is (0,0), (32768,0) or (0,32768)
+    const uint32_t enc[3] = {a.w, b.x, b.y};
+    uint32_t perm[3];
+#pragma unroll
+    for(int k = 0; k < 3; k++)
+      perm[k] = (enc[k] & 0xFFFFu) ? 1u : ((enc[k] >> 16) ? 2u : 0u);
+    // candidate c (0..2 corner of base vertex c, 3..5 midpoint of base edge (0,1) (1,2) (2,0)) -> pattern vertex index
+    uint32_t where = 0xFFFFFFu;
+#pragma unroll
+    for(uint32_t i = 0; i < TC_TESS_2X_MINI_VERTICES; i++)
+      if(i < e.numVertices)
+      {
+        const uint32_t pv = __ldg(&p.tblVertices[e.firstVertex + i]);
+        uint32_t h1 = (pv & 0xFFFFu) >> 14, h2 = pv >> 30, h0 = 2u - h1 - h2;  // weights in halves
+        if(flipped)
+        {
+          const uint32_t t = h0;
+          h0 = h1;
+          h1 = t;
+        }
+        // halves per BASE vertex, packed two bits each
+        const uint32_t hb = (h0 << (2 * perm[0])) + (h1 << (2 * perm[1])) + (h2 << (2 * perm[2]));
+        uint32_t c;
+        if(hb == 0x02u) c = 0;
+        else if(hb == 0x08u) c = 1;
+        else if(hb == 0x20u) c = 2;
+        else if(hb == 0x05u) c = 3;
+        else if(hb == 0x14u) c = 4;
+        else c = 5;  // 0x11
+        where = (where & ~(0xFu << (4 * c))) | (i << (4 * c));
+      }
+    const float*   positions = reinterpret_cast<const float*>(inst.positions);
+    const float*   normals   = reinterpret_cast<const float*>(inst.normals);
+    const float2*  texcoords = reinterpret_cast<const float2*>(inst.texcoords);
+    const int      ti        = TEX != 0 ? inst.displacementIndex : -1;
+    const bool     displaced = TEX != 0 && ti >= 0;
+    F3     P[3], N[3];
+    float2 T[3];
+#pragma unroll
+    for(int k = 0; k < 3; k++)
+    {
+      const uint32_t gi = a.y + ((a.z >> (8 * k)) & 0xFFu);
+      P[k] = ld_f3(positions, gi);
+      N[k] = f3(0.f, 0.f, 0.f);
+      T[k] = make_float2(0.f, 0.f);
+      if(pn || displaced)
+        N[k] = normalize3(ld_f3(normals, gi));
+      if(displaced)
+        T[k] = __ldg(texcoords + gi);
+    }
+    const float W = displaced ? (TEX == 1 ? uniW : float(p.textures[ti].width)) : 1.0f, H = displaced ? (TEX == 1 ? uniH : float(p.textures[ti].height)) : 1.0f;
+    const float scale = inst.displacementScale * viewScale, offset = inst.displacementOffset + viewOffset;
+    float* myStage = stage + lane * kMiniFloats;
+    // three candidates at a time (corners, then edge midpoints): position, displacement direction (not normalised), texture
+    // coordinate, pattern index nibbles; the three gathers are in flight together, results go to the lane's staging slot
+    auto finish3 = [&](F3 (&cp)[3], const F3 (&cn)[3], const float2 (&ct)[3], uint32_t where3) {
+      if(displaced)
+      {
+        float4 g[3];
+        float  ax[3], ay[3];
+#pragma unroll
+        for(int c = 0; c < 3; c++)
+        {  // sample_displacement_gather (same arithmetic)
+          const float x = fmaf(ct[c].x, W, -0.5f), y = fmaf(ct[c].y, H, -0.5f);
+          const float fx = floorf(x), fy = floorf(y);
+          ax[c] = x - fx;
+          ay[c] = y - fy;
+          g[c]  = make_float4(0.f, 0.f, 0.f, 0.f);
+          if(((where3 >> (4 * c)) & 0xFu) != 0xFu)
+          {
+            const float gx = __fdividef(fx + 1.0f, W), gy = __fdividef(fy + 1.0f, H);
+            g[c] = TEX == 1 ? tex2Dgather<float4>(uniformTex, gx, gy, 0) : tex2Dgather<float4>(p.textures[ti].gather, gx, gy, 0);  // (t01, t11, t10, t00)
+          }
+        }
+#pragma unroll
+        for(int c = 0; c < 3; c++)
+        {
+          const float top = fmaf(g[c].z - g[c].w, ax[c], g[c].w), bot = fmaf(g[c].y - g[c].x, ax[c], g[c].x);
+          const float h   = fmaf(fmaf(bot - top, ay[c], top), scale, offset);
+          cp[c] = fma3(cn[c], h * fast_rsqrt(dot3(cn[c], cn[c])), cp[c]);
+        }
+      }
+#pragma unroll
+      for(int c = 0; c < 3; c++)
+      {
+        const uint32_t i = (where3 >> (4 * c)) & 0xFu;
+        if(i != 0xFu)
+        {
+          F3 o = cp[c];
+          if(ANIM)
+            o = ripple_deform(p.view[0], o, instanceID, inst.geoHi[3]);
+          float* sv = myStage + i * 3;
+          sv[0] = o.x; sv[1] = o.y; sv[2] = o.z;
+        }
+      }
+    };
+    {
+      F3 cp[3] = {P[0], P[1], P[2]};
+      finish3(cp, N, T, where & 0xFFFu);
+    }
+    if((where >> 12) != 0xFFFu)
+    {
+      F3     cp[3], cn[3];
+      float2 ct[3];
 #pragma unroll
       for(int k = 0; k < 3; k++)
-        q[k] = __ldg(p.tblSlots + slotBase + k);  // one slot: the three planes are adjacent
-      float2 X[3], Y[3], Z[3];
-      eval_part_pairs<TEX, 3>(reinterpret_cast<const float4*>(rec), q, X, Y, Z, uniformTex);  // (reads only this lane's own record)
-      F3 o[6];
-#pragma unroll
-      for(int i = 0; i < 3; i++)
       {
-        o[2 * i]     = {X[i].x, Y[i].x, Z[i].x};
-        o[2 * i + 1] = {X[i].y, Y[i].y, Z[i].y};
-      }
-      if(ANIM)
-      {
-        const float geoSize = inst.geoHi[3];
-#pragma unroll
-        for(int i = 0; i < 6; i++)
-          o[i] = ripple_deform(p.view[0], o[i], instanceID, geoSize);
-      }
-      float* dst = genVertices + size_t(b.w) * 3;
-#pragma unroll
-      for(int i = 0; i < 6; i++)
-        if(uint32_t(i) < numV)
+        const int q = k == 2 ? 0 : k + 1;  // edge k: base vertex k -> q
+        cp[k] = (P[k] + P[q]) * 0.5f;
+        if(pn)
         {
-          __stcs(dst + i * 3 + 0, o[i].x); __stcs(dst + i * 3 + 1, o[i].y); __stcs(dst + i * 3 + 2, o[i].z);
+          const F3 ed = P[q] - P[k];
+          cp[k] = fma3(N[q], 0.125f * dot3(ed, N[q]), fma3(N[k], -0.125f * dot3(ed, N[k]), cp[k]));
         }
+        cn[k] = N[k] + N[q];
+        ct[k] = make_float2((T[k].x + T[q].x) * 0.5f, (T[k].y + T[q].y) * 0.5f);
+      }
+      finish3(cp, cn, ct, where >> 12);
     }
+    hdr[lane] = make_uint2(b.w * 3u, uint32_t(e.numVertices) * 3u);
+    }
+    // ... and let the warp write them: lane t handles float (t % 18) of mini triangle (t / 18), so consecutive lanes
+    // write consecutive addresses inside a mini triangle's slot and across the slots of a batch (which are adjacent);
+    // slots of absent vertices stay untouched, exactly like the reference leaves them
+    __syncwarp();
+    {
+      uint32_t m = lane >= kMiniFloats ? 1u : 0u, j = lane - m * kMiniFloats;
+#pragma unroll 6
+      for(uint32_t it = 0; it < kMiniFloats; it++)
+      {
+        const uint2 h = hdr[m];
+        if(j < h.y)
+          __stcs(genVertices + size_t(h.x) + j, stage[it * 32 + lane]);
+        j += 32 - kMiniFloats;  // 32 = 18 + 14
+        m += 1;
+        if(j >= kMiniFloats)
+        {
+          j -= kMiniFloats;
+          m += 1;
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -2828,15 +2952,16 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
   {  // vertices of the 2X mini triangles recorded by the kernel above
     const int    tex  = p.numTextures == 0 ? 0 : (p.numTextures == 1 ? 1 : 2);
     const bool   anim = (p.flags & TC_FLAG_ANIMATION) != 0;
-    const size_t ms   = mini_smem_bytes();
+    const size_t ms   = 0;
+    const uint32_t mg = miniGrid / 5 * 6;  // 6 CTAs of 4 warps per SM (78 registers)
     switch(tex * 2 + int(anim))
     {
-      case 0: launch_pdl(k_mini_vertices<0, false>, miniGrid, MINI_WARPS * 32, ms, s, p); break;
-      case 1: launch_pdl(k_mini_vertices<0, true>, miniGrid, MINI_WARPS * 32, ms, s, p); break;
-      case 2: launch_pdl(k_mini_vertices<1, false>, miniGrid, MINI_WARPS * 32, ms, s, p); break;
-      case 3: launch_pdl(k_mini_vertices<1, true>, miniGrid, MINI_WARPS * 32, ms, s, p); break;
-      case 4: launch_pdl(k_mini_vertices<2, false>, miniGrid, MINI_WARPS * 32, ms, s, p); break;
-      default: launch_pdl(k_mini_vertices<2, true>, miniGrid, MINI_WARPS * 32, ms, s, p); break;
+      case 0: launch_pdl(k_mini_vertices<0, false>, mg, MINI_WARPS * 32, ms, s, p); break;
+      case 1: launch_pdl(k_mini_vertices<0, true>, mg, MINI_WARPS * 32, ms, s, p); break;
+      case 2: launch_pdl(k_mini_vertices<1, false>, mg, MINI_WARPS * 32, ms, s, p); break;
+      case 3: launch_pdl(k_mini_vertices<1, true>, mg, MINI_WARPS * 32, ms, s, p); break;
+      case 4: launch_pdl(k_mini_vertices<2, false>, mg, MINI_WARPS * 32, ms, s, p); break;
+      default: launch_pdl(k_mini_vertices<2, true>, mg, MINI_WARPS * 32, ms, s, p); break;
     }
   }
 }
