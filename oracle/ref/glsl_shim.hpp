@@ -101,6 +101,7 @@ struct Swz  // writable swizzle view
     GLSL_ARITH(T) explicit V(T s) : x(S(s)), y(S(s)) {}                                                                \
     GLSL_ARITH2 V(A a, B b) : x(S(a)), y(S(b)) {}                                                                      \
     template <class O, class = decltype(O().x), class = decltype(O().y)> explicit V(const O& o) : x(S(o.x)), y(S(o.y)) {} \
+    template <class R2, class S2> explicit V(const Swz<R2, S2, 2>& s) : x(S(*s.p[0])), y(S(*s.p[1])) {}                 \
     S& operator[](int i) { return (&x)[i]; }                                                                           \
     const S& operator[](int i) const { return (&x)[i]; }                                                               \
     Swz<V, S, 2> xy() { return {{&x, &y}}; }                                                                           \
@@ -127,6 +128,7 @@ GLSL_VEC2(bvec2, bool)
     V(A a, B b_, C c) : x(S(a)), y(S(b_)), z(S(c)) {}                                                                  \
     GLSL_ARITH(T) V(const V2& a, T c) : x(a.x), y(a.y), z(S(c)) {}                                                     \
     template <class O, class = decltype(O().x), class = decltype(O().z)> explicit V(const O& o) : x(S(o.x)), y(S(o.y)), z(S(o.z)) {} \
+    template <class R2, class S2> explicit V(const Swz<R2, S2, 3>& s) : x(S(*s.p[0])), y(S(*s.p[1])), z(S(*s.p[2])) {}  \
     S& operator[](int i) { return (&x)[i]; }                                                                           \
     const S& operator[](int i) const { return (&x)[i]; }                                                               \
     Swz<V2, S, 2> xy() { return {{&x, &y}}; }                                                                          \
@@ -166,6 +168,8 @@ GLSL_VEC3(bvec3, bvec2, bool)
 
 GLSL_VEC4(vec4, vec3, vec2, float)
 GLSL_VEC4(uvec4, uvec3, uvec2, uint)
+GLSL_VEC4(ivec4, ivec3, ivec2, int)
+typedef uvec4 bvec4;  // a bool in a uniform / push-constant block occupies 32 bits
 
 struct u8vec4
 {
@@ -221,7 +225,7 @@ inline int   findLSB(uint v) { return v ? __builtin_ctz(v) : -1; }
 
 #define GLSL_MAP2(fn, V, N) inline V fn(const V& a, const V& b) { V r; for(int i = 0; i < N; i++) r[i] = fn(a[i], b[i]); return r; }
 #define GLSL_MAP1(fn, V, N) inline V fn(const V& a) { V r; for(int i = 0; i < N; i++) r[i] = fn(a[i]); return r; }
-GLSL_MAP2(min, vec2, 2) GLSL_MAP2(min, vec3, 3) GLSL_MAP2(min, vec4, 4) GLSL_MAP2(min, uvec2, 2) GLSL_MAP2(min, uvec3, 3) GLSL_MAP2(min, uvec4, 4)
+GLSL_MAP2(min, ivec2, 2) GLSL_MAP2(max, ivec2, 2) GLSL_MAP2(min, vec2, 2) GLSL_MAP2(min, vec3, 3) GLSL_MAP2(min, vec4, 4) GLSL_MAP2(min, uvec2, 2) GLSL_MAP2(min, uvec3, 3) GLSL_MAP2(min, uvec4, 4)
 GLSL_MAP2(max, vec2, 2) GLSL_MAP2(max, vec3, 3) GLSL_MAP2(max, vec4, 4) GLSL_MAP2(max, uvec2, 2) GLSL_MAP2(max, uvec3, 3) GLSL_MAP2(max, uvec4, 4)
 GLSL_MAP1(round, vec2, 2) GLSL_MAP1(round, vec3, 3) GLSL_MAP1(round, vec4, 4)
 GLSL_MAP1(abs, vec2, 2) GLSL_MAP1(abs, vec3, 3) GLSL_MAP1(abs, vec4, 4)
@@ -343,6 +347,30 @@ inline vec4 textureLod(sampler2D t, const vec2& uv, float lod)
   const float* p = t->texels + base;
   float a = p[size_t(y0) * size + x0], b = p[size_t(y0) * size + x1], d = p[size_t(y1) * size + x0], e = p[size_t(y1) * size + x1];
   return vec4(max(max(a, b), max(d, e)), 0.0f, 0.0f, 1.0f);
+}
+
+// texelFetchOffset: exact texel of one mip level.  A fetch outside the level is undefined in GLSL (robust buffer access
+// returns 0); DEFINED as 0 here, as in the oracle and the kernels (nvhiz-update).
+inline vec4 texelFetchOffset(sampler2D t, const ivec2& coord, int lod, const ivec2& offset)
+{
+  uint32_t w = t->mips > 1 || lod > 0 ? max(1u, t->width >> lod) : t->width, h = t->mips > 1 || lod > 0 ? max(1u, t->height >> lod) : t->height;
+  size_t   base = 0;
+  for(int l = 0; l < lod; l++)
+    base += size_t(max(1u, t->width >> l)) * max(1u, t->height >> l);
+  int x = coord.x + offset.x, y = coord.y + offset.y;
+  float v = (x >= 0 && y >= 0 && uint32_t(x) < w && uint32_t(y) < h) ? t->texels[base + size_t(y) * w + x] : 0.0f;
+  return vec4(v, 0.0f, 0.0f, 1.0f);
+}
+struct Image2D
+{
+  uint32_t width = 0, height = 0;
+  float*   texels = nullptr;
+};
+typedef const Image2D* image2D;
+inline void imageStore(image2D img, const ivec2& c, const vec4& v)  // writes outside the image are discarded
+{
+  if(img && c.x >= 0 && c.y >= 0 && uint32_t(c.x) < img->width && uint32_t(c.y) < img->height)
+    img->texels[size_t(c.y) * img->width + c.x] = v.x;
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -477,9 +505,11 @@ struct Simt
       }
   }
   // run one workgroup of localSize invocations to completion
-  void runWorkgroup(void (*fn)(), uint localSize, uint wgX, uint subgroupSize = 32)
+  void runWorkgroup(void (*fn)(), uint localSize, uint wgX, uint subgroupSize = 32, uint localSizeX = 0, uint wgY = 0)
   {
     entry = fn;
+    if(!localSizeX)
+      localSizeX = localSize;
     if(fibers.size() < localSize)
     {
       fibers.resize(localSize);
@@ -492,9 +522,9 @@ struct Simt
       initFiber(f, stacks.data() + size_t(i) * kStack);
       f.lane        = i % subgroupSize;
       f.subgroup    = i / subgroupSize;
-      f.localID     = uvec3(i, 0, 0);
-      f.workGroupID = uvec3(wgX, 0, 0);
-      f.globalID    = uvec3(wgX * localSize + i, 0, 0);
+      f.localID     = uvec3(i % localSizeX, i / localSizeX, 0);
+      f.workGroupID = uvec3(wgX, wgY, 0);
+      f.globalID    = uvec3(wgX * localSizeX + i % localSizeX, wgY * (localSize / localSizeX) + i / localSizeX, 0);
       f.state       = 0;
     }
     for(;;)

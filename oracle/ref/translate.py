@@ -108,6 +108,11 @@ def to_cpp(src: str, shader: str) -> str:
         members = _split_members(body)
         if "push_constant" in layout:
             fields = " ".join(x + ";" for x in members)
+            if not inst:  # members are globals: one struct behind the name `push`, one macro per member
+                for mem in members:
+                    out_pre.append(f"#define {mem.split()[-1]} (_p_push->{mem.split()[-1]})")
+                binds.append(("push_t", "push", None))
+                return f"struct push_t {{ {fields} }};\nstatic push_t* _p_push;\n"
             binds.append((f"{inst}_t", inst, False))
             return f"struct {inst}_t {{ {fields} }};\nstatic {inst}_t* _p_{inst};\n"
         txt = ""
@@ -125,11 +130,18 @@ def to_cpp(src: str, shader: str) -> str:
         return f"static sampler2D* _p_{name};\n"
     src = re.sub(r"layout\s*\([^)]*\)\s*uniform\s+sampler2D\s+(\w+)\s*(\[\s*\])?\s*;", sampler, src)
 
-    local = re.search(r"layout\s*\(\s*local_size_x\s*=\s*(\d+)\s*\)\s*in\s*;", src)
-    src = src.replace(local.group(0), f"static const uint _local_size_x = {local.group(1)};")
+    def image(m):
+        name, arr = m.group(1), m.group(2)
+        binds.append(("image2D", name, bool(arr)))
+        return f"static image2D* _p_{name};\n"
+    src = re.sub(r"layout\s*\([^)]*\)\s*uniform\s+image2D\s+(\w+)\s*(\[\s*\w*\s*\])?\s*;", image, src)
+
+    local = re.search(r"layout\s*\(\s*local_size_x\s*=\s*(\d+)\s*(?:,\s*local_size_y\s*=\s*(\d+)\s*)?\)\s*in\s*;", src)
+    src = src.replace(local.group(0), f"static const uint _local_size_x = {local.group(1)}, _local_size_y = {local.group(2) or 1};")
 
     for typ, name, arr in binds:
-        out_pre.append(f"#define {name} {'_p_' + name if arr else '(*_p_' + name + ')'}")
+        if arr is not None:
+            out_pre.append(f"#define {name} {'_p_' + name if arr else '(*_p_' + name + ')'}")
 
     # ---- qualifiers
     src = re.sub(r"\bshared\s+", "static ", src)

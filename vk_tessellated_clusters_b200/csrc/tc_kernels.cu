@@ -1282,8 +1282,35 @@ __global__ void __launch_bounds__(MINI_WARPS * 32, 6) k_mini_vertices(Params p)
   __shared__ float stageAll[MINI_WARPS][32 * kMiniFloats];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   __shared__ uint2 hdrAll[MINI_WARPS][32];  // per mini triangle: destination float index, floats to write
+  // [factors-1 (3 bits)][flipped][rotation]: for candidate c (0..2 corner of base vertex c, 3..5 midpoint of base edge (0,1) (1,2)
+  // (2,0)) the index of the pattern vertex that lands there (nibble c, 0xF = none), vertex count in bits 24..27
+  __shared__ uint32_t whereTbl[48];
   float* stage = stageAll[warp];
   uint2* hdr   = hdrAll[warp];
+  if(threadIdx.x < 48)
+  {
+    const uint32_t rot = threadIdx.x % 3u, flipped = (threadIdx.x / 3u) & 1u, c3 = threadIdx.x / 6u;
+    const uint32_t cfgIdx = (c3 & 1u) + 16u * ((c3 >> 1) & 1u) + 256u * (c3 >> 2);  // = x + 16 y + 256 z - 273 with factors in {1,2}
+    const tc_TessTableEntry e = p.tblEntries[cfgIdx];
+    const uint32_t perm[3] = {rot, (rot + 1u) % 3u, (rot + 2u) % 3u};  // base vertex behind each corner of the rotated triangle
+    uint32_t where = 0xFFFFFFu;
+    for(uint32_t i = 0; i < TC_TESS_2X_MINI_VERTICES && i < e.numVertices; i++)
+    {
+      const uint32_t pv = p.tblVertices[e.firstVertex + i];
+      uint32_t h1 = (pv & 0xFFFFu) >> 14, h2 = pv >> 30, h0 = 2u - h1 - h2;  // pattern barycentrics in halves
+      if(flipped)
+      {
+        const uint32_t t = h0;
+        h0 = h1;
+        h1 = t;
+      }
+      const uint32_t hb = (h0 << (2 * perm[0])) + (h1 << (2 * perm[1])) + (h2 << (2 * perm[2]));  // halves per BASE vertex
+      const uint32_t c  = hb == 0x02u ? 0u : hb == 0x08u ? 1u : hb == 0x20u ? 2u : hb == 0x05u ? 3u : hb == 0x14u ? 4u : 5u;
+      where = (where & ~(0xFu << (4 * c))) | (i << (4 * c));
+    }
+    whereTbl[threadIdx.x] = where | (min(uint32_t(e.numVertices), TC_TESS_2X_MINI_VERTICES) << 24);
+  }
+  __syncthreads();
   const uint32_t count = min(p.state->miniCount, p.maxMini);
   float* genVertices = reinterpret_cast<float*>(p.build->genVertices);
   const cudaTextureObject_t uniformTex = TEX == 1 ? p.texturesC[0].gather : 0;
@@ -1300,39 +1327,11 @@ __global__ void __launch_bounds__(MINI_WARPS * 32, 6) k_mini_vertices(Params p)
     const uint4 a = __ldcs(&p.miniList[size_t(idx) * 2]), b = __ldcs(&p.miniList[size_t(idx) * 2 + 1]);
     const uint32_t instanceID = a.x, cfg = b.z;
     const tc_RenderInstance& inst = p.instances[instanceID];
-    const tc_TessTableEntry  e    = tess_entry(p, cfg);
-    const bool flipped = (cfg & TC_CONFIG_FLIPPED_BIT) != 0;
-    // base vertex behind each corner of the (rotated) sub-triangle: vtxEncoded is (0,0), (32768,0) or (0,32768)
-    const uint32_t enc[3] = {a.w, b.x, b.y};
-    uint32_t perm[3];
-#pragma unroll
-    for(int k = 0; k < 3; k++)
-      perm[k] = (enc[k] & 0xFFFFu) ? 1u : ((enc[k] >> 16) ? 2u : 0u);
-    // candidate c (0..2 corner of base vertex c, 3..5 midpoint of base edge (0,1) (1,2) (2,0)) -> pattern vertex index
-    uint32_t where = 0xFFFFFFu;
-#pragma unroll
-    for(uint32_t i = 0; i < TC_TESS_2X_MINI_VERTICES; i++)
-      if(i < e.numVertices)
-      {
-        const uint32_t pv = __ldg(&p.tblVertices[e.firstVertex + i]);
-        uint32_t h1 = (pv & 0xFFFFu) >> 14, h2 = pv >> 30, h0 = 2u - h1 - h2;  // weights in halves
-        if(flipped)
-        {
-          const uint32_t t = h0;
-          h0 = h1;
-          h1 = t;
-        }
-        // halves per BASE vertex, packed two bits each
-        const uint32_t hb = (h0 << (2 * perm[0])) + (h1 << (2 * perm[1])) + (h2 << (2 * perm[2]));
-        uint32_t c;
-        if(hb == 0x02u) c = 0;
-        else if(hb == 0x08u) c = 1;
-        else if(hb == 0x20u) c = 2;
-        else if(hb == 0x05u) c = 3;
-        else if(hb == 0x14u) c = 4;
-        else c = 5;  // 0x11
-        where = (where & ~(0xFu << (4 * c))) | (i << (4 * c));
-      }
+    // candidate -> pattern index nibbles + vertex count: a function of (factors <= 2, flipped, rotation) only, see whereTbl
+    const uint32_t rot   = (a.w & 0xFFFFu) ? 1u : ((a.w >> 16) ? 2u : 0u);  // base vertex behind corner 0 of the rotated triangle
+    const uint32_t c3    = (cfg & 1u) | ((cfg >> 3) & 2u) | ((cfg >> 6) & 4u);
+    const uint32_t where = whereTbl[(c3 * 2u + ((cfg >> 15) & 1u)) * 3u + rot];
+    const uint32_t numV  = where >> 24;
     const float*   positions = reinterpret_cast<const float*>(inst.positions);
     const float*   normals   = reinterpret_cast<const float*>(inst.normals);
     const float2*  texcoords = reinterpret_cast<const float2*>(inst.texcoords);
@@ -1402,7 +1401,7 @@ __global__ void __launch_bounds__(MINI_WARPS * 32, 6) k_mini_vertices(Params p)
       F3 cp[3] = {P[0], P[1], P[2]};
       finish3(cp, N, T, where & 0xFFFu);
     }
-    if((where >> 12) != 0xFFFu)
+    if(((where >> 12) & 0xFFFu) != 0xFFFu)
     {
       F3     cp[3], cn[3];
       float2 ct[3];
@@ -1419,9 +1418,9 @@ __global__ void __launch_bounds__(MINI_WARPS * 32, 6) k_mini_vertices(Params p)
         cn[k] = N[k] + N[q];
         ct[k] = make_float2((T[k].x + T[q].x) * 0.5f, (T[k].y + T[q].y) * 0.5f);
       }
-      finish3(cp, cn, ct, where >> 12);
+      finish3(cp, cn, ct, (where >> 12) & 0xFFFu);
     }
-    hdr[lane] = make_uint2(b.w * 3u, uint32_t(e.numVertices) * 3u);
+    hdr[lane] = make_uint2(b.w * 3u, numV * 3u);
     }
     // ... and let the warp write them: lane t handles float (t % 18) of mini triangle (t / 18), so consecutive lanes
     // write consecutive addresses inside a mini triangle's slot and across the slots of a batch (which are adjacent);
