@@ -22,7 +22,7 @@
 namespace glsl {
 #define REF_SHADER(n)                                                                                                  \
   int  bind_##n(const char*, void*);                                                                                   \
-  void run_##n(uint groups);                                                                                           \
+  void run_##n(uint groupsX, uint groupsY = 1);                                                                                         \
   uint local_size_##n();
 REF_SHADER(instances_classify)
 REF_SHADER(clusters_cull)
@@ -32,6 +32,10 @@ REF_SHADER(triangle_split)
 REF_SHADER(triangle_tess_template_instantiate)
 REF_SHADER(blas_setup_insertion)
 REF_SHADER(blas_clusters_insert)
+REF_SHADER(hiz_first)
+REF_SHADER(hiz_rest)
+REF_SHADER(rchit)
+void set_hit_rchit(uint clusterID, uint primitiveID, uint instanceID, float b0, float b1, void* out);
 }  // namespace glsl
 
 namespace {
@@ -402,6 +406,135 @@ REF_API int ref_buffer(ref_context* c, const char* name, const void** ptr, size_
   BUF("tessEntries", tblEntries)
 #undef BUF
   return TC_ERR_INVALID_ARG;
+}
+
+// ---- hit decode: main() of shaders/render_raytrace_clusters.rchit.glsl up to where shading begins, one hit at a time -----
+// (the reference masks the sub-triangle id of a 2X hit with 4, rchit:163; callers compare with TC_HIT_REFERENCE_2X_QUIRK)
+REF_API int ref_resolve_hits(ref_context* c, const tc_hit* hits, uint32_t count, tc_hit_base* out, uint32_t /*flags*/)
+{
+  using namespace glsl;
+  struct B { const char* name; void* ptr; };
+  const B binds[] = {{"view", &c->frame[0]}, {"readback", &c->readback}, {"instances", c->instances.data()}, {"build", &c->build},
+                     {"tessTable", &c->tessTable}, {"displacementTextures", c->textureHandles.data()}};
+  for(const B& b : binds)
+    bind_rchit(b.name, b.ptr);
+  for(uint32_t i = 0; i < count; i++)
+  {
+    memset(&out[i], 0, sizeof(tc_hit_base));
+    set_hit_rchit(hits[i].clusterID, hits[i].primitiveID, hits[i].instanceID, hits[i].barycentrics[0], hits[i].barycentrics[1], &out[i]);
+    run_rchit(1);
+  }
+  return TC_OK;
+}
+
+// ---- far-HiZ builder: shaders/nvhiz-update.comp.glsl driven by the schedule of NVHizVK::cmdUpdateHiz ------------------
+// host arithmetic of NVHizVK::setupUpdateInfos (src/nvhiz_vk.cpp:278-308, hizFarLevel 0): pyramid size and mip count
+static void hiz_dims(uint32_t width, uint32_t height, uint32_t* size, uint32_t* mips)
+{
+  uint32_t dim = (width > height ? width : height) / 2, hiz = 1, m = 1;
+  while(hiz < dim)
+  {
+    hiz *= 2;
+    m++;
+  }
+  *size = hiz;
+  *mips = m;
+}
+
+REF_API int ref_update_hiz(ref_context* c, const float* depth, uint32_t width, uint32_t height, uint32_t /*depthIsDevice*/)
+{
+  using namespace glsl;
+  uint32_t size, mips;
+  hiz_dims(width, height, &size, &mips);
+  std::vector<size_t> levelOffset(mips);
+  size_t total = 0;
+  for(uint32_t l = 0; l < mips; l++)
+  {
+    levelOffset[l] = total;
+    total += size_t(std::max(1u, size >> l)) * std::max(1u, size >> l);
+  }
+  if(c->hiz.size() != total || c->hizTex.width != size || c->hizTex.mips != mips)
+    c->hiz.assign(total, 0.0f);
+  c->hizTex.width = c->hizTex.height = size;
+  c->hizTex.mips   = mips;
+  c->hizTex.texels = c->hiz.data();
+  c->hizHandle     = &c->hizTex;
+
+  Texture2D depthTex;
+  depthTex.width  = width;
+  depthTex.height = height;
+  depthTex.mips   = 1;
+  depthTex.texels = depth;
+  const Texture2D* texDepth = &depthTex;
+  const Texture2D* texFar   = &c->hizTex;  // binding 1 (BINDING_READ_FAR) is what the shader calls texNear
+  std::vector<Image2D>        levels(16);
+  std::vector<const Image2D*> levelHandles(16, nullptr);
+  for(uint32_t l = 0; l < mips && l < 16; l++)
+  {
+    levels[l].width = levels[l].height = std::max(1u, size >> l);
+    levels[l].texels = c->hiz.data() + levelOffset[l];
+    levelHandles[l]  = &levels[l];
+  }
+  const Image2D* imgNear = nullptr;
+  struct Push  // keep in sync with the shader's passUniforms block
+  {
+    int32_t  srcSize[4];
+    int32_t  writeLod, startLod, layer, _pad0;
+    uint32_t levelActive[4];
+  } push{};
+  struct B { const char* name; void* ptr; };
+  const B binds[] = {{"texDepth", &texDepth}, {"texNear", &texFar}, {"imgNear", &imgNear}, {"imgLevels", levelHandles.data()}, {"push", &push}};
+  for(const B& b : binds)
+  {
+    bind_hiz_first(b.name, b.ptr);
+    bind_hiz_rest(b.name, b.ptr);
+  }
+
+  // NVHizVK::cmdUpdateHiz, src/nvhiz_vk.cpp:484-594 (hizLevels 3, mono, far only)
+  const uint32_t hizLevels = 3, align = 8;
+  uint32_t inputW = width, inputH = height;
+  uint32_t subW = (inputW + 1) / 2, subH = (inputH + 1) / 2;
+  for(uint32_t i = 0; i < mips; i += hizLevels)
+  {
+    const uint32_t inputLod = (i == 0) ? 0 : i - 1;
+    for(uint32_t level = 0; level < hizLevels; level++)
+      push.levelActive[level] = level + i < mips;
+    subW = ((subW + align - 1) / align) * align;
+    subH = ((subH + align - 1) / align) * align;
+    push.srcSize[0] = int32_t(inputW);
+    push.srcSize[1] = int32_t(inputH);
+    push.srcSize[2] = int32_t(inputW) - 2;
+    push.srcSize[3] = int32_t(inputH) - 2;
+    push.startLod   = int32_t(inputLod);
+    push.writeLod   = int32_t(i);
+    push.layer      = 0;
+    if(i == 0)
+      run_hiz_first((subW + 7) / 8, (subH + 7) / 8);
+    else
+      run_hiz_rest((subW + 7) / 8, (subH + 7) / 8);
+    for(uint32_t level = 0; level < hizLevels; level++)
+    {
+      subW = (subW + 1) / 2;
+      subH = (subH + 1) / 2;
+    }
+    subW   = subW ? subW : 1;
+    subH   = subH ? subH : 1;
+    inputW = subW * 2;
+    inputH = subH * 2;
+  }
+  return TC_OK;
+}
+
+REF_API int ref_get_hiz(ref_context* c, float* out, size_t capacityFloats, uint32_t* size, uint32_t* mipLevels)
+{
+  if(size) *size = c->hizTex.width;
+  if(mipLevels) *mipLevels = c->hizTex.mips;
+  if(!out)
+    return TC_OK;
+  if(capacityFloats < c->hiz.size())
+    return TC_ERR_INVALID_ARG;
+  std::copy(c->hiz.begin(), c->hiz.end(), out);
+  return TC_OK;
 }
 
 // how many subgroup/workgroup collectives the emulator resolved, and how many of them with only part of the live lanes

@@ -52,7 +52,7 @@ def macro_set(a) -> dict:
 
 
 def variant_name(macros: dict) -> str:
-    key = ";".join(f"{k}={v}" for k, v in sorted(macros.items()))
+    key = ";".join(f"{k}={v}" for k, v in sorted(macros.items())) + repr(HIZ_PROGRAMS)
     for f in ("glsl_shim.hpp", "ref_harness.cpp", "translate.py"):
         with open(os.path.join(HERE, f), "rb") as fh:
             key += hashlib.sha1(fh.read()).hexdigest()
@@ -69,12 +69,22 @@ def stage_sources(stage: str):
             txt = re.sub(r"^[ \t]*#[ \t]*(version|extension)\b.*$", "", txt, flags=re.M)
             with open(os.path.join(stage, f), "w") as fh:
                 fh.write(txt)
+    with open(os.path.join(stage, "render_shading.glsl"), "w") as fh:
+        fh.write("\n")  # shading / AO rays of the closest-hit shader: after the decode the path ends at, not compiled
     with open(os.path.join(stage, "nvshaders", "sky_io.h.slang"), "w") as fh:
         fh.write("struct SkySimpleParameters { vec4 _stub; };\n")  # tail of FrameConstants, never read by the path
 
 
+# the far-HiZ builder: one shader, two pipelines -- the macro sets of NVHizVK::initPipelines
+# (src/nvhiz_vk.cpp:226-240) with the sample's configuration (src/resources.cpp:176-186, nvhiz_vk.cpp:79: 3 levels per
+# dispatch, no MSAA, no reversed Z, far pyramid only, mono)
+HIZ_COMMON = {"NV_HIZ_LEVELS": 3, "NV_HIZ_MSAA_SAMPLES": 0, "NV_HIZ_REVERSED_Z": 0, "NV_HIZ_NEAR_LEVEL": 0, "NV_HIZ_FAR_LEVEL": 0,
+              "NV_HIZ_OUTPUT_NEAR": 0, "NV_HIZ_USE_STEREO": 0}
+HIZ_PROGRAMS = [("hiz_first", "nvhiz-update", dict(HIZ_COMMON, NV_HIZ_IS_FIRST=1)), ("hiz_rest", "nvhiz-update", dict(HIZ_COMMON, NV_HIZ_IS_FIRST=0))]
+
+
 def preprocess(stage: str, shader: str, macros: dict) -> str:
-    cmd = ["gcc", "-E", "-P", "-undef", "-nostdinc", "-x", "c", "-I", stage] + [f"-D{k}={v}" for k, v in macros.items()] + [os.path.join(stage, shader + ".comp.glsl")]
+    cmd = ["gcc", "-E", "-P", "-undef", "-nostdinc", "-x", "c", "-I", stage] + [f"-D{k}={v}" for k, v in macros.items()] + [os.path.join(stage, shader if shader.endswith(".glsl") else shader + ".comp.glsl")]
     return subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
 
 
@@ -82,8 +92,32 @@ def _split_members(body: str):
     return [m.strip() for m in body.split(";") if m.strip()]
 
 
+RCHIT_CUT = "vec3 oPos = baryWeight.x * gl_HitTriangleVertexPositionsEXT[0]"
+RCHIT_EXPORT = """
+  // (translate.py) main() is cut where the hit decode ends and shading begins: hand the decoded values to the harness
+  _hit_out->mode = mode; _hit_out->clusterID = clusterID; _hit_out->triangleID = triangleID; _hit_out->subTriangleID = subTriangleID;
+  _hit_out->cfg = cfg; _hit_out->baseIndices[0] = baseIndices.x; _hit_out->baseIndices[1] = baseIndices.y; _hit_out->baseIndices[2] = baseIndices.z;
+  _hit_out->partID = partID; _hit_out->bary[0] = baryWeightBase.x; _hit_out->bary[1] = baryWeightBase.y; _hit_out->bary[2] = baryWeightBase.z;
+}
+"""
+
+
+def rchit_prepare(src: str) -> str:
+    """closest-hit shader -> a function: ray-tracing built-ins become plain variables the harness sets per hit"""
+    src = re.sub(r"spirv_decorate\s*\(.*?\)\s*in\s+int\s+gl_ClusterIDNV_\s*;", "", src, flags=re.S)
+    src = re.sub(r"layout\s*\([^)]*\)\s*uniform\s+accelerationStructureEXT\s+\w+\s*;", "", src)
+    src = re.sub(r"layout\s*\([^)]*\)\s*rayPayload(In)?EXT\s+\w+\s+\w+\s*;", "", src)
+    src = re.sub(r"hitAttributeEXT\s+vec2\s+barycentrics\s*;", "", src)
+    cut = src.index(RCHIT_CUT)
+    head = ("struct HitOut { uint mode, clusterID, triangleID, subTriangleID, cfg, baseIndices[3], partID; float bary[3]; };\n"
+            "static HitOut* _hit_out; static int gl_ClusterIDNV_, gl_PrimitiveID, gl_InstanceID; static vec2 barycentrics;\n")
+    return head + src[:cut] + RCHIT_EXPORT + "layout(local_size_x=1) in;\n"
+
+
 def to_cpp(src: str, shader: str) -> str:
     out_pre = []  # emitted before the translated text
+    if shader == "rchit":
+        src = rchit_prepare(src)
 
     # ---- float literals: GLSL literals are float, C++ literals are double
     def lit(m):
@@ -110,7 +144,8 @@ def to_cpp(src: str, shader: str) -> str:
             fields = " ".join(x + ";" for x in members)
             if not inst:  # members are globals: one struct behind the name `push`, one macro per member
                 for mem in members:
-                    out_pre.append(f"#define {mem.split()[-1]} (_p_push->{mem.split()[-1]})")
+                    out_pre.append(f"#define {mem.split()[-1]} (_p_push->m_{mem.split()[-1]})")
+                fields = " ".join(" ".join(x.split()[:-1]) + " m_" + x.split()[-1] + ";" for x in members)
                 binds.append(("push_t", "push", None))
                 return f"struct push_t {{ {fields} }};\nstatic push_t* _p_push;\n"
             binds.append((f"{inst}_t", inst, False))
@@ -206,14 +241,23 @@ int bind_{shader}(const char* name, void* ptr)
 {bind_fn}
   return 0;
 }}
+{RCHIT_SETTER if shader == "rchit" else ""}
 uint local_size_{shader}() {{ return _local_size_x; }}
-void run_{shader}(uint groups)
+void run_{shader}(uint groupsX, uint groupsY)
 {{
-  for(uint g = 0; g < groups; g++)
-    Simt::get().runWorkgroup(&shader_main, _local_size_x, g);
+  for(uint gy = 0; gy < groupsY; gy++)
+    for(uint gx = 0; gx < groupsX; gx++)
+      Simt::get().runWorkgroup(&shader_main, _local_size_x * _local_size_y, gx, 32, _local_size_x, gy);
 }}
 }}
 """
+
+
+RCHIT_SETTER = """void set_hit_rchit(uint clusterID, uint primitiveID, uint instanceID, float b0, float b1, void* out)
+{
+  gl_ClusterIDNV_ = int(clusterID); gl_PrimitiveID = int(primitiveID); gl_InstanceID = int(instanceID);
+  barycentrics = vec2(b0, b1); _hit_out = reinterpret_cast<HitOut*>(out);
+}"""
 
 
 def build(a) -> str:
@@ -231,10 +275,11 @@ def build(a) -> str:
     objs = []
     cxx = ["g++", "-std=c++17", "-O1", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-msse4.1", "-w", "-fvisibility=hidden", "-I", HERE,
            "-I", os.path.join(os.path.dirname(os.path.dirname(HERE)), "include")]
-    def compile_one(sh):
+    def compile_one(prog):
+        sh, file, defs = prog
         cpp = os.path.join(gen, sh + ".cpp")
         with open(cpp, "w") as fh:
-            fh.write(to_cpp(preprocess(stage, sh, macros), sh))
+            fh.write(to_cpp(preprocess(stage, file, defs), sh))
         obj = cpp[:-4] + ".o"
         r = subprocess.run(cxx + ["-c", cpp, "-o", obj], capture_output=True, text=True)
         if r.returncode != 0:
@@ -242,7 +287,8 @@ def build(a) -> str:
             raise SystemExit(f"compiling the translated {sh} failed")
         return obj
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
-        objs = list(pool.map(compile_one, SHADERS))
+        rchit = ("rchit", "render_raytrace_clusters.rchit.glsl", dict(macros, RAYTRACING_PAYLOAD_INDEX=0))
+        objs = list(pool.map(compile_one, [(sh, sh, macros) for sh in SHADERS] + HIZ_PROGRAMS + [rchit]))
     defs = [f"-DREF_{k}={v}" for k, v in macros.items()]
     with open(os.path.join(REF_SHADERS, "shaderio.h")) as fh:  # push-constant ids of build_setup.comp.glsl
         defs += [f"-DREF_{m.group(1)}={m.group(2)}" for m in re.finditer(r"^#define\s+(BUILD_SETUP_\w+)\s+(\d+)", fh.read(), flags=re.M)]

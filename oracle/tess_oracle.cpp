@@ -7,7 +7,7 @@
  *
  * PARITY PINNED AGAINST THE REFERENCE'S OWN SHADERS.  The reference ships no tests, golden vectors or fixtures for this
  * path and its implementation is GLSL executed by a Vulkan driver -- but the eight compute shaders of the path DO run
- * here: oracle/ref/translate.py compiles /root/reference/shaders/*.comp.glsl (read where they lie) with g++ on top of a
+ * here: oracle/ref/translate.py compiles the .comp.glsl files of /root/reference/shaders (read where they lie) with g++ on top of a
  * GLSL run-time + SIMT emulator (oracle/ref/glsl_shim.hpp) into oracle/_ref/, and tests/test_reference_shaders.py
  * checks this file against them on 19 scene cases: all counters equal, every record buffer identical byte for byte
  * (stronger than the order-normalised multiset north_star asks for), generated vertices within 2.4e-7.  What stays

@@ -96,3 +96,25 @@ def test_update_replaces_set_hiz_and_rejects_tiny_images():
     with pytest.raises(Exception):
         o.update_hiz(np.zeros((1, 8), np.float32))
     o.close()
+
+
+@pytest.mark.parametrize("w,h", SIZES + [(1023, 511), (1920, 1080)])
+def test_oracle_matches_reference_hiz_shader(w, h):
+    """The oracle's pyramid against the REFERENCE'S OWN nvhiz-update.comp.glsl, compiled for the host and run by the SIMT
+    emulator (oracle/ref/, two pipelines NV_HIZ_IS_FIRST 1/0, dispatch schedule of NVHizVK::cmdUpdateHiz): bit-identical."""
+    from oracle import ref_binding
+    from vk_tessellated_clusters_b200 import api
+
+    try:
+        ref = ref_binding.ReferenceShaders(api.Config(), True)
+    except SystemExit as e:
+        pytest.skip(str(e))
+    depth = np.random.default_rng(w * 7919 + h).random((h, w), dtype=np.float32)
+    o = Oracle()
+    for _ in range(2):  # second update reuses the pyramid storage
+        o.update_hiz(depth)
+        ref.update_hiz(depth)
+    a, sa, ma = ref.get_hiz()
+    b, sb, mb = o.get_hiz()
+    assert (sa, ma) == (sb, mb)
+    assert a.tobytes() == b.tobytes()

@@ -110,3 +110,67 @@ def test_oracle_matches_reference_shaders(name, table, oracle_lib, ref_mod):
     assert (same_bits | close).all(), f"generated vertices: {int((~(same_bits | close)).sum())} words off"
     ncoll, ndiv = ref.simt_stats()
     assert ncoll > 0
+
+
+def _all_mode_hits(orc, scene, cfg, table, rng, per_mode=4000):
+    """hits on generated CLAS of every kind the frame produced: (clusterID word incl. mode tag, primitive id, instance)"""
+    _, sb = orc.readback()
+    n_temp, n_trans = int(sb["tempInstantiateCounter"]), int(sb["transBuildCounter"])
+    temps, tinst = orc.buffer("tempInstantiations", n_temp), orc.buffer("tempInstanceIDs", n_temp)
+    parts = orc.buffer("partTriangles")
+    entries = orc.lookup_entries()
+    out = []
+    mode = temps["clusterIdOffset"] >> 30
+    # mode 1: one tessellated part per CLAS; primitive ids = triangles of the part's pattern
+    for k in np.nonzero(mode == 1)[0][:: max(1, int((mode == 1).sum()) // 400)]:
+        cfg_word = int(parts[int(temps["clusterIdOffset"][k]) & 0x3FFFFFFF]["triangleID_config"]) >> 16
+        nt = int(entries[cfg_word & 0x7FFF][2])
+        out += [(int(temps["clusterIdOffset"][k]), t, int(tinst[k])) for t in range(nt)]
+    # mode 0: full clusters; the CLAS carries the template's cluster id = cluster index, primitive id = cluster triangle
+    for k in np.nonzero(mode == 0)[0][:200]:
+        g = scene.geometries[int(scene.instances[int(tinst[k])]["geometryID"])]
+        c = int(np.nonzero(np.asarray(g.templ_addr, np.uint64) == temps["clusterTemplateAddress"][k])[0][0])
+        out += [(c, t, int(tinst[k])) for t in range(int(g.clusters[c]["numTriangles"]))]
+    # modes 2 / 3: transient builds (1X subsets, 2X batches)
+    if n_trans:
+        trans, xinst = orc.buffer("transBuilds", n_trans), orc.buffer("transInstanceIDs", n_trans)
+        for k in range(0, n_trans, max(1, n_trans // 400)):
+            out += [(int(trans["clusterID"][k]), t, int(xinst[k])) for t in range(int(trans["packed"][k]) & 0x1FF)]
+    hits = np.zeros(len(out), api.HIT_DTYPE)
+    arr = np.array(out, dtype=np.int64).reshape(-1, 3)
+    hits["clusterID"], hits["primitiveID"], hits["instanceID"] = arr[:, 0], arr[:, 1], arr[:, 2]
+    b = rng.random((len(out), 2), dtype=np.float32)
+    b[:, 1] *= 1.0 - b[:, 0]
+    hits["barycentrics"] = b
+    return hits
+
+
+@pytest.mark.parametrize("name", ["mini", "split", "only_1x", "only_2x", "far_field", "linear_no_transient", "icosphere"])
+def test_hit_decode_matches_reference_closest_hit_shader(name, table, oracle_lib, ref_mod):
+    """the oracle's hit decode against main() of the reference's render_raytrace_clusters.rchit.glsl (compiled
+    for the host, cut where shading begins) on hits of all four cluster modes: every decoded field bit-identical.  The
+    reference masks a 2X hit's sub-triangle id with 4 (rchit:163), hence reference_quirk=True."""
+    from oracle.oracle_binding import Oracle
+
+    scene, fcs, cfg, hiz = _case(name)
+    try:
+        ref = ref_mod.ReferenceShaders(cfg, len(scene.textures) > 0)
+    except SystemExit as e:
+        pytest.skip(str(e))
+    orc = Oracle(cfg)
+    for b in (ref, orc):
+        b.set_tess_table(table)
+        b.set_scene(scene)
+    ref.frame(fcs)
+    _, rsb = ref.readback()
+    orc.set_addresses(rsb)
+    orc.set_driver_standin(0)
+    orc.frame(fcs)
+    hits = _all_mode_hits(orc, scene, cfg, table, np.random.default_rng(2342))
+    a, b = ref.resolve_hits(hits), orc.resolve_hits(hits, reference_quirk=True)
+    modes = set(np.unique(a["mode"]).tolist())
+    assert len(hits) > 0 and len(modes) > 0
+    if name == "mini":
+        assert modes == {0, 1, 2, 3}
+    for f in a.dtype.names:
+        assert np.array_equal(a[f].view(np.uint32), b[f].view(np.uint32)), f"{f} differs"
