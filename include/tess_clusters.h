@@ -178,6 +178,45 @@ TC_API int tc_resolve_hits(tc_context* ctx, const tc_hit* hits, uint32_t count, 
 TC_API int tc_emit_part_triangles(tc_context* ctx, uint32_t* indices, uint32_t* tags, uint64_t capacityTriangles,
                                   uint64_t* numTriangles, uint32_t flags);
 
+/* ---- raster-side batching of part triangles into meshlets ------------------------------
+ * The rasteriser of the reference draws the part triangles through a task shader that packs the parts of every
+ * 32-part group, in order, into batches of at most TC_RASTER_BATCH_VERTICES vertices and TC_RASTER_BATCH_TRIANGLES
+ * triangles - one mesh-shader workgroup ("meshlet") per batch instead of one per part
+ * (shaders/render_raster_clusters_batched.task.glsl:110-215, dispatched over ceil(parts / 32) workgroups:
+ * build_setup.comp.glsl:138-139, renderer_raster_clusters_tess.cpp:476).  tc_batch_part_triangles runs that packing
+ * on the part list of the last frame (the entries instantiate visited):
+ *  - tasks[g]    = the TaskExchange block workgroup g hands to its mesh workgroups (task.glsl:99-104) plus
+ *                  gl_TaskCountNV; batchStartCount entries at and beyond taskCount are zero (unwritten in the reference);
+ *  - meshlets[m] = one record per mesh workgroup in (group, batch) order with what the mesh shader derives first
+ *                  (render_raster_clusters_batched.mesh.glsl:124-151): first part, part count, vertex and triangle
+ *                  totals, and the exclusive running vertex / triangle sums (where a compute consumer puts the
+ *                  meshlet's output);
+ *  - counts      : the reference adds every group's batch count to readback.numBlasClusters (task.glsl:212); here the
+ *                  sum is returned as numMeshlets and the frame's Readback is left alone.
+ * Either array may be NULL / shorter than the result (nothing is written beyond the capacities; counts are complete).
+ * Pointers are host pointers unless TC_HIT_DEVICE_POINTERS is set (counts is always a host pointer). */
+#define TC_RASTER_BATCH_VERTICES 96u   /* TESS_RASTER_BATCH_VERTICES, shaders/shaderio_scene.h:57 */
+#define TC_RASTER_BATCH_TRIANGLES 121u /* TESS_RASTER_BATCH_TRIANGLES = TESSTABLE_MAX_TRIANGLES, shaderio_scene.h:46,58 */
+typedef struct tc_task_exchange {
+  uint16_t batchStartCount[32];    /* batch b: first part of the group | number of parts << 8 */
+  uint16_t prefixsumTriangles[32]; /* exclusive sums over the 32 lanes; lanes beyond the part list count 121 / 96 */
+  uint16_t prefixsumVertices[32];
+  uint32_t baseIndex;              /* group * 32 */
+  uint32_t taskCount;              /* gl_TaskCountNV */
+} tc_task_exchange;
+typedef struct tc_meshlet {
+  uint32_t firstPart;      /* TASK.baseIndex + batchStart */
+  uint32_t counts;         /* parts | vertices << 8 | triangles << 16 */
+  uint32_t vertexOffset;   /* vertices of all earlier meshlets */
+  uint32_t triangleOffset; /* triangles of all earlier meshlets */
+} tc_meshlet;
+typedef struct tc_batch_counts {
+  uint32_t numParts, numTaskGroups, numMeshlets, reserved;
+  uint64_t numVertices, numTriangles;
+} tc_batch_counts;
+TC_API int tc_batch_part_triangles(tc_context* ctx, tc_task_exchange* tasks, uint32_t taskCapacity, tc_meshlet* meshlets,
+                                   uint32_t meshletCapacity, tc_batch_counts* counts, uint32_t flags);
+
 /* ---- Renderer::render ---------------------------------------------------------------------------------
  * frameConstants points at two consecutive FrameConstants (current, last) `strideBytes` apart
  * (sizeof(shaderio::FrameConstants) for a reference caller, sizeof(tc_FrameConstants) otherwise).

@@ -35,6 +35,8 @@ REF_SHADER(blas_clusters_insert)
 REF_SHADER(hiz_first)
 REF_SHADER(hiz_rest)
 REF_SHADER(rchit)
+REF_SHADER(raster_task)
+void run_groups_raster_task(uint groupsX, void* out);
 void set_hit_rchit(uint clusterID, uint primitiveID, uint instanceID, float b0, float b1, void* out);
 }  // namespace glsl
 
@@ -424,6 +426,39 @@ REF_API int ref_resolve_hits(ref_context* c, const tc_hit* hits, uint32_t count,
     set_hit_rchit(hits[i].clusterID, hits[i].primitiveID, hits[i].instanceID, hits[i].barycentrics[0], hits[i].barycentrics[1], &out[i]);
     run_rchit(1);
   }
+  return TC_OK;
+}
+
+// ---- raster-side batching: shaders/render_raster_clusters_batched.task.glsl over the part list of the last frame ---------
+// dispatched like the rasteriser does (build_setup.comp.glsl:132-139: ceil(min(parts, MAX_PART_TRIANGLES) / 32) workgroups,
+// renderer_raster_clusters_tess.cpp:476).  Only the TaskExchange blocks come from here; the shader's
+// atomicAdd(readback.numBlasClusters, batchIndex) is captured as counts->numMeshlets and the frame's Readback restored.
+REF_API int ref_batch_part_triangles(ref_context* c, tc_task_exchange* tasks, uint32_t taskCapacity, tc_meshlet* meshlets, uint32_t /*meshletCapacity*/,
+                                     tc_batch_counts* counts, uint32_t /*flags*/)
+{
+  using namespace glsl;
+  if(meshlets)
+    return TC_ERR_INVALID_ARG;  // the mesh-shader side is not compiled here
+  struct B { const char* name; void* ptr; };
+  const B binds[] = {{"view", &c->frame[0]}, {"readback", &c->readback}, {"instances", c->instances.data()}, {"build", &c->build},
+                     {"buildRW", &c->build}, {"tessTable", &c->tessTable}, {"push", &c->push}};
+  for(const B& b : binds)
+    bind_raster_task(b.name, b.ptr);
+  const uint32_t parts  = std::min(c->build.partTriangleCounter, c->maxPartTriangles);
+  const uint32_t groups = (parts + 31) / 32;
+  std::vector<tc_task_exchange> all(groups);
+  const tc_Readback saved = c->readback;
+  c->readback.numBlasClusters = 0;
+  run_groups_raster_task(groups, all.data());
+  tc_batch_counts total{};
+  total.numParts      = parts;
+  total.numTaskGroups = groups;
+  total.numMeshlets   = c->readback.numBlasClusters;
+  c->readback         = saved;
+  for(uint32_t g = 0; g < groups && tasks && g < taskCapacity; g++)
+    tasks[g] = all[g];
+  if(counts)
+    *counts = total;
   return TC_OK;
 }
 

@@ -114,10 +114,44 @@ def rchit_prepare(src: str) -> str:
     return head + src[:cut] + RCHIT_EXPORT + "layout(local_size_x=1) in;\n"
 
 
+def raster_macro_set(macros: dict) -> dict:
+    """src/renderer_raster_clusters_tess.cpp:93-113: the rasteriser's configuration of the same frame (no transient builds,
+    batched meshlets on); none of the differences touches a struct layout the harness's buffers depend on"""
+    m = dict(macros, TARGETS_RASTERIZATION=1, TESS_RASTER_USE_BATCH=1, TESS_USE_1X_TRANSIENTBUILDS=0, TESS_USE_2X_TRANSIENTBUILDS=0, MESHSHADER_WORKGROUP_SIZE=32)
+    for k in ("MAX_GENERATED_CLUSTER_MEGS", "MAX_GENERATED_CLUSTERS", "MAX_GENERATED_VERTICES"):
+        m.pop(k, None)
+    return m
+
+
+def raster_task_prepare(src: str) -> str:
+    """task shader -> compute-style function: the taskNV output block becomes a plain struct the runner copies out after
+    every workgroup, gl_TaskCountNV a variable"""
+    src, n = re.subn(r"\bout\s+taskNV\s+TaskExchange\s*\{([^}]*)\}\s*TASK\s*;",
+                     r"struct TaskExchange_t {\1};\nstatic TaskExchange_t TASK; static uint gl_TaskCountNV;", src)
+    assert n == 1
+    return src
+
+
+RASTER_TASK_RUNNER = """void run_groups_raster_task(uint groupsX, void* out)  // out: 200-byte records (TaskExchange + gl_TaskCountNV)
+{
+  static_assert(sizeof(TaskExchange_t) == 196, "TaskExchange");
+  for(uint gx = 0; gx < groupsX; gx++)
+  {
+    memset(&TASK, 0, sizeof(TASK));
+    gl_TaskCountNV = 0;
+    Simt::get().runWorkgroup(&shader_main, _local_size_x * _local_size_y, gx, 32, _local_size_x, 0);
+    memcpy(static_cast<char*>(out) + size_t(gx) * 200, &TASK, 196);
+    memcpy(static_cast<char*>(out) + size_t(gx) * 200 + 196, &gl_TaskCountNV, 4);
+  }
+}"""
+
+
 def to_cpp(src: str, shader: str) -> str:
     out_pre = []  # emitted before the translated text
     if shader == "rchit":
         src = rchit_prepare(src)
+    if shader == "raster_task":
+        src = raster_task_prepare(src)
 
     # ---- float literals: GLSL literals are float, C++ literals are double
     def lit(m):
@@ -242,6 +276,7 @@ int bind_{shader}(const char* name, void* ptr)
   return 0;
 }}
 {RCHIT_SETTER if shader == "rchit" else ""}
+{RASTER_TASK_RUNNER if shader == "raster_task" else ""}
 uint local_size_{shader}() {{ return _local_size_x; }}
 void run_{shader}(uint groupsX, uint groupsY)
 {{
@@ -288,7 +323,8 @@ def build(a) -> str:
         return obj
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         rchit = ("rchit", "render_raytrace_clusters.rchit.glsl", dict(macros, RAYTRACING_PAYLOAD_INDEX=0))
-        objs = list(pool.map(compile_one, [(sh, sh, macros) for sh in SHADERS] + HIZ_PROGRAMS + [rchit]))
+        raster_task = ("raster_task", "render_raster_clusters_batched.task.glsl", raster_macro_set(macros))
+        objs = list(pool.map(compile_one, [(sh, sh, macros) for sh in SHADERS] + HIZ_PROGRAMS + [rchit, raster_task]))
     defs = [f"-DREF_{k}={v}" for k, v in macros.items()]
     with open(os.path.join(REF_SHADERS, "shaderio.h")) as fh:  # push-constant ids of build_setup.comp.glsl
         defs += [f"-DREF_{m.group(1)}={m.group(2)}" for m in re.finditer(r"^#define\s+(BUILD_SETUP_\w+)\s+(\d+)", fh.read(), flags=re.M)]

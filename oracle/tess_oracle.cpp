@@ -1517,6 +1517,89 @@ ORC_API int orc_emit_part_triangles(orc_context* c, uint32_t* indices, uint32_t*
   return TC_OK;
 }
 
+// ---- raster-side batching ------------------------------------------------------------------
+// main() of shaders/render_raster_clusters_batched.task.glsl:110-215, one workgroup = one subgroup of 32 lanes walked lane
+// by lane (ballot / shuffle spelled out over arrays), plus the header arithmetic of the mesh workgroup each batch launches
+// (render_raster_clusters_batched.mesh.glsl:124-151).  The part list is the one instantiate visited.
+ORC_API int orc_batch_part_triangles(orc_context* c, tc_task_exchange* tasks, uint32_t taskCapacity, tc_meshlet* meshlets, uint32_t meshletCapacity,
+                                     tc_batch_counts* counts, uint32_t /*flags*/)
+{
+  if(!c)
+    return TC_ERR_INVALID_ARG;
+  const uint32_t SG = 32;
+  const uint32_t partTotalCount = std::min(c->build.partTriangleCounter, c->validParts);
+  const uint32_t numGroups      = (partTotalCount + SG - 1) / SG;  // build_setup.comp.glsl:139
+  tc_batch_counts total{};
+  total.numParts      = partTotalCount;
+  total.numTaskGroups = numGroups;
+  for(uint32_t wg = 0; wg < numGroups; wg++)
+  {
+    tc_task_exchange TASK{};
+    const uint32_t partLocalCount = std::min(partTotalCount, wg * SG + SG) - wg * SG;  // task.glsl:118
+    uint32_t numVertices[SG], numTriangles[SG], sumVertices[SG], sumTriangles[SG];
+    uint32_t accV = 0, accT = 0;
+    for(uint32_t lane = 0; lane < SG; lane++)
+    {
+      const uint32_t partIndex = wg * SG + lane;
+      numVertices[lane]  = TC_RASTER_BATCH_VERTICES;  // :124-125
+      numTriangles[lane] = TC_RASTER_BATCH_TRIANGLES;
+      if(partIndex < partTotalCount)
+      {  // :129-134
+        const uint32_t cfg = c->partTriangles[partIndex].subTriangle.triangleID_config >> 16;
+        numVertices[lane]  = tess_getConfigVertexCount(*c, cfg);
+        numTriangles[lane] = tess_getConfigTriangleCount(*c, cfg);
+      }
+      accV += numVertices[lane];  // subgroupInclusiveAdd :137-138
+      accT += numTriangles[lane];
+      sumVertices[lane]  = accV;
+      sumTriangles[lane] = accT;
+      TASK.prefixsumVertices[lane]  = uint16_t(sumVertices[lane] - numVertices[lane]);  // :139-140
+      TASK.prefixsumTriangles[lane] = uint16_t(sumTriangles[lane] - numTriangles[lane]);
+    }
+    uint32_t batchIndex = 0, lastBatchStart = 0, lastBatchVertices = 0, lastBatchTriangles = 0, left = partLocalCount;
+    while(left != 0 && batchIndex < SG)
+    {  // :160-205
+      uint32_t voteFit = 0;
+      for(uint32_t lane = 0; lane < SG; lane++)
+      {
+        const uint32_t batchVertices = sumVertices[lane] - lastBatchVertices, batchTriangles = sumTriangles[lane] - lastBatchTriangles;  // wraps for earlier lanes
+        if(batchVertices <= TC_RASTER_BATCH_VERTICES && batchTriangles <= TC_RASTER_BATCH_TRIANGLES)
+          voteFit |= 1u << lane;
+      }
+      const uint32_t batchEnd   = 31u - uint32_t(__builtin_clz(voteFit));  // subgroupBallotFindMSB :170 (the batch's first part always fits)
+      const uint32_t batchStart = lastBatchStart, batchCount = 1 + batchEnd - batchStart;
+      TASK.batchStartCount[batchIndex] = uint16_t(batchStart | (batchCount << 8));  // :191
+      if(meshlets)
+      {  // mesh.glsl:124-151: totals of the batch from the prefix sums + the last part's own counts
+        const uint32_t nV = (TASK.prefixsumVertices[batchStart + batchCount - 1] - TASK.prefixsumVertices[batchStart]) + numVertices[batchEnd];
+        const uint32_t nT = (TASK.prefixsumTriangles[batchStart + batchCount - 1] - TASK.prefixsumTriangles[batchStart]) + numTriangles[batchEnd];
+        if(total.numMeshlets + batchIndex < meshletCapacity)
+          meshlets[total.numMeshlets + batchIndex] = tc_meshlet{wg * SG + batchStart, batchCount | (nV << 8) | (nT << 16), uint32_t(total.numVertices), uint32_t(total.numTriangles)};
+        total.numVertices += nV;
+        total.numTriangles += nT;
+      }
+      else
+      {
+        total.numVertices += sumVertices[batchEnd] - lastBatchVertices;
+        total.numTriangles += sumTriangles[batchEnd] - lastBatchTriangles;
+      }
+      lastBatchStart     = 1 + batchEnd;  // :196-198
+      lastBatchVertices  = sumVertices[batchEnd];
+      lastBatchTriangles = sumTriangles[batchEnd];
+      left -= std::min(batchCount, left);
+      batchIndex++;
+    }
+    TASK.baseIndex = wg * SG;  // :209-213
+    TASK.taskCount = batchIndex;
+    total.numMeshlets += batchIndex;
+    if(tasks && wg < taskCapacity)
+      tasks[wg] = TASK;
+  }
+  if(counts)
+    *counts = total;
+  return TC_OK;
+}
+
 // ---- far-HiZ pyramid builder -------------------------------------------------------------------------------
 // NVHizVK::setupUpdateInfos + TextureInfo::getShaderFactors (src/nvhiz_vk.cpp:29-40, :278-309), hizFarLevel 0
 ORC_API int orc_hiz_info(uint32_t width, uint32_t height, uint32_t* size, uint32_t* mipLevels, float factors[4], float* sizeMax)

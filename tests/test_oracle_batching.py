@@ -1,0 +1,144 @@
+"""SURVEY 8f rank 3 on the CPU: the oracle's restatement of shaders/render_raster_clusters_batched.task.glsl
+
+* against the reference's own task shader, compiled for the host by oracle/ref/translate.py (the `out taskNV` block becomes a
+  struct the harness copies out after every workgroup): every TaskExchange block and gl_TaskCountNV byte for byte, and the sum
+  the shader adds to readback.numBlasClusters;
+* against the properties the packing must have whatever the part list is (limits respected, greedy = maximal, every part in
+  exactly one batch, in order);
+* the meshlet records against an independent numpy derivation from the TaskExchange blocks following the mesh shader's
+  header arithmetic (render_raster_clusters_batched.mesh.glsl:124-151).
+"""
+import numpy as np
+import pytest
+
+from tests.scene_cases import case
+from vk_tessellated_clusters_b200 import api
+
+CASES = ["plane", "plane_ragged", "split", "mini", "icosphere", "linear_no_transient", "far_field", "split_factor_4", "undisplaced"]
+
+
+def part_counts(binding, table_entries, num_parts):
+    """(numVertices, numTriangles) of every part of the list the operator visits"""
+    parts = binding.buffer("partTriangles")[:num_parts]
+    cfg = parts["triangleID_config"].astype(np.uint32) >> 16
+    e = table_entries[cfg & 0x7FFF]
+    return e[:, 3].astype(np.int64), e[:, 2].astype(np.int64)
+
+
+def meshlets_from_tasks(tasks, nv, nt):
+    """mesh.glsl:124-151, one record per (group, batch)"""
+    out = []
+    vo = to = 0
+    for t in tasks:
+        base = int(t["baseIndex"])
+        for b in range(int(t["taskCount"])):
+            info = int(t["batchStartCount"][b])
+            start, count = info & 0xFF, info >> 8
+            last = base + start + count - 1
+            v = int(t["prefixsumVertices"][start + count - 1]) - int(t["prefixsumVertices"][start]) + int(nv[last])
+            tr = int(t["prefixsumTriangles"][start + count - 1]) - int(t["prefixsumTriangles"][start]) + int(nt[last])
+            out.append((base + start, count | (v << 8) | (tr << 16), vo, to))
+            vo += v
+            to += tr
+    a = np.zeros(len(out), api.MESHLET_DTYPE)
+    if out:
+        arr = np.array(out, dtype=np.uint64)
+        for i, f in enumerate(api.MESHLET_DTYPE.names):
+            a[f] = arr[:, i]
+    return a, vo, to
+
+
+def check_packing(tasks, meshlets, counts, nv, nt):
+    n = counts["numParts"]
+    assert counts["numTaskGroups"] == (n + 31) // 32 == len(tasks)
+    assert counts["numMeshlets"] == int(tasks["taskCount"].sum()) == len(meshlets)
+    assert counts["numVertices"] == int(nv.sum()) and counts["numTriangles"] == int(nt.sum())
+    nxt = 0
+    for m in meshlets:
+        first, c = int(m["firstPart"]), int(m["counts"])
+        cnt, v, t = c & 0xFF, (c >> 8) & 0xFF, c >> 16
+        assert first == nxt and cnt >= 1  # every part exactly once, in order
+        assert first // 32 == (first + cnt - 1) // 32  # a batch never leaves its 32-part group
+        assert v == int(nv[first:first + cnt].sum()) <= api.RASTER_BATCH_VERTICES
+        assert t == int(nt[first:first + cnt].sum()) <= api.RASTER_BATCH_TRIANGLES
+        nxt = first + cnt
+        if nxt < n and nxt % 32 != 0:  # greedy: the next part of the group would not have fitted
+            assert v + int(nv[nxt]) > api.RASTER_BATCH_VERTICES or t + int(nt[nxt]) > api.RASTER_BATCH_TRIANGLES
+    assert nxt == n
+    for g, t in enumerate(tasks):
+        assert int(t["baseIndex"]) == g * 32
+        lo, hi = g * 32, min(n, g * 32 + 32)
+        pv = np.concatenate([nv[lo:hi], np.full(32 - (hi - lo), api.RASTER_BATCH_VERTICES)])
+        pt = np.concatenate([nt[lo:hi], np.full(32 - (hi - lo), api.RASTER_BATCH_TRIANGLES)])
+        assert np.array_equal(t["prefixsumVertices"], (np.cumsum(pv) - pv).astype(np.uint16))
+        assert np.array_equal(t["prefixsumTriangles"], (np.cumsum(pt) - pt).astype(np.uint16))
+        assert not t["batchStartCount"][int(t["taskCount"]):].any()
+
+
+@pytest.fixture(scope="module")
+def ref_mod():
+    from oracle import ref_binding
+
+    if not ref_binding.reference_available():
+        import glob
+        import os
+
+        if not glob.glob(os.path.join(os.path.dirname(ref_binding.__file__), "_ref", "libtess_ref_*.so")):
+            pytest.skip("no /root/reference and no prebuilt oracle/_ref")
+    return ref_binding
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_batching_matches_reference_task_shader(name, table, oracle_lib, ref_mod):
+    from oracle.oracle_binding import Oracle
+
+    scene, fcs, cfg, hiz = case(name)
+    try:
+        ref = ref_mod.ReferenceShaders(cfg, len(scene.textures) > 0)
+    except SystemExit as e:
+        pytest.skip(str(e))
+    orc = Oracle(cfg)
+    for b in (ref, orc):
+        b.set_tess_table(table)
+        b.set_scene(scene)
+        if hiz is not None:
+            b.set_hiz(*hiz)
+    ref.frame(fcs)
+    _, rsb = ref.readback()
+    orc.set_addresses(rsb)
+    orc.set_driver_standin(0)
+    orc.frame(fcs)
+    rb_before, _ = ref.readback()
+    rt, _, rc = ref.batch_part_triangles(want_meshlets=False)
+    ot, om, oc = orc.batch_part_triangles()
+    rb_after, _ = ref.readback()
+    assert rb_before["numBlasClusters"] == rb_after["numBlasClusters"]  # the frame's statistics are left alone
+    assert rc["numParts"] == oc["numParts"] and rc["numTaskGroups"] == oc["numTaskGroups"]
+    assert rc["numMeshlets"] == oc["numMeshlets"]  # = what the shader adds to readback.numBlasClusters
+    assert rt.tobytes() == ot.tobytes(), "TaskExchange blocks differ from the reference task shader's"
+    nv, nt = part_counts(orc, orc.lookup_entries(), oc["numParts"])
+    check_packing(ot, om, oc, nv, nt)
+    mm, vo, to = meshlets_from_tasks(rt, nv, nt)
+    assert mm.tobytes() == om.tobytes()
+
+
+@pytest.mark.parametrize("name", ["plane", "deep_split", "overflow_parts", "full"])
+def test_batching_properties(name, table, oracle_lib):
+    from oracle.oracle_binding import Oracle
+
+    scene, fcs, cfg, hiz = case(name)
+    orc = Oracle(cfg)
+    orc.set_tess_table(table)
+    orc.set_scene(scene)
+    orc.frame(fcs)
+    tasks, meshlets, counts = orc.batch_part_triangles()
+    nv, nt = part_counts(orc, orc.lookup_entries(), counts["numParts"])
+    check_packing(tasks, meshlets, counts, nv, nt)
+    if name == "full":
+        assert counts["numParts"] == 0 and counts["numMeshlets"] == 0
+    else:
+        assert counts["numMeshlets"] > 0
+    # capacities: nothing beyond them, counts complete
+    t2, m2, c2 = orc.batch_part_triangles(task_capacity=max(1, len(tasks) // 2), meshlet_capacity=max(1, len(meshlets) // 3))
+    assert c2 == counts
+    assert t2.tobytes() == tasks[:len(t2)].tobytes() and m2.tobytes() == meshlets[:len(m2)].tobytes()

@@ -276,3 +276,53 @@ def test_part_triangles_and_hit_decode_bit_exact(name, table, oracle_lib):
     finally:
         gpu.close()
         orc.close()
+
+
+# ---- raster-side batching of the part list into meshlets, CUDA vs oracle, bit-exact ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["plane", "plane_ragged", "split", "deep_split", "mini", "icosphere", "culling", "full", "overflow_parts", "linear_no_transient"])
+def test_batch_part_triangles_bit_exact(name, table, oracle_lib):
+    from tests.test_oracle_batching import check_packing, part_counts
+
+    scene, fcs, cfg, hiz = case(name)
+    gpu, orc = make_pair(scene, table, cfg, hiz)
+    try:
+        gpu.frame(fcs)
+        orc.frame(fcs)
+        gtk, gm, gc = gpu.batch_part_triangles()
+        otk, om, oc = orc.batch_part_triangles()
+        assert gc == oc
+        assert gtk.tobytes() == otk.tobytes() and gm.tobytes() == om.tobytes()
+        nv, nt = part_counts(orc, orc.lookup_entries(), oc["numParts"])
+        check_packing(gtk, gm, gc, nv, nt)
+        # a second call (fresh look-back epoch) with short capacities: same prefix, complete counts; tasks only
+        t2, m2, c2 = gpu.batch_part_triangles(task_capacity=max(1, len(gtk) // 2), meshlet_capacity=max(1, len(gm) // 3))
+        assert c2 == gc and t2.tobytes() == gtk[: len(t2)].tobytes() and m2.tobytes() == gm[: len(m2)].tobytes()
+        t3, m3, c3 = gpu.batch_part_triangles(want_meshlets=False)
+        assert m3 is None and c3 == gc and t3.tobytes() == gtk.tobytes()
+    finally:
+        gpu.close()
+        orc.close()
+
+
+@pytest.mark.gpu
+def test_batch_part_triangles_against_reference_task_shader(table):
+    """CUDA directly against the reference's task shader (prebuilt oracle/_ref), no oracle in between."""
+    from oracle import ref_binding
+
+    scene, fcs, cfg, hiz = case("split")
+    try:
+        ref = ref_binding.ReferenceShaders(cfg, len(scene.textures) > 0)
+    except SystemExit as e:
+        pytest.skip(str(e))
+    gpu = api.TessClusters(cfg)
+    for b in (ref, gpu):
+        b.set_tess_table(table)
+        b.set_scene(scene)
+    ref.frame(fcs)
+    gpu.frame(fcs)
+    rt, _, rc = ref.batch_part_triangles(want_meshlets=False)
+    gt, gm, gc = gpu.batch_part_triangles()
+    assert rc["numParts"] == gc["numParts"] > 0 and rc["numMeshlets"] == gc["numMeshlets"] == len(gm)
+    assert rt.tobytes() == gt.tobytes()
+    gpu.close()

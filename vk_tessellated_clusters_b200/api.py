@@ -181,6 +181,14 @@ HIT_DTYPE = np.dtype([("instanceID", "<u4"), ("clusterID", "<u4"), ("primitiveID
 HIT_BASE_DTYPE = np.dtype([("mode", "<u4"), ("clusterID", "<u4"), ("triangleID", "<u4"), ("subTriangleID", "<u4"), ("cfg", "<u4"), ("baseIndices", "<u4", 3),
                            ("partID", "<u4"), ("baryWeightBase", "<f4", 3)])
 assert HIT_DTYPE.itemsize == 20 and HIT_BASE_DTYPE.itemsize == 48
+# include/tess_clusters.h: tc_task_exchange / tc_meshlet / tc_batch_counts
+TASK_EXCHANGE_DTYPE = np.dtype([("batchStartCount", "<u2", 32), ("prefixsumTriangles", "<u2", 32), ("prefixsumVertices", "<u2", 32), ("baseIndex", "<u4"),
+                                ("taskCount", "<u4")])
+MESHLET_DTYPE = np.dtype([("firstPart", "<u4"), ("counts", "<u4"), ("vertexOffset", "<u4"), ("triangleOffset", "<u4")])
+BATCH_COUNTS_DTYPE = np.dtype([("numParts", "<u4"), ("numTaskGroups", "<u4"), ("numMeshlets", "<u4"), ("reserved", "<u4"), ("numVertices", "<u8"),
+                               ("numTriangles", "<u8")])
+assert TASK_EXCHANGE_DTYPE.itemsize == 200 and MESHLET_DTYPE.itemsize == 16 and BATCH_COUNTS_DTYPE.itemsize == 32
+RASTER_BATCH_VERTICES, RASTER_BATCH_TRIANGLES = 96, 121
 
 
 class Binding:
@@ -307,6 +315,21 @@ class Binding:
         self._check(self._fn("emit_part_triangles")(self._ctx, _ptr(idx), _ptr(tags), C.c_uint64(capacity), C.byref(total), C.c_uint32(0)), "emit_part_triangles")
         n = min(capacity, total.value)
         return idx[:n], tags[:n], total.value
+
+    def batch_part_triangles(self, want_meshlets: bool = True, task_capacity: int | None = None, meshlet_capacity: int | None = None):
+        """render_raster_clusters_batched.task over the last frame's part list
+        -> (tasks TASK_EXCHANGE_DTYPE[groups], meshlets MESHLET_DTYPE[n] or None, counts dict)"""
+        counts = np.zeros(1, BATCH_COUNTS_DTYPE)
+        fn = self._fn("batch_part_triangles")
+        self._check(fn(self._ctx, None, C.c_uint32(0), None, C.c_uint32(0), _ptr(counts), C.c_uint32(0)), "batch_part_triangles")
+        groups = int(counts["numTaskGroups"][0]) if task_capacity is None else task_capacity
+        nmesh = int(counts["numMeshlets"][0]) if meshlet_capacity is None else meshlet_capacity
+        tasks = np.zeros(max(groups, 1), TASK_EXCHANGE_DTYPE)
+        meshlets = np.zeros(max(nmesh, 1), MESHLET_DTYPE) if want_meshlets else None
+        self._check(fn(self._ctx, _ptr(tasks), C.c_uint32(groups), _ptr(meshlets) if want_meshlets else None, C.c_uint32(nmesh if want_meshlets else 0), _ptr(counts),
+                       C.c_uint32(0)), "batch_part_triangles")
+        c = {k: int(counts[k][0]) for k in BATCH_COUNTS_DTYPE.names}
+        return tasks[:min(groups, c["numTaskGroups"])], (meshlets[:min(nmesh, c["numMeshlets"])] if want_meshlets else None), c
 
     def set_driver_standin(self, mode: int):
         self._check(self._fn("set_driver_standin")(self._ctx, C.c_uint32(mode)), "set_driver_standin")

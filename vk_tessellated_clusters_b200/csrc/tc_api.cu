@@ -83,6 +83,8 @@ struct tc_context
   uint32_t          maxMini = 0;
   uint32_t*         dEmitState = nullptr;  // tc_emit_part_triangles: ticket, pad, total (u64)
   uint32_t          emitCalls = 0;
+  uint32_t*         dBatchState = nullptr;  // tc_batch_part_triangles: ticket, pad, tc_batch_counts
+  uint32_t          batchCalls = 0;
   uint32_t*         dShardBase   = nullptr;
 
   // path buffers
@@ -456,6 +458,7 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   TRY_RC(dalloc(c->dFrame, sizeof(FrameStaging)));
   TRY_RC(dalloc(c->dShardCounts, sizeof(tc_shard_counts)));
   TRY_RC(dalloc(c->dEmitState, 16));
+  TRY_RC(dalloc(c->dBatchState, 64));
   TRY_RC(dalloc(c->dMailbox, tc_shard_mailbox_bytes()));
   CUDA_TRY(cudaMemset(c->dMailbox, 0xFF, tc_shard_mailbox_bytes()));  // no slot carries a valid frame number yet
   TRY_RC(dalloc(c->dShardStatus, 16));
@@ -528,7 +531,7 @@ TC_API void tc_destroy(tc_context* c)
   drop_graph(c);
   free_scene(c);
   dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dClusterVertexDst); dfree(c->dFrame);
-  dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState); dfree(c->dMiniList); dfree(c->dMailbox); dfree(c->dShardStatus);
+  dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState); dfree(c->dBatchState); dfree(c->dMiniList); dfree(c->dMailbox); dfree(c->dShardStatus);
   if(c->hFrame)
     cudaFreeHost(c->hFrame);
   dfree(c->visibleClusters); dfree(c->splitTriangles); dfree(c->partTriangles); dfree(c->genVertices);
@@ -1158,6 +1161,67 @@ TC_API int tc_emit_part_triangles(tc_context* c, uint32_t* indices, uint32_t* ta
     return fail(TC_ERR_CUDA, cudaGetErrorString(e));
   if(numTriangles)
     *numTriangles = total;
+  return TC_OK;
+}
+
+TC_API int tc_batch_part_triangles(tc_context* c, tc_task_exchange* tasks, uint32_t taskCapacity, tc_meshlet* meshlets, uint32_t meshletCapacity,
+                                   tc_batch_counts* counts, uint32_t flags)
+{
+  int rc = check_ready(c);
+  if(rc)
+    return rc;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const bool onDevice = (flags & TC_HIT_DEVICE_POINTERS) != 0;
+  if(!tasks)
+    taskCapacity = 0;
+  if(!meshlets)
+    meshletCapacity = 0;
+  tc_task_exchange* dTasks    = taskCapacity ? tasks : nullptr;
+  tc_meshlet*       dMeshlets = meshletCapacity ? meshlets : nullptr;
+  if(!onDevice)
+  {
+    dTasks = nullptr;
+    dMeshlets = nullptr;
+    if(taskCapacity && (rc = dalloc(dTasks, size_t(taskCapacity) * sizeof(tc_task_exchange))))
+      return rc;
+    if(meshletCapacity && (rc = dalloc(dMeshlets, size_t(meshletCapacity) * sizeof(tc_meshlet))))
+    {
+      dfree(dTasks);
+      return rc;
+    }
+  }
+  // look-back flags of this launch differ from every frame's and every tc_emit_part_triangles call's
+  const uint32_t epoch = 0x30000000u + (++c->batchCalls & 0x0FFFFFFFu);
+  cudaError_t e = cudaMemsetAsync(c->dBatchState, 0, 64, c->stream);
+  if(e == cudaSuccess)
+  {
+    tc::launch_batch_part_triangles(c->params, dTasks, taskCapacity, dMeshlets, meshletCapacity, c->dBatchState, epoch, uint32_t(c->numSMs * 4), c->stream);
+    e = cudaGetLastError();
+  }
+  tc_batch_counts total{};
+  if(e == cudaSuccess && (counts || !onDevice))
+  {
+    e = cudaMemcpyAsync(&total, c->dBatchState + 2, sizeof(total), cudaMemcpyDeviceToHost, c->stream);
+    if(e == cudaSuccess)
+      e = cudaStreamSynchronize(c->stream);
+  }
+  if(e == cudaSuccess && !onDevice)
+  {
+    const size_t nT = std::min<size_t>(total.numTaskGroups, taskCapacity), nM = std::min<size_t>(total.numMeshlets, meshletCapacity);
+    if(nT)
+      e = cudaMemcpy(tasks, dTasks, nT * sizeof(tc_task_exchange), cudaMemcpyDeviceToHost);
+    if(e == cudaSuccess && nM)
+      e = cudaMemcpy(meshlets, dMeshlets, nM * sizeof(tc_meshlet), cudaMemcpyDeviceToHost);
+  }
+  if(!onDevice)
+  {
+    dfree(dTasks);
+    dfree(dMeshlets);
+  }
+  if(e != cudaSuccess)
+    return fail(TC_ERR_CUDA, cudaGetErrorString(e));
+  if(counts)
+    *counts = total;
   return TC_OK;
 }
 

@@ -2863,6 +2863,210 @@ __global__ void __launch_bounds__(128) k_emit_part_triangles(Params p, uint32_t*
   }
 }
 
+// Raster-side batching: main() of render_raster_clusters_batched.task.glsl.
+// The shader spends a whole subgroup on one 32-part group and one ballot + MSB round per batch; mapped 1:1 that is ~15
+// warp instructions per BATCH and the kernel is issue bound (measured 88 us for 68 k groups / 1.45 M batches).  The packing
+// is a greedy scan (a batch is the longest run of consecutive parts whose vertex and triangle sums stay within the limits:
+// the fitting lanes of the ballot are a prefix of the remaining ones), so here a LANE owns a group and walks its 32 parts
+// serially out of shared memory - ~10 thread instructions per part, all 32 lanes busy with different groups:
+//   A  the warp loads (numVertices | numTriangles << 8) of 32 groups x 32 parts, coalesced, rows padded to 33 words;
+//   B  lane = group: prefix sums (u16 pairs written back over the consumed row words), batches closed into slots
+//      {start | count << 8 | vertices << 16 | triangles << 24, vertices | triangles << 16 of the group's earlier batches};
+//   scan: tile = one CTA (128 groups); a tile publishes its (batches, vertices, triangles) and SUMS the aggregates of all
+//      earlier tiles (no inclusive-prefix chain: every wait is for a tile's phase B only; tiles are handed out by ticket, so
+//      earlier tiles are always running) - output order is canonical, no atomics;
+//   C  the 32 TaskExchange blocks of the warp (6400 contiguous bytes) leave as 50 coalesced 32-bit stores per lane;
+//   D  the warp's meshlet records, flattened over its groups, as coalesced 128-bit stores.
+// state[0] = tile ticket, state[2..9] = tc_batch_counts
+constexpr int BATCH_WARPS      = 4;
+constexpr int BATCH_ROW        = 33;  // lane g walking row g is bank-conflict free
+constexpr int BATCH_SLOT_ROW   = 65;  // 32 batch slots x 2 words
+constexpr int BATCH_WARP_WORDS = 32 * BATCH_ROW + 32 * BATCH_SLOT_ROW;
+constexpr int BATCH_TASK_WORDS = int(sizeof(tc_task_exchange) / 4);
+size_t batch_smem_bytes() { return size_t(BATCH_WARPS) * BATCH_WARP_WORDS * 4; }
+
+__global__ void __launch_bounds__(BATCH_WARPS * 32, 4) k_batch_part_triangles(Params p, uint32_t* tasks, uint32_t taskCapacity, uint4* meshlets,
+                                                                               uint32_t meshletCapacity, uint32_t* state, uint32_t epoch)
+{
+  extern __shared__ __align__(16) uint32_t batchSmem[];
+  __shared__ uint32_t shTile, shAgg[BATCH_WARPS][3], shBase[BATCH_WARPS][3];
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  uint32_t* rows  = batchSmem + warp * BATCH_WARP_WORDS;
+  uint32_t* slots = rows + 32 * BATCH_ROW;
+  const uint32_t numParts = p.state->numParts, numGroups = (numParts + 31) / 32, numTiles = (numGroups + BATCH_WARPS * 32 - 1) / (BATCH_WARPS * 32);
+  const tc_TessTriangleInfo* parts = reinterpret_cast<const tc_TessTriangleInfo*>(p.build->partTriangles);
+  uint4* descs = p.lookback16;
+  const uint32_t FLAG = (epoch << 2) | 1u;
+  if(numTiles == 0)
+  {
+    if(blockIdx.x == 0 && threadIdx.x < 8)
+      state[2 + threadIdx.x] = 0u;
+    return;
+  }
+  while(true)
+  {
+    if(threadIdx.x == 0)
+      shTile = atomicAdd(&state[0], 1u);
+    __syncthreads();
+    const uint32_t tile = shTile;
+    if(tile >= numTiles)
+      break;
+    const uint32_t groupBase = (tile * BATCH_WARPS + warp) * 32;
+    // ---- A (fully unrolled: all 32 record loads of a lane in flight, then the 32 table-entry loads)
+#pragma unroll
+    for(uint32_t r = 0; r < 32; r++)
+    {
+      const uint32_t partIndex = (groupBase + r) * 32 + lane;
+      uint32_t w = TC_RASTER_BATCH_VERTICES | (TC_RASTER_BATCH_TRIANGLES << 8);  // task.glsl:124-125
+      if(partIndex < numParts)
+      {
+        const tc_TessTableEntry e = tess_entry(p, __ldcs(&parts[partIndex].subTriangle.triangleID_config) >> 16);
+        w = uint32_t(e.numVertices) | (uint32_t(e.numTriangles) << 8);
+      }
+      rows[r * BATCH_ROW + lane] = w;
+    }
+    __syncwarp();
+    // ---- B
+    const uint32_t group = groupBase + lane;
+    const uint32_t cnt   = group < numGroups ? min(numParts - group * 32, 32u) : 0u;  // :118
+    uint32_t nb = 0, gV = 0, gT = 0;  // closed batches of the group: count, vertices, triangles
+    {
+      uint32_t* row  = rows + lane * BATCH_ROW;
+      uint32_t* slot = slots + lane * BATCH_SLOT_ROW;
+      uint32_t runV = 0, runT = 0, pairV = 0, pairT = 0, bStart = 0, bV = 0, bT = 0;
+#pragma unroll 4
+      for(uint32_t i = 0; i < 32; i++)
+      {
+        const uint32_t w = row[i], nV = w & 0xFFu, nT = w >> 8;
+        if(i & 1u)
+        {  // prefixsumTriangles / prefixsumVertices of parts i-1 and i as u16 pairs, over row words that were already consumed
+          row[i - 1] = pairT | (runT << 16);
+          row[i]     = pairV | (runV << 16);
+        }
+        else
+        {
+          pairT = runT; pairV = runV;
+        }
+        runV += nV; runT += nT;
+        if(i < cnt)
+        {
+          if(i != bStart && (bV + nV > TC_RASTER_BATCH_VERTICES || bT + nT > TC_RASTER_BATCH_TRIANGLES))
+          {  // part i does not fit: the batch ends at i - 1 (= subgroupBallotFindMSB of the fitting lanes, :169-170)
+            slot[2 * nb]     = bStart | ((i - bStart) << 8) | (bV << 16) | (bT << 24);
+            slot[2 * nb + 1] = gV | (gT << 16);
+            gV += bV; gT += bT; nb++;
+            bStart = i; bV = 0; bT = 0;
+          }
+          bV += nV; bT += nT;
+        }
+      }
+      if(cnt)
+      {
+        slot[2 * nb]     = bStart | ((cnt - bStart) << 8) | (bV << 16) | (bT << 24);
+        slot[2 * nb + 1] = gV | (gT << 16);
+        gV += bV; gT += bT; nb++;
+      }
+    }
+    const uint32_t incM = warp_inclusive_add(nb), incV = warp_inclusive_add(gV), incT = warp_inclusive_add(gT);
+    if(lane == 31)
+    {
+      shAgg[warp][0] = incM; shAgg[warp][1] = incV; shAgg[warp][2] = incT;
+    }
+    // ---- C: the warp's 32 consecutive TaskExchange blocks, one group per step (words 0-15 batchStartCount, 16-31
+    //         prefixsumTriangles, 32-47 prefixsumVertices, 48 baseIndex, 49 taskCount): lane = word, then word 32 + lane.
+    //         Needs no offsets, so warps 1.. write theirs while warp 0 sums the earlier tiles' aggregates.
+    auto write_tasks = [&]() {
+      if(!tasks)
+        return;
+      const uint32_t h = lane & 15u;
+      for(uint32_t gl = 0; gl < 32; gl++)
+      {
+        const uint32_t g = groupBase + gl;
+        if(g >= numGroups || g >= taskCapacity)
+          break;  // warp-uniform
+        const uint32_t  M    = __shfl_sync(0xffffffffu, nb, gl);
+        const uint32_t* srow = slots + gl * BATCH_SLOT_ROW;
+        const uint32_t* prow = rows + gl * BATCH_ROW;
+        const uint32_t  lo = 2 * h < M ? srow[4 * h] & 0xFFFFu : 0u, hi = 2 * h + 1 < M ? srow[4 * h + 2] & 0xFFFFu : 0u;
+        const uint32_t  pt = prow[2 * h], pv = prow[2 * h + 1];
+        uint32_t* dst = tasks + size_t(g) * BATCH_TASK_WORDS;
+        __stcs(dst + lane, lane < 16 ? (lo | (hi << 16)) : pt);
+        if(lane < 18)
+          __stcs(dst + 32 + lane, lane < 16 ? pv : (lane == 16 ? g * 32 : M));
+      }
+    };
+    __syncwarp();
+    if(warp != 0)
+      write_tasks();
+    __syncthreads();
+    // ---- scan over tiles
+    if(warp == 0)
+    {
+      uint32_t aM = 0, aV = 0, aT = 0;
+      for(int w = 0; w < BATCH_WARPS; w++)
+      {
+        aM += shAgg[w][0]; aV += shAgg[w][1]; aT += shAgg[w][2];
+      }
+      if(lane == 0)
+        st_desc16(&descs[tile], make_uint4(FLAG, aM, aV, aT));
+      uint32_t sM = 0, sV = 0, sT = 0;
+      for(uint32_t base = 0; base < tile; base += 128)
+      {
+        uint4 w[4];
+#pragma unroll
+        for(int k = 0; k < 4; k++)
+        {
+          const uint32_t t = base + k * 32 + lane;
+          w[k] = t < tile ? ld_desc16(&descs[t]) : make_uint4(FLAG, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for(int k = 0; k < 4; k++)
+        {
+          const uint32_t t = base + k * 32 + lane;
+          while(w[k].x != FLAG)
+            w[k] = ld_desc16(&descs[t]);
+          sM += w[k].y; sV += w[k].z; sT += w[k].w;
+        }
+      }
+      sM = warp_sum(sM); sV = warp_sum(sV); sT = warp_sum(sT);
+      if(lane == 0)
+      {
+        uint32_t m = sM, v = sV, t = sT;
+        for(int w = 0; w < BATCH_WARPS; w++)
+        {
+          shBase[w][0] = m; shBase[w][1] = v; shBase[w][2] = t;
+          m += shAgg[w][0]; v += shAgg[w][1]; t += shAgg[w][2];
+        }
+        if(tile == numTiles - 1)
+        {
+          state[2] = numParts; state[3] = numGroups; state[4] = m; state[5] = 0u;
+          *reinterpret_cast<unsigned long long*>(state + 6) = v;
+          *reinterpret_cast<unsigned long long*>(state + 8) = t;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- D: meshlet records, one group per step, lane = batch
+    if(meshlets)
+    {
+      const uint32_t myM = shBase[warp][0] + incM - nb, myV = shBase[warp][1] + incV - gV, myT = shBase[warp][2] + incT - gT;  // of lane's group
+      for(uint32_t gl = 0; gl < 32; gl++)
+      {
+        const uint32_t M = __shfl_sync(0xffffffffu, nb, gl), m0 = __shfl_sync(0xffffffffu, myM, gl);
+        const uint32_t v0 = __shfl_sync(0xffffffffu, myV, gl), t0 = __shfl_sync(0xffffffffu, myT, gl);
+        if(lane < M && m0 + lane < meshletCapacity)
+        {
+          const uint32_t w0 = slots[gl * BATCH_SLOT_ROW + 2 * lane], w1 = slots[gl * BATCH_SLOT_ROW + 2 * lane + 1];
+          __stcs(&meshlets[m0 + lane], make_uint4((groupBase + gl) * 32 + (w0 & 0xFFu), w0 >> 8, v0 + (w1 & 0xFFFFu), t0 + (w1 >> 16)));
+        }
+      }
+    }
+    if(warp == 0)
+      write_tasks();
+    __syncwarp();
+  }
+}
+
 __global__ void k_flush_l2(float4* buf, size_t n)
 {
   for(size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
@@ -2895,6 +3099,8 @@ int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, Kerne
     if(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, int(instantiate_smem_bytes())) != cudaSuccess)
       return -1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->instantiate, k_instantiate<1, false>, INST_THREADS, instantiate_smem_bytes());
+  if(cudaFuncSetAttribute(k_batch_part_triangles, cudaFuncAttributeMaxDynamicSharedMemorySize, int(batch_smem_bytes())) != cudaSuccess)
+    return -1;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -3005,6 +3211,12 @@ void launch_resolve_hits(const Params& p, const tc_hit* hits, uint32_t count, tc
 void launch_emit_part_triangles(const Params& p, uint32_t* indices, uint32_t* tags, unsigned long long capacity, uint32_t* state, uint32_t epoch, uint32_t grid, cudaStream_t s)
 {
   k_emit_part_triangles<<<grid, 128, 0, s>>>(p, indices, tags, capacity, state, epoch);
+}
+void launch_batch_part_triangles(const Params& p, tc_task_exchange* tasks, uint32_t taskCapacity, tc_meshlet* meshlets, uint32_t meshletCapacity, uint32_t* state,
+                                 uint32_t epoch, uint32_t grid, cudaStream_t s)
+{
+  static_assert(sizeof(tc_task_exchange) == 200 && sizeof(tc_meshlet) == 16 && sizeof(tc_batch_counts) == 32, "SURVEY 8f rank 3 records");
+  k_batch_part_triangles<<<grid, BATCH_WARPS * 32, batch_smem_bytes(), s>>>(p, reinterpret_cast<uint32_t*>(tasks), taskCapacity, reinterpret_cast<uint4*>(meshlets), meshletCapacity, state, epoch);
 }
 void launch_flush_l2(void* buf, size_t bytes, cudaStream_t s) { k_flush_l2<<<1184, 256, 0, s>>>(reinterpret_cast<float4*>(buf), bytes / 16); }
 

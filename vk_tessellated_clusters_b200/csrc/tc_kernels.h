@@ -53,6 +53,8 @@ void launch_hiz_update(const HizPass& q, cudaStream_t s);
 void launch_resolve_hits(const Params& p, const tc_hit* hits, uint32_t count, tc_hit_base* out, bool referenceQuirk, cudaStream_t s);
 void launch_emit_part_triangles(const Params& p, uint32_t* indices, uint32_t* tags, unsigned long long capacity, uint32_t* state, uint32_t epoch, uint32_t grid,
                                 cudaStream_t s);
+void launch_batch_part_triangles(const Params& p, tc_task_exchange* tasks, uint32_t taskCapacity, tc_meshlet* meshlets, uint32_t meshletCapacity, uint32_t* state,
+                                 uint32_t epoch, uint32_t grid, cudaStream_t s);
 void launch_flush_l2(void* buf, size_t bytes, cudaStream_t s);
 
 }  // namespace tc
