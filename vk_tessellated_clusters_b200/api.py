@@ -15,7 +15,7 @@ from . import scenes as S
 from .table import TessTable
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtess_clusters.so")
+LIB_PATH = os.environ.get("TC_LIB_PATH") or os.path.join(_HERE, "csrc", "libtess_clusters.so")  # TC_LIB_PATH: kernel-variant experiments (tools/build_variants.sh)
 
 # ---- flags (tc_config.flags) ----
 FLAG_PN_DISPLACEMENT = 1 << 0
