@@ -572,6 +572,63 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
       }
     }
     uint32_t needMask = __ballot_sync(0xffffffffu, needL);
+    // Lane-parallel fast paths: clusters whose whole contribution is ONE full-cluster template instantiation need no
+    // warp-cooperative work, so the 32 clusters of the chunk are handled at once (lane = cluster) instead of one per trip of
+    // the serial loop below.  Scenes dominated by hidden instances / untessellated clusters are bound by exactly this.
+    if(MODE == 0 && flag_culling(p))
+    {  // count pass, hidden instance: every triangle counts as simple (cluster_classify.comp.glsl:208-211)
+      const bool hiddenL = needL && (instanceStates[cinfoL.instanceID] & TC_INSTANCE_VISIBLE_BIT) == 0;
+      if(hiddenL)
+      {
+        ScanTuple t;
+        t.zero();
+        t.v[T_TEMP] = 1;
+        t.v[T_VERT] = chL.x & 0xFFFF;
+        t.d = __ldg(reinterpret_cast<const uint32_t*>(p.instances[cinfoL.instanceID].clusterTemplateInstantiatonSizes) + cinfoL.clusterID);
+        st_tuple(&tuples[chunk + lane], t);
+        p.classMeta[chunk + lane]        = chL.x >> 16;
+        p.clusterVertexDst[chunk + lane] = ~0u;
+      }
+      const uint32_t hiddenMask = __ballot_sync(0xffffffffu, hiddenL);
+      accClusterLevel += __popc(hiddenMask);
+      needMask &= ~hiddenMask;
+    }
+    if(MODE == 1)
+    {  // cluster-level emit, full cluster (:271-446): records + the destination of its displaced vertex copy
+      const uint32_t nV = chL.x & 0xFFFF, nT = chL.x >> 16;
+      const bool     fullL = needL && metaL == nT;
+      bool           okL   = false;
+      if(fullL)
+      {
+        const uint32_t           vi   = chunk + lane;
+        const tc_RenderInstance& in   = p.instances[cinfoL.instanceID];
+        const ScanTuple          run  = ld_tuple(&tuples[vi]);
+        const uint32_t           size = __ldg(reinterpret_cast<const uint32_t*>(in.clusterTemplateInstantiatonSizes) + cinfoL.clusterID);
+        const uint32_t genOffset = run.v[T_TEMP] + run.v[T_TRANS], vertexOffset = run.v[T_VERT], tempOffset = run.v[T_TEMP];
+        const bool fail = (vertexOffset + nV > p.maxGenVertices) || (genOffset + 1 > p.maxGenClusters) || (run.d + size > p.maxGenDataBytes);
+        if(!fail)
+        {
+          tc_TemplateInstantiateInfo ti;
+          ti.clusterIdOffset        = 0;
+          ti.geometryIndexOffset    = 0;
+          ti.clusterTemplateAddress = __ldg(reinterpret_cast<const unsigned long long*>(in.clusterTemplateAdresses) + cinfoL.clusterID);
+          ti.vertexBufferAddress    = genVerticesAddr + (unsigned long long)(uint32_t)(vertexOffset * 4u * 3u);
+          ti.vertexBufferStride     = 12;
+          tempInstantiations[tempOffset]   = ti;
+          tempInstanceIDs[tempOffset]      = cinfoL.instanceID;
+          tempClusterAddresses[tempOffset] = genClusterData + run.d;
+          if(p.driverStandin)
+            tempClusterSizes[tempOffset] = size;
+          p.clusterVertexDst[vi] = vertexOffset;
+          okL = true;
+        }
+      }
+      const uint32_t fullMask = __ballot_sync(0xffffffffu, fullL);
+      accSuccTemp += __popc(__ballot_sync(0xffffffffu, okL));
+      accTris += warp_sum(okL ? nT : 0u);
+      accFull += __popc(fullMask);
+      needMask &= ~fullMask;
+    }
   while(needMask)
   {
     const uint32_t src = __ffs(needMask) - 1;
