@@ -490,8 +490,11 @@ struct ClassifyShared  // only the CTA epilogue's statistics: one cluster per wa
 //   MODE 2 (emit, triangle level): part / split records and 2X mini batches.  Clusters that are entirely simple are skipped.
 // Splitting the emit step keeps both kernels light (registers -> occupancy): scenes dominated by untessellated clusters
 // (hidden instances, far field) are pure streaming work in MODE 1, tessellated scenes are pure record writing in MODE 2.
+#ifndef TC_CLASSIFY0_MIN_CTAS
+#define TC_CLASSIFY0_MIN_CTAS 4  // count pass: 64 registers, 32 warps per SM (one cluster per warp in flight: latency bound)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_CTAS : 3) k_cluster_classify(Params p)
+__global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_CTAS : (MODE == 0 ? TC_CLASSIFY0_MIN_CTAS : 3)) k_cluster_classify(Params p)
 {
   pdl_prologue();
   extern __shared__ __align__(16) uint8_t smemRaw[];
@@ -669,7 +672,20 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
 #pragma unroll
         for(int k = 0; k < 16; k++)
           m[k] = inst->worldMatrix[k];
+        // the index bytes of the first two triangle rounds are requested together with the positions: one memory round
+        // trip for both instead of two back to back (the warp has a single cluster in flight)
+        const uint8_t* localTriangles = reinterpret_cast<const uint8_t*>(inst->clusterLocalTriangles) + firstLocalTriangle;
+        uint32_t pre[2][3] = {{0, 0, 0}, {0, 0, 0}};
         if(!hidden)
+        {
+#pragma unroll
+          for(int r = 0; r < 2; r++)
+            if(r * 32 + lane < numTriangles)
+            {
+              pre[r][0] = __ldg(localTriangles + (r * 32 + lane) * 3 + 0);
+              pre[r][1] = __ldg(localTriangles + (r * 32 + lane) * 3 + 1);
+              pre[r][2] = __ldg(localTriangles + (r * 32 + lane) * 3 + 2);
+            }
           for(uint32_t v = lane; v < numVertices; v += 32)
           {
             F3 o = ld_f3(positions, firstLocalVertex + v);
@@ -677,12 +693,12 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
             float d = xdistance3(w, fcst.eye);
             reinterpret_cast<float4*>(sWorld)[v] = make_float4(w.x, w.y, w.z, d);
           }
+        }
         __syncwarp();
         if(hidden)
           simpleCount = numTriangles;
         else
         {
-          const uint8_t* localTriangles = reinterpret_cast<const uint8_t*>(inst->clusterLocalTriangles) + firstLocalTriangle;
           for(uint32_t base = 0; base < numTriangles; base += 32)
           {
             uint32_t tri = base + lane;
@@ -690,7 +706,15 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
             uint32_t f[3] = {1, 1, 1};
             if(tv)
             {
-              uint32_t i0 = __ldg(localTriangles + tri * 3 + 0), i1 = __ldg(localTriangles + tri * 3 + 1), i2 = __ldg(localTriangles + tri * 3 + 2);
+              uint32_t i0, i1, i2;
+              if(base < 64)
+              {
+                i0 = base == 0 ? pre[0][0] : pre[1][0]; i1 = base == 0 ? pre[0][1] : pre[1][1]; i2 = base == 0 ? pre[0][2] : pre[1][2];
+              }
+              else
+              {
+                i0 = __ldg(localTriangles + tri * 3 + 0); i1 = __ldg(localTriangles + tri * 3 + 1); i2 = __ldg(localTriangles + tri * 3 + 2);
+              }
               float4   a = reinterpret_cast<const float4*>(sWorld)[i0], b = reinterpret_cast<const float4*>(sWorld)[i1], c = reinterpret_cast<const float4*>(sWorld)[i2];
               tess_factors(fcst, F3{a.x, a.y, a.z}, F3{b.x, b.y, b.z}, F3{c.x, c.y, c.z}, a.w, b.w, c.w, f);
               const uint32_t w0 = f[0] | (i0 << 24), w1 = f[1] | (i1 << 24), w2 = f[2] | (i2 << 24);
@@ -3198,7 +3222,7 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
 {
   const size_t smem = classify_smem_bytes(p.clusterVertices, p.clusterTriangles);
   launch_pdl(k_cluster_classify<0>, grid, CLASSIFY_THREADS, smem, s, p);
-  launch_pdl(k_classify_scan, 148, CSCAN_THREADS, 0, s, p, epochCounter);
+  launch_pdl(k_classify_scan, 148 * 3, CSCAN_THREADS, 0, s, p, epochCounter);  // 3 CTAs per SM at 80 registers; tiles are handed out by ticket
   launch_pdl(k_cluster_classify<1>, grid, CLASSIFY_THREADS, smem, s, p);
   launch_pdl(k_cluster_classify<2>, grid, CLASSIFY_THREADS, smem, s, p);
   {  // displaced cluster-vertex copies recorded by the cluster-level emit kernel
