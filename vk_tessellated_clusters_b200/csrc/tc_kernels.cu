@@ -1403,6 +1403,12 @@ __global__ void __launch_bounds__(MINI_WARPS * 32, 6) k_mini_vertices(Params p)
   {
     const uint32_t idx = base + lane;
     hdr[lane] = make_uint2(0u, 0u);  // .y = 0: this lane has no mini triangle
+#ifndef TC_MINI_NO_PREFETCH
+    // the record of the warp's NEXT iteration is requested now (no registers held): the record load heads a chain of four
+    // dependent round trips (record -> instance -> base attributes -> gathers) and was 18 % of the stall samples
+    if(idx + warpsTotal * 32 < count)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(&p.miniList[size_t(idx + warpsTotal * 32) * 2]));
+#endif
     if(idx < count)
     {
     const uint4 a = __ldcs(&p.miniList[size_t(idx) * 2]), b = __ldcs(&p.miniList[size_t(idx) * 2 + 1]);
