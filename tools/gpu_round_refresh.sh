@@ -12,3 +12,4 @@ for k in 3 5; do
 done
 python tools/bench_hiz.py 2>&1 | tail -2 | tee gpurun_out/${TAG}_hiz.txt
 python tools/bench_emit.py 2>&1 | tail -3 | tee gpurun_out/${TAG}_emit.txt
+python tools/bench_batch.py 2>&1 | tail -1 | tee gpurun_out/${TAG}_batch.txt
