@@ -201,12 +201,15 @@ __device__ __forceinline__ FactorConsts load_factor_consts(const Params& p)
   return c;
 }
 
-// tess_getTessFactors (tessellation.glsl:78-99) on three world-space points whose eye distances are given
-__device__ __forceinline__ void tess_factors(const FactorConsts& c, F3 a, F3 b, F3 cc, float dA, float dB, float dC, uint32_t f[3])
+// 1 / max(near, distance to the eye) of ONE point.  tess_getTessFactors scales an edge by 1 / max(near, min(dA, dB)); a
+// correctly rounded reciprocal is monotonic, so that equals max(r(dA), r(dB)) bit for bit with r(d) = rn(1 / max(near, d)):
+// the division is paid once per vertex instead of three times per triangle.
+__device__ __forceinline__ float tess_eye_scale(const FactorConsts& c, F3 w) { return xdiv(1.0f, fmaxf(c.nearPlane, xdistance3(w, c.eye))); }
+
+// tess_getTessFactors (tessellation.glsl:78-99) on three world-space points whose eye scales (tess_eye_scale) are given
+__device__ __forceinline__ void tess_factors(const FactorConsts& c, F3 a, F3 b, F3 cc, float rA, float rB, float rC, uint32_t f[3])
 {
-  float sx = xdiv(1.0f, fmaxf(c.nearPlane, fminf(dA, dB)));
-  float sy = xdiv(1.0f, fmaxf(c.nearPlane, fminf(dB, dC)));
-  float sz = xdiv(1.0f, fmaxf(c.nearPlane, fminf(dC, dA)));
+  float sx = fmaxf(rA, rB), sy = fmaxf(rB, rC), sz = fmaxf(rC, rA);
   float ex = xdistance3(a, b), ey = xdistance3(b, cc), ez = xdistance3(cc, a);
   float fx = rintf(xmul(xmul(xmul(ex, sx), c.viewportY), c.tessRate));  // round(): ties-to-even, see DESIGN.md
   float fy = rintf(xmul(xmul(xmul(ey, sy), c.viewportY), c.tessRate));

@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
 
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t maxV = p.clusterVertices, maxT = p.clusterTriangles;
-  // per-warp regions: object positions [maxV*3], world positions + eye distance [maxV*4], factors [maxT*3]
+  // per-warp regions: object positions [maxV*3], world positions + eye scale [maxV*4], factors [maxT*3]
   const uint32_t warpWords = maxV * 3 + maxV * 4 + maxT * 3;
   float*    sObj     = reinterpret_cast<float*>(smemRaw) + size_t(warp) * warpWords;
   float*    sWorld   = sObj + maxV * 3;
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
           {
             F3 o = ld_f3(positions, firstLocalVertex + v);
             F3 w = xtransform_point(m, o);
-            float d = xdistance3(w, fcst.eye);
+            float d = tess_eye_scale(fcst, w);  // 1 / max(near, eye distance)
             reinterpret_cast<float4*>(sWorld)[v] = make_float4(w.x, w.y, w.z, d);
           }
         }
@@ -1627,7 +1627,7 @@ __global__ void __launch_bounds__(CSCAN_THREADS) k_classify_scan(Params p, const
 // Warps are independent (no CTA barrier in the tile loop): a tile is 32 consecutive items handled by ONE warp --
 // the reference's subgroup -- with its own ticket and a 16-byte decoupled look-back over (split, part) counts.
 //   V. lane = (item, pattern vertex): every vertex of the items' split patterns is evaluated ONCE (barycentric
-//      encode, world position, eye distance) into a per-warp shared-memory cache; a (3,3,3) pattern has 9 children
+//      encode, world position, eye scale) into a per-warp shared-memory cache; a (3,3,3) pattern has 9 children
 //      but only 10 distinct vertices, the child-level formulation evaluated 27 corners -- twice.
 //   C. lane = child, runs of 32 virtual threads exactly like processAllSubTasks: factors from the cached vertices,
 //      split / part decision, (cfg, rotation, kind) remembered as a 16-bit code; per-run counts.
@@ -1648,7 +1648,7 @@ constexpr int SPLIT_CCACHE       = 512;      // cached child codes per warp
 
 struct SplitWarpShared
 {
-  float4   vWorld[SPLIT_VCACHE];  // world position, eye distance
+  float4   vWorld[SPLIT_VCACHE];  // world position, eye scale (tess_eye_scale)
   uint32_t vEnc[SPLIT_VCACHE];    // encoded barycentrics inside the base triangle
   // per child: new cfg (bit 15 flip, low 12 bits lookup index) | rotation << 12 (0 none, 1 .yzx, 2 .zxy) | bit 14: split again
   uint16_t code[SPLIT_CCACHE];
@@ -1900,7 +1900,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
           const uint32_t enc = tess_encodeBarycentrics(xinterp3(baseBary, q));
           const F3       w   = xinterp3(bp, tess_decodeBarycentrics(enc));
           sh.vEnc[t]   = enc;
-          sh.vWorld[t] = make_float4(w.x, w.y, w.z, xdistance3(w, fcst.eye));
+          sh.vWorld[t] = make_float4(w.x, w.y, w.z, tess_eye_scale(fcst, w));
         }
       }
       __syncwarp();
@@ -1961,7 +1961,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
           for(int k = 0; k < 3; k++)
           {
             w[k] = xinterp3(bp, tess_decodeBarycentrics(enc[k]));
-            d[k] = xdistance3(w[k], fcst.eye);
+            d[k] = tess_eye_scale(fcst, w[k]);
           }
           code = split_child_code(fcst, p.splitFactor, w, d);
         }
@@ -2037,7 +2037,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
           for(int k = 0; k < 3; k++)
           {
             w[k] = xinterp3(bp, tess_decodeBarycentrics(enc[k]));
-            d[k] = xdistance3(w[k], fcst.eye);
+            d[k] = tess_eye_scale(fcst, w[k]);
           }
           code = split_child_code(fcst, p.splitFactor, w, d);
         }
