@@ -242,14 +242,19 @@ def main():
             ev.record_stop()
             frame_ms.append(ev.elapsed_ms())
     else:
+        # all K frames are enqueued back to back (events around each frame, the L2 flush between them outside the events) and
+        # the host synchronises once at the end: with a host sync per frame every launch hiccup of ONE rank's Python thread
+        # is paid by all ranks, because a frame waits on the device for its peers' counts
+        pairs = []
         for _ in range(args.steps):
             gpu.flush_l2()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             gathered = one_frame(use_graph)
             e1.record()
-            e1.synchronize()
-            frame_ms.append(e0.elapsed_time(e1))
+            pairs.append((e0, e1))
+        torch.cuda.synchronize()
+        frame_ms = [a.elapsed_time(b) for a, b in pairs]
     total_ms = float(np.sum(frame_ms))
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -290,19 +295,23 @@ def main():
     gpu.sync()
     clocks = sampler.stop()
 
+    # ---- roofline of the dominant kernel (k_instantiate), measured live with CUDA events on its stream ----
+    # (every rank runs these frames: with the peer exchange a frame waits for its peers' counts, a rank running alone
+    # would sit out the one-second time-out of the mailbox wait in every frame)
+    gpu.enable_stage_timers(True)
+    inst_ms, stage_acc = [], {}
+    for _ in range(max(5, min(args.steps, 20))):
+        gpu.flush_l2()
+        one_frame(False)
+        st = gpu.stage_times()
+        inst_ms.append(st["PrepInstantiate"])
+        for k, v in st.items():
+            stage_acc.setdefault(k, []).append(v)
+    gpu.enable_stage_timers(False)
+    if world > 1:
+        dist.barrier()
     line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (k_instantiate), measured live with CUDA events on its stream ----
-        gpu.enable_stage_timers(True)
-        inst_ms, stage_acc = [], {}
-        for _ in range(max(5, min(args.steps, 20))):
-            gpu.flush_l2()
-            gpu.frame(fcs)
-            st = gpu.stage_times()
-            inst_ms.append(st["PrepInstantiate"])
-            for k, v in st.items():
-                stage_acc.setdefault(k, []).append(v)
-        gpu.enable_stage_timers(False)
         rb, sb = gpu.readback()
         alg_bytes, n_parts, n_verts = instantiate_algorithmic_bytes(gpu, sb)
         peaks = {}
