@@ -289,9 +289,13 @@ def main():
         e2e_s = float(t.item())
 
     # keep the GPU busy a little longer so the 100 ms sampler sees clocks under load, then stop it
-    t_end = time.perf_counter() + 0.5
-    while time.perf_counter() < t_end:
-        one_frame(False)
+    if world == 1:
+        t_end = time.perf_counter() + 0.5
+        while time.perf_counter() < t_end:
+            one_frame(False)
+    else:  # the same number of frames on every rank: the peer exchange matches frames by number
+        for _ in range(700):
+            one_frame(False)
     gpu.sync()
     clocks = sampler.stop()
 
