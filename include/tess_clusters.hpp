@@ -96,6 +96,13 @@ public:
   // NVHizVK::cmdUpdateHiz: build the far pyramid from last frame's depth image (device pointer)
   bool updateHiz(const float* depthDevice, uint32_t width, uint32_t height) { return tc_update_hiz(m_ctx, depthDevice, width, height, 1) == TC_OK || failed(); }
 
+  /* RendererRasterClustersTess' batched part-triangle draw, task stage (src/renderer_raster_clusters_tess.cpp:476,
+   * shaders/render_raster_clusters_batched.task.glsl): device-resident TaskExchange blocks and meshlet list of the last frame */
+  bool batchPartTriangles(tc_task_exchange* tasksDevice, uint32_t taskCapacity, tc_meshlet* meshletsDevice, uint32_t meshletCapacity, tc_batch_counts& counts)
+  {
+    return tc_batch_part_triangles(m_ctx, tasksDevice, taskCapacity, meshletsDevice, meshletCapacity, &counts, TC_HIT_DEVICE_POINTERS) == TC_OK;
+  }
+
   /* Renderer::render: frame.frameConstants / frameConstantsLast are consecutive in FrameConfig (stride = sizeof one) */
   void render(const void* frameConstantsPair, size_t strideBytes, bool freezeCulling = false)
   {
