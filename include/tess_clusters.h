@@ -217,6 +217,22 @@ typedef struct tc_batch_counts {
 TC_API int tc_batch_part_triangles(tc_context* ctx, tc_task_exchange* tasks, uint32_t taskCapacity, tc_meshlet* meshlets,
                                    uint32_t meshletCapacity, tc_batch_counts* counts, uint32_t flags);
 
+/* Mesh stage of the same draw, primitive half (render_raster_clusters_batched.mesh.glsl:312-380): for every triangle of every
+ * meshlet, in meshlet order (= part order), what the mesh workgroup writes to gl_PrimitiveIndicesNV and gl_PrimitiveID:
+ *  - indices: three meshlet-local vertex indices (u8): the pattern triangle of the part's config (second and third swapped for
+ *    flipped configs, tess_getConfigTriangleVertices) + the part's first vertex inside its meshlet (taskVertexStart, :149);
+ *  - primitiveIDs: (triangleID & 0xFF) | ((partID | 1) << 8) with partID the xor of the part's three encoded corners as in
+ *    :356-362 (view.visualize != VISUALIZE_TRIANGLES).
+ * Triangle t of meshlet m sits at meshlets[m].triangleOffset + t.  The vertex half needs no kernel when the frame did not
+ * overflow: the object-space vertices the mesh shader evaluates for meshlet m (:214-306 before the world transform) are the
+ * ones instantiate generated for its parts, genVertices[V0 + meshlets[m].vertexOffset ...] with V0 = the vertexBufferAddress of
+ * part 0's instantiate record - so (meshlets, indices, genVertices) is a complete, fuller-cluster view of the part list, in the
+ * layout a u8-indexed CLAS build or a compute rasteriser consumes.
+ * Either array may be NULL; numTriangles receives the total even when it exceeds the capacity.  With TC_HIT_DEVICE_POINTERS
+ * `indices` must be 4-byte and `primitiveIDs` 16-byte aligned (quads of triangles leave as whole words). */
+TC_API int tc_emit_meshlet_triangles(tc_context* ctx, uint8_t* indices, uint32_t* primitiveIDs, uint64_t capacityTriangles,
+                                     uint64_t* numTriangles, uint32_t flags);
+
 /* ---- Renderer::render ---------------------------------------------------------------------------------
  * frameConstants points at two consecutive FrameConstants (current, last) `strideBytes` apart
  * (sizeof(shaderio::FrameConstants) for a reference caller, sizeof(tc_FrameConstants) otherwise).

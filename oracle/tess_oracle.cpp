@@ -1600,6 +1600,63 @@ ORC_API int orc_batch_part_triangles(orc_context* c, tc_task_exchange* tasks, ui
   return TC_OK;
 }
 
+// mesh stage of the batched draw, primitive half: main() of shaders/render_raster_clusters_batched.mesh.glsl:124-151 (header)
+// and :312-380 (triangle loop), one mesh workgroup per batch of every TaskExchange block, walked triangle by triangle
+ORC_API int orc_emit_meshlet_triangles(orc_context* c, uint8_t* indices, uint32_t* primitiveIDs, uint64_t capacityTriangles, uint64_t* numTriangles, uint32_t /*flags*/)
+{
+  if(!c)
+    return TC_ERR_INVALID_ARG;
+  tc_batch_counts counts{};
+  int rc = orc_batch_part_triangles(c, nullptr, 0, nullptr, 0, &counts, 0);
+  if(rc)
+    return rc;
+  std::vector<tc_task_exchange> tasks(counts.numTaskGroups ? counts.numTaskGroups : 1);
+  rc = orc_batch_part_triangles(c, tasks.data(), counts.numTaskGroups, nullptr, 0, &counts, 0);
+  if(rc)
+    return rc;
+  uint64_t n = 0;
+  for(uint32_t g = 0; g < counts.numTaskGroups; g++)
+  {
+    const tc_task_exchange& TASK = tasks[g];
+    for(uint32_t wg = 0; wg < TASK.taskCount; wg++)
+    {  // gl_WorkGroupID.x = wg
+      const uint32_t batchInfo = TASK.batchStartCount[wg], batchStart = batchInfo & 0xFF, batchCount = batchInfo >> 8;  // :126-128
+      const uint32_t baseNumVertices = TASK.prefixsumVertices[batchStart];                                            // :135
+      for(uint32_t task = 0; task < batchCount; task++)
+      {  // the triangle loop visits the tasks of the batch in order, triLocal ascending (:318-380)
+        const tc_TessTriangleInfo& tessInfo = c->partTriangles[TASK.baseIndex + batchStart + task];  // :133
+        const uint32_t vertexStart = uint32_t(TASK.prefixsumVertices[batchStart + task]) - baseNumVertices;  // :149
+        const uint32_t triangleID = tessInfo.subTriangle.triangleID_config & 0xFFFF, cfg = tessInfo.subTriangle.triangleID_config >> 16;
+        uint32_t partID = 0;
+        for(uint32_t v = 0; v < 3; v++)
+        {
+          const uint32_t vtxTemp = tessInfo.subTriangle.vtxEncoded[v];
+          partID ^= (vtxTemp >> 20) | ((vtxTemp >> 4) & 0xFFF);  // :361
+        }
+        const uint32_t numTris = tess_getConfigTriangleCount(*c, cfg);
+        for(uint32_t triLocal = 0; triLocal < numTris; triLocal++, n++)
+        {
+          if(n >= capacityTriangles)
+            continue;
+          uint32_t v[3];
+          tess_getConfigTriangleVertices(*c, cfg, triLocal, v);  // :352
+          if(indices)
+          {
+            indices[n * 3 + 0] = uint8_t(v[0] + vertexStart);  // :369-371
+            indices[n * 3 + 1] = uint8_t(v[1] + vertexStart);
+            indices[n * 3 + 2] = uint8_t(v[2] + vertexStart);
+          }
+          if(primitiveIDs)
+            primitiveIDs[n] = (triangleID & 0xFF) | ((partID | 1) << 8);  // :372
+        }
+      }
+    }
+  }
+  if(numTriangles)
+    *numTriangles = n;
+  return TC_OK;
+}
+
 // ---- far-HiZ pyramid builder -------------------------------------------------------------------------------
 // NVHizVK::setupUpdateInfos + TextureInfo::getShaderFactors (src/nvhiz_vk.cpp:29-40, :278-309), hizFarLevel 0
 ORC_API int orc_hiz_info(uint32_t width, uint32_t height, uint32_t* size, uint32_t* mipLevels, float factors[4], float* sizeMax)

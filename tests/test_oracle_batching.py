@@ -142,3 +142,49 @@ def test_batching_properties(name, table, oracle_lib):
     t2, m2, c2 = orc.batch_part_triangles(task_capacity=max(1, len(tasks) // 2), meshlet_capacity=max(1, len(meshlets) // 3))
     assert c2 == counts
     assert t2.tobytes() == tasks[:len(t2)].tobytes() and m2.tobytes() == meshlets[:len(m2)].tobytes()
+
+
+def meshlet_of_triangle(meshlets):
+    """index of the meshlet every triangle of the flat triangle list belongs to"""
+    return np.repeat(np.arange(len(meshlets)), (meshlets["counts"] >> 16).astype(np.int64))
+
+
+def check_meshlet_triangles(b, meshlets, counts, idx, ids, total):
+    """the primitive half of the mesh stage against what the rest of the path already pins: the meshlet-local indices, rebased
+    with the meshlet's vertex offset, must be the very index triples tc_emit_part_triangles lists for the instantiated parts
+    (the CLAS templates' triangles), and the primitive ids follow from the part records"""
+    assert total == counts["numTriangles"] == len(idx) == len(ids)
+    if total == 0:
+        return
+    m = meshlet_of_triangle(meshlets)
+    nv = ((meshlets["counts"] >> 8) & 0xFF).astype(np.int64)
+    assert (idx.astype(np.int64) < nv[m][:, None]).all()  # every index inside its meshlet
+    fi, ft, fn = b.emit_part_triangles()
+    _, sb = b.readback()
+    recs = b.buffer("tempInstantiations", int(sb["tempInstantiateCounter"]), sb) if b.prefix == "tc_" else b.buffer("tempInstantiations", int(sb["tempInstantiateCounter"]))
+    part_recs = recs[(recs["clusterIdOffset"] >> 30) == 1]
+    if fn == total and len(part_recs) == counts["numParts"]:  # nothing was dropped: instantiate-record order = part order
+        v0 = int(part_recs["vertexBufferAddress"][0] - sb["genVertices"]) // 12
+        glob = v0 + meshlets["vertexOffset"].astype(np.int64)[m][:, None] + idx.astype(np.int64)
+        assert np.array_equal(glob, fi.astype(np.int64)), "meshlet-local indices do not rebase to the instantiated parts' triangles"
+        parts = (b.buffer("partTriangles", None, sb) if b.prefix == "tc_" else b.buffer("partTriangles"))[ft[:, 0] & 0x3FFFFFFF]
+        pid = np.zeros(len(parts), np.uint32)
+        for k in range(3):
+            pid ^= (parts["vtxEncoded"][:, k] >> 20) | ((parts["vtxEncoded"][:, k] >> 4) & 0xFFF)
+        assert np.array_equal(ids, (parts["triangleID_config"] & 0xFF) | ((pid | 1) << 8))
+
+
+@pytest.mark.parametrize("name", ["plane", "split", "deep_split", "icosphere", "linear_no_transient", "mini", "overflow_parts", "full"])
+def test_meshlet_triangles_oracle(name, table, oracle_lib):
+    from oracle.oracle_binding import Oracle
+
+    scene, fcs, cfg, hiz = case(name)
+    orc = Oracle(cfg)
+    orc.set_tess_table(table)
+    orc.set_scene(scene)
+    orc.frame(fcs)
+    tasks, meshlets, counts = orc.batch_part_triangles()
+    idx, ids, total = orc.emit_meshlet_triangles()
+    check_meshlet_triangles(orc, meshlets, counts, idx, ids, total)
+    i2, d2, t2 = orc.emit_meshlet_triangles(capacity=max(1, total // 3))
+    assert t2 == total and i2.tobytes() == idx[: len(i2)].tobytes() and d2.tobytes() == ids[: len(d2)].tobytes()

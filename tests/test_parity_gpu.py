@@ -326,3 +326,26 @@ def test_batch_part_triangles_against_reference_task_shader(table):
     assert rc["numParts"] == gc["numParts"] > 0 and rc["numMeshlets"] == gc["numMeshlets"] == len(gm)
     assert rt.tobytes() == gt.tobytes()
     gpu.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["plane", "plane_ragged", "split", "deep_split", "mini", "icosphere", "culling", "full", "overflow_parts", "linear_no_transient"])
+def test_meshlet_triangles_bit_exact(name, table, oracle_lib):
+    """mesh stage of the batched draw, primitive half: CUDA vs oracle byte for byte, and the closed loop with tc_emit_part_triangles"""
+    from tests.test_oracle_batching import check_meshlet_triangles
+
+    scene, fcs, cfg, hiz = case(name)
+    gpu, orc = make_pair(scene, table, cfg, hiz)
+    try:
+        gpu.frame(fcs)
+        orc.frame(fcs)
+        gi, gd, gn = gpu.emit_meshlet_triangles()
+        oi, od, on = orc.emit_meshlet_triangles()
+        assert gn == on and gi.tobytes() == oi.tobytes() and gd.tobytes() == od.tobytes()
+        _, gm, gc = gpu.batch_part_triangles()
+        check_meshlet_triangles(gpu, gm, gc, gi, gd, gn)
+        gi2, gd2, gn2 = gpu.emit_meshlet_triangles(capacity=max(1, gn // 3))
+        assert gn2 == gn and gi2.tobytes() == gi[: len(gi2)].tobytes() and gd2.tobytes() == gd[: len(gd2)].tobytes()
+    finally:
+        gpu.close()
+        orc.close()

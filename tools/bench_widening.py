@@ -116,6 +116,21 @@ line("tc_batch_part_triangles", c["numParts"], "parts", t, c["numParts"] * 24 + 
      {"meshlets": c["numMeshlets"], "parts_per_meshlet": c["numParts"] / max(1, c["numMeshlets"])})
 del tasks, mesh
 
+# ---- rank 3, mesh stage (primitive half): tc_emit_meshlet_triangles --------------------------------------------------------
+nt = c["numTriangles"]
+midx = torch.empty(nt * 3, dtype=torch.uint8, device="cuda")
+mids = torch.empty(nt, dtype=torch.int32, device="cuda")
+fn2 = gpu.lib.tc_emit_meshlet_triangles
+t = timed(lambda: gpu._check(fn2(gpu._ctx, C.c_void_p(midx.data_ptr()), C.c_void_p(mids.data_ptr()), C.c_uint64(nt), None, C.c_uint32(1)), "meshlet triangles"))
+gpu.sync()
+cpu_s = parity = None
+if orc:
+    cpu_s, (oi, od, on) = cpu_timed(lambda: orc.emit_meshlet_triangles(capacity=nt), reps=1)
+    parity = bool(on == nt and midx.cpu().numpy().tobytes() == oi.tobytes() and mids.cpu().numpy().view(np.uint32).tobytes() == od.tobytes())
+    del oi, od
+line("tc_emit_meshlet_triangles", nt, "triangles", t, c["numParts"] * 24 + nt * 7, cpu_s, parity, {"parts": c["numParts"]})
+del midx, mids
+
 # ---- rank 2: tc_update_hiz -----------------------------------------------------------------------------------------------
 w, h = 3840, 2160
 depth = torch.rand((h, w), dtype=torch.float32, device="cuda:0")

@@ -10,4 +10,4 @@ python tools/bench_configs.py --steps 10 --json gpurun_out/${TAG}_configs.json 2
 for k in 3 5; do
   ncu --metrics gpu__time_duration.sum --clock-control none -s 34 -c 17 --csv --log-file gpurun_out/${TAG}_cfg${k}_launches.csv python tools/run_config_once.py $k > /dev/null 2>&1
 done
-python tools/bench_widening.py 2>&1 | tail -4 | tee gpurun_out/${TAG}_widening.jsonl
+python tools/bench_widening.py 2>&1 | tail -5 | tee gpurun_out/${TAG}_widening.jsonl

@@ -331,6 +331,19 @@ class Binding:
         c = {k: int(counts[k][0]) for k in BATCH_COUNTS_DTYPE.names}
         return tasks[:min(groups, c["numTaskGroups"])], (meshlets[:min(nmesh, c["numMeshlets"])] if want_meshlets else None), c
 
+    def emit_meshlet_triangles(self, capacity: int | None = None):
+        """mesh stage of the batched draw, primitive half -> (indices [n,3] u8 meshlet-local, primitive ids [n] u32, total count)"""
+        total = C.c_uint64()
+        fn = self._fn("emit_meshlet_triangles")
+        if capacity is None:
+            self._check(fn(self._ctx, None, None, C.c_uint64(0), C.byref(total), C.c_uint32(0)), "emit_meshlet_triangles")
+            capacity = total.value
+        idx = np.zeros((max(capacity, 1), 3), np.uint8)
+        ids = np.zeros(max(capacity, 1), np.uint32)
+        self._check(fn(self._ctx, _ptr(idx), _ptr(ids), C.c_uint64(capacity), C.byref(total), C.c_uint32(0)), "emit_meshlet_triangles")
+        n = min(capacity, total.value)
+        return idx[:n], ids[:n], total.value
+
     def set_driver_standin(self, mode: int):
         self._check(self._fn("set_driver_standin")(self._ctx, C.c_uint32(mode)), "set_driver_standin")
 

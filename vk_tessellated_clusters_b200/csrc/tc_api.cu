@@ -1225,6 +1225,63 @@ TC_API int tc_batch_part_triangles(tc_context* c, tc_task_exchange* tasks, uint3
   return TC_OK;
 }
 
+TC_API int tc_emit_meshlet_triangles(tc_context* c, uint8_t* indices, uint32_t* primitiveIDs, uint64_t capacityTriangles, uint64_t* numTriangles, uint32_t flags)
+{
+  int rc = check_ready(c);
+  if(rc)
+    return rc;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const bool onDevice = (flags & TC_HIT_DEVICE_POINTERS) != 0;
+  uint8_t*  dIdx = indices;
+  uint32_t* dIDs = primitiveIDs;
+  if(!onDevice)
+  {
+    dIdx = nullptr;
+    dIDs = nullptr;
+    if(indices && capacityTriangles && (rc = dalloc(dIdx, capacityTriangles * 3)))
+      return rc;
+    if(primitiveIDs && capacityTriangles && (rc = dalloc(dIDs, capacityTriangles * 4)))
+    {
+      dfree(dIdx);
+      return rc;
+    }
+  }
+  if((reinterpret_cast<uintptr_t>(dIdx) & 3u) || (reinterpret_cast<uintptr_t>(dIDs) & 15u))
+    return fail(TC_ERR_INVALID_ARG, "tc_emit_meshlet_triangles: device pointers must be 4-byte (indices) / 16-byte (primitiveIDs) aligned");
+  const uint32_t epoch = 0x30000000u + (++c->batchCalls & 0x0FFFFFFFu);  // shares the call counter of tc_batch_part_triangles
+  cudaError_t e = cudaMemsetAsync(c->dBatchState, 0, 64, c->stream);
+  if(e == cudaSuccess)
+  {
+    tc::launch_emit_meshlet_triangles(c->params, dIdx, dIDs, capacityTriangles, c->dBatchState, epoch, uint32_t(c->numSMs * 8), c->stream);
+    e = cudaGetLastError();
+  }
+  uint64_t total = 0;
+  if(e == cudaSuccess && (numTriangles || !onDevice))
+  {
+    e = cudaMemcpyAsync(&total, c->dBatchState + 2, 8, cudaMemcpyDeviceToHost, c->stream);
+    if(e == cudaSuccess)
+      e = cudaStreamSynchronize(c->stream);
+  }
+  if(e == cudaSuccess && !onDevice)
+  {
+    const uint64_t n = std::min<uint64_t>(total, capacityTriangles);
+    if(dIdx && n)
+      e = cudaMemcpy(indices, dIdx, n * 3, cudaMemcpyDeviceToHost);
+    if(e == cudaSuccess && dIDs && n)
+      e = cudaMemcpy(primitiveIDs, dIDs, n * 4, cudaMemcpyDeviceToHost);
+  }
+  if(!onDevice)
+  {
+    dfree(dIdx);
+    dfree(dIDs);
+  }
+  if(e != cudaSuccess)
+    return fail(TC_ERR_CUDA, cudaGetErrorString(e));
+  if(numTriangles)
+    *numTriangles = total;
+  return TC_OK;
+}
+
 TC_API int tc_device_scene_building(tc_context* c, uint64_t* deviceAddress)
 {
   if(!c || !deviceAddress)

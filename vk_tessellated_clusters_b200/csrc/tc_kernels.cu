@@ -3154,6 +3154,130 @@ __global__ void __launch_bounds__(BATCH_WARPS * 32, 4) k_batch_part_triangles(Pa
   }
 }
 
+// Mesh stage of the batched draw, primitive half (render_raster_clusters_batched.mesh.glsl:124-151, :312-380).
+// Persistent warps, tile = one task group of 32 parts.  lane = part: the group's batches are found exactly like the task
+// shader does (inclusive adds, one ballot + MSB round per batch), which gives every part its first vertex inside its
+// meshlet; the global triangle offsets come from a 16-byte decoupled look-back in part order (meshlets are consecutive in
+// part order, so a triangle's position does not depend on the batching).  Then lane = triangle of the tile's flat list
+// (owner by 5-step shuffle search, two packed words per part): pattern triangle + vertex start -> three u8, primitive id.
+// state[0] = tile ticket, state[2..3] = total triangle count (u64)
+__global__ void __launch_bounds__(128) k_emit_meshlet_triangles(Params p, uint8_t* indices, uint32_t* primitiveIDs, unsigned long long capacity,
+                                                                uint32_t* state, uint32_t epoch)
+{
+  const uint32_t lane = lane_id();
+  const uint32_t numParts = p.state->numParts, numTiles = (numParts + 31) / 32;
+  const tc_TessTriangleInfo* parts = reinterpret_cast<const tc_TessTriangleInfo*>(p.build->partTriangles);
+  if(numTiles == 0)
+  {
+    if(blockIdx.x == 0 && threadIdx.x == 0)
+      *reinterpret_cast<unsigned long long*>(state + 2) = 0ull;
+    return;
+  }
+  while(true)
+  {
+    uint32_t tile = 0;
+    if(lane == 0)
+      tile = atomicAdd(&state[0], 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if(tile >= numTiles)
+      break;
+    const uint32_t partIndex = tile * 32 + lane;
+    uint32_t numVertices = TC_RASTER_BATCH_VERTICES, numTriangles = TC_RASTER_BATCH_TRIANGLES;  // task.glsl:124-125
+    uint32_t packA = 0, primID = 0;
+    const bool valid = partIndex < numParts;
+    if(valid)
+    {
+      const uint2* src = reinterpret_cast<const uint2*>(&parts[partIndex]);
+      const uint2  c = __ldcs(src + 1), d = __ldcs(src + 2);  // vtxEncoded[0..1], vtxEncoded[2] + triangleID_config
+      const uint32_t cfg = d.y >> 16;
+      const tc_TessTableEntry e = tess_entry(p, cfg);
+      numVertices = e.numVertices; numTriangles = e.numTriangles;
+      uint32_t partID = ((c.x >> 20) | ((c.x >> 4) & 0xFFFu)) ^ ((c.y >> 20) | ((c.y >> 4) & 0xFFFu)) ^ ((d.x >> 20) | ((d.x >> 4) & 0xFFFu));  // mesh.glsl:361
+      primID = (d.y & 0xFFu) | ((partID | 1u) << 8);                                                                                       // :372
+      packA  = uint32_t(e.firstTriangle) | ((cfg & TC_CONFIG_FLIPPED_BIT) ? 0x80000000u : 0u);
+    }
+    const uint32_t sumVertices = warp_inclusive_add(numVertices), sumTriangles = warp_inclusive_add(numTriangles);
+    uint32_t left = min(numParts, tile * 32 + 32) - tile * 32;
+    uint32_t batchIndex = 0, lastStart = 0, lastV = 0, lastT = 0, myBaseV = 0;
+    while(left != 0 && batchIndex < 32)
+    {  // task.glsl:160-205; the batch's first vertex prefix = mesh.glsl:135 baseNumVertices
+      const uint32_t vote  = __ballot_sync(0xffffffffu, (sumVertices - lastV) <= TC_RASTER_BATCH_VERTICES && (sumTriangles - lastT) <= TC_RASTER_BATCH_TRIANGLES);
+      const uint32_t end   = 31u - uint32_t(__clz(vote));
+      const uint32_t count = 1u + end - lastStart;
+      if(lane >= lastStart && lane <= end)
+        myBaseV = lastV;
+      lastV = __shfl_sync(0xffffffffu, sumVertices, end); lastT = __shfl_sync(0xffffffffu, sumTriangles, end);
+      lastStart = end + 1;
+      left -= min(count, left);
+      batchIndex++;
+    }
+    const uint32_t vertexStart = (sumVertices - numVertices) - myBaseV;  // mesh.glsl:149 taskVertexStart (< 96)
+    packA |= vertexStart << 16;                                         // firstTriangle < 2^16 (table), vertexStart < 2^7
+    const uint32_t nT   = valid ? numTriangles : 0u;
+    const uint32_t endT = warp_inclusive_add(nT), startT = endT - nT, total = __shfl_sync(0xffffffffu, endT, 31);
+    lookback16_publish(p.lookback16, tile, 0u, total, epoch);
+    uint32_t           dummy;
+    unsigned long long excl;
+    lookback16_resolve(p.lookback16, tile, 0u, total, epoch, dummy, excl);
+    if(tile == numTiles - 1 && lane == 0)
+      *reinterpret_cast<unsigned long long*>(state + 2) = excl + total;
+    // lane = one QUAD of four consecutive triangles aligned to the GLOBAL triangle index: its 12 index bytes are three
+    // aligned words and its four primitive ids one 128-bit store.  The quads at the two ends of the tile are shared with the
+    // neighbouring tiles: there every tile writes only its own triangles, byte by byte.
+    const unsigned long long q0 = excl >> 2, q1 = (excl + total + 3ull) >> 2;
+    for(unsigned long long qb = q0; qb < q1; qb += 32)
+    {
+      const unsigned long long q = qb + lane;
+      uint32_t T[4], ID[4];
+      bool     ok[4];
+#pragma unroll
+      for(int i = 0; i < 4; i++)
+      {
+        const long long tl = (long long)(q * 4ull + i) - (long long)excl;  // tile-local triangle index
+        ok[i] = q < q1 && tl >= 0 && tl < (long long)total && q * 4ull + i < capacity;
+        const uint32_t t    = ok[i] ? uint32_t(tl) : 0u;
+        const uint32_t item = find_item(endT, t);
+        const uint32_t tri  = t - __shfl_sync(0xffffffffu, startT, item);
+        const uint32_t a    = __shfl_sync(0xffffffffu, packA, item);
+        ID[i] = __shfl_sync(0xffffffffu, primID, item);
+        T[i]  = 0;
+        if(ok[i] && indices)
+        {
+          const uint32_t packedTri = __ldg(&p.tblTriangles[(a & 0xFFFFu) + tri]) & 0xFFFFFFu;
+          T[i] = ((a >> 31) ? __byte_perm(packedTri, 0u, 0x3120) : packedTri) + ((a >> 16) & 0x7Fu) * 0x010101u;  // .xzy when flipped; + vertex start per byte
+        }
+      }
+      if(ok[0] && ok[3])
+      {  // (ok[0] && ok[3] implies all four: the tile's triangles are a contiguous range)
+        if(indices)
+        {
+          uint32_t* dst = reinterpret_cast<uint32_t*>(indices + q * 12ull);
+          __stcs(dst + 0, T[0] | (T[1] << 24));
+          __stcs(dst + 1, (T[1] >> 8) | (T[2] << 16));
+          __stcs(dst + 2, (T[2] >> 16) | (T[3] << 8));
+        }
+        if(primitiveIDs)
+          __stcs(reinterpret_cast<uint4*>(primitiveIDs + q * 4ull), make_uint4(ID[0], ID[1], ID[2], ID[3]));
+      }
+      else
+      {
+#pragma unroll
+        for(int i = 0; i < 4; i++)
+          if(ok[i])
+          {
+            const unsigned long long g = q * 4ull + i;
+            if(indices)
+            {
+              indices[g * 3 + 0] = uint8_t(T[i]); indices[g * 3 + 1] = uint8_t(T[i] >> 8); indices[g * 3 + 2] = uint8_t(T[i] >> 16);
+            }
+            if(primitiveIDs)
+              primitiveIDs[g] = ID[i];
+          }
+      }
+    }
+  }
+}
+
 __global__ void k_flush_l2(float4* buf, size_t n)
 {
   for(size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
@@ -3304,6 +3428,11 @@ void launch_batch_part_triangles(const Params& p, tc_task_exchange* tasks, uint3
 {
   static_assert(sizeof(tc_task_exchange) == 200 && sizeof(tc_meshlet) == 16 && sizeof(tc_batch_counts) == 32, "SURVEY 8f rank 3 records");
   k_batch_part_triangles<<<grid, BATCH_WARPS * 32, batch_smem_bytes(), s>>>(p, reinterpret_cast<uint32_t*>(tasks), taskCapacity, reinterpret_cast<uint4*>(meshlets), meshletCapacity, state, epoch);
+}
+void launch_emit_meshlet_triangles(const Params& p, uint8_t* indices, uint32_t* primitiveIDs, unsigned long long capacity, uint32_t* state, uint32_t epoch,
+                                   uint32_t grid, cudaStream_t s)
+{
+  k_emit_meshlet_triangles<<<grid, 128, 0, s>>>(p, indices, primitiveIDs, capacity, state, epoch);
 }
 void launch_flush_l2(void* buf, size_t bytes, cudaStream_t s) { k_flush_l2<<<1184, 256, 0, s>>>(reinterpret_cast<float4*>(buf), bytes / 16); }
 

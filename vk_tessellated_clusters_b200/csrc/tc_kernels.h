@@ -55,6 +55,8 @@ void launch_emit_part_triangles(const Params& p, uint32_t* indices, uint32_t* ta
                                 cudaStream_t s);
 void launch_batch_part_triangles(const Params& p, tc_task_exchange* tasks, uint32_t taskCapacity, tc_meshlet* meshlets, uint32_t meshletCapacity, uint32_t* state,
                                  uint32_t epoch, uint32_t grid, cudaStream_t s);
+void launch_emit_meshlet_triangles(const Params& p, uint8_t* indices, uint32_t* primitiveIDs, unsigned long long capacity, uint32_t* state, uint32_t epoch,
+                                   uint32_t grid, cudaStream_t s);
 void launch_flush_l2(void* buf, size_t bytes, cudaStream_t s);
 
 }  // namespace tc
