@@ -37,6 +37,8 @@ REF_SHADER(hiz_rest)
 REF_SHADER(rchit)
 REF_SHADER(raster_task)
 void run_groups_raster_task(uint groupsX, void* out);
+REF_SHADER(raster_mesh)
+void run_groups_raster_mesh(const void* task, uint numWorkgroups, void* out);
 void set_hit_rchit(uint clusterID, uint primitiveID, uint instanceID, float b0, float b1, void* out);
 }  // namespace glsl
 
@@ -459,6 +461,39 @@ REF_API int ref_batch_part_triangles(ref_context* c, tc_task_exchange* tasks, ui
     tasks[g] = all[g];
   if(counts)
     *counts = total;
+  return TC_OK;
+}
+
+// ---- mesh stage of the batched draw: shaders/render_raster_clusters_batched.mesh.glsl, one workgroup per batch of every task
+// workgroup (gl_TaskCountNV), fed with that workgroup's TaskExchange block.  `out` receives one MeshOut (translate.py) per mesh
+// workgroup in (group, batch) order: gl_PrimitiveCountNV, gl_PrimitiveIndicesNV, gl_PrimitiveID, OUT[].wPos, gl_Position, ids.
+REF_API int ref_emit_meshlets(ref_context* c, void* out, uint32_t bytesPerMeshlet, uint32_t capacityMeshlets, uint32_t* numMeshlets)
+{
+  using namespace glsl;
+  struct B { const char* name; void* ptr; };
+  const B binds[] = {{"view", &c->frame[0]}, {"readback", &c->readback}, {"instances", c->instances.data()}, {"build", &c->build},
+                     {"buildRW", &c->build}, {"tessTable", &c->tessTable}, {"displacementTextures", c->textureHandles.data()}, {"push", &c->push}};
+  for(const B& b : binds)
+  {
+    bind_raster_task(b.name, b.ptr);
+    bind_raster_mesh(b.name, b.ptr);
+  }
+  const uint32_t parts  = std::min(c->build.partTriangleCounter, c->maxPartTriangles);
+  const uint32_t groups = (parts + 31) / 32;
+  std::vector<tc_task_exchange> all(groups);
+  const tc_Readback saved = c->readback;
+  run_groups_raster_task(groups, all.data());
+  uint32_t m = 0;
+  for(uint32_t g = 0; g < groups; g++)
+  {
+    const uint32_t n = all[g].taskCount;
+    if(out && m + n <= capacityMeshlets)
+      run_groups_raster_mesh(&all[g], n, static_cast<char*>(out) + size_t(m) * bytesPerMeshlet);
+    m += n;
+  }
+  c->readback = saved;
+  if(numMeshlets)
+    *numMeshlets = m;
   return TC_OK;
 }
 

@@ -132,6 +132,50 @@ def raster_task_prepare(src: str) -> str:
     return src
 
 
+def raster_mesh_prepare(src: str) -> str:
+    """mesh shader -> compute-style function: the taskNV input block, the per-vertex interface block and the mesh built-ins
+    become plain statics the runner fills / copies out around every workgroup"""
+    src, n = re.subn(r"\btaskNV\s+in\s+TaskExchange\s*\{([^}]*)\}\s*TASK\s*;", r"struct TaskExchange_t {\1};\nstatic TaskExchange_t TASK;", src)
+    assert n == 1
+    src, n = re.subn(r"layout\s*\(\s*location\s*=\s*0\s*\)\s*out\s+Interpolants\s*\{([^}]*)\}\s*OUT\s*\[\s*\]\s*;",
+                     lambda m: "struct Interpolants_t {" + re.sub(r"\bflat\s+", "", m.group(1)) + "};\nstatic Interpolants_t OUT[96];", src)
+    assert n == 1
+    src, n = re.subn(r"layout\s*\(\s*max_vertices.*?\)\s*out\s*;", "", src)
+    assert n == 1
+    src, n = re.subn(r"layout\s*\(\s*triangles\s*\)\s*out\s*;", "", src)
+    assert n == 1
+    head = ("struct MeshVertex_t { vec4 gl_Position; };\nstatic MeshVertex_t gl_MeshVerticesNV[96];\n"
+            "struct MeshPrimitive_t { int gl_PrimitiveID; };\nstatic MeshPrimitive_t gl_MeshPrimitivesNV[128];\n"
+            "static uint gl_PrimitiveIndicesNV[3 * 128];\nstatic uint gl_PrimitiveCountNV;\n")
+    return head + src
+
+
+RASTER_MESH_RUNNER = """struct MeshOut { uint primitiveCount; uint indices[3 * 128]; int primitiveIDs[128]; float wPos[96 * 3]; float clip[96 * 4]; uint clusterID[96]; uint instanceID[96]; };
+void run_groups_raster_mesh(const void* task, uint numWorkgroups, void* out)  // task: one 200-byte record; out: numWorkgroups MeshOut
+{
+  static_assert(sizeof(TaskExchange_t) == 196, "TaskExchange");
+  memcpy(&TASK, task, 196);
+  MeshOut* o = static_cast<MeshOut*>(out);
+  for(uint gx = 0; gx < numWorkgroups; gx++)
+  {
+    memset(gl_MeshVerticesNV, 0, sizeof(gl_MeshVerticesNV)); memset(gl_MeshPrimitivesNV, 0, sizeof(gl_MeshPrimitivesNV));
+    memset(gl_PrimitiveIndicesNV, 0, sizeof(gl_PrimitiveIndicesNV)); memset(OUT, 0, sizeof(OUT));
+    gl_PrimitiveCountNV = 0;
+    Simt::get().runWorkgroup(&shader_main, _local_size_x * _local_size_y, gx, 32, _local_size_x, 0);
+    o[gx].primitiveCount = gl_PrimitiveCountNV;
+    memcpy(o[gx].indices, gl_PrimitiveIndicesNV, sizeof(gl_PrimitiveIndicesNV));
+    for(int t = 0; t < 128; t++) o[gx].primitiveIDs[t] = gl_MeshPrimitivesNV[t].gl_PrimitiveID;
+    for(int v = 0; v < 96; v++)
+    {
+      o[gx].wPos[v * 3 + 0] = OUT[v].wPos.x; o[gx].wPos[v * 3 + 1] = OUT[v].wPos.y; o[gx].wPos[v * 3 + 2] = OUT[v].wPos.z;
+      o[gx].clip[v * 4 + 0] = gl_MeshVerticesNV[v].gl_Position.x; o[gx].clip[v * 4 + 1] = gl_MeshVerticesNV[v].gl_Position.y;
+      o[gx].clip[v * 4 + 2] = gl_MeshVerticesNV[v].gl_Position.z; o[gx].clip[v * 4 + 3] = gl_MeshVerticesNV[v].gl_Position.w;
+      o[gx].clusterID[v] = OUT[v].clusterID; o[gx].instanceID[v] = OUT[v].instanceID;
+    }
+  }
+}"""
+
+
 RASTER_TASK_RUNNER = """void run_groups_raster_task(uint groupsX, void* out)  // out: 200-byte records (TaskExchange + gl_TaskCountNV)
 {
   static_assert(sizeof(TaskExchange_t) == 196, "TaskExchange");
@@ -152,6 +196,8 @@ def to_cpp(src: str, shader: str) -> str:
         src = rchit_prepare(src)
     if shader == "raster_task":
         src = raster_task_prepare(src)
+    if shader == "raster_mesh":
+        src = raster_mesh_prepare(src)
 
     # ---- float literals: GLSL literals are float, C++ literals are double
     def lit(m):
@@ -277,6 +323,7 @@ int bind_{shader}(const char* name, void* ptr)
 }}
 {RCHIT_SETTER if shader == "rchit" else ""}
 {RASTER_TASK_RUNNER if shader == "raster_task" else ""}
+{RASTER_MESH_RUNNER if shader == "raster_mesh" else ""}
 uint local_size_{shader}() {{ return _local_size_x; }}
 void run_{shader}(uint groupsX, uint groupsY)
 {{
@@ -324,7 +371,8 @@ def build(a) -> str:
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         rchit = ("rchit", "render_raytrace_clusters.rchit.glsl", dict(macros, RAYTRACING_PAYLOAD_INDEX=0))
         raster_task = ("raster_task", "render_raster_clusters_batched.task.glsl", raster_macro_set(macros))
-        objs = list(pool.map(compile_one, [(sh, sh, macros) for sh in SHADERS] + HIZ_PROGRAMS + [rchit, raster_task]))
+        raster_mesh = ("raster_mesh", "render_raster_clusters_batched.mesh.glsl", raster_macro_set(macros))
+        objs = list(pool.map(compile_one, [(sh, sh, macros) for sh in SHADERS] + HIZ_PROGRAMS + [rchit, raster_task, raster_mesh]))
     defs = [f"-DREF_{k}={v}" for k, v in macros.items()]
     with open(os.path.join(REF_SHADERS, "shaderio.h")) as fh:  # push-constant ids of build_setup.comp.glsl
         defs += [f"-DREF_{m.group(1)}={m.group(2)}" for m in re.finditer(r"^#define\s+(BUILD_SETUP_\w+)\s+(\d+)", fh.read(), flags=re.M)]

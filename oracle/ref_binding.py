@@ -55,6 +55,19 @@ class ReferenceShaders(api.Binding):
         raw = (C.c_uint8 * (n * dt.itemsize)).from_address(ptr.value)
         return np.frombuffer(raw, dtype=dt).copy()
 
+    MESH_OUT_DTYPE = np.dtype([("primitiveCount", "<u4"), ("indices", "<u4", 3 * 128), ("primitiveIDs", "<i4", 128), ("wPos", "<f4", (96, 3)),
+                               ("clip", "<f4", (96, 4)), ("clusterID", "<u4", 96), ("instanceID", "<u4", 96)])
+
+    def emit_meshlets(self) -> np.ndarray:
+        """the reference's batched mesh shader run over every batch of the last frame's part list -> one MESH_OUT_DTYPE record per
+        mesh workgroup (what it wrote to gl_PrimitiveCountNV / gl_PrimitiveIndicesNV / gl_PrimitiveID / OUT[] / gl_Position)"""
+        n = C.c_uint32()
+        sz = self.MESH_OUT_DTYPE.itemsize
+        self._check(self.lib.ref_emit_meshlets(self._ctx, None, C.c_uint32(sz), C.c_uint32(0), C.byref(n)), "emit_meshlets")
+        out = np.zeros(max(n.value, 1), self.MESH_OUT_DTYPE)
+        self._check(self.lib.ref_emit_meshlets(self._ctx, out.ctypes.data_as(C.c_void_p), C.c_uint32(sz), C.c_uint32(n.value), C.byref(n)), "emit_meshlets")
+        return out[: n.value]
+
     def simt_stats(self):
         """-> (collectives resolved, of which with only part of the subgroup's live lanes)"""
         a, b = C.c_uint64(), C.c_uint64()

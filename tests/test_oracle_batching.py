@@ -188,3 +188,64 @@ def test_meshlet_triangles_oracle(name, table, oracle_lib):
     check_meshlet_triangles(orc, meshlets, counts, idx, ids, total)
     i2, d2, t2 = orc.emit_meshlet_triangles(capacity=max(1, total // 3))
     assert t2 == total and i2.tobytes() == idx[: len(i2)].tobytes() and d2.tobytes() == ids[: len(d2)].tobytes()
+
+
+@pytest.mark.parametrize("name", ["plane_ragged", "split", "icosphere", "linear_no_transient", "undisplaced", "culling"])
+def test_meshlets_match_reference_mesh_shader(name, table, oracle_lib, ref_mod):
+    """The reference's batched MESH shader (render_raster_clusters_batched.mesh.glsl, compiled for the host; task input block,
+    interface block and mesh built-ins become statics the harness fills / copies out) run over every batch:
+    * gl_PrimitiveCountNV, gl_PrimitiveIndicesNV and gl_PrimitiveID of every workgroup equal the oracle's tc_emit_meshlet_triangles
+      output bit for bit;
+    * the vertices it evaluates are the ones instantiate generated: OUT[v].wPos == worldMatrix * genVertices[V0 + vertexOffset + v]
+      within 1e-5 relative (the claim behind "the vertex half needs no kernel"), flat clusterID / instanceID from the part records."""
+    from oracle.oracle_binding import Oracle
+
+    scene, fcs, cfg, hiz = case(name)
+    try:
+        ref = ref_mod.ReferenceShaders(cfg, len(scene.textures) > 0)
+    except SystemExit as e:
+        pytest.skip(str(e))
+    orc = Oracle(cfg)
+    for b in (ref, orc):
+        b.set_tess_table(table)
+        b.set_scene(scene)
+        if hiz is not None:
+            b.set_hiz(*hiz)
+    ref.frame(fcs)
+    _, rsb = ref.readback()
+    orc.set_addresses(rsb)
+    orc.set_driver_standin(0)
+    orc.frame(fcs)
+    tasks, meshlets, counts = orc.batch_part_triangles()
+    idx, ids, total = orc.emit_meshlet_triangles()
+    out = ref.emit_meshlets()
+    assert len(out) == counts["numMeshlets"] > 0
+    nt = (meshlets["counts"] >> 16).astype(np.int64)
+    nv = ((meshlets["counts"] >> 8) & 0xFF).astype(np.int64)
+    assert np.array_equal(out["primitiveCount"], nt)
+    ref_idx = np.concatenate([o["indices"][: 3 * n] for o, n in zip(out, nt)]).reshape(-1, 3)
+    ref_ids = np.concatenate([o["primitiveIDs"][:n] for o, n in zip(out, nt)]).astype(np.uint32)
+    assert np.array_equal(ref_idx, idx.astype(np.uint32)), "gl_PrimitiveIndicesNV differs"
+    assert np.array_equal(ref_ids, ids), "gl_PrimitiveID differs"
+    # vertex half: the mesh shader's world positions against the instantiated vertices of the same frame
+    n_temp = int(rsb["tempInstantiateCounter"])
+    recs = ref.buffer("tempInstantiations", n_temp)
+    part_recs = recs[(recs["clusterIdOffset"] >> 30) == 1]
+    assert len(part_recs) == counts["numParts"]
+    v0 = int(part_recs["vertexBufferAddress"][0] - rsb["genVertices"]) // 12
+    gen = ref.buffer("genVertices").reshape(-1, 3)
+    parts = ref.buffer("partTriangles")
+    scale = float(scene.radius) if hasattr(scene, "radius") else 1.0
+    entries = orc.lookup_entries()
+    for m, o in zip(meshlets, out):
+        k, vo = 0, v0 + int(m["vertexOffset"])
+        for part in parts[int(m["firstPart"]): int(m["firstPart"]) + int(m["counts"] & 0xFF)]:  # a batch may span instances
+            n = int(entries[(int(part["triangleID_config"]) >> 16) & 0x7FFF][3])
+            opos = gen[vo + k: vo + k + n].astype(np.float64)
+            W = np.asarray(scene.instances[int(part["instanceID"])]["worldMatrix"], np.float64).reshape(4, 4).T  # column-major
+            wpos = opos @ W[:3, :3].T + W[:3, 3]
+            err = np.abs(o["wPos"][k: k + n].astype(np.float64) - wpos)
+            assert (err <= 1e-5 * np.maximum(np.abs(wpos), scale)).all(), f"meshlet at part {int(m['firstPart'])}: max error {err.max()}"
+            assert (o["instanceID"][k: k + n] == part["instanceID"]).all() and (o["clusterID"][k: k + n] == part["clusterID"]).all()
+            k += n
+        assert k == int((m["counts"] >> 8) & 0xFF)
