@@ -325,6 +325,13 @@ def test_batch_part_triangles_against_reference_task_shader(table):
     gt, gm, gc = gpu.batch_part_triangles()
     assert rc["numParts"] == gc["numParts"] > 0 and rc["numMeshlets"] == gc["numMeshlets"] == len(gm)
     assert rt.tobytes() == gt.tobytes()
+    # ... and the primitive half of the mesh stage against the reference's mesh shader
+    out = ref.emit_meshlets()
+    gi, gd, gn = gpu.emit_meshlet_triangles()
+    nt = (gm["counts"] >> 16).astype(np.int64)
+    assert len(out) == len(gm) and np.array_equal(out["primitiveCount"], nt) and int(nt.sum()) == gn
+    assert np.array_equal(np.concatenate([o["indices"][: 3 * n] for o, n in zip(out, nt)]).reshape(-1, 3), gi.astype(np.uint32))
+    assert np.array_equal(np.concatenate([o["primitiveIDs"][:n] for o, n in zip(out, nt)]).astype(np.uint32), gd)
     gpu.close()
 
 
