@@ -3165,6 +3165,8 @@ __global__ void __launch_bounds__(128) k_emit_meshlet_triangles(Params p, uint8_
                                                                 uint32_t* state, uint32_t epoch)
 {
   const uint32_t lane = lane_id();
+  __shared__ uint4 ownerTbl[4][33];  // per warp and part: (end triangle, first triangle, packA, primitive id); entry 32 = sentinel
+  uint4* owner = ownerTbl[threadIdx.x >> 5];
   const uint32_t numParts = p.state->numParts, numTiles = (numParts + 31) / 32;
   const tc_TessTriangleInfo* parts = reinterpret_cast<const tc_TessTriangleInfo*>(p.build->partTriangles);
   if(numTiles == 0)
@@ -3173,6 +3175,8 @@ __global__ void __launch_bounds__(128) k_emit_meshlet_triangles(Params p, uint8_
       *reinterpret_cast<unsigned long long*>(state + 2) = 0ull;
     return;
   }
+  if(lane == 0)
+    owner[32] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
   while(true)
   {
     uint32_t tile = 0;
@@ -3224,22 +3228,31 @@ __global__ void __launch_bounds__(128) k_emit_meshlet_triangles(Params p, uint8_
     // lane = one QUAD of four consecutive triangles aligned to the GLOBAL triangle index: its 12 index bytes are three
     // aligned words and its four primitive ids one 128-bit store.  The quads at the two ends of the tile are shared with the
     // neighbouring tiles: there every tile writes only its own triangles, byte by byte.
+    // The owner of a quad's FIRST triangle comes from the 5-step shuffle search; its other three triangles walk on from there
+    // through a per-warp table in shared memory (almost always the same part: ~59 triangles per part), which needs no
+    // convergence and costs one shared load per triangle instead of eight shuffles.
+    __syncwarp();
+    owner[lane] = make_uint4(endT, startT, packA, primID);
+    __syncwarp();
     const unsigned long long q0 = excl >> 2, q1 = (excl + total + 3ull) >> 2;
     for(unsigned long long qb = q0; qb < q1; qb += 32)
     {
       const unsigned long long q = qb + lane;
       uint32_t T[4], ID[4];
       bool     ok[4];
+      const long long tl0 = (long long)(q * 4ull) - (long long)excl;  // tile-local index of the quad's first triangle
+      uint32_t item = find_item(endT, uint32_t(max(tl0, 0ll)));
 #pragma unroll
       for(int i = 0; i < 4; i++)
       {
-        const long long tl = (long long)(q * 4ull + i) - (long long)excl;  // tile-local triangle index
+        const long long tl = tl0 + i;
         ok[i] = q < q1 && tl >= 0 && tl < (long long)total && q * 4ull + i < capacity;
-        const uint32_t t    = ok[i] ? uint32_t(tl) : 0u;
-        const uint32_t item = find_item(endT, t);
-        const uint32_t tri  = t - __shfl_sync(0xffffffffu, startT, item);
-        const uint32_t a    = __shfl_sync(0xffffffffu, packA, item);
-        ID[i] = __shfl_sync(0xffffffffu, primID, item);
+        const uint32_t t = ok[i] ? uint32_t(tl) : 0u;
+        uint4 o = owner[item];
+        while(ok[i] && t >= o.x)  // next part (parts of one triangle may be skipped over)
+          o = owner[++item];
+        const uint32_t tri = t - o.y, a = o.z;
+        ID[i] = o.w;
         T[i]  = 0;
         if(ok[i] && indices)
         {
