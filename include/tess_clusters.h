@@ -36,7 +36,8 @@ typedef enum tc_status {
   TC_ERR_CUDA         = -2, /* no device / CUDA runtime failure; tc_last_error() has the text */
   TC_ERR_OUT_OF_MEMORY = -3,
   TC_ERR_NOT_READY    = -4, /* table / scene not set yet */
-  TC_ERR_LIMIT        = -5  /* configuration beyond what the kernels support (e.g. cluster > 256 tris) */
+  TC_ERR_LIMIT        = -5, /* configuration beyond what the kernels support (e.g. cluster > 256 tris) */
+  TC_ERR_SHARD_TIMEOUT = -6 /* multi-GPU: a peer's per-frame counts never arrived; sticky until tc_set_shard_peers */
 } tc_status;
 
 /* RendererConfig switches that the reference bakes into its shaders as #defines
@@ -246,7 +247,9 @@ TC_API int tc_frame_build(tc_context* ctx, const void* frameConstants, size_t st
                           const float* viewPosOverride);   /* :412-582  reset .. BUILD_SETUP_BUILD_BLAS */
 TC_API int tc_frame_insert(tc_context* ctx);               /* :661-686  blas_setup_insertion + inserts */
 
-/* Same frame replayed from a captured CUDA graph (frame constants re-read from a pinned staging copy). */
+/* Same frame replayed from a captured CUDA graph.  The frame constants are snapshotted into a ring of pinned staging
+ * slots at call time (like vkCmdUpdateBuffer at record time), so the caller may reuse its buffer immediately and submit
+ * frames without synchronising. */
 TC_API int tc_frame_graph(tc_context* ctx, const void* frameConstants, size_t strideBytes,
                           const float* viewPosOverride);
 /* The two halves as separately captured graphs, for callers that put work (driver CLAS builds, the multi-GPU
@@ -254,6 +257,17 @@ TC_API int tc_frame_graph(tc_context* ctx, const void* frameConstants, size_t st
 TC_API int tc_frame_build_graph(tc_context* ctx, const void* frameConstants, size_t strideBytes,
                                 const float* viewPosOverride);
 TC_API int tc_frame_insert_graph(tc_context* ctx);
+
+/* Batch submission (a camera path, a benchmark): `numFrames` frames enqueued back to back from ONE native host loop, so
+ * no interpreter or per-frame caller work sits between the launches.  Frame f reads its two FrameConstants at
+ * frameConstants + f * frameStrideBytes (frameStrideBytes 0: the same pair every frame).  Flags: TC_RUN_GRAPH replays the
+ * captured frame graph (else stream launches), TC_RUN_FLUSH_L2 writes a buffer larger than the L2 before every frame
+ * (outside the frame's events).  frameMsOut (NULL or numFrames floats) receives the device time of every frame, CUDA
+ * events on the context stream around the frame alone.  Synchronises before returning. */
+#define TC_RUN_GRAPH 1u
+#define TC_RUN_FLUSH_L2 2u
+TC_API int tc_run_frames(tc_context* ctx, const void* frameConstants, size_t strideBytes, size_t frameStrideBytes,
+                         uint32_t numFrames, uint32_t flags, float* frameMsOut);
 
 TC_API int tc_sync(tc_context* ctx);
 
@@ -313,13 +327,20 @@ typedef struct tc_shard_counts {
 /* ---- exchange fused into the frame: peer mailboxes over NVLink/NVSwitch ------------------------------------
  * Instead of a collective between the two halves, the last CTA of the instantiate kernel STORES the rank's
  * tc_shard_counts straight into a mailbox slot on every peer GPU (peer memory: cudaIpcOpenMemHandle across
- * processes, plain device pointers inside one process), and the BLAS setup kernel waits for the world's slots of
- * the current frame and forms its own exclusive prefix.  The whole frame (tc_frame / tc_frame_graph) then is ONE
- * stream-ordered sequence per rank with no collective call, no host round trip and no second graph.
- * A mailbox is tc_shard_mailbox_slot[2][TC_MAX_SHARDS] (two frame parities: a rank can run at most one frame
- * ahead of a peer, because its own insert half waits for every peer's counts).  A rank that never shows up makes
- * the wait give up after about a second: bases are then 0 and tc_shard_gathered reports timedOut. */
+ * processes, plain device pointers inside one process).  Nothing in the frame itself waits for a peer: regions,
+ * counts and the BLAS insert are local, and the frame (tc_frame / tc_frame_graph) stays ONE stream-ordered sequence
+ * per rank with no collective call and no host round trip.  Only the 16 bytes per instance that place the shard in
+ * the rank-concatenated list (tc_global_blas_range) need the peers: a small resolve kernel on a SIDE stream of the
+ * context waits for the world's records of that frame and rebases the frame's ranges -- a late peer delays those
+ * bytes, not the frame.
+ * A mailbox is tc_shard_mailbox_slot[TC_SHARD_RING][TC_MAX_SHARDS], indexed by frame number modulo the ring.  A rank
+ * may run up to TC_SHARD_RING/2 frames ahead of its slowest peer (frame k is enqueued behind the resolve of frame
+ * k - TC_SHARD_RING/2, which bounds the skew so that no slot is overwritten before every rank has read it).
+ * A rank that never shows up makes the resolve give up after about two seconds: the ranges of that frame are
+ * poisoned (all ones), the context enters a sticky error state and tc_sync / tc_readback / tc_frame* return
+ * TC_ERR_SHARD_TIMEOUT until tc_set_shard_peers is called again. */
 #define TC_MAX_SHARDS 16
+#define TC_SHARD_RING 16
 typedef struct tc_shard_mailbox_slot {
   tc_shard_counts counts;
   uint32_t        frame;   /* frame number the counts belong to (written last, release order) */
@@ -332,15 +353,19 @@ TC_API int tc_device_shard_mailbox(tc_context* ctx, uint64_t* deviceAddress);
  * exchange off again (tc_device_shard_base is then the caller's to fill, as before).  Frame tags restart with this
  * call: every rank makes it, then a barrier, then frames in lockstep (each rank the same number of tc_frame calls). */
 TC_API int tc_set_shard_peers(tc_context* ctx, uint32_t rank, uint32_t world, const uint64_t* mailboxAddresses);
-/* the records of the last completed frame as this rank received them (synchronises the stream) */
+/* the records of the last frame as this rank received them (synchronises both streams); *timedOut != 0 reports the
+ * sticky error state without failing the call */
 TC_API int tc_shard_gathered(tc_context* ctx, tc_shard_counts* out, uint32_t capacity, uint32_t* timedOut);
 
 /* Device address of the rank's tc_shard_counts block, valid after tc_frame_build (no sync). */
 TC_API int tc_device_shard_counts(tc_context* ctx, uint64_t* deviceAddress);
 /* Device address of a 2 x u32 block {globalBlasClusterBase, globalInstanceBase} the insert step adds. */
 TC_API int tc_device_shard_base(tc_context* ctx, uint64_t* deviceAddress);
-/* Global BLAS insertion list of this shard, written by the insert step: one record per local instance giving its
- * global instance id and where its cluster references start in the concatenation over all ranks. */
+/* Global BLAS insertion list of this shard: one record per local instance giving its global instance id and where its
+ * cluster references start in the concatenation over all ranks.  Written by the insert step (bases from
+ * tc_device_shard_base) or, with peer mailboxes, shard-relative by the insert step and rebased by the resolve kernel;
+ * tc_device_global_blas_ranges returns the block of the most recently enqueued frame (a ring slot: ask again after
+ * every frame), complete after tc_sync. */
 typedef struct tc_global_blas_range {
   uint32_t globalInstanceID;
   uint32_t clusterReferencesCount;

@@ -83,7 +83,10 @@ __global__ void k_frame_setup(Params p, const tc_SceneBuilding* tmpl, const floa
   if(t < 3)
     p.build->viewPos[t] = viewPosOverride ? viewPosOverride[t] : p.view[0].viewPos[t];
   if(t == 0)
-    *epochCounter += 32;  // 32 launch slots per frame
+  {
+    epochCounter[0] += 32;  // 32 launch slots per frame (the host clears the descriptor arrays and restarts this word long before it wraps)
+    epochCounter[1] += 1;   // frame serial: never restarted; tags the peer-mailbox records
+  }
 }
 
 // ============================================================================================================
@@ -2471,19 +2474,20 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
       sc->numInstances           = p.numInstances;
       if(p.shardWorld > 1)
       {  // exchange fused into the frame: the record goes straight into this rank's slot on every peer (NVLink stores)
-        const uint32_t frame = (*epochCounter >> 5) - p.shardFrameBase;  // frames since tc_set_shard_peers, the same number on every rank
+        const uint32_t frame = epochCounter[1] - p.shardFrameBase;  // frames since tc_set_shard_peers, the same number on every rank
+        const uint32_t ring  = (frame % TC_SHARD_RING) * TC_MAX_SHARDS + p.shardRank;
         const uint4 c0 = make_uint4(sc->tempInstantiateCounter, sc->transBuildCounter, sc->genVertexCounter, sc->blasClusterCounter);
         const uint4 c1 = make_uint4(uint32_t(sc->genClusterDataCounter), uint32_t(sc->genClusterDataCounter >> 32), sc->numTotalTriangles, sc->numInstances);
         for(uint32_t r = 0; r < p.shardWorld; r++)
         {
-          uint4* slot = reinterpret_cast<uint4*>(&p.peerMailbox[r][(frame & 1u) * TC_MAX_SHARDS + p.shardRank]);
+          uint4* slot = reinterpret_cast<uint4*>(&p.peerMailbox[r][ring]);
           slot[0] = c0;
           slot[1] = c1;
         }
         __threadfence_system();  // counts before the frame tags, system wide
         for(uint32_t r = 0; r < p.shardWorld; r++)
         {
-          uint32_t* tag = &p.peerMailbox[r][(frame & 1u) * TC_MAX_SHARDS + p.shardRank].frame;
+          uint32_t* tag = &p.peerMailbox[r][ring].frame;
           asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(tag), "r"(frame) : "memory");
         }
       }
@@ -2572,58 +2576,18 @@ __global__ void __launch_bounds__(1024) k_blas_setup(Params p, const uint32_t* e
   pdl_prologue();
   __shared__ uint32_t warpSums[32];
   __shared__ uint32_t carry, sizesSum, blockTotal;
-  __shared__ uint32_t shardClusters[TC_MAX_SHARDS], shardInstances[TC_MAX_SHARDS], shardBaseS[2], shardTimedOut;
-  if(p.shardWorld > 1)
-  {  // peer-mailbox exchange: wait for every rank's counts of THIS frame, exclusive prefix over the ranks before ours
-    const uint32_t frame = (*epochCounter >> 5) - p.shardFrameBase;
-    if(threadIdx.x == 0)
-      shardTimedOut = 0;
-    __syncthreads();
-    if(threadIdx.x < p.shardWorld)
-    {
-      const tc_shard_mailbox_slot* slot = &p.peerMailbox[p.shardRank][(frame & 1u) * TC_MAX_SHARDS + threadIdx.x];
-      unsigned long long t0;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-      uint32_t tag;
-      bool     ok = true;
-      while(true)
-      {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(tag) : "l"(&slot->frame) : "memory");
-        if(tag == frame)
-          break;
-        __nanosleep(200);
-        unsigned long long t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if(t1 - t0 > 1000000000ull)
-        {  // a peer never showed up: give up instead of hanging the GPU
-          ok = false;
-          break;
-        }
-      }
-      shardClusters[threadIdx.x]  = ok ? slot->counts.blasClusterCounter : 0u;
-      shardInstances[threadIdx.x] = ok ? slot->counts.numInstances : 0u;
-      if(!ok)
-        shardTimedOut = 1;
-    }
-    __syncthreads();
-    if(threadIdx.x == 0)
-    {
-      uint32_t bc = 0, bi = 0;
-      for(uint32_t r = 0; r < p.shardRank; r++)
-      {
-        bc += shardClusters[r];
-        bi += shardInstances[r];
-      }
-      shardBaseS[0] = shardTimedOut ? 0u : bc;
-      shardBaseS[1] = shardTimedOut ? 0u : bi;
-      p.shardStatus[0] = shardTimedOut;
-    }
-  }
-  else if(threadIdx.x == 0)
+  __shared__ uint32_t shardBaseS[2];
+  // Multi-GPU: with the peer-mailbox exchange this kernel needs NOTHING from the peers -- regions, counts and the insert
+  // are local.  It writes this frame's ranges shard-relative into a ring slot; k_shard_resolve (own stream, off the
+  // frame's critical path) waits for the peers' counts and rebases them.  Otherwise the caller's bases apply.
+  tc_global_blas_range* ranges = p.globalRanges;
+  if(threadIdx.x == 0)
   {
-    shardBaseS[0] = p.shardBase[0];
-    shardBaseS[1] = p.shardBase[1];
+    shardBaseS[0] = p.shardWorld > 1 ? 0u : p.shardBase[0];
+    shardBaseS[1] = p.shardWorld > 1 ? 0u : p.shardBase[1];
   }
+  if(p.shardWorld > 1)
+    ranges += size_t((epochCounter[1] - p.shardFrameBase) % TC_SHARD_RING) * p.numInstances;
   const SegmentTable segs = load_segments(p);
   const uint32_t     N    = p.numInstances;
   tc_BlasBuildInfo*  blas = reinterpret_cast<tc_BlasBuildInfo*>(p.build->blasBuildInfos);
@@ -2668,7 +2632,7 @@ __global__ void __launch_bounds__(1024) k_blas_setup(Params p, const uint32_t* e
       blas[i].clusterReferencesStride = 8;
       blas[i].clusterReferences       = p.build->blasClusterAddresses + (unsigned long long)(uint32_t)(offset * 8u);
       // multi-GPU: position of this instance's list in the rank-concatenated insertion list
-      p.globalRanges[i] = tc_global_blas_range{shardBaseS[1] + i, total, (unsigned long long)shardBaseS[0] + offset};
+      ranges[i] = tc_global_blas_range{shardBaseS[1] + i, total, (unsigned long long)shardBaseS[0] + offset};
     }
     __syncthreads();
     if(threadIdx.x == 0)
@@ -2749,6 +2713,73 @@ __global__ void __launch_bounds__(256) k_blas_insert(Params p)
   __syncthreads();
   if(threadIdx.x == 0 && blockSizes)
     atomicAdd(reinterpret_cast<unsigned long long*>(&p.readback->numGenActualDatas), blockSizes);
+}
+
+// Peer-mailbox exchange, consumer side.  Runs on the context's SIDE stream after frame `frame` (frames since
+// tc_set_shard_peers), so a late peer delays these few bytes and never the frame: waits until every rank's record of this
+// frame has arrived in the own mailbox (stored there by the peers' k_instantiate epilogues over NVLink), forms the exclusive
+// prefix over the ranks before ours and rebases the frame's shard-relative ranges (ring slot written by k_blas_setup).
+// A rank that does not show up within ~2 s is a hard error: the ranges are poisoned, status[0] is set and stays set.
+__global__ void __launch_bounds__(256) k_shard_resolve(Params p, uint32_t frame)
+{
+  __shared__ uint32_t shClusters[TC_MAX_SHARDS], shInstances[TC_MAX_SHARDS], shBase[2], shTimedOut;
+  if(threadIdx.x == 0)
+    shTimedOut = 0;
+  __syncthreads();
+  const uint32_t ringSlot = frame % TC_SHARD_RING;
+  if(threadIdx.x < p.shardWorld)
+  {
+    const tc_shard_mailbox_slot* slot = &p.peerMailbox[p.shardRank][ringSlot * TC_MAX_SHARDS + threadIdx.x];
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    uint32_t tag;
+    bool     ok = true;
+    while(true)
+    {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(tag) : "l"(&slot->frame) : "memory");
+      if(tag == frame)
+        break;
+      __nanosleep(500);
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if(t1 - t0 > 2000000000ull)
+      {
+        ok = false;
+        break;
+      }
+    }
+    shClusters[threadIdx.x]  = ok ? slot->counts.blasClusterCounter : 0u;
+    shInstances[threadIdx.x] = ok ? slot->counts.numInstances : 0u;
+    if(!ok)
+      shTimedOut = 1;
+  }
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    uint32_t bc = 0, bi = 0;
+    for(uint32_t r = 0; r < p.shardRank; r++)
+    {
+      bc += shClusters[r];
+      bi += shInstances[r];
+    }
+    shBase[0] = bc;
+    shBase[1] = bi;
+    if(shTimedOut)
+      p.shardStatus[0] = 1;  // sticky: only tc_set_shard_peers clears it
+    p.shardStatus[1] = frame;
+  }
+  __syncthreads();
+  tc_global_blas_range* ranges = p.globalRanges + size_t(ringSlot) * p.numInstances;
+  for(uint32_t i = threadIdx.x; i < p.numInstances; i += blockDim.x)
+  {
+    if(shTimedOut)
+      ranges[i] = tc_global_blas_range{0xFFFFFFFFu, 0u, ~0ull};
+    else
+    {
+      ranges[i].globalInstanceID += shBase[1];
+      ranges[i].globalFirstReference += shBase[0];
+    }
+  }
 }
 
 // ============================================================================================================
@@ -3420,6 +3451,7 @@ void launch_blas(const Params& p, const uint32_t* epochCounter, uint32_t numSegm
   launch_pdl(k_blas_setup, 1, 1024, 0, s, p, epochCounter);
   launch_pdl(k_blas_insert, grid, 256, 0, s, p);
 }
+void launch_shard_resolve(const Params& p, uint32_t frame, cudaStream_t s) { k_shard_resolve<<<1, 256, 0, s>>>(p, frame); }
 void launch_hiz_update(const HizPass& q, cudaStream_t s)
 {
   dim3 block(32, 4);

@@ -49,6 +49,7 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
 void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32_t pass, bool lastPass, uint32_t grid, cudaStream_t s);
 void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s);
 void launch_blas(const Params& p, const uint32_t* epochCounter, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s);
+void launch_shard_resolve(const Params& p, uint32_t frame, cudaStream_t s);
 void launch_hiz_update(const HizPass& q, cudaStream_t s);
 void launch_resolve_hits(const Params& p, const tc_hit* hits, uint32_t count, tc_hit_base* out, bool referenceQuirk, cudaStream_t s);
 void launch_emit_part_triangles(const Params& p, uint32_t* indices, uint32_t* tags, unsigned long long capacity, uint32_t* state, uint32_t epoch, uint32_t grid,
