@@ -1,14 +1,20 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the per-frame tessellation path (BASELINE.json metric).
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N ...            # CPU restatement of the reference on the host cores
+  python bench.py --gpus N --steps K --warmup W [--config 1..5]     # this repo's CUDA path
+  python bench.py --impl reference --gpus N ...                     # CPU restatement of the reference on the host cores
 
-A "step" is one frame: instances_classify .. blas_clusters_insert over the whole scene.  Workload at N=1 is
+A "step" is one frame: instances_classify .. blas_clusters_insert over the whole scene.  The default workload is
 BASELINE.json configs[1] sized to the north_star target (>= 100 M displaced output triangles per frame): displaced
-icosphere, 1 310 720 base triangles, view-adaptive mixed factors with a split load.  For N > 1 every rank owns one
-instance of an N-instance scene (instance sharding, weak scaling) and the ranks exchange one tc_shard_counts record
-per frame with an NCCL allgather between the build and the BLAS-insert half of the frame.
+icosphere, 1 310 720 base triangles, view-adaptive mixed factors with a split load.  `--config K` selects any of the five
+BASELINE configurations (vk_tessellated_clusters_b200/workloads.py).
+
+N > 1 (one process per GPU, torchrun): a scene with at least N instances (configs 3 and 5) is ONE scene sharded by
+contiguous instance ranges, balanced by the previous frame's generated clusters per instance (strong scaling); a
+single-instance scene (configs 1, 2, 4) gives every rank its own copy of the instance (weak scaling, the default line).
+Either way the only exchange is one 32-byte tc_shard_counts record per rank and frame, stored into peer mailboxes over
+NVLink from inside the frame's own kernels (`--exchange nccl`: an allgather between the frame's halves instead).
+The timed frames are submitted by the library's own host loop (tc_run_frames): no interpreter between the launches.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -16,7 +22,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -27,69 +32,87 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from vk_tessellated_clusters_b200 import api, scenes, table  # noqa: E402
+from vk_tessellated_clusters_b200 import api, table, workloads  # noqa: E402
 
 METRIC = "displaced output triangles/sec per frame"
 UNIT = "triangles/s"
-WORKLOAD = "icosphere subdiv8 (1310720 base tris, 20480 clusters), 2048^2 noise displacement, PN on, 1X+2X transient on, camera 1.5r, 0.75 px/segment @3840x2160"
+WORKLOAD = workloads.HEADLINE
 
 
 def workload(rank: int = 0, world: int = 1, small: bool = False):
-    """Scene + frame constants of rank `rank`.  All ranks see a statistically identical instance: instance r sits on
-    a ring around the eye at the same distance, the tess metric only depends on eye distance and edge length."""
-    subdiv, tex = (5, 256) if small else (8, 2048)
-    scene, fcs = scenes.config_icosphere(subdiv, tex_size=tex, distance=1.5, tess_rate_pixels=0.75)
-    if world > 1:
-        eye = fcs[0]["viewPos"][:3].astype(np.float64)
-        ang = 2 * np.pi * rank / world
-        c, s = np.cos(ang), np.sin(ang)
-        rot = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
-        centre = eye + rot @ (-eye)  # instance 0 is at the origin
-        scene.instances[0]["worldMatrix"] = scenes.translation(centre).T.reshape(16)
-    cfg = api.Config(
-        numVisibleClusterBits=15 if not small else 12,
-        numPartTriangleBits=22 if not small else 16,
-        numSplitTriangleBits=20 if not small else 14,
-        numGeneratedVerticesBits=27 if not small else 22,
-        numGeneratedClusterMegs=4095,
-    )
-    return scene, fcs, cfg
+    """(scene, frame constants, limits) of the headline workload for rank `rank` (kept for the tests and tools)."""
+    w = workloads.place_on_ring(workloads.make(2, small), rank, world)
+    return w.scene, w.frame_constants, w.config
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons of one GPU sampled through NVML from a thread of this process (B200_PROFILING.md's clocks
+    line without a child process per rank: eight `nvidia-smi -lms` children starting up inside the timed region were the
+    prime suspect for round 1's N = 8 outlier).  Samples taken between mark_timed(True) and mark_timed(False) are reported
+    separately."""
 
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    def __init__(self, device: int, period_s: float = 0.002):
+        self.device, self.period, self.rows, self.timed = device, period_s, [], False
+        self._stop = threading.Event()
+        self.thread = None
+        self.nv = None
+        try:
+            import pynvml as nv
 
-    def __init__(self, device: int):
-        self.device, self.rows, self.proc = device, [], None
+            nv.nvmlInit()
+            self.nv = nv
+            self.handle = nv.nvmlDeviceGetHandleByIndex(self._nvml_index(nv, device))
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001 - no NVML: the line then carries nulls
+            self.nv = None
+
+    @staticmethod
+    def _nvml_index(nv, device: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if device < len(ids) and ids[device].isdigit():
+                return int(ids[device])
+        return device
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(
+                    nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((self.timed, sm, reasons))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def mark_timed(self, on: bool):
+        self.timed = on
 
     def stop(self) -> dict:
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        self._stop.set()
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        if self.nv is None or not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvml unavailable"}
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        timed = [r for r in self.rows if r[0]]
+        use = timed if len(timed) >= 3 else self.rows
+        bits = 0
         for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except (ValueError, IndexError):
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+            bits |= r[2]
+        return {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": self.max_sm, "reasons": sorted(n for n, b in names.items() if bits & b),
+                "samples": len(self.rows), "samples_in_timed_region": len(timed), "sm_mhz_all_samples_median": float(np.median([r[1] for r in self.rows])),
+                "source": "NVML in-process, 2 ms period"}
 
 
 def instantiate_algorithmic_bytes(gpu, sb, displaced=True) -> int:
@@ -111,31 +134,36 @@ def run_cpu_reference(args, rank, world):
 
     if rank != 0:
         return None
-    scene, fcs, cfg = workload(0, 1, args.small)
+    w = workloads.make(args.config, args.small)
     tbl = table.load_tess_table()
-    orc = Oracle(cfg)
+    orc = Oracle(w.config)
     try:
         orc.set_num_threads(len(os.sched_getaffinity(0)))  # all host cores (torchrun pins OMP_NUM_THREADS=1)
     except AttributeError:
         orc.set_num_threads(os.cpu_count() or 1)
     orc.set_tess_table(tbl)
-    orc.set_scene(scene)
+    orc.set_scene(w.scene)
+    if w.hiz is not None:
+        orc.set_hiz(*w.hiz)
     orc.set_default_addresses()
-    for _ in range(max(1, min(args.warmup, 2))):
-        orc.frame(fcs)
-    steps = max(1, min(args.steps, 10))
-    t0 = time.perf_counter()
+    for _ in range(args.warmup):
+        orc.frame(w.frame_constants)
+    steps = max(1, args.steps)
+    per = []
     for _ in range(steps):
-        orc.frame(fcs)
-    dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        orc.frame(w.frame_constants)
+        per.append(time.perf_counter() - t0)
+    dt = float(np.sum(per))
     rb, _ = orc.readback()
     tris = int(rb["numTotalTriangles"])
     value = tris * steps / dt
-    sample = f"{steps} full frames of the workload ({tris} output triangles each), {max(1, min(args.warmup, 2))} warm-up"
+    sample = f"{steps} full frames of the workload ({tris} output triangles each), {args.warmup} warm-up"
     return {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD if not args.small else "small icosphere (debug)", "l2": "n/a (CPU)"},
+        "ms_per_step": dt / steps * 1e3, "ms_per_step_median": float(np.median(per)) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w.name, "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "clusters_per_sec": int(rb["numBlasClusters"]) * steps / dt,
@@ -148,6 +176,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json configuration (default 2 = the headline)")
     ap.add_argument("--small", action="store_true", help="debug-size workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
@@ -176,12 +205,36 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    scene, fcs, cfg = workload(rank, world, args.small)
-    cfg.device = local_rank
+    # clocks are sampled in-process from before the set-up to the end of the measurements
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    w = workloads.make(args.config, args.small)
     tbl = table.load_tess_table()
-    gpu = api.TessClusters(cfg)
-    gpu.set_tess_table(tbl)
-    gpu.set_scene(scene)
+    sharded = world > 1 and len(w.scene.instances) >= world
+    full_scene = w.scene
+    if world > 1 and not sharded:
+        w = workloads.place_on_ring(w, rank, world)
+    gpu = workloads.setup(w, tbl, local_rank)
+    fcs = w.frame_constants
+    shard_info = None
+    if sharded:
+        from vk_tessellated_clusters_b200 import sharding
+
+        # one unsharded frame on every rank (identical everywhere) gives last frame's generated clusters per instance
+        gpu.frame(fcs)
+        _, sb_full = gpu.readback()
+        n_inst = len(full_scene.instances)
+        generated = gpu.buffer("blasBuildInfos", n_inst, sb_full)["clusterReferencesCount"]
+        clusters = np.array([full_scene.geometries[int(i["geometryID"])].num_clusters for i in full_scene.instances])
+        weights = sharding.frame_weights(clusters, generated)
+        bounds = sharding.partition_instances(weights, world)
+        first, last = bounds[rank]
+        gpu.set_scene(sharding.shard_scene(full_scene, first, last))
+        if w.hiz is not None:
+            gpu.set_hiz(*w.hiz)
+        shard_info = {"instances_per_rank": [b - a for a, b in bounds], "weight_share_per_rank": [float(weights[a:b].sum() / weights.sum()) for a, b in bounds],
+                      "balance": "previous frame's generated clusters per instance + 0.25 x clusters"}
 
     shard = None
     if world > 1:
@@ -197,14 +250,13 @@ def main():
         if args.exchange == "peer":
             sharding.connect_peer_mailboxes(gpu, rank, world)
 
+    peer = world == 1 or args.exchange == "peer"  # the frame is one library call
+
     def one_frame(use_graph: bool):
-        if world == 1:
+        if peer:
             (gpu.frame_graph if use_graph else gpu.frame)(fcs)
             return None
         sharding_, counts_t_ = shard
-        if args.exchange == "peer":  # the whole frame incl. the exchange is one stream-ordered sequence (one graph)
-            (gpu.frame_graph if use_graph else gpu.frame)(fcs)
-            return None
         (gpu.frame_build_graph if use_graph else gpu.frame_build)(fcs)
         gpu.copy_async(counts_t_.data_ptr(), gpu.device_shard_counts(), 32)
         gathered, base = sharding_.exchange_shard_counts(counts_t_)
@@ -212,11 +264,12 @@ def main():
         (gpu.frame_insert_graph if use_graph else gpu.frame_insert)()
         return gathered
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     use_graph = not args.no_graph
-    # clocks are sampled from before the warm-up to the end of the measurements (nvidia-smi takes ~0.5 s to start)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.6)
     # warm-up (also builds the graph)
     for _ in range(args.warmup):
         one_frame(use_graph)
@@ -225,26 +278,15 @@ def main():
     tris_local = int(rb["numTotalTriangles"])
     clusters_local = int(rb["numBlasClusters"])
 
-    # ---- timed region: K frames, device events, L2 flushed between frames (outside the events) ----
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-    frame_ms = []
+    # ---- timed region: K frames, device events around every frame, L2 flushed between frames (outside the events) ----
+    barrier()
     gathered = None
-    if world == 1:
-        # whole-frame CUDA events recorded on the context's own stream (the stream the kernels are launched on)
-        gpu.enable_stage_timers(False)
-        ev = _Events(gpu)
-        for _ in range(args.steps):
-            gpu.flush_l2()
-            ev.record_start()
-            one_frame(use_graph)
-            ev.record_stop()
-            frame_ms.append(ev.elapsed_ms())
+    sampler.mark_timed(True)
+    t_wall = time.perf_counter()
+    if peer:
+        # submitted back to back by the library's own host loop, one synchronisation at the end
+        frame_ms = [float(x) for x in gpu.run_frames(fcs, args.steps, graph=use_graph, flush_l2=True)]
     else:
-        # all K frames are enqueued back to back (events around each frame, the L2 flush between them outside the events) and
-        # the host synchronises once at the end: with a host sync per frame every launch hiccup of ONE rank's Python thread
-        # is paid by all ranks, because a frame waits on the device for its peers' counts
         pairs = []
         for _ in range(args.steps):
             gpu.flush_l2()
@@ -255,13 +297,18 @@ def main():
             pairs.append((e0, e1))
         torch.cuda.synchronize()
         frame_ms = [a.elapsed_time(b) for a, b in pairs]
+    bracket_ms = (time.perf_counter() - t_wall) * 1e3
+    sampler.mark_timed(False)
     total_ms = float(np.sum(frame_ms))
+    rank_totals = [total_ms]
     if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-        dist.barrier()
-        torch.cuda.synchronize()
+        t = torch.tensor([total_ms, bracket_ms], dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_totals = [float(x[0].item()) for x in allt]
+        bracket_ms = max(float(x[1].item()) for x in allt)
+        total_ms = max(rank_totals)
+        barrier()
 
     if world > 1:
         if args.exchange == "peer":
@@ -276,32 +323,20 @@ def main():
     # ---- e2e: public API with HOST inputs/outputs every step: H2D frame constants + D2H readback, wall clock ----
     h2d = int(fcs.nbytes + 16)
     d2h = int(api.READBACK_DTYPE.itemsize + api.SCENE_BUILDING_DTYPE.itemsize)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
+    barrier()
+    e2e_per = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         one_frame(False)
         rb_e, _ = gpu.readback()
-    e2e_s = time.perf_counter() - t0
+        e2e_per.append(time.perf_counter() - t0)
+    e2e_s = float(np.sum(e2e_per))
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
-    # keep the GPU busy a little longer so the 100 ms sampler sees clocks under load, then stop it
-    if world == 1:
-        t_end = time.perf_counter() + 0.5
-        while time.perf_counter() < t_end:
-            one_frame(False)
-    else:  # the same number of frames on every rank: the peer exchange matches frames by number
-        for _ in range(700):
-            one_frame(False)
-    gpu.sync()
-    clocks = sampler.stop()
-
     # ---- roofline of the dominant kernel (k_instantiate), measured live with CUDA events on its stream ----
-    # (every rank runs these frames: with the peer exchange a frame waits for its peers' counts, a rank running alone
-    # would sit out the one-second time-out of the mailbox wait in every frame)
     gpu.enable_stage_timers(True)
     inst_ms, stage_acc = [], {}
     for _ in range(max(5, min(args.steps, 20))):
@@ -312,12 +347,30 @@ def main():
         for k, v in st.items():
             stage_acc.setdefault(k, []).append(v)
     gpu.enable_stage_timers(False)
-    if world > 1:
-        dist.barrier()
+
+    # keep the GPU busy a little longer so that the clock samples also cover a steady state, the same number of frames on
+    # every rank (the peer exchange matches frames by number): chunks until rank 0's half second is over
+    t_end = time.perf_counter() + 0.5
+    while True:
+        if peer:
+            gpu.run_frames(fcs, 50, graph=use_graph, flush_l2=False)
+        else:
+            for _ in range(50):
+                one_frame(use_graph)
+            gpu.sync()
+        more = 1 if time.perf_counter() < t_end else 0
+        if world > 1:
+            t = torch.tensor([more], dtype=torch.int32, device="cuda")
+            dist.broadcast(t, src=0)
+            more = int(t.item())
+        if not more:
+            break
+    clocks = sampler.stop()
+    barrier()
+
     line = None
     if rank == 0:
         rb, sb = gpu.readback()
-        alg_bytes, n_parts, n_verts = instantiate_algorithmic_bytes(gpu, sb)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -325,40 +378,69 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        inst_avg_ms = float(np.mean(inst_ms))
-        # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/), per launch
-        traffic = None
-        try:
-            raw = {l.split(",")[0]: l.strip().split(",")[1:] for l in open(os.path.join(ROOT, "profiles", "r01_instantiate_ncu_raw.csv"))}
-            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            traffic = int(sum(float(raw[k][1]) * scale[raw[k][0]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")))
-        except (OSError, KeyError, ValueError):
-            pass
-        achieved = alg_bytes / (inst_avg_ms * 1e-3) / 1e9
-        frame_alg = api.algorithmic_bytes(rb, sb, scene, tbl)
+        ms_per_step = total_ms / args.steps
+        ms_median = float(np.median(frame_ms))
+        frame_alg = api.algorithmic_bytes(rb, sb, w.scene, tbl)  # rank 0's shard
+        frame_roof = {"algorithmic_bytes": frame_alg, "achieved": frame_alg / (ms_median * 1e-3) / 1e9, "frac": frame_alg / (ms_median * 1e-3) / 1e9 / peak,
+                      "note": "rank 0's frame: compulsory bytes of the whole chain / median frame time"}
+        if args.config == 2:
+            alg_bytes, n_parts, n_verts = instantiate_algorithmic_bytes(gpu, sb)
+            inst_avg_ms = float(np.mean(inst_ms))
+            # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/), per launch
+            traffic = None
+            for name in ("r02_instantiate_ncu_raw.csv", "r01_instantiate_ncu_raw.csv"):
+                try:
+                    raw = {l.split(",")[0]: l.strip().split(",")[1:] for l in open(os.path.join(ROOT, "profiles", name))}
+                    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                    traffic = int(sum(float(raw[k][1]) * scale[raw[k][0]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")))
+                    break
+                except (OSError, KeyError, ValueError):
+                    continue
+            achieved = alg_bytes / (inst_avg_ms * 1e-3) / 1e9
+            roofline = {"kernel": "k_instantiate", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": inst_avg_ms, "launch_ms_median": float(np.median(inst_ms)),
+                        "frac_of_8000_nominal": achieved / 8000.0, "frame_frac": frame_roof["frac"], "frame_achieved": frame_roof["achieved"], "frame": frame_roof}
+        else:
+            n_parts, n_verts = int(sb["partTriangleCounter"]), int(sb["genVertexCounter"])
+            roofline = {"kernel": "whole frame (all kernels of the chain)", "bound": "hbm", "achieved": frame_roof["achieved"], "peak": peak, "unit": "GB/s",
+                        "frac": frame_roof["frac"], "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": frame_alg, "launch_ms": ms_median,
+                        "frame_frac": frame_roof["frac"], "frame_achieved": frame_roof["achieved"], "frame": frame_roof}
 
         cpu_baseline = None
         if not args.no_cpu_baseline:
-            ref = run_cpu_reference(argparse.Namespace(steps=3, warmup=1, gpus=1, small=args.small), 0, 1)
+            ref = run_cpu_reference(argparse.Namespace(steps=3, warmup=1, gpus=1, small=args.small, config=args.config), 0, 1)
             cpu_baseline = ref["cpu_baseline"]
 
-        ms_per_step = total_ms / args.steps
+        if world == 1:
+            par = "one GPU"
+        elif sharded:
+            par = f"ONE scene of {len(full_scene.instances)} instances sharded by contiguous instance ranges over {world} ranks"
+        else:
+            par = f"instance-sharded x{world}: every rank owns one copy of the instance"
+        if world > 1:
+            par += (", counts exchanged by peer-mailbox stores from inside the frame's kernels, resolved off the frame's critical path (no collective call)"
+                    if args.exchange == "peer" else ", NCCL allgather of the counts between the frame's halves")
+        slowest = int(np.argmax(rank_totals))
         line = {
             "metric": METRIC, "value": tris_total * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if not args.small else "small icosphere (debug)", "parallelism": f"instance-sharded x{world}" + ("" if world == 1 else (", counts exchanged by peer-mailbox stores inside the frame's kernels (no collective call)" if args.exchange == "peer" else ", NCCL allgather of the counts between the frame's halves")),
-                       "l2": "flushed between timed frames (256 MiB write)", "launch": "cuda graph" if use_graph else "stream launches",
-                       "triangles_per_frame": tris_total, "clusters_per_frame": clusters_total, "parts_per_frame_rank0": n_parts,
-                       "generated_vertices_rank0": n_verts},
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.name, "parallelism": par, "l2": "flushed between timed frames (256 MiB write)",
+                       "launch": ("cuda graph" if use_graph else "stream launches") + (", frames submitted by the library's host loop (tc_run_frames)" if peer else ""),
+                       "triangles_per_frame": tris_total, "clusters_per_frame": clusters_total, "parts_per_frame_rank0": n_parts, "generated_vertices_rank0": n_verts,
+                       "baseline_config": args.config, "shards": shard_info},
+            "frame_ms": {"median": ms_median, "mean": float(np.mean(frame_ms)), "p99": float(np.percentile(frame_ms, 99)), "min": float(np.min(frame_ms)),
+                         "max": float(np.max(frame_ms)), "per_frame_rank0": [round(x, 4) for x in frame_ms], "sum_per_rank": [round(x, 4) for x in rank_totals],
+                         "slowest_rank": slowest, "bracket_ms_incl_flushes_max_over_ranks": bracket_ms},
+            "value_at_median": tris_total / (ms_median * 1e-3),
             "clusters_per_sec": clusters_total * args.steps / (total_ms * 1e-3),
             "clocks": clocks,
-            "e2e": {"value": tris_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": gpu.last_launch_count() * args.steps,
-            "roofline": {"kernel": "k_instantiate", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": inst_avg_ms,
-                         "frac_of_8000_nominal": achieved / 8000.0,
-                         "frame": {"algorithmic_bytes": frame_alg, "achieved": frame_alg / (ms_per_step * 1e-3) / 1e9, "frac": frame_alg / (ms_per_step * 1e-3) / 1e9 / peak}},
+            "e2e": {"value": tris_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "ms_per_step_median_rank0": float(np.median(e2e_per)) * 1e3},
+            "gpu_launches": (gpu.last_launch_count() + (1 if world > 1 and args.exchange == "peer" else 0)) * args.steps,
+            "roofline": roofline,
+            "roofline_frame": frame_roof,
             "stage_ms": {k: float(np.mean(v)) for k, v in stage_acc.items()},
+            "stage_ms_median": {k: float(np.median(v)) for k, v in stage_acc.items()},
             "cpu_baseline": cpu_baseline,
         }
     if world > 1:

@@ -91,11 +91,14 @@ def compare_frame(gpu: api.TessClusters, orc, scene_scale: float = 1.0, check_ve
         # index bytes of transient builds alias genVertices: those ranges are compared exactly
         is_index = np.zeros(n_v * 3, dtype=bool)
         base = int(sb_o["genVertices"])
-        for r in to:
-            tris = int(r["packed"]) & 0x1FF
-            start = int(r["indexBuffer"]) - base
+        if len(to):  # vectorised: millions of transient builds at BASELINE sizes
+            tris = (to["packed"] & 0x1FF).astype(np.int64)
+            start = to["indexBuffer"].astype(np.int64) - base
             first, last = start // 4, (start + tris * 3 + 3) // 4
-            is_index[first:last] = True
+            length = last - first
+            offs = np.concatenate([[0], np.cumsum(length)])
+            words = np.repeat(first - offs[:-1], length) + np.arange(int(offs[-1]), dtype=np.int64)
+            is_index[words] = True
         stats["index_bytes"] = int(is_index.sum()) * 4
         if is_index.any():
             _eq("transTriIndices", vg.view(np.uint32)[is_index], vo.view(np.uint32)[is_index])

@@ -5,6 +5,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 from vk_tessellated_clusters_b200 import scenes as S, sharding
 
@@ -75,6 +76,27 @@ def test_partition_instances_balanced_contiguous():
     two = sharding.partition_instances(counts, 2)
     loads = [counts[a:b].sum() for a, b in two]
     assert abs(loads[0] - loads[1]) <= 40
+    # no empty shards: the library rejects a scene without instances, so asking for more ranks than instances is an error
+    with pytest.raises(ValueError):
+        sharding.partition_instances([5], 3)
+    # weights from the previous frame (half of the instances culled: they generate one CLAS per cluster, the others many)
+    clusters = np.full(8, 100)
+    generated = np.array([100, 100, 100, 100, 5000, 5000, 5000, 5000])
+    parts = sharding.partition_instances(sharding.frame_weights(clusters, generated), 2)
+    assert parts[0][1] >= 5  # the split point moves into the heavy half
+
+
+def test_shard_scene_is_a_contiguous_instance_range():
+    scene, _ = S.config_plane(16, tex_size=16)
+    inst = np.repeat(scene.instances, 5)
+    inst["geometryID"] = 0
+    inst["displacementScale"] = np.arange(5)
+    import dataclasses
+
+    big = dataclasses.replace(scene, instances=inst)
+    sub = sharding.shard_scene(big, 1, 4)
+    assert len(sub.instances) == 3 and sub.geometries is big.geometries and sub.textures is big.textures
+    assert sub.instances["displacementScale"].tolist() == [1.0, 2.0, 3.0]
 
 
 _WORKER = r"""

@@ -128,8 +128,9 @@ def test_shard_summary_record_matches_readback(table):
 
 def test_peer_mailbox_exchange_two_ranks_one_gpu(table):
     """The exchange fused into the frame, with two contexts (= two ranks) in one process on one GPU: each rank's
-    instantiate kernel stores its counts into both mailboxes, each rank's BLAS setup kernel waits for both and forms
-    its own base.  The global insertion list must be the concatenation of the ranks' lists."""
+    instantiate kernel stores its counts into both mailboxes; nothing in a frame waits for the peer, the resolve kernel on
+    each context's side stream rebases that frame's ranges.  The global insertion list must be the concatenation of the
+    ranks' lists, over more frames than the mailbox ring has slots."""
     from tests.scene_cases import case
     from vk_tessellated_clusters_b200 import sharding
 
@@ -144,9 +145,11 @@ def test_peer_mailbox_exchange_two_ranks_one_gpu(table):
     boxes = [g.device_shard_mailbox() for g in gpus]
     for r, g in enumerate(gpus):
         g.set_shard_peers(r, 2, boxes)
-    for frame in range(3):  # several frames: both mailbox parities, tags advance in lockstep
-        for g in gpus:
-            g.frame(fcs)  # asynchronous: rank 0's setup kernel waits on the GPU for rank 1's instantiate
+    for frame in range(20):  # ring of 16 slots wraps; rank 0 runs graph replays, rank 1 stream launches
+        gpus[0].frame_graph(fcs)
+        gpus[1].frame(fcs)
+        if frame % 7 != 6:
+            continue  # no host synchronisation between most frames: the skew bound of the ring is all that orders the ranks
         recs = []
         for r, g in enumerate(gpus):
             got, timed_out = g.shard_gathered()
@@ -162,9 +165,148 @@ def test_peer_mailbox_exchange_two_ranks_one_gpu(table):
             base_i = sum(c["numInstances"] for c in cnt[:r])
             assert int(ranges["globalInstanceID"][0]) == base_i
             assert int(ranges["globalFirstReference"][0]) == base_c
-    # a rank that never shows up must not hang the GPU: the wait gives up and reports it
+            blas = g.buffer("blasBuildInfos", g.num_instances, sb)
+            np.testing.assert_array_equal(ranges["clusterReferencesCount"], blas["clusterReferencesCount"])
+    # a rank that never shows up must not hang the GPU: the frame itself completes (nothing in it waits), the resolve gives
+    # up and the context enters a hard error state instead of handing out a wrong range
     gpus[0].frame(fcs)
     got, timed_out = gpus[0].shard_gathered()
     assert timed_out
+    assert (gpus[0].global_blas_ranges()["globalFirstReference"] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+    with pytest.raises(api.TessError, match="-6"):
+        gpus[0].readback()
+    with pytest.raises(api.TessError, match="-6"):
+        gpus[0].frame(fcs)
+    for r, g in enumerate(gpus):  # restarting the exchange clears the error
+        g.set_shard_peers(r, 2, boxes)
+    for g in gpus:
+        g.frame(fcs)
+    assert not gpus[0].shard_gathered()[1] and not gpus[1].shard_gathered()[1]
     for g in gpus:
         g.close()
+
+
+def _instance_multisets(gpu, sb, first_global=0):
+    """{global instance id: sorted list of (kind, payload)} of every CLAS the frame generated, resolved so that nothing depends
+    on allocation order or on the shard: template instantiations by (clusterIdOffset tag, template address, part record),
+    transient builds by (clusterID tag mode, triangle count)."""
+    n_temp, n_trans = int(sb["tempInstantiateCounter"]), int(sb["transBuildCounter"])
+    ti = gpu.buffer("tempInstantiations", n_temp, sb)
+    tid = gpu.buffer("tempInstanceIDs", n_temp, sb)
+    parts = gpu.buffer("partTriangles", int(sb["partTriangleCounter"]), sb)
+    out = {}
+    mode = ti["clusterIdOffset"] >> 30
+    idx = ti["clusterIdOffset"] & 0x3FFFFFFF
+    for j in range(n_temp):
+        if mode[j] == 1:
+            p = parts[idx[j]]
+            key = (1, int(p["clusterID"]), int(p["triangleID_config"]), tuple(int(x) for x in p["vtxEncoded"]))
+        else:
+            key = (0, int(ti["clusterTemplateAddress"][j]), 0, ())
+        out.setdefault(int(tid[j]) + first_global, []).append(key)
+    tb = gpu.buffer("transBuilds", n_trans, sb)
+    trid = gpu.buffer("transInstanceIDs", n_trans, sb)
+    for j in range(n_trans):
+        out.setdefault(int(trid[j]) + first_global, []).append((2 + (int(tb["clusterID"][j]) >> 30), int(tb["packed"][j]) & 0x3FFFF, 0, ()))
+    return {k: sorted(v) for k, v in out.items()}
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_frame_equals_unsharded(table, world):
+    """a 36-instance scene with frustum + HiZ instance culling, once on one context and once sharded over
+    `world` contexts (contiguous instance ranges from partition_instances, peer mailboxes in-process).  After rebasing with
+    tc_global_blas_range the shards must reproduce the unsharded frame: the same CLAS multiset per global instance, the
+    same per-instance reference counts at the same global positions, counters that sum to the unsharded ones, the same
+    visibility bits."""
+    from vk_tessellated_clusters_b200 import sharding
+
+    scene, fcs, pyr, size, mips = S.config_instances(36, subdiv=4, tex_size=128, tess_rate_pixels=4.0)
+    cfg = api.Config(flags=api.FLAG_DEFAULT | api.FLAG_CULLING, numVisibleClusterBits=14, numPartTriangleBits=21, numSplitTriangleBits=18,
+                     numGeneratedVerticesBits=26, numGeneratedClusterMegs=4095)
+
+    def make(sc):
+        g = api.TessClusters(cfg)
+        g.set_tess_table(table)
+        g.set_scene(sc)
+        g.set_hiz(pyr, size, mips)
+        return g
+
+    ref = make(scene)
+    ref.frame(fcs)
+    rb0, sb0 = ref.readback()
+    # no limit is hit: with an overflow the unsharded frame drops work that the (smaller) shards would keep
+    assert int(rb0["numPartTriangles"]) <= cfg.max_part_triangles and int(rb0["numSplitTriangles"]) <= cfg.max_split_triangles
+    assert int(rb0["numGenVertices"]) <= cfg.max_generated_vertices and int(rb0["numGenDatas"]) <= cfg.numGeneratedClusterMegs << 20
+    N = len(scene.instances)
+    states0 = ref.buffer("instanceStates", N, sb0)
+    assert 0 < int(((states0 & 2) != 0).sum()) < N
+    blas0 = ref.buffer("blasBuildInfos", N, sb0)
+    ranges0 = ref.global_blas_ranges()  # unsharded: global == local
+    np.testing.assert_array_equal(ranges0["globalInstanceID"], np.arange(N, dtype=np.uint32))
+    starts0 = ((blas0["clusterReferences"] - sb0["blasClusterAddresses"]) // 8).astype(np.uint64)
+    np.testing.assert_array_equal(ranges0["globalFirstReference"], starts0)
+    sets0 = _instance_multisets(ref, sb0)
+    # balance by the frame just rendered: generated clusters per instance + a share per cluster for classify
+    n_clusters = scene.geometries[0].num_clusters
+    weights = sharding.frame_weights(np.full(N, n_clusters), blas0["clusterReferencesCount"])
+    bounds = sharding.partition_instances(weights, world)
+    assert bounds != sharding.partition_instances(np.full(N, n_clusters), world)  # culling moves the split points
+
+    shards = [make(sharding.shard_scene(scene, a, b)) for a, b in bounds]
+    boxes = [g.device_shard_mailbox() for g in shards]
+    for r, g in enumerate(shards):
+        g.set_shard_peers(r, world, boxes)
+    for _ in range(2):
+        for g in shards:
+            g.frame(fcs)
+    sums = {}
+    sets = {}
+    for (a, b), g in zip(bounds, shards):
+        recs, timed_out = g.shard_gathered()
+        assert not timed_out
+        rb, sb = g.readback()
+        for f in ("numTotalTriangles", "numBlasClusters", "numTempInstantiations", "numTransBuilds", "numGenVertices", "numPartTriangles", "numSplitTriangles",
+                  "numFullClusters", "numVisibleClusters", "numGenDatas"):
+            sums[f] = sums.get(f, 0) + int(rb[f])
+        np.testing.assert_array_equal(g.buffer("instanceStates", b - a, sb), states0[a:b])
+        ranges = g.global_blas_ranges()
+        np.testing.assert_array_equal(ranges["globalInstanceID"], np.arange(a, b, dtype=np.uint32))
+        np.testing.assert_array_equal(ranges["clusterReferencesCount"], blas0["clusterReferencesCount"][a:b])
+        np.testing.assert_array_equal(ranges["globalFirstReference"], starts0[a:b])  # same place in the rank-concatenated list
+        sets.update(_instance_multisets(g, sb, first_global=a))
+        g.close()
+    for f, v in sums.items():
+        assert v == int(rb0[f]), f
+    assert sets == sets0
+    ref.close()
+
+
+def test_run_frames_batch_submission(table):
+    """tc_run_frames: K frames from the library's own host loop, per-frame constants from an array (the pinned staging ring
+    snapshots them at submission), per-frame device times; the last frame's outputs equal a plain tc_frame with its constants."""
+    from tests.scene_cases import case
+
+    scene, fcs, cfg, _ = case("split")
+    gpu = api.TessClusters(cfg)
+    gpu.set_tess_table(table)
+    gpu.set_scene(scene)
+    far = fcs.copy()
+    far["tessRate"] *= np.float32(0.25)
+    gpu.frame(far)
+    rb_far, sb_far = gpu.readback()
+    gpu.frame(fcs)
+    rb_near, sb_near = gpu.readback()
+    assert int(rb_far["numTotalTriangles"]) < int(rb_near["numTotalTriangles"])
+    ref = gpu.buffer("tempInstantiations", int(sb_near["tempInstantiateCounter"]), sb_near).tobytes()
+    K = 40  # more frames than the staging ring has slots
+    seq = np.stack([far if k % 2 == 0 else fcs for k in range(K)])
+    for graph in (False, True):
+        ms = gpu.run_frames(seq, K, graph=graph, flush_l2=True)
+        assert ms.shape == (K,) and (ms > 0).all()
+        rb, sb = gpu.readback()
+        assert int(rb["numTotalTriangles"]) == int(rb_near["numTotalTriangles"])
+        assert gpu.buffer("tempInstantiations", int(sb["tempInstantiateCounter"]), sb).tobytes() == ref
+        ms = gpu.run_frames(seq[: K - 1], K - 1, graph=graph, flush_l2=False)  # ends on a `far` frame
+        rb, sb = gpu.readback()
+        assert int(rb["numTotalTriangles"]) == int(rb_far["numTotalTriangles"])
+    gpu.close()

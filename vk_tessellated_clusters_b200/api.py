@@ -177,6 +177,10 @@ class TessError(RuntimeError):
     pass
 
 
+RUN_GRAPH, RUN_FLUSH_L2 = 1, 2  # tc_run_frames flags
+ERR_SHARD_TIMEOUT = -6
+
+
 HIT_DTYPE = np.dtype([("instanceID", "<u4"), ("clusterID", "<u4"), ("primitiveID", "<u4"), ("barycentrics", "<f4", 2)])
 HIT_BASE_DTYPE = np.dtype([("mode", "<u4"), ("clusterID", "<u4"), ("triangleID", "<u4"), ("subTriangleID", "<u4"), ("cfg", "<u4"), ("baseIndices", "<u4", 3),
                            ("partID", "<u4"), ("baryWeightBase", "<f4", 3)])
@@ -391,6 +395,19 @@ class TessClusters(Binding):
 
     def frame_insert_graph(self):
         self._check(self.lib.tc_frame_insert_graph(self._ctx), "frame_insert_graph")
+
+    def run_frames(self, frame_constants, num_frames: int, graph: bool = True, flush_l2: bool = True) -> np.ndarray:
+        """tc_run_frames: `num_frames` frames submitted back to back by the library's own host loop.  `frame_constants` is
+        one (current, last) pair used for every frame, or an array [num_frames, 2].  Returns the device time of every frame
+        in ms (CUDA events around the frame alone, the L2 flush in between outside them).  Synchronises."""
+        fc = np.ascontiguousarray(frame_constants)
+        assert fc.dtype == S.FRAME_CONSTANTS_DTYPE and fc.shape in ((2,), (num_frames, 2))
+        frame_stride = 0 if fc.ndim == 1 else 2 * fc.dtype.itemsize
+        ms = np.zeros(num_frames, np.float32)
+        flags = (RUN_GRAPH if graph else 0) | (RUN_FLUSH_L2 if flush_l2 else 0)
+        self._check(self.lib.tc_run_frames(self._ctx, _ptr(fc), C.c_size_t(fc.dtype.itemsize), C.c_size_t(frame_stride), C.c_uint32(num_frames),
+                                           C.c_uint32(flags), _ptr(ms)), "run_frames")
+        return ms
 
     def sync(self):
         self._check(self.lib.tc_sync(self._ctx), "sync")

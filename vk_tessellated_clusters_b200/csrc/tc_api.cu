@@ -73,12 +73,29 @@ struct tc_context
   uint32_t*         dClassMeta = nullptr;
   uint32_t*         dClusterVertexDst = nullptr;
   FrameStaging*     dFrame     = nullptr;
-  FrameStaging*     hFrame     = nullptr;  // pinned
+  // Ring of pinned staging slots: a frame's constants are snapshotted into a slot at call time and copied to the device
+  // in stream order; a slot is rewritten only after the copy that read it has completed (event per slot).  The caller
+  // may therefore submit frames without synchronising (vkCmdUpdateBuffer semantics, rt.cpp:412-415).
+  static constexpr uint32_t kStagingSlots = 32;
+  FrameStaging*     hFrameRing = nullptr;  // pinned, kStagingSlots entries
+  FrameStaging*     hFrame     = nullptr;  // slot of the frame being submitted
+  cudaEvent_t       stagingEv[kStagingSlots]{};
+  bool              stagingBusy[kStagingSlots]{};
+  uint64_t          frameSerial = 0;       // frames submitted so far (= device frame serial dEpoch[1] once they have run)
+  uint64_t          epochFrames = 0;       // frames since the look-back descriptor arrays were last cleared
+  size_t            lookbackBytes = 0, lookback16Bytes = 0;
   tc_shard_counts*  dShardCounts = nullptr;
   tc_shard_mailbox_slot* dMailbox = nullptr;  // own mailbox: its own allocation so that it can be IPC-exported
   uint32_t*         dShardStatus = nullptr;
   uint32_t          shardRank = 0, shardWorld = 0, shardFrameBase = 0;
   uint64_t          peerMailbox[TC_MAX_SHARDS] = {};
+  // peer-mailbox exchange: the resolve kernel of every frame runs on its own stream (tc_kernels.cu, k_shard_resolve)
+  cudaStream_t      shardStream = nullptr;
+  cudaEvent_t       shardFrameEv = nullptr;              // frame enqueued on the main stream
+  cudaEvent_t       shardResolveEv[TC_SHARD_RING]{};     // resolve of frame f done, slot f % TC_SHARD_RING
+  uint64_t          shardFrames = 0;                     // frames submitted since tc_set_shard_peers
+  bool              shardFailed = false;                 // sticky: a peer's counts never arrived
+  std::vector<cudaEvent_t> runEvents;                    // tc_run_frames: event pairs
   void*             dMiniList = nullptr;
   uint32_t          maxMini = 0;
   uint32_t*         dEmitState = nullptr;  // tc_emit_part_triangles: ticket, pad, total (u64)
@@ -310,10 +327,61 @@ int stage_frame_inputs(tc_context* c, const void* frameConstants, size_t strideB
 {
   if(!frameConstants || strideBytes < sizeof(tc_FrameConstants))
     return fail(TC_ERR_INVALID_ARG, "frameConstants/stride invalid");
+  if(c->shardFailed)
+    return fail(TC_ERR_SHARD_TIMEOUT, "a peer's per-frame counts never arrived (call tc_set_shard_peers to restart the exchange)");
+  const uint32_t slot = uint32_t(c->frameSerial % tc_context::kStagingSlots);
+  if(c->stagingBusy[slot])
+    CUDA_TRY(cudaEventSynchronize(c->stagingEv[slot]));  // the copy that read this slot (32 frames ago) has finished
+  c->hFrame = c->hFrameRing + slot;
   memcpy(&c->hFrame->view[0], frameConstants, sizeof(tc_FrameConstants));
   memcpy(&c->hFrame->view[1], static_cast<const uint8_t*>(frameConstants) + strideBytes, sizeof(tc_FrameConstants));
   const float* vp = viewPosOverride ? viewPosOverride : c->hFrame->view[0].viewPos;  // freezeCulling, rt.cpp:412
   c->hFrame->viewPos[0] = vp[0]; c->hFrame->viewPos[1] = vp[1]; c->hFrame->viewPos[2] = vp[2]; c->hFrame->viewPos[3] = 0.f;
+  // Look-back flags carry epoch << 2 | state and the arrays are never cleared per frame; long before the 30-bit epoch can
+  // alias (32 epochs per frame; emit / batch calls own the ranges above 0x20000000) clear them and restart the epoch word.
+  if(++c->epochFrames >= (1ull << 23))
+  {
+    CUDA_TRY(cudaMemsetAsync(c->dLookback, 0, c->lookbackBytes, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->dLookback16, 0, c->lookback16Bytes, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->dEpoch, 0, 4, c->stream));
+    c->epochFrames = 0;
+  }
+  // stream-ordered upload (outside the captured graph: the graph then has no host-memory node at all)
+  if(c->shardWorld > 1 && c->shardFrames >= TC_SHARD_RING / 2)  // skew bound of the mailbox ring, see tess_clusters.h
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->shardResolveEv[(c->shardFrames - TC_SHARD_RING / 2) % TC_SHARD_RING], 0));
+  CUDA_TRY(cudaMemcpyAsync(c->dFrame, c->hFrame, sizeof(FrameStaging), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaEventRecord(c->stagingEv[slot], c->stream));
+  c->stagingBusy[slot] = true;
+  c->frameSerial++;
+  return TC_OK;
+}
+
+// peer-mailbox exchange: after frame f has been enqueued on the main stream, its resolve goes to the side stream
+int enqueue_shard_resolve(tc_context* c)
+{
+  if(c->shardWorld <= 1)
+    return TC_OK;
+  const uint32_t frame = uint32_t(++c->shardFrames);  // device side: epochCounter[1] - shardFrameBase, the same number
+  CUDA_TRY(cudaEventRecord(c->shardFrameEv, c->stream));
+  CUDA_TRY(cudaStreamWaitEvent(c->shardStream, c->shardFrameEv, 0));
+  tc::launch_shard_resolve(c->params, frame, c->shardStream);
+  CUDA_TRY(cudaEventRecord(c->shardResolveEv[frame % TC_SHARD_RING], c->shardStream));
+  CUDA_TRY(cudaGetLastError());
+  return TC_OK;
+}
+
+// both streams idle; turns a resolve time-out into the sticky error state
+int sync_all(tc_context* c)
+{
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if(c->shardWorld > 1)
+  {
+    CUDA_TRY(cudaStreamSynchronize(c->shardStream));
+    uint32_t status = 0;
+    CUDA_TRY(cudaMemcpy(&status, c->dShardStatus, 4, cudaMemcpyDeviceToHost));
+    if(status)
+      c->shardFailed = true;
+  }
   return TC_OK;
 }
 
@@ -323,19 +391,14 @@ int enqueue_build(tc_context* c)
   cudaStream_t s = c->stream;
   tc::Params&  p = c->params;
   uint32_t     launches = 0;
-  CUDA_TRY(cudaMemcpyAsync(c->dFrame, c->hFrame, sizeof(FrameStaging), cudaMemcpyHostToDevice, s));
   {
+    // resets (rt.cpp:412-419) + instances_classify + clusters_cull + BUILD_SETUP_CLASSIFY: one launch (k_frame_begin)
     StageScope sc(c, TC_STAGE_INSTANCES_CLASSIFY);
-    // vkCmdFillBuffer(splitTriangles, ~0) (:419)
-    CUDA_TRY(cudaMemsetAsync(c->splitTriangles, 0xFF, size_t(c->maxSplit) * sizeof(tc_TessTriangleInfo), s));
-    tc::launch_frame_setup(p, c->dBuildTmpl, c->dFrame->viewPos, c->dEpoch, s);
-    tc::launch_instances_classify(p, s);
-    launches += 2;
+    tc::launch_frame_begin(p, c->dBuildTmpl, c->dFrame->viewPos, c->dEpoch, uint32_t(c->numSMs), s);
+    launches += 1;
   }
   {
-    StageScope sc(c, TC_STAGE_CULL);
-    tc::launch_clusters_cull(p, s);
-    launches += 1;
+    StageScope sc(c, TC_STAGE_CULL);  // (fused into the launch above; the stage keeps its slot in the timer table)
   }
   {
     StageScope sc(c, TC_STAGE_CLUSTER_CLASSIFY);
@@ -364,8 +427,7 @@ int enqueue_build(tc_context* c)
   }
   {
     StageScope sc(c, TC_STAGE_PREP_INSTANTIATE);
-    uint32_t grid = std::max(1u, uint32_t(c->numSMs * c->occ.instantiate));
-    tc::launch_instantiate(p, c->dEpoch, grid, s);
+    tc::launch_instantiate(p, c->dEpoch, uint32_t(c->numSMs), c->occ, s);
     launches += 1;
   }
   c->lastLaunches = launches;  // (the shard summary for the multi-GPU allgather is written by k_instantiate's last CTA)
@@ -460,18 +522,27 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   TRY_RC(dalloc(c->dEmitState, 16));
   TRY_RC(dalloc(c->dBatchState, 64));
   TRY_RC(dalloc(c->dMailbox, tc_shard_mailbox_bytes()));
-  CUDA_TRY(cudaMemset(c->dMailbox, 0xFF, tc_shard_mailbox_bytes()));  // no slot carries a valid frame number yet
+  TRY_CUDA(cudaMemsetAsync(c->dMailbox, 0xFF, tc_shard_mailbox_bytes(), c->stream));  // no slot carries a valid frame number yet
   TRY_RC(dalloc(c->dShardStatus, 16));
-  CUDA_TRY(cudaMemset(c->dShardStatus, 0, 16));
+  TRY_CUDA(cudaMemsetAsync(c->dShardStatus, 0, 16, c->stream));
   TRY_RC(dalloc(c->dShardBase, 16));
-  TRY_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->hFrame), sizeof(FrameStaging)));
-  memset(c->hFrame, 0, sizeof(FrameStaging));
+  TRY_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->hFrameRing), sizeof(FrameStaging) * tc_context::kStagingSlots));
+  memset(c->hFrameRing, 0, sizeof(FrameStaging) * tc_context::kStagingSlots);
+  c->hFrame = c->hFrameRing;
+  for(uint32_t i = 0; i < tc_context::kStagingSlots; i++)
+    TRY_CUDA(cudaEventCreateWithFlags(&c->stagingEv[i], cudaEventDisableTiming));
+  TRY_CUDA(cudaStreamCreateWithFlags(&c->shardStream, cudaStreamNonBlocking));
+  TRY_CUDA(cudaEventCreateWithFlags(&c->shardFrameEv, cudaEventDisableTiming));
+  for(uint32_t i = 0; i < TC_SHARD_RING; i++)
+    TRY_CUDA(cudaEventCreateWithFlags(&c->shardResolveEv[i], cudaEventDisableTiming));
   size_t lbBytes = size_t(tc::lookback_tiles_needed(c->maxVisible, c->maxSplit, c->maxPart)) * tc::lookback_desc_bytes();
+  c->lookbackBytes = lbBytes;
   TRY_RC(dalloc(c->dLookback, lbBytes));
-  TRY_CUDA(cudaMemset(c->dLookback, 0, lbBytes));
+  TRY_CUDA(cudaMemsetAsync(c->dLookback, 0, lbBytes, c->stream));
   size_t lb16Bytes = size_t(tc::lookback16_tiles_needed(std::max(c->maxPart, c->maxSplit))) * 16;
+  c->lookback16Bytes = lb16Bytes;
   TRY_RC(dalloc(c->dLookback16, lb16Bytes));
-  TRY_CUDA(cudaMemset(c->dLookback16, 0, lb16Bytes));
+  TRY_CUDA(cudaMemsetAsync(c->dLookback16, 0, lb16Bytes, c->stream));
   TRY_RC(dalloc(c->dClassTuples, size_t(c->maxVisible) * tc::classify_tuple_bytes()));
   TRY_RC(dalloc(c->dFactorStash, size_t(c->maxVisible) * config->clusterTriangles * 12));
   TRY_RC(dalloc(c->dClassMeta, size_t(c->maxVisible) * 4));
@@ -480,10 +551,10 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   c->maxMini = (config->flags & TC_FLAG_TRANSIENT_2X) ? uint32_t(std::min<uint64_t>(uint64_t(c->maxVerts) / 7 + 64, 0xFFFFFFF0ull)) : 0u;
   if(c->maxMini)
     TRY_RC(dalloc(c->dMiniList, size_t(c->maxMini) * 32));
-  TRY_CUDA(cudaMemset(c->dEpoch, 0, 16));
-  TRY_CUDA(cudaMemset(c->dShardBase, 0, 16));
-  TRY_CUDA(cudaMemset(c->dReadback, 0, sizeof(tc_Readback)));
-  TRY_CUDA(cudaMemset(c->dState, 0, tc::frame_state_bytes()));
+  TRY_CUDA(cudaMemsetAsync(c->dEpoch, 0, 16, c->stream));
+  TRY_CUDA(cudaMemsetAsync(c->dShardBase, 0, 16, c->stream));
+  TRY_CUDA(cudaMemsetAsync(c->dReadback, 0, sizeof(tc_Readback), c->stream));
+  TRY_CUDA(cudaMemsetAsync(c->dState, 0, tc::frame_state_bytes(), c->stream));
 
   const size_t G = c->maxGenClusters;
   TRY_RC(dalloc(c->visibleClusters, size_t(c->maxVisible) * sizeof(tc_ClusterInfo)));
@@ -506,15 +577,17 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
     TRY_RC(dalloc(c->genClusterData, size_t(config->numGeneratedClusterMegs) * 1024 * 1024));
   else
     c->genClusterData = reinterpret_cast<void*>(0x0000700000000000ull);  // address range only; nothing dereferences it
-  TRY_CUDA(cudaMemset(c->partTriangles, 0, size_t(c->maxPart) * sizeof(tc_TessTriangleInfo)));
-  TRY_CUDA(cudaMemset(c->genVertices, 0, size_t(c->maxVerts) * 12));
-  TRY_CUDA(cudaMemset(c->tempClusterSizes, 0, G * 4));
-  TRY_CUDA(cudaMemset(c->blasClusterAddresses, 0, G * 8));
+  TRY_CUDA(cudaMemsetAsync(c->splitTriangles, 0xFF, size_t(c->maxSplit) * sizeof(tc_TessTriangleInfo), c->stream));  // vkCmdFillBuffer (rt.cpp:419); per frame only what was written is refilled
+  TRY_CUDA(cudaMemsetAsync(c->partTriangles, 0, size_t(c->maxPart) * sizeof(tc_TessTriangleInfo), c->stream));
+  TRY_CUDA(cudaMemsetAsync(c->genVertices, 0, size_t(c->maxVerts) * 12, c->stream));
+  TRY_CUDA(cudaMemsetAsync(c->tempClusterSizes, 0, G * 4, c->stream));
+  TRY_CUDA(cudaMemsetAsync(c->blasClusterAddresses, 0, G * 8, c->stream));
   if(c->transClusterSizes)
-    TRY_CUDA(cudaMemset(c->transClusterSizes, 0, G * 4));
+    TRY_CUDA(cudaMemsetAsync(c->transClusterSizes, 0, G * 4, c->stream));
   for(int i = 0; i <= TC_STAGE_COUNT; i++)
     TRY_CUDA(cudaEventCreate(&c->ev[i]));
   c->evValid = true;
+  TRY_CUDA(cudaStreamSynchronize(c->stream));  // all initialisation above is ordered on the context stream
 #undef TRY_RC
 #undef TRY_CUDA
   *out = c;
@@ -532,8 +605,22 @@ TC_API void tc_destroy(tc_context* c)
   free_scene(c);
   dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dClusterVertexDst); dfree(c->dFrame);
   dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState); dfree(c->dBatchState); dfree(c->dMiniList); dfree(c->dMailbox); dfree(c->dShardStatus);
-  if(c->hFrame)
-    cudaFreeHost(c->hFrame);
+  if(c->shardStream)
+    cudaStreamSynchronize(c->shardStream);
+  if(c->hFrameRing)
+    cudaFreeHost(c->hFrameRing);
+  for(cudaEvent_t e : c->stagingEv)
+    if(e)
+      cudaEventDestroy(e);
+  for(cudaEvent_t e : c->shardResolveEv)
+    if(e)
+      cudaEventDestroy(e);
+  if(c->shardFrameEv)
+    cudaEventDestroy(c->shardFrameEv);
+  for(cudaEvent_t e : c->runEvents)
+    cudaEventDestroy(e);
+  if(c->shardStream)
+    cudaStreamDestroy(c->shardStream);
   dfree(c->visibleClusters); dfree(c->splitTriangles); dfree(c->partTriangles); dfree(c->genVertices);
   dfree(c->tempInstanceIDs); dfree(c->tempInstantiations); dfree(c->tempClusterAddresses); dfree(c->tempClusterSizes);
   dfree(c->transInstanceIDs); dfree(c->transBuilds); dfree(c->transClusterAddresses); dfree(c->transClusterSizes);
@@ -639,6 +726,7 @@ TC_API int tc_set_tess_table(tc_context* c, const uint32_t* vertices, uint32_t n
   CUDA_TRY(cudaMemcpy(c->tblEntries, lookup.data(), lookup.size() * sizeof(tc_TessTableEntry), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->tblTemplAddr, templAddr4096, TC_TESSTABLE_LOOKUP_ENTRIES * 8, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->tblTemplSize, templSize4096, TC_TESSTABLE_LOOKUP_ENTRIES * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaDeviceSynchronize());  // the blocking copies above ran on the legacy stream; c->stream does not order with it
   c->tableSet = true;
   drop_graph(c);
   fill_params(c);
@@ -715,14 +803,14 @@ TC_API int tc_set_scene(tc_context* c, const tc_geometry* geoms, uint32_t numGeo
   if((rc = dalloc(c->dInstances, size_t(numInstances) * sizeof(tc_RenderInstance))) || (rc = dalloc(c->dClusterPrefix, size_t(numInstances + 1) * 4))
      || (rc = dalloc(c->instanceStates, size_t(numInstances) * 4)) || (rc = dalloc(c->blasBuildInfos, size_t(numInstances) * sizeof(tc_BlasBuildInfo)))
      || (rc = dalloc(c->blasBuildSizes, size_t(numInstances) * 4)) || (rc = dalloc(c->basicClusterSizes, size_t(std::max(numBasicClusterSizes, 1u)) * 4))
-     || (rc = dalloc(c->globalRanges, size_t(numInstances) * sizeof(tc_global_blas_range)))
+     || (rc = dalloc(c->globalRanges, size_t(numInstances) * TC_SHARD_RING * sizeof(tc_global_blas_range)))
      || (rc = dalloc(c->segLo, size_t(TC_MAX_SEGMENTS + 2) * (numInstances + 1) * 4)) || (rc = dalloc(c->rankBase, size_t(TC_MAX_SEGMENTS + 2) * (numInstances + 1) * 4)))
     return rc;
   CUDA_TRY(cudaMemcpy(c->dInstances, inst.data(), size_t(numInstances) * sizeof(tc_RenderInstance), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->dClusterPrefix, prefix.data(), size_t(numInstances + 1) * 4, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemset(c->instanceStates, 0, size_t(numInstances) * 4));
-  CUDA_TRY(cudaMemset(c->blasBuildInfos, 0, size_t(numInstances) * sizeof(tc_BlasBuildInfo)));
-  CUDA_TRY(cudaMemset(c->blasBuildSizes, 0, size_t(numInstances) * 4));
+  CUDA_TRY(cudaMemsetAsync(c->instanceStates, 0, size_t(numInstances) * 4, c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->blasBuildInfos, 0, size_t(numInstances) * sizeof(tc_BlasBuildInfo), c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->blasBuildSizes, 0, size_t(numInstances) * 4, c->stream));
   if(basicClusterSizes && numBasicClusterSizes)
     CUDA_TRY(cudaMemcpy(c->basicClusterSizes, basicClusterSizes, size_t(numBasicClusterSizes) * 4, cudaMemcpyHostToDevice));
 
@@ -764,6 +852,7 @@ TC_API int tc_set_scene(tc_context* c, const tc_geometry* geoms, uint32_t numGeo
   c->params.textures = c->dTextureTable;
   for(uint32_t t = 0; t < numTextures; t++)
     c->params.texturesC[t] = c->hTextureTable[t];
+  CUDA_TRY(cudaDeviceSynchronize());  // as in tc_set_tess_table
   c->sceneSet = true;
   fill_params(c);
   return upload_template(c);
@@ -789,6 +878,7 @@ TC_API int tc_set_hiz(tc_context* c, const float* mips, uint32_t size, uint32_t 
     return rc;
   c->hizFloats = total;
   CUDA_TRY(cudaMemcpy(c->hiz, mips, total * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaDeviceSynchronize());
   c->params.hizSize = size;
   c->params.hizMips = mipLevels;
   drop_graph(c);
@@ -849,7 +939,7 @@ TC_API int tc_update_hiz(tc_context* c, const float* depth, uint32_t width, uint
     if((rc = dalloc(c->hiz, total * 4)))
       return rc;
     c->hizFloats = total;
-    CUDA_TRY(cudaMemset(c->hiz, 0, total * 4));
+    CUDA_TRY(cudaMemsetAsync(c->hiz, 0, total * 4, c->stream));
     c->params.hizSize = size;
     c->params.hizMips = mips;
     drop_graph(c);
@@ -961,7 +1051,9 @@ TC_API int tc_frame_insert(tc_context* c)
   int rc = check_ready(c);
   if(rc)
     return rc;
-  return enqueue_insert(c);
+  if((rc = enqueue_insert(c)))
+    return rc;
+  return enqueue_shard_resolve(c);
 }
 
 TC_API int tc_frame(tc_context* c, const void* frameConstants, size_t strideBytes, const float* viewPosOverride)
@@ -969,8 +1061,39 @@ TC_API int tc_frame(tc_context* c, const void* frameConstants, size_t strideByte
   int rc = tc_frame_build(c, frameConstants, strideBytes, viewPosOverride);
   if(rc)
     return rc;
-  return enqueue_insert(c);
+  if((rc = enqueue_insert(c)))
+    return rc;
+  return enqueue_shard_resolve(c);
 }
+
+namespace {
+// capture `what` (0: build half, 1: insert half, 2: whole frame) once and replay it
+int replay_graph(tc_context* c, cudaGraphExec_t& exec, int what)
+{
+  if(!exec)
+  {
+    bool savedTimers = c->timers;
+    c->timers        = false;
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = what == 1 ? TC_OK : enqueue_build(c);
+    if(rc == TC_OK && what != 0)
+      rc = enqueue_insert(c);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    c->timers     = savedTimers;
+    if(rc == TC_OK && e != cudaSuccess)
+      rc = fail(TC_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    if(rc == TC_OK && (e = cudaGraphInstantiate(&exec, graph, 0)) != cudaSuccess)
+      rc = fail(TC_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+    if(graph)
+      cudaGraphDestroy(graph);
+    if(rc != TC_OK)
+      return rc;
+  }
+  CUDA_TRY(cudaGraphLaunch(exec, c->stream));
+  return TC_OK;
+}
+}  // namespace
 
 TC_API int tc_frame_graph(tc_context* c, const void* frameConstants, size_t strideBytes, const float* viewPosOverride)
 {
@@ -979,56 +1102,10 @@ TC_API int tc_frame_graph(tc_context* c, const void* frameConstants, size_t stri
     return rc;
   if((rc = stage_frame_inputs(c, frameConstants, strideBytes, viewPosOverride)))
     return rc;
-  if(!c->graphExec)
-  {
-    bool savedTimers = c->timers;
-    c->timers        = false;
-    cudaGraph_t graph = nullptr;
-    CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue_build(c);
-    if(rc == TC_OK)
-      rc = enqueue_insert(c);
-    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
-    c->timers     = savedTimers;
-    if(rc != TC_OK)
-      return rc;
-    if(e != cudaSuccess)
-      return fail(TC_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&c->graphExec, graph, 0);
-    cudaGraphDestroy(graph);
-    if(e != cudaSuccess)
-      return fail(TC_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
-  }
-  CUDA_TRY(cudaGraphLaunch(c->graphExec, c->stream));
-  return TC_OK;
+  if((rc = replay_graph(c, c->graphExec, 2)))
+    return rc;
+  return enqueue_shard_resolve(c);
 }
-
-namespace {
-// capture `what` (0: build half, 1: insert half) once and replay it
-int replay_half(tc_context* c, cudaGraphExec_t& exec, int what)
-{
-  if(!exec)
-  {
-    bool savedTimers = c->timers;
-    c->timers        = false;
-    cudaGraph_t graph = nullptr;
-    CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    int         rc = what == 0 ? enqueue_build(c) : enqueue_insert(c);
-    cudaError_t e  = cudaStreamEndCapture(c->stream, &graph);
-    c->timers      = savedTimers;
-    if(rc != TC_OK)
-      return rc;
-    if(e != cudaSuccess)
-      return fail(TC_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if(e != cudaSuccess)
-      return fail(TC_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
-  }
-  CUDA_TRY(cudaGraphLaunch(exec, c->stream));
-  return TC_OK;
-}
-}  // namespace
 
 TC_API int tc_frame_build_graph(tc_context* c, const void* frameConstants, size_t strideBytes, const float* viewPosOverride)
 {
@@ -1037,7 +1114,7 @@ TC_API int tc_frame_build_graph(tc_context* c, const void* frameConstants, size_
     return rc;
   if((rc = stage_frame_inputs(c, frameConstants, strideBytes, viewPosOverride)))
     return rc;
-  return replay_half(c, c->graphBuild, 0);
+  return replay_graph(c, c->graphBuild, 0);
 }
 
 TC_API int tc_frame_insert_graph(tc_context* c)
@@ -1045,7 +1122,56 @@ TC_API int tc_frame_insert_graph(tc_context* c)
   int rc = check_ready(c);
   if(rc)
     return rc;
-  return replay_half(c, c->graphInsert, 1);
+  if((rc = replay_graph(c, c->graphInsert, 1)))
+    return rc;
+  return enqueue_shard_resolve(c);
+}
+
+// Batch submission from one native loop (tess_clusters.h): per frame at most a staging copy, an optional L2 flush, two
+// event records and one graph launch (or the stream launches of tc_frame); with peer mailboxes also the side-stream resolve.
+TC_API int tc_run_frames(tc_context* c, const void* frameConstants, size_t strideBytes, size_t frameStrideBytes, uint32_t numFrames, uint32_t flags,
+                         float* frameMsOut)
+{
+  int rc = check_ready(c);
+  if(rc)
+    return rc;
+  if(!frameConstants || numFrames == 0)
+    return fail(TC_ERR_INVALID_ARG, "frameConstants missing or numFrames == 0");
+  while(c->runEvents.size() < size_t(numFrames) * 2)
+  {
+    cudaEvent_t e = nullptr;
+    CUDA_TRY(cudaEventCreate(&e));
+    c->runEvents.push_back(e);
+  }
+  if(flags & TC_RUN_FLUSH_L2)
+    if((rc = tc_flush_l2(c)))  // allocates the flush buffer on first use
+      return rc;
+  for(uint32_t f = 0; f < numFrames; f++)
+  {
+    const uint8_t* fc = static_cast<const uint8_t*>(frameConstants) + size_t(f) * frameStrideBytes;
+    if(f && (flags & TC_RUN_FLUSH_L2))
+      tc::launch_flush_l2(c->flushBuf, c->flushBytes, c->stream);
+    if((rc = stage_frame_inputs(c, fc, strideBytes, nullptr)))
+      return rc;
+    CUDA_TRY(cudaEventRecord(c->runEvents[2 * f], c->stream));
+    if(flags & TC_RUN_GRAPH)
+      rc = replay_graph(c, c->graphExec, 2);
+    else if((rc = enqueue_build(c)) == TC_OK)
+      rc = enqueue_insert(c);
+    if(rc)
+      return rc;
+    CUDA_TRY(cudaEventRecord(c->runEvents[2 * f + 1], c->stream));
+    if((rc = enqueue_shard_resolve(c)))
+      return rc;
+  }
+  if((rc = sync_all(c)))
+    return rc;
+  if(frameMsOut)
+    for(uint32_t f = 0; f < numFrames; f++)
+      CUDA_TRY(cudaEventElapsedTime(&frameMsOut[f], c->runEvents[2 * f], c->runEvents[2 * f + 1]));
+  if(c->shardFailed)
+    return fail(TC_ERR_SHARD_TIMEOUT, "a peer's per-frame counts never arrived");
+  return TC_OK;
 }
 
 TC_API int tc_sync(tc_context* c)
@@ -1053,7 +1179,11 @@ TC_API int tc_sync(tc_context* c)
   if(!c)
     return fail(TC_ERR_INVALID_ARG, "null context");
   CUDA_TRY(cudaSetDevice(c->device));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  int rc = sync_all(c);
+  if(rc)
+    return rc;
+  if(c->shardFailed)
+    return fail(TC_ERR_SHARD_TIMEOUT, "a peer's per-frame counts never arrived");
   return TC_OK;
 }
 
@@ -1066,7 +1196,11 @@ TC_API int tc_readback(tc_context* c, tc_Readback* readback, tc_SceneBuilding* b
     CUDA_TRY(cudaMemcpyAsync(readback, c->dReadback, sizeof(tc_Readback), cudaMemcpyDeviceToHost, c->stream));
   if(building)
     CUDA_TRY(cudaMemcpyAsync(building, c->dBuild, sizeof(tc_SceneBuilding), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  int rc = sync_all(c);
+  if(rc)
+    return rc;
+  if(c->shardFailed)
+    return fail(TC_ERR_SHARD_TIMEOUT, "a peer's per-frame counts never arrived");
   return TC_OK;
 }
 
@@ -1352,7 +1486,8 @@ TC_API int tc_device_global_blas_ranges(tc_context* c, uint64_t* deviceAddress)
 {
   if(!c || !deviceAddress)
     return fail(TC_ERR_INVALID_ARG, "null argument");
-  *deviceAddress = uint64_t(c->globalRanges);
+  // peer mailboxes: the ring slot of the most recently submitted frame (k_blas_setup / k_shard_resolve)
+  *deviceAddress = uint64_t(c->globalRanges + (c->shardWorld > 1 ? size_t(c->shardFrames % TC_SHARD_RING) * c->numInstances : 0));
   return TC_OK;
 }
 
@@ -1415,7 +1550,7 @@ TC_API int tc_device_shard_counts(tc_context* c, uint64_t* deviceAddress)
   return TC_OK;
 }
 
-TC_API size_t tc_shard_mailbox_bytes(void) { return sizeof(tc_shard_mailbox_slot) * 2 * TC_MAX_SHARDS; }
+TC_API size_t tc_shard_mailbox_bytes(void) { return sizeof(tc_shard_mailbox_slot) * TC_SHARD_RING * TC_MAX_SHARDS; }
 
 TC_API int tc_device_shard_mailbox(tc_context* c, uint64_t* deviceAddress)
 {
@@ -1433,6 +1568,7 @@ TC_API int tc_set_shard_peers(tc_context* c, uint32_t rank, uint32_t world, cons
     return fail(TC_ERR_INVALID_ARG, "bad rank / world / addresses");
   CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->shardStream));
   c->shardRank  = world > 1 ? rank : 0;
   c->shardWorld = world > 1 ? world : 0;
   for(uint32_t r = 0; r < TC_MAX_SHARDS; r++)
@@ -1440,11 +1576,14 @@ TC_API int tc_set_shard_peers(tc_context* c, uint32_t rank, uint32_t world, cons
   if(world > 1 && c->peerMailbox[rank] != uint64_t(c->dMailbox))
     return fail(TC_ERR_INVALID_ARG, "mailboxAddresses[rank] must be this context's own mailbox");
   // frame tags restart at 1; the caller separates this call from the first frame of ANY rank by a barrier
-  uint32_t epoch = 0;
-  CUDA_TRY(cudaMemcpy(&epoch, c->dEpoch, 4, cudaMemcpyDeviceToHost));
-  c->shardFrameBase = epoch >> 5;
-  CUDA_TRY(cudaMemset(c->dMailbox, 0xFF, tc_shard_mailbox_bytes()));
-  CUDA_TRY(cudaMemset(c->dShardStatus, 0, 16));
+  uint32_t serial = 0;
+  CUDA_TRY(cudaMemcpy(&serial, c->dEpoch + 1, 4, cudaMemcpyDeviceToHost));  // device frame serial (k_frame_setup)
+  c->shardFrameBase = serial;
+  c->shardFrames    = 0;
+  c->shardFailed    = false;
+  CUDA_TRY(cudaMemsetAsync(c->dMailbox, 0xFF, tc_shard_mailbox_bytes(), c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->dShardStatus, 0, 16, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
   drop_graph(c);
   fill_params(c);
   return TC_OK;
@@ -1455,17 +1594,16 @@ TC_API int tc_shard_gathered(tc_context* c, tc_shard_counts* out, uint32_t capac
   if(!c || !out || capacity < c->shardWorld)
     return fail(TC_ERR_INVALID_ARG, "null argument or capacity below the world size");
   CUDA_TRY(cudaSetDevice(c->device));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
-  uint32_t epoch = 0, status = 0;
-  CUDA_TRY(cudaMemcpy(&epoch, c->dEpoch, 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(&status, c->dShardStatus, 4, cudaMemcpyDeviceToHost));
-  std::vector<tc_shard_mailbox_slot> slots(2 * TC_MAX_SHARDS);
+  int rc = sync_all(c);
+  if(rc)
+    return rc;
+  std::vector<tc_shard_mailbox_slot> slots(size_t(TC_SHARD_RING) * TC_MAX_SHARDS);
   CUDA_TRY(cudaMemcpy(slots.data(), c->dMailbox, tc_shard_mailbox_bytes(), cudaMemcpyDeviceToHost));
-  const uint32_t frame = (epoch >> 5) - c->shardFrameBase;
+  const uint32_t frame = uint32_t(c->shardFrames);  // most recently submitted frame (complete: both streams are idle)
   for(uint32_t r = 0; r < c->shardWorld; r++)
-    out[r] = slots[(frame & 1u) * TC_MAX_SHARDS + r].counts;
+    out[r] = slots[size_t(frame % TC_SHARD_RING) * TC_MAX_SHARDS + r].counts;
   if(timedOut)
-    *timedOut = status;
+    *timedOut = c->shardFailed ? 1u : 0u;
   return TC_OK;
 }
 

@@ -707,19 +707,27 @@ __device__ __forceinline__ F3 eval_pn(const BaseTriangle& b, float u, float v, f
 //   words 8..37  position polynomial in the power basis, P = sum c_jk s^j t^k (10 x float3), converted from the PN
 //                control net of displacement.glsl:47-79 (9 FMA per component instead of 44 mul/add)
 //   words 38,39  displacement scale / offset
-//   words 40..47, 56 normal n0, n1-n0, n2-n0 (the last component sits in word 56)
+//   words 40..47, 54 normal n0, n1-n0, n2-n0 (the last component sits in word 54)
 //   words 48..53 texel-space texcoord x = u*W-0.5 and y = v*H-0.5 as affine functions of (s,t), interleaved for packed
-//                (x,y) arithmetic: X0,Y0,X1,Y1,X2,Y2      words 54,55  1/W, 1/H
-//   words 57,58  cudaTextureObject_t of the gather view      word 59 part index
+//                (x,y) arithmetic: X0,Y0,X1,Y1,X2,Y2      word 55 part index
+//   per-part texture handles only (TEX == 2): words 56,57  1/W, 1/H      words 58,59  cudaTextureObject_t of the gather view
+// Scenes with one texture (or none) take 1/W, 1/H and the handle from the kernel parameters: 56 words, which is what lets
+// 24 warps of k_instantiate share an SM's shared memory.
 // ------------------------------------------------------------------------------------------------------------
 
-#define TC_REC_WORDS 60
+#define TC_REC_WORDS_MAX 60
+template <int TEX>
+struct RecWords
+{
+  static constexpr int value = TEX == 2 ? 60 : 56;
+};
 
 __device__ __forceinline__ void st3(float* dst, F3 v)
 {
   dst[0] = v.x; dst[1] = v.y; dst[2] = v.z;
 }
 
+template <int TEX>
 __device__ __forceinline__ void build_part_record(const Params& p, const tc_RenderInstance& inst, uint32_t instanceID, uint32_t firstLocalVertex,
                                                   uint32_t i0, uint32_t i1, uint32_t i2, const uint32_t vtxEncoded[3], bool flipped,
                                                   uint32_t slotBase, uint32_t numSlots, uint32_t partIndex, float* rec)
@@ -746,8 +754,8 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
   const float buO = flipped ? bu[1] : bu[0], buA = flipped ? bu[0] : bu[1];  // origin corner, corner multiplied by q1
   const float bvO = flipped ? bv[1] : bv[0], bvA = flipped ? bv[0] : bv[1];
   const int texture = (p.numTextures > 0 && inst.displacementIndex >= 0) ? inst.displacementIndex : -1;
-  // the record is written as 15 float4: 128-bit shared stores of 8 lanes at a 60-word stride touch 32 distinct banks
-  // (scalar stores at that stride are 4-way conflicted)
+  // the record is written as 14 (15) float4: 128-bit shared stores of 8 lanes at a 56- or 60-word stride touch 32 distinct
+  // banks (scalar stores at that stride are 4-way conflicted)
   float4* rec4 = reinterpret_cast<float4*>(rec);
   rec4[0] = make_float4(buO, buA - buO, bu[2] - buO, bvO);
   rec4[1] = make_float4(bvA - bvO, bv[2] - bvO, __uint_as_float(slotBase), __uint_as_float(numSlots));
@@ -809,8 +817,9 @@ __device__ __forceinline__ void build_part_record(const Params& p, const tc_Rend
     texObj = p.texturesC[ti].gather;
   }
   rec4[12] = make_float4(fmaf(tu[0], W, -0.5f), fmaf(tv[0], H, -0.5f), (tu[1] - tu[0]) * W, (tv[1] - tv[0]) * H);
-  rec4[13] = make_float4((tu[2] - tu[0]) * W, (tv[2] - tv[0]) * H, 1.0f / W, 1.0f / H);
-  rec4[14] = make_float4(dn2.z, __uint_as_float(uint32_t(texObj)), __uint_as_float(uint32_t(texObj >> 32)), __uint_as_float(partIndex));
+  rec4[13] = make_float4((tu[2] - tu[0]) * W, (tv[2] - tv[0]) * H, dn2.z, __uint_as_float(partIndex));
+  if(TEX == 2)
+    rec4[14] = make_float4(1.0f / W, 1.0f / H, __uint_as_float(uint32_t(texObj)), __uint_as_float(uint32_t(texObj >> 32)));
 }
 
 // (takes plain pointers: passing the by-value kernel parameter block to a non-inlined function would copy it to local memory)
@@ -888,7 +897,7 @@ __device__ __forceinline__ void eval_position2(const PositionCoeffs& k, float2 s
 // the distinct handles of the warp, which also stops it from batching the gathers.
 template <int TEX, int NP>
 __device__ __forceinline__ void eval_part_pairs(const float4* rec, const float4 (&q)[NP], float2 (&X)[NP], float2 (&Y)[NP], float2 (&Z)[NP],
-                                                cudaTextureObject_t uniformTex)
+                                                cudaTextureObject_t uniformTex, float2 uniformInvSize)
 {
   float2 s[NP], t[NP];
   {
@@ -906,8 +915,15 @@ __device__ __forceinline__ void eval_part_pairs(const float4* rec, const float4 
   float4 g[2 * NP];
   if(DISPLACED)
   {
-    // c0 = (X0, Y0, X1, Y1), c1 = (X2, Y2, 1/W, 1/H), texture object = (m.y, m.z)
+    // c0 = (X0, Y0, X1, Y1), c1 = (X2, Y2, dn2.z, part index); 1/W, 1/H and the texture object: uniform, or rec[14] (TEX == 2)
     const float4 c0 = rec[12], c1 = rec[13];
+    float2       inv = uniformInvSize;
+    float4       m   = make_float4(0.f, 0.f, 0.f, 0.f);
+    if(TEX == 2)
+    {
+      m   = rec[14];
+      inv = make_float2(m.x, m.y);
+    }
     const float  M  = 12582912.0f;  // 1.5 * 2^23: (v + M) - M = rint(v) for |v| < 2^22, on the FMA pipe
     float2       gc[2 * NP];
 #pragma unroll
@@ -917,7 +933,7 @@ __device__ __forceinline__ void eval_part_pairs(const float4* rec, const float4 
       const float2 xy = fma2(bc2(tv), make_float2(c1.x, c1.y), fma2(bc2(sv), make_float2(c0.z, c0.w), make_float2(c0.x, c0.y)));
       const float2 f  = add2(add2(add2(xy, bc2(-0.5f)), bc2(M)), bc2(-M));
       axy[i] = fma2(f, bc2(-1.0f), xy);
-      gc[i]  = fma2(f, make_float2(c1.z, c1.w), make_float2(c1.z, c1.w));
+      gc[i]  = fma2(f, inv, inv);
     }
     if(TEX == 1)
     {
@@ -927,8 +943,7 @@ __device__ __forceinline__ void eval_part_pairs(const float4* rec, const float4 
     }
     else
     {
-      const float4 m = rec[14];
-      const cudaTextureObject_t tex = (unsigned long long)__float_as_uint(m.y) | ((unsigned long long)__float_as_uint(m.z) << 32);
+      const cudaTextureObject_t tex = (unsigned long long)__float_as_uint(m.z) | ((unsigned long long)__float_as_uint(m.w) << 32);
 #pragma unroll
       for(int i = 0; i < 2 * NP; i++)
         g[i] = tex2Dgather<float4>(tex, gc[i].x, gc[i].y, 0);
@@ -946,9 +961,9 @@ __device__ __forceinline__ void eval_part_pairs(const float4* rec, const float4 
   }
   if(DISPLACED)
   {
-    // n0 = n0.xyz, dn1 = (n0.w,n1.x,n1.y), dn2 = (n1.z,n1.w,rec[14].x)
+    // n0 = n0.xyz, dn1 = (n0.w,n1.x,n1.y), dn2 = (n1.z,n1.w,rec[13].z)
     const float4 n0 = rec[10], n1 = rec[11];
-    const float  n2z = rec[14].x;
+    const float  n2z = rec[13].z;
 #pragma unroll
     for(int i = 0; i < NP; i++)
     {

@@ -64,9 +64,8 @@ __device__ __forceinline__ uint32_t hi32(unsigned long long v) { return uint32_t
 // frame setup: rt.cpp:412-419
 // ============================================================================================================
 
-__global__ void k_frame_setup(Params p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter)
+__device__ __forceinline__ void frame_setup_body(const Params& p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter)
 {
-  pdl_prologue();
   const uint32_t t = threadIdx.x;
   // SceneBuilding <- host template (all counters zero), word by word
   const uint32_t* src = reinterpret_cast<const uint32_t*>(tmpl);
@@ -86,6 +85,13 @@ __global__ void k_frame_setup(Params p, const tc_SceneBuilding* tmpl, const floa
   {
     epochCounter[0] += 32;  // 32 launch slots per frame (the host clears the descriptor arrays and restarts this word long before it wraps)
     epochCounter[1] += 1;   // frame serial: never restarted; tags the peer-mailbox records
+    // BUILD_SETUP_CLASSIFY (build_setup.comp.glsl:105-119): in the ray-tracing build every cluster is visible
+    const uint32_t total = p.totalClusters, count = min(total, p.maxVisibleClusters);
+    p.readback->numVisibleClusters  = total;
+    p.build->visibleClusterCounter  = count;
+    p.build->dispatchClassify.gridX = count;
+    p.build->dispatchClassify.gridY = 1;
+    p.build->dispatchClassify.gridZ = 1;
   }
 }
 
@@ -240,10 +246,10 @@ __device__ float sample_hiz_max(const Params& p, float u, float v, float lod)
   return fmaxf(fmaxf(a, b), fmaxf(d, e));
 }
 
-__global__ void k_instances_classify(Params p)  // instances_classify.comp.glsl:102-128
+// instanceStates / blasBuildInfos are taken from the host TEMPLATE of SceneBuilding (same addresses as the live block, which
+// another CTA of the fused kernel is resetting at this moment)
+__device__ __forceinline__ void instances_classify_body(const Params& p, const tc_SceneBuilding* tmpl, uint32_t i)  // instances_classify.comp.glsl:102-128
 {
-  pdl_prologue();
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= p.numInstances)
     return;
   const tc_RenderInstance& inst     = p.instances[i];
@@ -310,8 +316,8 @@ __global__ void k_instances_classify(Params p)  // instances_classify.comp.glsl:
       isVisible = sizeOk && hizOk;
     }
   }
-  tc_BlasBuildInfo* blas = reinterpret_cast<tc_BlasBuildInfo*>(p.build->blasBuildInfos);
-  reinterpret_cast<uint32_t*>(p.build->instanceStates)[i] = (inFrustum ? TC_INSTANCE_FRUSTUM_BIT : 0) | (isVisible ? TC_INSTANCE_VISIBLE_BIT : 0);
+  tc_BlasBuildInfo* blas = reinterpret_cast<tc_BlasBuildInfo*>(tmpl->blasBuildInfos);
+  reinterpret_cast<uint32_t*>(tmpl->instanceStates)[i] = (inFrustum ? TC_INSTANCE_FRUSTUM_BIT : 0) | (isVisible ? TC_INSTANCE_VISIBLE_BIT : 0);
   blas[i].clusterReferencesCount = 0;
 }
 
@@ -319,20 +325,9 @@ __global__ void k_instances_classify(Params p)  // instances_classify.comp.glsl:
 // clusters_cull (ray-tracing build: every cluster is appended) + BUILD_SETUP_CLASSIFY
 // ============================================================================================================
 
-__global__ void k_clusters_cull(Params p)  // clusters_cull.comp.glsl:112-161, build_setup.comp.glsl:105-119
+__device__ __forceinline__ void clusters_cull_body(const Params& p, const tc_SceneBuilding* tmpl, uint32_t j)  // clusters_cull.comp.glsl:112-161
 {
-  pdl_prologue();
-  uint32_t j     = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t total = p.totalClusters;
-  uint32_t count = min(total, p.maxVisibleClusters);
-  if(j == 0)
-  {
-    p.readback->numVisibleClusters   = total;
-    p.build->visibleClusterCounter   = count;
-    p.build->dispatchClassify.gridX  = count;
-    p.build->dispatchClassify.gridY  = 1;
-    p.build->dispatchClassify.gridZ  = 1;
-  }
+  const uint32_t count = min(p.totalClusters, p.maxVisibleClusters);
   if(j >= count)
     return;
   // instance = last i with prefix[i] <= j
@@ -345,8 +340,44 @@ __global__ void k_clusters_cull(Params p)  // clusters_cull.comp.glsl:112-161, b
     else
       hi = mid;
   }
-  tc_ClusterInfo* vis = reinterpret_cast<tc_ClusterInfo*>(p.build->visibleClusters);
+  tc_ClusterInfo* vis = reinterpret_cast<tc_ClusterInfo*>(tmpl->visibleClusters);
   vis[j]              = tc_ClusterInfo{lo, j - __ldg(&p.instanceClusterPrefix[lo])};
+}
+
+// ONE launch for everything of the frame that depends on nothing but the frame's inputs (rt.cpp:412-460): CTA 0 resets the
+// frame state (SceneBuilding from the host template, Readback, internal state) and runs BUILD_SETUP_CLASSIFY; the next
+// ceil(N / 256) CTAs classify the instances; the next ceil(C / 256) CTAs write the visible-cluster list; the rest restore
+// the 0xFFFFFFFF fill of the split list (vkCmdFillBuffer, rt.cpp:419) -- only over the entries the PREVIOUS frame wrote
+// (epochCounter[2], left by its last split pass; the whole buffer is filled once at creation), not over all 2^bits * 24 bytes.
+constexpr uint32_t FRAME_BEGIN_THREADS = 256;
+__global__ void __launch_bounds__(FRAME_BEGIN_THREADS) k_frame_begin(Params p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter,
+                                                                     uint32_t instanceCtas, uint32_t cullCtas)
+{
+  pdl_prologue();
+  uint32_t cta = blockIdx.x;
+  if(cta == 0)
+  {
+    frame_setup_body(p, tmpl, viewPosOverride, epochCounter);
+    return;
+  }
+  cta -= 1;
+  if(cta < instanceCtas)
+  {
+    instances_classify_body(p, tmpl, cta * FRAME_BEGIN_THREADS + threadIdx.x);
+    return;
+  }
+  cta -= instanceCtas;
+  if(cta < cullCtas)
+  {
+    clusters_cull_body(p, tmpl, cta * FRAME_BEGIN_THREADS + threadIdx.x);
+    return;
+  }
+  cta -= cullCtas;
+  const uint32_t fillCtas = gridDim.x - 1 - instanceCtas - cullCtas;
+  const uint32_t words    = min(epochCounter[2], p.maxSplitTriangles) * uint32_t(sizeof(tc_TessTriangleInfo) / 8);  // 64-bit words to restore
+  uint2* dst = reinterpret_cast<uint2*>(tmpl->splitTriangles);
+  for(uint32_t i = cta * FRAME_BEGIN_THREADS + threadIdx.x; i < words; i += fillCtas * FRAME_BEGIN_THREADS)
+    dst[i] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
 }
 
 // ============================================================================================================
@@ -1721,7 +1752,7 @@ __device__ __forceinline__ void split_child_corners(const Params& p, uint32_t cf
 
 // BUILD_SETUP_SPLIT_PASS (build_setup.comp.glsl:168-190) or, after the last pass, BUILD_SETUP_INSTANTIATE_TESS (:236-264);
 // executed by exactly one thread after every CTA of the pass has finished
-__device__ void split_pass_epilogue(const Params& p, uint32_t baseSplit, uint32_t baseLo, uint32_t hi, uint32_t totSplit, uint32_t totPart, bool lastPass)
+__device__ void split_pass_epilogue(const Params& p, uint32_t baseSplit, uint32_t baseLo, uint32_t hi, uint32_t totSplit, uint32_t totPart, bool lastPass, uint32_t* epochCounter)
 {
   tc_SceneBuilding* b  = p.build;
   FrameState*       st = p.state;
@@ -1762,6 +1793,7 @@ __device__ void split_pass_epilogue(const Params& p, uint32_t baseSplit, uint32_
     else
       p.readback->numPartTriangles = counterPart;
     p.readback->numSplitTriangles = b->splitWriteCounter;
+    epochCounter[2] = min(b->splitWriteCounter, p.maxSplitTriangles);  // entries of the split list the next frame has to refill (k_frame_begin)
     if(transient)
       counterPart = b->partTriangleCounter;
     else
@@ -1818,7 +1850,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
   if(numTiles == 0)
   {  // nothing to split in this pass: one thread runs the setup step, nobody else touches any state
     if(blockIdx.x == 0 && threadIdx.x == 0)
-      split_pass_epilogue(p, baseSplit, baseLo, hi, 0u, 0u, lastPass != 0);
+      split_pass_epilogue(p, baseSplit, baseLo, hi, 0u, 0u, lastPass != 0, const_cast<uint32_t*>(epochCounter));
     return;
   }
   if(threadIdx.x == 0)
@@ -2101,7 +2133,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
     {
       __threadfence();
       const uint32_t totSplit = *(volatile uint32_t*)&st->splitTotal[0], totPart = *(volatile uint32_t*)&st->splitTotal[1];
-      split_pass_epilogue(p, baseSplit, baseLo, hi, totSplit, totPart, lastPass != 0);
+      split_pass_epilogue(p, baseSplit, baseLo, hi, totSplit, totPart, lastPass != 0, const_cast<uint32_t*>(epochCounter));
     }
   }
 }
@@ -2110,13 +2142,18 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
 // triangle_tess_template_instantiate + BUILD_SETUP_BUILD_BLAS
 //
 // Persistent warps; a tile is 32 consecutive parts handled by ONE warp with no CTA-level barrier:
-//   1. lane = part: load record, table entry; warp scan of (numVertices, CLAS bytes); decoupled look-back gives the
-//      tile's base offsets in canonical (part) order; overflow test; instantiate records written with 128-bit stores.
-//   2. lane = part: fold everything constant per part into a 60-word record in shared memory (build_part_record).
-//   3. lane = vertex: the tile's vertices form one contiguous run of genVertices; iteration i generates vertices
-//      [32i, 32i+32) -- perfectly balanced regardless of the parts' sizes.  The owning part of each lane is found with
-//      a start-bit mask + popc (no search).  Records are read with broadcast 128-bit shared loads.
-//   4. vertices are staged in shared memory (4 iterations = 128 vertices) and flushed as aligned 128-bit stores.
+//   1. lane = part: load record, table entry; warp scan of (numVertices, CLAS bytes); decoupled look-back (one 16-byte
+//      descriptor per tile) gives the tile's base offsets in canonical (part) order; overflow test; instantiate records
+//      written with 128-bit stores.  The NEXT tile's parts are fetched, scanned and published before this tile's heavy work.
+//   2. lane = part: fold everything constant per part into a 56-word record in shared memory (build_part_record; 60 words
+//      when parts carry their own texture handles).
+//   3. lane = SLOT of 6 consecutive vertices of ONE part (slots are allotted per part: ceil(numVertices / 6), so a slot never
+//      straddles two parts and the loop body is divergence free); iteration i evaluates slots [32i, 32i+32) of the tile.
+//      The owning part of a lane's slot is found with a start-bit mask + popc; the slot's pattern vertices come as three
+//      coalesced 128-bit loads from the slotted table; all arithmetic is packed fp32 on vertex pairs (eval_part_pairs).
+//   4. the iteration's vertices (one contiguous run of genVertices) are staged in shared memory with the 16-byte phase of
+//      their global address and leave the SM as ONE bulk copy (cp.async.bulk shared -> global) per iteration; the <= 3
+//      head / tail floats outside the 16-byte aligned body go out as scalar stores.
 // ============================================================================================================
 
 #ifndef TC_INST_WARPS
@@ -2134,7 +2171,8 @@ constexpr int INST_STAGE_WORDS = INST_ITER_VERTS * 3 + 4;
 // staging buffers per warp.  1: the bulk copy of iteration i has the whole evaluation phase of iteration i+1 to finish
 // reading before the buffer is rewritten (measured faster than 2, and 2.3 KB less shared memory per warp)
 constexpr int INST_STAGES      = TC_INST_STAGES;
-constexpr int INST_WARP_WORDS  = 32 * TC_REC_WORDS + INST_STAGES * INST_STAGE_WORDS;  // 2 stages: 3080 words = 12320 B per warp
+template <int TEX>
+constexpr int inst_warp_words() { return 32 * RecWords<TEX>::value + INST_STAGES * INST_STAGE_WORDS; }  // 56-word records, 1 stage: 2372 words = 9488 B per warp
 
 __device__ __forceinline__ uint32_t lanemask_le()
 {
@@ -2203,8 +2241,9 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
   // the warp index as a warp-UNIFORM value (REDUX writes a uniform register): shared-memory bases and the bulk-copy
   // operands are then computed on the uniform datapath instead of per lane
   const uint32_t warp = __reduce_max_sync(0xffffffffu, threadIdx.x >> 5), lane = lane_id();
-  float* recBase = instSmem + size_t(warp) * INST_WARP_WORDS;
-  float* stageBase = recBase + 32 * TC_REC_WORDS;
+  constexpr int REC_WORDS = RecWords<TEX>::value;
+  float* recBase = instSmem + size_t(warp) * inst_warp_words<TEX>();
+  float* stageBase = recBase + 32 * REC_WORDS;
   uint32_t stageSel = 0;  // a staging buffer is rewritten only after the bulk copy issued from it has read it
   const uint64_t streamPolicy = policy_evict_first();
 
@@ -2231,6 +2270,7 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
   }
   uint32_t accSucc = 0, accTris = 0;  // per-warp statistics, folded once at the end
   const cudaTextureObject_t uniformTex = TEX == 1 ? p.texturesC[0].gather : 0;  // warp-uniform handle
+  const float2 uniformInvSize = TEX == 1 ? make_float2(1.0f / float(p.texturesC[0].width), 1.0f / float(p.texturesC[0].height)) : make_float2(1.f, 1.f);
 
   // One tile ahead: while a warp generates the vertices of tile k it already holds the ticket of its next tile, has
   // loaded those parts, scanned them and published their aggregate -- successors never wait on this warp's heavy work
@@ -2326,9 +2366,9 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
         tempClusterSizes[tempOffset] = dataSize;
 
       const tc_RenderInstance& inst = p.instances[instanceID];
-      build_part_record(p, inst, instanceID, cur.firstLocalVertex, cur.lt0, cur.lt1, cur.lt2, vtxEnc,
-                        ((triCfg >> 16) & TC_CONFIG_FLIPPED_BIT) != 0,
-                        slotBase, (numVertices + INST_SLOT - 1) / INST_SLOT, partIndex, recBase + lane * TC_REC_WORDS);
+      build_part_record<TEX>(p, inst, instanceID, cur.firstLocalVertex, cur.lt0, cur.lt1, cur.lt2, vtxEnc,
+                             ((triCfg >> 16) & TC_CONFIG_FLIPPED_BIT) != 0,
+                             slotBase, (numVertices + INST_SLOT - 1) / INST_SLOT, partIndex, recBase + lane * REC_WORDS);
     }
     __syncwarp();
 
@@ -2340,6 +2380,79 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
     const uint32_t startS     = incS - slotCount;
     const uint32_t totalSlots = __shfl_sync(0xffffffffu, incS, 31);
     const size_t   tileFloat0 = size_t(tileVertexBase) * 3;
+#ifdef TC_INST_PREFETCH_Q
+    uint32_t partsBefore = 0;  // parts whose first slot lies before the current iteration
+    // Iteration header: which part a lane's slot belongs to, where its vertices go, and the slot's pattern vertices (three
+    // coalesced 128-bit loads).  TC_INST_PREFETCH_Q: the header of iteration i+1 -- including those loads -- is formed
+    // before iteration i is evaluated, so their latency overlaps a whole iteration of arithmetic.
+    struct IterHeader
+    {
+      uint32_t part, t0, cnt, itStart, itEnd;
+      bool     active;
+      float4   q[INST_SLOT / 2];
+    };
+    auto header = [&](uint32_t w0, IterHeader& h) {
+      const uint32_t rel   = startS - w0;
+      const uint32_t bits  = __reduce_or_sync(0xffffffffu, (slotCount != 0 && rel < 32u) ? (1u << rel) : 0u);
+      h.part               = (partsBefore + __popc(bits & lanemask_le()) - 1u) & 31u;
+      partsBefore += __popc(bits);
+      h.active             = w0 + lane < totalSlots;
+      const uint32_t pStartS = __shfl_sync(0xffffffffu, startS, h.part);
+      const uint32_t pStartV = __shfl_sync(0xffffffffu, startV, h.part);
+      const uint32_t pNV     = __shfl_sync(0xffffffffu, numVertices, h.part);
+      const uint32_t v0      = (w0 + lane - pStartS) * INST_SLOT;
+      h.cnt                  = min(uint32_t(INST_SLOT), pNV - v0);  // vertices of this slot (>= 1 when active)
+      h.t0                   = pStartV + v0;                        // tile-relative index of the slot's first vertex
+      // contiguous vertex range covered by this iteration
+      const uint32_t lastLane = min(31u, totalSlots - w0 - 1u);
+      h.itStart = __shfl_sync(0xffffffffu, h.t0, 0);
+      h.itEnd   = __shfl_sync(0xffffffffu, h.t0 + h.cnt, lastLane);
+      if(h.active)
+      {
+        const float4   r1   = reinterpret_cast<const float4*>(recBase + h.part * REC_WORDS)[1];
+        const uint32_t nS   = __float_as_uint(r1.w);
+        const float4*  qsrc = p.tblSlots + (__float_as_uint(r1.z) + (w0 + lane - pStartS));  // coalesced across the lanes of a part
+#pragma unroll
+        for(int i = 0; i < INST_SLOT / 2; i++)
+          h.q[i] = __ldg(qsrc + i * nS);
+      }
+    };
+    IterHeader nh;
+    if(totalSlots)
+      header(0, nh);
+    for(uint32_t w0 = 0; w0 < totalSlots; w0 += 32)
+    {
+      const IterHeader h = nh;
+      if(w0 + 32 < totalSlots)
+        header(w0 + 32, nh);
+      const uint32_t part = h.part, t0 = h.t0, cnt = h.cnt, itStart = h.itStart, itEnd = h.itEnd;
+      const bool     active = h.active;
+      const size_t   itFloat0 = tileFloat0 + size_t(itStart) * 3;
+      const uint32_t shift    = uint32_t(itFloat0 & 3);  // keep shared and global 16-byte phases equal
+      static_assert(INST_SLOT == 6, "the slot outputs below are spelled out for 6 vertices");
+      F3 o0, o1, o2, o3, o4, o5;
+      if(active)
+      {
+        const float4* rec = reinterpret_cast<const float4*>(recBase + part * REC_WORDS);
+        float2 X[INST_SLOT / 2], Y[INST_SLOT / 2], Z[INST_SLOT / 2];
+        eval_part_pairs<TEX, INST_SLOT / 2>(rec, h.q, X, Y, Z, uniformTex, uniformInvSize);
+        F3 o[INST_SLOT];
+#pragma unroll
+        for(int i = 0; i < INST_SLOT / 2; i++)
+        {
+          o[2 * i]     = {X[i].x, Y[i].x, Z[i].x};
+          o[2 * i + 1] = {X[i].y, Y[i].y, Z[i].y};
+        }
+        if(ANIM)
+        {
+          const uint32_t partIdx = __float_as_uint(rec[13].w);
+#pragma unroll
+          for(int i = 0; i < INST_SLOT; i++)
+            o[i] = ripple_deform_part(p.view, p.build, p.instances, o[i], partIdx);
+        }
+        o0 = o[0]; o1 = o[1]; o2 = o[2]; o3 = o[3]; o4 = o[4]; o5 = o[5];
+      }
+#else
     uint32_t partsBefore = 0;  // parts whose first slot lies before the current iteration
     for(uint32_t w0 = 0; w0 < totalSlots; w0 += 32)
     {
@@ -2364,7 +2477,7 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
       F3 o0, o1, o2, o3, o4, o5;
       if(active)
       {
-        const float4*  rec  = reinterpret_cast<const float4*>(recBase + part * TC_REC_WORDS);
+        const float4*  rec  = reinterpret_cast<const float4*>(recBase + part * REC_WORDS);
         const float4   r1   = rec[1];
         const uint32_t nS   = __float_as_uint(r1.w);
         const float4*  qsrc = p.tblSlots + (__float_as_uint(r1.z) + (w0 + lane - pStartS));  // coalesced across the lanes of a part
@@ -2373,7 +2486,7 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
         for(int i = 0; i < INST_SLOT / 2; i++)
           q[i] = __ldg(qsrc + i * nS);
         float2 X[INST_SLOT / 2], Y[INST_SLOT / 2], Z[INST_SLOT / 2];
-        eval_part_pairs<TEX, INST_SLOT / 2>(rec, q, X, Y, Z, uniformTex);
+        eval_part_pairs<TEX, INST_SLOT / 2>(rec, q, X, Y, Z, uniformTex, uniformInvSize);
         F3 o[INST_SLOT];
 #pragma unroll
         for(int i = 0; i < INST_SLOT / 2; i++)
@@ -2383,13 +2496,14 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
         }
         if(ANIM)
         {
-          const uint32_t partIdx = __float_as_uint(rec[14].w);
+          const uint32_t partIdx = __float_as_uint(rec[13].w);
 #pragma unroll
           for(int i = 0; i < INST_SLOT; i++)
             o[i] = ripple_deform_part(p.view, p.build, p.instances, o[i], partIdx);
         }
         o0 = o[0]; o1 = o[1]; o2 = o[2]; o3 = o[3]; o4 = o[4]; o5 = o[5];
       }
+#endif
       float* stage = stageBase + stageSel * INST_STAGE_WORDS;
       stageSel = (stageSel + 1u) % INST_STAGES;
       if(lane == 0)
@@ -3332,7 +3446,7 @@ __global__ void k_flush_l2(float4* buf, size_t n)
 // launch wrappers
 // ============================================================================================================
 
-size_t instantiate_smem_bytes() { return size_t(INST_WARPS) * INST_WARP_WORDS * 4; }
+size_t instantiate_smem_bytes(int tex) { return size_t(INST_WARPS) * (tex == 2 ? inst_warp_words<2>() : inst_warp_words<1>()) * 4; }
 
 size_t classify_smem_bytes(uint32_t clusterVertices, uint32_t clusterTriangles)
 {
@@ -3350,10 +3464,11 @@ int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, Kerne
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->split, k_triangle_split, SPLIT_THREADS, 0);
   const void* variants[6] = {(const void*)k_instantiate<0, false>, (const void*)k_instantiate<0, true>, (const void*)k_instantiate<1, false>,
                              (const void*)k_instantiate<1, true>,  (const void*)k_instantiate<2, false>, (const void*)k_instantiate<2, true>};
-  for(const void* f : variants)
-    if(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, int(instantiate_smem_bytes())) != cudaSuccess)
+  for(int v = 0; v < 6; v++)
+    if(cudaFuncSetAttribute(variants[v], cudaFuncAttributeMaxDynamicSharedMemorySize, int(instantiate_smem_bytes(v / 2))) != cudaSuccess)
       return -1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->instantiate, k_instantiate<1, false>, INST_THREADS, instantiate_smem_bytes());
+  for(int tex = 0; tex < 3; tex++)  // resident CTAs per SM of each texture mode (the record of per-part handles is larger)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->instantiate[tex], variants[tex * 2], INST_THREADS, instantiate_smem_bytes(tex));
   if(cudaFuncSetAttribute(k_batch_part_triangles, cudaFuncAttributeMaxDynamicSharedMemorySize, int(batch_smem_bytes())) != cudaSuccess)
     return -1;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -3376,21 +3491,12 @@ size_t   classify_tuple_bytes() { return sizeof(ScanTuple); }
 uint32_t lookback16_tiles_needed(uint32_t maxItems) { return (maxItems + 31) / 32 + 2; }
 size_t frame_state_bytes() { return sizeof(FrameState); }
 
-void launch_frame_setup(const Params& p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter, cudaStream_t s)
+void launch_frame_begin(const Params& p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter, uint32_t numSMs, cudaStream_t s)
 {
-  launch_pdl(k_frame_setup, 1, 128, 0, s, p, tmpl, viewPosOverride, epochCounter);
+  const uint32_t n = p.totalClusters < p.maxVisibleClusters ? p.totalClusters : p.maxVisibleClusters;
+  const uint32_t instanceCtas = (p.numInstances + FRAME_BEGIN_THREADS - 1) / FRAME_BEGIN_THREADS, cullCtas = (n + FRAME_BEGIN_THREADS - 1) / FRAME_BEGIN_THREADS;
+  launch_pdl(k_frame_begin, 1 + instanceCtas + cullCtas + numSMs * 2, FRAME_BEGIN_THREADS, 0, s, p, tmpl, viewPosOverride, epochCounter, instanceCtas, cullCtas);
 }
-void launch_instances_classify(const Params& p, cudaStream_t s)
-{
-  if(p.numInstances)
-    launch_pdl(k_instances_classify, (p.numInstances + 63) / 64, 64, 0, s, p);
-}
-void launch_clusters_cull(const Params& p, cudaStream_t s)
-{
-  uint32_t n = p.totalClusters < p.maxVisibleClusters ? p.totalClusters : p.maxVisibleClusters;
-  launch_pdl(k_clusters_cull, (n + 255) / 256 + (n == 0 ? 1 : 0), 256, 0, s, p);
-}
-size_t mini_smem_bytes() { return size_t(MINI_WARPS) * 32 * TC_REC_WORDS * 4; }
 
 void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, uint32_t miniGrid, cudaStream_t s)
 {
@@ -3429,11 +3535,12 @@ void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32
 {
   launch_pdl(k_triangle_split, grid, SPLIT_THREADS, 0, s, p, epochCounter, pass, lastPass ? 1u : 0u);
 }
-void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s)
+void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t numSMs, const KernelOccupancy& occ, cudaStream_t s)
 {
   const int  tex  = p.numTextures == 0 ? 0 : (p.numTextures == 1 ? 1 : 2);
   const bool anim = (p.flags & TC_FLAG_ANIMATION) != 0;
-  const size_t smem = instantiate_smem_bytes();
+  const size_t smem = instantiate_smem_bytes(tex);
+  const uint32_t grid = numSMs * uint32_t(occ.instantiate[tex] > 0 ? occ.instantiate[tex] : 1);  // persistent: every resident slot
   switch(tex * 2 + int(anim))
   {
     case 0: launch_pdl(k_instantiate<0, false>, grid, INST_THREADS, smem, s, p, epochCounter); break;

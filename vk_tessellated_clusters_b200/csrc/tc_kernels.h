@@ -31,7 +31,7 @@ struct HizPass
 
 struct KernelOccupancy
 {
-  int classify = 1, split = 1, instantiate = 1;
+  int classify = 1, split = 1, instantiate[3] = {1, 1, 1};  // instantiate: per texture mode (none / one / per-part handles)
 };
 
 int      configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, KernelOccupancy* occ);
@@ -42,12 +42,10 @@ size_t   classify_tuple_bytes();
 uint32_t lookback16_tiles_needed(uint32_t maxPart);
 size_t   frame_state_bytes();
 
-void launch_frame_setup(const Params& p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter, cudaStream_t s);
-void launch_instances_classify(const Params& p, cudaStream_t s);
-void launch_clusters_cull(const Params& p, cudaStream_t s);
+void launch_frame_begin(const Params& p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter, uint32_t numSMs, cudaStream_t s);
 void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, uint32_t miniGrid, cudaStream_t s);
 void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32_t pass, bool lastPass, uint32_t grid, cudaStream_t s);
-void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t grid, cudaStream_t s);
+void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t numSMs, const KernelOccupancy& occ, cudaStream_t s);
 void launch_blas(const Params& p, const uint32_t* epochCounter, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s);
 void launch_shard_resolve(const Params& p, uint32_t frame, cudaStream_t s);
 void launch_hiz_update(const HizPass& q, cudaStream_t s);

@@ -23,12 +23,17 @@ def unpack_shard_counts(words) -> dict:
 
 
 def partition_instances(cluster_counts, world_size: int):
-    """Contiguous instance ranges balanced by cluster count.  Returns list of (first, last_exclusive) per rank."""
-    cluster_counts = np.asarray(cluster_counts, dtype=np.int64)
+    """Contiguous instance ranges balanced by a per-instance weight: the cluster count, or -- better when part of the scene
+    is culled or far away -- last frame's generated clusters per instance (BlasBuildInfo.clusterReferencesCount plus a
+    constant for the per-cluster classify cost).  Returns list of (first, last_exclusive) per rank; every rank gets at
+    least one instance (the library has no empty shard), so world_size must not exceed the instance count."""
+    cluster_counts = np.asarray(cluster_counts, dtype=np.float64)
     n = cluster_counts.shape[0]
     if world_size <= 1:
         return [(0, n)]
-    total = int(cluster_counts.sum())
+    if world_size > n:
+        raise ValueError(f"cannot shard {n} instance(s) over {world_size} ranks: every rank needs at least one instance")
+    total = float(cluster_counts.sum())
     prefix = np.concatenate([[0], np.cumsum(cluster_counts)])
     bounds = [0]
     for r in range(1, world_size):
@@ -41,6 +46,19 @@ def partition_instances(cluster_counts, world_size: int):
         bounds.append(i)
     bounds.append(n)
     return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+
+
+def shard_scene(scene, first: int, last: int):
+    """The sub-scene a rank owns: instances [first, last) of `scene`; geometries and textures are replicated."""
+    import dataclasses
+
+    return dataclasses.replace(scene, instances=np.ascontiguousarray(scene.instances[first:last]))
+
+
+def frame_weights(cluster_counts, generated_clusters, classify_cost: float = 0.25):
+    """Per-instance load estimate from the previous frame: generated CLAS of the instance + a share per cluster for the
+    classify pass every cluster goes through, whether it tessellates or not."""
+    return np.asarray(generated_clusters, np.float64) + classify_cost * np.asarray(cluster_counts, np.float64)
 
 
 def exchange_shard_counts(local_counts, group=None):
