@@ -423,7 +423,7 @@ def main():
         slowest = int(np.argmax(rank_totals))
         line = {
             "metric": METRIC, "value": tris_total * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if (sharded or (world == 1 and len(full_scene.instances) >= 2)) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "parallelism": par, "l2": "flushed between timed frames (256 MiB write)",
                        "launch": ("cuda graph" if use_graph else "stream launches") + (", frames submitted by the library's host loop (tc_run_frames)" if peer else ""),
                        "triangles_per_frame": tris_total, "clusters_per_frame": clusters_total, "parts_per_frame_rank0": n_parts, "generated_vertices_rank0": n_verts,

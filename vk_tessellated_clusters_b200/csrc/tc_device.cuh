@@ -89,7 +89,7 @@ struct Params
   uint32_t epoch;  // look-back flag epoch of this launch (set per kernel by the host)
   // look-back descriptors
   void*    lookback;
-  uint4*   lookback16;  // 16-byte (flag, value) descriptors of the instantiate scan
+  uint4*   lookback16;  // 16-byte (flag, value) descriptors of the instantiate / split / emit scans
   // classify runs as count -> scan -> emit: per visible cluster an 8-word tuple and the packed per-triangle factors
   void*     classTuples;   // ScanTuple[maxVisibleClusters]: counts, then (in place) exclusive prefixes
   uint32_t* factorStash;   // [maxVisibleClusters][clusterTriangles][3]: factor | local vertex index << 24

@@ -2014,9 +2014,12 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
     __syncwarp();
 
     // ---------------- look-back over (split, part) counts ----------------
-    lookback16_publish(p.lookback16, tile, nSplitW, nPartW, epoch);
+    // (a fixed-depth tree of block / superblock totals and prefixes instead of the chained look-back -- no descriptor polled by
+    // more than 32 warps, five hops whatever the number of tiles in flight -- was measured SLOWER: pass 0 68.8 vs 57.5 us; a
+    // flat direct sum, a thousand warps polling one descriptor, 1214 us.  profiles/r02_notes.md)
     uint32_t           exclSplit;
     unsigned long long exclPart64;
+    lookback16_publish(p.lookback16, tile, nSplitW, nPartW, epoch);
     lookback16_resolve_wide<TC_SPLIT_LOOKBACK_W>(p.lookback16, tile, nSplitW, nPartW, epoch, exclSplit, exclPart64);
     const uint32_t exclPart = uint32_t(exclPart64);
     if(tile == numTiles - 1 && lane == 0)

@@ -39,7 +39,7 @@ uint32_t lookback_tiles_needed(uint32_t maxVisible, uint32_t maxSplit, uint32_t 
 size_t   lookback_desc_bytes();
 uint32_t classify_tile_clusters();
 size_t   classify_tuple_bytes();
-uint32_t lookback16_tiles_needed(uint32_t maxPart);
+uint32_t lookback16_tiles_needed(uint32_t maxItems);
 size_t   frame_state_bytes();
 
 void launch_frame_begin(const Params& p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter, uint32_t numSMs, cudaStream_t s);
