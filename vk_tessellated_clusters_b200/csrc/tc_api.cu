@@ -72,6 +72,7 @@ struct tc_context
   uint32_t*         dFactorStash = nullptr;
   uint32_t*         dClassMeta = nullptr;
   uint32_t*         dClusterVertexDst = nullptr;
+  uint32_t*         dTriWorkList = nullptr;
   FrameStaging*     dFrame     = nullptr;
   // Ring of pinned staging slots: a frame's constants are snapshotted into a slot at call time and copied to the device
   // in stream order; a slot is rewritten only after the copy that read it has completed (event per slot).  The caller
@@ -292,6 +293,7 @@ void fill_params(tc_context* c)
   p.factorStash        = c->dFactorStash;
   p.classMeta          = c->dClassMeta;
   p.clusterVertexDst   = c->dClusterVertexDst;
+  p.triWorkList        = c->dTriWorkList;
   p.segLo              = c->segLo;
   p.rankBase           = c->rankBase;
   p.shardBase          = c->dShardBase;
@@ -435,12 +437,15 @@ int enqueue_build(tc_context* c)
   return TC_OK;
 }
 
+#ifndef TC_BLAS_GRID_MULT
+#define TC_BLAS_GRID_MULT 4
+#endif
 // rt.cpp:661-686 : blas_setup_insertion + blas_clusters_insert x2
 int enqueue_insert(tc_context* c)
 {
   StageScope sc(c, TC_STAGE_INSERT);
   uint32_t passes = split_pass_count(std::max(2u, c->cfg.splitFactor));
-  tc::launch_blas(c->params, c->dEpoch, passes + 3, uint32_t(c->numSMs * 4), c->stream);
+  tc::launch_blas(c->params, c->dEpoch, passes + 3, uint32_t(c->numSMs * TC_BLAS_GRID_MULT), c->stream);
   c->lastLaunches += 3;
   CUDA_TRY(cudaGetLastError());
   return TC_OK;
@@ -547,6 +552,7 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   TRY_RC(dalloc(c->dFactorStash, size_t(c->maxVisible) * config->clusterTriangles * 12));
   TRY_RC(dalloc(c->dClassMeta, size_t(c->maxVisible) * 4));
   TRY_RC(dalloc(c->dClusterVertexDst, size_t(c->maxVisible) * 4));
+  TRY_RC(dalloc(c->dTriWorkList, size_t(c->maxVisible) * 4));
   // one 32-byte record per 2X mini triangle: a batch of 8 occupies 56 vertex slots of genVertices
   c->maxMini = (config->flags & TC_FLAG_TRANSIENT_2X) ? uint32_t(std::min<uint64_t>(uint64_t(c->maxVerts) / 7 + 64, 0xFFFFFFF0ull)) : 0u;
   if(c->maxMini)
@@ -603,7 +609,7 @@ TC_API void tc_destroy(tc_context* c)
     cudaStreamSynchronize(c->stream);
   drop_graph(c);
   free_scene(c);
-  dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dClusterVertexDst); dfree(c->dFrame);
+  dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dClusterVertexDst); dfree(c->dTriWorkList); dfree(c->dFrame);
   dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState); dfree(c->dBatchState); dfree(c->dMiniList); dfree(c->dMailbox); dfree(c->dShardStatus);
   if(c->shardStream)
     cudaStreamSynchronize(c->shardStream);

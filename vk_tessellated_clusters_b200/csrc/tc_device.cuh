@@ -43,7 +43,7 @@ struct FrameState
   uint32_t hiAfterClassify;  // transient (back) side of the dual counter, constant during split
   uint32_t instTotalV;       // grand totals of the instantiate scan (written by the warp that owns the last tile)
   uint32_t clusterLevelWork;   // visible clusters the cluster-level emit kernel has to touch (counted by the count pass)
-  uint32_t triangleLevelWork;  // ... and the triangle-level emit kernel
+  uint32_t triangleLevelWork;  // ... and the triangle-level emit kernel (= entries of Params::triWorkList)
   uint32_t splitTotal[2];      // grand totals (split, part) of the current split pass (written by the warp that owns the last tile)
   uint32_t miniCount;          // 2X mini triangles whose vertices k_mini_vertices has to generate (records in Params::miniList)
   uint32_t pad2;
@@ -94,6 +94,7 @@ struct Params
   void*     classTuples;   // ScanTuple[maxVisibleClusters]: counts, then (in place) exclusive prefixes
   uint32_t* factorStash;   // [maxVisibleClusters][clusterTriangles][3]: factor | local vertex index << 24
   uint32_t* classMeta;     // [maxVisibleClusters]: number of triangles that need no tessellation (simpleCount)
+  uint32_t* triWorkList;   // [maxVisibleClusters]: visible-list indices of the clusters with triangle-level work (count pass -> emit), any order
   uint32_t* clusterVertexDst;  // [maxVisibleClusters]: first vertex in genVertices of the cluster's displaced vertex copy, ~0u: none
   // 2X mini triangles: classify only writes one 32-byte record per mini triangle, k_mini_vertices generates the vertices
   uint4*    miniList;   // [maxMini][2]: {instanceID, firstLocalVertex, i0|i1<<8|i2<<16, v0} {v1, v2, cfg, first vertex in genVertices}

@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
   }
   __syncthreads();
   uint32_t accSuccTemp = 0, accSuccTrans = 0, accTris = 0, accFull = 0, accValidParts = 0;  // per warp, folded once at the end
-  uint32_t accClusterLevel = 0, accTriangleLevel = 0;  // count pass: clusters each emit kernel will have to touch
+  uint32_t accClusterLevel = 0;  // count pass: clusters the cluster-level emit kernel will have to touch
   // an emit kernel with nothing to do leaves before it reads a single cluster descriptor
   if(MODE == 1 && p.state->clusterLevelWork == 0)
     return;
@@ -586,23 +586,30 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
   // with nothing to do in this pass are skipped without touching their data.
   // (the chunk shrinks to a power of two >= 1 when there are fewer clusters than 32 per launched warp, so small scenes
   // still spread over the whole chip)
+  // The triangle-level emit walks the WORK LIST the count pass compacted (visible-list indices of the clusters with part / split /
+  // 2X work, in any order: every cluster's offsets come from the scanned tuples) instead of the visible list: in scenes where
+  // most clusters are hidden or untessellated the clusters with work are contiguous, and chunks of 32 of them processed one
+  // cluster at a time by a single warp set the kernel's duration while most warps found nothing to do (config 3: 334 us).
+  const uint32_t numItems = MODE == 2 ? min(p.state->triangleLevelWork, numVisible) : numVisible;
   uint32_t chunkSize = 32;
-  while(chunkSize > 1 && numVisible / chunkSize < gridDim.x * CLASSIFY_WARPS)
+  while(chunkSize > 1 && numItems / chunkSize < gridDim.x * CLASSIFY_WARPS)
     chunkSize >>= 1;
-  for(uint32_t chunk = (blockIdx.x * CLASSIFY_WARPS + warp) * chunkSize; chunk < (idle2 ? 0u : numVisible); chunk += gridDim.x * CLASSIFY_WARPS * chunkSize)
+  for(uint32_t chunk = (blockIdx.x * CLASSIFY_WARPS + warp) * chunkSize; chunk < (idle2 ? 0u : numItems); chunk += gridDim.x * CLASSIFY_WARPS * chunkSize)
   {
     tc_ClusterInfo cinfoL{0, 0};
     uint4          chL   = make_uint4(0, 0, 0, 0);
-    uint32_t       metaL = 0;
+    uint32_t       metaL = 0, viL = 0;
     bool           needL = false;
-    if(lane < chunkSize && chunk + lane < numVisible)
+    uint32_t       triMask = 0;  // count pass: clusters of this chunk with triangle-level work
+    if(lane < chunkSize && chunk + lane < numItems)
     {
-      cinfoL = visibleClusters[chunk + lane];
+      viL    = MODE == 2 ? __ldcs(&p.triWorkList[chunk + lane]) : chunk + lane;
+      cinfoL = visibleClusters[viL];
       chL    = __ldg(reinterpret_cast<const uint4*>(p.instances[cinfoL.instanceID].clusters) + cinfoL.clusterID);
       needL  = true;
       if(MODE != 0)
       {
-        metaL = __ldg(&p.classMeta[chunk + lane]);
+        metaL = __ldg(&p.classMeta[viL]);
         const uint32_t nT = chL.x >> 16;
         const bool clusterLevelL = use1X ? (metaL == nT || metaL > 1) : (metaL == nT);
         needL = (MODE == 1) ? clusterLevelL : (metaL != nT);
@@ -670,7 +677,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
   {
     const uint32_t src = __ffs(needMask) - 1;
     needMask &= needMask - 1;
-    const uint32_t vi    = chunk + src;
+    const uint32_t vi    = __shfl_sync(0xffffffffu, viL, src);
     const bool     valid = true;
     uint32_t*      stash = p.factorStash + size_t(vi) * maxT * 3;
 
@@ -833,7 +840,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
         p.clusterVertexDst[vi] = ~0u;  // set by the cluster-level emit kernel when the cluster gets a displaced vertex copy
       }
       accClusterLevel += clusterLevel ? 1u : 0u;
-      accTriangleLevel += (simpleCount != numTriangles) ? 1u : 0u;
+      triMask |= (simpleCount != numTriangles) ? (1u << src) : 0u;
       __syncwarp();
       continue;
     }
@@ -1147,14 +1154,20 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
     }
     __syncwarp();  // the per-warp shared staging is reused by the next cluster
   }
+    if(MODE == 0 && triMask)
+    {  // one counter increment per chunk; list order is irrelevant (see above)
+      uint32_t base = 0;
+      if(lane == 0)
+        base = atomicAdd(&p.state->triangleLevelWork, uint32_t(__popc(triMask)));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if(triMask & (1u << lane))
+        p.triWorkList[base + __popc(triMask & lanemask_lt())] = chunk + lane;
+    }
   }
   if(MODE == 0)
   {
-    if(lane == 0)
-    {
-      if(accClusterLevel) atomicAdd(&p.state->clusterLevelWork, accClusterLevel);
-      if(accTriangleLevel) atomicAdd(&p.state->triangleLevelWork, accTriangleLevel);
-    }
+    if(lane == 0 && accClusterLevel)
+      atomicAdd(&p.state->clusterLevelWork, accClusterLevel);
     return;
   }
   if(lane == 0)
