@@ -97,8 +97,7 @@ struct tc_context
   uint64_t          shardFrames = 0;                     // frames submitted since tc_set_shard_peers
   bool              shardFailed = false;                 // sticky: a peer's counts never arrived
   std::vector<cudaEvent_t> runEvents;                    // tc_run_frames: event pairs
-  void*             dMiniList = nullptr;
-  uint32_t          maxMini = 0;
+  uint32_t*         dTransVertexOffsets = nullptr;
   uint32_t*         dEmitState = nullptr;  // tc_emit_part_triangles: ticket, pad, total (u64)
   uint32_t          emitCalls = 0;
   uint32_t*         dBatchState = nullptr;  // tc_batch_part_triangles: ticket, pad, tc_batch_counts
@@ -116,6 +115,11 @@ struct tc_context
   uint32_t*          dClusterPrefix = nullptr;
   uint32_t *         segLo = nullptr, *rankBase = nullptr;
   tc_global_blas_range* globalRanges = nullptr;
+  // instancing-aware displaced-vertex cache (tc_kernels.cu, k_class_cache)
+  uint32_t *dInstanceVertexCache = nullptr, *dInstanceMidCache = nullptr;
+  uint4*    dCacheClasses = nullptr;
+  float*    dClassCache = nullptr;
+  uint32_t  numCacheClasses = 0, numCacheClusters = 0, allInstancesCached = 0;
   std::vector<DeviceGeometry> geoms;
   std::vector<void*>          textures;
   std::vector<cudaArray_t>    textureArrays;
@@ -202,6 +206,11 @@ void free_scene(tc_context* c)
   dfree(c->instanceStates); dfree(c->blasBuildInfos); dfree(c->blasBuildSizes); dfree(c->basicClusterSizes);
   dfree(c->dInstances); dfree(c->dClusterPrefix); dfree(c->segLo); dfree(c->rankBase); dfree(c->globalRanges);
   c->globalRanges = nullptr;
+  dfree(c->dInstanceVertexCache); dfree(c->dInstanceMidCache); dfree(c->dCacheClasses); dfree(c->dClassCache);
+  c->dInstanceVertexCache = c->dInstanceMidCache = nullptr;
+  c->dCacheClasses = nullptr;
+  c->dClassCache = nullptr;
+  c->numCacheClasses = c->numCacheClusters = c->allInstancesCached = 0;
   c->instanceStates = c->blasBuildInfos = c->blasBuildSizes = c->basicClusterSizes = nullptr;
   c->dInstances = nullptr;
   c->dClusterPrefix = nullptr;
@@ -297,8 +306,7 @@ void fill_params(tc_context* c)
   p.segLo              = c->segLo;
   p.rankBase           = c->rankBase;
   p.shardBase          = c->dShardBase;
-  p.miniList           = reinterpret_cast<uint4*>(c->dMiniList);
-  p.maxMini            = c->maxMini;
+  p.transVertexOffsets = c->dTransVertexOffsets;
   p.shardCounts        = c->dShardCounts;
   p.shardRank          = c->shardRank;
   p.shardWorld         = c->shardWorld;
@@ -307,6 +315,13 @@ void fill_params(tc_context* c)
     p.peerMailbox[r] = reinterpret_cast<tc_shard_mailbox_slot*>(c->peerMailbox[r]);
   p.shardStatus        = c->dShardStatus;
   p.globalRanges       = c->globalRanges;
+  p.instanceVertexCache = c->dInstanceVertexCache;
+  p.instanceMidCache    = c->dInstanceMidCache;
+  p.cacheClasses        = c->dCacheClasses;
+  p.numCacheClasses     = c->numCacheClasses;
+  p.numCacheClusters    = c->numCacheClusters;
+  p.allInstancesCached  = c->allInstancesCached;
+  p.classCache          = c->dClassCache;
 }
 
 struct StageScope
@@ -409,7 +424,8 @@ int enqueue_build(tc_context* c)
     uint32_t grid = std::max(1u, (std::min(c->totalClusters, c->maxVisible) + tc::classify_tile_clusters() - 1) / tc::classify_tile_clusters());
     grid          = std::min(grid, uint32_t(c->numSMs) * 32u);
     tc::launch_cluster_classify(p, c->dEpoch, grid, uint32_t(c->numSMs * 5), s);  // count -> scan -> emit (cluster level) -> emit (triangle level) -> 2X mini vertices
-    launches += (c->cfg.flags & TC_FLAG_TRANSIENT_2X) ? 6 : 5;
+    const bool anim = (c->cfg.flags & TC_FLAG_ANIMATION) != 0;
+    launches += 5 + (((c->cfg.flags & TC_FLAG_TRANSIENT_2X) && !(c->allInstancesCached && !anim)) ? 1 : 0) + ((c->numCacheClasses && !anim) ? 2 : 0);
   }
   {
     StageScope sc(c, TC_STAGE_SPLIT);
@@ -553,10 +569,8 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   TRY_RC(dalloc(c->dClassMeta, size_t(c->maxVisible) * 4));
   TRY_RC(dalloc(c->dClusterVertexDst, size_t(c->maxVisible) * 4));
   TRY_RC(dalloc(c->dTriWorkList, size_t(c->maxVisible) * 4));
-  // one 32-byte record per 2X mini triangle: a batch of 8 occupies 56 vertex slots of genVertices
-  c->maxMini = (config->flags & TC_FLAG_TRANSIENT_2X) ? uint32_t(std::min<uint64_t>(uint64_t(c->maxVerts) / 7 + 64, 0xFFFFFFF0ull)) : 0u;
-  if(c->maxMini)
-    TRY_RC(dalloc(c->dMiniList, size_t(c->maxMini) * 32));
+  if(config->flags & TC_FLAG_TRANSIENT_2X)
+    TRY_RC(dalloc(c->dTransVertexOffsets, size_t(c->maxVisible + c->maxPart) * 4));
   TRY_CUDA(cudaMemsetAsync(c->dEpoch, 0, 16, c->stream));
   TRY_CUDA(cudaMemsetAsync(c->dShardBase, 0, 16, c->stream));
   TRY_CUDA(cudaMemsetAsync(c->dReadback, 0, sizeof(tc_Readback), c->stream));
@@ -610,7 +624,7 @@ TC_API void tc_destroy(tc_context* c)
   drop_graph(c);
   free_scene(c);
   dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dClusterVertexDst); dfree(c->dTriWorkList); dfree(c->dFrame);
-  dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState); dfree(c->dBatchState); dfree(c->dMiniList); dfree(c->dMailbox); dfree(c->dShardStatus);
+  dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState); dfree(c->dBatchState); dfree(c->dTransVertexOffsets); dfree(c->dMailbox); dfree(c->dShardStatus);
   if(c->shardStream)
     cudaStreamSynchronize(c->shardStream);
   if(c->hFrameRing)
@@ -819,6 +833,70 @@ TC_API int tc_set_scene(tc_context* c, const tc_geometry* geoms, uint32_t numGeo
   CUDA_TRY(cudaMemsetAsync(c->blasBuildSizes, 0, size_t(numInstances) * 4, c->stream));
   if(basicClusterSizes && numBasicClusterSizes)
     CUDA_TRY(cudaMemcpy(c->basicClusterSizes, basicClusterSizes, size_t(numBasicClusterSizes) * 4, cudaMemcpyHostToDevice));
+
+  {
+    // Displacement classes: instances with the same geometry and displacement parameters generate identical object-space
+    // cluster-vertex copies and 2X mini-triangle vertices; classes of >= 2 instances get a per-frame cache (k_class_cache).
+    std::vector<uint32_t> vcache(numInstances, ~0u), mcache(numInstances, ~0u), classOf(numInstances, ~0u);
+    std::vector<uint4>    classes;
+    std::vector<uint32_t> members;
+    uint64_t cacheFloat3 = 0;
+    uint32_t clusterItems = 0;
+    const bool use2X = (c->cfg.flags & TC_FLAG_TRANSIENT_2X) != 0, anim = (c->cfg.flags & TC_FLAG_ANIMATION) != 0;
+    auto sameClass = [&](const tc_RenderInstance& a, const tc_RenderInstance& b) {
+      return a.geometryID == b.geometryID && a.displacementIndex == b.displacementIndex && memcmp(&a.displacementScale, &b.displacementScale, 4) == 0
+             && memcmp(&a.displacementOffset, &b.displacementOffset, 4) == 0;
+    };
+    if(!anim)
+    {
+      std::vector<uint32_t> reps;  // representative instance of every class seen so far (scenes have few distinct classes)
+      for(uint32_t i = 0; i < numInstances; i++)
+      {
+        uint32_t k = 0;
+        while(k < reps.size() && !sameClass(inst[reps[k]], inst[i]))
+          k++;
+        if(k == reps.size())
+        {
+          reps.push_back(i);
+          members.push_back(0);
+        }
+        classOf[i] = k;
+        members[k]++;
+      }
+      std::vector<uint32_t> slot(reps.size(), ~0u);
+      for(uint32_t k = 0; k < reps.size(); k++)
+      {
+        const tc_geometry& g = geoms[inst[reps[k]].geometryID];
+        const uint64_t need = uint64_t(g.numVertices) + (use2X ? uint64_t(g.numTriangles) * 3 : 0);
+        if(members[k] < 2 || cacheFloat3 + need > 0xFFFF0000ull)
+          continue;
+        slot[k] = uint32_t(classes.size());
+        const uint32_t vbase = uint32_t(cacheFloat3), mbase = use2X ? uint32_t(cacheFloat3 + g.numVertices) : ~0u;
+        classes.push_back(make_uint4(reps[k], clusterItems, vbase, mbase));
+        cacheFloat3 += need;
+        clusterItems += g.numClusters;
+      }
+      for(uint32_t i = 0; i < numInstances; i++)
+        if(slot[classOf[i]] != ~0u)
+        {
+          vcache[i] = classes[slot[classOf[i]]].z;
+          mcache[i] = classes[slot[classOf[i]]].w;
+        }
+    }
+    c->allInstancesCached = 1;
+    for(uint32_t i = 0; i < numInstances; i++)
+      if(vcache[i] == ~0u || mcache[i] == ~0u)
+        c->allInstancesCached = 0;
+    c->numCacheClasses  = uint32_t(classes.size());
+    c->numCacheClusters = clusterItems;
+    if((rc = dalloc(c->dInstanceVertexCache, size_t(numInstances) * 4)) || (rc = dalloc(c->dInstanceMidCache, size_t(numInstances) * 4))
+       || (rc = dalloc(c->dCacheClasses, std::max<size_t>(classes.size(), 1) * sizeof(uint4))) || (rc = dalloc(c->dClassCache, std::max<uint64_t>(cacheFloat3, 1) * 12)))
+      return rc;
+    CUDA_TRY(cudaMemcpy(c->dInstanceVertexCache, vcache.data(), size_t(numInstances) * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->dInstanceMidCache, mcache.data(), size_t(numInstances) * 4, cudaMemcpyHostToDevice));
+    if(!classes.empty())
+      CUDA_TRY(cudaMemcpy(c->dCacheClasses, classes.data(), classes.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+  }
 
   c->params.numTextures = numTextures;
   for(uint32_t t = 0; t < numTextures; t++)

@@ -45,7 +45,7 @@ struct FrameState
   uint32_t clusterLevelWork;   // visible clusters the cluster-level emit kernel has to touch (counted by the count pass)
   uint32_t triangleLevelWork;  // ... and the triangle-level emit kernel (= entries of Params::triWorkList)
   uint32_t splitTotal[2];      // grand totals (split, part) of the current split pass (written by the warp that owns the last tile)
-  uint32_t miniCount;          // 2X mini triangles whose vertices k_mini_vertices has to generate (records in Params::miniList)
+  uint32_t miniCount;          // != 0: the frame has 2X mini batches (k_mini_vertices / k_class_cache have work)
   uint32_t pad2;
   unsigned long long instTotalD;
   uint32_t classTotal[8];    // grand totals of the classify scan: v[0..5], data lo, data hi
@@ -96,14 +96,23 @@ struct Params
   uint32_t* classMeta;     // [maxVisibleClusters]: number of triangles that need no tessellation (simpleCount)
   uint32_t* triWorkList;   // [maxVisibleClusters]: visible-list indices of the clusters with triangle-level work (count pass -> emit), any order
   uint32_t* clusterVertexDst;  // [maxVisibleClusters]: first vertex in genVertices of the cluster's displaced vertex copy, ~0u: none
-  // 2X mini triangles: classify only writes one 32-byte record per mini triangle, k_mini_vertices generates the vertices
-  uint4*    miniList;   // [maxMini][2]: {instanceID, firstLocalVertex, i0|i1<<8|i2<<16, v0} {v1, v2, cfg, first vertex in genVertices}
-  uint32_t  maxMini;
+  // 2X mini batches: k_mini_vertices generates the vertices from the transient build records themselves; only the batch's
+  // UN-WRAPPED first vertex travels on the side (ClasBuildInfo.vertexBuffer wraps at 2^32 bytes like the reference's)
+  uint32_t* transVertexOffsets;  // [maxGenClusters], indexed like transBuilds (2X batches only)
   // blas helpers
   uint32_t* segLo;     // [TC_MAX_SEGMENTS+1][numInstances]
   uint32_t* rankBase;  // [TC_MAX_SEGMENTS+1][numInstances]
   const uint32_t* shardBase;  // {globalBlasClusterBase, globalInstanceBase}
   tc_global_blas_range* globalRanges;  // [numInstances]
+  // Instancing-aware displaced-vertex cache (k_class_cache): instances that share geometry AND displacement parameters share
+  // the object-space result of every displaced cluster vertex and of every displaced base-edge midpoint (what the full-cluster /
+  // 1X copies and the 2X mini triangles are made of), so it is evaluated once per frame per such CLASS and copied per instance.
+  const uint32_t* instanceVertexCache;  // [numInstances] first float3 of the instance's class in classCache (geometry vertex order), ~0u: not cached
+  const uint32_t* instanceMidCache;     // [numInstances] first float3 of the class's edge midpoints (3 per geometry triangle), ~0u: none
+  const uint4*    cacheClasses;         // [numCacheClasses] {representative instance, first cluster item (prefix), vertex base, midpoint base}
+  uint32_t        numCacheClasses, numCacheClusters;  // classes, sum of their geometries' clusters
+  uint32_t        allInstancesCached;   // every instance has both caches: k_mini_vertices has nothing to do
+  float*          classCache;
   tc_shard_counts*      shardCounts;   // summary record for the multi-GPU allgather, written by the last CTA of k_instantiate
   // peer-mailbox exchange (tess_clusters.h): world <= 1 = off
   uint32_t               shardRank, shardWorld;

@@ -496,6 +496,89 @@ __device__ __forceinline__ void flush_floats(const float* stage, float* dst, uin
     dst[tailStart + lane] = stage[shift + tailStart + lane];
 }
 
+// ---- 2X mini triangles: pieces shared by k_cluster_classify<2> (cached instances: inline copies) and k_mini_vertices ----
+// [factors-1 (3 bits)][flipped][rotation]: for candidate c (0..2 corner of base vertex c, 3..5 midpoint of base edge (0,1) (1,2)
+// (2,0)) the index of the pattern vertex that lands there (nibble c, 0xF = none), vertex count in bits 24..27.  48 entries,
+// filled by the first 48 threads of the CTA (the caller synchronises).
+__device__ __forceinline__ void mini_where_table_init(const Params& p, uint32_t* whereTbl)
+{
+  if(threadIdx.x < 48)
+  {
+    const uint32_t rot = threadIdx.x % 3u, flipped = (threadIdx.x / 3u) & 1u, c3 = threadIdx.x / 6u;
+    const uint32_t cfgIdx = (c3 & 1u) + 16u * ((c3 >> 1) & 1u) + 256u * (c3 >> 2);  // = x + 16 y + 256 z - 273 with factors in {1,2}
+    const tc_TessTableEntry e = p.tblEntries[cfgIdx];
+    const uint32_t perm[3] = {rot, (rot + 1u) % 3u, (rot + 2u) % 3u};  // base vertex behind each corner of the rotated triangle
+    uint32_t where = 0xFFFFFFu;
+    for(uint32_t i = 0; i < TC_TESS_2X_MINI_VERTICES && i < e.numVertices; i++)
+    {
+      const uint32_t pv = p.tblVertices[e.firstVertex + i];
+      uint32_t h1 = (pv & 0xFFFFu) >> 14, h2 = pv >> 30, h0 = 2u - h1 - h2;  // pattern barycentrics in halves
+      if(flipped)
+      {
+        const uint32_t t = h0;
+        h0 = h1;
+        h1 = t;
+      }
+      const uint32_t hb = (h0 << (2 * perm[0])) + (h1 << (2 * perm[1])) + (h2 << (2 * perm[2]));  // halves per BASE vertex
+      const uint32_t c  = hb == 0x02u ? 0u : hb == 0x08u ? 1u : hb == 0x20u ? 2u : hb == 0x05u ? 3u : hb == 0x14u ? 4u : 5u;
+      where = (where & ~(0xFu << (4 * c))) | (i << (4 * c));
+    }
+    whereTbl[threadIdx.x] = where | (min(uint32_t(e.numVertices), TC_TESS_2X_MINI_VERTICES) << 24);
+  }
+}
+__device__ __forceinline__ uint32_t mini_where(const uint32_t* whereTbl, uint32_t cfg, uint32_t rotatedV0)
+{
+  const uint32_t rot = (rotatedV0 & 0xFFFFu) ? 1u : ((rotatedV0 >> 16) ? 2u : 0u);  // base vertex behind corner 0 of the rotated triangle
+  const uint32_t c3  = (cfg & 1u) | ((cfg >> 3) & 2u) | ((cfg >> 6) & 4u);
+  return whereTbl[(c3 * 2u + ((cfg >> 15) & 1u)) * 3u + rot];
+}
+// the <= 6 vertices of a mini triangle of an instance with a cached displacement class: corners and edge midpoints are copies
+__device__ __forceinline__ void mini_copy_cached(const Params& p, uint32_t where, uint32_t vcache, uint32_t mcache, uint32_t firstLocalVertex, uint32_t i0, uint32_t i1,
+                                                 uint32_t i2, uint32_t geometryTriangle, float* myStage)
+{
+  const uint32_t iv[3] = {i0, i1, i2};
+#pragma unroll
+  for(int k = 0; k < 3; k++)
+  {
+    const uint32_t ic = (where >> (4 * k)) & 0xFu, im = (where >> (12 + 4 * k)) & 0xFu;
+    if(ic != 0xFu)
+    {
+      const float* c = p.classCache + size_t(vcache + firstLocalVertex + iv[k]) * 3;
+      float* sv = myStage + ic * 3;
+      sv[0] = __ldg(c); sv[1] = __ldg(c + 1); sv[2] = __ldg(c + 2);
+    }
+    if(im != 0xFu)
+    {
+      const float* c = p.classCache + size_t(mcache + geometryTriangle * 3u + k) * 3;
+      float* sv = myStage + im * 3;
+      sv[0] = __ldg(c); sv[1] = __ldg(c + 1); sv[2] = __ldg(c + 2);
+    }
+  }
+}
+// Warp write of up to 32 staged mini triangles (stage[32][18], hdr[m] = {first float in genVertices, floats to write}): lane t
+// handles float (t % 18) of mini triangle (t / 18), so consecutive lanes write consecutive addresses inside a mini triangle's slot
+// and across the slots of a batch (which are adjacent); slots of absent vertices stay untouched, exactly like the reference
+// leaves them.  The caller has synchronised the warp.
+__device__ __forceinline__ void mini_write_staged(float* genVertices, const float* stage, const uint2* hdr, uint32_t lane)
+{
+  constexpr uint32_t kMiniFloats = TC_TESS_2X_MINI_VERTICES * 3;
+  uint32_t m = lane >= kMiniFloats ? 1u : 0u, j = lane - m * kMiniFloats;
+#pragma unroll 6
+  for(uint32_t it = 0; it < kMiniFloats; it++)
+  {
+    const uint2 h = hdr[m];
+    if(j < h.y)
+      __stcs(genVertices + size_t(h.x) + j, stage[it * 32 + lane]);
+    j += 32 - kMiniFloats;  // 32 = 18 + 14
+    m += 1;
+    if(j >= kMiniFloats)
+    {
+      j -= kMiniFloats;
+      m += 1;
+    }
+  }
+}
+
 #ifndef TC_CLASSIFY_WARPS
 #define TC_CLASSIFY_WARPS 8
 #endif
@@ -505,6 +588,7 @@ __device__ __forceinline__ void flush_floats(const float* stage, float* dst, uin
 #define TC_CLASSIFY_MIN_CTAS 4
 #endif
 constexpr int CLASSIFY_WARPS   = TC_CLASSIFY_WARPS;
+constexpr uint32_t CLASSIFY_MINI_STAGE_WORDS = 32 * TC_TESS_2X_MINI_VERTICES * 3 + 64;  // even: the headers behind the floats stay 8-byte aligned
 constexpr int CLASSIFY_THREADS = CLASSIFY_WARPS * 32;
 
 // tuple lanes
@@ -522,6 +606,8 @@ struct ClassifyShared  // only the CTA epilogue's statistics: one cluster per wa
 //   MODE 1 (emit, cluster level): full-cluster template instantiations and 1X transient builds: records, displaced copies
 //                   of the cluster vertices, ordered index/mapping bytes.  Clusters without such work are skipped at once.
 //   MODE 2 (emit, triangle level): part / split records and 2X mini batches.  Clusters that are entirely simple are skipped.
+//   MODE 3 = MODE 2 for scenes with cached displacement classes (k_class_cache): the vertices of the 2X mini triangles of such
+//                   instances are copied from the cache right where the batch is formed (own variant: the copy path costs registers).
 // Splitting the emit step keeps both kernels light (registers -> occupancy): scenes dominated by untessellated clusters
 // (hidden instances, far field) are pure streaming work in MODE 1, tessellated scenes are pure record writing in MODE 2.
 #ifndef TC_CLASSIFY0_MIN_CTAS
@@ -536,11 +622,15 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
 
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t maxV = p.clusterVertices, maxT = p.clusterTriangles;
-  // per-warp regions: object positions [maxV*3], world positions + eye scale [maxV*4], factors [maxT*3]
-  const uint32_t warpWords = maxV * 3 + maxV * 4 + maxT * 3;
+  // per-warp regions: object positions [maxV*3], world positions + eye scale [maxV*4], factors [maxT*3], 2X mini staging
+  // [32 mini triangles x 18 floats + 32 headers]
+  const uint32_t warpWords = maxV * 3 + maxV * 4 + maxT * 3 + CLASSIFY_MINI_STAGE_WORDS;
   float*    sObj     = reinterpret_cast<float*>(smemRaw) + size_t(warp) * warpWords;
   float*    sWorld   = sObj + maxV * 3;
   uint32_t* sFactors = reinterpret_cast<uint32_t*>(sWorld + maxV * 4);
+  float*    sMiniStage = reinterpret_cast<float*>(sFactors + maxT * 3);
+  uint2*    sMiniHdr   = reinterpret_cast<uint2*>(sMiniStage + 32 * TC_TESS_2X_MINI_VERTICES * 3);
+  __shared__ uint32_t whereTbl[48];
 
   const uint32_t numVisible = p.build->visibleClusterCounter;
   ScanTuple*     tuples     = reinterpret_cast<ScanTuple*>(p.classTuples);
@@ -571,13 +661,16 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
   {
     sh.succTemp = sh.succTrans = sh.totalTris = sh.fullClusters = sh.validParts = 0;
   }
+  if(MODE == 3 && use2X)
+    mini_where_table_init(p, whereTbl);
   __syncthreads();
   uint32_t accSuccTemp = 0, accSuccTrans = 0, accTris = 0, accFull = 0, accValidParts = 0;  // per warp, folded once at the end
   uint32_t accClusterLevel = 0;  // count pass: clusters the cluster-level emit kernel will have to touch
+  uint32_t accMini = 0;          // triangle-level emit: this warp wrote 2X batches
   // an emit kernel with nothing to do leaves before it reads a single cluster descriptor
   if(MODE == 1 && p.state->clusterLevelWork == 0)
     return;
-  const bool idle2 = MODE == 2 && p.state->triangleLevelWork == 0;
+  const bool idle2 = MODE >= 2 && p.state->triangleLevelWork == 0;
   if(idle2 && blockIdx.x != 0)
     return;  // (CTA 0 stays, skips the cluster loop and runs the setup step that follows the last emit kernel)
 
@@ -590,7 +683,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
   // 2X work, in any order: every cluster's offsets come from the scanned tuples) instead of the visible list: in scenes where
   // most clusters are hidden or untessellated the clusters with work are contiguous, and chunks of 32 of them processed one
   // cluster at a time by a single warp set the kernel's duration while most warps found nothing to do (config 3: 334 us).
-  const uint32_t numItems = MODE == 2 ? min(p.state->triangleLevelWork, numVisible) : numVisible;
+  const uint32_t numItems = MODE >= 2 ? min(p.state->triangleLevelWork, numVisible) : numVisible;
   uint32_t chunkSize = 32;
   while(chunkSize > 1 && numItems / chunkSize < gridDim.x * CLASSIFY_WARPS)
     chunkSize >>= 1;
@@ -603,7 +696,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
     uint32_t       triMask = 0;  // count pass: clusters of this chunk with triangle-level work
     if(lane < chunkSize && chunk + lane < numItems)
     {
-      viL    = MODE == 2 ? __ldcs(&p.triWorkList[chunk + lane]) : chunk + lane;
+      viL    = MODE >= 2 ? __ldcs(&p.triWorkList[chunk + lane]) : chunk + lane;
       cinfoL = visibleClusters[viL];
       chL    = __ldg(reinterpret_cast<const uint4*>(p.instances[cinfoL.instanceID].clusters) + cinfoL.clusterID);
       needL  = true;
@@ -770,7 +863,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
       else
       {
         simpleCount = metaSimple;  // hidden instances were counted as all-simple by the count pass
-        const bool needFactors = (MODE == 2) ? (simpleCount != numTriangles) : (use1X && simpleCount > 1 && simpleCount != numTriangles);
+        const bool needFactors = (MODE >= 2) ? (simpleCount != numTriangles) : (use1X && simpleCount > 1 && simpleCount != numTriangles);
         if(needFactors)
           for(uint32_t i = lane; i < numTriangles * 3; i += 32)
             sFactors[i] = __ldcs(stash + i);
@@ -844,7 +937,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
       __syncwarp();
       continue;
     }
-    if((MODE == 1 && !clusterLevel) || (MODE == 2 && simpleCount == numTriangles))
+    if((MODE == 1 && !clusterLevel) || (MODE >= 2 && simpleCount == numTriangles))
     {
       __syncwarp();
       continue;
@@ -963,8 +1056,13 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
           run.v[T_TRANS] += 1;
       }
 
-      if(MODE == 2 && simpleCount != numTriangles)
+      if(MODE >= 2 && simpleCount != numTriangles)
       {  // :543-905
+        // instance of a cached displacement class (k_class_cache): the vertices of its 2X mini triangles are copies, made right here
+        const uint32_t vcacheI = (MODE == 3 && use2X && !flag_animation(p)) ? __ldg(&p.instanceVertexCache[instanceID]) : ~0u;
+        const uint32_t mcacheI = vcacheI != ~0u ? __ldg(&p.instanceMidCache[instanceID]) : ~0u;
+        const bool     inlineMini = vcacheI != ~0u && mcacheI != ~0u;
+        float*         genVerticesF = reinterpret_cast<float*>(genVerticesAddr);
         for(uint32_t base = 0; base < numTriangles; base += 32)
         {
           uint32_t tri = base + lane;
@@ -1061,23 +1159,20 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
                        || (transDataOffset + basic32 > p.maxGenDataBytes) || (transPartOffset + miniPartSize > p.maxPartTriangles);
           uint32_t transOffset = run.v[T_TRANS] + batchIdx;
 
-          {  // vertices are generated by k_mini_vertices from one 32-byte record per mini triangle (any order: the record
-             // carries its destination); one counter increment per 32-triangle iteration
-            const bool     emitV    = mini && !failB;
-            const uint32_t voteEmit = __ballot_sync(0xffffffffu, emitV);
-            if(voteEmit)
+          // the vertices of the batch are generated by k_mini_vertices FROM THE BUILD RECORD written below (no side list)
+          accMini = 1;
+          if(MODE == 3 && inlineMini)
+          {  // (warp-uniform) corners and edge midpoints from the class cache -> staging -> coalesced stores
+            sMiniHdr[lane] = make_uint2(0u, 0u);
+            if(mini && !failB)
             {
-              uint32_t baseIdx = 0;
-              if(lane == uint32_t(__ffs(voteEmit) - 1))
-                baseIdx = atomicAdd(&p.state->miniCount, uint32_t(__popc(voteEmit)));
-              baseIdx = __shfl_sync(0xffffffffu, baseIdx, __ffs(voteEmit) - 1);
-              const uint32_t idx = baseIdx + __popc(voteEmit & lanemask_lt());
-              if(emitV && idx < p.maxMini)
-              {
-                p.miniList[size_t(idx) * 2 + 0] = make_uint4(instanceID, firstLocalVertex, i0 | (i1 << 8) | (i2 << 16), v0);
-                p.miniList[size_t(idx) * 2 + 1] = make_uint4(v1, v2, cfg, transVertexOffset + relMini * miniVertices);
-              }
+              const uint32_t where = mini_where(whereTbl, cfg, v0);
+              mini_copy_cached(p, where, vcacheI, mcacheI, firstLocalVertex, i0, i1, i2, firstLocalTriangle / 3u + tri, sMiniStage + lane * (TC_TESS_2X_MINI_VERTICES * 3));
+              sMiniHdr[lane] = make_uint2((transVertexOffset + relMini * miniVertices) * 3u, (where >> 24) * 3u);
             }
+            __syncwarp();
+            mini_write_staged(genVerticesF, sMiniStage, sMiniHdr, lane);
+            __syncwarp();
           }
           if(mini && !failB)
           {
@@ -1104,6 +1199,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
               if(p.driverStandin)
                 transClusterSizes[transOffset] = basic32;
               partTriangles[transPartOffset].cluster = cinfo;
+              p.transVertexOffsets[transOffset]  = transVertexOffset;  // un-wrapped (the record's address wraps at 2^32 bytes)
             }
             uint32_t baseTris      = numTrisInclusive - numTris - firstTris;
             uint32_t packedFactors = (f0 - 1) | ((f1 - 1) << 1) | ((f2 - 1) << 2);  // un-rotated factors
@@ -1172,6 +1268,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
   }
   if(lane == 0)
   {
+    if(accMini) p.state->miniCount = 1;  // 2X batches exist this frame (k_class_cache: edge midpoints are needed); same value from every warp
     if(accSuccTemp) atomicAdd(&sh.succTemp, accSuccTemp);
     if(accSuccTrans) atomicAdd(&sh.succTrans, accSuccTrans);
     if(accTris) atomicAdd(&sh.totalTris, accTris);
@@ -1188,7 +1285,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
     if(sh.totalTris) atomicAdd(&p.readback->numTotalTriangles, sh.totalTris);
     if(sh.fullClusters) atomicAdd(&p.readback->numFullClusters, sh.fullClusters);
     if(sh.validParts) atomicMax(&p.state->validParts, sh.validParts);
-    if(MODE != 2)
+    if(MODE < 2)
       return;  // the setup step runs once, after the last emit kernel (stream order makes MODE 1's counters visible)
     __threadfence();
     uint32_t done = atomicAdd(&p.state->done[SLOT_CLASSIFY], 1u);
@@ -1278,6 +1375,169 @@ __device__ __forceinline__ uint32_t find_item(uint32_t endOffset, uint32_t t)
 // streaming work at high occupancy instead of a serial per-vertex gather chain inside the 80-register emit kernel.
 // ============================================================================================================
 
+// pos + normalize(dir) * (texel(uv) * scale + offset): sample_displacement_gather's arithmetic with the texture state per TEX mode
+template <int TEX>
+__device__ __forceinline__ F3 displace_along(const Params& p, cudaTextureObject_t uniformTex, float uniW, float uniH, int ti, F3 pos, F3 dir, float2 uv, float scale,
+                                             float offset)
+{
+  const float W = TEX == 1 ? uniW : float(p.textures[ti].width), H = TEX == 1 ? uniH : float(p.textures[ti].height);
+  const float x = fmaf(uv.x, W, -0.5f), y = fmaf(uv.y, H, -0.5f);
+  const float fx = floorf(x), fy = floorf(y);
+  const float ax = x - fx, ay = y - fy;
+  const float gx = __fdividef(fx + 1.0f, W), gy = __fdividef(fy + 1.0f, H);
+  const float4 g = TEX == 1 ? tex2Dgather<float4>(uniformTex, gx, gy, 0) : tex2Dgather<float4>(p.textures[ti].gather, gx, gy, 0);  // (t01, t11, t10, t00)
+  const float top = fmaf(g.z - g.w, ax, g.w), bot = fmaf(g.y - g.x, ax, g.x);
+  const float h   = fmaf(fmaf(bot - top, ay, top), scale, offset);
+  return fma3(dir, h * fast_rsqrt(dot3(dir, dir)), pos);
+}
+
+// ============================================================================================================
+// Instancing-aware displaced-vertex cache.  Generated vertices are OBJECT space (the BLAS instance carries the matrix,
+// instantiate.comp.glsl:343-371), so instances that share a geometry and its displacement parameters produce bit-identical
+// cluster-vertex copies (cluster_classify.comp.glsl:465-488) and bit-identical 2X mini-triangle vertices (:817-875: base corners and
+// base-edge midpoints).  The reference evaluates them per instance; scenes are made of instances (its default scene is one mesh x 121,
+// BASELINE config 3 one mesh x 1024), so here a CLASS of >= 2 such instances evaluates every cluster vertex -- and, with 2X builds on,
+// every base-edge midpoint -- of its geometry ONCE per frame into a cache, and k_cluster_vertices / k_mini_vertices copy from it (the
+// copies stream at memory speed; the evaluation was ~120 instructions per vertex).  One warp per cluster of a class's geometry.
+// Not used with animation (the ripple is seeded per instance) or for classes of one instance.
+// ============================================================================================================
+
+template <int TEX>
+__global__ void __launch_bounds__(256) k_class_cache(Params p)
+{
+  pdl_prologue();
+  // (runs right after the count pass: whether 2X batches will exist is not known yet, triangle-level work is the proxy)
+  const bool needMid = p.state->triangleLevelWork != 0, needVertices = p.state->clusterLevelWork != 0 || needMid;
+  if(!needVertices)
+    return;
+  const uint32_t lane = lane_id(), warpsTotal = gridDim.x * (blockDim.x >> 5);
+  const cudaTextureObject_t uniformTex = TEX == 1 ? p.texturesC[0].gather : 0;
+  const float uniW = TEX == 1 ? float(p.texturesC[0].width) : 1.0f, uniH = TEX == 1 ? float(p.texturesC[0].height) : 1.0f;
+  const float viewScale = p.view[0].displacementScale, viewOffset = p.view[0].displacementOffset;
+  const bool  pn = flag_pn(p);
+  for(uint32_t item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < p.numCacheClusters; item += warpsTotal)
+  {
+    // class of this cluster item: last class whose first item <= item (few classes: linear walk from the end)
+    uint32_t c = p.numCacheClasses - 1;
+    while(c > 0 && __ldg(&p.cacheClasses[c]).y > item)
+      c--;
+    const uint4 cls = __ldg(&p.cacheClasses[c]);
+    const tc_RenderInstance& inst = p.instances[cls.x];
+    const uint4 ch = __ldg(reinterpret_cast<const uint4*>(inst.clusters) + (item - cls.y));
+    const uint32_t nV = ch.x & 0xFFFF, nT = ch.x >> 16, first = ch.z;
+    const float*  positions = reinterpret_cast<const float*>(inst.positions);
+    const float*  normals   = reinterpret_cast<const float*>(inst.normals);
+    const float2* texcoords = reinterpret_cast<const float2*>(inst.texcoords);
+    const int   ti = TEX != 0 ? inst.displacementIndex : -1;
+    const bool  displaced = TEX != 0 && ti >= 0;
+    const float scale = inst.displacementScale * viewScale, offset = inst.displacementOffset + viewOffset;
+    for(uint32_t v = lane; v < nV; v += 32)
+    {  // displaced copy of a cluster vertex: exactly k_cluster_vertices' arithmetic
+      F3 o = ld_f3(positions, first + v);
+      if(displaced)
+        o = displace_along<TEX>(p, uniformTex, uniW, uniH, ti, o, ld_f3(normals, first + v), __ldg(texcoords + first + v), scale, offset);
+      float* d = p.classCache + size_t(cls.z + first + v) * 3;
+      d[0] = o.x; d[1] = o.y; d[2] = o.z;
+    }
+    if(needMid && cls.w != ~0u)
+    {
+      const uint8_t* lt = reinterpret_cast<const uint8_t*>(inst.clusterLocalTriangles) + ch.w;
+      for(uint32_t e = lane; e < nT * 3; e += 32)
+      {  // displaced midpoint of base edge k -> q of triangle `tri`: exactly k_mini_vertices' arithmetic
+        const uint32_t tri = e / 3u, k = e - tri * 3u, q = k == 2u ? 0u : k + 1u;
+        const uint32_t gk = first + __ldg(lt + tri * 3 + k), gq = first + __ldg(lt + tri * 3 + q);
+        const F3 Pk = ld_f3(positions, gk), Pq = ld_f3(positions, gq);
+        F3 Nk = f3(0.f, 0.f, 0.f), Nq = f3(0.f, 0.f, 0.f);
+        if(pn || displaced)
+        {
+          Nk = normalize3(ld_f3(normals, gk));
+          Nq = normalize3(ld_f3(normals, gq));
+        }
+        F3 cp = (Pk + Pq) * 0.5f;
+        if(pn)
+        {
+          const F3 ed = Pq - Pk;
+          cp = fma3(Nq, 0.125f * dot3(ed, Nq), fma3(Nk, -0.125f * dot3(ed, Nk), cp));
+        }
+        if(displaced)
+        {
+          const float2 Tk = __ldg(texcoords + gk), Tq = __ldg(texcoords + gq);
+          cp = displace_along<TEX>(p, uniformTex, uniW, uniH, ti, cp, Nk + Nq, make_float2((Tk.x + Tq.x) * 0.5f, (Tk.y + Tq.y) * 0.5f), scale, offset);
+        }
+        float* d = p.classCache + size_t(cls.w + (ch.w / 3u + tri) * 3u + k) * 3;
+        d[0] = cp.x; d[1] = cp.y; d[2] = cp.z;
+      }
+    }
+  }
+}
+
+// Displaced cluster-vertex copies of instances whose displacement class is cached (k_class_cache): a plain float stream from the
+// cache (L2 resident: one geometry) to the cluster's slot in genVertices.  A warp takes 32 consecutive visible clusters (lane =
+// cluster: destination + descriptor), compacts the ones with a copy and streams FOUR clusters at a time: for each of them the 32
+// lanes cover 128 contiguous bytes per instruction (eight-lane groups per cluster were measured LSU-wavefront bound: every
+// instruction touched eight lines), and all loads of the four clusters -- up to 24 per lane -- are in flight before the first store.
+__global__ void __launch_bounds__(256) k_cluster_copies(Params p)
+{
+  pdl_prologue();
+  if(p.state->clusterLevelWork == 0)
+    return;
+  const uint32_t lane = lane_id(), warpsTotal = gridDim.x * (blockDim.x >> 5);
+  const uint32_t numVisible = p.build->visibleClusterCounter;
+  const tc_ClusterInfo* visibleClusters = reinterpret_cast<const tc_ClusterInfo*>(p.build->visibleClusters);
+  float* __restrict__ genVertices = reinterpret_cast<float*>(p.build->genVertices);
+  const float* __restrict__ cache = p.classCache;
+  for(uint32_t chunk = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; chunk < numVisible; chunk += warpsTotal * 32)
+  {
+    uint32_t dstL = 0, srcL = 0, numL = 0;
+    if(chunk + lane < numVisible)
+    {
+      const uint32_t d = __ldcs(&p.clusterVertexDst[chunk + lane]);
+      if(d != ~0u)
+      {
+        const tc_ClusterInfo ci = visibleClusters[chunk + lane];
+        const uint32_t cls = __ldg(&p.instanceVertexCache[ci.instanceID]);
+        if(cls != ~0u)
+        {
+          const uint4 ch = __ldg(reinterpret_cast<const uint4*>(p.instances[ci.instanceID].clusters) + ci.clusterID);
+          dstL = d; srcL = cls + ch.z; numL = (ch.x & 0xFFFF) * 3;
+        }
+      }
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, numL != 0), count = __popc(mask);
+    for(uint32_t r0 = 0; r0 < count; r0 += 4)
+    {
+      const float* src[4];
+      float*       dst[4];
+      uint32_t     nF[4], maxF = 0;
+#pragma unroll
+      for(int j = 0; j < 4; j++)
+      {
+        const uint32_t from = __fns(mask, 0, min(r0 + j, count - 1) + 1);  // lane that holds the (r0 + j)-th cluster with a copy
+        const uint32_t n = __shfl_sync(0xffffffffu, numL, from), s = __shfl_sync(0xffffffffu, srcL, from), d = __shfl_sync(0xffffffffu, dstL, from);
+        nF[j]  = r0 + j < count ? n : 0u;
+        src[j] = cache + size_t(s) * 3;
+        dst[j] = genVertices + size_t(d) * 3;
+        maxF   = max(maxF, nF[j]);
+      }
+      for(uint32_t f0 = lane; f0 < maxF; f0 += 192)
+      {
+        float x[4][6];
+#pragma unroll
+        for(int j = 0; j < 4; j++)
+#pragma unroll
+          for(int k = 0; k < 6; k++)
+            x[j][k] = f0 + k * 32 < nF[j] ? __ldg(src[j] + f0 + k * 32) : 0.0f;
+#pragma unroll
+        for(int j = 0; j < 4; j++)
+#pragma unroll
+          for(int k = 0; k < 6; k++)
+            if(f0 + k * 32 < nF[j])
+              __stcs(dst[j] + f0 + k * 32, x[j][k]);
+      }
+    }
+  }
+}
+
 // TEX: 0 no textures, 1 one texture (warp-uniform handle from the parameter block), 2 per-instance handles
 template <int TEX>
 __global__ void __launch_bounds__(256, 2) k_cluster_vertices(Params p)
@@ -1308,6 +1568,8 @@ __global__ void __launch_bounds__(256, 2) k_cluster_vertices(Params p)
         dstL = d; instL = ci.instanceID; firstL = ch.z; numL = ch.x & 0xFFFF;
       }
     }
+    if(numL && __ldg(&p.instanceVertexCache[instL]) != ~0u)
+      numL = 0;  // instance of a cached displacement class: k_cluster_copies streams its copy from the cache
     const uint32_t endV = warp_inclusive_add(numL), startV = endV - numL, total = __shfl_sync(0xffffffffu, endV, 31);
     // lane = vertex of the chunk's flat vertex list
     for(uint32_t t0 = 0; t0 < total; t0 += 32 * U)
@@ -1415,57 +1677,90 @@ __global__ void __launch_bounds__(MINI_WARPS * 32, 6) k_mini_vertices(Params p)
   __shared__ uint32_t whereTbl[48];
   float* stage = stageAll[warp];
   uint2* hdr   = hdrAll[warp];
-  if(threadIdx.x < 48)
-  {
-    const uint32_t rot = threadIdx.x % 3u, flipped = (threadIdx.x / 3u) & 1u, c3 = threadIdx.x / 6u;
-    const uint32_t cfgIdx = (c3 & 1u) + 16u * ((c3 >> 1) & 1u) + 256u * (c3 >> 2);  // = x + 16 y + 256 z - 273 with factors in {1,2}
-    const tc_TessTableEntry e = p.tblEntries[cfgIdx];
-    const uint32_t perm[3] = {rot, (rot + 1u) % 3u, (rot + 2u) % 3u};  // base vertex behind each corner of the rotated triangle
-    uint32_t where = 0xFFFFFFu;
-    for(uint32_t i = 0; i < TC_TESS_2X_MINI_VERTICES && i < e.numVertices; i++)
-    {
-      const uint32_t pv = p.tblVertices[e.firstVertex + i];
-      uint32_t h1 = (pv & 0xFFFFu) >> 14, h2 = pv >> 30, h0 = 2u - h1 - h2;  // pattern barycentrics in halves
-      if(flipped)
-      {
-        const uint32_t t = h0;
-        h0 = h1;
-        h1 = t;
-      }
-      const uint32_t hb = (h0 << (2 * perm[0])) + (h1 << (2 * perm[1])) + (h2 << (2 * perm[2]));  // halves per BASE vertex
-      const uint32_t c  = hb == 0x02u ? 0u : hb == 0x08u ? 1u : hb == 0x20u ? 2u : hb == 0x05u ? 3u : hb == 0x14u ? 4u : 5u;
-      where = (where & ~(0xFu << (4 * c))) | (i << (4 * c));
-    }
-    whereTbl[threadIdx.x] = where | (min(uint32_t(e.numVertices), TC_TESS_2X_MINI_VERTICES) << 24);
-  }
+  mini_where_table_init(p, whereTbl);
   __syncthreads();
-  const uint32_t count = min(p.state->miniCount, p.maxMini);
+  // Work items = the 2X batch records classify wrote (transBuilds entries with mode 3, build order): an 8-lane group takes one
+  // batch, lane r of the group its r-th mini triangle.  Everything a mini triangle needs is in what the path outputs anyway:
+  // the build record (part-list slot of the batch, triangle count, vertex destination), the batch header (instance, cluster) and
+  // the u16 mapping words (base triangle | pattern triangle << 8 | un-rotated factors - 1 << 12): a mini triangle starts where the
+  // pattern-triangle field is 0.  No side list, no extra DRAM round trip (it was 32 B written + read per mini triangle).
+  const uint32_t count = p.state->miniCount ? min(p.build->transBuildCounter, p.maxGenClusters) : 0u;
   float* genVertices = reinterpret_cast<float*>(p.build->genVertices);
   const cudaTextureObject_t uniformTex = TEX == 1 ? p.texturesC[0].gather : 0;
   const float uniW = TEX == 1 ? float(p.texturesC[0].width) : 0.0f, uniH = TEX == 1 ? float(p.texturesC[0].height) : 0.0f;
   const float viewScale = p.view[0].displacementScale, viewOffset = p.view[0].displacementOffset;
   const bool  pn = flag_pn(p);
-  const uint32_t warpsTotal = gridDim.x * MINI_WARPS;
-  for(uint32_t base = (blockIdx.x * MINI_WARPS + warp) * 32; base < count; base += warpsTotal * 32)
+  const uint32_t warpsTotal = gridDim.x * MINI_WARPS, group = lane >> 3, sub = lane & 7u;
+  const uint4*    builds = reinterpret_cast<const uint4*>(p.build->transBuilds);
+  const uint16_t* map16  = reinterpret_cast<const uint16_t*>(p.build->partTriangles);
+  const tc_TessTriangleInfo* partTriangles = reinterpret_cast<const tc_TessTriangleInfo*>(p.build->partTriangles);
+  for(uint32_t base = (blockIdx.x * MINI_WARPS + warp) * 4; base < count; base += warpsTotal * 4)
   {
-    const uint32_t idx = base + lane;
+    const uint32_t bIdx = base + group;
     hdr[lane] = make_uint2(0u, 0u);  // .y = 0: this lane has no mini triangle
 #ifndef TC_MINI_NO_PREFETCH
-    // the record of the warp's NEXT iteration is requested now (no registers held): the record load heads a chain of four
-    // dependent round trips (record -> instance -> base attributes -> gathers) and was 18 % of the stall samples
-    if(idx + warpsTotal * 32 < count)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(&p.miniList[size_t(idx + warpsTotal * 32) * 2]));
+    // the records of the warp's NEXT iteration are requested now (no registers held): the record load heads a chain of
+    // dependent round trips (record -> header + mappings -> instance -> base attributes / cache)
+    if(bIdx + warpsTotal * 4 < count && sub == 0)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(&builds[size_t(bIdx + warpsTotal * 4) * 4]));
 #endif
-    if(idx < count)
+    uint32_t partOffset = 0, numBatchTris = 0;
+    if(bIdx < count)
     {
-    const uint4 a = __ldcs(&p.miniList[size_t(idx) * 2]), b = __ldcs(&p.miniList[size_t(idx) * 2 + 1]);
-    const uint32_t instanceID = a.x, cfg = b.z;
+      const uint4 q0 = __ldcs(&builds[size_t(bIdx) * 4]);  // clusterID, clusterFlags, packed, baseGeometryIndexAndFlags
+      if((q0.x >> 30) == TC_RT_CLUSTER_MODE_2X_BATCHED_TESSELLATED)
+      {
+        partOffset   = q0.x & 0x3FFFFFFFu;
+        numBatchTris = q0.z & 0x1FFu;
+      }
+    }
+    // mapping words of the batch, t = sub + 8 k, and where its mini triangles start
+    uint32_t m[4], groupMask = 0;
+#pragma unroll
+    for(int k = 0; k < 4; k++)
+    {
+      const uint32_t t = sub + 8u * k;
+      m[k] = t < numBatchTris ? uint32_t(__ldcs(map16 + size_t(partOffset) * (sizeof(tc_TessTriangleInfo) / 2) + sizeof(tc_ClusterInfo) / 2 + t)) : 0xFFFFu;
+      const uint32_t starts = __ballot_sync(0xffffffffu, t < numBatchTris && ((m[k] >> 8) & 0xFu) == 0u);
+      groupMask |= ((starts >> (8u * group)) & 0xFFu) << (8u * k);
+    }
+    const uint32_t numMinis = __popc(groupMask);
+    const uint32_t tr = __fns(groupMask, 0, min(sub, numMinis ? numMinis - 1u : 0u) + 1);  // mapping index of this lane's mini triangle
+    const uint32_t srcLane = (tr & 7u) + 8u * group;
+    uint32_t mine = 0;
+#pragma unroll
+    for(int k = 0; k < 4; k++)
+    {
+      const uint32_t v = __shfl_sync(0xffffffffu, m[k], srcLane);
+      if((tr >> 3) == uint32_t(k))
+        mine = v;
+    }
+    if(sub < numMinis)
+    {
+    const tc_ClusterInfo cinfo = partTriangles[partOffset].cluster;  // batch header (cluster_classify.comp.glsl:436)
+    const uint32_t instanceID = cinfo.instanceID;
     const tc_RenderInstance& inst = p.instances[instanceID];
+    const uint4    ch  = __ldg(reinterpret_cast<const uint4*>(inst.clusters) + cinfo.clusterID);
+    const uint32_t tri = mine & 0xFFu, pf = mine >> 12;
+    const uint8_t* lt  = reinterpret_cast<const uint8_t*>(inst.clusterLocalTriangles) + ch.w + tri * 3u;
+    uint4 a, b;
+    a.x = instanceID;
+    a.y = ch.z;  // firstLocalVertex
+    a.z = uint32_t(__ldg(lt)) | (uint32_t(__ldg(lt + 1)) << 8) | (uint32_t(__ldg(lt + 2)) << 16);
+    b.x = ch.w / 3u + tri;  // triangle of the geometry (edge-midpoint cache)
+    // config + rotation exactly as classify derived them from the un-rotated factors (tess_getConfig rotates the corner triple)
+    uint32_t v0 = 0u, v1 = TC_TESSTABLE_COORD_MAX, v2 = TC_TESSTABLE_COORD_MAX << 16;
+    const uint32_t cfg = tess_getConfig(1u + (pf & 1u), 1u + ((pf >> 1) & 1u), 1u + ((pf >> 2) & 1u), v0, v1, v2);
+    a.w = v0;
+    b.w = __ldg(&p.transVertexOffsets[bIdx]) + sub * TC_TESS_2X_MINI_VERTICES;  // first vertex of this mini triangle in genVertices
     // candidate -> pattern index nibbles + vertex count: a function of (factors <= 2, flipped, rotation) only, see whereTbl
-    const uint32_t rot   = (a.w & 0xFFFFu) ? 1u : ((a.w >> 16) ? 2u : 0u);  // base vertex behind corner 0 of the rotated triangle
-    const uint32_t c3    = (cfg & 1u) | ((cfg >> 3) & 2u) | ((cfg >> 6) & 4u);
-    const uint32_t where = whereTbl[(c3 * 2u + ((cfg >> 15) & 1u)) * 3u + rot];
+    const uint32_t where = mini_where(whereTbl, cfg, a.w);
     const uint32_t numV  = where >> 24;
+    float* myStage = stage + lane * kMiniFloats;
+    const uint32_t vcache = __ldg(&p.instanceVertexCache[instanceID]), mcache = __ldg(&p.instanceMidCache[instanceID]);
+    const bool doneInline = !ANIM && vcache != ~0u && mcache != ~0u;  // cached displacement class: k_cluster_classify<2> copied the vertices
+    if(!doneInline)
+    {
     const float*   positions = reinterpret_cast<const float*>(inst.positions);
     const float*   normals   = reinterpret_cast<const float*>(inst.normals);
     const float2*  texcoords = reinterpret_cast<const float2*>(inst.texcoords);
@@ -1487,7 +1782,6 @@ __global__ void __launch_bounds__(MINI_WARPS * 32, 6) k_mini_vertices(Params p)
     }
     const float W = displaced ? (TEX == 1 ? uniW : float(p.textures[ti].width)) : 1.0f, H = displaced ? (TEX == 1 ? uniH : float(p.textures[ti].height)) : 1.0f;
     const float scale = inst.displacementScale * viewScale, offset = inst.displacementOffset + viewOffset;
-    float* myStage = stage + lane * kMiniFloats;
     // three candidates at a time (corners, then edge midpoints): position, displacement direction (not normalised), texture
     // coordinate, pattern index nibbles; the three gathers are in flight together, results go to the lane's staging slot
     auto finish3 = [&](F3 (&cp)[3], const F3 (&cn)[3], const float2 (&ct)[3], uint32_t where3) {
@@ -1556,27 +1850,12 @@ __global__ void __launch_bounds__(MINI_WARPS * 32, 6) k_mini_vertices(Params p)
     }
     hdr[lane] = make_uint2(b.w * 3u, numV * 3u);
     }
+    }
     // ... and let the warp write them: lane t handles float (t % 18) of mini triangle (t / 18), so consecutive lanes
     // write consecutive addresses inside a mini triangle's slot and across the slots of a batch (which are adjacent);
     // slots of absent vertices stay untouched, exactly like the reference leaves them
     __syncwarp();
-    {
-      uint32_t m = lane >= kMiniFloats ? 1u : 0u, j = lane - m * kMiniFloats;
-#pragma unroll 6
-      for(uint32_t it = 0; it < kMiniFloats; it++)
-      {
-        const uint2 h = hdr[m];
-        if(j < h.y)
-          __stcs(genVertices + size_t(h.x) + j, stage[it * 32 + lane]);
-        j += 32 - kMiniFloats;  // 32 = 18 + 14
-        m += 1;
-        if(j >= kMiniFloats)
-        {
-          j -= kMiniFloats;
-          m += 1;
-        }
-      }
-    }
+    mini_write_staged(genVertices, stage, hdr, lane);
     __syncwarp();
   }
 }
@@ -3466,7 +3745,7 @@ size_t instantiate_smem_bytes(int tex) { return size_t(INST_WARPS) * (tex == 2 ?
 
 size_t classify_smem_bytes(uint32_t clusterVertices, uint32_t clusterTriangles)
 {
-  return size_t(CLASSIFY_WARPS) * (size_t(clusterVertices) * 7 + size_t(clusterTriangles) * 3) * 4;
+  return size_t(CLASSIFY_WARPS) * (size_t(clusterVertices) * 7 + size_t(clusterTriangles) * 3 + CLASSIFY_MINI_STAGE_WORDS) * 4;
 }
 
 int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, KernelOccupancy* occ)
@@ -3474,7 +3753,8 @@ int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, Kerne
   size_t smem = classify_smem_bytes(clusterVertices, clusterTriangles);
   if(cudaFuncSetAttribute(k_cluster_classify<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess
      || cudaFuncSetAttribute(k_cluster_classify<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess
-     || cudaFuncSetAttribute(k_cluster_classify<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+     || cudaFuncSetAttribute(k_cluster_classify<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess
+     || cudaFuncSetAttribute(k_cluster_classify<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
     return -1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->classify, k_cluster_classify<1>, CLASSIFY_THREADS, smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->split, k_triangle_split, SPLIT_THREADS, 0);
@@ -3519,8 +3799,23 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
   const size_t smem = classify_smem_bytes(p.clusterVertices, p.clusterTriangles);
   launch_pdl(k_cluster_classify<0>, grid, CLASSIFY_THREADS, smem, s, p);
   launch_pdl(k_classify_scan, 148 * 3, CSCAN_THREADS, 0, s, p, epochCounter);  // 3 CTAs per SM at 80 registers; tiles are handed out by ticket
+  if(p.numCacheClasses && !(p.flags & TC_FLAG_ANIMATION))
+  {  // instancing-aware cache of displaced cluster vertices / base-edge midpoints: one warp per cluster of every cached class
+    const uint32_t ccGrid = (p.numCacheClusters + 7) / 8 < miniGrid / 5 * 8 ? (p.numCacheClusters + 7) / 8 : miniGrid / 5 * 8;
+    if(p.numTextures == 0)
+      launch_pdl(k_class_cache<0>, ccGrid, 256, 0, s, p);
+    else if(p.numTextures == 1)
+      launch_pdl(k_class_cache<1>, ccGrid, 256, 0, s, p);
+    else
+      launch_pdl(k_class_cache<2>, ccGrid, 256, 0, s, p);
+  }
   launch_pdl(k_cluster_classify<1>, grid, CLASSIFY_THREADS, smem, s, p);
-  launch_pdl(k_cluster_classify<2>, grid, CLASSIFY_THREADS, smem, s, p);
+  if(p.numCacheClasses && (p.flags & TC_FLAG_TRANSIENT_2X) && !(p.flags & TC_FLAG_ANIMATION))
+    launch_pdl(k_cluster_classify<3>, grid, CLASSIFY_THREADS, smem, s, p);
+  else
+    launch_pdl(k_cluster_classify<2>, grid, CLASSIFY_THREADS, smem, s, p);
+  if(p.numCacheClasses && !(p.flags & TC_FLAG_ANIMATION))
+    launch_pdl(k_cluster_copies, miniGrid / 5 * 8, 256, 0, s, p);  // copies of cached classes: 8 CTAs of 256 threads per SM (4 resident)
   {  // displaced cluster-vertex copies recorded by the cluster-level emit kernel
     const uint32_t cvGrid = miniGrid / 5 * 2;  // 2 CTAs of 256 threads per SM
     if(p.numTextures == 0)
@@ -3530,8 +3825,8 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
     else
       launch_pdl(k_cluster_vertices<2>, cvGrid, 256, 0, s, p);
   }
-  if(p.flags & TC_FLAG_TRANSIENT_2X)
-  {  // vertices of the 2X mini triangles recorded by the kernel above
+  if((p.flags & TC_FLAG_TRANSIENT_2X) && !(p.allInstancesCached && !(p.flags & TC_FLAG_ANIMATION)))
+  {  // vertices of the 2X mini batches of instances without a cached displacement class (the others were copied inline)
     const int    tex  = p.numTextures == 0 ? 0 : (p.numTextures == 1 ? 1 : 2);
     const bool   anim = (p.flags & TC_FLAG_ANIMATION) != 0;
     const size_t ms   = 0;
