@@ -864,18 +864,24 @@ TC_API int tc_set_scene(tc_context* c, const tc_geometry* geoms, uint32_t numGeo
         members[k]++;
       }
       std::vector<uint32_t> slot(reps.size(), ~0u);
+      // layout of classCache: [packed float3 vertex caches of all classes][16-byte aligned: float4 edge-midpoint caches]
+      uint64_t vertexFloat3 = 0, midFloat4 = 0;
       for(uint32_t k = 0; k < reps.size(); k++)
       {
         const tc_geometry& g = geoms[inst[reps[k]].geometryID];
-        const uint64_t need = uint64_t(g.numVertices) + (use2X ? uint64_t(g.numTriangles) * 3 : 0);
-        if(members[k] < 2 || cacheFloat3 + need > 0xFFFF0000ull)
+        if(members[k] < 2 || vertexFloat3 + g.numVertices > 0x7FFF0000ull || midFloat4 + uint64_t(g.numTriangles) * 3 > 0x3FFF0000ull)
           continue;
         slot[k] = uint32_t(classes.size());
-        const uint32_t vbase = uint32_t(cacheFloat3), mbase = use2X ? uint32_t(cacheFloat3 + g.numVertices) : ~0u;
-        classes.push_back(make_uint4(reps[k], clusterItems, vbase, mbase));
-        cacheFloat3 += need;
+        classes.push_back(make_uint4(reps[k], clusterItems, uint32_t(vertexFloat3), use2X ? uint32_t(midFloat4) : ~0u));
+        vertexFloat3 += g.numVertices;
+        midFloat4 += use2X ? uint64_t(g.numTriangles) * 3 : 0;
         clusterItems += g.numClusters;
       }
+      const uint64_t midBase4 = (vertexFloat3 * 12 + 15) / 16;  // first float4 of the midpoint region
+      for(uint4& cl : classes)
+        if(cl.w != ~0u)
+          cl.w += uint32_t(midBase4);
+      cacheFloat3 = ((midBase4 + midFloat4) * 16 + 11) / 12;  // allocation size in float3 units
       for(uint32_t i = 0; i < numInstances; i++)
         if(slot[classOf[i]] != ~0u)
         {

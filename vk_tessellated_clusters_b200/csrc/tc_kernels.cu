@@ -549,9 +549,9 @@ __device__ __forceinline__ void mini_copy_cached(const Params& p, uint32_t where
     }
     if(im != 0xFu)
     {
-      const float* c = p.classCache + size_t(mcache + geometryTriangle * 3u + k) * 3;
+      const float4 c = __ldg(reinterpret_cast<const float4*>(p.classCache) + mcache + geometryTriangle * 3u + k);
       float* sv = myStage + im * 3;
-      sv[0] = __ldg(c); sv[1] = __ldg(c + 1); sv[2] = __ldg(c + 2);
+      sv[0] = c.x; sv[1] = c.y; sv[2] = c.z;
     }
   }
 }
@@ -771,6 +771,15 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
     const uint32_t src = __ffs(needMask) - 1;
     needMask &= needMask - 1;
     const uint32_t vi    = __shfl_sync(0xffffffffu, viL, src);
+    if(MODE >= 2 && needMask)
+    {  // lines of the NEXT cluster's stash (and its scan tuple) requested now: they are DRAM reads at the head of its dependent chain
+      const uint32_t viNext = __shfl_sync(0xffffffffu, viL, __ffs(needMask) - 1);
+      const char*    nextStash = reinterpret_cast<const char*>(p.factorStash + size_t(viNext) * maxT * 3);
+      if(lane * 128u < maxT * 12u)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nextStash + lane * 128u));
+      else if(lane == 31)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(&tuples[viNext]));
+    }
     const bool     valid = true;
     uint32_t*      stash = p.factorStash + size_t(vi) * maxT * 3;
 
@@ -1162,16 +1171,40 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
           // the vertices of the batch are generated by k_mini_vertices FROM THE BUILD RECORD written below (no side list)
           accMini = 1;
           if(MODE == 3 && inlineMini)
-          {  // (warp-uniform) corners and edge midpoints from the class cache -> staging -> coalesced stores
-            sMiniHdr[lane] = make_uint2(0u, 0u);
-            if(mini && !failB)
+          {  // (warp-uniform) corners and edge midpoints from the class cache -> staging -> coalesced stores.  Mini triangle of
+             // rank r (among the round's mini triangles) is staged in slot r; ranks are dense, batches hold 8 and are 56 vertices
+             // apart, so staged float t belongs to rank t / 18 and goes to roundBase + t + 24 * (t / 144): no per-float header.
+            uint8_t* sMiniCnt = reinterpret_cast<uint8_t*>(sMiniHdr);
+            if(mini)
             {
-              const uint32_t where = mini_where(whereTbl, cfg, v0);
-              mini_copy_cached(p, where, vcacheI, mcacheI, firstLocalVertex, i0, i1, i2, firstLocalTriangle / 3u + tri, sMiniStage + lane * (TC_TESS_2X_MINI_VERTICES * 3));
-              sMiniHdr[lane] = make_uint2((transVertexOffset + relMini * miniVertices) * 3u, (where >> 24) * 3u);
+              uint32_t nFloats = 0;
+              if(!failB)
+              {
+                const uint32_t where = mini_where(whereTbl, cfg, v0);
+                mini_copy_cached(p, where, vcacheI, mcacheI, firstLocalVertex, i0, i1, i2, firstLocalTriangle / 3u + tri, sMiniStage + offsetMini * (TC_TESS_2X_MINI_VERTICES * 3));
+                nFloats = (where >> 24) * 3u;
+              }
+              sMiniCnt[offsetMini] = uint8_t(nFloats);  // 0: the batch failed its allocation, nothing is written
             }
             __syncwarp();
-            mini_write_staged(genVerticesF, sMiniStage, sMiniHdr, lane);
+            {
+              const float*   ps = sMiniStage + lane;
+              float*         pd = genVerticesF + size_t(run.v[T_VERT]) * 3 + lane;
+              const uint32_t total = nMini * (TC_TESS_2X_MINI_VERTICES * 3);
+              uint32_t       boundary = 8 * TC_TESS_2X_MINI_VERTICES * 3;  // first staged float of the next batch
+#pragma unroll 2
+              for(uint32_t t = lane; t < total; t += 32, ps += 32, pd += 32)
+              {
+                if(t >= boundary)
+                {  // (a step is 32 floats, a batch 144: at most one boundary per step)
+                  pd += 24;
+                  boundary += 8 * TC_TESS_2X_MINI_VERTICES * 3;
+                }
+                const uint32_t r = (t * 3641u) >> 16;  // t / 18 for t < 576
+                if(t - r * 18u < sMiniCnt[r])
+                  __stcs(pd, *ps);
+              }
+            }
             __syncwarp();
           }
           if(mini && !failB)
@@ -1464,8 +1497,7 @@ __global__ void __launch_bounds__(256) k_class_cache(Params p)
           const float2 Tk = __ldg(texcoords + gk), Tq = __ldg(texcoords + gq);
           cp = displace_along<TEX>(p, uniformTex, uniW, uniH, ti, cp, Nk + Nq, make_float2((Tk.x + Tq.x) * 0.5f, (Tk.y + Tq.y) * 0.5f), scale, offset);
         }
-        float* d = p.classCache + size_t(cls.w + (ch.w / 3u + tri) * 3u + k) * 3;
-        d[0] = cp.x; d[1] = cp.y; d[2] = cp.z;
+        reinterpret_cast<float4*>(p.classCache)[cls.w + (ch.w / 3u + tri) * 3u + k] = make_float4(cp.x, cp.y, cp.z, 0.0f);
       }
     }
   }
@@ -1503,8 +1535,8 @@ __global__ void __launch_bounds__(256) k_cluster_copies(Params p)
         }
       }
     }
-    const uint32_t mask = __ballot_sync(0xffffffffu, numL != 0), count = __popc(mask);
-    for(uint32_t r0 = 0; r0 < count; r0 += 4)
+    uint32_t remaining = __ballot_sync(0xffffffffu, numL != 0);  // lanes that hold a cluster with a copy
+    while(remaining)
     {
       const float* src[4];
       float*       dst[4];
@@ -1512,9 +1544,11 @@ __global__ void __launch_bounds__(256) k_cluster_copies(Params p)
 #pragma unroll
       for(int j = 0; j < 4; j++)
       {
-        const uint32_t from = __fns(mask, 0, min(r0 + j, count - 1) + 1);  // lane that holds the (r0 + j)-th cluster with a copy
+        const bool     have = remaining != 0;
+        const uint32_t from = have ? __ffs(remaining) - 1 : 0u;
+        remaining &= remaining - 1;  // (0 stays 0)
         const uint32_t n = __shfl_sync(0xffffffffu, numL, from), s = __shfl_sync(0xffffffffu, srcL, from), d = __shfl_sync(0xffffffffu, dstL, from);
-        nF[j]  = r0 + j < count ? n : 0u;
+        nF[j]  = have ? n : 0u;
         src[j] = cache + size_t(s) * 3;
         dst[j] = genVertices + size_t(d) * 3;
         maxF   = max(maxF, nF[j]);
