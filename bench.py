@@ -227,14 +227,15 @@ def main():
         n_inst = len(full_scene.instances)
         generated = gpu.buffer("blasBuildInfos", n_inst, sb_full)["clusterReferencesCount"]
         clusters = np.array([full_scene.geometries[int(i["geometryID"])].num_clusters for i in full_scene.instances])
-        weights = sharding.frame_weights(clusters, generated)
+        visible = (gpu.buffer("instanceStates", n_inst, sb_full) & 2) != 0
+        weights = sharding.frame_weights(clusters, generated, visible)
         bounds = sharding.partition_instances(weights, world)
         first, last = bounds[rank]
         gpu.set_scene(sharding.shard_scene(full_scene, first, last))
         if w.hiz is not None:
             gpu.set_hiz(*w.hiz)
         shard_info = {"instances_per_rank": [b - a for a, b in bounds], "weight_share_per_rank": [float(weights[a:b].sum() / weights.sum()) for a, b in bounds],
-                      "balance": "previous frame's generated clusters per instance + 0.25 x clusters"}
+                      "balance": "previous frame: clusters x (4 if the instance was visible else 1) + 0.5 x generated CLAS beyond one per cluster"}
 
     shard = None
     if world > 1:

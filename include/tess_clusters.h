@@ -234,6 +234,39 @@ TC_API int tc_batch_part_triangles(tc_context* ctx, tc_task_exchange* tasks, uin
 TC_API int tc_emit_meshlet_triangles(tc_context* ctx, uint8_t* indices, uint32_t* primitiveIDs, uint64_t capacityTriangles,
                                      uint64_t* numTriangles, uint32_t flags);
 
+/* ---- load-time cluster builder ------------------------------------------------------------
+ * Scene::processGeometry (src/scene.cpp:365-552) for one indexed triangle mesh: clusters of at most maxClusterTriangles
+ * triangles / maxClusterVertices vertices with u8 local indices, per-cluster vertex arrays, cluster bounding boxes with
+ * shortest / longest edge -- i.e. a tc_geometry the path can consume (the CLAS template tables stay NULL: driver outputs).
+ *  - tc_cluster_bboxes   = Scene::buildGeometryClusterBboxes   (:463-517), bit-exact against the reference's code;
+ *  - tc_cluster_vertices = Scene::buildGeometryClusterVertices (:519-552), bit-exact copies;
+ *  - tc_build_clusters   = the whole step.  The clusteriser itself (:393-441) is meshoptimizer's
+ *    meshopt_buildMeshletsSpatial in the reference -- third-party code that is not part of the reference tree and is not
+ *    pinned; here it is a documented deterministic stand-in: triangles ordered along the Morton curve of their centroids
+ *    (30 bits, keys computed on the GPU), packed greedily in that order under the two limits, local vertices in first-use
+ *    order; meshopt_optimizeMeshlet (:444-461, a locality reorder inside a cluster) is not applied.
+ * All pointers are host pointers; the calls synchronise.  tc_cluster_last_error() has the text of a failure. */
+typedef struct tc_mesh {
+  uint32_t        numVertices, numTriangles;
+  const float*    positions; /* float3[numVertices] */
+  const float*    normals;   /* float3[numVertices] */
+  const float*    texcoords; /* float2[numVertices] */
+  const uint32_t* triangles; /* 3 x u32 per triangle */
+} tc_mesh;
+typedef struct tc_cluster_build tc_cluster_build; /* owns the result arrays */
+TC_API int  tc_build_clusters(const tc_mesh* mesh, uint32_t maxClusterVertices, uint32_t maxClusterTriangles, int device, tc_cluster_build** out);
+/* geometry's pointers stay valid until tc_cluster_build_free; clusterLocalVertices (may be NULL) receives the cluster-vertex ->
+ * mesh-vertex indirection the reference drops after processGeometry */
+TC_API int  tc_cluster_build_geometry(const tc_cluster_build* build, tc_geometry* geometry, const uint32_t** clusterLocalVertices);
+TC_API void tc_cluster_build_free(tc_cluster_build* build);
+TC_API int  tc_cluster_bboxes(const float* positions, uint32_t numVertices, const tc_Cluster* clusters, uint32_t numClusters,
+                              const uint32_t* clusterLocalVertices, uint32_t numLocalVertices, const uint8_t* clusterLocalTriangles,
+                              uint32_t numLocalTriangleBytes, int device, tc_BBox* out);
+TC_API int  tc_cluster_vertices(const float* positions, const float* normals, const float* texcoords, uint32_t numVertices,
+                                const uint32_t* clusterLocalVertices, uint32_t numClusterVertices, int device, float* outPositions,
+                                float* outNormals, float* outTexcoords);
+TC_API const char* tc_cluster_last_error(void);
+
 /* ---- Renderer::render ---------------------------------------------------------------------------------
  * frameConstants points at two consecutive FrameConstants (current, last) `strideBytes` apart
  * (sizeof(shaderio::FrameConstants) for a reference caller, sizeof(tc_FrameConstants) otherwise).

@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(_HERE, "_build", "libtess_oracle.so")
 
 def build_oracle(force: bool = False) -> str:
     src = os.path.join(_HERE, "tess_oracle.cpp")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+    srcs = [src, os.path.join(_HERE, "cluster_oracle.cpp")]
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return LIB_PATH
 

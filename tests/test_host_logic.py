@@ -82,7 +82,7 @@ def test_partition_instances_balanced_contiguous():
     # weights from the previous frame (half of the instances culled: they generate one CLAS per cluster, the others many)
     clusters = np.full(8, 100)
     generated = np.array([100, 100, 100, 100, 5000, 5000, 5000, 5000])
-    parts = sharding.partition_instances(sharding.frame_weights(clusters, generated), 2)
+    parts = sharding.partition_instances(sharding.frame_weights(clusters, generated, generated > 100), 2)
     assert parts[0][1] >= 5  # the split point moves into the heavy half
 
 

@@ -248,7 +248,7 @@ def test_sharded_frame_equals_unsharded(table, world):
     sets0 = _instance_multisets(ref, sb0)
     # balance by the frame just rendered: generated clusters per instance + a share per cluster for classify
     n_clusters = scene.geometries[0].num_clusters
-    weights = sharding.frame_weights(np.full(N, n_clusters), blas0["clusterReferencesCount"])
+    weights = sharding.frame_weights(np.full(N, n_clusters), blas0["clusterReferencesCount"], (states0 & 2) != 0)
     bounds = sharding.partition_instances(weights, world)
     assert bounds != sharding.partition_instances(np.full(N, n_clusters), world)  # culling moves the split points
 

@@ -55,10 +55,17 @@ def shard_scene(scene, first: int, last: int):
     return dataclasses.replace(scene, instances=np.ascontiguousarray(scene.instances[first:last]))
 
 
-def frame_weights(cluster_counts, generated_clusters, classify_cost: float = 0.25):
-    """Per-instance load estimate from the previous frame: generated CLAS of the instance + a share per cluster for the
-    classify pass every cluster goes through, whether it tessellates or not."""
-    return np.asarray(generated_clusters, np.float64) + classify_cost * np.asarray(cluster_counts, np.float64)
+def frame_weights(cluster_counts, generated_clusters, visible=None, visible_cost: float = 4.0, part_cost: float = 0.5):
+    """Per-instance load estimate from the previous frame, in units of "one cluster streamed through the path":
+    every cluster of the instance once (a hidden or untessellated instance is little more than that: a template record and a
+    displaced vertex copy per cluster), `visible_cost` times that for instances the classify pass evaluates per triangle
+    (visible ones, BlasBuildInfo / instanceStates of the last frame), and `part_cost` per generated CLAS beyond one per cluster
+    (split, instantiate and insert work of tessellated instances).  The constants come from the per-kernel times of
+    BASELINE config 3 on one B200 (profiles/r02_notes.md)."""
+    clusters = np.asarray(cluster_counts, np.float64)
+    generated = np.asarray(generated_clusters, np.float64)
+    vis = np.ones_like(clusters) if visible is None else np.asarray(visible, np.float64)
+    return clusters * (1.0 + (visible_cost - 1.0) * vis) + part_cost * np.maximum(generated - clusters, 0.0)
 
 
 def exchange_shard_counts(local_counts, group=None):
