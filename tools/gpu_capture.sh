@@ -11,7 +11,7 @@ if [[ ",$WHAT," == *",2,"* ]]; then
 fi
 for k in 3 5; do
   if [[ ",$WHAT," == *",$k,"* ]]; then
-    $NCU -k regex:"k_cluster_classify|k_classify_scan|k_cluster_vertices|k_mini_vertices|k_instantiate" -s 14 -c 7 -o gpurun_out/${TAG}_cfg$k -f python tools/run_config_once.py $k > /dev/null 2>&1
+    $NCU -k regex:"k_cluster_classify|k_classify_scan|k_class_cache|k_cluster_copies|k_cluster_vertices|k_mini_vertices|k_instantiate" -s 14 -c 7 -o gpurun_out/${TAG}_cfg$k -f python tools/run_config_once.py $k > /dev/null 2>&1
   fi
 done
 for r in gpurun_out/${TAG}_cfg*.ncu-rep; do

@@ -4,10 +4,10 @@
 # usage: tools/gpu_round_refresh.sh <tag>
 TAG=${1:-r01x}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/${TAG}_pytest.txt
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/${TAG}_pytest.txt
 bash tools/gpu_profile_round.sh ${TAG} | tail -1
-python tools/bench_configs.py --steps 10 --json gpurun_out/${TAG}_configs.json 2>&1 | tail -9
-for k in 3 5; do
-  ncu --metrics gpu__time_duration.sum --clock-control none -s 34 -c 17 --csv --log-file gpurun_out/${TAG}_cfg${k}_launches.csv python tools/run_config_once.py $k > /dev/null 2>&1
-done
-python tools/bench_widening.py 2>&1 | tail -5 | tee gpurun_out/${TAG}_widening.jsonl
+timeout 900 python tools/bench_configs.py --steps 10 --parity --json gpurun_out/${TAG}_configs.json 2>&1 | tail -9
+timeout 300 bash tools/gpu_launchlist.sh ${TAG} "3 5" | tee gpurun_out/${TAG}_cfg35_launchlist.txt
+timeout 600 bash tools/gpu_capture.sh ${TAG} 3,5 > /dev/null 2>&1
+for k in 3 5; do python tools/ncu_table.py gpurun_out/${TAG}_cfg${k}_raw.csv --md > gpurun_out/${TAG}_cfg${k}_kernels.md; done
+timeout 600 python tools/bench_widening.py 2>&1 | tail -5 | tee gpurun_out/${TAG}_widening.jsonl

@@ -119,7 +119,7 @@ struct tc_context
   uint32_t *dInstanceVertexCache = nullptr, *dInstanceMidCache = nullptr;
   uint4*    dCacheClasses = nullptr;
   float*    dClassCache = nullptr;
-  uint32_t  numCacheClasses = 0, numCacheClusters = 0, allInstancesCached = 0;
+  uint32_t  numCacheClasses = 0, numCacheClusters = 0, allInstancesCached = 0, allVerticesCached = 0;
   std::vector<DeviceGeometry> geoms;
   std::vector<void*>          textures;
   std::vector<cudaArray_t>    textureArrays;
@@ -210,7 +210,7 @@ void free_scene(tc_context* c)
   c->dInstanceVertexCache = c->dInstanceMidCache = nullptr;
   c->dCacheClasses = nullptr;
   c->dClassCache = nullptr;
-  c->numCacheClasses = c->numCacheClusters = c->allInstancesCached = 0;
+  c->numCacheClasses = c->numCacheClusters = c->allInstancesCached = c->allVerticesCached = 0;
   c->instanceStates = c->blasBuildInfos = c->blasBuildSizes = c->basicClusterSizes = nullptr;
   c->dInstances = nullptr;
   c->dClusterPrefix = nullptr;
@@ -321,6 +321,7 @@ void fill_params(tc_context* c)
   p.numCacheClasses     = c->numCacheClasses;
   p.numCacheClusters    = c->numCacheClusters;
   p.allInstancesCached  = c->allInstancesCached;
+  p.allVerticesCached   = c->allVerticesCached;
   p.classCache          = c->dClassCache;
 }
 
@@ -425,7 +426,8 @@ int enqueue_build(tc_context* c)
     grid          = std::min(grid, uint32_t(c->numSMs) * 32u);
     tc::launch_cluster_classify(p, c->dEpoch, grid, uint32_t(c->numSMs * 5), s);  // count -> scan -> emit (cluster level) -> emit (triangle level) -> 2X mini vertices
     const bool anim = (c->cfg.flags & TC_FLAG_ANIMATION) != 0;
-    launches += 5 + (((c->cfg.flags & TC_FLAG_TRANSIENT_2X) && !(c->allInstancesCached && !anim)) ? 1 : 0) + ((c->numCacheClasses && !anim) ? 2 : 0);
+    launches += 4 + ((c->allVerticesCached && !anim) ? 0 : 1) + (((c->cfg.flags & TC_FLAG_TRANSIENT_2X) && !(c->allInstancesCached && !anim)) ? 1 : 0)
+                + ((c->numCacheClasses && !anim) ? 2 : 0);
   }
   {
     StageScope sc(c, TC_STAGE_SPLIT);
@@ -889,10 +891,14 @@ TC_API int tc_set_scene(tc_context* c, const tc_geometry* geoms, uint32_t numGeo
           mcache[i] = classes[slot[classOf[i]]].w;
         }
     }
-    c->allInstancesCached = 1;
+    c->allInstancesCached = c->allVerticesCached = 1;
     for(uint32_t i = 0; i < numInstances; i++)
+    {
       if(vcache[i] == ~0u || mcache[i] == ~0u)
         c->allInstancesCached = 0;
+      if(vcache[i] == ~0u)
+        c->allVerticesCached = 0;
+    }
     c->numCacheClasses  = uint32_t(classes.size());
     c->numCacheClusters = clusterItems;
     if((rc = dalloc(c->dInstanceVertexCache, size_t(numInstances) * 4)) || (rc = dalloc(c->dInstanceMidCache, size_t(numInstances) * 4))

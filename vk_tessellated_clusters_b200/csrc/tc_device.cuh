@@ -112,6 +112,7 @@ struct Params
   const uint4*    cacheClasses;         // [numCacheClasses] {representative instance, first cluster item (prefix), vertex base, midpoint base}
   uint32_t        numCacheClasses, numCacheClusters;  // classes, sum of their geometries' clusters
   uint32_t        allInstancesCached;   // every instance has both caches: k_mini_vertices has nothing to do
+  uint32_t        allVerticesCached;    // every instance has the vertex cache: k_cluster_vertices has nothing to do
   float*          classCache;
   tc_shard_counts*      shardCounts;   // summary record for the multi-GPU allgather, written by the last CTA of k_instantiate
   // peer-mailbox exchange (tess_clusters.h): world <= 1 = off

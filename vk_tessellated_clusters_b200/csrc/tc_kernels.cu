@@ -3850,7 +3850,8 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
     launch_pdl(k_cluster_classify<2>, grid, CLASSIFY_THREADS, smem, s, p);
   if(p.numCacheClasses && !(p.flags & TC_FLAG_ANIMATION))
     launch_pdl(k_cluster_copies, miniGrid / 5 * 8, 256, 0, s, p);  // copies of cached classes: 8 CTAs of 256 threads per SM (4 resident)
-  {  // displaced cluster-vertex copies recorded by the cluster-level emit kernel
+  if(!(p.allVerticesCached && !(p.flags & TC_FLAG_ANIMATION)))
+  {  // displaced cluster-vertex copies recorded by the cluster-level emit kernel, for instances without a cached displacement class
     const uint32_t cvGrid = miniGrid / 5 * 2;  // 2 CTAs of 256 threads per SM
     if(p.numTextures == 0)
       launch_pdl(k_cluster_vertices<0>, cvGrid, 256, 0, s, p);
