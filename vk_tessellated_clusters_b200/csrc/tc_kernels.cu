@@ -1,14 +1,14 @@
 // tc_kernels.cu -- hand-written sm_100a kernels of the per-frame tessellation path.
 //
 // Stage map (reference shader -> kernel here), all cited relative to /root/reference:
-//   rt.cpp:412-419 resets                         -> k_frame_setup
-//   instances_classify.comp.glsl                  -> k_instances_classify
-//   clusters_cull.comp.glsl + BUILD_SETUP_CLASSIFY-> k_clusters_cull
-//   cluster_classify.comp.glsl + BUILD_SETUP_SPLIT-> k_cluster_classify   (persistent, decoupled look-back scan)
+//   rt.cpp:412-419 resets + instances_classify.comp.glsl + clusters_cull.comp.glsl + BUILD_SETUP_CLASSIFY -> k_frame_begin (one launch)
+//   cluster_classify.comp.glsl + BUILD_SETUP_SPLIT-> k_cluster_classify<0..3> + k_classify_scan (count -> scan -> emit), k_cluster_vertices,
+//                                                    k_mini_vertices; k_class_cache / k_cluster_copies for instanced geometry
 //   triangle_split.comp.glsl + SPLIT_PASS / INSTANTIATE_TESS setup -> k_triangle_split (one launch per pass)
 //   triangle_tess_template_instantiate.comp.glsl + BUILD_SETUP_BUILD_BLAS -> k_instantiate
-//   blas_setup_insertion.comp.glsl                -> k_blas_setup
+//   blas_setup_insertion.comp.glsl                -> k_blas_segments + k_blas_setup
 //   blas_clusters_insert.comp.glsl                -> k_blas_insert
+//   (multi-GPU) the counts exchange                -> k_instantiate's epilogue (peer stores) + k_shard_resolve (side stream)
 //
 // Where the reference appends with global atomics (nondeterministic order) these kernels assign offsets with
 // prefix sums in the canonical order documented in DESIGN.md, so every output buffer is bit-reproducible and
