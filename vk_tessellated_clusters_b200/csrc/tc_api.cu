@@ -423,7 +423,10 @@ int enqueue_build(tc_context* c)
     // count / emit have no inter-CTA ordering (grid-stride over clusters); cap the grid so that the per-CTA epilogue
     // (statistics atomics + fence) stays negligible for scenes with millions of clusters
     uint32_t grid = std::max(1u, (std::min(c->totalClusters, c->maxVisible) + tc::classify_tile_clusters() - 1) / tc::classify_tile_clusters());
-    grid          = std::min(grid, uint32_t(c->numSMs) * 32u);
+    // CTAs per SM the grid is capped at, measured per scene size (profiles/r02_notes.md): few CTAs whose warps loop beat many
+    // one-cluster-per-warp CTAs on small scenes (no CTA relaunch per wave), large scenes want the finer interleave
+    const uint32_t gridMult = c->totalClusters < 32768u ? 8u : (c->totalClusters < 524288u ? 16u : 32u);
+    grid          = std::min(grid, uint32_t(c->numSMs) * gridMult);
     tc::launch_cluster_classify(p, c->dEpoch, grid, uint32_t(c->numSMs * 5), s);  // count -> scan -> emit (cluster level) -> emit (triangle level) -> 2X mini vertices
     const bool anim = (c->cfg.flags & TC_FLAG_ANIMATION) != 0;
     launches += 4 + ((c->allVerticesCached && !anim) ? 0 : 1) + (((c->cfg.flags & TC_FLAG_TRANSIENT_2X) && !(c->allInstancesCached && !anim)) ? 1 : 0)
