@@ -1,1 +1,2 @@
-for i in 1 2; do timeout 300 bash tools/gpu_cfgs.sh r02w 3,5; done
+timeout 400 python -m pytest tests -m gpu -x -q -k "parity_case or config5 or config3 or culling or properties" 2>&1 | tail -3
+timeout 300 bash tools/gpu_cfgs.sh r02z 2,3,5

@@ -91,6 +91,7 @@ struct tc_context
   uint32_t          shardRank = 0, shardWorld = 0, shardFrameBase = 0;
   uint64_t          peerMailbox[TC_MAX_SHARDS] = {};
   // peer-mailbox exchange: the resolve kernel of every frame runs on its own stream (tc_kernels.cu, k_shard_resolve)
+  tc::ClassifyFork  fork;                                // vertex-work side branch of the classify DAG (own stream + events)
   cudaStream_t      shardStream = nullptr;
   cudaEvent_t       shardFrameEv = nullptr;              // frame enqueued on the main stream
   cudaEvent_t       shardResolveEv[TC_SHARD_RING]{};     // resolve of frame f done, slot f % TC_SHARD_RING
@@ -427,7 +428,7 @@ int enqueue_build(tc_context* c)
     // one-cluster-per-warp CTAs on small scenes (no CTA relaunch per wave), large scenes want the finer interleave
     const uint32_t gridMult = c->totalClusters < 32768u ? 8u : (c->totalClusters < 524288u ? 16u : 32u);
     grid          = std::min(grid, uint32_t(c->numSMs) * gridMult);
-    tc::launch_cluster_classify(p, c->dEpoch, grid, uint32_t(c->numSMs * 5), s);  // count -> scan -> emit (cluster level) -> emit (triangle level) -> 2X mini vertices
+    tc::launch_cluster_classify(p, c->dEpoch, grid, uint32_t(c->numSMs * 5), s, c->timers ? tc::ClassifyFork{} : c->fork);  // (stage timers: everything in order on one stream)
     const bool anim = (c->cfg.flags & TC_FLAG_ANIMATION) != 0;
     launches += 4 + ((c->allVerticesCached && !anim) ? 0 : 1) + (((c->cfg.flags & TC_FLAG_TRANSIENT_2X) && !(c->allInstancesCached && !anim)) ? 1 : 0)
                 + ((c->numCacheClasses && !anim) ? 2 : 0);
@@ -453,6 +454,8 @@ int enqueue_build(tc_context* c)
     tc::launch_instantiate(p, c->dEpoch, uint32_t(c->numSMs), c->occ, s);
     launches += 1;
   }
+  if(!c->timers && c->fork.side)
+    CUDA_TRY(cudaStreamWaitEvent(s, c->fork.evJoin, 0));  // vertex-work branch of the classify DAG rejoins: the build half is complete
   c->lastLaunches = launches;  // (the shard summary for the multi-GPU allgather is written by k_instantiate's last CTA)
   CUDA_TRY(cudaGetLastError());
   return TC_OK;
@@ -557,6 +560,11 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   c->hFrame = c->hFrameRing;
   for(uint32_t i = 0; i < tc_context::kStagingSlots; i++)
     TRY_CUDA(cudaEventCreateWithFlags(&c->stagingEv[i], cudaEventDisableTiming));
+#ifndef TC_NO_FORK
+  TRY_CUDA(cudaStreamCreateWithFlags(&c->fork.side, cudaStreamNonBlocking));
+  for(cudaEvent_t* e : {&c->fork.evCount, &c->fork.evCache, &c->fork.evCluster, &c->fork.evTriangle, &c->fork.evJoin})
+    TRY_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+#endif
   TRY_CUDA(cudaStreamCreateWithFlags(&c->shardStream, cudaStreamNonBlocking));
   TRY_CUDA(cudaEventCreateWithFlags(&c->shardFrameEv, cudaEventDisableTiming));
   for(uint32_t i = 0; i < TC_SHARD_RING; i++)
@@ -630,6 +638,14 @@ TC_API void tc_destroy(tc_context* c)
   free_scene(c);
   dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dClusterVertexDst); dfree(c->dTriWorkList); dfree(c->dFrame);
   dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState); dfree(c->dBatchState); dfree(c->dTransVertexOffsets); dfree(c->dMailbox); dfree(c->dShardStatus);
+  if(c->fork.side)
+  {
+    cudaStreamSynchronize(c->fork.side);
+    for(cudaEvent_t e : {c->fork.evCount, c->fork.evCache, c->fork.evCluster, c->fork.evTriangle, c->fork.evJoin})
+      if(e)
+        cudaEventDestroy(e);
+    cudaStreamDestroy(c->fork.side);
+  }
   if(c->shardStream)
     cudaStreamSynchronize(c->shardStream);
   if(c->hFrameRing)

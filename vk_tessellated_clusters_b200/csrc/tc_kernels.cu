@@ -57,6 +57,12 @@ enum
   SLOT_INSTANTIATE = 16
 };
 
+__device__ __forceinline__ uint32_t lanemask_le()
+{
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+  return m;
+}
 __device__ __forceinline__ uint32_t lo32(unsigned long long v) { return uint32_t(v); }
 __device__ __forceinline__ uint32_t hi32(unsigned long long v) { return uint32_t(v >> 32); }
 
@@ -1143,16 +1149,17 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
             entry = tess_entry(p, cfg);
           uint32_t numTris          = mini ? entry.numTriangles : 0;
           uint32_t numTrisInclusive = warp_inclusive_add(numTris);
-          // first lane of my batch = the mini lane whose offsetMini == batchIdx*8
-          uint32_t miniRankTarget = batchIdx * miniBatch;
-          // lane index of the n-th set bit in voteMini
-          uint32_t startLane = __fns(voteMini, 0, miniRankTarget + 1);
-          uint32_t lastRank  = min(miniRankTarget + miniBatch, nMini) - 1;
-          uint32_t lastLane  = __fns(voteMini, 0, lastRank + 1);
-          if(!mini)
+          // first / last lane of my batch.  Batches are runs of 8 consecutive mini triangles by rank, so the first lane is the
+          // nearest batch leader (rank % 8 == 0) at or below this lane and the last one is the last mini lane before the next
+          // leader: two ballot masks and a few bit operations (the n-th-set-bit search __fns costs ~50 instructions a call)
+          const uint32_t leaderMask = __ballot_sync(0xffffffffu, mini && relMini == 0);
+          const uint32_t leadersAbove = leaderMask & ~lanemask_le();
+          const uint32_t belowNext    = leadersAbove ? ((1u << (__ffs(leadersAbove) - 1)) - 1u) : 0xffffffffu;  // lanes before the next batch
+          uint32_t startLane = 0, lastLane = 0;
+          if(mini)
           {
-            startLane = 0;
-            lastLane  = 0;
+            startLane = 31u - __clz(leaderMask & lanemask_le());
+            lastLane  = 31u - __clz(voteMini & belowNext);
           }
           uint32_t firstTris     = __shfl_sync(0xffffffffu, numTrisInclusive - numTris, startLane);
           uint32_t lastBatchTris = __shfl_sync(0xffffffffu, numTrisInclusive, lastLane);
@@ -2503,12 +2510,6 @@ constexpr int INST_STAGES      = TC_INST_STAGES;
 template <int TEX>
 constexpr int inst_warp_words() { return 32 * RecWords<TEX>::value + INST_STAGES * INST_STAGE_WORDS; }  // 56-word records, 1 stage: 2372 words = 9488 B per warp
 
-__device__ __forceinline__ uint32_t lanemask_le()
-{
-  uint32_t m;
-  asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
-  return m;
-}
 
 // Bulk (TMA engine) copy shared -> global: the staged vertices leave the SM without LDS/STG instructions, i.e. without
 // wavefronts on the LSU data pipe (the kernel's busiest unit).
@@ -3828,54 +3829,97 @@ void launch_frame_begin(const Params& p, const tc_SceneBuilding* tmpl, const flo
   launch_pdl(k_frame_begin, 1 + instanceCtas + cullCtas + numSMs * 2, FRAME_BEGIN_THREADS, 0, s, p, tmpl, viewPosOverride, epochCounter, instanceCtas, cullCtas);
 }
 
-void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, uint32_t miniGrid, cudaStream_t s)
+// cluster_classify as a small DAG.  The emit kernels only RECORD vertex work (destinations, build records); generating / copying
+// those vertices depends on nothing that follows in the frame, so it runs on a side branch (`fork.side`, joined by the caller at the
+// end of the build half) next to the triangle-level emit, the split passes and instantiate:
+//   main: count -> scan -> emit(cluster) ------------------> emit(triangle) -> [split, instantiate: caller] -> join
+//   side:   \-> k_class_cache (evCache) -> [after emit(cluster)] k_cluster_copies, k_cluster_vertices -> [after emit(triangle)] k_mini_vertices (evJoin)
+// The copies stream at memory speed while the emit / split kernels are latency bound: config 3 0.873 -> ms see profiles/r02_notes.md.
+// Under stream capture the same calls build the forked graph.  fork.side == nullptr: everything in order on `s`.
+void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, uint32_t miniGrid, cudaStream_t s, const ClassifyFork& fork)
 {
   const size_t smem = classify_smem_bytes(p.clusterVertices, p.clusterTriangles);
+  const bool   anim = (p.flags & TC_FLAG_ANIMATION) != 0;
+  const bool   cached = p.numCacheClasses != 0 && !anim;
+  const bool   forked = fork.side != nullptr;
+  cudaStream_t v = forked ? fork.side : s;  // the stream of the vertex work
   launch_pdl(k_cluster_classify<0>, grid, CLASSIFY_THREADS, smem, s, p);
-  launch_pdl(k_classify_scan, 148 * 3, CSCAN_THREADS, 0, s, p, epochCounter);  // 3 CTAs per SM at 80 registers; tiles are handed out by ticket
-  if(p.numCacheClasses && !(p.flags & TC_FLAG_ANIMATION))
+  if(forked)
+  {
+    cudaEventRecord(fork.evCount, s);
+    cudaStreamWaitEvent(v, fork.evCount, 0);
+  }
+  if(cached)
   {  // instancing-aware cache of displaced cluster vertices / base-edge midpoints: one warp per cluster of every cached class
     const uint32_t ccGrid = (p.numCacheClusters + 7) / 8 < miniGrid / 5 * 8 ? (p.numCacheClusters + 7) / 8 : miniGrid / 5 * 8;
     if(p.numTextures == 0)
-      launch_pdl(k_class_cache<0>, ccGrid, 256, 0, s, p);
+      launch_pdl(k_class_cache<0>, ccGrid, 256, 0, v, p);
     else if(p.numTextures == 1)
-      launch_pdl(k_class_cache<1>, ccGrid, 256, 0, s, p);
+      launch_pdl(k_class_cache<1>, ccGrid, 256, 0, v, p);
     else
-      launch_pdl(k_class_cache<2>, ccGrid, 256, 0, s, p);
+      launch_pdl(k_class_cache<2>, ccGrid, 256, 0, v, p);
+    if(forked)
+      cudaEventRecord(fork.evCache, v);
   }
+  launch_pdl(k_classify_scan, 148 * 3, CSCAN_THREADS, 0, s, p, epochCounter);  // 3 CTAs per SM at 80 registers; tiles are handed out by ticket
   launch_pdl(k_cluster_classify<1>, grid, CLASSIFY_THREADS, smem, s, p);
-  if(p.numCacheClasses && (p.flags & TC_FLAG_TRANSIENT_2X) && !(p.flags & TC_FLAG_ANIMATION))
+  if(forked)
+  {
+    cudaEventRecord(fork.evCluster, s);
+    cudaStreamWaitEvent(v, fork.evCluster, 0);
+  }
+  // (the vertex branch is enqueued first when everything runs on one stream: order is irrelevant for correctness)
+  auto vertexWorkOfClusterLevel = [&]() {
+    if(cached)
+#ifndef TC_COPIES_CTAS
+#define TC_COPIES_CTAS 8
+#endif
+      launch_pdl(k_cluster_copies, miniGrid / 5 * (forked ? TC_COPIES_CTAS : 8), 256, 0, v, p);  // copies of cached classes: CTAs of 256 threads per SM (4 fit)
+    if(!(p.allVerticesCached && !anim))
+    {  // displaced cluster-vertex copies recorded by the cluster-level emit kernel, for instances without a cached displacement class
+      const uint32_t cvGrid = miniGrid / 5 * 2;  // 2 CTAs of 256 threads per SM
+      if(p.numTextures == 0)
+        launch_pdl(k_cluster_vertices<0>, cvGrid, 256, 0, v, p);
+      else if(p.numTextures == 1)
+        launch_pdl(k_cluster_vertices<1>, cvGrid, 256, 0, v, p);
+      else
+        launch_pdl(k_cluster_vertices<2>, cvGrid, 256, 0, v, p);
+    }
+  };
+  if(forked)
+    vertexWorkOfClusterLevel();
+  if(cached && (p.flags & TC_FLAG_TRANSIENT_2X))
+  {
+    if(forked)
+      cudaStreamWaitEvent(s, fork.evCache, 0);  // the triangle-level emit copies 2X vertices from the cache
     launch_pdl(k_cluster_classify<3>, grid, CLASSIFY_THREADS, smem, s, p);
+  }
   else
     launch_pdl(k_cluster_classify<2>, grid, CLASSIFY_THREADS, smem, s, p);
-  if(p.numCacheClasses && !(p.flags & TC_FLAG_ANIMATION))
-    launch_pdl(k_cluster_copies, miniGrid / 5 * 8, 256, 0, s, p);  // copies of cached classes: 8 CTAs of 256 threads per SM (4 resident)
-  if(!(p.allVerticesCached && !(p.flags & TC_FLAG_ANIMATION)))
-  {  // displaced cluster-vertex copies recorded by the cluster-level emit kernel, for instances without a cached displacement class
-    const uint32_t cvGrid = miniGrid / 5 * 2;  // 2 CTAs of 256 threads per SM
-    if(p.numTextures == 0)
-      launch_pdl(k_cluster_vertices<0>, cvGrid, 256, 0, s, p);
-    else if(p.numTextures == 1)
-      launch_pdl(k_cluster_vertices<1>, cvGrid, 256, 0, s, p);
-    else
-      launch_pdl(k_cluster_vertices<2>, cvGrid, 256, 0, s, p);
-  }
-  if((p.flags & TC_FLAG_TRANSIENT_2X) && !(p.allInstancesCached && !(p.flags & TC_FLAG_ANIMATION)))
+  if(!forked)
+    vertexWorkOfClusterLevel();
+  if((p.flags & TC_FLAG_TRANSIENT_2X) && !(p.allInstancesCached && !anim))
   {  // vertices of the 2X mini batches of instances without a cached displacement class (the others were copied inline)
+    if(forked)
+    {
+      cudaEventRecord(fork.evTriangle, s);
+      cudaStreamWaitEvent(v, fork.evTriangle, 0);
+    }
     const int    tex  = p.numTextures == 0 ? 0 : (p.numTextures == 1 ? 1 : 2);
-    const bool   anim = (p.flags & TC_FLAG_ANIMATION) != 0;
     const size_t ms   = 0;
     const uint32_t mg = miniGrid / 5 * 6;  // 6 CTAs of 4 warps per SM (78 registers)
     switch(tex * 2 + int(anim))
     {
-      case 0: launch_pdl(k_mini_vertices<0, false>, mg, MINI_WARPS * 32, ms, s, p); break;
-      case 1: launch_pdl(k_mini_vertices<0, true>, mg, MINI_WARPS * 32, ms, s, p); break;
-      case 2: launch_pdl(k_mini_vertices<1, false>, mg, MINI_WARPS * 32, ms, s, p); break;
-      case 3: launch_pdl(k_mini_vertices<1, true>, mg, MINI_WARPS * 32, ms, s, p); break;
-      case 4: launch_pdl(k_mini_vertices<2, false>, mg, MINI_WARPS * 32, ms, s, p); break;
-      default: launch_pdl(k_mini_vertices<2, true>, mg, MINI_WARPS * 32, ms, s, p); break;
+      case 0: launch_pdl(k_mini_vertices<0, false>, mg, MINI_WARPS * 32, ms, v, p); break;
+      case 1: launch_pdl(k_mini_vertices<0, true>, mg, MINI_WARPS * 32, ms, v, p); break;
+      case 2: launch_pdl(k_mini_vertices<1, false>, mg, MINI_WARPS * 32, ms, v, p); break;
+      case 3: launch_pdl(k_mini_vertices<1, true>, mg, MINI_WARPS * 32, ms, v, p); break;
+      case 4: launch_pdl(k_mini_vertices<2, false>, mg, MINI_WARPS * 32, ms, v, p); break;
+      default: launch_pdl(k_mini_vertices<2, true>, mg, MINI_WARPS * 32, ms, v, p); break;
     }
   }
+  if(forked)
+    cudaEventRecord(fork.evJoin, v);  // the caller makes `s` wait for it at the end of the build half
 }
 void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32_t pass, bool lastPass, uint32_t grid, cudaStream_t s)
 {

@@ -43,7 +43,13 @@ uint32_t lookback16_tiles_needed(uint32_t maxItems);
 size_t   frame_state_bytes();
 
 void launch_frame_begin(const Params& p, const tc_SceneBuilding* tmpl, const float* viewPosOverride, uint32_t* epochCounter, uint32_t numSMs, cudaStream_t s);
-void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, uint32_t miniGrid, cudaStream_t s);
+// side branch of the classify DAG (launch_cluster_classify): vertex generation / copies next to the emit, split and instantiate kernels
+struct ClassifyFork
+{
+  cudaStream_t side = nullptr;  // nullptr: no fork
+  cudaEvent_t  evCount = nullptr, evCache = nullptr, evCluster = nullptr, evTriangle = nullptr, evJoin = nullptr;
+};
+void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, uint32_t miniGrid, cudaStream_t s, const ClassifyFork& fork);
 void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32_t pass, bool lastPass, uint32_t grid, cudaStream_t s);
 void launch_instantiate(const Params& p, const uint32_t* epochCounter, uint32_t numSMs, const KernelOccupancy& occ, cudaStream_t s);
 void launch_blas(const Params& p, const uint32_t* epochCounter, uint32_t numSegmentsMax, uint32_t grid, cudaStream_t s);
