@@ -186,6 +186,54 @@ def test_peer_mailbox_exchange_two_ranks_one_gpu(table):
         g.close()
 
 
+def test_peer_mailbox_exchange_two_real_gpus(table):
+    """The same exchange over REAL peers when the box has two GPUs (skipped otherwise; tools/gpu_multi.sh covers the multi-process
+    case with IPC handles): one context per device in this process, peer access enabled both ways, the mailboxes plain device
+    pointers (unified addressing) -- every rank's instantiate kernel stores its record into the other GPU's mailbox over NVLink."""
+    import ctypes as C
+
+    from tests.scene_cases import case
+    from vk_tessellated_clusters_b200 import sharding
+
+    rt = C.CDLL("libcudart.so.12")
+    n = C.c_int()
+    assert rt.cudaGetDeviceCount(C.byref(n)) == 0
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    for a, b in ((0, 1), (1, 0)):
+        assert rt.cudaSetDevice(a) == 0
+        rc = rt.cudaDeviceEnablePeerAccess(b, 0)
+        assert rc in (0, 704), rc  # 704: already enabled
+    scenes = [case("mini")[0], case("split")[0]]
+    fcs, cfg0 = case("mini")[1], case("mini")[2]
+    gpus = []
+    for dev, scene in enumerate(scenes):
+        cfg = api.Config(numVisibleClusterBits=cfg0.numVisibleClusterBits, numPartTriangleBits=cfg0.numPartTriangleBits,
+                         numSplitTriangleBits=cfg0.numSplitTriangleBits, numGeneratedVerticesBits=cfg0.numGeneratedVerticesBits)
+        cfg.device = dev
+        g = api.TessClusters(cfg)
+        g.set_tess_table(table)
+        g.set_scene(scene)
+        gpus.append(g)
+    boxes = [g.device_shard_mailbox() for g in gpus]
+    for r, g in enumerate(gpus):
+        g.set_shard_peers(r, 2, boxes)
+    for frame in range(40):  # well past the mailbox ring, no host synchronisation in between
+        for g in gpus:
+            g.frame_graph(fcs)
+    recs = [g.shard_gathered() for g in gpus]
+    assert not recs[0][1] and not recs[1][1] and np.array_equal(recs[0][0], recs[1][0])
+    cnt = [sharding.unpack_shard_counts(w) for w in recs[0][0]]
+    for r, g in enumerate(gpus):
+        rb, sb = g.readback()
+        assert cnt[r]["blasClusterCounter"] == int(sb["tempInstantiateCounter"]) + int(sb["transBuildCounter"]) > 0
+        ranges = g.global_blas_ranges()
+        assert int(ranges["globalInstanceID"][0]) == sum(c["numInstances"] for c in cnt[:r])
+        assert int(ranges["globalFirstReference"][0]) == sum(c["blasClusterCounter"] for c in cnt[:r])
+    for g in gpus:
+        g.close()
+
+
 def _instance_multisets(gpu, sb, first_global=0):
     """{global instance id: sorted list of (kind, payload)} of every CLAS the frame generated, resolved so that nothing depends
     on allocation order or on the shard: template instantiations by (clusterIdOffset tag, template address, part record),
