@@ -3136,10 +3136,35 @@ __global__ void __launch_bounds__(256) k_blas_insert(Params p)
       const uint4      sz4 = __ldcs(reinterpret_cast<const uint4*>(sizes + j0));
       const ulonglong2 a01 = __ldcs(reinterpret_cast<const ulonglong2*>(addrs + j0));
       const ulonglong2 a23 = __ldcs(reinterpret_cast<const ulonglong2*>(addrs + j0 + 2));
-      blas_insert_one(p, segs, N, isTrans, j0 + 0, id4.x, a01.x);
-      blas_insert_one(p, segs, N, isTrans, j0 + 1, id4.y, a01.y);
-      blas_insert_one(p, segs, N, isTrans, j0 + 2, id4.z, a23.x);
-      blas_insert_one(p, segs, N, isTrans, j0 + 3, id4.w, a23.y);
+      uint32_t s = 0;
+      if(isTrans)
+        s = segs.count - 1;
+      else
+        while(s + 2 < segs.count && j0 >= segs.end[s])
+          s++;
+      if(id4.x == id4.w && (isTrans || j0 + 3 < segs.end[s]))
+      {  // the common case: four consecutive CLAS of one instance inside one segment (ids are sorted inside a segment) take
+         // consecutive places in that instance's list: one rank lookup instead of four
+        const uint32_t idx = p.rankBase[size_t(s) * (N + 1) + id4.x] + (j0 - p.segLo[size_t(s) * (N + 1) + id4.x]);
+        const tc_BlasBuildInfo* blas = reinterpret_cast<const tc_BlasBuildInfo*>(p.build->blasBuildInfos);
+        unsigned long long*     dst  = reinterpret_cast<unsigned long long*>(blas[id4.x].clusterReferences) + idx;
+        if((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)
+        {
+          reinterpret_cast<ulonglong2*>(dst)[0] = a01;
+          reinterpret_cast<ulonglong2*>(dst)[1] = a23;
+        }
+        else
+        {
+          dst[0] = a01.x; dst[1] = a01.y; dst[2] = a23.x; dst[3] = a23.y;
+        }
+      }
+      else
+      {
+        blas_insert_one(p, segs, N, isTrans, j0 + 0, id4.x, a01.x);
+        blas_insert_one(p, segs, N, isTrans, j0 + 1, id4.y, a01.y);
+        blas_insert_one(p, segs, N, isTrans, j0 + 2, id4.z, a23.x);
+        blas_insert_one(p, segs, N, isTrans, j0 + 3, id4.w, a23.y);
+      }
       mySize += (unsigned long long)sz4.x + sz4.y + sz4.z + sz4.w;
     }
     else
