@@ -2803,8 +2803,11 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
       const uint32_t itEnd    = __shfl_sync(0xffffffffu, t0 + cnt, lastLane);
       const size_t   itFloat0 = tileFloat0 + size_t(itStart) * 3;
       const uint32_t shift    = uint32_t(itFloat0 & 3);  // keep shared and global 16-byte phases equal
-      static_assert(INST_SLOT == 6, "the slot outputs below are spelled out for 6 vertices");
+#if TC_INST_SLOT == 6
       F3 o0, o1, o2, o3, o4, o5;
+#else
+      F3 oOut[INST_SLOT];
+#endif
       if(active)
       {
         const float4*  rec  = reinterpret_cast<const float4*>(recBase + part * REC_WORDS);
@@ -2831,7 +2834,13 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
           for(int i = 0; i < INST_SLOT; i++)
             o[i] = ripple_deform_part(p.view, p.build, p.instances, o[i], partIdx);
         }
+#if TC_INST_SLOT == 6
         o0 = o[0]; o1 = o[1]; o2 = o[2]; o3 = o[3]; o4 = o[4]; o5 = o[5];
+#else
+#pragma unroll
+        for(int i = 0; i < INST_SLOT; i++)
+          oOut[i] = o[i];
+#endif
       }
 #endif
       float* stage = stageBase + stageSel * INST_STAGE_WORDS;
@@ -2841,7 +2850,11 @@ __global__ void __launch_bounds__(INST_THREADS, TC_INST_MIN_CTAS) k_instantiate(
       __syncwarp();
       if(active)
       {
+#if TC_INST_SLOT == 6
         const F3 o[INST_SLOT] = {o0, o1, o2, o3, o4, o5};
+#else
+        const F3* o = oOut;
+#endif
         float* sdst = stage + shift + (t0 - itStart) * 3;
 #pragma unroll
         for(int i = 0; i < INST_SLOT; i++)
