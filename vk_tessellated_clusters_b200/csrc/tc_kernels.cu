@@ -630,11 +630,12 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
   const uint32_t maxV = p.clusterVertices, maxT = p.clusterTriangles;
   // per-warp regions: object positions [maxV*3], world positions + eye scale [maxV*4], factors [maxT*3], 2X mini staging
   // [32 mini triangles x 18 floats + 32 headers]
-  const uint32_t warpWords = maxV * 3 + maxV * 4 + maxT * 3 + CLASSIFY_MINI_STAGE_WORDS;
+  const uint32_t maxVa = (maxV + 3u) & ~3u, maxTa = (maxT + 3u) & ~3u;  // regions start on 16-byte boundaries (sWorld is accessed as float4)
+  const uint32_t warpWords = maxVa * 3 + maxVa * 4 + maxTa * 3 + CLASSIFY_MINI_STAGE_WORDS;
   float*    sObj     = reinterpret_cast<float*>(smemRaw) + size_t(warp) * warpWords;
-  float*    sWorld   = sObj + maxV * 3;
-  uint32_t* sFactors = reinterpret_cast<uint32_t*>(sWorld + maxV * 4);
-  float*    sMiniStage = reinterpret_cast<float*>(sFactors + maxT * 3);
+  float*    sWorld   = sObj + maxVa * 3;
+  uint32_t* sFactors = reinterpret_cast<uint32_t*>(sWorld + maxVa * 4);
+  float*    sMiniStage = reinterpret_cast<float*>(sFactors + maxTa * 3);
   uint2*    sMiniHdr   = reinterpret_cast<uint2*>(sMiniStage + 32 * TC_TESS_2X_MINI_VERTICES * 3);
   __shared__ uint32_t whereTbl[48];
 
@@ -3818,7 +3819,8 @@ size_t instantiate_smem_bytes(int tex) { return size_t(INST_WARPS) * (tex == 2 ?
 
 size_t classify_smem_bytes(uint32_t clusterVertices, uint32_t clusterTriangles)
 {
-  return size_t(CLASSIFY_WARPS) * (size_t(clusterVertices) * 7 + size_t(clusterTriangles) * 3 + CLASSIFY_MINI_STAGE_WORDS) * 4;
+  const size_t va = (size_t(clusterVertices) + 3) & ~size_t(3), ta = (size_t(clusterTriangles) + 3) & ~size_t(3);
+  return size_t(CLASSIFY_WARPS) * (va * 7 + ta * 3 + CLASSIFY_MINI_STAGE_WORDS) * 4;
 }
 
 int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, KernelOccupancy* occ)
