@@ -6,7 +6,7 @@ import pytest
 
 from tests.parity_utils import compare_frame, make_pair
 from tests.scene_cases import ALL_CASES, case
-from vk_tessellated_clusters_b200 import api
+from vk_tessellated_clusters_b200 import api, scenes as S
 
 pytestmark = pytest.mark.gpu
 
@@ -21,6 +21,38 @@ def test_parity_case(name, table, oracle_lib):
             orc.frame(fcs)
             stats = compare_frame(gpu, orc, scene_scale=scene.radius)
         assert stats["triangles"] > 0
+    finally:
+        gpu.close()
+        orc.close()
+
+
+@pytest.mark.parametrize("limits", [(30, 42), (33, 50), (45, 64)])
+def test_cluster_limits_that_are_not_multiples_of_four(limits, table, oracle_lib):
+    """tc_config.clusterVertices / clusterTriangles size the per-warp shared-memory regions of cluster_classify; limits that are not
+    multiples of four must not misalign them (the world positions are accessed as float4).  Plane of 5x4-quad tiles: 40 triangles, 30
+    vertices per cluster, factors from 1 to beyond 11 so that every route (full, 1X, 2X, part, split) is taken."""
+    cv, ct = limits
+    g = S.make_grid_plane(35, tile=(5, 4))
+    g.displacement_index, g.displacement_scale = 0, 0.02
+    scene = S._scene([g], S.make_instances([g], [0], [np.eye(4)]), [S.value_noise_texture(64)], cv=cv, ct=ct)
+    r = scene.radius
+    fc = S.make_frame_constants(scene.center + np.array([0.0, -1.05 * r, 0.12 * r]), scene.center + np.array([0.0, 0.3 * r, 0.0]), up=(0, 0, 1), near=0.001 * r,
+                                far=100 * r, tess_rate_pixels=4.0)
+    fc["tessRate"] = np.float32(1.0)
+    raw = S._max_raw_factor(scene, fc)
+    cfg = api.Config(clusterVertices=cv, clusterTriangles=ct, numVisibleClusterBits=10, numPartTriangleBits=16, numSplitTriangleBits=12, numGeneratedVerticesBits=22)
+    gpu, orc = make_pair(scene, table, cfg)
+    try:
+        seen = {"trans": 0, "splits": 0, "parts": 0}
+        for max_factor in (4.45, 40.45):  # low: full / 1X / 2X / part routes; high: split
+            fc["tessRate"] = np.float32(max_factor / raw)
+            fcs = S.frame_pair(fc)
+            gpu.frame(fcs)
+            orc.frame(fcs)
+            stats = compare_frame(gpu, orc, scene_scale=scene.radius)
+            for k in seen:
+                seen[k] += stats[k]
+        assert seen["parts"] > 0 and seen["splits"] > 0 and seen["trans"] > 0
     finally:
         gpu.close()
         orc.close()
