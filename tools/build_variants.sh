@@ -12,7 +12,7 @@ for spec in "$@"; do
     tmp=$(mktemp -d)
     nvcc -gencode arch=compute_100a,code=sm_100a $flags -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden --expt-relaxed-constexpr -c tc_kernels.cu -o $tmp/k.o
     nvcc -gencode arch=compute_100a,code=sm_100a $flags -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden --expt-relaxed-constexpr -c tc_api.cu -o $tmp/a.o
-    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/libtess_$name.so $tmp/k.o $tmp/a.o
+    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/libtess_$name.so $tmp/k.o $tmp/a.o tc_clusterize.o
     rm -rf $tmp
     echo "built $name ($flags)"
   ) &

@@ -72,6 +72,7 @@ struct tc_context
   uint32_t*         dFactorStash = nullptr;
   uint32_t*         dClassMeta = nullptr;
   uint32_t*         dClusterVertexDst = nullptr;
+  uint4*            dCopyDesc = nullptr;  // allocated by tc_set_scene when the scene has cached displacement classes
   uint32_t*         dTriWorkList = nullptr;
   FrameStaging*     dFrame     = nullptr;
   // Ring of pinned staging slots: a frame's constants are snapshotted into a slot at call time and copied to the device
@@ -117,7 +118,7 @@ struct tc_context
   uint32_t *         segLo = nullptr, *rankBase = nullptr;
   tc_global_blas_range* globalRanges = nullptr;
   // instancing-aware displaced-vertex cache (tc_kernels.cu, k_class_cache)
-  uint32_t *dInstanceVertexCache = nullptr, *dInstanceMidCache = nullptr;
+  uint32_t *dInstanceVertexCache = nullptr, *dInstanceMidCache = nullptr, *dInstanceCacheStride = nullptr;
   uint4*    dCacheClasses = nullptr;
   float*    dClassCache = nullptr;
   uint32_t  numCacheClasses = 0, numCacheClusters = 0, allInstancesCached = 0, allVerticesCached = 0;
@@ -207,10 +208,12 @@ void free_scene(tc_context* c)
   dfree(c->instanceStates); dfree(c->blasBuildInfos); dfree(c->blasBuildSizes); dfree(c->basicClusterSizes);
   dfree(c->dInstances); dfree(c->dClusterPrefix); dfree(c->segLo); dfree(c->rankBase); dfree(c->globalRanges);
   c->globalRanges = nullptr;
-  dfree(c->dInstanceVertexCache); dfree(c->dInstanceMidCache); dfree(c->dCacheClasses); dfree(c->dClassCache);
-  c->dInstanceVertexCache = c->dInstanceMidCache = nullptr;
+  dfree(c->dInstanceVertexCache); dfree(c->dInstanceMidCache); dfree(c->dInstanceCacheStride); dfree(c->dCacheClasses); dfree(c->dClassCache);
+  c->dInstanceVertexCache = c->dInstanceMidCache = c->dInstanceCacheStride = nullptr;
   c->dCacheClasses = nullptr;
   c->dClassCache = nullptr;
+  dfree(c->dCopyDesc);
+  c->dCopyDesc = nullptr;
   c->numCacheClasses = c->numCacheClusters = c->allInstancesCached = c->allVerticesCached = 0;
   c->instanceStates = c->blasBuildInfos = c->blasBuildSizes = c->basicClusterSizes = nullptr;
   c->dInstances = nullptr;
@@ -303,6 +306,7 @@ void fill_params(tc_context* c)
   p.factorStash        = c->dFactorStash;
   p.classMeta          = c->dClassMeta;
   p.clusterVertexDst   = c->dClusterVertexDst;
+  p.copyDesc           = c->dCopyDesc;
   p.triWorkList        = c->dTriWorkList;
   p.segLo              = c->segLo;
   p.rankBase           = c->rankBase;
@@ -318,6 +322,7 @@ void fill_params(tc_context* c)
   p.globalRanges       = c->globalRanges;
   p.instanceVertexCache = c->dInstanceVertexCache;
   p.instanceMidCache    = c->dInstanceMidCache;
+  p.instanceCacheStride = c->dInstanceCacheStride;
   p.cacheClasses        = c->dCacheClasses;
   p.numCacheClasses     = c->numCacheClasses;
   p.numCacheClusters    = c->numCacheClusters;
@@ -561,7 +566,11 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   for(uint32_t i = 0; i < tc_context::kStagingSlots; i++)
     TRY_CUDA(cudaEventCreateWithFlags(&c->stagingEv[i], cudaEventDisableTiming));
 #ifndef TC_NO_FORK
-  TRY_CUDA(cudaStreamCreateWithFlags(&c->fork.side, cudaStreamNonBlocking));
+  {  // the vertex-work branch gets the higher priority: its light CTAs (k_cluster_copies_bulk) are placed first and the main branch fills the rest
+    int prLo = 0, prHi = 0;
+    TRY_CUDA(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+    TRY_CUDA(cudaStreamCreateWithPriority(&c->fork.side, cudaStreamNonBlocking, prHi));
+  }
   for(cudaEvent_t* e : {&c->fork.evCount, &c->fork.evCache, &c->fork.evCluster, &c->fork.evTriangle, &c->fork.evJoin})
     TRY_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 #endif
@@ -858,7 +867,7 @@ TC_API int tc_set_scene(tc_context* c, const tc_geometry* geoms, uint32_t numGeo
   {
     // Displacement classes: instances with the same geometry and displacement parameters generate identical object-space
     // cluster-vertex copies and 2X mini-triangle vertices; classes of >= 2 instances get a per-frame cache (k_class_cache).
-    std::vector<uint32_t> vcache(numInstances, ~0u), mcache(numInstances, ~0u), classOf(numInstances, ~0u);
+    std::vector<uint32_t> vcache(numInstances, ~0u), mcache(numInstances, ~0u), vstride(numInstances, 0u), classOf(numInstances, ~0u);
     std::vector<uint4>    classes;
     std::vector<uint32_t> members;
     uint64_t cacheFloat3 = 0;
@@ -885,16 +894,23 @@ TC_API int tc_set_scene(tc_context* c, const tc_geometry* geoms, uint32_t numGeo
         members[k]++;
       }
       std::vector<uint32_t> slot(reps.size(), ~0u);
-      // layout of classCache: [packed float3 vertex caches of all classes][16-byte aligned: float4 edge-midpoint caches]
+      // layout of classCache: [vertex caches of all classes][16-byte aligned: float4 edge-midpoint caches].  A class's vertex cache
+      // holds FOUR copies of its packed float3 vertices, copy k starting k floats past a 16-byte boundary (k * (stride + 1) floats
+      // after copy 0, stride a multiple of four): whatever the 16-byte phase of a cluster's slot in genVertices, one copy of the
+      // cluster's vertices has the same phase, and k_cluster_copies_bulk moves whole 16-byte granules of it with the TMA engine.
       uint64_t vertexFloat3 = 0, midFloat4 = 0;
+      std::vector<uint32_t> strideOf(reps.size(), 0u);
       for(uint32_t k = 0; k < reps.size(); k++)
       {
         const tc_geometry& g = geoms[inst[reps[k]].geometryID];
-        if(members[k] < 2 || vertexFloat3 + g.numVertices > 0x7FFF0000ull || midFloat4 + uint64_t(g.numTriangles) * 3 > 0x3FFF0000ull)
+        const uint64_t strideF = (uint64_t(g.numVertices) * 3 + 3) / 4 * 4 + 4;          // floats between copies (+1 each)
+        const uint64_t span3   = ((4 * strideF + 2) / 3 + 3) / 4 * 4;                     // float3 units, keeps the next class 16-byte aligned
+        if(members[k] < 2 || vertexFloat3 + span3 > 0x3FFF0000ull || midFloat4 + uint64_t(g.numTriangles) * 3 > 0x3FFF0000ull)
           continue;
-        slot[k] = uint32_t(classes.size());
+        slot[k]     = uint32_t(classes.size());
+        strideOf[k] = uint32_t(strideF);
         classes.push_back(make_uint4(reps[k], clusterItems, uint32_t(vertexFloat3), use2X ? uint32_t(midFloat4) : ~0u));
-        vertexFloat3 += g.numVertices;
+        vertexFloat3 += span3;
         midFloat4 += use2X ? uint64_t(g.numTriangles) * 3 : 0;
         clusterItems += g.numClusters;
       }
@@ -908,6 +924,7 @@ TC_API int tc_set_scene(tc_context* c, const tc_geometry* geoms, uint32_t numGeo
         {
           vcache[i] = classes[slot[classOf[i]]].z;
           mcache[i] = classes[slot[classOf[i]]].w;
+          vstride[i] = strideOf[classOf[i]];
         }
     }
     c->allInstancesCached = c->allVerticesCached = 1;
@@ -921,10 +938,14 @@ TC_API int tc_set_scene(tc_context* c, const tc_geometry* geoms, uint32_t numGeo
     c->numCacheClasses  = uint32_t(classes.size());
     c->numCacheClusters = clusterItems;
     if((rc = dalloc(c->dInstanceVertexCache, size_t(numInstances) * 4)) || (rc = dalloc(c->dInstanceMidCache, size_t(numInstances) * 4))
+       || (rc = dalloc(c->dInstanceCacheStride, size_t(numInstances) * 4))
        || (rc = dalloc(c->dCacheClasses, std::max<size_t>(classes.size(), 1) * sizeof(uint4))) || (rc = dalloc(c->dClassCache, std::max<uint64_t>(cacheFloat3, 1) * 12)))
       return rc;
     CUDA_TRY(cudaMemcpy(c->dInstanceVertexCache, vcache.data(), size_t(numInstances) * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(c->dInstanceMidCache, mcache.data(), size_t(numInstances) * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->dInstanceCacheStride, vstride.data(), size_t(numInstances) * 4, cudaMemcpyHostToDevice));
+    if(!classes.empty() && (rc = dalloc(c->dCopyDesc, size_t(c->maxVisible) * sizeof(uint4))))
+      return rc;
     if(!classes.empty())
       CUDA_TRY(cudaMemcpy(c->dCacheClasses, classes.data(), classes.size() * sizeof(uint4), cudaMemcpyHostToDevice));
   }

@@ -96,6 +96,7 @@ struct Params
   uint32_t* classMeta;     // [maxVisibleClusters]: number of triangles that need no tessellation (simpleCount)
   uint32_t* triWorkList;   // [maxVisibleClusters]: visible-list indices of the clusters with triangle-level work (count pass -> emit), any order
   uint32_t* clusterVertexDst;  // [maxVisibleClusters]: first vertex in genVertices of the cluster's displaced vertex copy, ~0u: none
+  uint4*    copyDesc;          // [maxVisibleClusters] cluster_copy_desc of every cluster with a displaced vertex copy; nullptr: no cached classes
   // 2X mini batches: k_mini_vertices generates the vertices from the transient build records themselves; only the batch's
   // UN-WRAPPED first vertex travels on the side (ClasBuildInfo.vertexBuffer wraps at 2^32 bytes like the reference's)
   uint32_t* transVertexOffsets;  // [maxGenClusters], indexed like transBuilds (2X batches only)
@@ -108,6 +109,7 @@ struct Params
   // the object-space result of every displaced cluster vertex and of every displaced base-edge midpoint (what the full-cluster /
   // 1X copies and the 2X mini triangles are made of), so it is evaluated once per frame per such CLASS and copied per instance.
   const uint32_t* instanceVertexCache;  // [numInstances] first float3 of the instance's class in classCache (geometry vertex order), ~0u: not cached
+  const uint32_t* instanceCacheStride;  // [numInstances] floats between the four phase copies of the class's vertex cache (k_cluster_copies), 0: not cached
   const uint32_t* instanceMidCache;     // [numInstances] first float3 of the class's edge midpoints (3 per geometry triangle), ~0u: none
   const uint4*    cacheClasses;         // [numCacheClasses] {representative instance, first cluster item (prefix), vertex base, midpoint base}
   uint32_t        numCacheClasses, numCacheClusters;  // classes, sum of their geometries' clusters

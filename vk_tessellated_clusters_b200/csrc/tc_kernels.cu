@@ -3,7 +3,7 @@
 // Stage map (reference shader -> kernel here), all cited relative to /root/reference:
 //   rt.cpp:412-419 resets + instances_classify.comp.glsl + clusters_cull.comp.glsl + BUILD_SETUP_CLASSIFY -> k_frame_begin (one launch)
 //   cluster_classify.comp.glsl + BUILD_SETUP_SPLIT-> k_cluster_classify<0..3> + k_classify_scan (count -> scan -> emit), k_cluster_vertices,
-//                                                    k_mini_vertices; k_class_cache / k_cluster_copies for instanced geometry
+//                                                    k_mini_vertices; k_class_cache / k_cluster_copies_bulk for instanced geometry
 //   triangle_split.comp.glsl + SPLIT_PASS / INSTANTIATE_TESS setup -> k_triangle_split (one launch per pass)
 //   triangle_tess_template_instantiate.comp.glsl + BUILD_SETUP_BUILD_BLAS -> k_instantiate
 //   blas_setup_insertion.comp.glsl                -> k_blas_segments + k_blas_setup
@@ -619,6 +619,20 @@ struct ClassifyShared  // only the CTA epilogue's statistics: one cluster per wa
 #ifndef TC_CLASSIFY0_MIN_CTAS
 #define TC_CLASSIFY0_MIN_CTAS 4  // count pass: 64 registers, 32 warps per SM (one cluster per warp in flight: latency bound)
 #endif
+// What k_cluster_copies_bulk needs to move one cluster's displaced vertices from the class cache: {first vertex in genVertices,
+// first float of the cache copy whose 16-byte phase equals the destination's, number of floats (0: instance not cached), -}
+__device__ __forceinline__ uint4 cluster_copy_desc(const Params& p, uint32_t instanceID, uint32_t firstVertex, uint32_t numVertices, uint32_t vertexOffset,
+                                                   unsigned long long genVerticesAddr)
+{
+  const uint32_t cls = __ldg(&p.instanceVertexCache[instanceID]);
+  if(cls == ~0u)
+    return make_uint4(vertexOffset, 0u, 0u, 0u);
+  const uint32_t src0 = (cls + firstVertex) * 3u;  // copy 0 (classCache itself is 256-byte aligned)
+  const uint32_t lead = (uint32_t(genVerticesAddr >> 2) + vertexOffset * 3u) & 3u;
+  const uint32_t k    = (lead - src0) & 3u;
+  return make_uint4(vertexOffset, src0 + k * (__ldg(&p.instanceCacheStride[instanceID]) + 1u), numVertices * 3u, 0u);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_CTAS : (MODE == 0 ? TC_CLASSIFY0_MIN_CTAS : 3)) k_cluster_classify(Params p)
 {
@@ -764,6 +778,8 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
           if(p.driverStandin)
             tempClusterSizes[tempOffset] = size;
           p.clusterVertexDst[vi] = vertexOffset;
+          if(p.copyDesc)
+            p.copyDesc[vi] = cluster_copy_desc(p, cinfoL.instanceID, chL.z, nV, vertexOffset, genVerticesAddr);
           okL = true;
         }
       }
@@ -1037,7 +1053,11 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
 
           // displaced copy of the cluster vertices (:465-488): generated by k_cluster_vertices, here only its destination
           if(lane == 0)
+          {
             p.clusterVertexDst[vi] = vertexOffset;
+            if(p.copyDesc)
+              p.copyDesc[vi] = cluster_copy_desc(p, instanceID, firstLocalVertex, numVertices, vertexOffset, genVerticesAddr);
+          }
           if(transient1X)
           {  // ordered export of the simple triangles (:497-534)
             uint32_t indexOffset      = (vertexOffset + numVertices) * 4u * 3u;
@@ -1472,13 +1492,18 @@ __global__ void __launch_bounds__(256) k_class_cache(Params p)
     const int   ti = TEX != 0 ? inst.displacementIndex : -1;
     const bool  displaced = TEX != 0 && ti >= 0;
     const float scale = inst.displacementScale * viewScale, offset = inst.displacementOffset + viewOffset;
+    const size_t copyStride = size_t(__ldg(&p.instanceCacheStride[cls.x])) + 1;
     for(uint32_t v = lane; v < nV; v += 32)
     {  // displaced copy of a cluster vertex: exactly k_cluster_vertices' arithmetic
       F3 o = ld_f3(positions, first + v);
       if(displaced)
         o = displace_along<TEX>(p, uniformTex, uniW, uniH, ti, o, ld_f3(normals, first + v), __ldg(texcoords + first + v), scale, offset);
       float* d = p.classCache + size_t(cls.z + first + v) * 3;
-      d[0] = o.x; d[1] = o.y; d[2] = o.z;
+#pragma unroll
+      for(int k = 0; k < 4; k++, d += copyStride)  // the four 16-byte phases (tc_set_scene: layout of classCache)
+      {
+        d[0] = o.x; d[1] = o.y; d[2] = o.z;
+      }
     }
     if(needMid && cls.w != ~0u)
     {
@@ -1506,75 +1531,6 @@ __global__ void __launch_bounds__(256) k_class_cache(Params p)
           cp = displace_along<TEX>(p, uniformTex, uniW, uniH, ti, cp, Nk + Nq, make_float2((Tk.x + Tq.x) * 0.5f, (Tk.y + Tq.y) * 0.5f), scale, offset);
         }
         reinterpret_cast<float4*>(p.classCache)[cls.w + (ch.w / 3u + tri) * 3u + k] = make_float4(cp.x, cp.y, cp.z, 0.0f);
-      }
-    }
-  }
-}
-
-// Displaced cluster-vertex copies of instances whose displacement class is cached (k_class_cache): a plain float stream from the
-// cache (L2 resident: one geometry) to the cluster's slot in genVertices.  A warp takes 32 consecutive visible clusters (lane =
-// cluster: destination + descriptor), compacts the ones with a copy and streams FOUR clusters at a time: for each of them the 32
-// lanes cover 128 contiguous bytes per instruction (eight-lane groups per cluster were measured LSU-wavefront bound: every
-// instruction touched eight lines), and all loads of the four clusters -- up to 24 per lane -- are in flight before the first store.
-__global__ void __launch_bounds__(256) k_cluster_copies(Params p)
-{
-  pdl_prologue();
-  if(p.state->clusterLevelWork == 0)
-    return;
-  const uint32_t lane = lane_id(), warpsTotal = gridDim.x * (blockDim.x >> 5);
-  const uint32_t numVisible = p.build->visibleClusterCounter;
-  const tc_ClusterInfo* visibleClusters = reinterpret_cast<const tc_ClusterInfo*>(p.build->visibleClusters);
-  float* __restrict__ genVertices = reinterpret_cast<float*>(p.build->genVertices);
-  const float* __restrict__ cache = p.classCache;
-  for(uint32_t chunk = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; chunk < numVisible; chunk += warpsTotal * 32)
-  {
-    uint32_t dstL = 0, srcL = 0, numL = 0;
-    if(chunk + lane < numVisible)
-    {
-      const uint32_t d = __ldcs(&p.clusterVertexDst[chunk + lane]);
-      if(d != ~0u)
-      {
-        const tc_ClusterInfo ci = visibleClusters[chunk + lane];
-        const uint32_t cls = __ldg(&p.instanceVertexCache[ci.instanceID]);
-        if(cls != ~0u)
-        {
-          const uint4 ch = __ldg(reinterpret_cast<const uint4*>(p.instances[ci.instanceID].clusters) + ci.clusterID);
-          dstL = d; srcL = cls + ch.z; numL = (ch.x & 0xFFFF) * 3;
-        }
-      }
-    }
-    uint32_t remaining = __ballot_sync(0xffffffffu, numL != 0);  // lanes that hold a cluster with a copy
-    while(remaining)
-    {
-      const float* src[4];
-      float*       dst[4];
-      uint32_t     nF[4], maxF = 0;
-#pragma unroll
-      for(int j = 0; j < 4; j++)
-      {
-        const bool     have = remaining != 0;
-        const uint32_t from = have ? __ffs(remaining) - 1 : 0u;
-        remaining &= remaining - 1;  // (0 stays 0)
-        const uint32_t n = __shfl_sync(0xffffffffu, numL, from), s = __shfl_sync(0xffffffffu, srcL, from), d = __shfl_sync(0xffffffffu, dstL, from);
-        nF[j]  = have ? n : 0u;
-        src[j] = cache + size_t(s) * 3;
-        dst[j] = genVertices + size_t(d) * 3;
-        maxF   = max(maxF, nF[j]);
-      }
-      for(uint32_t f0 = lane; f0 < maxF; f0 += 192)
-      {
-        float x[4][6];
-#pragma unroll
-        for(int j = 0; j < 4; j++)
-#pragma unroll
-          for(int k = 0; k < 6; k++)
-            x[j][k] = f0 + k * 32 < nF[j] ? __ldg(src[j] + f0 + k * 32) : 0.0f;
-#pragma unroll
-        for(int j = 0; j < 4; j++)
-#pragma unroll
-          for(int k = 0; k < 6; k++)
-            if(f0 + k * 32 < nF[j])
-              __stcs(dst[j] + f0 + k * 32, x[j][k]);
       }
     }
   }
@@ -1611,7 +1567,7 @@ __global__ void __launch_bounds__(256, 2) k_cluster_vertices(Params p)
       }
     }
     if(numL && __ldg(&p.instanceVertexCache[instL]) != ~0u)
-      numL = 0;  // instance of a cached displacement class: k_cluster_copies streams its copy from the cache
+      numL = 0;  // instance of a cached displacement class: k_cluster_copies_bulk streams its copy from the cache
     const uint32_t endV = warp_inclusive_add(numL), startV = endV - numL, total = __shfl_sync(0xffffffffu, endV, 31);
     // lane = vertex of the chunk's flat vertex list
     for(uint32_t t0 = 0; t0 < total; t0 += 32 * U)
@@ -2553,6 +2509,216 @@ __device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint
       bulk_store(dst + head, stage + shift + head, bodyVec << 4, policy);
     bulk_commit();
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_cluster_copies_bulk: the cluster copies of cached displacement classes moved by the TMA engine.
+//
+// A copy kernel that stages the vertices in registers (four clusters per warp, 128-bit loads and stores from the phase-matched
+// cache copy) needs the whole SM to stream: 155 us for config 3's 645 MB, bound by the SM's 32 B/clk store port to the crossbar
+// at 65 % (a pure store stream reaches ~71 %), and it time-sliced with the main branch's kernels instead of running next to
+// them (r02_notes.md).  Here the data in flight sits in shared memory and no thread ever touches it.  Consecutive visible
+// clusters of one instance are consecutive in the class cache AND (prefix sums in canonical order) in genVertices, so a warp
+// merges the clusters of a batch into RUNS -- usually one per batch -- and moves each run with ONE bulk load cache -> shared
+// (the 16-byte granules that cover the run in the phase-matched copy, completion on an mbarrier) and ONE bulk store shared ->
+// genVertices of the whole granules; the <= 3 floats at either end of a run that share a granule with a neighbour are read
+// back from shared memory and stored as scalars.  Two buffers per warp: the loads of batch b+1 are issued before the warp
+// waits for batch b.  Eight warps of 45 registers per SM do what took 32 warps of 64: the kernel stays resident beside the
+// classify CTAs of the main branch.
+// ------------------------------------------------------------------------------------------------------------
+#ifndef TC_COPYB_BATCH_BYTES
+#define TC_COPYB_BATCH_BYTES 6656
+#endif
+#ifndef TC_COPYB_WARPS
+#define TC_COPYB_WARPS 4
+#endif
+constexpr int COPYB_WARPS = TC_COPYB_WARPS;
+constexpr int COPYB_RINGS = 2;
+struct CopyRunDesc
+{
+  float*   dst;     // first float of the run in genVertices
+  uint32_t n;       // floats
+  uint32_t offset;  // byte offset of the run's first granule in the batch buffer
+  uint32_t lead;    // floats of the first granule that belong to whatever precedes the run
+  uint32_t pad[3];
+};
+static_assert(sizeof(CopyRunDesc) == 32, "descriptor size");
+__host__ __device__ inline uint32_t copyb_slot_bytes(uint32_t clusterVertices) { return (clusterVertices * 12u + 15u) / 16u * 16u + 32u; }
+__host__ __device__ inline uint32_t copyb_batch(uint32_t clusterVertices)  // clusters per batch: <= 26 KB of vertices
+{
+  const uint32_t b = uint32_t(TC_COPYB_BATCH_BYTES) / copyb_slot_bytes(clusterVertices);
+  return b < 1u ? 1u : (b > 32u ? 32u : b);
+}
+__host__ __device__ inline uint32_t copyb_ring_bytes(uint32_t clusterVertices)
+{
+  return copyb_batch(clusterVertices) * (copyb_slot_bytes(clusterVertices) + uint32_t(sizeof(CopyRunDesc))) + 16u;
+}
+__host__ __device__ inline uint32_t copyb_warp_bytes(uint32_t clusterVertices) { return COPYB_RINGS * copyb_ring_bytes(clusterVertices); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+
+#ifndef TC_COPYB_MIN_CTAS
+#define TC_COPYB_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(COPYB_WARPS * 32, TC_COPYB_MIN_CTAS) k_cluster_copies_bulk(Params p)
+{
+  pdl_prologue();
+  if(p.state->clusterLevelWork == 0)
+    return;
+  extern __shared__ __align__(128) unsigned char copySmem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t slotBytes = copyb_slot_bytes(p.clusterVertices), batch = copyb_batch(p.clusterVertices);
+  const uint32_t ringBytes = copyb_ring_bytes(p.clusterVertices);
+  unsigned char* warpBase  = copySmem + size_t(warp) * COPYB_RINGS * ringBytes;
+  // ring r: [batch * slotBytes of vertices][batch run descriptors][mbarrier]
+  auto ring_data  = [&](uint32_t r) { return warpBase + size_t(r) * ringBytes; };
+  auto ring_descs = [&](uint32_t r) { return reinterpret_cast<CopyRunDesc*>(warpBase + size_t(r) * ringBytes + size_t(batch) * slotBytes); };
+  auto ring_bar   = [&](uint32_t r) { return uint32_t(__cvta_generic_to_shared(warpBase + size_t(r) * ringBytes + size_t(batch) * (slotBytes + sizeof(CopyRunDesc)))); };
+  if(lane < COPYB_RINGS)
+    mbar_init(ring_bar(lane), 1u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  fence_async_shared();
+  __syncwarp();
+
+  const uint32_t numVisible = p.build->visibleClusterCounter;
+  float* __restrict__ genVertices = reinterpret_cast<float*>(p.build->genVertices);
+  const float* __restrict__ cache = p.classCache;
+  const uint64_t streamPolicy = policy_evict_first();
+  const uint32_t warpsTotal = gridDim.x * COPYB_WARPS;
+
+  uint32_t seq = 0;       // batches issued by this warp
+  uint32_t runsPrev = 0;  // runs of batch seq-1 (loads in flight, not yet stored); 0: none
+  // batch `b` (ring b % 2, phase parity (b / 2) & 1): wait for its loads, store whole granules in bulk, run ends as scalars
+  auto retire = [&](uint32_t b, uint32_t runs) {
+    const uint32_t r = b % COPYB_RINGS, parity = (b / COPYB_RINGS) & 1u, bar = ring_bar(r);
+    while(!mbar_try_wait(bar, parity))
+      ;
+    const CopyRunDesc*   descs = ring_descs(r);
+    const unsigned char* data  = ring_data(r);
+    if(lane < runs)
+    {
+      const CopyRunDesc d = descs[lane];
+      const uint32_t g0 = d.lead ? 1u : 0u, g1 = (d.lead + d.n) >> 2;
+      if(g1 > g0)
+        bulk_store(d.dst - d.lead + g0 * 4u, reinterpret_cast<const float*>(data + d.offset) + g0 * 4u, (g1 - g0) << 4, streamPolicy);
+    }
+    bulk_commit();  // every lane, every batch: the per-thread group counts stay in step
+    // end floats: pair t = (run, k): k < 3 head float k, else tail float k - 3
+    for(uint32_t t = lane; t < runs * 6u; t += 32)
+    {
+      const uint32_t run = t / 6u, k = t - run * 6u;
+      const CopyRunDesc d = descs[run];
+      const uint32_t g0 = d.lead ? 1u : 0u, g1 = (d.lead + d.n) >> 2;
+      const uint32_t headCount = d.lead ? min(4u - d.lead, d.n) : 0u;
+      const uint32_t tailCount = g1 >= g0 ? d.lead + d.n - g1 * 4u : 0u;
+      const float*   sl = reinterpret_cast<const float*>(data + d.offset);
+      if(k < 3u)
+      {
+        if(k < headCount)
+          __stcs(d.dst + k, sl[d.lead + k]);
+      }
+      else if(k - 3u < tailCount)
+        __stcs(d.dst - d.lead + g1 * 4u + (k - 3u), sl[g1 * 4u + (k - 3u)]);
+    }
+  };
+
+  uint32_t chunk = (blockIdx.x * COPYB_WARPS + warp) * 32;
+  uint32_t dstN = ~0u;
+  uint4    descN = make_uint4(0, 0, 0, 0);
+  if(chunk + lane < numVisible)
+  {
+    dstN = __ldcs(&p.clusterVertexDst[chunk + lane]);
+    descN = __ldcs(&p.copyDesc[chunk + lane]);
+  }
+  for(; chunk < numVisible; chunk += warpsTotal * 32)
+  {
+    const uint32_t dstL = dstN;
+    const uint4    desc = descN;
+    {  // the next chunk's descriptors: one coalesced load, a whole chunk ahead of its use
+      const uint32_t next = chunk + warpsTotal * 32;
+      dstN = ~0u;
+      if(next + lane < numVisible)
+      {
+        dstN = __ldcs(&p.clusterVertexDst[next + lane]);
+        descN = __ldcs(&p.copyDesc[next + lane]);
+      }
+    }
+    const bool     have  = dstL != ~0u && desc.z != 0u;
+    const uint32_t mask  = __ballot_sync(0xffffffffu, have);
+    const uint32_t count = __popc(mask), rank = __popc(mask & lanemask_lt());
+    // does this cluster continue the previous lane's run?  (same instance, next cluster: adjacent in the cache and in genVertices)
+    const uint32_t prevSrcEnd = __shfl_up_sync(0xffffffffu, desc.y + desc.z, 1), prevDstEnd = __shfl_up_sync(0xffffffffu, desc.x * 3u + desc.z, 1);
+    const bool     prevHave   = __shfl_up_sync(0xffffffffu, uint32_t(have), 1) != 0u;
+    const bool     continues  = lane > 0 && have && prevHave && prevSrcEnd == desc.y && prevDstEnd == desc.x * 3u;
+    for(uint32_t q0 = 0; q0 < count; q0 += batch)
+    {
+      const uint32_t r = seq % COPYB_RINGS, bar = ring_bar(r);
+      // the ring's previous user (batch seq-2) must have been read out of shared memory by its stores.  Every lane waits on its
+      // own groups, the warp barrier makes that hold for all runs.
+      bulk_wait_read<0>();
+      fence_async_shared();  // (this warp's scalar reads of the ring, batch seq-2, before the engine rewrites it)
+      __syncwarp();
+      const bool     mine    = have && rank >= q0 && rank < q0 + batch;
+      const bool     start   = mine && (!continues || rank == q0);
+      const uint32_t startMask = __ballot_sync(0xffffffffu, start), mineMask = __ballot_sync(0xffffffffu, mine);
+      const uint32_t incl    = warp_inclusive_add(mine ? desc.z : 0u);  // floats, running over the batch
+      // a run ends before the next start (or with the batch's last cluster): its floats = incl[end] - excl[start]
+      const uint32_t later   = startMask & ~((2u << lane) - 1u);
+      const uint32_t endLane = later ? uint32_t(__ffs(later)) - 2u : 31u - uint32_t(__clz(mineMask));
+      const uint32_t inclEnd = __shfl_sync(0xffffffffu, incl, start ? endLane : lane);
+      uint32_t bytes = 0, lead = 0, nRun = 0;
+      float*   dst = nullptr;
+      if(start)
+      {
+        nRun  = inclEnd - (incl - desc.z);
+        dst   = genVertices + size_t(desc.x) * 3;
+        lead  = uint32_t(reinterpret_cast<uintptr_t>(dst) >> 2) & 3u;
+        bytes = ((lead + nRun + 3u) >> 2) << 4;
+      }
+      const uint32_t inclBytes = warp_inclusive_add(bytes);
+      const uint32_t total = __shfl_sync(0xffffffffu, inclBytes, 31);
+      const uint32_t runs  = __popc(startMask);
+      if(start)
+      {
+        CopyRunDesc d;
+        d.dst = dst; d.n = nRun; d.offset = inclBytes - bytes; d.lead = lead;
+        d.pad[0] = d.pad[1] = d.pad[2] = 0;
+        ring_descs(r)[__popc(startMask & lanemask_lt())] = d;
+      }
+      if(lane == 0)
+        mbar_expect_tx(bar, total);
+      __syncwarp();
+      if(start)  // 16-byte aligned source: the copy was chosen for this phase
+        bulk_load(uint32_t(__cvta_generic_to_shared(ring_data(r) + (inclBytes - bytes))), cache + desc.y - lead, bytes, bar);
+      if(runsPrev)
+        retire(seq - 1, runsPrev);
+      runsPrev = runs;
+      seq++;
+    }
+  }
+  if(runsPrev)
+    retire(seq - 1, runsPrev);
+  bulk_wait_all();
 }
 
 // 5 CTAs x 4 warps = 20 warps/SM at 96 registers (measured: 16 warps at 128 registers 0.467 ms, 20 warps 0.444 ms)
@@ -3831,6 +3997,8 @@ int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, Kerne
      || cudaFuncSetAttribute(k_cluster_classify<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess
      || cudaFuncSetAttribute(k_cluster_classify<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
     return -1;
+  if(cudaFuncSetAttribute(k_cluster_copies_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(COPYB_WARPS * copyb_warp_bytes(clusterVertices))) != cudaSuccess)
+    return -1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->classify, k_cluster_classify<1>, CLASSIFY_THREADS, smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->split, k_triangle_split, SPLIT_THREADS, 0);
   const void* variants[6] = {(const void*)k_instantiate<0, false>, (const void*)k_instantiate<0, true>, (const void*)k_instantiate<1, false>,
@@ -3873,7 +4041,7 @@ void launch_frame_begin(const Params& p, const tc_SceneBuilding* tmpl, const flo
 // those vertices depends on nothing that follows in the frame, so it runs on a side branch (`fork.side`, joined by the caller at the
 // end of the build half) next to the triangle-level emit, the split passes and instantiate:
 //   main: count -> scan -> emit(cluster) ------------------> emit(triangle) -> [split, instantiate: caller] -> join
-//   side:   \-> k_class_cache (evCache) -> [after emit(cluster)] k_cluster_copies, k_cluster_vertices -> [after emit(triangle)] k_mini_vertices (evJoin)
+//   side:   \-> k_class_cache (evCache) -> [after emit(cluster)] k_cluster_copies_bulk, k_cluster_vertices -> [after emit(triangle)] k_mini_vertices (evJoin)
 // The copies stream at memory speed while the emit / split kernels are latency bound: config 3 0.873 -> ms see profiles/r02_notes.md.
 // Under stream capture the same calls build the forked graph.  fork.side == nullptr: everything in order on `s`.
 void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, uint32_t miniGrid, cudaStream_t s, const ClassifyFork& fork)
@@ -3911,10 +4079,16 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
   // (the vertex branch is enqueued first when everything runs on one stream: order is irrelevant for correctness)
   auto vertexWorkOfClusterLevel = [&]() {
     if(cached)
-#ifndef TC_COPIES_CTAS
-#define TC_COPIES_CTAS 8
+#ifndef TC_COPYB_CTAS_FORKED
+#define TC_COPYB_CTAS_FORKED 2
 #endif
-      launch_pdl(k_cluster_copies, miniGrid / 5 * (forked ? TC_COPIES_CTAS : 8), 256, 0, v, p);  // copies of cached classes: CTAs of 256 threads per SM (4 fit)
+    {  // copies of cached classes.  Forked: two light CTAs per SM beside the main branch's kernels; alone on the device (stage timers, profiler)
+       // as many as fit.  (frame ms of config 3, CTAs x warps x clusters per batch: 1x2x32 0.834, 1x4x16 0.796, 2x4x8 0.783, 4x2x8 0.787, 1x8x8 0.791,
+       // 3x4x8 0.812, 2x8x4 0.818, 2x8x2 0.875)
+      const size_t   cb = size_t(COPYB_WARPS) * copyb_warp_bytes(p.clusterVertices);
+      const uint32_t perSM = forked ? TC_COPYB_CTAS_FORKED : uint32_t(std::max<size_t>(1, std::min<size_t>(6, (224u << 10) / (cb + 1024))));
+      launch_pdl(k_cluster_copies_bulk, miniGrid / 5 * perSM, COPYB_WARPS * 32, cb, v, p);
+    }
     if(!(p.allVerticesCached && !anim))
     {  // displaced cluster-vertex copies recorded by the cluster-level emit kernel, for instances without a cached displacement class
       const uint32_t cvGrid = miniGrid / 5 * 2;  // 2 CTAs of 256 threads per SM
