@@ -118,6 +118,7 @@ struct tc_context
   uint32_t *         segLo = nullptr, *rankBase = nullptr;
   tc_global_blas_range* globalRanges = nullptr;
   // instancing-aware displaced-vertex cache (tc_kernels.cu, k_class_cache)
+  bool      capturing = false;  // enqueue_* called under stream capture (replay_graph)
   uint32_t *dInstanceVertexCache = nullptr, *dInstanceMidCache = nullptr, *dInstanceCacheStride = nullptr;
   uint4*    dCacheClasses = nullptr;
   float*    dClassCache = nullptr;
@@ -155,6 +156,10 @@ struct tc_context
 
   // graph
   cudaGraphExec_t graphExec = nullptr, graphBuild = nullptr, graphInsert = nullptr;
+  // the same graphs with k_cluster_copies_bulk inside an IF node (launch_cluster_classify): replayed while the last finished frame
+  // had no cluster-level work (*hCopyHint == 0, written by k_classify_scan into pinned host memory)
+  cudaGraphExec_t graphExecGated = nullptr, graphBuildGated = nullptr;
+  uint32_t*       hCopyHint = nullptr;
 };
 
 namespace {
@@ -224,7 +229,7 @@ void free_scene(tc_context* c)
 
 void drop_graph(tc_context* c)
 {
-  for(cudaGraphExec_t* g : {&c->graphExec, &c->graphBuild, &c->graphInsert})
+  for(cudaGraphExec_t* g : {&c->graphExec, &c->graphBuild, &c->graphInsert, &c->graphExecGated, &c->graphBuildGated})
     if(*g)
     {
       cudaGraphExecDestroy(*g);
@@ -307,6 +312,7 @@ void fill_params(tc_context* c)
   p.classMeta          = c->dClassMeta;
   p.clusterVertexDst   = c->dClusterVertexDst;
   p.copyDesc           = c->dCopyDesc;
+  p.hostCopyHint       = c->hCopyHint;
   p.triWorkList        = c->dTriWorkList;
   p.segLo              = c->segLo;
   p.rankBase           = c->rankBase;
@@ -436,7 +442,8 @@ int enqueue_build(tc_context* c)
     tc::launch_cluster_classify(p, c->dEpoch, grid, uint32_t(c->numSMs * 5), s, c->timers ? tc::ClassifyFork{} : c->fork);  // (stage timers: everything in order on one stream)
     const bool anim = (c->cfg.flags & TC_FLAG_ANIMATION) != 0;
     launches += 4 + ((c->allVerticesCached && !anim) ? 0 : 1) + (((c->cfg.flags & TC_FLAG_TRANSIENT_2X) && !(c->allInstancesCached && !anim)) ? 1 : 0)
-                + ((c->numCacheClasses && !anim) ? 2 : 0);
+                + ((c->numCacheClasses && !anim) ? 2 : 0)   // k_class_cache, k_cluster_copies_bulk
+                + ((c->numCacheClasses && !anim && c->capturing && c->fork.gateCopies) ? 1 : 0);  // k_copies_gate of the graph's IF node
   }
   {
     StageScope sc(c, TC_STAGE_SPLIT);
@@ -562,6 +569,8 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   TRY_RC(dalloc(c->dShardBase, 16));
   TRY_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->hFrameRing), sizeof(FrameStaging) * tc_context::kStagingSlots));
   memset(c->hFrameRing, 0, sizeof(FrameStaging) * tc_context::kStagingSlots);
+  TRY_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->hCopyHint), 64));
+  *c->hCopyHint = 1;
   c->hFrame = c->hFrameRing;
   for(uint32_t i = 0; i < tc_context::kStagingSlots; i++)
     TRY_CUDA(cudaEventCreateWithFlags(&c->stagingEv[i], cudaEventDisableTiming));
@@ -569,6 +578,9 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   {  // the vertex-work branch gets the higher priority: its light CTAs (k_cluster_copies_bulk) are placed first and the main branch fills the rest
     int prLo = 0, prHi = 0;
     TRY_CUDA(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+#ifdef TC_SIDE_STREAM_DEFAULT_PRIORITY
+    prHi = prLo;
+#endif
     TRY_CUDA(cudaStreamCreateWithPriority(&c->fork.side, cudaStreamNonBlocking, prHi));
   }
   for(cudaEvent_t* e : {&c->fork.evCount, &c->fork.evCache, &c->fork.evCluster, &c->fork.evTriangle, &c->fork.evJoin})
@@ -659,6 +671,8 @@ TC_API void tc_destroy(tc_context* c)
     cudaStreamSynchronize(c->shardStream);
   if(c->hFrameRing)
     cudaFreeHost(c->hFrameRing);
+  if(c->hCopyHint)
+    cudaFreeHost(c->hCopyHint);
   for(cudaEvent_t e : c->stagingEv)
     if(e)
       cudaEventDestroy(e);
@@ -1204,12 +1218,17 @@ TC_API int tc_frame(tc_context* c, const void* frameConstants, size_t strideByte
 
 namespace {
 // capture `what` (0: build half, 1: insert half, 2: whole frame) once and replay it
-int replay_graph(tc_context* c, cudaGraphExec_t& exec, int what)
+int replay_graph(tc_context* c, cudaGraphExec_t& execPlain, int what)
 {
+  // frames without cluster-level work replay the variant whose copy kernel sits behind an IF node (see tc_context::graphExecGated)
+  const bool gated = what != 1 && c->numCacheClasses != 0 && !(c->cfg.flags & TC_FLAG_ANIMATION) && *reinterpret_cast<volatile uint32_t*>(c->hCopyHint) == 0;
+  cudaGraphExec_t& exec = gated ? (what == 2 ? c->graphExecGated : c->graphBuildGated) : execPlain;
   if(!exec)
   {
     bool savedTimers = c->timers;
     c->timers        = false;
+    c->capturing     = true;
+    c->fork.gateCopies = gated;
     cudaGraph_t graph = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     int rc = what == 1 ? TC_OK : enqueue_build(c);
@@ -1217,6 +1236,7 @@ int replay_graph(tc_context* c, cudaGraphExec_t& exec, int what)
       rc = enqueue_insert(c);
     cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
     c->timers     = savedTimers;
+    c->capturing  = false;
     if(rc == TC_OK && e != cudaSuccess)
       rc = fail(TC_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
     if(rc == TC_OK && (e = cudaGraphInstantiate(&exec, graph, 0)) != cudaSuccess)

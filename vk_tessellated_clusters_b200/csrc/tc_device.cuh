@@ -97,6 +97,7 @@ struct Params
   uint32_t* triWorkList;   // [maxVisibleClusters]: visible-list indices of the clusters with triangle-level work (count pass -> emit), any order
   uint32_t* clusterVertexDst;  // [maxVisibleClusters]: first vertex in genVertices of the cluster's displaced vertex copy, ~0u: none
   uint4*    copyDesc;          // [maxVisibleClusters] cluster_copy_desc of every cluster with a displaced vertex copy; nullptr: no cached classes
+  uint32_t* hostCopyHint;      // pinned host word: clusterLevelWork of the last finished frame (graph variant choice, tc_api.cu replay_graph)
   // 2X mini batches: k_mini_vertices generates the vertices from the transient build records themselves; only the batch's
   // UN-WRAPPED first vertex travels on the side (ClasBuildInfo.vertexBuffer wraps at 2^32 bytes like the reference's)
   uint32_t* transVertexOffsets;  // [maxGenClusters], indexed like transBuilds (2X batches only)

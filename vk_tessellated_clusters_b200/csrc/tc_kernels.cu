@@ -539,8 +539,8 @@ __device__ __forceinline__ uint32_t mini_where(const uint32_t* whereTbl, uint32_
   return whereTbl[(c3 * 2u + ((cfg >> 15) & 1u)) * 3u + rot];
 }
 // the <= 6 vertices of a mini triangle of an instance with a cached displacement class: corners and edge midpoints are copies
-__device__ __forceinline__ void mini_copy_cached(const Params& p, uint32_t where, uint32_t vcache, uint32_t mcache, uint32_t firstLocalVertex, uint32_t i0, uint32_t i1,
-                                                 uint32_t i2, uint32_t geometryTriangle, float* myStage)
+__device__ __forceinline__ void mini_copy_cached(const Params& p, uint32_t where, const float* sCorners, uint32_t mcache, uint32_t i0, uint32_t i1, uint32_t i2,
+                                                 uint32_t geometryTriangle, float* myStage)
 {
   const uint32_t iv[3] = {i0, i1, i2};
 #pragma unroll
@@ -549,9 +549,9 @@ __device__ __forceinline__ void mini_copy_cached(const Params& p, uint32_t where
     const uint32_t ic = (where >> (4 * k)) & 0xFu, im = (where >> (12 + 4 * k)) & 0xFu;
     if(ic != 0xFu)
     {
-      const float* c = p.classCache + size_t(vcache + firstLocalVertex + iv[k]) * 3;
+      const float* c = sCorners + iv[k] * 3;  // the cluster's cached vertices, staged by the caller
       float* sv = myStage + ic * 3;
-      sv[0] = __ldg(c); sv[1] = __ldg(c + 1); sv[2] = __ldg(c + 2);
+      sv[0] = c[0]; sv[1] = c[1]; sv[2] = c[2];
     }
     if(im != 0xFu)
     {
@@ -899,6 +899,17 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
         if(needFactors)
           for(uint32_t i = lane; i < numTriangles * 3; i += 32)
             sFactors[i] = __ldcs(stash + i);
+        if(MODE == 3 && needFactors && use2X)
+        {  // cached displacement class: the cluster's displaced vertices are one contiguous run of the cache -- fetched once, in the same
+           // memory round trip as the factors, instead of three scalar loads per mini-triangle corner (each vertex is a corner ~6 times)
+          const uint32_t vc = __ldg(&p.instanceVertexCache[cinfo.instanceID]);
+          if(vc != ~0u)
+          {
+            const float* c = p.classCache + size_t(vc + firstLocalVertex) * 3;
+            for(uint32_t i = lane; i < numVertices * 3; i += 32)
+              sObj[i] = __ldg(c + i);
+          }
+        }
       }
       __syncwarp();
 
@@ -1209,7 +1220,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
               if(!failB)
               {
                 const uint32_t where = mini_where(whereTbl, cfg, v0);
-                mini_copy_cached(p, where, vcacheI, mcacheI, firstLocalVertex, i0, i1, i2, firstLocalTriangle / 3u + tri, sMiniStage + offsetMini * (TC_TESS_2X_MINI_VERTICES * 3));
+                mini_copy_cached(p, where, sObj, mcacheI, i0, i1, i2, firstLocalTriangle / 3u + tri, sMiniStage + offsetMini * (TC_TESS_2X_MINI_VERTICES * 3));
                 nFloats = (where >> 24) * 3u;
               }
               sMiniCnt[offsetMini] = uint8_t(nFloats);  // 0: the batch failed its allocation, nothing is written
@@ -1922,6 +1933,8 @@ __global__ void __launch_bounds__(CSCAN_THREADS) k_classify_scan(Params p, const
             ct[i] = excl.v[i];
           ct[6] = uint32_t(excl.d);
           ct[7] = uint32_t(excl.d >> 32);
+          if(p.hostCopyHint)
+            *p.hostCopyHint = p.state->clusterLevelWork;
         }
       }
     }
@@ -2719,6 +2732,13 @@ __global__ void __launch_bounds__(COPYB_WARPS * 32, TC_COPYB_MIN_CTAS) k_cluster
   if(runsPrev)
     retire(seq - 1, runsPrev);
   bulk_wait_all();
+}
+
+// condition of the graph's IF node around k_cluster_copies_bulk (launch_cluster_classify)
+__global__ void k_copies_gate(Params p, cudaGraphConditionalHandle handle)
+{
+  if(threadIdx.x == 0)
+    cudaGraphSetConditional(handle, p.state->clusterLevelWork != 0 ? 1u : 0u);
 }
 
 // 5 CTAs x 4 warps = 20 warps/SM at 96 registers (measured: 16 warps at 128 registers 0.467 ms, 20 warps 0.444 ms)
@@ -3999,6 +4019,14 @@ int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, Kerne
     return -1;
   if(cudaFuncSetAttribute(k_cluster_copies_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(COPYB_WARPS * copyb_warp_bytes(clusterVertices))) != cudaSuccess)
     return -1;
+#ifdef TC_COPYB_CARVEOUT
+  cudaFuncSetAttribute(k_cluster_copies_bulk, cudaFuncAttributePreferredSharedMemoryCarveout, TC_COPYB_CARVEOUT);
+#endif
+#ifdef TC_CLASSIFY_CARVEOUT
+  cudaFuncSetAttribute(k_cluster_classify<3>, cudaFuncAttributePreferredSharedMemoryCarveout, TC_CLASSIFY_CARVEOUT);
+  cudaFuncSetAttribute(k_cluster_classify<2>, cudaFuncAttributePreferredSharedMemoryCarveout, TC_CLASSIFY_CARVEOUT);
+  cudaFuncSetAttribute(k_cluster_classify<1>, cudaFuncAttributePreferredSharedMemoryCarveout, TC_CLASSIFY_CARVEOUT);
+#endif
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->classify, k_cluster_classify<1>, CLASSIFY_THREADS, smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->split, k_triangle_split, SPLIT_THREADS, 0);
   const void* variants[6] = {(const void*)k_instantiate<0, false>, (const void*)k_instantiate<0, true>, (const void*)k_instantiate<1, false>,
@@ -4051,6 +4079,8 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
   const bool   cached = p.numCacheClasses != 0 && !anim;
   const bool   forked = fork.side != nullptr;
   cudaStream_t v = forked ? fork.side : s;  // the stream of the vertex work
+  cudaGraphConditionalHandle copiesGate{};
+  bool                       gated = false;
   launch_pdl(k_cluster_classify<0>, grid, CLASSIFY_THREADS, smem, s, p);
   if(forked)
   {
@@ -4068,6 +4098,18 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
       launch_pdl(k_class_cache<2>, ccGrid, 256, 0, v, p);
     if(forked)
       cudaEventRecord(fork.evCache, v);
+    // condition of the IF node around k_cluster_copies_bulk (below): known since the count pass, set here so that nothing but the
+    // node itself sits between the cluster-level emit and the copies
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaGraph_t             g  = nullptr;
+#ifndef TC_COPIES_NO_GATE
+    if(fork.gateCopies && cudaStreamGetCaptureInfo(v, &cs, nullptr, &g, nullptr, nullptr) == cudaSuccess && cs == cudaStreamCaptureStatusActive
+       && cudaGraphConditionalHandleCreate(&copiesGate, g, 0, cudaGraphCondAssignDefault) == cudaSuccess)
+    {
+      k_copies_gate<<<1, 32, 0, v>>>(p, copiesGate);
+      gated = true;
+    }
+#endif
   }
   launch_pdl(k_classify_scan, 148 * 3, CSCAN_THREADS, 0, s, p, epochCounter);  // 3 CTAs per SM at 80 registers; tiles are handed out by ticket
   launch_pdl(k_cluster_classify<1>, grid, CLASSIFY_THREADS, smem, s, p);
@@ -4087,7 +4129,43 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
        // 3x4x8 0.812, 2x8x4 0.818, 2x8x2 0.875)
       const size_t   cb = size_t(COPYB_WARPS) * copyb_warp_bytes(p.clusterVertices);
       const uint32_t perSM = forked ? TC_COPYB_CTAS_FORKED : uint32_t(std::max<size_t>(1, std::min<size_t>(6, (224u << 10) / (cb + 1024))));
-      launch_pdl(k_cluster_copies_bulk, miniGrid / 5 * perSM, COPYB_WARPS * 32, cb, v, p);
+      const uint32_t cgrid = miniGrid / 5 * perSM;
+      // While the frame is being captured into a graph the kernel goes into the body of an IF node whose condition a one-thread gate kernel sets
+      // from the count pass's result: a frame without cluster-level work must not even launch it -- its CTAs would leave at once, but they
+      // switch every SM to the large shared-memory carve-out first, and the triangle-level emit that starts next to them then runs its whole
+      // duration with 28 KB of L1 (measured on config 5: 1.49 -> 1.56 ms).
+      bool inGraph = false;
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaGraph_t             g  = nullptr;
+      const cudaGraphNode_t*  deps = nullptr;
+      size_t                  nd = 0;
+      if(gated)
+      {
+        cudaGraphConditionalHandle handle = copiesGate;
+        cudaGraphNodeParams np = {};
+        np.type                = cudaGraphNodeTypeConditional;
+        np.conditional.handle  = handle;
+        np.conditional.type    = cudaGraphCondTypeIf;
+        np.conditional.size    = 1;
+        cudaGraphNode_t cnode  = nullptr;
+        if(cudaStreamGetCaptureInfo(v, &cs, nullptr, &g, &deps, &nd) == cudaSuccess && cudaGraphAddNode(&cnode, g, deps, nd, &np) == cudaSuccess)
+        {
+          Params               pc = p;
+          void*                args[] = {&pc};
+          cudaKernelNodeParams kp = {};
+          kp.func           = reinterpret_cast<void*>(k_cluster_copies_bulk);
+          kp.gridDim        = dim3(cgrid);
+          kp.blockDim       = dim3(COPYB_WARPS * 32);
+          kp.sharedMemBytes = unsigned(cb);
+          kp.kernelParams   = args;
+          cudaGraphNode_t kn = nullptr;
+          if(cudaGraphAddKernelNode(&kn, np.conditional.phGraph_out[0], nullptr, 0, &kp) == cudaSuccess
+             && cudaStreamUpdateCaptureDependencies(v, &cnode, 1, cudaStreamSetCaptureDependencies) == cudaSuccess)
+            inGraph = true;
+        }
+      }
+      if(!inGraph)
+        launch_pdl(k_cluster_copies_bulk, cgrid, COPYB_WARPS * 32, cb, v, p);
     }
     if(!(p.allVerticesCached && !anim))
     {  // displaced cluster-vertex copies recorded by the cluster-level emit kernel, for instances without a cached displacement class

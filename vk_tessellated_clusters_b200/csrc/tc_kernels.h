@@ -48,6 +48,7 @@ struct ClassifyFork
 {
   cudaStream_t side = nullptr;  // nullptr: no fork
   cudaEvent_t  evCount = nullptr, evCache = nullptr, evCluster = nullptr, evTriangle = nullptr, evJoin = nullptr;
+  bool         gateCopies = false;  // under stream capture: k_cluster_copies_bulk goes behind an IF node (frames without cluster-level work)
 };
 void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint32_t grid, uint32_t miniGrid, cudaStream_t s, const ClassifyFork& fork);
 void launch_triangle_split(const Params& p, const uint32_t* epochCounter, uint32_t pass, bool lastPass, uint32_t grid, cudaStream_t s);
