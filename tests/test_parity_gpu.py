@@ -388,3 +388,39 @@ def test_meshlet_triangles_bit_exact(name, table, oracle_lib):
     finally:
         gpu.close()
         orc.close()
+
+
+@pytest.mark.gpu
+def test_instanced_scene_alternating_cluster_level_work_through_the_frame_graph(table, oracle_lib):
+    """Instanced geometry (cached displacement class): far frames are all full clusters -- their vertices are bulk copies from the
+    class cache (k_cluster_copies_bulk, runs of adjacent clusters) -- near frames have no cluster-level work at all.  The library
+    replays one of two graph variants depending on the last finished frame (copy kernel plain / behind an IF node), so the
+    sequence below crosses every transition; every frame must match the oracle."""
+    g = S.make_icosphere(4)
+    g.displacement_index, g.displacement_scale = 0, 0.03
+    mats = [S.translation((2.6 * (i % 3), 2.6 * (i // 3), 0.0)) for i in range(6)]
+    scene = S._scene([g], S.make_instances([g], [0] * 6, mats), [S.value_noise_texture(64)])
+    r = scene.radius
+    cfg = api.Config(numVisibleClusterBits=12, numPartTriangleBits=20, numSplitTriangleBits=16, numGeneratedVerticesBits=25, numGeneratedClusterMegs=2048)
+    gpu, orc = make_pair(scene, table, cfg)
+    try:
+        def frame(dist, px):
+            fc = S.make_frame_constants(scene.center + np.array([0.3, -dist * r, 0.4 * r]), scene.center, up=(0, 0, 1), near=0.01 * r, far=400 * r, tess_rate_pixels=px)
+            return S.frame_pair(fc)
+
+        # far: 480 full clusters; near: parts + splits only; mixed: full clusters in broken runs next to 1X / 2X / part work
+        far, near, mixed = frame(60.0, 8.0), frame(1.6, 2.0), frame(3.0, 8.0)
+        seen_copy = seen_none = 0
+        for fcs in (far, far, near, near, near, mixed, far, near, mixed):
+            gpu.frame_graph(fcs)
+            orc.frame(fcs)
+            compare_frame(gpu, orc, scene_scale=scene.radius)
+            rb, _ = gpu.readback()
+            if int(rb["numFullClusters"]) > 0:
+                seen_copy += 1
+            else:
+                seen_none += 1
+        assert seen_copy == 5 and seen_none == 4
+    finally:
+        gpu.close()
+        orc.close()
