@@ -233,6 +233,68 @@ __device__ __forceinline__ void tess_factors(const FactorConsts& c, F3 a, F3 b, 
   f[2] = (uint32_t)fminf(fmaxf(fz, 1.0f), 32768.0f);
 }
 
+// ---- filtered evaluation of tess_getTessFactors (count pass) ----
+// The factors are integers: rint of a product of correctly rounded operations.  Like an exact geometric predicate they are first
+// evaluated with the SFU approximations of the square roots and of the reciprocal (1 instruction each instead of ~9 for the
+// IEEE sequences) and accepted when the result cannot depend on the approximation: sqrt.approx and rcp.approx are within
+// 2^-23 (relative) of the true value, the IEEE results within 2^-24, every product and fused sum rounds once more in either
+// chain; the approximate product u is therefore within 10 x 2^-23 of the exact v.  With a threefold margin, rint(u) == rint(v) whenever u is
+// further than 32 x 2^-23 x u from a half-integer (and below 0.45, or above the clamp, without looking).  Otherwise -- about one
+// triangle in 10^4 -- the triangle is recomputed with the exact sequence (tess_factors_exact_slow).
+constexpr float TC_FILTER_REL = 32.0f / 8388608.0f;
+__device__ __forceinline__ float approx_sqrt(float x)
+{
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float approx_rcp(float x)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float tess_eye_scale_approx(const FactorConsts& c, F3 w)
+{
+  const F3 d = xsub3(w, c.eye);
+  return approx_rcp(fmaxf(c.nearPlane, approx_sqrt(fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z)))));  // (fused: two more roundings of 2^-24, inside the margin)
+}
+// (arguments and result by value: an array parameter would put the caller's factors into local memory on every path)
+static __device__ __noinline__ unsigned long long tess_factors_exact_slow(F3 eye, float nearPlane, float viewportY, float tessRate, F3 a, F3 b, F3 cc)
+{
+  FactorConsts c;
+  c.eye = eye; c.nearPlane = nearPlane; c.viewportY = viewportY; c.tessRate = tessRate;
+  uint32_t f[3];
+  tess_factors(c, a, b, cc, tess_eye_scale(c, a), tess_eye_scale(c, b), tess_eye_scale(c, cc), f);
+  return (unsigned long long)f[0] | ((unsigned long long)f[1] << 16) | ((unsigned long long)f[2] << 32);
+}
+// k = rint(u): certain when u is further than the margin from the half-integers on either side of k
+__device__ __forceinline__ bool tess_filter_certain(float u, float k) { return fabsf(u - k) < fmaf(-TC_FILTER_REL, u, 0.5f) || u > 40000.0f; }
+// rA..rC: tess_eye_scale_approx of the three points
+__device__ __forceinline__ void tess_factors_filtered(const FactorConsts& c, F3 a, F3 b, F3 cc, float rA, float rB, float rC, uint32_t f[3])
+{
+  const F3    dab = xsub3(a, b), dbc = xsub3(b, cc), dca = xsub3(cc, a);  // (exact: differences of nearby points cancel)
+  const float vr = c.viewportY * c.tessRate;
+  const float ux = approx_sqrt(fmaf(dab.x, dab.x, fmaf(dab.y, dab.y, dab.z * dab.z))) * fmaxf(rA, rB) * vr;
+  const float uy = approx_sqrt(fmaf(dbc.x, dbc.x, fmaf(dbc.y, dbc.y, dbc.z * dbc.z))) * fmaxf(rB, rC) * vr;
+  const float uz = approx_sqrt(fmaf(dca.x, dca.x, fmaf(dca.y, dca.y, dca.z * dca.z))) * fmaxf(rC, rA) * vr;
+  if(fmaxf(ux, fmaxf(uy, uz)) < 0.45f)
+  {  // every edge rounds to 0 -> clamped to 1 (also when a product is NaN: the exact sequence clamps NaN to 1 as well)
+    f[0] = f[1] = f[2] = 1u;
+    return;
+  }
+  const float kx = rintf(ux), ky = rintf(uy), kz = rintf(uz);
+  if(tess_filter_certain(ux, kx) && tess_filter_certain(uy, ky) && tess_filter_certain(uz, kz))
+  {
+    f[0] = (uint32_t)fminf(fmaxf(kx, 1.0f), 32768.0f);
+    f[1] = (uint32_t)fminf(fmaxf(ky, 1.0f), 32768.0f);
+    f[2] = (uint32_t)fminf(fmaxf(kz, 1.0f), 32768.0f);
+    return;
+  }
+  const unsigned long long packed = tess_factors_exact_slow(c.eye, c.nearPlane, c.viewportY, c.tessRate, a, b, cc);
+  f[0] = uint32_t(packed) & 0xFFFFu; f[1] = uint32_t(packed >> 16) & 0xFFFFu; f[2] = uint32_t(packed >> 32) & 0xFFFFu;
+}
+
 __device__ __forceinline__ uint32_t tess_splitFactor(uint32_t f, uint32_t maxSplit)  // tessellation.glsl:101-104
 {
   return min((f + TC_TESSTABLE_SIZE - 1) / TC_TESSTABLE_SIZE, maxSplit);

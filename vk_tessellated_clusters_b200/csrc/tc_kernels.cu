@@ -856,7 +856,11 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
           {
             F3 o = ld_f3(positions, firstLocalVertex + v);
             F3 w = xtransform_point(m, o);
+#ifdef TC_EXACT_COUNT_FACTORS
             float d = tess_eye_scale(fcst, w);  // 1 / max(near, eye distance)
+#else
+            float d = tess_eye_scale_approx(fcst, w);  // filtered evaluation (tess_factors_filtered)
+#endif
             reinterpret_cast<float4*>(sWorld)[v] = make_float4(w.x, w.y, w.z, d);
           }
         }
@@ -882,7 +886,11 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_
                 i0 = __ldg(localTriangles + tri * 3 + 0); i1 = __ldg(localTriangles + tri * 3 + 1); i2 = __ldg(localTriangles + tri * 3 + 2);
               }
               float4   a = reinterpret_cast<const float4*>(sWorld)[i0], b = reinterpret_cast<const float4*>(sWorld)[i1], c = reinterpret_cast<const float4*>(sWorld)[i2];
+#ifdef TC_EXACT_COUNT_FACTORS
               tess_factors(fcst, F3{a.x, a.y, a.z}, F3{b.x, b.y, b.z}, F3{c.x, c.y, c.z}, a.w, b.w, c.w, f);
+#else
+              tess_factors_filtered(fcst, F3{a.x, a.y, a.z}, F3{b.x, b.y, b.z}, F3{c.x, c.y, c.z}, a.w, b.w, c.w, f);
+#endif
               const uint32_t w0 = f[0] | (i0 << 24), w1 = f[1] | (i1 << 24), w2 = f[2] | (i2 << 24);
               sFactors[tri * 3 + 0] = w0; sFactors[tri * 3 + 1] = w1; sFactors[tri * 3 + 2] = w2;
               stash[tri * 3 + 0] = w0; stash[tri * 3 + 1] = w1; stash[tri * 3 + 2] = w2;
