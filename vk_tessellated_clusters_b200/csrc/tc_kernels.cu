@@ -1877,13 +1877,40 @@ __global__ void __launch_bounds__(MINI_WARPS * 32, 6) k_mini_vertices(Params p)
   }
 }
 
+// Tile descriptor of the classify scan: the 32-byte tuple travels as three self-validating 16-byte words {flag, a, b, c} (one L2
+// transaction each, like the 16-byte descriptors of the split / instantiate scans), once as the tile's aggregate and once as its
+// inclusive prefix: no acquire / release fences, hence no L1 invalidations (CCTL.IVALL) or membars on the chain.  A reader
+// accepts a state only when all three of its words carry that state's flag of the current epoch.
+__device__ __forceinline__ void scan_desc_store(LookbackDesc* d, uint32_t which, uint32_t flag, const ScanTuple& t)
+{
+  uint4* w = reinterpret_cast<uint4*>(d) + which * 3;
+  st_desc16(w + 0, make_uint4(flag, t.v[0], t.v[1], t.v[2]));
+  st_desc16(w + 1, make_uint4(flag, t.v[3], t.v[4], t.v[5]));
+  st_desc16(w + 2, make_uint4(flag, uint32_t(t.d), uint32_t(t.d >> 32), 0u));
+}
+__device__ __forceinline__ bool scan_desc_load(const LookbackDesc* d, uint32_t which, uint32_t flag, ScanTuple& t)
+{
+  const uint4* w = reinterpret_cast<const uint4*>(d) + which * 3;
+  const uint4  a = ld_desc16(w + 0), b = ld_desc16(w + 1), c = ld_desc16(w + 2);
+  t.v[0] = a.y; t.v[1] = a.z; t.v[2] = a.w; t.v[3] = b.y; t.v[4] = b.z; t.v[5] = b.w;
+  t.d    = (unsigned long long)c.y | ((unsigned long long)c.z << 32);
+  return a.x == flag && b.x == flag && c.x == flag;
+}
+
+// Exclusive prefix of the per-cluster allocation tuples in visible-list order, in place; single pass with a decoupled look-back
+// over tiles of 1024 clusters.  The look-back is run by the WHOLE CTA: warp w reads the 32 tiles [base - 32 w - 31, base - 32 w],
+// so one step covers 256 predecessors (with one warp the last tile of the first wave of 444 needed 14 dependent steps, and the
+// other seven warps spent half of the kernel at the barrier behind it).
 __global__ void __launch_bounds__(CSCAN_THREADS) k_classify_scan(Params p, const uint32_t* epochCounter)
 {
   pdl_prologue();
-  __shared__ ScanTuple warpTotals[CSCAN_THREADS / 32];
-  __shared__ ScanTuple tileExclusive;
+  constexpr int NW = CSCAN_THREADS / 32;
+  __shared__ ScanTuple warpTotals[NW];   // inclusive over the warps of the tile
+  __shared__ ScanTuple stepPartial[NW];  // look-back step: sum of the warp's window up to (and including) its nearest inclusive prefix
+  __shared__ uint32_t  stepHasInc[NW];
   __shared__ uint32_t  shTile;
   const uint32_t epoch      = *epochCounter + SLOT_CLASSIFY;
+  const uint32_t AGG = (epoch << 2) | 1u, INC = (epoch << 2) | 2u;
   const uint32_t numVisible = p.build->visibleClusterCounter;
   const uint32_t numTiles   = (numVisible + CSCAN_TILE - 1) / CSCAN_TILE;
   ScanTuple*     tuples     = reinterpret_cast<ScanTuple*>(p.classTuples);
@@ -1914,41 +1941,90 @@ __global__ void __launch_bounds__(CSCAN_THREADS) k_classify_scan(Params p, const
       warpTotals[warp] = inc;
     __syncthreads();
     if(warp == 0)
-    {
-      ScanTuple total;
-      total.zero();
-      if(lane == 0)
-        for(int w = 0; w < CSCAN_THREADS / 32; w++)
-        {
-          ScanTuple tmp = warpTotals[w];
-          warpTotals[w] = total;  // exclusive over warps
-          total.add(tmp);
-        }
-#pragma unroll
-      for(int i = 0; i < 6; i++)
-        total.v[i] = __shfl_sync(0xffffffffu, total.v[i], 0);
-      total.d = __shfl_sync(0xffffffffu, total.d, 0);
-      ScanTuple excl = lookback_exclusive(descs, tile, total, epoch);
-      if(lane == 0)
-      {
-        tileExclusive = excl;
-        if(tile == numTiles - 1)
-        {
-          excl.add(total);
-          uint32_t* ct = p.state->classTotal;
-#pragma unroll
-          for(int i = 0; i < 6; i++)
-            ct[i] = excl.v[i];
-          ct[6] = uint32_t(excl.d);
-          ct[7] = uint32_t(excl.d >> 32);
-          if(p.hostCopyHint)
-            *p.hostCopyHint = p.state->clusterLevelWork;
-        }
-      }
+    {  // inclusive over the warps (lanes 0..NW-1), the tile's aggregate published at once
+      ScanTuple t;
+      t.zero();
+      if(lane < NW)
+        t = warpTotals[lane];
+      t = warp_inclusive_tuple(t);
+      if(lane < NW)
+        warpTotals[lane] = t;
+      if(lane == NW - 1)
+        scan_desc_store(&descs[tile], tile == 0 ? 1u : 0u, tile == 0 ? INC : AGG, t);
     }
     __syncthreads();
-    ScanTuple run = tileExclusive;
-    run.add(warpTotals[warp]);
+    const ScanTuple total = warpTotals[NW - 1];
+
+    // ---- look-back, 256 predecessors per step ----
+    ScanTuple exclusive;
+    exclusive.zero();
+    int32_t base = int32_t(tile) - 1;
+    bool    done = tile == 0;
+    while(!done)
+    {
+      const int32_t t = base - int32_t(warp * 32 + lane);
+      uint32_t  state = 2;  // tiles before 0 behave as "inclusive = 0"
+      ScanTuple val;
+      val.zero();
+      if(t >= 0)
+      {
+        while(true)
+        {
+          if(scan_desc_load(&descs[t], 1u, INC, val))
+          {
+            state = 2;
+            break;
+          }
+          if(scan_desc_load(&descs[t], 0u, AGG, val))
+          {
+            state = 1;
+            break;
+          }
+        }
+      }
+      const uint32_t incMask  = __ballot_sync(0xffffffffu, state == 2);
+      const uint32_t firstInc = incMask ? (__ffs(incMask) - 1) : 32;
+      if(lane > firstInc)
+        val.zero();
+      val = warp_reduce_tuple(val);
+      if(lane == 0)
+      {
+        stepPartial[warp] = val;
+        stepHasInc[warp]  = incMask != 0;
+      }
+      __syncthreads();
+#pragma unroll
+      for(int w = 0; w < NW; w++)
+        if(!done)
+        {
+          exclusive.add(stepPartial[w]);
+          done = stepHasInc[w] != 0;
+        }
+      __syncthreads();  // (the step buffers are rewritten by the next step)
+      base -= NW * 32;
+    }
+    if(threadIdx.x == 0 && tile != 0)
+    {
+      ScanTuple incl = exclusive;
+      incl.add(total);
+      scan_desc_store(&descs[tile], 1u, INC, incl);
+    }
+    if(threadIdx.x == 0 && tile == numTiles - 1)
+    {
+      ScanTuple all = exclusive;
+      all.add(total);
+      uint32_t* ct = p.state->classTotal;
+#pragma unroll
+      for(int i = 0; i < 6; i++)
+        ct[i] = all.v[i];
+      ct[6] = uint32_t(all.d);
+      ct[7] = uint32_t(all.d >> 32);
+      if(p.hostCopyHint)
+        *p.hostCopyHint = p.state->clusterLevelWork;
+    }
+    ScanTuple run = exclusive;
+    if(warp > 0)
+      run.add(warpTotals[warp - 1]);
     ScanTuple exclLane = inc;  // inclusive over lanes -> exclusive for this thread
 #pragma unroll
     for(int i = 0; i < 6; i++)
@@ -2124,7 +2200,7 @@ __device__ void split_pass_epilogue(const Params& p, uint32_t baseSplit, uint32_
 __device__ __forceinline__ uint32_t split_child_code(const FactorConsts& fcst, uint32_t splitFactor, const F3 w[3], const float d[3])
 {
   uint32_t f[3];
-  tess_factors(fcst, w[0], w[1], w[2], d[0], d[1], d[2], f);
+  tess_factors_filtered(fcst, w[0], w[1], w[2], d[0], d[1], d[2], f);  // d: tess_eye_scale_approx
   const bool split = max(max(f[0], f[1]), f[2]) > TC_TESSTABLE_SIZE;
   if(split)
   {
@@ -2246,7 +2322,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
           const uint32_t enc = tess_encodeBarycentrics(xinterp3(baseBary, q));
           const F3       w   = xinterp3(bp, tess_decodeBarycentrics(enc));
           sh.vEnc[t]   = enc;
-          sh.vWorld[t] = make_float4(w.x, w.y, w.z, tess_eye_scale(fcst, w));
+          sh.vWorld[t] = make_float4(w.x, w.y, w.z, tess_eye_scale_approx(fcst, w));
         }
       }
       __syncwarp();
@@ -2307,7 +2383,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
           for(int k = 0; k < 3; k++)
           {
             w[k] = xinterp3(bp, tess_decodeBarycentrics(enc[k]));
-            d[k] = tess_eye_scale(fcst, w[k]);
+            d[k] = tess_eye_scale_approx(fcst, w[k]);
           }
           code = split_child_code(fcst, p.splitFactor, w, d);
         }
@@ -2386,7 +2462,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_triangle_split(Params p, cons
           for(int k = 0; k < 3; k++)
           {
             w[k] = xinterp3(bp, tess_decodeBarycentrics(enc[k]));
-            d[k] = tess_eye_scale(fcst, w[k]);
+            d[k] = tess_eye_scale_approx(fcst, w[k]);
           }
           code = split_child_code(fcst, p.splitFactor, w, d);
         }
