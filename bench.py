@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="debug-size workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--rebalance", type=int, default=3, help="sharded scenes: rounds of measured load-balance feedback before the warm-up (0: model only)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the ranks' counts meet -- 'peer': stores into peer mailboxes from inside the frame's own kernels (default), "
                          "'nccl': an allgather between the two halves of the frame")
@@ -252,6 +253,33 @@ def main():
             sharding.connect_peer_mailboxes(gpu, rank, world)
 
     peer = world == 1 or args.exchange == "peer"  # the frame is one library call
+    use_graph = not args.no_graph
+
+    if sharded and peer and args.rebalance > 0:
+        # measured feedback on the load model (what a renderer does from frame to frame): a few untimed frames with the current
+        # partition, every rank's device time allgathered, instances re-weighted by their rank's cost per modelled unit, repartitioned
+        history = []
+        for _ in range(args.rebalance):
+            t_local = float(np.median(gpu.run_frames(fcs, 3, graph=use_graph, flush_l2=True)))
+            t = torch.tensor([t_local], dtype=torch.float64, device="cuda")
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            rank_ms = [float(x.item()) for x in allt]
+            history.append([round(x, 4) for x in rank_ms])
+            new_weights = sharding.rebalance_weights(weights, bounds, rank_ms)
+            new_bounds = sharding.partition_instances(new_weights, world)
+            weights = new_weights
+            if new_bounds == bounds:
+                break
+            bounds = new_bounds
+            first, last = bounds[rank]
+            gpu.set_scene(sharding.shard_scene(full_scene, first, last))
+            if w.hiz is not None:
+                gpu.set_hiz(*w.hiz)
+        shard_info["instances_per_rank"] = [b - a for a, b in bounds]
+        shard_info["weight_share_per_rank"] = [float(weights[a:b].sum() / weights.sum()) for a, b in bounds]
+        shard_info["rebalance_rank_ms"] = history
+        shard_info["balance"] += "; then measured feedback: " + str(len(history)) + " round(s) of 3 untimed frames, instances re-weighted by their rank's device time per modelled unit"
 
     def one_frame(use_graph: bool):
         if peer:
@@ -270,7 +298,6 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    use_graph = not args.no_graph
     # warm-up (also builds the graph)
     for _ in range(args.warmup):
         one_frame(use_graph)

@@ -133,3 +133,24 @@ def test_shard_count_exchange_gloo_world2(tmp_path):
                          env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert (tmp_path / "rank0.ok").exists() and (tmp_path / "rank1.ok").exists()
+
+
+def test_rebalance_weights_moves_work_off_the_slow_rank():
+    """Measured feedback of the shard load model (sharding.rebalance_weights): the slow rank's instances get heavier, the total is
+    preserved, and repartitioning shrinks the slow rank's range; equal times leave the partition alone."""
+    from vk_tessellated_clusters_b200 import sharding
+
+    w = np.ones(100)
+    bounds = sharding.partition_instances(w, 4)
+    assert [b - a for a, b in bounds] == [25, 25, 25, 25]
+    w2 = sharding.rebalance_weights(w, bounds, [0.35, 0.23, 0.23, 0.22])
+    assert abs(w2.sum() - w.sum()) < 1e-9 and w2[0] > w2[30] > 0
+    b2 = sharding.partition_instances(w2, 4)
+    assert b2[0][1] - b2[0][0] < 25 and b2[-1][1] == 100 and all(b > a for a, b in b2)
+    # predicted times with the new partition are closer than the measured ones
+    density = np.repeat([(0.35 - 0.1) / 25, (0.23 - 0.1) / 25, (0.23 - 0.1) / 25, (0.22 - 0.1) / 25], 25)
+    pred = [0.1 + density[a:b].sum() for a, b in b2]
+    assert max(pred) - min(pred) < 0.03 < 0.35 - 0.22
+    assert sharding.partition_instances(sharding.rebalance_weights(w, bounds, [0.3, 0.3, 0.3, 0.3]), 4) == bounds
+    with pytest.raises(ValueError):
+        sharding.rebalance_weights(w, bounds, [0.3, 0.3])

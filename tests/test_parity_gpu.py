@@ -26,21 +26,25 @@ def test_parity_case(name, table, oracle_lib):
         orc.close()
 
 
+@pytest.mark.parametrize("instances", [1, 2])
 @pytest.mark.parametrize("limits", [(30, 42), (33, 50), (45, 64)])
-def test_cluster_limits_that_are_not_multiples_of_four(limits, table, oracle_lib):
+def test_cluster_limits_that_are_not_multiples_of_four(limits, instances, table, oracle_lib):
     """tc_config.clusterVertices / clusterTriangles size the per-warp shared-memory regions of cluster_classify; limits that are not
     multiples of four must not misalign them (the world positions are accessed as float4).  Plane of 5x4-quad tiles: 40 triangles, 30
-    vertices per cluster, factors from 1 to beyond 11 so that every route (full, 1X, 2X, part, split) is taken."""
+    vertices per cluster, factors from 1 to beyond 11 so that every route (full, 1X, 2X, part, split) is taken.  With two instances the
+    geometry forms a cached displacement class: bulk cluster copies and inline 2X copies with 30-vertex clusters (90 floats: every
+    16-byte phase at the run ends)."""
     cv, ct = limits
     g = S.make_grid_plane(35, tile=(5, 4))
     g.displacement_index, g.displacement_scale = 0, 0.02
-    scene = S._scene([g], S.make_instances([g], [0], [np.eye(4)]), [S.value_noise_texture(64)], cv=cv, ct=ct)
+    mats = [np.eye(4), S.translation((0.0, 0.0, -0.35))][:instances]  # (the second plane lies just below the first)
+    scene = S._scene([g], S.make_instances([g], [0] * instances, mats), [S.value_noise_texture(64)], cv=cv, ct=ct)
     r = scene.radius
     fc = S.make_frame_constants(scene.center + np.array([0.0, -1.05 * r, 0.12 * r]), scene.center + np.array([0.0, 0.3 * r, 0.0]), up=(0, 0, 1), near=0.001 * r,
                                 far=100 * r, tess_rate_pixels=4.0)
     fc["tessRate"] = np.float32(1.0)
     raw = S._max_raw_factor(scene, fc)
-    cfg = api.Config(clusterVertices=cv, clusterTriangles=ct, numVisibleClusterBits=10, numPartTriangleBits=16, numSplitTriangleBits=12, numGeneratedVerticesBits=22)
+    cfg = api.Config(clusterVertices=cv, clusterTriangles=ct, numVisibleClusterBits=10, numPartTriangleBits=17, numSplitTriangleBits=13, numGeneratedVerticesBits=23)
     gpu, orc = make_pair(scene, table, cfg)
     try:
         seen = {"trans": 0, "splits": 0, "parts": 0}
