@@ -575,14 +575,7 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   for(uint32_t i = 0; i < tc_context::kStagingSlots; i++)
     TRY_CUDA(cudaEventCreateWithFlags(&c->stagingEv[i], cudaEventDisableTiming));
 #ifndef TC_NO_FORK
-  {  // the vertex-work branch gets the higher priority: its light CTAs (k_cluster_copies_bulk) are placed first and the main branch fills the rest
-    int prLo = 0, prHi = 0;
-    TRY_CUDA(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
-#ifdef TC_SIDE_STREAM_DEFAULT_PRIORITY
-    prHi = prLo;
-#endif
-    TRY_CUDA(cudaStreamCreateWithPriority(&c->fork.side, cudaStreamNonBlocking, prHi));
-  }
+  TRY_CUDA(cudaStreamCreateWithFlags(&c->fork.side, cudaStreamNonBlocking));  // (a higher priority for this branch was measured: no effect)
   for(cudaEvent_t* e : {&c->fork.evCount, &c->fork.evCache, &c->fork.evCluster, &c->fork.evTriangle, &c->fork.evJoin})
     TRY_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 #endif

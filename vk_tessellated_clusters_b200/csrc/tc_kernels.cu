@@ -4103,14 +4103,6 @@ int configure_kernels(uint32_t clusterVertices, uint32_t clusterTriangles, Kerne
     return -1;
   if(cudaFuncSetAttribute(k_cluster_copies_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(COPYB_WARPS * copyb_warp_bytes(clusterVertices))) != cudaSuccess)
     return -1;
-#ifdef TC_COPYB_CARVEOUT
-  cudaFuncSetAttribute(k_cluster_copies_bulk, cudaFuncAttributePreferredSharedMemoryCarveout, TC_COPYB_CARVEOUT);
-#endif
-#ifdef TC_CLASSIFY_CARVEOUT
-  cudaFuncSetAttribute(k_cluster_classify<3>, cudaFuncAttributePreferredSharedMemoryCarveout, TC_CLASSIFY_CARVEOUT);
-  cudaFuncSetAttribute(k_cluster_classify<2>, cudaFuncAttributePreferredSharedMemoryCarveout, TC_CLASSIFY_CARVEOUT);
-  cudaFuncSetAttribute(k_cluster_classify<1>, cudaFuncAttributePreferredSharedMemoryCarveout, TC_CLASSIFY_CARVEOUT);
-#endif
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->classify, k_cluster_classify<1>, CLASSIFY_THREADS, smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ->split, k_triangle_split, SPLIT_THREADS, 0);
   const void* variants[6] = {(const void*)k_instantiate<0, false>, (const void*)k_instantiate<0, true>, (const void*)k_instantiate<1, false>,
@@ -4186,14 +4178,12 @@ void launch_cluster_classify(const Params& p, const uint32_t* epochCounter, uint
     // node itself sits between the cluster-level emit and the copies
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaGraph_t             g  = nullptr;
-#ifndef TC_COPIES_NO_GATE
     if(fork.gateCopies && cudaStreamGetCaptureInfo(v, &cs, nullptr, &g, nullptr, nullptr) == cudaSuccess && cs == cudaStreamCaptureStatusActive
        && cudaGraphConditionalHandleCreate(&copiesGate, g, 0, cudaGraphCondAssignDefault) == cudaSuccess)
     {
       k_copies_gate<<<1, 32, 0, v>>>(p, copiesGate);
       gated = true;
     }
-#endif
   }
   launch_pdl(k_classify_scan, 148 * 3, CSCAN_THREADS, 0, s, p, epochCounter);  // 3 CTAs per SM at 80 registers; tiles are handed out by ticket
   launch_pdl(k_cluster_classify<1>, grid, CLASSIFY_THREADS, smem, s, p);
