@@ -49,6 +49,8 @@ struct FrameStaging  // pinned host block copied to the device once per frame
 
 }  // namespace
 
+constexpr size_t kReadbackOffset = (sizeof(tc_SceneBuilding) + 255) / 256 * 256;  // tc_Readback behind tc_SceneBuilding in one allocation
+
 struct tc_context
 {
   tc_config    cfg{};
@@ -63,7 +65,8 @@ struct tc_context
   // device blocks
   tc_SceneBuilding* dBuild     = nullptr;
   tc_SceneBuilding* dBuildTmpl = nullptr;
-  tc_Readback*      dReadback  = nullptr;
+  tc_Readback*      dReadback  = nullptr;  // same allocation as dBuild (kReadbackOffset behind it): tc_readback is ONE device-to-host copy
+  unsigned char*    hReadbackBlock = nullptr;  // pinned mirror of that block
   tc::FrameState*   dState     = nullptr;
   uint32_t*         dEpoch     = nullptr;
   void*             dLookback  = nullptr;
@@ -553,9 +556,14 @@ TC_API int tc_create(const tc_config* config, tc_context** out)
   if(tc::configure_kernels(config->clusterVertices, config->clusterTriangles, &c->occ) != 0)
     return bail(fail(TC_ERR_CUDA, std::string("kernel configuration failed: ") + cudaGetErrorString(cudaGetLastError())));
 
-  TRY_RC(dalloc(c->dBuild, sizeof(tc_SceneBuilding)));
+  {
+    unsigned char* block = nullptr;
+    TRY_RC(dalloc(block, kReadbackOffset + sizeof(tc_Readback)));
+    c->dBuild    = reinterpret_cast<tc_SceneBuilding*>(block);
+    c->dReadback = reinterpret_cast<tc_Readback*>(block + kReadbackOffset);
+    TRY_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->hReadbackBlock), kReadbackOffset + sizeof(tc_Readback)));
+  }
   TRY_RC(dalloc(c->dBuildTmpl, sizeof(tc_SceneBuilding)));
-  TRY_RC(dalloc(c->dReadback, sizeof(tc_Readback)));
   TRY_RC(dalloc(c->dState, tc::frame_state_bytes()));
   TRY_RC(dalloc(c->dEpoch, 16));
   TRY_RC(dalloc(c->dFrame, sizeof(FrameStaging)));
@@ -650,7 +658,7 @@ TC_API void tc_destroy(tc_context* c)
     cudaStreamSynchronize(c->stream);
   drop_graph(c);
   free_scene(c);
-  dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dReadback); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dClusterVertexDst); dfree(c->dTriWorkList); dfree(c->dFrame);
+  dfree(c->dBuild); dfree(c->dBuildTmpl); dfree(c->dState); dfree(c->dEpoch); dfree(c->dLookback); dfree(c->dLookback16); dfree(c->dClassTuples); dfree(c->dFactorStash); dfree(c->dClassMeta); dfree(c->dClusterVertexDst); dfree(c->dTriWorkList); dfree(c->dFrame);
   dfree(c->dShardCounts); dfree(c->dShardBase); dfree(c->dEmitState); dfree(c->dBatchState); dfree(c->dTransVertexOffsets); dfree(c->dMailbox); dfree(c->dShardStatus);
   if(c->fork.side)
   {
@@ -666,6 +674,8 @@ TC_API void tc_destroy(tc_context* c)
     cudaFreeHost(c->hFrameRing);
   if(c->hCopyHint)
     cudaFreeHost(c->hCopyHint);
+  if(c->hReadbackBlock)
+    cudaFreeHost(c->hReadbackBlock);
   for(cudaEvent_t e : c->stagingEv)
     if(e)
       cudaEventDestroy(e);
@@ -1341,13 +1351,17 @@ TC_API int tc_readback(tc_context* c, tc_Readback* readback, tc_SceneBuilding* b
   if(!c)
     return fail(TC_ERR_INVALID_ARG, "null context");
   CUDA_TRY(cudaSetDevice(c->device));
-  if(readback)
-    CUDA_TRY(cudaMemcpyAsync(readback, c->dReadback, sizeof(tc_Readback), cudaMemcpyDeviceToHost, c->stream));
-  if(building)
-    CUDA_TRY(cudaMemcpyAsync(building, c->dBuild, sizeof(tc_SceneBuilding), cudaMemcpyDeviceToHost, c->stream));
+  // both records live in one device block: one asynchronous copy into pinned memory (a copy into the caller's pageable memory is
+  // staged by the driver and blocks), then plain memcpy to the caller
+  if(readback || building)
+    CUDA_TRY(cudaMemcpyAsync(c->hReadbackBlock, c->dBuild, kReadbackOffset + sizeof(tc_Readback), cudaMemcpyDeviceToHost, c->stream));
   int rc = sync_all(c);
   if(rc)
     return rc;
+  if(readback)
+    memcpy(readback, c->hReadbackBlock + kReadbackOffset, sizeof(tc_Readback));
+  if(building)
+    memcpy(building, c->hReadbackBlock, sizeof(tc_SceneBuilding));
   if(c->shardFailed)
     return fail(TC_ERR_SHARD_TIMEOUT, "a peer's per-frame counts never arrived");
   return TC_OK;
