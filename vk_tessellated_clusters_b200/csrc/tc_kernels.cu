@@ -3,7 +3,8 @@
 // Stage map (reference shader -> kernel here), all cited relative to /root/reference:
 //   rt.cpp:412-419 resets + instances_classify.comp.glsl + clusters_cull.comp.glsl + BUILD_SETUP_CLASSIFY -> k_frame_begin (one launch)
 //   cluster_classify.comp.glsl + BUILD_SETUP_SPLIT-> k_cluster_classify<0..3> + k_classify_scan (count -> scan -> emit), k_cluster_vertices,
-//                                                    k_mini_vertices; k_class_cache / k_cluster_copies_bulk for instanced geometry
+//                                                    k_mini_vertices; k_class_cache / k_cluster_copies_bulk (TMA; k_copies_gate: condition
+//                                                    of the frame graph's IF node around it) for instanced geometry
 //   triangle_split.comp.glsl + SPLIT_PASS / INSTANTIATE_TESS setup -> k_triangle_split (one launch per pass)
 //   triangle_tess_template_instantiate.comp.glsl + BUILD_SETUP_BUILD_BLAS -> k_instantiate
 //   blas_setup_insertion.comp.glsl                -> k_blas_segments + k_blas_setup
