@@ -261,14 +261,8 @@ def main():
         history = []
         for _ in range(args.rebalance):
             t_local = float(np.median(gpu.run_frames(fcs, 3, graph=use_graph, flush_l2=True)))
-            t = torch.tensor([t_local], dtype=torch.float64, device="cuda")
-            allt = [torch.zeros_like(t) for _ in range(world)]
-            dist.all_gather(allt, t)
-            rank_ms = [float(x.item()) for x in allt]
+            weights, new_bounds, rank_ms = sharding.rebalance_round(weights, bounds, t_local)
             history.append([round(x, 4) for x in rank_ms])
-            new_weights = sharding.rebalance_weights(weights, bounds, rank_ms)
-            new_bounds = sharding.partition_instances(new_weights, world)
-            weights = new_weights
             if new_bounds == bounds:
                 break
             bounds = new_bounds

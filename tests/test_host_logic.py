@@ -115,6 +115,15 @@ assert base.tolist() == [want_cluster_base, want_instance_base], (rank, base.tol
 tot = sharding.global_totals(gathered)
 assert tot["blasClusters"] == sum(105 + 11 * r for r in range(world)) and tot["instances"] == sum(3 + r for r in range(world))
 assert tot["totalTriangles"] == sum(7 * (r + 1) for r in range(world))
+# measured load-balance feedback: rank 0 reports the slower frame -> both ranks agree on a partition that shrinks rank 0's range
+w = np.ones(40)
+bounds = sharding.partition_instances(w, world)
+w2, b2, rank_ms = sharding.rebalance_round(w, bounds, 0.50 if rank == 0 else 0.30, device="cpu")
+assert rank_ms == [0.50, 0.30] and abs(w2.sum() - 40) < 1e-9
+assert b2[0][1] - b2[0][0] < bounds[0][1] - bounds[0][0] and b2[-1][1] == 40
+gathered_b = [None] * world
+dist.all_gather_object(gathered_b, b2)
+assert gathered_b[0] == gathered_b[1]
 dist.barrier()
 dist.destroy_process_group()
 open(os.path.join(os.environ["TC_OUT"], f"rank{rank}.ok"), "w").write("ok")

@@ -87,6 +87,22 @@ def rebalance_weights(weights, bounds, rank_ms, fixed_ms: float = 0.1):
     return w * (float(np.asarray(weights, np.float64).sum()) / total) if total > 0.0 else np.asarray(weights, np.float64).copy()
 
 
+def rebalance_round(weights, bounds, local_ms: float, device="cuda", group=None, fixed_ms: float = 0.1):
+    """One round of the measured feedback, collectively: every rank contributes the device time of its last frame(s) with the
+    partition `bounds`; all ranks get the same (new_weights, new_bounds, rank_ms).  `device`: where the allgathered tensor lives
+    ("cuda" under NCCL, "cpu" under gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    t = torch.tensor([float(local_ms)], dtype=torch.float64, device=device)
+    allt = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allt, t, group=group)
+    rank_ms = [float(x.item()) for x in allt]
+    new_weights = rebalance_weights(weights, bounds, rank_ms, fixed_ms)
+    return new_weights, partition_instances(new_weights, world), rank_ms
+
+
 def exchange_shard_counts(local_counts, group=None):
     """local_counts: int32 tensor [SHARD_WORDS] (device of the backend).  Returns (gathered [world, SHARD_WORDS],
     base [2] int32 = {globalBlasClusterBase, globalInstanceBase}) -- both stay on the tensor's device."""
