@@ -634,8 +634,11 @@ __device__ __forceinline__ uint4 cluster_copy_desc(const Params& p, uint32_t ins
   return make_uint4(vertexOffset, src0 + k * (__ldg(&p.instanceCacheStride[instanceID]) + 1u), numVertices * 3u, 0u);
 }
 
+#ifndef TC_CLASSIFY3_MIN_CTAS
+#define TC_CLASSIFY3_MIN_CTAS 3
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_CTAS : (MODE == 0 ? TC_CLASSIFY0_MIN_CTAS : 3)) k_cluster_classify(Params p)
+__global__ void __launch_bounds__(CLASSIFY_THREADS, MODE == 2 ? TC_CLASSIFY_MIN_CTAS : (MODE == 0 ? TC_CLASSIFY0_MIN_CTAS : (MODE == 3 ? TC_CLASSIFY3_MIN_CTAS : 3))) k_cluster_classify(Params p)
 {
   pdl_prologue();
   extern __shared__ __align__(16) uint8_t smemRaw[];
