@@ -163,3 +163,19 @@ def test_rebalance_weights_moves_work_off_the_slow_rank():
     assert sharding.partition_instances(sharding.rebalance_weights(w, bounds, [0.3, 0.3, 0.3, 0.3]), 4) == bounds
     with pytest.raises(ValueError):
         sharding.rebalance_weights(w, bounds, [0.3, 0.3])
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) needs no GPU: one JSON line with the contract's keys,
+    honouring --steps / --warmup, same metric and unit as the GPU arm."""
+    import json
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--small", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600,
+                         cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["warmup"] == 1 and line["higher_is_better"] is True
+    assert line["metric"] == "displaced output triangles/sec per frame" and line["unit"] == "triangles/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "triangles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert abs(line["ms_per_step"] * line["value"] / 1e3 - int(line["cpu_baseline"]["sample"].split("(")[1].split()[0])) < 1.0
