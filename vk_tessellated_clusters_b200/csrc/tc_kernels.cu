@@ -2624,8 +2624,8 @@ __device__ __forceinline__ void flush_stage(const float* stage, float* dst, uint
 // (the 16-byte granules that cover the run in the phase-matched copy, completion on an mbarrier) and ONE bulk store shared ->
 // genVertices of the whole granules; the <= 3 floats at either end of a run that share a granule with a neighbour are read
 // back from shared memory and stored as scalars.  Two buffers per warp: the loads of batch b+1 are issued before the warp
-// waits for batch b.  Eight warps of 45 registers per SM do what took 32 warps of 64: the kernel stays resident beside the
-// classify CTAs of the main branch.
+// waits for batch b.  Eight warps of 54 registers per SM do what took 32 warps of 64: the kernel stays resident beside the
+// classify CTAs of the main branch (two of them per SM instead of three while the copies run).
 // ------------------------------------------------------------------------------------------------------------
 #ifndef TC_COPYB_BATCH_BYTES
 #define TC_COPYB_BATCH_BYTES 6656
